@@ -1,0 +1,533 @@
+"""CPU oracle for the RSSM latent-dynamics hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy restatement of the reference algorithm.  It is the
+*checker* used by ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.  Nothing under
+``safe_dreamer_b200/`` (the product) imports it; the product path has no CPU
+fallback and fails loudly when the CUDA library is missing.
+
+Parity status: PINNED.  The reference ships no tests or golden vectors
+(SURVEY.md section 4), so the pins are outputs of the unmodified reference
+modules executed in the build container by ``tests/golden/make_golden.py``
+and committed under ``tests/golden/*.npz``; ``tests/test_oracle_golden.py``
+checks every function here against them.
+
+Reference lines followed (all relative to the reference checkout):
+  world_model/rssm.py:36-75        Deter.forward           -> deter_step
+  world_model/rssm.py:158-178      RSSM.obs_step           -> obs_step
+  world_model/rssm.py:140-156      RSSM.observe            -> observe
+  world_model/rssm.py:180-195      RSSM.img_step / prior   -> img_step / prior
+  world_model/rssm.py:197-209      imagine_with_action     -> imagine_with_action
+  world_model/rssm.py:211-217      get_feat                -> get_feat
+  world_model/rssm.py:222-230      kl_loss                 -> kl_loss
+  world_model/networks.py:43-56    BlockLinear.forward     -> block_linear
+  world_model/networks.py:331-336  MLP.forward             -> mlp
+  world_model/networks.py:374-377  MLPHead.forward         -> head_*
+  world_model/distributions.py:16-36   OneHotDist (unimix + ST gumbel) -> sample_onehot
+  world_model/distributions.py:78-98   TwoHot.mode             -> twohot_mode
+  world_model/distributions.py:217-222 bounded_normal          -> actor_sample
+  world_model/distributions.py:238-251 binary / symexp_twohot  -> twohot_bins
+  world_model/distributions.py:266-271 kl                      -> kl
+  world_model/dreamer.py:673-692   Dreamer._imagine        -> imagine
+  world_model/dreamer.py:589-602   heads + weights + return-> heads_lambda
+  world_model/dreamer.py:694-707   Dreamer._lambda_return  -> lambda_return
+Third-party arithmetic restated from its published definition: torch
+(``requirements.txt:1`` pins 2.8.0; 2.11.0 is installed here) --
+``F.gumbel_softmax`` (torch/nn/functional.py), ``nn.RMSNorm``,
+``OneHotCategorical`` logit normalisation, ``torch.linspace``.
+
+Noise is *injected*: categorical draws take uniforms ``u`` in (0,1) and use
+``g = -log(-log(u))`` (the Gumbel that ``-log(Exponential(1))`` produces);
+the continuous actor takes standard normals ``eps``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+RMS_EPS = 1e-4
+
+
+# --------------------------------------------------------------------------- config
+class Cfg:
+    """Sizes of the hot path (configs/base.yaml:117-127,252-276,340-420)."""
+
+    def __init__(self, D=2048, U=256, S=32, K=16, G=8, E=1024, A=6, unimix=0.01,
+                 img_layers=2, obs_layers=1, act_kind="cont", act_unimix=0.01,
+                 min_std=0.1, max_std=1.0, units=256, actor_layers=3,
+                 value_layers=3, reward_layers=1, cont_layers=1, bins=255,
+                 horizon=333, lamb=0.95):
+        self.D, self.U, self.S, self.K, self.G, self.E, self.A = D, U, S, K, G, E, A
+        self.unimix = unimix
+        self.img_layers, self.obs_layers = img_layers, obs_layers
+        self.act_kind, self.act_unimix = act_kind, act_unimix
+        self.min_std, self.max_std = min_std, max_std
+        self.units = units
+        self.actor_layers, self.value_layers = actor_layers, value_layers
+        self.reward_layers, self.cont_layers = reward_layers, cont_layers
+        self.bins = bins
+        self.horizon, self.lamb = horizon, lamb
+
+    @property
+    def SK(self):
+        return self.S * self.K
+
+    @property
+    def F(self):
+        return self.S * self.K + self.D
+
+    @property
+    def act_out(self):
+        return 2 * self.A if self.act_kind == "cont" else self.A
+
+    def as_dict(self):
+        return dict(self.__dict__)
+
+
+# --------------------------------------------------------------------------- params
+def rssm_param_shapes(c: Cfg):
+    """state_dict names/shapes of reference ``RSSM``."""
+    Dg = c.D // c.G
+    sh = {
+        "_deter_net._dyn_in0.0.weight": (c.U, c.D), "_deter_net._dyn_in0.0.bias": (c.U,),
+        "_deter_net._dyn_in0.1.weight": (c.U,),
+        "_deter_net._dyn_in1.0.weight": (c.U, c.SK), "_deter_net._dyn_in1.0.bias": (c.U,),
+        "_deter_net._dyn_in1.1.weight": (c.U,),
+        "_deter_net._dyn_in2.0.weight": (c.U, c.A), "_deter_net._dyn_in2.0.bias": (c.U,),
+        "_deter_net._dyn_in2.1.weight": (c.U,),
+        "_deter_net._dyn_hid.dyn_hid_0.weight": (Dg, Dg + 3 * c.U, c.G),
+        "_deter_net._dyn_hid.dyn_hid_0.bias": (c.D,),
+        "_deter_net._dyn_hid.norm_0.weight": (c.D,),
+        "_deter_net._dyn_gru.weight": (3 * Dg, Dg, c.G), "_deter_net._dyn_gru.bias": (3 * c.D,),
+    }
+    inp = c.D + c.E
+    for i in range(c.obs_layers):
+        sh[f"_obs_net.obs_net_{i}.weight"] = (c.U, inp)
+        sh[f"_obs_net.obs_net_{i}.bias"] = (c.U,)
+        sh[f"_obs_net.obs_net_n_{i}.weight"] = (c.U,)
+        inp = c.U
+    sh["_obs_net.obs_net_logit.weight"] = (c.SK, inp)
+    sh["_obs_net.obs_net_logit.bias"] = (c.SK,)
+    inp = c.D
+    for i in range(c.img_layers):
+        sh[f"_img_net.img_net_{i}.weight"] = (c.U, inp)
+        sh[f"_img_net.img_net_{i}.bias"] = (c.U,)
+        sh[f"_img_net.img_net_n_{i}.weight"] = (c.U,)
+        inp = c.U
+    sh["_img_net.img_net_logit.weight"] = (c.SK, inp)
+    sh["_img_net.img_net_logit.bias"] = (c.SK,)
+    return sh
+
+
+def head_param_shapes(name, layers, inp, units, out):
+    """state_dict names/shapes of reference ``MLPHead`` (networks.py:313-377)."""
+    sh = {}
+    for i in range(layers):
+        sh[f"mlp.layers.{name}_linear{i}.weight"] = (units, inp)
+        sh[f"mlp.layers.{name}_linear{i}.bias"] = (units,)
+        sh[f"mlp.layers.{name}_norm{i}.weight"] = (units,)
+        inp = units
+    sh["last.weight"] = (out, inp)
+    sh["last.bias"] = (out,)
+    return sh
+
+
+def all_param_shapes(c: Cfg):
+    return {
+        "rssm": rssm_param_shapes(c),
+        "actor": head_param_shapes("actor", c.actor_layers, c.F, c.units, c.act_out),
+        "reward": head_param_shapes("reward", c.reward_layers, c.F, c.units, c.bins),
+        "cont": head_param_shapes("cont", c.cont_layers, c.F, c.units, 1),
+        "value": head_param_shapes("value", c.value_layers, c.F, c.units, c.bins),
+        "slow_value": head_param_shapes("value", c.value_layers, c.F, c.units, c.bins),
+    }
+
+
+def init_params(c: Cfg, seed=0):
+    """Deterministic synthetic weights (numpy Philox; reproducible on any box).
+
+    Follows the *spirit* of SURVEY.md section 8(d): fan-in scaled weights,
+    non-trivial biases / RMS scales, a peaked bias on the two-hot heads so
+    that ``TwoHot.mode`` is O(1) (distributions.py:81-92 cancellation hazard).
+    Exact values need not match ``weight_init_``; parity tests load *these*
+    arrays into the reference modules.
+    """
+    rng = np.random.Generator(np.random.Philox(seed))
+    out = {}
+    for mod, shapes in all_param_shapes(c).items():
+        p = {}
+        for name, shp in shapes.items():
+            if name.endswith("bias"):
+                v = (rng.random(shp, dtype=np.float32) * 2 - 1) * 0.1
+            elif len(shp) == 1:  # RMSNorm scale
+                v = 0.5 + rng.random(shp, dtype=np.float32)
+            else:
+                fan_in = shp[1]
+                std = 1.1368 / np.sqrt(fan_in)
+                v = (rng.random(shp, dtype=np.float32) * 2 - 1) * np.float32(std * 1.7)
+            p[name] = v.astype(np.float32)
+        if mod == "actor":
+            p["last.weight"] *= np.float32(0.5)
+        if mod in ("reward", "value", "slow_value"):
+            n = c.bins
+            p["last.weight"] *= np.float32(0.05)
+            centre = (n - 1) / 2 + (3.0 if mod == "reward" else -5.0)
+            p["last.bias"] = (-0.5 * np.abs(np.arange(n) - centre)).astype(np.float32)
+        out[mod] = p
+    return out
+
+
+# --------------------------------------------------------------------------- primitives
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def silu(x):
+    return x * sigmoid(x)
+
+
+def rms_norm(x, w):
+    """nn.RMSNorm(eps=1e-4): x * rsqrt(mean(x^2) + eps) * w (rssm.py:17)."""
+    ms = np.mean(x * x, axis=-1, keepdims=True)
+    return x * (1.0 / np.sqrt(ms + x.dtype.type(RMS_EPS))) * w
+
+
+def linear(x, w, b=None):
+    y = x @ w.T
+    return y if b is None else y + b
+
+
+def block_linear(x, w, b, G):
+    """BlockLinear.forward (networks.py:43-56); weight is (O/G, I/G, G)."""
+    R = x.shape[0]
+    xg = x.reshape(R, G, -1)
+    ys = [xg[:, g, :] @ w[:, :, g].T for g in range(G)]
+    return np.stack(ys, axis=1).reshape(R, -1) + b
+
+
+def softmax(x):
+    m = x.max(-1, keepdims=True)
+    e = np.exp(x - m)
+    return e / e.sum(-1, keepdims=True)
+
+
+def logsumexp(x):
+    m = x.max(-1, keepdims=True)
+    return m + np.log(np.exp(x - m).sum(-1, keepdims=True))
+
+
+def log_softmax(x):
+    return x - logsumexp(x)
+
+
+def mlp(x, p, prefix_lin, prefix_norm, layers):
+    """[Linear -> RMSNorm(1e-4) -> SiLU] x layers (networks.py:313-336, rssm.py:106-130)."""
+    for i in range(layers):
+        x = silu(rms_norm(linear(x, p[f"{prefix_lin}{i}.weight"], p[f"{prefix_lin}{i}.bias"]),
+                          p[f"{prefix_norm}{i}.weight"]))
+    return x
+
+
+# --------------------------------------------------------------------------- distributions
+def unimix_logits(logit, unimix):
+    """OneHotDist.__init__ (distributions.py:17-23) incl. OneHotCategorical renormalisation."""
+    one = logit.dtype.type(1.0)
+    um = logit.dtype.type(unimix)
+    p = softmax(logit)
+    p = p * (one - um) + um / logit.dtype.type(logit.shape[-1])
+    l = np.log(p)
+    return l - logsumexp(l)
+
+
+def sample_onehot(logit, u, unimix):
+    """OneHotDist.rsample = F.gumbel_softmax(hard=True) with injected uniforms.
+
+    Returns (straight-through value, index, y_soft, normalised logits).
+    """
+    l = unimix_logits(logit, unimix)
+    g = -np.log(-np.log(u.astype(logit.dtype)))
+    y = softmax(l + g)
+    idx = np.argmax(y, axis=-1)  # first max, like torch.max
+    hard = np.zeros_like(y)
+    np.put_along_axis(hard, idx[..., None], 1.0, axis=-1)
+    return (hard - y) + y, idx, y, l
+
+
+def onehot_entropy(logit, unimix):
+    l = unimix_logits(logit, unimix)
+    return -(np.exp(l) * l).sum(-1)
+
+
+def kl(l_left, l_right):
+    """distributions.kl (distributions.py:266-271) on raw logits."""
+    a, b = log_softmax(l_left), log_softmax(l_right)
+    return (softmax(l_left) * (a - b)).sum(-1)
+
+
+def kl_loss(post_logit, prior_logit, free):
+    """RSSM.kl_loss (rssm.py:222-230): values only (detach only matters for grads)."""
+    k = kl(post_logit, prior_logit).sum(-1)
+    v = np.maximum(k, post_logit.dtype.type(free))
+    return v.copy(), v.copy()  # dyn_loss, rep_loss
+
+
+def torch_linspace_f32(start, end, steps):
+    """torch.linspace's symmetric fp32 algorithm (front half from start, back half from end)."""
+    start, end = np.float32(start), np.float32(end)
+    step = np.float32((end - start) / np.float32(steps - 1))
+    i = np.arange(steps)
+    half = steps // 2
+    front = (start + step * i.astype(np.float32)).astype(np.float32)
+    back = (end - step * (steps - 1 - i).astype(np.float32)).astype(np.float32)
+    return np.where(i < half, front, back).astype(np.float32)
+
+
+def symexp(x):
+    return np.sign(x) * np.expm1(np.abs(x))
+
+
+def twohot_bins(n=255):
+    """symexp_twohot bins (distributions.py:242-251)."""
+    if n % 2 == 1:
+        half = symexp(torch_linspace_f32(-20.0, 0.0, (n - 1) // 2 + 1)).astype(np.float32)
+        return np.concatenate([half, -half[:-1][::-1]]).astype(np.float32)
+    half = symexp(torch_linspace_f32(-20.0, 0.0, n // 2)).astype(np.float32)
+    return np.concatenate([half, -half[::-1]]).astype(np.float32)
+
+
+def twohot_mode(logit, bins):
+    """TwoHot.mode with the reference's symmetric pairing (distributions.py:78-98)."""
+    p = softmax(logit)
+    n = logit.shape[-1]
+    b = bins.astype(logit.dtype)
+    if n % 2 == 1:
+        m = (n - 1) // 2
+        pair = (p[..., :m] * b[:m])[..., ::-1] + p[..., m + 1:] * b[m + 1:]
+        return (p[..., m:m + 1] * b[m:m + 1]).sum(-1, keepdims=True) + pair.sum(-1, keepdims=True)
+    h = n // 2
+    pair = (p[..., :h] * b[:h])[..., ::-1] + p[..., h:] * b[h:]
+    return pair.sum(-1, keepdims=True)
+
+
+# --------------------------------------------------------------------------- RSSM
+def get_feat(stoch, deter):
+    """RSSM.get_feat (rssm.py:211-217): [stoch.flat | deter]."""
+    return np.concatenate([stoch.reshape(*stoch.shape[:-2], -1), deter], -1)
+
+
+def deter_step(c: Cfg, P, stoch, deter, action, tape=None):
+    """Deter.forward (rssm.py:36-75).  stoch (R,S,K) or (R,SK); deter (R,D); action (R,A)."""
+    R = deter.shape[0]
+    z = stoch.reshape(R, -1)
+    a = action / np.maximum(np.abs(action), action.dtype.type(1.0))
+    pre = "_deter_net."
+    v0 = linear(deter, P[pre + "_dyn_in0.0.weight"], P[pre + "_dyn_in0.0.bias"])
+    v1 = linear(z, P[pre + "_dyn_in1.0.weight"], P[pre + "_dyn_in1.0.bias"])
+    v2 = linear(a, P[pre + "_dyn_in2.0.weight"], P[pre + "_dyn_in2.0.bias"])
+    x0 = silu(rms_norm(v0, P[pre + "_dyn_in0.1.weight"]))
+    x1 = silu(rms_norm(v1, P[pre + "_dyn_in1.1.weight"]))
+    x2 = silu(rms_norm(v2, P[pre + "_dyn_in2.1.weight"]))
+    x = np.concatenate([x0, x1, x2], -1)
+    dg = deter.reshape(R, c.G, -1)
+    xin = np.concatenate([dg, np.broadcast_to(x[:, None, :], (R, c.G, x.shape[-1]))], -1).reshape(R, -1)
+    hpre = block_linear(xin, P[pre + "_dyn_hid.dyn_hid_0.weight"], P[pre + "_dyn_hid.dyn_hid_0.bias"], c.G)
+    h = silu(rms_norm(hpre, P[pre + "_dyn_hid.norm_0.weight"]))
+    q = block_linear(h, P[pre + "_dyn_gru.weight"], P[pre + "_dyn_gru.bias"], c.G)
+    qg = q.reshape(R, c.G, 3, -1)
+    r_ = sigmoid(qg[:, :, 0, :].reshape(R, -1))
+    cand = np.tanh(r_ * qg[:, :, 1, :].reshape(R, -1))
+    upd = sigmoid(qg[:, :, 2, :].reshape(R, -1) - q.dtype.type(1.0))
+    new = upd * cand + (q.dtype.type(1.0) - upd) * deter
+    if tape is not None:
+        tape.update(z=z, a=a, act_raw=action, deter_in=deter, v0=v0, v1=v1, v2=v2, x=x, hpre=hpre, h=h, q=q)
+    return new
+
+
+def obs_logit(c: Cfg, P, deter, embed, tape=None):
+    """_obs_net (rssm.py:106-117) on [deter | embed]."""
+    x = np.concatenate([deter, embed], -1)
+    acts = []
+    for i in range(c.obs_layers):
+        v = linear(x, P[f"_obs_net.obs_net_{i}.weight"], P[f"_obs_net.obs_net_{i}.bias"])
+        acts.append((x, v))
+        x = silu(rms_norm(v, P[f"_obs_net.obs_net_n_{i}.weight"]))
+    lg = linear(x, P["_obs_net.obs_net_logit.weight"], P["_obs_net.obs_net_logit.bias"])
+    if tape is not None:
+        tape.update(obs_acts=acts, obs_last_in=x)
+    return lg.reshape(-1, c.S, c.K)
+
+
+def img_logit(c: Cfg, P, deter, tape=None):
+    """_img_net (rssm.py:119-130)."""
+    x = deter
+    acts = []
+    for i in range(c.img_layers):
+        v = linear(x, P[f"_img_net.img_net_{i}.weight"], P[f"_img_net.img_net_{i}.bias"])
+        acts.append((x, v))
+        x = silu(rms_norm(v, P[f"_img_net.img_net_n_{i}.weight"]))
+    lg = linear(x, P["_img_net.img_net_logit.weight"], P["_img_net.img_net_logit.bias"])
+    if tape is not None:
+        tape.update(img_acts=acts, img_last_in=x)
+    return lg.reshape(*deter.shape[:-1], c.S, c.K)
+
+
+def obs_step(c: Cfg, P, stoch, deter, prev_action, embed, reset, u, tape=None):
+    """RSSM.obs_step (rssm.py:158-178).  reset: (R,) or (R,1) bool."""
+    rs = np.asarray(reset).reshape(-1).astype(bool)
+    stoch = np.where(rs[:, None, None], 0, stoch).astype(deter.dtype)
+    deter = np.where(rs[:, None], 0, deter).astype(deter.dtype)
+    prev_action = np.where(rs[:, None], 0, prev_action).astype(deter.dtype)
+    deter = deter_step(c, P, stoch, deter, prev_action, tape)
+    logit = obs_logit(c, P, deter, embed, tape)
+    st, idx, y, l = sample_onehot(logit, u, c.unimix)
+    if tape is not None:
+        tape.update(reset=rs, logit=logit, y=y, idx=idx, u=u, deter_out=deter)
+    return st, deter, logit, idx
+
+
+def observe(c: Cfg, P, embed, action, initial, reset, u, tapes=None):
+    """RSSM.observe (rssm.py:140-156).  embed (B,T,E) action (B,T,A) reset (B,T[,1]) u (B,T,S,K)."""
+    B, T = action.shape[:2]
+    stoch, deter = initial
+    reset = np.asarray(reset).reshape(B, T)
+    S_, D_, L_, I_ = [], [], [], []
+    for t in range(T):
+        tp = {} if tapes is not None else None
+        stoch, deter, logit, idx = obs_step(c, P, stoch, deter, action[:, t], embed[:, t], reset[:, t], u[:, t], tp)
+        if tapes is not None:
+            tapes.append(tp)
+        S_.append(stoch); D_.append(deter); L_.append(logit); I_.append(idx)
+    return np.stack(S_, 1), np.stack(D_, 1), np.stack(L_, 1), np.stack(I_, 1)
+
+
+def prior(c: Cfg, P, deter, u):
+    """RSSM.prior (rssm.py:189-195)."""
+    logit = img_logit(c, P, deter)
+    st, idx, _, _ = sample_onehot(logit, u, c.unimix)
+    return st, logit, idx
+
+
+def img_step(c: Cfg, P, stoch, deter, prev_action, u, tape=None):
+    """RSSM.img_step (rssm.py:180-187)."""
+    deter = deter_step(c, P, stoch, deter, prev_action, tape)
+    logit = img_logit(c, P, deter, tape)
+    st, idx, y, l = sample_onehot(logit, u, c.unimix)
+    if tape is not None:
+        tape.update(logit=logit, y=y, idx=idx, u=u, deter_out=deter)
+    return st, deter, logit, idx
+
+
+def imagine_with_action(c: Cfg, P, stoch, deter, actions, u):
+    """RSSM.imagine_with_action (rssm.py:197-209)."""
+    S_, D_ = [], []
+    for t in range(actions.shape[1]):
+        stoch, deter, _, _ = img_step(c, P, stoch, deter, actions[:, t], u[:, t])
+        S_.append(stoch); D_.append(deter)
+    return np.stack(S_, 1), np.stack(D_, 1)
+
+
+# --------------------------------------------------------------------------- heads
+def head_logits(p, name, layers, feat):
+    """MLPHead.forward up to the distribution factory (networks.py:339-377)."""
+    x = mlp(feat, p, f"mlp.layers.{name}_linear", f"mlp.layers.{name}_norm", layers)
+    return linear(x, p["last.weight"], p["last.bias"])
+
+
+def actor_sample(c: Cfg, PA, feat, noise, tape=None):
+    """_frozen_actor(feat).rsample() (dreamer.py:684; distributions.py:217-222,230-231).
+
+    cont: noise = eps ~ N(0,1) (R,A) -> tanh(mean) + std*eps (unclipped).
+    onehot: noise = uniforms (R,A) -> straight-through gumbel one-hot.
+    """
+    out = head_logits(PA, "actor", c.actor_layers, feat)
+    if c.act_kind == "cont":
+        mean, sraw = out[..., :c.A], out[..., c.A:]
+        std = feat.dtype.type(c.max_std - c.min_std) * sigmoid(sraw + feat.dtype.type(2.0)) + feat.dtype.type(c.min_std)
+        tm = np.tanh(mean)
+        if tape is not None:
+            tape.update(act_out=out, act_std=std, act_tm=tm, act_noise=noise)
+        return tm + std * noise.astype(feat.dtype)
+    st, idx, y, l = sample_onehot(out, noise, c.act_unimix)
+    if tape is not None:
+        tape.update(act_out=out, act_y=y, act_idx=idx, act_noise=noise)
+    return st
+
+
+def imagine(c: Cfg, P, PA, start, H, u, act_noise, tapes=None):
+    """Dreamer._imagine (dreamer.py:673-692): returns feats (N,H,F), actions (N,H,A)."""
+    stoch, deter = start
+    feats, actions = [], []
+    for t in range(H):
+        tp = {} if tapes is not None else None
+        feat = get_feat(stoch, deter)
+        action = actor_sample(c, PA, feat, act_noise[:, t], tp)
+        feats.append(feat); actions.append(action)
+        stoch, deter, _, _ = img_step(c, P, stoch, deter, action, u[:, t], tp)
+        if tapes is not None:
+            tp["feat"] = feat
+            tapes.append(tp)
+    return np.stack(feats, 1), np.stack(actions, 1)
+
+
+def lambda_return(last, term, reward, value, boot, disc, lamb):
+    """Dreamer._lambda_return (dreamer.py:694-707).  All inputs (N,T,1)."""
+    dt = reward.dtype.type
+    live = (dt(1.0) - term)[:, 1:] * dt(disc)
+    cont = (dt(1.0) - last)[:, 1:] * dt(lamb)
+    interm = reward[:, 1:] + (dt(1.0) - cont) * live * boot[:, 1:]
+    out = [boot[:, -1]]
+    for i in reversed(range(live.shape[1])):
+        out.append(interm[:, i] + live[:, i] * cont[:, i] * out[-1])
+    return np.stack(list(reversed(out))[:-1], 1)
+
+
+def heads_lambda(c: Cfg, PR, PC, PV, PSV, feats):
+    """dreamer.py:589-602: frozen reward/cont/value/slow-value on imagined feats,
+    discount weights and the lambda-return."""
+    bins = twohot_bins(c.bins)
+    dt = feats.dtype.type
+    rew = twohot_mode(head_logits(PR, "reward", c.reward_layers, feats), bins)
+    cont = sigmoid(head_logits(PC, "cont", c.cont_layers, feats))
+    val = twohot_mode(head_logits(PV, "value", c.value_layers, feats), bins)
+    sval = twohot_mode(head_logits(PSV, "value", c.value_layers, feats), bins)
+    disc = dt(1.0 - 1.0 / c.horizon)
+    weight = np.cumprod(cont * disc, axis=1)
+    ret = lambda_return(np.zeros_like(cont), dt(1.0) - cont, rew, val, val, disc, c.lamb)
+    return rew, cont, val, sval, weight, ret
+
+
+# --------------------------------------------------------------------------- synthetic inputs
+def synth_observe_inputs(c: Cfg, B, T, seed=2, p_reset=1.0 / 64):
+    """SURVEY.md section 8(d) inputs: embed~N(0,1), action~U(-1,1), is_first[:,0]=1 + Bernoulli."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    embed = rng.standard_normal((B, T, c.E), dtype=np.float32)
+    if c.act_kind == "cont":
+        action = (rng.random((B, T, c.A), dtype=np.float32) * 2 - 1).astype(np.float32)
+    else:
+        ai = rng.integers(0, c.A, size=(B, T))
+        action = np.eye(c.A, dtype=np.float32)[ai]
+    reset = rng.random((B, T)) < p_reset
+    reset[:, 0] = True
+    u = clamp_u(rng.random((B, T, c.S, c.K), dtype=np.float32))
+    return embed, action, reset, u
+
+
+def synth_imagine_inputs(c: Cfg, N, H, seed=3):
+    rng = np.random.Generator(np.random.Philox(seed))
+    idx = rng.integers(0, c.K, size=(N, c.S))
+    stoch = np.eye(c.K, dtype=np.float32)[idx]
+    deter = np.tanh(rng.standard_normal((N, c.D), dtype=np.float32)).astype(np.float32)
+    u = clamp_u(rng.random((N, H, c.S, c.K), dtype=np.float32))
+    if c.act_kind == "cont":
+        noise = rng.standard_normal((N, H, c.A), dtype=np.float32)
+    else:
+        noise = clamp_u(rng.random((N, H, c.A), dtype=np.float32))
+    return stoch, deter, u, noise
+
+
+def clamp_u(u):
+    lo = np.float32(2.0 ** -24)
+    return np.clip(u, lo, np.float32(1.0) - lo).astype(np.float32)
+
+
+def cast_params(P, dtype):
+    return {m: {k: v.astype(dtype) for k, v in d.items()} for m, d in P.items()}

@@ -1,0 +1,255 @@
+"""Generate golden vectors by executing the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  The GPU box never runs this; tests read the
+committed .npz files.
+
+How the reference is imported: ``world_model``,
+``utils`` and ``ablations`` are pre-registered as empty namespace packages so
+their ``__init__`` (which pull tensordict / torchrl) are skipped, and
+``tensordict.TensorDict`` is stubbed.  Noise is injected by replacing the two
+RNG draws the path makes: ``OneHotDist.rsample`` (same formula as
+``F.gumbel_softmax(hard=True)`` with g=-log(-log(u)) from a queue) and
+``torch.distributions.utils._standard_normal`` (queue of eps).
+Weights/inputs come from ``oracle.rssm_oracle.init_params`` / ``synth_*`` (seeded
+numpy Philox), so only *outputs* need to be stored for the full-size config.
+"""
+import os
+import sys
+import types
+from types import SimpleNamespace as NS
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("SD_REFERENCE", "/root/reference")
+
+from oracle import rssm_oracle as O  # noqa: E402
+
+
+def import_reference():
+    for pkg in ("world_model", "utils", "ablations"):
+        m = types.ModuleType(pkg)
+        m.__path__ = [os.path.join(REF, pkg)]
+        sys.modules[pkg] = m
+    td = types.ModuleType("tensordict")
+
+    class TensorDict(dict):
+        pass
+
+    td.TensorDict = TensorDict
+    sys.modules["tensordict"] = td
+    sys.path.insert(0, REF)
+    import world_model.rssm as rssm
+    import world_model.distributions as dists
+    import world_model.networks as networks
+    try:
+        import world_model.dreamer as dreamer
+    except Exception as e:  # pragma: no cover - depends on optional deps
+        print("dreamer.py not importable:", repr(e))
+        dreamer = None
+    return rssm, dists, networks, dreamer
+
+
+U_QUEUE, EPS_QUEUE = [], []
+
+
+def patch_noise(dists):
+    def rsample(self, sample_shape=(), temperature=1.0):
+        u = U_QUEUE.pop(0)
+        assert u.shape == self.logits.shape, (u.shape, self.logits.shape)
+        g = -torch.log(-torch.log(u))
+        y = ((self.logits + g) / temperature).softmax(-1)
+        index = y.max(-1, keepdim=True)[1]
+        y_hard = torch.zeros_like(self.logits, memory_format=torch.legacy_contiguous_format).scatter_(-1, index, 1.0)
+        return y_hard - y.detach() + y
+
+    dists.OneHotDist.rsample = rsample
+    import torch.distributions.normal as tdn
+
+    def std_normal(shape, dtype, device):
+        e = EPS_QUEUE.pop(0)
+        assert tuple(e.shape) == tuple(shape), (e.shape, shape)
+        return e.to(dtype)
+
+    tdn._standard_normal = std_normal
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def rssm_cfg(c):
+    return NS(stoch=c.S, deter=c.D, hidden=c.U, discrete=c.K, act="SiLU", unimix_ratio=c.unimix,
+              initial="learned", device="cpu", obs_layers=c.obs_layers, img_layers=c.img_layers,
+              dyn_layers=1, blocks=c.G, norm=True)
+
+
+def head_cfg(c, name, layers, out, dist):
+    return NS(act="SiLU", symlog_inputs=False, device="cpu", layers=layers, units=c.units, name=name,
+              dist=dist, outscale=1.0, shape=[out], norm=True)
+
+
+def build_reference(c, P, rssm_mod, networks):
+    R = rssm_mod.RSSM(rssm_cfg(c), c.E, c.A)
+    R.load_state_dict({k: t(v) for k, v in P["rssm"].items()}, strict=True)
+    if c.act_kind == "cont":
+        adist = NS(name="bounded_normal", min_std=c.min_std, max_std=c.max_std)
+    else:
+        adist = NS(name="onehot", unimix_ratio=c.act_unimix)
+    heads = {}
+    spec = {
+        "actor": ("actor", c.actor_layers, c.A, adist),
+        "reward": ("reward", c.reward_layers, c.bins, NS(name="symexp_twohot", bin_num=c.bins)),
+        "cont": ("cont", c.cont_layers, 1, NS(name="binary")),
+        "value": ("value", c.value_layers, c.bins, NS(name="symexp_twohot", bin_num=c.bins)),
+        "slow_value": ("value", c.value_layers, c.bins, NS(name="symexp_twohot", bin_num=c.bins)),
+    }
+    for key, (name, layers, out, dist) in spec.items():
+        h = networks.MLPHead(head_cfg(c, name, layers, out, dist), c.F)
+        h.load_state_dict({k: t(v) for k, v in P[key].items()}, strict=True)
+        heads[key] = h
+    return R, heads
+
+
+def run_case(tag, c, B, T, N, H, rssm_mod, dists, networks, dreamer, store_inputs):
+    torch.manual_seed(0)
+    P = O.init_params(c, seed=0)
+    R, heads = build_reference(c, P, rssm_mod, networks)
+    embed, action, reset, u = O.synth_observe_inputs(c, B, T, seed=2)
+    out = {"cfg_keys": np.array(sorted(c.as_dict().keys())),
+           "cfg_vals": np.array([str(c.as_dict()[k]) for k in sorted(c.as_dict().keys())]),
+           "B": B, "T": T, "N": N, "H": H}
+
+    # ---- observe (rssm.py:140-156) with a non-trivial initial state
+    rng = np.random.Generator(np.random.Philox(7))
+    init_idx = rng.integers(0, c.K, size=(B, c.S))
+    init_stoch = np.eye(c.K, dtype=np.float32)[init_idx]
+    init_deter = np.tanh(rng.standard_normal((B, c.D), dtype=np.float32)).astype(np.float32)
+    reset2 = reset.copy()
+    reset2[0, 0] = False  # row 0 keeps its initial state: exercises the carried-in path
+    emb_t = t(embed).requires_grad_(True)
+    is_t, id_t = t(init_stoch).requires_grad_(True), t(init_deter).requires_grad_(True)
+    U_QUEUE[:] = [t(u[:, i]) for i in range(T)]
+    stochs, deters, logits = R.observe(emb_t, t(action), (is_t, id_t), t(reset2)[..., None])
+    assert not U_QUEUE
+    out.update(obs_stoch_idx=stochs.detach().argmax(-1).numpy().astype(np.int8),
+               obs_stoch_maxdev=np.float32((stochs.detach() - torch.nn.functional.one_hot(stochs.detach().argmax(-1), c.K)).abs().max()),
+               obs_deter=deters.detach().numpy(), obs_logit=logits.detach().numpy())
+    # batched prior + kl (dreamer.py:485-486) + entropy metrics (dreamer.py:575-576)
+    up = O.clamp_u(np.random.Generator(np.random.Philox(11)).random((B, T, c.S, c.K), dtype=np.float32))
+    U_QUEUE[:] = [t(up)]
+    pst, plog = R.prior(deters)
+    dyn, rep = R.kl_loss(logits, plog, 1.0)
+    out.update(prior_logit=plog.detach().numpy(), prior_idx=pst.detach().argmax(-1).numpy().astype(np.int8),
+               kl_dyn=dyn.detach().numpy(), kl_rep=rep.detach().numpy(),
+               ent_post=R.get_dist(logits).entropy().detach().numpy(),
+               ent_prior=R.get_dist(plog).entropy().detach().numpy())
+    # backward through observe + prior + kl with seeded cotangents (autograd == ground truth for K2)
+    g = np.random.Generator(np.random.Philox(13))
+    c_st = g.standard_normal(stochs.shape, dtype=np.float32)
+    c_dt = g.standard_normal(deters.shape, dtype=np.float32) * np.float32(0.1)
+    c_lg = g.standard_normal(logits.shape, dtype=np.float32) * np.float32(0.1)
+    loss = (stochs * t(c_st)).sum() + (deters * t(c_dt)).sum() + (logits * t(c_lg)).sum()
+    params = dict(R.named_parameters())
+    grads = torch.autograd.grad(loss, [emb_t, is_t, id_t] + list(params.values()), allow_unused=True)
+    out.update(bwd_d_embed=grads[0].numpy(), bwd_d_init_stoch=grads[1].numpy(), bwd_d_init_deter=grads[2].numpy())
+    for (name, _), gr in zip(params.items(), grads[3:]):
+        gnp = np.zeros(P["rssm"][name].shape, np.float32) if gr is None else gr.numpy()
+        if store_inputs or gnp.size <= 4096:
+            out["bwd_g/" + name] = gnp
+        else:  # full-size config: keep a strided slice + norms to stay small
+            out["bwd_gs/" + name] = gnp.reshape(-1)[:: max(1, gnp.size // 2048)][:2048].copy()
+        out["bwd_gn/" + name] = np.float64(np.sqrt((gnp.astype(np.float64) ** 2).sum()))
+
+    # ---- single obs_step / img_step (rssm.py:158-187): the act() shape, reset as (B,1)
+    U_QUEUE[:] = [t(u[:, 0])]
+    s1, d1, l1 = R.obs_step(t(init_stoch), t(init_deter), t(action[:, 0]), t(embed[:, 0]), t(reset2[:, :1]))
+    out.update(step_obs_idx=s1.argmax(-1).numpy().astype(np.int8), step_obs_deter=d1.detach().numpy(),
+               step_obs_logit=l1.detach().numpy())
+    U_QUEUE[:] = [t(u[:, 1])]
+    s2, d2 = R.img_step(t(init_stoch), t(init_deter), t(action[:, 1]))
+    out.update(step_img_idx=s2.argmax(-1).numpy().astype(np.int8), step_img_deter=d2.detach().numpy())
+    # imagine_with_action (rssm.py:197-209)
+    U_QUEUE[:] = [t(u[:, i]) for i in range(T)]
+    ws, wd = R.imagine_with_action(t(init_stoch), t(init_deter), t(action))
+    out.update(iwa_idx=ws.argmax(-1).numpy().astype(np.int8), iwa_deter=wd.detach().numpy())
+
+    # ---- imagination (dreamer.py:673-692) with grad enabled (attack shape: dgrad-only)
+    st0, dt0, ui, noise = O.synth_imagine_inputs(c, N, H, seed=3)
+    st_t, dt_t = t(st0).requires_grad_(True), t(dt0).requires_grad_(True)
+    fake = NS(_frozen_rssm=R, _frozen_actor=heads["actor"])
+    for p_ in list(R.parameters()) + [q for h in heads.values() for q in h.parameters()]:
+        p_.requires_grad_(False)
+    imagine = dreamer.Dreamer._imagine.__wrapped__ if dreamer is not None else None
+    U_QUEUE[:] = []
+    EPS_QUEUE[:] = []
+    for i in range(H):
+        if c.act_kind == "cont":
+            EPS_QUEUE.append(t(noise[:, i]))
+        else:
+            U_QUEUE.append(t(noise[:, i]))
+        U_QUEUE.append(t(ui[:, i]))
+    if imagine is not None:
+        feats, acts = imagine(fake, (st_t, dt_t), H)
+    else:  # literal restatement of dreamer.py:680-688 on the reference modules
+        fl, al = [], []
+        s_, d_ = st_t, dt_t
+        for _ in range(H):
+            f_ = R.get_feat(s_, d_)
+            a_ = heads["actor"](f_).rsample()
+            fl.append(f_); al.append(a_)
+            s_, d_ = R.img_step(s_, d_, a_)
+        feats, acts = torch.stack(fl, 1), torch.stack(al, 1)
+    assert not U_QUEUE and not EPS_QUEUE
+    out.update(imag_feat_idx=feats.detach()[..., :c.SK].reshape(N, H, c.S, c.K).argmax(-1).numpy().astype(np.int8),
+               imag_deter=feats.detach()[..., c.SK:].numpy(), imag_action=acts.detach().numpy())
+    # heads + lambda-return (dreamer.py:589-602)
+    rew = heads["reward"](feats).mode()
+    cont = heads["cont"](feats).mean
+    val = heads["value"](feats).mode()
+    sval = heads["slow_value"](feats).mode()
+    disc = 1 - 1 / c.horizon
+    weight = torch.cumprod(cont * disc, dim=1)
+    if dreamer is not None:
+        lam = dreamer.Dreamer._lambda_return.__wrapped__
+        ret = lam(None, torch.zeros_like(cont), 1 - cont, rew, val, val, disc, c.lamb)
+    else:
+        ret = t(O.lambda_return(np.zeros_like(cont.detach().numpy()), 1 - cont.detach().numpy(),
+                                rew.detach().numpy(), val.detach().numpy(), val.detach().numpy(), disc, c.lamb))
+    out.update(imag_reward=rew.detach().numpy(), imag_cont=cont.detach().numpy(), imag_value=val.detach().numpy(),
+               imag_slow_value=sval.detach().numpy(), imag_weight=weight.detach().numpy(), imag_ret=ret.detach().numpy(),
+               used_dreamer_py=np.bool_(dreamer is not None))
+    # dgrad-only backward through imagination + heads (attack shape, README.md:70)
+    g2 = np.random.Generator(np.random.Philox(17))
+    c_f = g2.standard_normal(feats.shape, dtype=np.float32) * np.float32(0.1)
+    c_a = g2.standard_normal(acts.shape, dtype=np.float32)
+    loss2 = (feats * t(c_f)).sum() + (acts * t(c_a)).sum()
+    gs, gd = torch.autograd.grad(loss2, [st_t, dt_t])
+    out.update(imag_bwd_d_stoch=gs.numpy(), imag_bwd_d_deter=gd.numpy())
+
+    if store_inputs:
+        for mod, d in P.items():
+            for k, v in d.items():
+                out[f"P/{mod}/{k}"] = v
+    path = os.path.join(ROOT, "tests", "golden", f"{tag}.npz")
+    np.savez_compressed(path, **out)
+    print(tag, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", "dreamer.py used:", dreamer is not None)
+
+
+def main():
+    rssm_mod, dists, networks, dreamer = import_reference()
+    patch_noise(dists)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    tiny = dict(D=256, U=64, S=8, K=8, G=4, E=48, units=64)
+    run_case("tiny_cont", O.Cfg(A=3, **tiny), 3, 6, 5, 4, rssm_mod, dists, networks, dreamer, True)
+    run_case("tiny_onehot", O.Cfg(A=5, act_kind="onehot", **tiny), 3, 6, 5, 4, rssm_mod, dists, networks, dreamer, True)
+    run_case("base_cont", O.Cfg(), 2, 5, 4, 3, rssm_mod, dists, networks, dreamer, False)
+    run_case("base_onehot18", O.Cfg(A=18, act_kind="onehot"), 2, 3, 3, 3, rssm_mod, dists, networks, dreamer, False)
+
+
+if __name__ == "__main__":
+    main()
