@@ -1,0 +1,168 @@
+/*
+ * safedreamer.h -- C ABI of the B200-native RSSM latent-dynamics library
+ * (libsafedreamer.so, built from safe_dreamer_b200/csrc/, sm_100a only).
+ *
+ * The reference (sharmaabhijith/safe-dreamer) has no FFI; its boundary for
+ * this path is the Python method surface of world_model/rssm.py and the
+ * imagination / lambda-return helpers of world_model/dreamer.py.  Every entry
+ * point below names the reference method it replaces (file:line).  Tensors
+ * cross the ABI as raw device pointers in the reference's own layouts
+ * (row-major, fp32 unless noted); weights are passed in state_dict layout and
+ * repacked internally (sd_set_weights).  No torch types, no exceptions, no
+ * host synchronisation and no allocation inside the compute calls: the
+ * workspace is sized by sd_workspace_bytes() and owned by the handle.
+ *
+ * All compute calls enqueue on `stream` (a cudaStream_t passed as void*) and
+ * return 0 on success or a negative sd_status; sd_last_error_string() gives
+ * the reason.  There is no CPU fallback: without a CUDA device sd_create()
+ * fails.
+ */
+#ifndef SAFEDREAMER_H_
+#define SAFEDREAMER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+typedef enum sd_status {
+  SD_OK = 0,
+  SD_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  SD_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  SD_ERR_WORKSPACE = -3,   /* rows/steps exceed what the handle was created for */
+  SD_ERR_WEIGHTS = -4,     /* weights for a needed module were never set */
+  SD_ERR_NO_TAPE = -5      /* backward called without a matching SD_FLAG_SAVE_TAPE forward */
+} sd_status;
+
+/* Weight modules (state_dict owners in world_model/dreamer.py:65-160). */
+typedef enum sd_module {
+  SD_MOD_RSSM = 0,        /* Dreamer.rssm / _frozen_rssm   (rssm.py:78-131)   */
+  SD_MOD_ACTOR = 1,       /* Dreamer.actor                 (networks.py:339)  */
+  SD_MOD_REWARD = 2,      /* Dreamer.reward                                   */
+  SD_MOD_CONT = 3,        /* Dreamer.cont                                     */
+  SD_MOD_VALUE = 4,       /* Dreamer.value                                    */
+  SD_MOD_SLOW_VALUE = 5,  /* Dreamer._slow_value                              */
+  SD_MOD_COUNT = 6
+} sd_module;
+
+/* Call flags. */
+#define SD_FLAG_BF16       1u  /* dense layers on tcgen05 (bf16 operands, fp32 accumulate) when rows >= 128;
+                                  default is the fp32 SIMT path (bit-faithful parity mode, small batches) */
+#define SD_FLAG_SAVE_TAPE  2u  /* keep per-step activations for the matching *_bwd call */
+#define SD_FLAG_GRAPH      4u  /* replay the step sequence as a cached CUDA graph (ignored while the stream is
+                                  already being captured, e.g. under torch.compile reduce-overhead) */
+
+/* Sizes of the path: configs/base.yaml:117-127,252-276,340-420. */
+typedef struct sd_config {
+  int32_t D;            /* deter (2048) */
+  int32_t U;            /* rssm hidden (256) */
+  int32_t S;            /* stoch categories per row (32) */
+  int32_t K;            /* classes per category, `discrete` (16); <= 32 */
+  int32_t G;            /* blocks (8) */
+  int32_t E;            /* embed size (1024 vision / 256 proprio) */
+  int32_t A;            /* action dim */
+  int32_t obs_layers;   /* 1 */
+  int32_t img_layers;   /* 2 */
+  int32_t act_kind;     /* 0 = bounded_normal (continuous), 1 = onehot (discrete, A <= 32) */
+  int32_t units;        /* head hidden (256) */
+  int32_t actor_layers, value_layers, reward_layers, cont_layers; /* 3,3,1,1 */
+  int32_t bins;         /* two-hot bins (255) */
+  float unimix;         /* rssm.unimix_ratio (0.01) */
+  float act_unimix;     /* actor.dist.disc.unimix_ratio (0.01) */
+  float min_std, max_std; /* actor.dist.cont (0.1, 1.0) */
+  int32_t max_rows;     /* largest row count of any call (B for observe, N for imagine) */
+  int32_t max_steps;    /* largest T / H of any call */
+  int32_t max_tape_rows;/* largest B of a SD_FLAG_SAVE_TAPE call (0 = no backward) */
+} sd_config;
+
+typedef struct sd_handle sd_handle;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int sd_abi_version(void);
+const char* sd_last_error_string(void);
+/* Bytes of device workspace sd_create() will allocate for this config. */
+size_t sd_workspace_bytes(const sd_config* cfg);
+int sd_create(const sd_config* cfg, sd_handle** out);
+int sd_destroy(sd_handle* h);
+
+/* Number / state_dict name / element count of the i-th weight tensor of a module, in the order
+ * sd_set_weights() expects (names as in SURVEY.md section 8b, e.g. "_deter_net._dyn_gru.weight"). */
+int sd_weight_count(const sd_handle* h, int module);
+const char* sd_weight_name(const sd_handle* h, int module, int i);
+int64_t sd_weight_numel(const sd_handle* h, int module, int i);
+
+/* Repack one module's weights (fp32, reference layouts, device pointers) into the internal layouts.
+ * Must be called again whenever the parameters changed (optimizer step; laprop.py:116 updates
+ * storage in place) -- the host mirror keys this on (data_ptr, _version). */
+int sd_set_weights(sd_handle* h, int module, const float* const* tensors, int count, void* stream);
+
+/* ---- posterior scan ------------------------------------------------------------------------- */
+/* RSSM.observe (rssm.py:140-156); T == 1 is RSSM.obs_step (rssm.py:158-178).
+ *   embed (B,T,E)  action (B,T,A)  init_stoch (B,S,K)  init_deter (B,D)
+ *   is_first (B,T) uint8   u (B,T,S,K) uniforms in (0,1) that drive the Gumbel draws
+ *   out: stochs (B,T,S,K) exact one-hot, deters (B,T,D), logits (B,T,S,K)            */
+int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, const float* action,
+                   const float* init_stoch, const float* init_deter, const uint8_t* is_first,
+                   const float* u, float* stochs, float* deters, float* logits,
+                   uint32_t flags, void* stream);
+
+/* Reverse-time backward of the last SD_FLAG_SAVE_TAPE sd_observe_fwd (autograd of rssm.py:140-178).
+ *   d_stochs/d_deters/d_logits: upstream grads (nullable = zero)
+ *   out: d_embed (B,T,E), d_init_stoch (B,S,K), d_init_deter (B,D) (each nullable),
+ *        weight_grads: sd_weight_count(SD_MOD_RSSM) fp32 tensors in reference layouts, ACCUMULATED into
+ *        (nullable entries / nullable array = skip: dgrad-only, the frozen-weights attack shape). */
+int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs, const float* d_deters,
+                   const float* d_logits, float* d_embed, float* d_init_stoch, float* d_init_deter,
+                   float* const* weight_grads, uint32_t flags, void* stream);
+
+/* ---- prior steps ---------------------------------------------------------------------------- */
+/* RSSM.prior (rssm.py:189-195) on R rows: logit = _img_net(deter); stoch = rsample. */
+int sd_prior(sd_handle* h, int R, const float* deter, const float* u, float* stoch, float* logit,
+             uint32_t flags, void* stream);
+/* RSSM.imagine_with_action (rssm.py:197-209); T == 1 is RSSM.img_step (rssm.py:180-187).
+ *   stoch (R,S,K) deter (R,D) actions (R,T,A) u (R,T,S,K) -> stochs (R,T,S,K) deters (R,T,D) */
+int sd_imagine_with_action(sd_handle* h, int R, int T, const float* stoch, const float* deter,
+                           const float* actions, const float* u, float* stochs, float* deters,
+                           uint32_t flags, void* stream);
+
+/* ---- imagination rollout with in-loop actor -------------------------------------------------- */
+/* Dreamer._imagine (dreamer.py:673-692): H iterations of get_feat -> actor.rsample -> img_step.
+ *   stoch0 (N,S,K) deter0 (N,D)  u (N,H,S,K) uniforms  act_noise (N,H,A): N(0,1) eps for the
+ *   bounded-normal actor, uniforms for the one-hot actor
+ *   out: feats (N,H,S*K+D) [stoch first, rssm.py:211-217], actions (N,H,A)          */
+int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, const float* deter0,
+                   const float* u, const float* act_noise, float* feats, float* actions,
+                   uint32_t flags, void* stream);
+/* dgrad-only backward of the last SD_FLAG_SAVE_TAPE sd_imagine_fwd (frozen weights; the patch-attack
+ * shape, README.md:68-116): d_feats (N,H,F), d_actions (N,H,A) -> d_stoch0 (N,S,K), d_deter0 (N,D). */
+int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, const float* d_actions,
+                   float* d_stoch0, float* d_deter0, uint32_t flags, void* stream);
+
+/* ---- heads + lambda-return on imagined trajectories ------------------------------------------ */
+/* dreamer.py:589-602: frozen reward/cont/value/slow-value heads on feats (N,H,F), TwoHot.mode with the
+ * reference pairing (distributions.py:78-98), weight = cumprod(cont*disc), ret = _lambda_return(...).
+ *   out (each nullable): reward, cont, value, slow_value, weight (N,H,1); ret (N,H-1,1). */
+int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feats, float disc, float lamb,
+                        float* reward, float* cont, float* value, float* slow_value, float* weight,
+                        float* ret, uint32_t flags, void* stream);
+/* Dreamer._lambda_return (dreamer.py:694-707) on (N,T,1) inputs -> out (N,T-1,1). */
+int sd_lambda_return(int N, int T, const float* last, const float* term, const float* reward,
+                     const float* value, const float* boot, float disc, float lamb, float* out,
+                     void* stream);
+/* RSSM.kl_loss (rssm.py:222-230, distributions.py:266-271) on R rows of (S,K) raw logits:
+ * dyn = rep = max(sum_s KL(post||prior), free); also the unimix entropies logged at dreamer.py:575-576
+ * (each output nullable). */
+int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
+               float* dyn_loss, float* rep_loss, float* post_entropy, float* prior_entropy, void* stream);
+
+/* Kernels launched by this library since process start (all handles): bench.py's gpu_launches. */
+uint64_t sd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAFEDREAMER_H_ */

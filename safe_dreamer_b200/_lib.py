@@ -1,0 +1,116 @@
+"""ctypes binding of libsafedreamer.so (include/safedreamer.h) + the in-tree nvcc build.
+
+PyTorch is plumbing here: it owns device memory and streams; every compute call
+goes through the C ABI with raw device pointers.  There is no CPU fallback: if the
+shared library is missing or no sm_100 device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_HERE, "libsafedreamer.so")
+_INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "safedreamer.h")
+_SOURCES = ["sd_api.cu", "sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+SD_FLAG_BF16, SD_FLAG_SAVE_TAPE, SD_FLAG_GRAPH = 1, 2, 4
+MOD_RSSM, MOD_ACTOR, MOD_REWARD, MOD_CONT, MOD_VALUE, MOD_SLOW_VALUE = range(6)
+
+
+class sd_config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("D", "U", "S", "K", "G", "E", "A", "obs_layers", "img_layers", "act_kind", "units",
+                 "actor_layers", "value_layers", "reward_layers", "cont_layers", "bins")] + \
+               [(n, C.c_float) for n in ("unimix", "act_unimix", "min_std", "max_std")] + \
+               [(n, C.c_int32) for n in ("max_rows", "max_steps", "max_tape_rows")]
+
+
+def _stale():
+    if not os.path.exists(_SO):
+        return True
+    t = os.path.getmtime(_SO)
+    srcs = [os.path.join(_CSRC, s) for s in _SOURCES] + [_INCLUDE]
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU). Returns the .so path."""
+    if not force and not _stale():
+        return _SO
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(_CSRC, "sd_api.cu"), "-o", _SO]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return _SO
+
+
+_lib = None
+_lock = threading.Lock()
+
+_P = C.c_void_p
+_SIGS = {
+    "sd_abi_version": (C.c_int, []),
+    "sd_last_error_string": (C.c_char_p, []),
+    "sd_workspace_bytes": (C.c_size_t, [C.POINTER(sd_config)]),
+    "sd_create": (C.c_int, [C.POINTER(sd_config), C.POINTER(_P)]),
+    "sd_destroy": (C.c_int, [_P]),
+    "sd_weight_count": (C.c_int, [_P, C.c_int]),
+    "sd_weight_name": (C.c_char_p, [_P, C.c_int, C.c_int]),
+    "sd_weight_numel": (C.c_int64, [_P, C.c_int, C.c_int]),
+    "sd_set_weights": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.c_int, _P]),
+    "sd_observe_fwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 9 + [C.c_uint32, _P]),
+    "sd_observe_bwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 6 + [C.POINTER(_P), C.c_uint32, _P]),
+    "sd_prior": (C.c_int, [_P, C.c_int] + [_P] * 4 + [C.c_uint32, _P]),
+    "sd_imagine_with_action": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 6 + [C.c_uint32, _P]),
+    "sd_imagine_fwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 6 + [C.c_uint32, _P]),
+    "sd_imagine_bwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 4 + [C.c_uint32, _P]),
+    "sd_heads_lambda_fwd": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_float, C.c_float] + [_P] * 6 + [C.c_uint32, _P]),
+    "sd_lambda_return": (C.c_int, [C.c_int, C.c_int] + [_P] * 5 + [C.c_float, C.c_float, _P, _P]),
+    "sd_kl_loss": (C.c_int, [_P, C.c_int, _P, _P, C.c_float] + [_P] * 4 + [_P]),
+    "sd_launch_count": (C.c_uint64, []),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load():
+    """Load the shared library (building it if the sources are newer). Raises if unavailable."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _stale():
+            build()
+        lib = C.CDLL(_SO)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.sd_abi_version() != 1:
+            raise RuntimeError("libsafedreamer ABI mismatch")
+        _lib = lib
+        return lib
+
+
+def last_error():
+    return load().sd_last_error_string().decode()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")
+
+
+def launch_count():
+    return int(load().sd_launch_count())

@@ -1,0 +1,1051 @@
+// sd_api.cu -- C ABI (include/safedreamer.h) and host-side orchestration of the RSSM hot path.
+//
+// The scans are sequences of fused kernels on one CUDA stream, optionally replayed as a cached CUDA
+// graph.  Dense layers go through `linear()`, which picks the fp32 SIMT skinny GEMM (parity path,
+// small batches) or the tcgen05 bf16 GEMM (SD_FLAG_BF16 and rows >= 128).  All state lives in a
+// workspace owned by the handle; the compute calls never allocate or synchronise.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/safedreamer.h"
+#include "sd_kernels.cuh"
+#include "sd_tc.cuh"
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t e_ = (expr);                                                                         \
+    if (e_ != cudaSuccess) return fail(SD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ structs
+struct LinearW {
+  int G = 1, N = 0, K = 0;
+  int ldw = 0;    // fp32 Wt row stride (N padded to 16)
+  int ldk = 0;    // fp32 Wn row stride (K padded to 16)
+  int npad = 0;   // bf16 rows per block (N padded to 256)
+  float* wt = nullptr;    // [G][K][ldw]   forward operand (n contiguous)
+  float* wn = nullptr;    // [G][N][ldk]   dgrad operand (k contiguous)
+  bf16* w_bf = nullptr;   // [G][npad][K]  tcgen05 forward operand (K-major rows)
+  float* bias = nullptr;  // [G*N]
+  float* gain = nullptr;  // RMSNorm scale that follows this layer (nullable)
+  bool tc_ok() const { return (K % 64) == 0; }
+};
+
+struct HeadW {
+  int layers = 0, out = 0;
+  std::vector<LinearW> l;  // hidden layers (gain set)
+  LinearW last;
+  bool set = false;
+};
+
+struct WeightDesc {
+  std::string name;
+  int64_t numel;
+};
+
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t off = 0, cap = 0;
+  bool dry = true;
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// Per-step activations (the backward tape when `stride` != 0).
+struct StepBufs {
+  float *zin, *din, *ain, *vin, *x, *hpre, *h, *q, *lg, *ucopy;
+  float* vobs[4];
+  float* o[4];
+  float *va[4], *ao[4], *aout;  // actor pre-activations / activations / last-layer output
+  size_t stride;                 // floats between consecutive steps (0 = reuse)
+};
+
+struct GraphEntry {
+  uint64_t key;
+  cudaGraphExec_t exec;
+  uint64_t launches;
+};
+
+struct sd_handle {
+  sd_config c;
+  int SK, F, Dg, act_out;
+  Arena ws;
+  // weights
+  LinearW in0, in1, in2, hid, gru, obs[4], obs_logit, img[4], img_logit;
+  bool rssm_set = false;
+  HeadW heads[SD_MOD_COUNT];  // index by sd_module (RSSM slot unused)
+  std::vector<WeightDesc> wdesc[SD_MOD_COUNT];
+  float* bins = nullptr;
+  // activations
+  StepBufs sb;        // non-taped (max_rows)
+  StepBufs tape;      // taped (max_tape_rows x max_steps)
+  int tape_B = 0, tape_T = 0;
+  bool tape_valid = false;
+  // bf16 staging for the tcgen05 path
+  bf16 *feat_bf, *x_bf, *h_bf, *o_bf[4], *a_bf[4], *emb_bf, *big_bf;
+  float *scratch_stoch, *scratch_deter, *abar, *abar0;
+  // heads workspace
+  float *hv, *ho, *hl, *h_rew, *h_cont, *h_val, *kl_a, *kl_b, *kl_c;
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
+  bf16* trunk_bf = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// bf16 row-major [rows x cols] with row stride ld (elements); box = 64 columns x box_rows rows, 128B swizzle.
+static bool make_map(CUtensorMap* m, const bf16* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(bf16)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------ launch ctx
+struct Ctx {
+  sd_handle* h;
+  cudaStream_t st;
+  bool tc;        // tcgen05 path requested and eligible (rows >= 128)
+  int err = 0;
+  uint64_t launches = 0;
+  void check(const char* what) {
+    ++launches;
+    if (err) return;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      err = fail(SD_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    }
+  }
+};
+
+// An activation matrix: fp32 view and (tcgen05 path) bf16 view; gstride = per-block column offset.
+struct Operand {
+  const float* f = nullptr; int ldf = 0;
+  const bf16* b = nullptr;  int ldb = 0;
+  int gstride = 0;
+};
+static Operand opf(const float* f, int ldf, int gstride = 0) { Operand o; o.f = f; o.ldf = ldf; o.gstride = gstride; return o; }
+static Operand opfb(const float* f, int ldf, const bf16* b, int ldb, int gstride = 0) {
+  Operand o; o.f = f; o.ldf = ldf; o.b = b; o.ldb = ldb; o.gstride = gstride; return o;
+}
+
+static inline int grid1d(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  if (g > 148 * 32) g = 148 * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+struct LinCall {  // one dense layer applied to (up to) two concatenated operands
+  const LinearW* L;
+  Operand a1; int K1;
+  Operand a2;
+  float* C; int ldc; int c_gstride;
+};
+
+template <int BN>
+static void launch_tc(Ctx& cx, const sd::tc::Batch& b, int ntiles_n, int R) {
+  using L = sd::tc::SmemLayout<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    attr_done = true;
+  }
+  dim3 grid(ntiles_n, (R + sd::tc::BM - 1) / sd::tc::BM, b.count);
+  sd::tc::gemm_bf16_tc_kernel<BN><<<grid, sd::tc::THREADS, L::kTotal, cx.st>>>(b);
+  cx.check("gemm_bf16_tc_kernel");
+}
+
+// Run a set of independent dense layers (same row count) as ONE launch per backend.
+static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
+  if (cx.err) return;
+  // ---- tcgen05 problems
+  sd::tc::Batch tb;
+  memset(&tb, 0, sizeof(tb));
+  int nmaps = 0, ntc = 0, max_n_tc = 0;
+  bool batch_wide = false;
+  sd::GemmBatch gb;
+  memset(&gb, 0, sizeof(gb));
+  gb.R = R;
+  int max_n_f = 0;
+  auto flush_f = [&]() {
+    if (gb.count == 0) return;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
+      attr_done = true;
+    }
+    dim3 grid((max_n_f + 15) / 16, (R + 15) / 16, gb.count);
+    sd::gemm_f32_kernel<<<grid, 256, sd::GB_SMEM, cx.st>>>(gb);
+    cx.check("gemm_f32_kernel");
+    gb.count = 0;
+    max_n_f = 0;
+  };
+  auto flush_tc = [&]() {
+    if (ntc == 0) return;
+    tb.count = ntc;
+    tb.R = R;
+    // small-N problems: 64-wide tiles spread the work over more SMs; wide ones use 256.
+    if (batch_wide) launch_tc<256>(cx, tb, (max_n_tc + 255) / 256, R);
+    else launch_tc<64>(cx, tb, (max_n_tc + 63) / 64, R);
+    ntc = 0; nmaps = 0; max_n_tc = 0;
+  };
+  for (int ci = 0; ci < ncalls && !cx.err; ++ci) {
+    const LinCall& c = calls[ci];
+    const LinearW& L = *c.L;
+    const int K2 = L.K - c.K1;
+    const bool use_tc = cx.tc && L.tc_ok() && (c.K1 % 64) == 0 && L.N >= 64 && c.a1.b && (K2 == 0 || c.a2.b);
+    if (use_tc) {
+      // maps: a1, (a2), w  -- one set per call, shared by its G block problems
+      const bool wide = (R >= 4096 && L.N >= 256);  // a batch never mixes tile widths
+      if (ntc > 0 && (wide != batch_wide || ntc + L.G > sd::tc::kMaxProblems || nmaps + 3 > sd::tc::kMaxMaps)) flush_tc();
+      batch_wide = wide;
+      const int m_a1 = nmaps++;
+      bool ok = make_map(&tb.maps[m_a1], c.a1.b, (uint64_t)R, (uint64_t)c.a1.ldb, (uint64_t)c.a1.ldb, 128);
+      int m_a2 = m_a1;
+      if (K2 > 0) {
+        m_a2 = nmaps++;
+        ok = ok && make_map(&tb.maps[m_a2], c.a2.b, (uint64_t)R, (uint64_t)c.a2.ldb, (uint64_t)c.a2.ldb, 128);
+      }
+      const int m_w = nmaps++;
+      ok = ok && make_map(&tb.maps[m_w], L.w_bf, (uint64_t)L.G * L.npad, (uint64_t)L.K, (uint64_t)L.K, wide ? 256 : 64);
+      if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed"); return; }
+      for (int g = 0; g < L.G; ++g) {
+        sd::tc::Problem& p = tb.p[ntc++];
+        p.a1_map = m_a1; p.a1_col = g * c.a1.gstride;
+        p.a2_map = m_a2; p.a2_col = g * c.a2.gstride;
+        p.w_map = m_w;   p.w_row = g * L.npad;
+        p.K1 = c.K1; p.K = L.K; p.N = L.N; p.ldc = c.ldc;
+        p.C = c.C + (size_t)g * c.c_gstride;
+        p.bias = L.bias ? L.bias + (size_t)g * L.N : nullptr;
+      }
+      if (L.N > max_n_tc) max_n_tc = L.N;
+    } else {
+      if (!c.a1.f || (K2 > 0 && !c.a2.f)) { cx.err = fail(SD_ERR_INVALID, "linear: fp32 operand missing"); return; }
+      for (int g = 0; g < L.G; ++g) {
+        if (gb.count == sd::kMaxBatch) flush_f();
+        sd::GemmP& p = gb.p[gb.count++];
+        p.A = c.a1.f + (size_t)g * c.a1.gstride; p.lda = c.a1.ldf;
+        p.A2 = K2 > 0 ? c.a2.f + (size_t)g * c.a2.gstride : nullptr; p.lda2 = c.a2.ldf;
+        p.K1 = c.K1; p.K = L.K;
+        p.Wt = L.wt + (size_t)g * L.K * L.ldw; p.ldw = L.ldw;
+        p.bias = L.bias ? L.bias + (size_t)g * L.N : nullptr;
+        p.C = c.C + (size_t)g * c.c_gstride; p.ldc = c.ldc; p.N = L.N;
+        if (L.N > max_n_f) max_n_f = L.N;
+      }
+    }
+  }
+  flush_tc();
+  flush_f();
+}
+static void linear(Ctx& cx, int R, const LinearW& L, Operand a1, int K1, Operand a2, float* C, int ldc, int c_gstride = 0) {
+  LinCall c{&L, a1, K1, a2, C, ldc, c_gstride};
+  linear_multi(cx, R, &c, 1);
+}
+
+static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
+  if (cx.err) return;
+  sd::NormActBatch b;
+  b.count = n;
+  for (int i = 0; i < n; ++i) b.p[i] = ps[i];
+  sd::normact_kernel<<<dim3(R, n), 256, 0, cx.st>>>(b);
+  cx.check("normact_kernel");
+}
+static sd::NormActP nap(const float* in, int ld_in, const float* w, int width, float* out, int ld_out, bf16* ob, int ld_bf) {
+  sd::NormActP p;
+  p.in = in; p.ld_in = ld_in; p.w = w; p.out = out; p.ld_out = ld_out; p.out_bf = ob; p.ld_bf = ld_bf; p.width = width;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------ config / layout
+static int validate(const sd_config& c) {
+  if (c.D <= 0 || c.U <= 0 || c.S <= 0 || c.K <= 0 || c.G <= 0 || c.E <= 0 || c.A <= 0)
+    return fail(SD_ERR_INVALID, "sd_config: sizes must be positive");
+  if (c.K > 32) return fail(SD_ERR_INVALID, "sd_config: K (discrete) > 32 unsupported");
+  if (c.D % c.G) return fail(SD_ERR_INVALID, "sd_config: D %% G != 0");
+  if (c.D > 2048 || c.U > 2048 || c.units > 2048) return fail(SD_ERR_INVALID, "sd_config: norm width > 2048 unsupported");
+  if (c.obs_layers < 1 || c.obs_layers > 4 || c.img_layers < 1 || c.img_layers > 4)
+    return fail(SD_ERR_INVALID, "sd_config: obs/img layers must be in [1,4]");
+  if (c.actor_layers < 1 || c.actor_layers > 4 || c.value_layers < 1 || c.value_layers > 4 || c.reward_layers < 1 ||
+      c.reward_layers > 4 || c.cont_layers < 1 || c.cont_layers > 4)
+    return fail(SD_ERR_INVALID, "sd_config: head layers must be in [1,4]");
+  if (c.act_kind != 0 && c.act_kind != 1) return fail(SD_ERR_INVALID, "sd_config: act_kind must be 0 or 1");
+  if (c.act_kind == 1 && c.A > 32) return fail(SD_ERR_INVALID, "sd_config: one-hot actor with A > 32 unsupported");
+  if (c.max_rows < 1 || c.max_steps < 1) return fail(SD_ERR_INVALID, "sd_config: max_rows/max_steps must be >= 1");
+  if (c.bins < 2 || c.bins > 1024) return fail(SD_ERR_INVALID, "sd_config: bins out of range");
+  return 0;
+}
+
+static int up(int v, int m) { return (v + m - 1) / m * m; }
+
+static void alloc_linear(Arena& a, LinearW& L, int G, int N, int K, bool has_bias, bool has_gain, int gain_n) {
+  L.G = G; L.N = N; L.K = K;
+  L.ldw = up(N, 16); L.ldk = up(K, 16); L.npad = up(N, 256);
+  L.wt = a.take<float>((size_t)G * K * L.ldw);
+  L.wn = a.take<float>((size_t)G * N * L.ldk);
+  L.w_bf = (K % 64 == 0) ? a.take<bf16>((size_t)G * L.npad * K) : nullptr;
+  L.bias = has_bias ? a.take<float>((size_t)G * N) : nullptr;
+  L.gain = has_gain ? a.take<float>((size_t)gain_n) : nullptr;
+}
+
+static void alloc_stepbufs(Arena& a, StepBufs& sb, const sd_handle& h, size_t rows, size_t steps, bool with_actor) {
+  const sd_config& c = h.c;
+  const size_t n = rows * steps;
+  sb.stride = 0;
+  sb.zin = a.take<float>(n * h.SK);
+  sb.din = a.take<float>(n * c.D);
+  sb.ain = a.take<float>(n * c.A);
+  sb.vin = a.take<float>(n * 3 * c.U);
+  sb.x = a.take<float>(n * 3 * c.U);
+  sb.hpre = a.take<float>(n * c.D);
+  sb.h = a.take<float>(n * c.D);
+  sb.q = a.take<float>(n * 3 * c.D);
+  sb.lg = a.take<float>(n * h.SK);
+  sb.ucopy = a.take<float>(n * h.SK);
+  const int nl = c.obs_layers > c.img_layers ? c.obs_layers : c.img_layers;
+  for (int i = 0; i < 4; ++i) {
+    sb.vobs[i] = i < nl ? a.take<float>(n * c.U) : nullptr;
+    sb.o[i] = i < nl ? a.take<float>(n * c.U) : nullptr;
+    sb.va[i] = (with_actor && i < c.actor_layers) ? a.take<float>(n * c.units) : nullptr;
+    sb.ao[i] = (with_actor && i < c.actor_layers) ? a.take<float>(n * c.units) : nullptr;
+  }
+  sb.aout = with_actor ? a.take<float>(n * up(h.act_out, 4)) : nullptr;
+}
+
+static void layout(sd_handle& h, Arena& a) {
+  const sd_config& c = h.c;
+  const int SK = h.SK, F = h.F, Dg = h.Dg;
+  alloc_linear(a, h.in0, 1, c.U, c.D, true, true, c.U);
+  alloc_linear(a, h.in1, 1, c.U, SK, true, true, c.U);
+  alloc_linear(a, h.in2, 1, c.U, c.A, true, true, c.U);
+  alloc_linear(a, h.hid, c.G, Dg, Dg + 3 * c.U, true, true, c.D);
+  alloc_linear(a, h.gru, c.G, 3 * Dg, Dg, true, false, 0);
+  for (int i = 0; i < c.obs_layers; ++i) alloc_linear(a, h.obs[i], 1, c.U, i == 0 ? c.D + c.E : c.U, true, true, c.U);
+  alloc_linear(a, h.obs_logit, 1, SK, c.U, true, false, 0);
+  for (int i = 0; i < c.img_layers; ++i) alloc_linear(a, h.img[i], 1, c.U, i == 0 ? c.D : c.U, true, true, c.U);
+  alloc_linear(a, h.img_logit, 1, SK, c.U, true, false, 0);
+  const int hl[SD_MOD_COUNT] = {0, c.actor_layers, c.reward_layers, c.cont_layers, c.value_layers, c.value_layers};
+  const int ho[SD_MOD_COUNT] = {0, h.act_out, c.bins, 1, c.bins, c.bins};
+  for (int m = 1; m < SD_MOD_COUNT; ++m) {
+    HeadW& hw = h.heads[m];
+    hw.layers = hl[m]; hw.out = ho[m];
+    hw.l.resize(hl[m]);
+    for (int i = 0; i < hl[m]; ++i) alloc_linear(a, hw.l[i], 1, c.units, i == 0 ? F : c.units, true, true, c.units);
+    alloc_linear(a, hw.last, 1, ho[m], c.units, true, false, 0);
+  }
+  h.bins = a.take<float>(c.bins);
+  const size_t R = c.max_rows, T = c.max_steps;
+  alloc_stepbufs(a, h.sb, h, R, 1, true);
+  if (c.max_tape_rows > 0) alloc_stepbufs(a, h.tape, h, c.max_tape_rows, T, true);
+  h.feat_bf = a.take<bf16>(R * F);
+  h.x_bf = a.take<bf16>(R * 3 * c.U);
+  h.h_bf = a.take<bf16>(R * c.D);
+  for (int i = 0; i < 4; ++i) {
+    h.o_bf[i] = a.take<bf16>(R * c.U);
+    h.a_bf[i] = a.take<bf16>(R * c.units);
+  }
+  h.emb_bf = a.take<bf16>(R * T * c.E);
+  h.big_bf = a.take<bf16>(R * T * F);  // heads: bf16 copy of (N*H, F) feats
+  h.scratch_stoch = a.take<float>(R * SK);
+  h.scratch_deter = a.take<float>(R * c.D);
+  h.abar = a.take<float>(R * c.A);
+  h.abar0 = a.take<float>(R * c.A);
+  // heads workspace over N*H rows
+  const size_t NH = R * T;
+  h.trunk_bf = a.take<bf16>(NH * c.units);
+  h.hv = a.take<float>(NH * c.units);
+  h.ho = a.take<float>(NH * c.units);
+  h.hl = a.take<float>(NH * up(c.bins, 4));
+  h.h_rew = a.take<float>(NH);
+  h.h_cont = a.take<float>(NH);
+  h.h_val = a.take<float>(NH);
+  h.kl_a = a.take<float>(NH * c.S);
+  h.kl_b = a.take<float>(NH * c.S);
+  h.kl_c = a.take<float>(NH * c.S);
+}
+
+static void describe_weights(sd_handle& h) {
+  const sd_config& c = h.c;
+  auto& r = h.wdesc[SD_MOD_RSSM];
+  const int64_t U = c.U, D = c.D, SK = h.SK, Dg = h.Dg, A = c.A;
+  const char* in_names[3] = {"_deter_net._dyn_in0", "_deter_net._dyn_in1", "_deter_net._dyn_in2"};
+  const int64_t in_k[3] = {D, SK, A};
+  for (int i = 0; i < 3; ++i) {
+    r.push_back({std::string(in_names[i]) + ".0.weight", U * in_k[i]});
+    r.push_back({std::string(in_names[i]) + ".0.bias", U});
+    r.push_back({std::string(in_names[i]) + ".1.weight", U});
+  }
+  r.push_back({"_deter_net._dyn_hid.dyn_hid_0.weight", Dg * (Dg + 3 * U) * c.G});
+  r.push_back({"_deter_net._dyn_hid.dyn_hid_0.bias", D});
+  r.push_back({"_deter_net._dyn_hid.norm_0.weight", D});
+  r.push_back({"_deter_net._dyn_gru.weight", 3 * Dg * Dg * c.G});
+  r.push_back({"_deter_net._dyn_gru.bias", 3 * D});
+  char buf[128];
+  for (int i = 0; i < c.obs_layers; ++i) {
+    const int64_t k = i == 0 ? D + c.E : U;
+    snprintf(buf, sizeof(buf), "_obs_net.obs_net_%d.weight", i); r.push_back({buf, U * k});
+    snprintf(buf, sizeof(buf), "_obs_net.obs_net_%d.bias", i); r.push_back({buf, U});
+    snprintf(buf, sizeof(buf), "_obs_net.obs_net_n_%d.weight", i); r.push_back({buf, U});
+  }
+  r.push_back({"_obs_net.obs_net_logit.weight", SK * U});
+  r.push_back({"_obs_net.obs_net_logit.bias", SK});
+  for (int i = 0; i < c.img_layers; ++i) {
+    const int64_t k = i == 0 ? D : U;
+    snprintf(buf, sizeof(buf), "_img_net.img_net_%d.weight", i); r.push_back({buf, U * k});
+    snprintf(buf, sizeof(buf), "_img_net.img_net_%d.bias", i); r.push_back({buf, U});
+    snprintf(buf, sizeof(buf), "_img_net.img_net_n_%d.weight", i); r.push_back({buf, U});
+  }
+  r.push_back({"_img_net.img_net_logit.weight", SK * U});
+  r.push_back({"_img_net.img_net_logit.bias", SK});
+  const char* hn[SD_MOD_COUNT] = {"", "actor", "reward", "cont", "value", "value"};
+  for (int m = 1; m < SD_MOD_COUNT; ++m) {
+    const HeadW& hw = h.heads[m];
+    for (int i = 0; i < hw.layers; ++i) {
+      const int64_t k = i == 0 ? h.F : c.units;
+      snprintf(buf, sizeof(buf), "mlp.layers.%s_linear%d.weight", hn[m], i); h.wdesc[m].push_back({buf, c.units * k});
+      snprintf(buf, sizeof(buf), "mlp.layers.%s_linear%d.bias", hn[m], i); h.wdesc[m].push_back({buf, c.units});
+      snprintf(buf, sizeof(buf), "mlp.layers.%s_norm%d.weight", hn[m], i); h.wdesc[m].push_back({buf, c.units});
+    }
+    h.wdesc[m].push_back({"last.weight", (int64_t)hw.out * c.units});
+    h.wdesc[m].push_back({"last.bias", hw.out});
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ lifetime
+extern "C" int sd_abi_version(void) { return SD_ABI_VERSION; }
+extern "C" const char* sd_last_error_string(void) { return g_err; }
+extern "C" uint64_t sd_launch_count(void) { return g_launches.load(); }
+
+static void init_dims(sd_handle& h) {
+  h.SK = h.c.S * h.c.K;
+  h.F = h.SK + h.c.D;
+  h.Dg = h.c.D / h.c.G;
+  h.act_out = h.c.act_kind == 0 ? 2 * h.c.A : h.c.A;
+}
+
+extern "C" size_t sd_workspace_bytes(const sd_config* cfg) {
+  if (!cfg || validate(*cfg)) return 0;
+  sd_handle h;
+  h.c = *cfg;
+  init_dims(h);
+  Arena a;
+  a.dry = true;
+  layout(h, a);
+  return a.off + 256;
+}
+
+extern "C" int sd_create(const sd_config* cfg, sd_handle** out) {
+  if (!cfg || !out) return fail(SD_ERR_INVALID, "sd_create: null argument");
+  if (int e = validate(*cfg)) return e;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return fail(SD_ERR_CUDA, "sd_create: no CUDA device (this library has no CPU fallback)");
+  }
+  int dev = 0, major = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail(SD_ERR_CUDA, "sd_create: device is sm_%d0, this build is sm_100a only", major);
+  sd_handle* h = new sd_handle();
+  h->c = *cfg;
+  init_dims(*h);
+  Arena dry;
+  dry.dry = true;
+  layout(*h, dry);
+  const size_t bytes = dry.off + 256;
+  void* base = nullptr;
+  cudaError_t e = cudaMalloc(&base, bytes);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(SD_ERR_CUDA, "sd_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  cudaMemset(base, 0, bytes);
+  h->ws.base = static_cast<uint8_t*>(base);
+  h->ws.cap = bytes;
+  h->ws.off = 0;
+  h->ws.dry = false;
+  for (int m = 0; m < SD_MOD_COUNT; ++m) h->heads[m] = HeadW();
+  layout(*h, h->ws);
+  describe_weights(*h);
+  // two-hot bins: symexp(linspace(-20, 0, n/2+1)) mirrored, torch.linspace's symmetric fp32 algorithm
+  // (distributions.py:242-251).
+  {
+    const int n = cfg->bins;
+    std::vector<float> b(n);
+    const int half_n = (n % 2) ? (n - 1) / 2 + 1 : n / 2;
+    std::vector<float> half(half_n);
+    const float start = -20.f, end = 0.f;
+    const float step = (end - start) / (float)(half_n - 1);
+    for (int i = 0; i < half_n; ++i) {
+      const float x = (i < half_n / 2) ? start + step * (float)i : end - step * (float)(half_n - 1 - i);
+      const float ax = fabsf(x);
+      half[i] = (x < 0 ? -1.f : (x > 0 ? 1.f : 0.f)) * expm1f(ax);
+    }
+    if (n % 2) {
+      for (int i = 0; i < half_n; ++i) b[i] = half[i];
+      for (int i = 0; i < half_n - 1; ++i) b[half_n + i] = -half[half_n - 2 - i];
+    } else {
+      for (int i = 0; i < half_n; ++i) b[i] = half[i];
+      for (int i = 0; i < half_n; ++i) b[half_n + i] = -half[half_n - 1 - i];
+    }
+    cudaMemcpy(h->bins, b.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = h;
+  return SD_OK;
+}
+
+extern "C" int sd_destroy(sd_handle* h) {
+  if (!h) return SD_OK;
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->ws.base) cudaFree(h->ws.base);
+  delete h;
+  return SD_OK;
+}
+
+extern "C" int sd_weight_count(const sd_handle* h, int module) {
+  if (!h || module < 0 || module >= SD_MOD_COUNT) return -1;
+  return (int)h->wdesc[module].size();
+}
+extern "C" const char* sd_weight_name(const sd_handle* h, int module, int i) {
+  if (!h || module < 0 || module >= SD_MOD_COUNT || i < 0 || i >= (int)h->wdesc[module].size()) return nullptr;
+  return h->wdesc[module][i].name.c_str();
+}
+extern "C" int64_t sd_weight_numel(const sd_handle* h, int module, int i) {
+  if (!h || module < 0 || module >= SD_MOD_COUNT || i < 0 || i >= (int)h->wdesc[module].size()) return -1;
+  return h->wdesc[module][i].numel;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+static void pack_linear(Ctx& cx, LinearW& L, const float* w, const float* bias, const float* gain, int gain_n,
+                        bool block_layout) {
+  if (cx.err) return;
+  const long long s_g = block_layout ? 1 : 0;
+  const long long s_n = block_layout ? (long long)L.K * L.G : L.K;
+  const long long s_k = block_layout ? L.G : 1;
+  sd::pack_weight_kernel<<<grid1d((long long)L.G * L.N * L.K, 256), 256, 0, cx.st>>>(
+      w, L.G, L.N, L.K, s_g, s_n, s_k, L.wt, L.ldw, L.wn, L.ldk, L.w_bf, nullptr);
+  cx.check("pack_weight_kernel");
+  if (L.w_bf == nullptr) { /* K not a multiple of 64: SIMT only */ }
+  if (bias && L.bias) cudaMemcpyAsync(L.bias, bias, (size_t)L.G * L.N * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+  if (gain && L.gain) cudaMemcpyAsync(L.gain, gain, (size_t)gain_n * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+}
+// bf16 rows are addressed [G][npad][K] but pack_weight_kernel writes [g][n][ldk]: for the bf16 copy the row
+// stride must be K and the block stride npad*K, so it gets its own call below.
+static void pack_linear_bf(Ctx& cx, LinearW& L, const float* w, bool block_layout) {
+  if (cx.err || !L.w_bf) return;
+  const long long s_n = block_layout ? (long long)L.K * L.G : L.K;
+  const long long s_k = block_layout ? L.G : 1;
+  for (int g = 0; g < L.G; ++g) {
+    sd::pack_weight_kernel<<<grid1d((long long)L.N * L.K, 256), 256, 0, cx.st>>>(
+        w + (block_layout ? g : 0), 1, L.N, L.K, 0, s_n, s_k, nullptr, 0, nullptr, L.K,
+        L.w_bf + (size_t)g * L.npad * L.K, nullptr);
+    cx.check("pack_weight_kernel(bf16)");
+  }
+}
+
+extern "C" int sd_set_weights(sd_handle* h, int module, const float* const* t, int count, void* stream) {
+  if (!h || !t) return fail(SD_ERR_INVALID, "sd_set_weights: null argument");
+  if (module < 0 || module >= SD_MOD_COUNT) return fail(SD_ERR_INVALID, "sd_set_weights: bad module %d", module);
+  if (count != (int)h->wdesc[module].size())
+    return fail(SD_ERR_INVALID, "sd_set_weights: module %d expects %zu tensors, got %d", module, h->wdesc[module].size(), count);
+  for (int i = 0; i < count; ++i)
+    if (!t[i]) return fail(SD_ERR_INVALID, "sd_set_weights: tensor %d (%s) is null", i, h->wdesc[module][i].name.c_str());
+  Ctx cx{h, (cudaStream_t)stream, false};
+  const sd_config& c = h->c;
+  auto pack = [&](LinearW& L, const float* w, const float* b, const float* g, int gn, bool blk) {
+    LinearW tmp = L;
+    tmp.w_bf = nullptr;  // fp32 layouts first (the generic kernel's bf16 strides differ)
+    pack_linear(cx, tmp, w, b, g, gn, blk);
+    pack_linear_bf(cx, L, w, blk);
+  };
+  int i = 0;
+  if (module == SD_MOD_RSSM) {
+    pack(h->in0, t[0], t[1], t[2], c.U, false);
+    pack(h->in1, t[3], t[4], t[5], c.U, false);
+    pack(h->in2, t[6], t[7], t[8], c.U, false);
+    pack(h->hid, t[9], t[10], t[11], c.D, true);
+    pack(h->gru, t[12], t[13], nullptr, 0, true);
+    i = 14;
+    for (int l = 0; l < c.obs_layers; ++l, i += 3) pack(h->obs[l], t[i], t[i + 1], t[i + 2], c.U, false);
+    pack(h->obs_logit, t[i], t[i + 1], nullptr, 0, false); i += 2;
+    for (int l = 0; l < c.img_layers; ++l, i += 3) pack(h->img[l], t[i], t[i + 1], t[i + 2], c.U, false);
+    pack(h->img_logit, t[i], t[i + 1], nullptr, 0, false); i += 2;
+    h->rssm_set = true;
+  } else {
+    HeadW& hw = h->heads[module];
+    for (int l = 0; l < hw.layers; ++l, i += 3) pack(hw.l[l], t[i], t[i + 1], t[i + 2], c.units, false);
+    pack(hw.last, t[i], t[i + 1], nullptr, 0, false);
+    hw.set = true;
+  }
+  g_launches += cx.launches;
+  if (cx.err) return cx.err;
+  return SD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ graphs
+static uint64_t fnv(uint64_t h, const void* p, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+struct Key {
+  uint64_t v = 1469598103934665603ull;
+  template <class T> Key& add(const T& x) { v = fnv(v, &x, sizeof(T)); return *this; }
+};
+
+template <class F>
+static int run(sd_handle* h, uint64_t key, uint32_t flags, cudaStream_t st, bool tc, F&& body) {
+  auto direct = [&]() -> int {
+    Ctx cx{h, st, tc};
+    body(cx);
+    g_launches += cx.launches;
+    return cx.err;
+  };
+  if (!(flags & SD_FLAG_GRAPH)) return direct();
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return direct();
+  }
+  for (auto& g : h->graphs)
+    if (g.key == key) {
+      CUDA_TRY(cudaGraphLaunch(g.exec, st));
+      g_launches += g.launches;
+      return SD_OK;
+    }
+  // warm any lazily-set function attributes / driver entry points outside capture with a direct run
+  // (results are identical; the captured replay below overwrites them).
+  if (int e = direct()) return e;
+  CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+  Ctx cx{h, h->cap_stream, tc};
+  body(cx);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ee = cudaStreamEndCapture(h->cap_stream, &graph);
+  if (cx.err) { if (graph) cudaGraphDestroy(graph); return cx.err; }
+  if (ee != cudaSuccess) return fail(SD_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ee));
+  cudaGraphExec_t exec = nullptr;
+  ee = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ee != cudaSuccess) return fail(SD_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ee));
+  if (h->graphs.size() >= 16) {
+    cudaGraphExecDestroy(h->graphs.front().exec);
+    h->graphs.erase(h->graphs.begin());
+  }
+  h->graphs.push_back({key, exec, cx.launches});
+  // the direct warm-up run above already produced this call's results; no replay needed now.
+  return SD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ step pieces
+static StepBufs at_step(const StepBufs& s, size_t t, size_t rows, const sd_handle& h) {
+  if (s.stride == 0) return s;
+  StepBufs r = s;
+  const sd_config& c = h.c;
+  const size_t o = t * rows;
+  r.zin += o * h.SK; r.din += o * c.D; r.ain += o * c.A; r.vin += o * 3 * c.U; r.x += o * 3 * c.U;
+  r.hpre += o * c.D; r.h += o * c.D; r.q += o * 3 * c.D; r.lg += o * h.SK; r.ucopy += o * h.SK;
+  for (int i = 0; i < 4; ++i) {
+    if (r.vobs[i]) r.vobs[i] += o * c.U;
+    if (r.o[i]) r.o[i] += o * c.U;
+    if (r.va[i]) r.va[i] += o * c.units;
+    if (r.ao[i]) r.ao[i] += o * c.units;
+  }
+  if (r.aout) r.aout += o * up(h.act_out, 4);
+  return r;
+}
+
+// Deter.forward (rssm.py:36-75).  z/d: stoch (R,SK) and deter (R,D) operands; abar: magnitude-normalised
+// action (R,A) fp32.  Writes the new deter (fp32, + bf16 copy on the tcgen05 path).
+static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d, const float* abar, float* deter_out,
+                       int ld_out, bf16* out_bf, int ld_bf) {
+  sd_handle& h = *cx.h;
+  const sd_config& c = h.c;
+  const int U = c.U, D = c.D, Dg = h.Dg;
+  LinCall in[3] = {
+      {&h.in0, d, D, Operand(), sb.vin, 3 * U, 0},
+      {&h.in1, z, h.SK, Operand(), sb.vin + U, 3 * U, 0},
+      {&h.in2, opf(abar, c.A), c.A, Operand(), sb.vin + 2 * U, 3 * U, 0},
+  };
+  linear_multi(cx, R, in, 3);
+  sd::NormActP na[3];
+  const float* gains[3] = {h.in0.gain, h.in1.gain, h.in2.gain};
+  for (int j = 0; j < 3; ++j)
+    na[j] = nap(sb.vin + j * U, 3 * U, gains[j], U, sb.x + j * U, 3 * U, cx.tc ? h.x_bf + j * U : nullptr, 3 * U);
+  normact(cx, R, na, 3);
+  Operand dg = d; dg.gstride = Dg;
+  linear(cx, R, h.hid, dg, Dg, opfb(sb.x, 3 * U, cx.tc ? h.x_bf : nullptr, 3 * U), sb.hpre, D, Dg);
+  sd::NormActP nh = nap(sb.hpre, D, h.hid.gain, D, sb.h, D, cx.tc ? h.h_bf : nullptr, D);
+  normact(cx, R, &nh, 1);
+  linear(cx, R, h.gru, opfb(sb.h, D, cx.tc ? h.h_bf : nullptr, D, Dg), Dg, Operand(), sb.q, 3 * D, 3 * Dg);
+  if (cx.err) return;
+  sd::gates_kernel<<<grid1d((long long)R * D, 256), 256, 0, cx.st>>>(sb.q, d.f, d.ldf, deter_out, ld_out, out_bf, ld_bf,
+                                                                  R, D, Dg);
+  cx.check("gates_kernel");
+}
+
+// [Linear -> RMSNorm -> SiLU] x layers -> Linear(SK) (rssm.py:106-130).  Returns raw logits in `lg`.
+static void latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* layers, int nl, const LinearW& last,
+                          Operand a1, int K1, Operand a2, float* lg) {
+  sd_handle& h = *cx.h;
+  const int U = h.c.U;
+  Operand cur1 = a1, cur2 = a2;
+  int k1 = K1;
+  for (int i = 0; i < nl; ++i) {
+    linear(cx, R, layers[i], cur1, k1, cur2, sb.vobs[i], U);
+    sd::NormActP p = nap(sb.vobs[i], U, layers[i].gain, U, sb.o[i], U, cx.tc ? h.o_bf[i] : nullptr, U);
+    normact(cx, R, &p, 1);
+    cur1 = opfb(sb.o[i], U, cx.tc ? h.o_bf[i] : nullptr, U);
+    cur2 = Operand();
+    k1 = U;
+  }
+  linear(cx, R, last, cur1, k1, cur2, lg, h.SK);
+}
+
+static void sample(Ctx& cx, int R, const float* lg, const float* u, int ld_u, float* stoch, int ld_o, bf16* stoch_bf,
+                   int ld_bf, float* logit_copy, int ld_c) {
+  if (cx.err) return;
+  sd_handle& h = *cx.h;
+  const int n = R * h.c.S;
+  sd::sample_kernel<<<(n + 127) / 128, 128, 0, cx.st>>>(lg, h.SK, u, ld_u, R, h.c.S, h.c.K, h.c.unimix, stoch, ld_o,
+                                                        stoch_bf, ld_bf, logit_copy, ld_c, nullptr);
+  cx.check("sample_kernel");
+}
+
+static void cast_bf(Ctx& cx, const float* in, int ld_in, bf16* out, int ld_out, int R, int W) {
+  if (cx.err) return;
+  sd::cast_bf16_kernel<<<grid1d((long long)R * W, 256), 256, 0, cx.st>>>(in, ld_in, out, ld_out, R, W);
+  cx.check("cast_bf16_kernel");
+}
+static void copy_f32(Ctx& cx, const float* in, int ld_in, float* out, int ld_out, int R, int W) {
+  if (cx.err) return;
+  sd::copy_f32_kernel<<<grid1d((long long)R * W, 256), 256, 0, cx.st>>>(in, ld_in, out, ld_out, R, W);
+  cx.check("copy_f32_kernel");
+}
+
+static int check_rows(sd_handle* h, const char* fn, long long rows, long long steps) {
+  if (!h) return fail(SD_ERR_INVALID, "%s: null handle", fn);
+  if (rows < 1 || steps < 1) return fail(SD_ERR_INVALID, "%s: rows/steps must be >= 1", fn);
+  if (rows > h->c.max_rows || steps > h->c.max_steps)
+    return fail(SD_ERR_WORKSPACE, "%s: rows=%lld steps=%lld exceed handle limits (%d, %d)", fn, rows, steps,
+                h->c.max_rows, h->c.max_steps);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ observe
+extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, const float* action,
+                              const float* init_stoch, const float* init_deter, const uint8_t* is_first,
+                              const float* u, float* stochs, float* deters, float* logits, uint32_t flags,
+                              void* stream) {
+  if (int e = check_rows(h, "sd_observe_fwd", B, T)) return e;
+  if (!embed || !action || !init_stoch || !init_deter || !is_first || !u || !stochs || !deters || !logits)
+    return fail(SD_ERR_INVALID, "sd_observe_fwd: null tensor");
+  if (!h->rssm_set) return fail(SD_ERR_WEIGHTS, "sd_observe_fwd: RSSM weights not set");
+  const bool tape = flags & SD_FLAG_SAVE_TAPE;
+  if (tape && (B > h->c.max_tape_rows)) return fail(SD_ERR_WORKSPACE, "sd_observe_fwd: B=%d > max_tape_rows=%d", B, h->c.max_tape_rows);
+  const sd_config& c = h->c;
+  const int SK = h->SK, D = c.D, E = c.E, A = c.A;
+  const bool tc = (flags & SD_FLAG_BF16) && B >= 128;
+  Key key;
+  key.add(1).add(B).add(T).add(embed).add(action).add(init_stoch).add(init_deter).add(is_first).add(u).add(stochs)
+      .add(deters).add(logits).add(flags);
+  if (tape) { h->tape_valid = false; }
+  int rc = run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
+    StepBufs base = tape ? h->tape : h->sb;
+    base.stride = tape ? 1 : 0;
+    if (cx.tc) cast_bf(cx, embed, E, h->emb_bf, E, B * T, E);
+    for (int t = 0; t < T && !cx.err; ++t) {
+      StepBufs sb = at_step(base, t, B, *h);
+      const float* ps = t == 0 ? init_stoch : stochs + (size_t)(t - 1) * SK;
+      const float* pd = t == 0 ? init_deter : deters + (size_t)(t - 1) * D;
+      const int lds = t == 0 ? SK : T * SK, ldd = t == 0 ? D : T * D;
+      sd::prep_obs_kernel<<<grid1d((long long)B * (SK + D + A), 256), 256, 0, cx.st>>>(
+          ps, lds, pd, ldd, action + (size_t)t * A, T * A, is_first + t, T, B, SK, D, A, sb.zin, sb.din, sb.ain);
+      cx.check("prep_obs_kernel");
+      if (cx.tc) {
+        cast_bf(cx, sb.zin, SK, h->feat_bf, h->F, B, SK);
+        cast_bf(cx, sb.din, D, h->feat_bf + SK, h->F, B, D);
+      }
+      float* dout = deters + (size_t)t * D;
+      deter_core(cx, sb, B, opfb(sb.zin, SK, cx.tc ? h->feat_bf : nullptr, h->F),
+                 opfb(sb.din, D, cx.tc ? h->feat_bf + SK : nullptr, h->F), sb.ain, dout, T * D,
+                 cx.tc ? h->h_bf : nullptr, D);
+      // posterior logits on [deter' | embed_t] (rssm.py:171-173); h_bf is free again after the gru GEMM,
+      // so it carries the bf16 copy of deter' on the tcgen05 path.
+      latent_logits(cx, sb, B, h->obs, c.obs_layers, h->obs_logit, opfb(dout, T * D, cx.tc ? h->h_bf : nullptr, D), D,
+                    opfb(embed + (size_t)t * E, T * E, cx.tc ? h->emb_bf + (size_t)t * E : nullptr, T * E), sb.lg);
+      sample(cx, B, sb.lg, u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, nullptr, 0,
+             logits + (size_t)t * SK, T * SK);
+      if (tape) copy_f32(cx, u + (size_t)t * SK, T * SK, sb.ucopy, SK, B, SK);
+    }
+  });
+  if (rc == 0 && tape) { h->tape_valid = true; h->tape_B = B; h->tape_T = T; }
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ prior / img
+extern "C" int sd_prior(sd_handle* h, int R, const float* deter, const float* u, float* stoch, float* logit,
+                        uint32_t flags, void* stream) {
+  if (!h) return fail(SD_ERR_INVALID, "sd_prior: null handle");
+  if (R < 1 || (long long)R > (long long)h->c.max_rows * h->c.max_steps)
+    return fail(SD_ERR_WORKSPACE, "sd_prior: R=%d exceeds max_rows*max_steps", R);
+  if (!deter || !u || !stoch || !logit) return fail(SD_ERR_INVALID, "sd_prior: null tensor");
+  if (!h->rssm_set) return fail(SD_ERR_WEIGHTS, "sd_prior: RSSM weights not set");
+  const sd_config& c = h->c;
+  // batched over (B,T) rows (dreamer.py:485): chunk by max_rows so the step buffers suffice
+  Key key;
+  key.add(2).add(R).add(deter).add(u).add(stoch).add(logit).add(flags);
+  const bool tc_req = (flags & SD_FLAG_BF16) != 0;
+  return run(h, key.v, flags, (cudaStream_t)stream, tc_req, [&](Ctx& cx) {
+    for (int r0 = 0; r0 < R && !cx.err; r0 += c.max_rows) {
+      const int n = (R - r0) < c.max_rows ? (R - r0) : c.max_rows;
+      cx.tc = tc_req && n >= 128;
+      const float* d = deter + (size_t)r0 * c.D;
+      if (cx.tc) cast_bf(cx, d, c.D, h->h_bf, c.D, n, c.D);
+      latent_logits(cx, h->sb, n, h->img, c.img_layers, h->img_logit, opfb(d, c.D, cx.tc ? h->h_bf : nullptr, c.D), c.D,
+                    Operand(), h->sb.lg);
+      sample(cx, n, h->sb.lg, u + (size_t)r0 * h->SK, h->SK, stoch + (size_t)r0 * h->SK, h->SK, nullptr, 0,
+             logit + (size_t)r0 * h->SK, h->SK);
+    }
+  });
+}
+
+extern "C" int sd_imagine_with_action(sd_handle* h, int R, int T, const float* stoch, const float* deter,
+                                      const float* actions, const float* u, float* stochs, float* deters,
+                                      uint32_t flags, void* stream) {
+  if (int e = check_rows(h, "sd_imagine_with_action", R, T)) return e;
+  if (!stoch || !deter || !actions || !u || !stochs || !deters) return fail(SD_ERR_INVALID, "sd_imagine_with_action: null tensor");
+  if (!h->rssm_set) return fail(SD_ERR_WEIGHTS, "sd_imagine_with_action: RSSM weights not set");
+  const sd_config& c = h->c;
+  const int SK = h->SK, D = c.D, A = c.A;
+  const bool tc = (flags & SD_FLAG_BF16) && R >= 128;
+  Key key;
+  key.add(3).add(R).add(T).add(stoch).add(deter).add(actions).add(u).add(stochs).add(deters).add(flags);
+  return run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
+    const StepBufs& sb = h->sb;
+    for (int t = 0; t < T && !cx.err; ++t) {
+      const float* ps = t == 0 ? stoch : stochs + (size_t)(t - 1) * SK;
+      const float* pd = t == 0 ? deter : deters + (size_t)(t - 1) * D;
+      const int lds = t == 0 ? SK : T * SK, ldd = t == 0 ? D : T * D;
+      sd::prep_obs_kernel<<<grid1d((long long)R * (SK + D + A), 256), 256, 0, cx.st>>>(
+          ps, lds, pd, ldd, actions + (size_t)t * A, T * A, nullptr, 0, R, SK, D, A, sb.zin, sb.din, sb.ain);
+      cx.check("prep_obs_kernel");
+      if (cx.tc) {
+        cast_bf(cx, sb.zin, SK, h->feat_bf, h->F, R, SK);
+        cast_bf(cx, sb.din, D, h->feat_bf + SK, h->F, R, D);
+      }
+      float* dout = deters + (size_t)t * D;
+      deter_core(cx, sb, R, opfb(sb.zin, SK, cx.tc ? h->feat_bf : nullptr, h->F),
+                 opfb(sb.din, D, cx.tc ? h->feat_bf + SK : nullptr, h->F), sb.ain, dout, T * D,
+                 cx.tc ? h->h_bf : nullptr, D);
+      latent_logits(cx, sb, R, h->img, c.img_layers, h->img_logit, opfb(dout, T * D, cx.tc ? h->h_bf : nullptr, D), D,
+                    Operand(), sb.lg);
+      sample(cx, R, sb.lg, u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, nullptr, 0, nullptr, 0);
+    }
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ imagine
+// MLPHead trunk + last layer on `R` rows of feat (networks.py:339-377); returns last-layer output in `out`.
+static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, float* const* v, float* const* o,
+                         bf16* const* o_bf, float* out, int ld_out) {
+  sd_handle& h = *cx.h;
+  const int units = h.c.units;
+  Operand cur = feat;
+  int k = F;
+  for (int i = 0; i < hw.layers; ++i) {
+    linear(cx, R, hw.l[i], cur, k, Operand(), v[i], units);
+    sd::NormActP p = nap(v[i], units, hw.l[i].gain, units, o[i], units, cx.tc ? o_bf[i] : nullptr, units);
+    normact(cx, R, &p, 1);
+    cur = opfb(o[i], units, cx.tc ? o_bf[i] : nullptr, units);
+    k = units;
+  }
+  linear(cx, R, hw.last, cur, k, Operand(), out, ld_out);
+}
+
+extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, const float* deter0, const float* u,
+                              const float* act_noise, float* feats, float* actions, uint32_t flags, void* stream) {
+  if (int e = check_rows(h, "sd_imagine_fwd", N, H)) return e;
+  if (!stoch0 || !deter0 || !u || !act_noise || !feats || !actions) return fail(SD_ERR_INVALID, "sd_imagine_fwd: null tensor");
+  if (!h->rssm_set || !h->heads[SD_MOD_ACTOR].set) return fail(SD_ERR_WEIGHTS, "sd_imagine_fwd: RSSM/actor weights not set");
+  if (flags & SD_FLAG_SAVE_TAPE) return fail(SD_ERR_INVALID, "sd_imagine_fwd: tape (backward) not available yet");
+  const sd_config& c = h->c;
+  const int SK = h->SK, D = c.D, A = c.A, F = h->F;
+  const bool tc = (flags & SD_FLAG_BF16) && N >= 128;
+  Key key;
+  key.add(4).add(N).add(H).add(stoch0).add(deter0).add(u).add(act_noise).add(feats).add(actions).add(flags);
+  return run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
+    const StepBufs& sb = h->sb;
+    const HeadW& actor = h->heads[SD_MOD_ACTOR];
+    const int ldf = H * F;
+    // feats[:, 0] = [stoch0 | deter0] (rssm.py:211-217)
+    copy_f32(cx, stoch0, SK, feats, ldf, N, SK);
+    copy_f32(cx, deter0, D, feats + SK, ldf, N, D);
+    if (cx.tc) cast_bf(cx, feats, ldf, h->feat_bf, F, N, F);
+    for (int t = 0; t < H && !cx.err; ++t) {
+      float* ft = feats + (size_t)t * F;
+      Operand feat = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
+      // action = actor(feat).rsample() (dreamer.py:684)
+      head_forward(cx, N, actor, feat, F, sb.va, sb.ao, h->a_bf, sb.aout, h->act_out);
+      if (cx.err) return;
+      {
+        const int n = c.act_kind == 0 ? N * A : N;
+        sd::actor_sample_kernel<<<(n + 127) / 128, 128, 0, cx.st>>>(sb.aout, N, A, c.act_kind, c.min_std, c.max_std,
+                                                                    c.act_unimix, act_noise + (size_t)t * A, H * A,
+                                                                    actions + (size_t)t * A, H * A, h->abar);
+        cx.check("actor_sample_kernel");
+      }
+      // stoch, deter = img_step(stoch, deter, action) (dreamer.py:688).  The H-th img_step result is
+      // dropped by the reference and nothing downstream consumes it, so it is not computed.
+      if (t == H - 1) break;
+      float* dnext = ft + F + SK;
+      const int ldn = ldf;
+      Operand z = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
+      Operand d = opfb(ft + SK, ldf, cx.tc ? h->feat_bf + SK : nullptr, F);
+      deter_core(cx, sb, N, z, d, h->abar, dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F);
+      latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit, opfb(dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F), D,
+                    Operand(), sb.lg);
+      sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, cx.tc ? h->feat_bf : nullptr, F, nullptr, 0);
+    }
+  });
+}
+
+extern "C" int sd_imagine_bwd(sd_handle*, int, int, const float*, const float*, float*, float*, uint32_t, void*) {
+  return fail(SD_ERR_INVALID, "sd_imagine_bwd: not implemented in this build");
+}
+extern "C" int sd_observe_bwd(sd_handle*, int, int, const float*, const float*, const float*, float*, float*, float*,
+                              float* const*, uint32_t, void*) {
+  return fail(SD_ERR_INVALID, "sd_observe_bwd: not implemented in this build");
+}
+
+// ------------------------------------------------------------------------------------------------ heads + returns
+extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feats, float disc, float lamb,
+                                   float* reward, float* cont, float* value, float* slow_value, float* weight,
+                                   float* ret, uint32_t flags, void* stream) {
+  if (int e = check_rows(h, "sd_heads_lambda_fwd", N, H)) return e;
+  if (!feats) return fail(SD_ERR_INVALID, "sd_heads_lambda_fwd: null feats");
+  for (int m : {SD_MOD_REWARD, SD_MOD_CONT, SD_MOD_VALUE})
+    if (!h->heads[m].set) return fail(SD_ERR_WEIGHTS, "sd_heads_lambda_fwd: head %d weights not set", m);
+  if (slow_value && !h->heads[SD_MOD_SLOW_VALUE].set) return fail(SD_ERR_WEIGHTS, "sd_heads_lambda_fwd: slow value weights not set");
+  const sd_config& c = h->c;
+  const int F = h->F;
+  const long long NH = (long long)N * H;
+  const bool tc = (flags & SD_FLAG_BF16) && NH >= 128;
+  Key key;
+  key.add(5).add(N).add(H).add(feats).add(disc).add(lamb).add(reward).add(cont).add(value).add(slow_value).add(weight)
+      .add(ret).add(flags);
+  return run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
+    const int R = (int)NH;
+    if (cx.tc) cast_bf(cx, feats, F, h->big_bf, F, R, F);
+    Operand feat = opfb(feats, F, cx.tc ? h->big_bf : nullptr, F);
+    // the MLP trunks reuse two (N*H, units) buffers; bf16 copies alias the per-step actor staging only
+    // when rows fit, so the heads keep their own: hv (pre-norm), ho (post-act) and big bf16 views.
+    float* v[4] = {h->hv, h->hv, h->hv, h->hv};
+    float* o[4] = {h->ho, h->ho, h->ho, h->ho};
+    bf16* ob[4];
+    for (int i = 0; i < 4; ++i) ob[i] = h->trunk_bf;
+    const bool tc_saved = cx.tc;
+    auto run_head = [&](int m, float* rew_like, bool twohot) {
+      const HeadW& hw = h->heads[m];
+      head_forward(cx, R, hw, feat, F, v, o, ob, h->hl, up(hw.out, 4));
+      if (cx.err) return;
+      if (twohot) {
+        sd::twohot_mode_kernel<<<(R * 32 + 255) / 256, 256, 0, cx.st>>>(h->hl, up(hw.out, 4), h->bins, c.bins, R, rew_like);
+        cx.check("twohot_mode_kernel");
+      } else {
+        sd::sigmoid_kernel<<<(R + 255) / 256, 256, 0, cx.st>>>(h->hl, rew_like, R);
+        cx.check("sigmoid_kernel");
+      }
+    };
+    float* rw = reward ? reward : h->h_rew;
+    float* ct = cont ? cont : h->h_cont;
+    float* vl = value ? value : h->h_val;
+    run_head(SD_MOD_REWARD, rw, true);
+    run_head(SD_MOD_CONT, ct, false);
+    run_head(SD_MOD_VALUE, vl, true);
+    if (slow_value) run_head(SD_MOD_SLOW_VALUE, slow_value, true);
+    cx.tc = tc_saved;
+    if (cx.err) return;
+    if (weight || ret) {
+      sd::imag_weight_ret_kernel<<<(N + 127) / 128, 128, 0, cx.st>>>(N, H, rw, ct, vl, disc, lamb, weight, ret);
+      cx.check("imag_weight_ret_kernel");
+    }
+  });
+}
+
+extern "C" int sd_lambda_return(int N, int T, const float* last, const float* term, const float* reward,
+                                const float* value, const float* boot, float disc, float lamb, float* out,
+                                void* stream) {
+  if (N < 1 || T < 2) return fail(SD_ERR_INVALID, "sd_lambda_return: need N >= 1, T >= 2");
+  if (!term || !reward || !value || !boot || !out) return fail(SD_ERR_INVALID, "sd_lambda_return: null tensor");
+  (void)value;  // the reference signature carries `value` but only `boot` enters the recursion (dreamer.py:701-706)
+  sd::lambda_return_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, T, last, term, reward, value, boot, disc,
+                                                                            lamb, out);
+  ++g_launches;
+  CUDA_TRY(cudaPeekAtLastError());
+  return SD_OK;
+}
+
+extern "C" int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
+                          float* dyn_loss, float* rep_loss, float* post_entropy, float* prior_entropy, void* stream) {
+  if (!h) return fail(SD_ERR_INVALID, "sd_kl_loss: null handle");
+  if (R < 1 || (long long)R > (long long)h->c.max_rows * h->c.max_steps)
+    return fail(SD_ERR_WORKSPACE, "sd_kl_loss: R=%d exceeds max_rows*max_steps", R);
+  if (!post_logit || !prior_logit) return fail(SD_ERR_INVALID, "sd_kl_loss: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = R * h->c.S;
+  sd::kl_entropy_kernel<<<(n + 127) / 128, 128, 0, st>>>(post_logit, prior_logit, R, h->c.S, h->c.K, h->c.unimix, h->kl_a,
+                                                        post_entropy ? h->kl_b : nullptr, prior_entropy ? h->kl_c : nullptr);
+  sd::kl_finish_kernel<<<(R + 127) / 128, 128, 0, st>>>(h->kl_a, h->kl_b, h->kl_c, R, h->c.S, free_nats, dyn_loss, rep_loss,
+                                                       post_entropy, prior_entropy);
+  g_launches += 2;
+  CUDA_TRY(cudaPeekAtLastError());
+  return SD_OK;
+}

@@ -1,0 +1,576 @@
+// sd_kernels.cuh -- fp32 SIMT kernels and the fused row-wise kernels of the RSSM hot path.
+//
+// Everything here computes in fp32 with IEEE division / sqrt and the accurate expf/logf/tanhf
+// (the library is built WITHOUT --use_fast_math): this is the parity path that reproduces the
+// reference's sampled category indices bit for bit except at fp32 near-ties.  The bf16 tensor-core
+// GEMM that replaces gemm_f32_kernel for large row counts lives in sd_tc.cuh; all row-wise kernels
+// below are shared by both paths (they optionally emit a bf16 copy for the next tcgen05 operand).
+//
+// Reference math: world_model/rssm.py:36-75 (Deter), :158-195 (obs_step / img_step / prior),
+// world_model/distributions.py:16-36 (OneHotDist), :78-98 (TwoHot.mode), :217-222 (bounded_normal),
+// world_model/dreamer.py:694-707 (_lambda_return).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sd {
+
+constexpr float kRmsEps = 1e-4f;
+
+// ------------------------------------------------------------------------------------------------
+// Batched skinny GEMM:  C[R x N] = [A | A2][R x K] * Wt[K x N] + bias, fp32.
+// A CTA owns a 16-row x 16-column output tile and splits K over its 64 thread groups (intra-CTA
+// split-K, reduced through shared memory in a fixed order => deterministic).  Built for the
+// latency-bound regime of the posterior scan (R = 16): the grid spreads N over many SMs and every
+// thread does <= ~2k FMAs.  Rows are tiled by 16, so it is also the fp32 parity path for large R.
+// ------------------------------------------------------------------------------------------------
+struct GemmP {
+  const float* A;    // [R x K1], row stride lda
+  const float* A2;   // [R x (K-K1)], row stride lda2 (second K segment; may be null when K1 == K)
+  const float* Wt;   // [K x ldw] (n contiguous, ldw % 16 == 0, zero padded)
+  const float* bias; // [N] or null
+  float* C;          // [R x N], row stride ldc
+  int lda, lda2, K1, K, ldw, ldc, N;
+};
+constexpr int kMaxBatch = 8;
+struct GemmBatch {
+  int count;
+  int R;
+  GemmP p[kMaxBatch];
+};
+
+constexpr int GB_KC = 512;           // K chunk staged in shared memory
+constexpr int GB_XLD = GB_KC + 4;    // padded row stride of the staged activations
+constexpr int GB_RLD = 16 * 16 + 4;  // padded stride of the split-K reduction buffer
+constexpr int GB_SMEM = (64 * GB_RLD > 16 * GB_XLD ? 64 * GB_RLD : 16 * GB_XLD) * 4;
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
+  const GemmP& p = b.p[blockIdx.z];
+  const int n0 = blockIdx.x * 16;
+  if (n0 >= p.N) return;
+  const int r0 = blockIdx.y * 16;
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  const int tid = threadIdx.x, tx = tid & 3, ty = tid >> 2;
+  float acc[16][4];
+#pragma unroll
+  for (int r = 0; r < 16; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  for (int kc = 0; kc < p.K; kc += GB_KC) {
+    const int kw = min(GB_KC, (p.K - kc + 3) & ~3);
+    for (int i = tid; i < 16 * kw; i += 256) {
+      const int r = i / kw, k = i - r * kw;
+      const int kk = kc + k, row = r0 + r;
+      float v = 0.f;
+      if (row < b.R && kk < p.K)
+        v = (kk < p.K1) ? p.A[(size_t)row * p.lda + kk] : p.A2[(size_t)row * p.lda2 + (kk - p.K1)];
+      xs[r * GB_XLD + k] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < GB_KC / 4 / 64; ++i) {
+      const int kq = ty + 64 * i;
+      const int kbase = kc + kq * 4;
+      if (kq * 4 < kw) {
+        float4 w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kbase + j;
+          w[j] = (k < p.K) ? *reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + n0 + tx * 4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(xs + r * GB_XLD + kq * 4);
+          acc[r][0] = fmaf(x.x, w[0].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[0].y, acc[r][1]);
+          acc[r][2] = fmaf(x.x, w[0].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[0].w, acc[r][3]);
+          acc[r][0] = fmaf(x.y, w[1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[1].y, acc[r][1]);
+          acc[r][2] = fmaf(x.y, w[1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[1].w, acc[r][3]);
+          acc[r][0] = fmaf(x.z, w[2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[2].y, acc[r][1]);
+          acc[r][2] = fmaf(x.z, w[2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[2].w, acc[r][3]);
+          acc[r][0] = fmaf(x.w, w[3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[3].y, acc[r][1]);
+          acc[r][2] = fmaf(x.w, w[3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[3].w, acc[r][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* red = smem;
+#pragma unroll
+  for (int r = 0; r < 16; ++r)
+    *reinterpret_cast<float4*>(red + ty * GB_RLD + r * 16 + tx * 4) =
+        make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll 8
+  for (int t = 0; t < 64; ++t) s += red[t * GB_RLD + tid];
+  const int row = r0 + (tid >> 4), n = n0 + (tid & 15);
+  if (row < b.R && n < p.N) p.C[(size_t)row * p.ldc + n] = s + (p.bias ? p.bias[n] : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight-gradient GEMM (contraction over rows):  dW[n][k] (+)= sum_r dY[r][n] * X[r][k].
+// Classic 64x64 tile, 4x4 per thread; output addressed with arbitrary strides so it can write the
+// reference layouts directly (nn.Linear (N,K); BlockLinear (O/G, I/G, G) via sn = I*G/G.., sk = G).
+// X may be a 2-segment concat like the forward operand.
+// ------------------------------------------------------------------------------------------------
+struct WgradP {
+  const float* dY; int ldy;   // [R x N]
+  const float* X;  int ldx;   // [R x K1]
+  const float* X2; int ldx2;  // [R x (K-K1)]
+  int K1, K, N;
+  float* dW; long long sn, sk; // dW[n*sn + k*sk]
+};
+struct WgradBatch {
+  int count;
+  int R;
+  WgradP p[kMaxBatch];
+};
+
+__global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
+  const WgradP& p = b.p[blockIdx.z];
+  const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  if (n0 >= p.N || k0 >= p.K) return;
+  __shared__ float ys[16][64 + 4];
+  __shared__ float xs[16][64 + 4];
+  const int tid = threadIdx.x, tn = tid & 15, tk = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int rc = 0; rc < b.R; rc += 16) {
+    for (int i = tid; i < 16 * 64; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      const int row = rc + r;
+      float yv = 0.f, xv = 0.f;
+      if (row < b.R) {
+        if (n0 + c < p.N) yv = p.dY[(size_t)row * p.ldy + n0 + c];
+        const int k = k0 + c;
+        if (k < p.K) xv = (k < p.K1) ? p.X[(size_t)row * p.ldx + k] : p.X2[(size_t)row * p.ldx2 + (k - p.K1)];
+      }
+      ys[r][c] = yv;
+      xs[r][c] = xv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float4 y = *reinterpret_cast<const float4*>(&ys[r][tn * 4]);
+      const float4 x = *reinterpret_cast<const float4*>(&xs[r][tk * 4]);
+      const float yy[4] = {y.x, y.y, y.z, y.w}, xx[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yy[i], xx[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn * 4 + i, k = k0 + tk * 4 + j;
+      if (n < p.N && k < p.K) p.dW[n * p.sn + k * p.sk] += acc[i][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight repacking: reference layout -> Wt[g][k][ldw] fp32 (forward operand, n contiguous),
+// Wn[g][n][ldk] fp32 (dgrad operand, k contiguous) and bf16 copies of both for the tcgen05 path.
+// Source element (g,n,k) sits at src[g*s_g + n*s_n + k*s_k]:
+//   nn.Linear (N,K): s_g=0, s_n=K, s_k=1;   BlockLinear (O/G, I/G, G): s_g=1, s_n=(I/G)*G, s_k=G.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ src, int G, int N, int K, long long s_g,
+                                   long long s_n, long long s_k, float* wt, int ldw, float* wn, int ldk,
+                                   __nv_bfloat16* wn_bf, __nv_bfloat16* wt_bf) {
+  const long long total = (long long)G * N * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int n = (int)((i / K) % N);
+    const int g = (int)(i / ((long long)K * N));
+    const float v = src[g * s_g + n * s_n + k * s_k];
+    if (wt) wt[((size_t)g * K + k) * ldw + n] = v;
+    if (wn) wn[((size_t)g * N + n) * ldk + k] = v;
+    if (wn_bf) wn_bf[((size_t)g * N + n) * ldk + k] = __float2bfloat16(v);
+    if (wt_bf) wt_bf[((size_t)g * K + k) * ldw + n] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-wise helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Deterministic block-wide sum (every thread gets the result); blockDim.x <= 1024.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < nw; ++i) s += sh[i];
+  return s;
+}
+
+// y = SiLU(RMSNorm_width(v) * w): one CTA per (row, segment).  rssm.py:16-31,106-130; networks.py:325-327.
+struct NormActP {
+  const float* in; int ld_in;   // segment base (row 0), row stride
+  const float* w;               // [width]
+  float* out; int ld_out;       // nullable
+  __nv_bfloat16* out_bf; int ld_bf; // nullable
+  int width;
+};
+struct NormActBatch {
+  int count;
+  NormActP p[4];
+};
+__global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
+  __shared__ float sh[32];
+  const NormActP& p = b.p[blockIdx.y];
+  const size_t row = blockIdx.x;
+  const float* in = p.in + row * p.ld_in;
+  float v[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    v[i] = (c < p.width) ? in[c] : 0.f;
+    ss = fmaf(v[i], v[i], ss);
+  }
+  ss = block_sum(ss, sh);
+  const float rs = 1.f / sqrtf(ss / (float)p.width + kRmsEps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < p.width) {
+      const float y = siluf_((v[i] * rs) * p.w[c]);
+      if (p.out) p.out[row * p.ld_out + c] = y;
+      if (p.out_bf) p.out_bf[row * p.ld_bf + c] = __float2bfloat16(y);
+    }
+  }
+}
+
+// GRU-style gates (rssm.py:63-75): q (R, 3D) laid out [g][reset|cand|update][D/G].
+__global__ void gates_kernel(const float* __restrict__ q, const float* __restrict__ deter_in, int ld_in,
+                             float* __restrict__ deter_out, int ld_out, __nv_bfloat16* out_bf, int ld_bf,
+                             int R, int D, int Dg) {
+  const long long total = (long long)R * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const size_t row = (size_t)(i / D);
+    const int g = d / Dg, o = d - g * Dg;
+    const float* qr = q + row * 3 * D + (size_t)g * 3 * Dg + o;
+    const float reset = sigmoidf_(qr[0]);
+    const float cand = tanhf(reset * qr[Dg]);
+    const float upd = sigmoidf_(qr[2 * Dg] - 1.f);
+    const float out = upd * cand + (1.f - upd) * deter_in[row * ld_in + d];
+    deter_out[row * ld_out + d] = out;
+    if (out_bf) out_bf[row * ld_bf + d] = __float2bfloat16(out);
+  }
+}
+
+// OneHotDist(logit, unimix).rsample() with injected uniforms (distributions.py:16-36 +
+// F.gumbel_softmax(hard=True)); K <= 32 classes held in registers, one thread per category.
+// Returns the first-max index of y = softmax(l + g); y[] is left in yv (for the backward).
+__device__ __forceinline__ int sample_category(const float* lg, const float* u, int K, float unimix, float* yv) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) m = fmaxf(m, lg[k]);
+  float e[32];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) { e[k] = expf(lg[k] - m); s += e[k]; }
+  const float uni = unimix / (float)K;
+  float m2 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) { e[k] = logf((e[k] / s) * (1.f - unimix) + uni); m2 = fmaxf(m2, e[k]); }
+  float s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) s2 += expf(e[k] - m2);
+  const float lse = m2 + logf(s2);
+  float m3 = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) { e[k] = (e[k] - lse) + (-logf(-logf(u[k]))); m3 = fmaxf(m3, e[k]); }
+  float s3 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) { e[k] = expf(e[k] - m3); s3 += e[k]; }
+  int best = 0;
+  float bv = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) {
+      const float y = e[k] / s3;
+      if (yv) yv[k] = y;
+      if (y > bv) { bv = y; best = k; }
+    }
+  return best;
+}
+
+// Sample all S categories of R rows.  logits (R, S*K) row stride ld_l; u (R, S*K) row stride ld_u.
+// Writes exact one-hot fp32 (row stride ld_o), optional bf16 copy, optional copy of the logits
+// (the `logits` output of observe) and the indices.
+__global__ void sample_kernel(const float* __restrict__ logits, int ld_l, const float* __restrict__ u, int ld_u,
+                              int R, int S, int K, float unimix, float* stoch, int ld_o, __nv_bfloat16* stoch_bf,
+                              int ld_bf, float* logit_copy, int ld_c, int* idx_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * S) return;
+  const size_t row = i / S;
+  const int s = i - (int)row * S;
+  float lg[32], uu[32];
+  const float* lp = logits + row * ld_l + s * K;
+  const float* up = u + row * ld_u + s * K;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) { lg[k] = lp[k]; uu[k] = up[k]; }
+  const int best = sample_category(lg, uu, K, unimix, nullptr);
+  if (idx_out) idx_out[i] = best;
+#pragma unroll
+  for (int k = 0; k < 32; ++k)
+    if (k < K) {
+      const float v = (k == best) ? 1.f : 0.f;
+      if (stoch) stoch[row * ld_o + s * K + k] = v;
+      if (stoch_bf) stoch_bf[row * ld_bf + s * K + k] = __float2bfloat16(v);
+      if (logit_copy) logit_copy[row * ld_c + s * K + k] = lg[k];
+    }
+}
+
+// obs_step prologue (rssm.py:161-165 + :44): zero stoch/deter/action where is_first, normalise the
+// action magnitude, and stage the three step inputs contiguously (they are also the backward tape).
+__global__ void prep_obs_kernel(const float* __restrict__ stoch, int ld_s, const float* __restrict__ deter, int ld_d,
+                                const float* __restrict__ action, int ld_a, const uint8_t* __restrict__ is_first,
+                                int ld_f, int R, int SK, int D, int A, float* zin, float* din, float* ain) {
+  const int W = SK + D + A;
+  const long long total = (long long)R * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const size_t row = (size_t)(i / W);
+    const int c = (int)(i - (long long)row * W);
+    const bool rs = is_first ? (is_first[row * ld_f] != 0) : false;
+    if (c < SK) {
+      zin[row * SK + c] = rs ? 0.f : stoch[row * ld_s + c];
+    } else if (c < SK + D) {
+      const int d = c - SK;
+      din[row * D + d] = rs ? 0.f : deter[row * ld_d + d];
+    } else {
+      const int a = c - SK - D;
+      const float v = rs ? 0.f : action[row * ld_a + a];
+      ain[row * A + a] = v / fmaxf(fabsf(v), 1.f);
+    }
+  }
+}
+
+// fp32 -> bf16 copy of a strided (R x W) matrix.
+__global__ void cast_bf16_kernel(const float* __restrict__ in, int ld_in, __nv_bfloat16* out, int ld_out, int R,
+                                 int W) {
+  const long long total = (long long)R * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const size_t row = (size_t)(i / W);
+    const int c = (int)(i - (long long)row * W);
+    out[row * ld_out + c] = __float2bfloat16(in[row * ld_in + c]);
+  }
+}
+// strided (R x W) fp32 copy.
+__global__ void copy_f32_kernel(const float* __restrict__ in, int ld_in, float* out, int ld_out, int R, int W) {
+  const long long total = (long long)R * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const size_t row = (size_t)(i / W);
+    const int c = (int)(i - (long long)row * W);
+    out[row * ld_out + c] = in[row * ld_in + c];
+  }
+}
+
+// Actor sampling (dreamer.py:684).  Continuous (distributions.py:217-222): out (R, 2A) = [mean | std_raw],
+// action = tanh(mean) + ((max-min)*sigmoid(std_raw+2)+min) * eps.  Discrete (distributions.py:230-231):
+// one OneHotDist over A classes with injected uniforms.  Also emits the magnitude-normalised action
+// (rssm.py:44) that dyn_in2 consumes.
+__global__ void actor_sample_kernel(const float* __restrict__ out, int R, int A, int act_kind, float min_std,
+                                    float max_std, float unimix, const float* __restrict__ noise, int ld_n,
+                                    float* action, int ld_act, float* abar) {
+  if (act_kind == 0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * A) return;
+    const size_t row = i / A;
+    const int a = i - (int)row * A;
+    const float mean = out[row * 2 * A + a], sraw = out[row * 2 * A + A + a];
+    const float std = (max_std - min_std) * sigmoidf_(sraw + 2.f) + min_std;
+    const float v = tanhf(mean) + std * noise[row * ld_n + a];
+    action[row * ld_act + a] = v;
+    abar[row * A + a] = v / fmaxf(fabsf(v), 1.f);
+  } else {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= R) return;
+    float lg[32], uu[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < A) { lg[k] = out[(size_t)row * A + k]; uu[k] = noise[(size_t)row * ld_n + k]; }
+    const int best = sample_category(lg, uu, A, unimix, nullptr);
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      if (k < A) {
+        const float v = (k == best) ? 1.f : 0.f;
+        action[(size_t)row * ld_act + k] = v;
+        abar[(size_t)row * A + k] = v;  // |v| <= 1: normalisation is the identity
+      }
+  }
+}
+
+// TwoHot.mode (distributions.py:78-98): softmax over `bins` logits, then the reference's symmetric
+// pairing sum_j (p[m-1-j]*b[m-1-j] + p[m+1+j]*b[m+1+j]) + p[m]*b[m].  One warp per row.
+__global__ void twohot_mode_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ bins, int n,
+                                   int R, float* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float* lp = logits + (size_t)warp * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < n; j += 32) m = fmaxf(m, lp[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s += expf(lp[j] - m);
+  s = warp_sum(s);
+  float acc = 0.f;
+  if (n & 1) {
+    const int mid = (n - 1) / 2;
+    for (int j = lane; j < mid; j += 32) {
+      const float lo = (expf(lp[mid - 1 - j] - m) / s) * bins[mid - 1 - j];
+      const float hi = (expf(lp[mid + 1 + j] - m) / s) * bins[mid + 1 + j];
+      acc += lo + hi;
+    }
+    acc = warp_sum(acc);
+    acc += (expf(lp[mid] - m) / s) * bins[mid];
+  } else {
+    const int h = n / 2;
+    for (int j = lane; j < h; j += 32) {
+      const float lo = (expf(lp[h - 1 - j] - m) / s) * bins[h - 1 - j];
+      const float hi = (expf(lp[h + j] - m) / s) * bins[h + j];
+      acc += lo + hi;
+    }
+    acc = warp_sum(acc);
+  }
+  if (lane == 0) out[warp] = acc;
+}
+
+// cont head mean = sigmoid(logit) (distributions.py:238-239, Bernoulli.mean).
+__global__ void sigmoid_kernel(const float* __restrict__ in, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sigmoidf_(in[i]);
+}
+
+// weight = cumprod(cont*disc) (dreamer.py:596) and the lambda-return reverse scan
+// (dreamer.py:694-707).  One thread per row; T <= 128.
+__global__ void lambda_return_kernel(int N, int T, const float* __restrict__ last, const float* __restrict__ term,
+                                     const float* __restrict__ reward, const float* __restrict__ value,
+                                     const float* __restrict__ boot, float disc, float lamb, float* out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t o = (size_t)n * T;
+  float nxt = boot[o + T - 1];
+  for (int i = T - 2; i >= 0; --i) {
+    const float live = (1.f - term[o + i + 1]) * disc;
+    const float cont = (1.f - (last ? last[o + i + 1] : 0.f)) * lamb;
+    const float interm = reward[o + i + 1] + (1.f - cont) * live * boot[o + i + 1];
+    nxt = interm + live * cont * nxt;
+    out[(size_t)n * (T - 1) + i] = nxt;
+  }
+}
+__global__ void imag_weight_ret_kernel(int N, int H, const float* __restrict__ reward, const float* __restrict__ cont,
+                                       const float* __restrict__ value, float disc, float lamb, float* weight,
+                                       float* ret) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t o = (size_t)n * H;
+  if (weight) {
+    float w = 1.f;
+    for (int i = 0; i < H; ++i) {
+      w *= cont[o + i] * disc;
+      weight[o + i] = w;
+    }
+  }
+  if (ret) {
+    float nxt = value[o + H - 1];
+    for (int i = H - 2; i >= 0; --i) {
+      const float live = (1.f - (1.f - cont[o + i + 1])) * disc;  // term = 1 - cont, as the reference computes it
+      const float c = lamb;                                      // last = 0
+      const float interm = reward[o + i + 1] + (1.f - c) * live * value[o + i + 1];
+      nxt = interm + live * c * nxt;
+      ret[(size_t)n * (H - 1) + i] = nxt;
+    }
+  }
+}
+
+// RSSM.kl_loss values + unimix entropies (rssm.py:222-230; distributions.py:266-271; dreamer.py:575-576).
+// One thread per (row, category); per-row sums are reduced in a fixed order by the last stage.
+__global__ void kl_entropy_kernel(const float* __restrict__ post, const float* __restrict__ prior, int R, int S, int K,
+                                  float unimix, float* kl_sk, float* ent_post_sk, float* ent_prior_sk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * S) return;
+  const float* a = post + (size_t)i * K;
+  const float* b = prior + (size_t)i * K;
+  float ma = -INFINITY, mb = -INFINITY;
+  for (int k = 0; k < K; ++k) { ma = fmaxf(ma, a[k]); mb = fmaxf(mb, b[k]); }
+  float sa = 0.f, sb = 0.f;
+  for (int k = 0; k < K; ++k) { sa += expf(a[k] - ma); sb += expf(b[k] - mb); }
+  const float lsa = ma + logf(sa), lsb = mb + logf(sb);
+  float kl = 0.f;
+  for (int k = 0; k < K; ++k) kl += (expf(a[k] - ma) / sa) * ((a[k] - lsa) - (b[k] - lsb));
+  kl_sk[i] = kl;
+  const float uni = unimix / (float)K;
+  for (int which = 0; which < 2; ++which) {
+    const float* x = which ? b : a;
+    const float mx = which ? mb : ma, sx = which ? sb : sa;
+    float* dst = which ? ent_prior_sk : ent_post_sk;
+    if (!dst) continue;
+    float l[32];
+    float m2 = -INFINITY;
+    for (int k = 0; k < K; ++k) { l[k] = logf((expf(x[k] - mx) / sx) * (1.f - unimix) + uni); m2 = fmaxf(m2, l[k]); }
+    float s2 = 0.f;
+    for (int k = 0; k < K; ++k) s2 += expf(l[k] - m2);
+    const float lse = m2 + logf(s2);
+    float ent = 0.f;
+    for (int k = 0; k < K; ++k) { const float ll = l[k] - lse; ent -= expf(ll) * ll; }
+    dst[i] = ent;
+  }
+}
+__global__ void kl_finish_kernel(const float* __restrict__ kl_sk, const float* __restrict__ ep_sk,
+                                 const float* __restrict__ eq_sk, int R, int S, float free_nats, float* dyn, float* rep,
+                                 float* ent_post, float* ent_prior) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float k = 0.f, ep = 0.f, eq = 0.f;
+  for (int s = 0; s < S; ++s) {
+    k += kl_sk[(size_t)r * S + s];
+    if (ent_post) ep += ep_sk[(size_t)r * S + s];
+    if (ent_prior) eq += eq_sk[(size_t)r * S + s];
+  }
+  const float v = fmaxf(k, free_nats);
+  if (dyn) dyn[r] = v;
+  if (rep) rep[r] = v;
+  if (ent_post) ent_post[r] = ep;
+  if (ent_prior) ent_prior[r] = eq;
+}
+
+}  // namespace sd

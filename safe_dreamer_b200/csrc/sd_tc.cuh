@@ -1,0 +1,243 @@
+// sd_tc.cuh -- tcgen05 (5th-gen tensor core) batched GEMM for the large-row dense layers.
+//
+//   C[R x N] (fp32) = [A1 | A2][R x K] (bf16) * W[N x K]^T (bf16) + bias        (fp32 accumulate in TMEM)
+//
+// sm_100a only.  One CTA computes one 128 x BN output tile of one problem of the batch:
+//   warp 0    : TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4-stage mbarrier ring)
+//   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128,N=BN,K=16)
+//   warps 2-5 : epilogue (tcgen05.ld 32x32b -> +bias -> fp32 global store), one TMEM lane quadrant each
+// Both operands are K-major (activations row-major [R x K], weights in nn.Linear [N x K] layout), so the
+// shared-memory tiles are the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect
+// (8-row x 128-byte swizzle atoms, SBO = 1024 B); K advances inside an atom by bumping the descriptor
+// start address by 32 B per UMMA_K=16.
+// The A operand may be the concatenation of two buffers along K (block input [deter_g | x] of the
+// block-GRU, feat = [stoch | deter], obs input [deter | embed]) and every problem has its own column
+// offsets, which is how the 8 block-diagonal problems of a BlockLinear share two tensor maps.
+//
+// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sd {
+namespace tc {
+
+constexpr int BM = 128;      // UMMA M (rows of the output tile == TMEM lanes)
+constexpr int BK = 64;       // K elements per stage: 64 bf16 = 128 B = one swizzle atom row
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;
+constexpr int kMaxProblems = 8;
+constexpr int kMaxMaps = 12;
+
+struct Problem {
+  int a1_map, a1_col;  // tensor-map index + starting column of K segment 1
+  int a2_map, a2_col;  // K segment 2 (unused when K1 == K)
+  int w_map, w_row;    // weight map + first weight row (n offset inside the stacked [G*Npad x K] matrix)
+  int K1, K;           // both multiples of 64
+  int N;               // logical output columns (store guard); tiles cover ceil(N/BN)*BN
+  int ldc;
+  float* C;
+  const float* bias;   // nullable
+};
+struct alignas(64) Batch {
+  CUtensorMap maps[kMaxMaps];
+  Problem p[kMaxProblems];
+  int count;
+  int R;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: ~seconds of polling, then trap (turns a protocol bug into an error, never a hang).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 26); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) (ignored for swizzled K-major), SBO>>4 [32,46) = 1024 B, version=1 [46,48), layout=2 [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 [4,6), a/b_format=BF16 [7,10)/[10,13),
+// a/b K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kABytes = BM * BK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kBarOff = STAGES * kStage;
+  static constexpr int kTotal = kBarOff + 128 + 1024;  // barriers + tmem slot, + 1 KB alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ Batch batch) {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "TMEM allocation must be a power of two >= 32 columns");
+  using L = SmemLayout<BN>;
+  const Problem& pr = batch.p[blockIdx.z];
+  const int n0 = blockIdx.x * BN;
+  if (n0 >= pr.N) return;  // whole CTA exits before any barrier/TMEM use
+  const int m0 = blockIdx.y * BM;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_full = base + L::kBarOff;           // STAGES x 8 B
+  const uint32_t bar_empty = bar_full + STAGES * 8;      // STAGES x 8 B
+  const uint32_t bar_acc = bar_empty + STAGES * 8;       // 8 B
+  const uint32_t tmem_slot = bar_acc + 8;                // 4 B
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + L::kBarOff + STAGES * 16 + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = pr.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + s * 8, 1);
+      mbar_init(bar_empty + s * 8, 1);
+    }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* ma1 = &batch.maps[pr.a1_map];
+      const CUtensorMap* ma2 = &batch.maps[pr.a2_map];
+      const CUtensorMap* mw = &batch.maps[pr.w_map];
+      const int kb1 = pr.K1 / BK;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_empty + s * 8, ph ^ 1u);
+        const uint32_t sa = base + s * L::kStage, sb = sa + L::kABytes;
+        mbar_expect_tx(bar_full + s * 8, L::kStage);
+        if (kb < kb1) tma_load_2d(sa, ma1, pr.a1_col + kb * BK, m0, bar_full + s * 8);
+        else          tma_load_2d(sa, ma2, pr.a2_col + (kb - kb1) * BK, m0, bar_full + s * 8);
+        tma_load_2d(sb, mw, kb * BK, pr.w_row + n0, bar_full + s * 8);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(bar_full + s * 8, ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * L::kStage, sb = sa + L::kABytes;
+        const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // +32 B per UMMA_K inside the 128 B swizzle row => +2 in the >>4 field
+          tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        tc_commit(bar_empty + s * 8);  // frees the smem stage once these MMAs have read it
+      }
+      tc_commit(bar_acc);              // accumulator complete
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes [32*(w%4), +32) == output rows m0 + 32*(w%4) + lane
+    const int quad = warp & 3;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int row = m0 + quad * 32 + lane;
+    float* crow = pr.C + (size_t)row * pr.ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      if (row < batch.R) {
+        const int nb = n0 + c0;
+        if (nb + 32 <= pr.N && (pr.ldc & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (pr.bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(pr.bias + nb + j);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(crow + nb + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < pr.N) crow[nb + j] = v[j] + (pr.bias ? pr.bias[nb + j] : 0.f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+}  // namespace tc
+}  // namespace sd

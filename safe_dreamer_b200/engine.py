@@ -1,0 +1,204 @@
+"""Engine: one libsafedreamer handle + typed wrappers taking torch CUDA tensors.
+
+Thin by design: shape checks, contiguity, the current CUDA stream, and the C call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (MOD_ACTOR, MOD_CONT, MOD_REWARD, MOD_RSSM, MOD_SLOW_VALUE, MOD_VALUE, SD_FLAG_BF16,
+                   SD_FLAG_GRAPH, SD_FLAG_SAVE_TAPE, sd_config)
+
+__all__ = ["Engine", "SD_FLAG_BF16", "SD_FLAG_GRAPH", "SD_FLAG_SAVE_TAPE", "MOD_RSSM", "MOD_ACTOR", "MOD_REWARD",
+           "MOD_CONT", "MOD_VALUE", "MOD_SLOW_VALUE"]
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the RSSM hot path has no CPU implementation)")
+    return t.contiguous()
+
+
+class Engine:
+    """Owns one sd_handle (device workspace + packed weights) for a fixed model configuration."""
+
+    def __init__(self, *, D, U, S, K, G, E, A, obs_layers=1, img_layers=2, act_kind=0, units=256,
+                 actor_layers=3, value_layers=3, reward_layers=1, cont_layers=1, bins=255, unimix=0.01,
+                 act_unimix=0.01, min_std=0.1, max_std=1.0, max_rows=1024, max_steps=64, max_tape_rows=0,
+                 device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("safe_dreamer_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.cfg = sd_config(D=D, U=U, S=S, K=K, G=G, E=E, A=A, obs_layers=obs_layers, img_layers=img_layers,
+                             act_kind=act_kind, units=units, actor_layers=actor_layers, value_layers=value_layers,
+                             reward_layers=reward_layers, cont_layers=cont_layers, bins=bins, unimix=unimix,
+                             act_unimix=act_unimix, min_std=min_std, max_std=max_std, max_rows=max_rows,
+                             max_steps=max_steps, max_tape_rows=max_tape_rows)
+        self.SK, self.F = S * K, S * K + D
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sd_create(C.byref(self.cfg), C.byref(h)), "sd_create")
+        self.h = h
+        self._keep = {}
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                self.lib.sd_destroy(h)
+            except Exception:
+                pass
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace_bytes(self):
+        return int(self.lib.sd_workspace_bytes(C.byref(self.cfg)))
+
+    def weight_names(self, module):
+        n = self.lib.sd_weight_count(self.h, module)
+        return [self.lib.sd_weight_name(self.h, module, i).decode() for i in range(n)]
+
+    def set_weights(self, module, named):
+        """named: mapping state_dict-name -> fp32 CUDA tensor (reference layouts)."""
+        names = self.weight_names(module)
+        ts = []
+        for i, n in enumerate(names):
+            if n not in named:
+                raise KeyError(f"set_weights(module={module}): missing tensor '{n}'")
+            t = _f32c(named[n].detach(), n)
+            if t.numel() != self.lib.sd_weight_numel(self.h, module, i):
+                raise ValueError(f"set_weights: '{n}' has {t.numel()} elements, expected "
+                                 f"{self.lib.sd_weight_numel(self.h, module, i)}")
+            ts.append(t)
+        arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        _lib.check(self.lib.sd_set_weights(self.h, module, arr, len(ts), self.stream), "sd_set_weights")
+        self._keep[module] = ts  # keep sources alive until the async repack has been enqueued and run
+
+    def _new(self, *shape):
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ entry points
+    def observe(self, embed, action, init_stoch, init_deter, is_first, u, flags=0):
+        B, T = action.shape[:2]
+        embed, action, u = _f32c(embed, "embed"), _f32c(action, "action"), _f32c(u, "u")
+        init_stoch, init_deter = _f32c(init_stoch, "init_stoch"), _f32c(init_deter, "init_deter")
+        first = is_first.reshape(B, T).to(torch.uint8).contiguous()
+        c = self.cfg
+        assert embed.shape == (B, T, c.E) and action.shape == (B, T, c.A) and u.numel() == B * T * self.SK
+        stochs, deters, logits = self._new(B, T, c.S, c.K), self._new(B, T, c.D), self._new(B, T, c.S, c.K)
+        _lib.check(self.lib.sd_observe_fwd(self.h, B, T, _ptr(embed), _ptr(action), _ptr(init_stoch), _ptr(init_deter),
+                                           _ptr(first), _ptr(u), _ptr(stochs), _ptr(deters), _ptr(logits), flags,
+                                           self.stream), "sd_observe_fwd")
+        return stochs, deters, logits
+
+    def observe_bwd(self, B, T, d_stochs, d_deters, d_logits, want_embed=True, want_init=True, weight_grads=None,
+                    flags=0):
+        c = self.cfg
+        ds = None if d_stochs is None else _f32c(d_stochs, "d_stochs")
+        dd = None if d_deters is None else _f32c(d_deters, "d_deters")
+        dl = None if d_logits is None else _f32c(d_logits, "d_logits")
+        d_embed = self._new(B, T, c.E) if want_embed else None
+        d_is = self._new(B, c.S, c.K) if want_init else None
+        d_id = self._new(B, c.D) if want_init else None
+        if weight_grads is not None:
+            names = self.weight_names(MOD_RSSM)
+            arr = (C.c_void_p * len(names))(*[0 if weight_grads.get(n) is None else weight_grads[n].data_ptr()
+                                              for n in names])
+        else:
+            arr = None
+        _lib.check(self.lib.sd_observe_bwd(self.h, B, T, _ptr(ds), _ptr(dd), _ptr(dl), _ptr(d_embed), _ptr(d_is),
+                                           _ptr(d_id), arr, flags, self.stream), "sd_observe_bwd")
+        return d_embed, d_is, d_id
+
+    def prior(self, deter, u, flags=0):
+        c = self.cfg
+        lead = deter.shape[:-1]
+        deter, u = _f32c(deter, "deter").reshape(-1, c.D), _f32c(u, "u")
+        R = deter.shape[0]
+        assert u.numel() == R * self.SK
+        stoch, logit = self._new(R, c.S, c.K), self._new(R, c.S, c.K)
+        _lib.check(self.lib.sd_prior(self.h, R, _ptr(deter), _ptr(u), _ptr(stoch), _ptr(logit), flags, self.stream),
+                   "sd_prior")
+        return stoch.reshape(*lead, c.S, c.K), logit.reshape(*lead, c.S, c.K)
+
+    def imagine_with_action(self, stoch, deter, actions, u, flags=0):
+        c = self.cfg
+        R, T = actions.shape[:2]
+        stoch, deter, actions, u = (_f32c(stoch, "stoch"), _f32c(deter, "deter"), _f32c(actions, "actions"),
+                                    _f32c(u, "u"))
+        assert u.numel() == R * T * self.SK
+        stochs, deters = self._new(R, T, c.S, c.K), self._new(R, T, c.D)
+        _lib.check(self.lib.sd_imagine_with_action(self.h, R, T, _ptr(stoch), _ptr(deter), _ptr(actions), _ptr(u),
+                                                   _ptr(stochs), _ptr(deters), flags, self.stream),
+                   "sd_imagine_with_action")
+        return stochs, deters
+
+    def imagine(self, stoch0, deter0, u, act_noise, H, flags=0, out=None):
+        c = self.cfg
+        N = deter0.shape[0]
+        stoch0, deter0, u, act_noise = (_f32c(stoch0, "stoch0"), _f32c(deter0, "deter0"), _f32c(u, "u"),
+                                        _f32c(act_noise, "act_noise"))
+        assert u.numel() == N * H * self.SK and act_noise.numel() == N * H * c.A
+        feats, actions = out if out is not None else (self._new(N, H, self.F), self._new(N, H, c.A))
+        _lib.check(self.lib.sd_imagine_fwd(self.h, N, H, _ptr(stoch0), _ptr(deter0), _ptr(u), _ptr(act_noise),
+                                           _ptr(feats), _ptr(actions), flags, self.stream), "sd_imagine_fwd")
+        return feats, actions
+
+    def imagine_bwd(self, N, H, d_feats, d_actions, flags=0):
+        c = self.cfg
+        df = None if d_feats is None else _f32c(d_feats, "d_feats")
+        da = None if d_actions is None else _f32c(d_actions, "d_actions")
+        d_s, d_d = self._new(N, c.S, c.K), self._new(N, c.D)
+        _lib.check(self.lib.sd_imagine_bwd(self.h, N, H, _ptr(df), _ptr(da), _ptr(d_s), _ptr(d_d), flags, self.stream),
+                   "sd_imagine_bwd")
+        return d_s, d_d
+
+    def heads_lambda(self, feats, disc, lamb, flags=0, slow=True, out=None):
+        N, H = feats.shape[:2]
+        feats = _f32c(feats, "feats")
+        if out is None:
+            rew, cont, val, wgt = (self._new(N, H, 1) for _ in range(4))
+            sval = self._new(N, H, 1) if slow else None
+            ret = self._new(N, H - 1, 1)
+        else:
+            rew, cont, val, sval, wgt, ret = out
+        _lib.check(self.lib.sd_heads_lambda_fwd(self.h, N, H, _ptr(feats), float(disc), float(lamb), _ptr(rew),
+                                                _ptr(cont), _ptr(val), _ptr(sval), _ptr(wgt), _ptr(ret), flags,
+                                                self.stream), "sd_heads_lambda_fwd")
+        return rew, cont, val, sval, wgt, ret
+
+    def lambda_return(self, last, term, reward, value, boot, disc, lamb):
+        N, T = reward.shape[:2]
+        last, term, reward, value, boot = (_f32c(x, "lambda_return input") for x in (last, term, reward, value, boot))
+        out = self._new(N, T - 1, 1)
+        _lib.check(self.lib.sd_lambda_return(N, T, _ptr(last), _ptr(term), _ptr(reward), _ptr(value), _ptr(boot),
+                                             float(disc), float(lamb), _ptr(out), self.stream), "sd_lambda_return")
+        return out
+
+    def kl_loss(self, post_logit, prior_logit, free, entropies=False):
+        c = self.cfg
+        lead = post_logit.shape[:-2]
+        a, b = _f32c(post_logit, "post_logit"), _f32c(prior_logit, "prior_logit")
+        R = a.numel() // self.SK
+        dyn, rep = self._new(R), self._new(R)
+        ep = self._new(R) if entropies else None
+        eq = self._new(R) if entropies else None
+        _lib.check(self.lib.sd_kl_loss(self.h, R, _ptr(a), _ptr(b), float(free), _ptr(dyn), _ptr(rep), _ptr(ep),
+                                       _ptr(eq), self.stream), "sd_kl_loss")
+        outs = [dyn.reshape(lead), rep.reshape(lead)]
+        if entropies:
+            outs += [ep.reshape(lead), eq.reshape(lead)]
+        return tuple(outs)

@@ -56,3 +56,41 @@ def index_mismatch_report(idx_a, idx_b, score, tol):
     gap = top2_gap(score)
     unexplained = mism & (gap > tol)
     return int(mism.sum()), int(unexplained.sum()), int(mism.size)
+
+
+# ----------------------------------------------------------------------------- GPU-side helpers
+def make_engine(c, P, max_rows, max_steps, max_tape_rows=0):
+    """Engine for oracle config `c` with oracle weights `P` loaded (CUDA only)."""
+    import torch
+    from safe_dreamer_b200.engine import Engine
+    eng = Engine(D=c.D, U=c.U, S=c.S, K=c.K, G=c.G, E=c.E, A=c.A, obs_layers=c.obs_layers,
+                 img_layers=c.img_layers, act_kind=0 if c.act_kind == "cont" else 1, units=c.units,
+                 actor_layers=c.actor_layers, value_layers=c.value_layers, reward_layers=c.reward_layers,
+                 cont_layers=c.cont_layers, bins=c.bins, unimix=c.unimix, act_unimix=c.act_unimix,
+                 min_std=c.min_std, max_std=c.max_std, max_rows=max_rows, max_steps=max_steps,
+                 max_tape_rows=max_tape_rows)
+    for mod, key in enumerate(["rssm", "actor", "reward", "cont", "value", "slow_value"]):
+        eng.set_weights(mod, {k: torch.from_numpy(v).cuda() for k, v in P[key].items()})
+    torch.cuda.synchronize()
+    return eng
+
+
+def cu(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def assert_indices(idx_gpu, idx_ref, score_ref, tol, max_rate, what):
+    """Categorical indices must match except at near ties (top-2 gap of the checker's perturbed
+    logits below `tol`); the near-tie rate is printed (logged) and bounded by `max_rate`."""
+    n_mis, n_bad, n = index_mismatch_report(np.asarray(idx_gpu), np.asarray(idx_ref), score_ref, tol)
+    print(f"[near-tie log] {what}: {n_mis}/{n} indices differ ({n_mis / n:.2e}), {n_bad} not explained by a gap < {tol}")
+    assert n_bad == 0, f"{what}: {n_bad} index mismatches are not near ties"
+    assert n_mis / n <= max_rate, f"{what}: mismatch rate {n_mis / n:.3e} > {max_rate}"
+    return n_mis
+
+
+def perturbed_scores(logit, u, unimix):
+    """l + g of the oracle (what argmax is taken over)."""
+    l = O.unimix_logits(logit, unimix)
+    return l + (-np.log(-np.log(u.astype(logit.dtype))))
