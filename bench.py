@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the RSSM hot path (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one synthetic replay batch of the base.yaml shape
+(config C2): posterior scan RSSM.observe (B=16, T=64, E=1024; fwd [+bwd when the
+handle supports it]) -> imagination rollout Dreamer._imagine from all B*T posterior states
+(N=1024 rows, H=16, in-loop actor) -> frozen reward/cont/value/slow-value heads + lambda-return.
+metric = imagined RSSM steps/s (N*H row-steps per pass / device time), whole job over all ranks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Under torchrun every rank runs the same per-GPU workload on its own replay slice (weak scaling).
+--impl reference times the CPU port of the reference path (oracle/, numpy on all host cores).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, T, E, A, H = 16, 64, 1024, 6, 16
+N = B * T
+FLOP_IMAG_STEP = 11_674_624       # fwd FLOP per imagined row-step (A=6 continuous)
+FLOP_POST_STEP = 10_488_832       # fwd FLOP per posterior row-step (E=1024)
+FLOP_HEADS_ROW = 6_159_360        # reward+cont+value+slow value per imagined row
+METRIC = "imagined RSSM steps/s"
+WORKLOAD = "C2 dmc-vision r2dreamer base.yaml: observe B=16,T=64,E=1024 + imagine N=1024,H=16,A=6 + heads/lambda-return"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1371.4), d.get("bf16_tflops", 1614.7), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def oracle_step(c, P, inputs, rows_frac=1.0):
+    """The CPU port of the reference path on the same workload (oracle/rssm_oracle.py)."""
+    import numpy as np
+    from oracle import rssm_oracle as O
+    embed, action, reset, u, ui, noise = inputs
+    Bn = max(1, int(round(B * rows_frac)))
+    s0 = np.zeros((Bn, c.S, c.K), np.float32)
+    d0 = np.zeros((Bn, c.D), np.float32)
+    st, dt, lg, _ = O.observe(c, P["rssm"], embed[:Bn], action[:Bn], (s0, d0), reset[:Bn], u[:Bn])
+    n = Bn * T
+    feats, acts = O.imagine(c, P["rssm"], P["actor"], (st.reshape(n, c.S, c.K), dt.reshape(n, c.D)), H, ui[:n], noise[:n])
+    out = O.heads_lambda(c, P["reward"], P["cont"], P["value"], P["slow_value"], feats)
+    return n * H, float(out[-1].mean())
+
+
+def make_np_inputs(c):
+    from oracle import rssm_oracle as O
+    embed, action, reset, u = O.synth_observe_inputs(c, B, T, seed=2)
+    _, _, ui, noise = O.synth_imagine_inputs(c, N, H, seed=3)
+    return embed, action, reset, u, ui, noise
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    from oracle import rssm_oracle as O
+    cores = os.cpu_count() or 1
+    c = O.Cfg(E=E, A=A)
+    P = O.init_params(c, seed=0)
+    inputs = make_np_inputs(c)
+    tw = time.perf_counter()
+    oracle_step(c, P, inputs)
+    t_full = time.perf_counter() - tw
+    # bounded sample: shrink the replay rows per step so K steps stay within ~2 minutes
+    frac = min(1.0, 120.0 / (args.steps * t_full))
+    frac = max(1, int(frac * B)) / B
+    for _ in range(max(0, args.warmup - 1)):
+        oracle_step(c, P, inputs, frac)
+    t0 = time.perf_counter()
+    units = 0
+    for _ in range(args.steps):
+        n, _ = oracle_step(c, P, inputs, frac)
+        units += n
+    dt = time.perf_counter() - t0
+    val = units / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows": N, "horizon": H},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{int(frac * B)}/{B} of the replay rows per step x{args.steps} steps (numpy/BLAS, all host threads)"},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import rssm_oracle as O          # cpu_baseline leg + synthetic weights/inputs only
+    from safe_dreamer_b200 import _lib
+    from tests.helpers import make_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c = O.Cfg(E=E, A=A)
+    P = O.init_params(c, seed=0)
+    lib = _lib.load()
+    lib.sd_observe_bwd(None, 1, 1, None, None, None, None, None, None, None, 0, None)  # probes the build
+    have_bwd = (not args.no_bwd) and b"not implemented" not in lib.sd_last_error_string()
+    eng = make_engine(c, P, max_rows=N, max_steps=max(T, H), max_tape_rows=B if have_bwd else 0)
+    emb_np, act_np, rst_np, u_np, ui_np, nz_np = make_np_inputs(c)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)   # each rank scans its own replay slice
+    emb_np = emb_np + 0.01 * torch.randn(emb_np.shape, generator=g).numpy().astype(np.float32) * (rank > 0)
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    embed, action, reset, u, ui, noise = cu(emb_np), cu(act_np), cu(rst_np), cu(u_np), cu(ui_np), cu(nz_np)
+    s0 = torch.zeros(B, c.S, c.K, device=dev)
+    d0 = torch.zeros(B, c.D, device=dev)
+    feats = torch.empty(N, H, c.F, device=dev)
+    actions = torch.empty(N, H, c.A, device=dev)
+    outs = tuple(torch.empty(N, H, 1, device=dev) for _ in range(5)) + (torch.empty(N, H - 1, 1, device=dev),)
+    disc = 1 - 1 / c.horizon
+    GRAPH, BF16, TAPE = 4, 1, 2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # upstream cotangents for the posterior backward (what dreamer.py:486-573 would send back)
+    if have_bwd:
+        gst = torch.randn(B, T, c.S, c.K, device=dev) * 0.01
+        gdt = torch.randn(B, T, c.D, device=dev) * 0.01
+        glg = torch.randn(B, T, c.S, c.K, device=dev) * 0.01
+        wgrads = {n: torch.zeros(P["rssm"][n].shape, device=dev) for n in eng.weight_names(0)}
+
+    def hot_path():
+        st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | (TAPE if have_bwd else 0))
+        if have_bwd:
+            eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
+            if world > 1:   # DP: one bucketed all-reduce of the RSSM weight grads, overlapped with imagination
+                flat = torch.cat([w.reshape(-1) for w in wgrads.values()])
+                work = dist.all_reduce(flat, async_op=True)
+        eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions))
+        eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
+        if have_bwd and world > 1:
+            work.wait()
+        return outs[-1]
+
+    def timed(fn, iters, do_flush=True):
+        total = 0.0
+        for _ in range(iters):
+            if do_flush:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            total += a.elapsed_time(b)
+        return total
+
+    for _ in range(max(args.warmup, 3)):
+        hot_path()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    ms = timed(hot_path, args.steps)
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # dominant kernel sequence: the imagination scan alone (CUDA events on the launching stream)
+    st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH)
+    st, dt = st.reshape(N, c.S, c.K), dt.reshape(N, c.D)
+    ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions)), args.steps)
+    ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH), args.steps)
+    ms_heads = timed(lambda: eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs), args.steps)
+    ms_obs_fb = None
+    if have_bwd:
+        def fb():
+            eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | TAPE)
+            eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
+        ms_obs_fb = timed(fb, args.steps)
+    # ---- end-to-end through the public module API with HOST buffers (pinned) and a D2H result read
+    from types import SimpleNamespace as NS
+    from safe_dreamer_b200 import dreamer_ops
+    from safe_dreamer_b200.networks import MLPHead
+    from safe_dreamer_b200.rssm import RSSM
+    cfgr = NS(stoch=c.S, deter=c.D, hidden=c.U, discrete=c.K, act="SiLU", unimix_ratio=c.unimix, initial="learned",
+              device=str(dev), obs_layers=c.obs_layers, img_layers=c.img_layers, dyn_layers=1, blocks=c.G)
+    rssm = RSSM(cfgr, E, A).to(dev)
+    rssm.load_state_dict({k: cu(v) for k, v in P["rssm"].items()})
+    heads = {}
+    for key, (name, layers, out) in {"actor": ("actor", c.actor_layers, 2 * A), "reward": ("reward", c.reward_layers, c.bins),
+                                     "cont": ("cont", c.cont_layers, 1), "value": ("value", c.value_layers, c.bins),
+                                     "slow_value": ("value", c.value_layers, c.bins)}.items():
+        m = MLPHead(name, layers, c.units, c.F, out).to(dev)
+        m.load_state_dict({k: cu(v) for k, v in P[key].items()})
+        heads[key] = m
+    dreamer_ops.attach_heads(rssm, **heads)
+    rssm.use_graph, rssm.auto_refresh = True, False
+    rssm.max_rows, rssm.max_steps = N, max(T, H)
+    h_embed = torch.from_numpy(emb_np).pin_memory()
+    h_action = torch.from_numpy(act_np).pin_memory()
+    h_first = torch.from_numpy(rst_np.astype(np.uint8)).pin_memory()
+    h_s0, h_d0 = torch.zeros(B, c.S, c.K).pin_memory(), torch.zeros(B, c.D).pin_memory()
+    h2d = sum(x.numel() * x.element_size() for x in (h_embed, h_action, h_first, h_s0, h_d0))
+
+    def e2e_step():
+        with torch.no_grad():
+            e_, a_, f_ = h_embed.to(dev, non_blocking=True), h_action.to(dev, non_blocking=True), h_first.to(dev, non_blocking=True)
+            s_, d_ = h_s0.to(dev, non_blocking=True), h_d0.to(dev, non_blocking=True)
+            rssm.refresh_weights(force=True)            # weights change once per update in training
+            rssm.precision = "fp32"
+            st_, dt_, lg_ = rssm.observe(e_, a_, (s_, d_), f_)
+            rssm.precision = "bf16"
+            ft_, ac_ = dreamer_ops.imagine(rssm, (st_.reshape(N, c.S, c.K), dt_.reshape(N, c.D)), H)
+            r_ = dreamer_ops.heads_lambda(rssm, ft_, c.horizon, c.lamb)
+            return float(r_[-1].mean().item())           # D2H read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        sus, burst, how = peaks()
+        units = N * H * args.steps * world
+        imag_tflops = N * H * FLOP_IMAG_STEP / (ms_imag / args.steps * 1e-3) / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            inputs = (emb_np, act_np, rst_np, u_np, ui_np, nz_np)
+            oracle_step(c, P, inputs, 0.25)
+            t1 = time.perf_counter()
+            reps, n_units = 0, 0
+            while time.perf_counter() - t1 < 10.0:
+                n_, _ = oracle_step(c, P, inputs)
+                n_units += n_; reps += 1
+            cpu = {"value": n_units / (time.perf_counter() - t1), "unit": "steps/s", "cores": cores, "kind": "port",
+                   "sample": f"full workload x{reps} on the host (numpy oracle port of the reference path)"}
+        line = {
+            "metric": METRIC, "value": units / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (imagination/heads GEMMs, fp32 accumulate) + f32 (posterior scan, all sampling)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows": N, "horizon": H, "posterior_bwd": bool(have_bwd),
+                       "l2": "256 MB flush write between timed iterations (outside the event pairs)",
+                       "multi_gpu": "each rank scans its own replay slice; RSSM grad all-reduce (NCCL) overlapped with imagination" if have_bwd else "replicas only"},
+            "gpu_launches": int(launches),
+            "breakdown_ms": {"observe_fwd": ms_obs / args.steps, "observe_fwd_bwd": None if ms_obs_fb is None else ms_obs_fb / args.steps,
+                             "imagine_fwd": ms_imag / args.steps, "heads_lambda": ms_heads / args.steps},
+            "roofline": {"bound": "tensor", "achieved": imag_tflops, "peak": sus, "unit": "TFLOP/s", "frac": imag_tflops / sus,
+                         "traffic": None, "kernel": "sd_imagine_fwd scan (tcgen05 GEMMs + fused row kernels, one CUDA graph)",
+                         "peak_source": f"{how} bf16_tflops_sustained (burst {burst})",
+                         "flop_per_unit": FLOP_IMAG_STEP, "units_per_launch": N * H},
+            "cpu_baseline": cpu,
+            "e2e": {"value": N * H * args.steps * world / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-bwd", action="store_true", help="time the forward-only hot path")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1000,7 +1000,7 @@ extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feat
         sd::twohot_mode_kernel<<<(R * 32 + 255) / 256, 256, 0, cx.st>>>(h->hl, up(hw.out, 4), h->bins, c.bins, R, rew_like);
         cx.check("twohot_mode_kernel");
       } else {
-        sd::sigmoid_kernel<<<(R + 255) / 256, 256, 0, cx.st>>>(h->hl, rew_like, R);
+        sd::sigmoid_kernel<<<(R + 255) / 256, 256, 0, cx.st>>>(h->hl, up(hw.out, 4), rew_like, R);
         cx.check("sigmoid_kernel");
       }
     };

@@ -475,9 +475,9 @@ __global__ void twohot_mode_kernel(const float* __restrict__ logits, int ld, con
 }
 
 // cont head mean = sigmoid(logit) (distributions.py:238-239, Bernoulli.mean).
-__global__ void sigmoid_kernel(const float* __restrict__ in, float* out, int n) {
+__global__ void sigmoid_kernel(const float* __restrict__ in, int ld, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = sigmoidf_(in[i]);
+  if (i < n) out[i] = sigmoidf_(in[(size_t)i * ld]);
 }
 
 // weight = cumprod(cont*disc) (dreamer.py:596) and the lambda-return reverse scan

@@ -1,0 +1,68 @@
+"""CUDA replacements for the imagination part of world_model/dreamer.py:
+`imagine`  == Dreamer._imagine (dreamer.py:673-692),
+`heads_lambda` == frozen heads + weights + `_lambda_return` on imagined feats (dreamer.py:589-602),
+`lambda_return` == Dreamer._lambda_return (dreamer.py:694-707).
+Heads are passed as modules whose state_dict follows networks.MLPHead; they are registered on the
+RSSM so their weights are repacked together with it."""
+import torch
+
+from .engine import MOD_ACTOR, MOD_CONT, MOD_REWARD, MOD_SLOW_VALUE, MOD_VALUE
+
+_U_LO = 2.0 ** -24
+
+
+def _layers(m):
+    return sum(1 for n, _ in m.named_parameters() if n.endswith(".weight") and "_linear" in n)
+
+
+def attach_heads(rssm, actor=None, reward=None, cont=None, value=None, slow_value=None, act_kind="cont",
+                 min_std=0.1, max_std=1.0, act_unimix=0.01, bins=255):
+    """Register head modules on `rssm` (fixes the engine's head dimensions)."""
+    mods = {MOD_ACTOR: actor, MOD_REWARD: reward, MOD_CONT: cont, MOD_VALUE: value, MOD_SLOW_VALUE: slow_value}
+    rssm.head_modules = {k: v for k, v in mods.items() if v is not None}
+    dims = dict(act_kind=0 if act_kind == "cont" else 1, min_std=min_std, max_std=max_std, act_unimix=act_unimix,
+                bins=bins)
+    some = next(iter(rssm.head_modules.values()))
+    dims["units"] = some.last.in_features
+    if actor is not None:
+        dims["actor_layers"] = _layers(actor)
+    if value is not None:
+        dims["value_layers"] = _layers(value)
+    if reward is not None:
+        dims["reward_layers"] = _layers(reward)
+    if cont is not None:
+        dims["cont_layers"] = _layers(cont)
+    rssm._head_dims = dims
+    rssm._rt.engine = None  # dimensions changed: rebuild lazily
+    rssm._rt.limits = (0, 0, 0)
+
+
+@torch.no_grad()
+def imagine(rssm, start, imag_horizon, act_noise=None, u=None):
+    """Dreamer._imagine: returns feats (N,H,F), actions (N,H,A)."""
+    stoch, deter = start
+    N = deter.shape[0]
+    eng = rssm._get_engine(N, imag_horizon)
+    dev = deter.device
+    if u is None:
+        u = rssm._uniform(N, imag_horizon, rssm._stoch, rssm._discrete)
+    if act_noise is None:
+        if eng.cfg.act_kind == 0:
+            act_noise = torch.randn(N, imag_horizon, rssm._act_dim, device=dev)
+        else:
+            act_noise = torch.rand(N, imag_horizon, rssm._act_dim, device=dev).clamp_(_U_LO, 1 - _U_LO)
+    return eng.imagine(stoch, deter, u, act_noise, imag_horizon, flags=rssm._flags())
+
+
+@torch.no_grad()
+def heads_lambda(rssm, imag_feat, horizon=333, lamb=0.95, slow=True):
+    """dreamer.py:589-602 -> reward, cont, value, slow_value, weight, ret."""
+    N, H = imag_feat.shape[:2]
+    eng = rssm._get_engine(N, H)
+    return eng.heads_lambda(imag_feat, 1 - 1 / horizon, lamb, flags=rssm._flags(), slow=slow)
+
+
+@torch.no_grad()
+def lambda_return(rssm, last, term, reward, value, boot, disc, lamb):
+    eng = rssm._get_engine(1, 1)
+    return eng.lambda_return(last, term, reward, value, boot, disc, lamb)

@@ -1,0 +1,292 @@
+"""Drop-in mirror of the reference ``world_model/rssm.py`` whose scans run in libsafedreamer.
+
+Same constructor, method names, argument meaning, parameter names and shapes as the reference
+(``RSSM(config.rssm, embed_size, act_dim)``, world_model/rssm.py:78-230), so ``state_dict``s
+interchange and ``dreamer.py`` can call it unchanged.  The modules below are parameter
+containers: the math runs in CUDA through :class:`safe_dreamer_b200.engine.Engine`.
+
+Noise: the reference draws Gumbel noise inside ``F.gumbel_softmax``; here each call draws
+uniforms with ``torch.rand`` on the device (or takes them from ``noise_source`` for parity
+tests) and the kernels turn them into Gumbels, g = -log(-log(u)).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import engine as _engine
+from .engine import MOD_RSSM, SD_FLAG_BF16, SD_FLAG_GRAPH, SD_FLAG_SAVE_TAPE
+
+_U_LO = 2.0 ** -24
+
+
+def rpad(x, pad):
+    """utils/tools.py:413-416."""
+    for _ in range(pad):
+        x = x.unsqueeze(-1)
+    return x
+
+
+def weight_init_(m):
+    """Same initial distribution as utils/tools.py:76-100: trunc-normal(std=1.1368/sqrt(fan_in)),
+    zero bias, unit RMSNorm scale."""
+    if isinstance(m, nn.RMSNorm):
+        with torch.no_grad():
+            m.weight.fill_(1.0)
+        return
+    w = getattr(m, "weight", None)
+    if w is None or w.numel() == 0:
+        return
+    fan_in = w.shape[1] * (math.prod(w.shape[2:]) if w.dim() > 2 else 1) if w.dim() > 1 else w.shape[0]
+    std = 1.1368 * math.sqrt(1.0 / fan_in)
+    with torch.no_grad():
+        nn.init.trunc_normal_(w, mean=0.0, std=std, a=-2.0 * std, b=2.0 * std)
+        b = getattr(m, "bias", None)
+        if b is not None:
+            b.fill_(0.0)
+
+
+class BlockLinear(nn.Module):
+    """Parameter container with the reference layout (networks.py:24-41): weight (O/G, I/G, G)."""
+
+    def __init__(self, in_ch, out_ch, blocks, outscale=1.0):
+        super().__init__()
+        self.in_ch, self.out_ch, self.blocks, self.outscale = int(in_ch), int(out_ch), int(blocks), float(outscale)
+        self.weight = nn.Parameter(torch.empty(self.out_ch // self.blocks, self.in_ch // self.blocks, self.blocks))
+        self.bias = nn.Parameter(torch.empty(self.out_ch))
+
+    def forward(self, x):  # pragma: no cover - the block GEMMs run inside the fused scan
+        raise NotImplementedError("BlockLinear is evaluated inside the CUDA scan; call RSSM.obs_step/img_step")
+
+
+class Deter(nn.Module):
+    """Parameter container mirroring rssm.py:10-34 (same sub-module names => same state_dict keys)."""
+
+    def __init__(self, deter, stoch, act_dim, hidden, blocks, dynlayers, act="SiLU"):
+        super().__init__()
+        if int(dynlayers) != 1:
+            raise NotImplementedError("dyn_layers != 1 is not supported by the CUDA scan (base.yaml:266 uses 1)")
+        if act != "SiLU":
+            raise NotImplementedError("only act='SiLU' is implemented (base.yaml:129)")
+        self.blocks, self.dynlayers = int(blocks), int(dynlayers)
+        A = getattr(nn, act)
+
+        def inp(k):
+            return nn.Sequential(nn.Linear(k, hidden, bias=True), nn.RMSNorm(hidden, eps=1e-04, dtype=torch.float32), A())
+
+        self._dyn_in0, self._dyn_in1, self._dyn_in2 = inp(deter), inp(stoch), inp(act_dim)
+        self._dyn_hid = nn.Sequential()
+        in_ch = (3 * hidden + deter // self.blocks) * self.blocks
+        self._dyn_hid.add_module("dyn_hid_0", BlockLinear(in_ch, deter, self.blocks))
+        self._dyn_hid.add_module("norm_0", nn.RMSNorm(deter, eps=1e-04, dtype=torch.float32))
+        self._dyn_hid.add_module("act_0", A())
+        self._dyn_gru = BlockLinear(deter, 3 * deter, self.blocks)
+
+    def forward(self, stoch, deter, action):  # pragma: no cover
+        raise NotImplementedError("Deter is evaluated inside the CUDA scan; call RSSM.img_step")
+
+
+class _Runtime:
+    """Per-module CUDA state (engine handle, weight signature). Never copied or pickled."""
+
+    def __init__(self):
+        self.engine = None
+        self.sig = None
+        self.limits = (0, 0, 0)
+
+    def __deepcopy__(self, memo):
+        return _Runtime()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+
+class _ObserveFn(torch.autograd.Function):
+    """observe forward/backward through the C ABI (sd_observe_fwd / sd_observe_bwd)."""
+
+    @staticmethod
+    def forward(ctx, rssm, embed, action, init_stoch, init_deter, reset, u, *params):
+        eng = rssm._get_engine(action.shape[0], action.shape[1], tape=True)
+        flags = rssm._flags() | SD_FLAG_SAVE_TAPE
+        stochs, deters, logits = eng.observe(embed, action, init_stoch, init_deter, reset, u, flags=flags)
+        ctx.rssm, ctx.B, ctx.T = rssm, action.shape[0], action.shape[1]
+        ctx.need = (ctx.needs_input_grad[1], ctx.needs_input_grad[3] or ctx.needs_input_grad[4],
+                    any(ctx.needs_input_grad[7:]))
+        ctx.flags = rssm._flags()
+        return stochs, deters, logits
+
+    @staticmethod
+    def backward(ctx, d_st, d_dt, d_lg):
+        rssm = ctx.rssm
+        eng = rssm._rt.engine
+        need_embed, need_init, need_w = ctx.need
+        names = eng.weight_names(MOD_RSSM)
+        wg = None
+        if need_w:
+            wg = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in rssm.named_parameters()}
+        d_embed, d_is, d_id = eng.observe_bwd(ctx.B, ctx.T, d_st, d_dt, d_lg, need_embed, need_init, wg, ctx.flags)
+        pg = [None if wg is None else wg[n] for n, _ in rssm.named_parameters()]
+        assert set(names) == set(n for n, _ in rssm.named_parameters())
+        return (None, d_embed, None, d_is, d_id, None, None, *pg)
+
+
+class RSSM(nn.Module):
+    """world_model/rssm.py:78-230 with the scans in CUDA."""
+
+    def __init__(self, config, embed_size, act_dim):
+        super().__init__()
+        self._stoch, self._deter = int(config.stoch), int(config.deter)
+        self._hidden, self._discrete = int(config.hidden), int(config.discrete)
+        self._unimix_ratio = float(config.unimix_ratio)
+        self._initial = str(config.initial)
+        self._device = torch.device(config.device)
+        self._act_dim, self._embed_size = int(act_dim), int(embed_size)
+        self._obs_layers, self._img_layers = int(config.obs_layers), int(config.img_layers)
+        self._dyn_layers, self._blocks = int(config.dyn_layers), int(config.blocks)
+        self.flat_stoch = self._stoch * self._discrete
+        self.feat_size = self.flat_stoch + self._deter
+        A = getattr(nn, config.act)
+        self._deter_net = Deter(self._deter, self.flat_stoch, act_dim, self._hidden, blocks=self._blocks,
+                                dynlayers=self._dyn_layers, act=config.act)
+        self._obs_net = nn.Sequential()
+        inp = self._deter + embed_size
+        for i in range(self._obs_layers):
+            self._obs_net.add_module(f"obs_net_{i}", nn.Linear(inp, self._hidden, bias=True))
+            self._obs_net.add_module(f"obs_net_n_{i}", nn.RMSNorm(self._hidden, eps=1e-04, dtype=torch.float32))
+            self._obs_net.add_module(f"obs_net_a_{i}", A())
+            inp = self._hidden
+        self._obs_net.add_module("obs_net_logit", nn.Linear(inp, self.flat_stoch, bias=True))
+        self._img_net = nn.Sequential()
+        inp = self._deter
+        for i in range(self._img_layers):
+            self._img_net.add_module(f"img_net_{i}", nn.Linear(inp, self._hidden, bias=True))
+            self._img_net.add_module(f"img_net_n_{i}", nn.RMSNorm(self._hidden, eps=1e-04, dtype=torch.float32))
+            self._img_net.add_module(f"img_net_a_{i}", A())
+            inp = self._hidden
+        self._img_net.add_module("img_net_logit", nn.Linear(inp, self.flat_stoch))
+        self.apply(weight_init_)
+        # runtime knobs (not part of the reference signature)
+        self.precision = "fp32"        # "bf16" => tcgen05 path when rows >= 128
+        self.use_graph = False         # replay scans as cached CUDA graphs
+        self.auto_refresh = True       # repack weights on every call (safe with in-place optimizers)
+        self.noise_source = None       # callable(shape, device) -> uniforms, for injected-noise parity
+        self.max_rows, self.max_steps = 1024, 64
+        self.head_modules = {}         # module id -> nn.Module (actor / reward / cont / value / slow value)
+        self._rt = _Runtime()
+
+    # ------------------------------------------------------------------ runtime plumbing
+    def _flags(self):
+        f = SD_FLAG_BF16 if self.precision == "bf16" else 0
+        return f | (SD_FLAG_GRAPH if self.use_graph else 0)
+
+    def engine_dims(self):
+        return dict(D=self._deter, U=self._hidden, S=self._stoch, K=self._discrete, G=self._blocks,
+                    E=self._embed_size, A=self._act_dim, obs_layers=self._obs_layers, img_layers=self._img_layers,
+                    unimix=self._unimix_ratio)
+
+    def _get_engine(self, rows, steps, tape=False, extra=None):
+        rt = self._rt
+        need = (max(rows, rt.limits[0]), max(steps, rt.limits[1]), max(rows if tape else 0, rt.limits[2]))
+        if rt.engine is None or need != rt.limits:
+            kw = self.engine_dims()
+            kw.update(getattr(self, "_head_dims", {}))
+            if extra:
+                kw.update(extra)
+            rt.engine = _engine.Engine(max_rows=max(need[0], 1), max_steps=max(need[1], 1), max_tape_rows=need[2],
+                                       device=next(self.parameters()).device, **kw)
+            rt.limits, rt.sig = need, None
+        self.refresh_weights(force=False)
+        return rt.engine
+
+    def refresh_weights(self, force=True):
+        """Repack the (possibly updated in place) parameters into the kernels' layouts."""
+        rt = self._rt
+        if rt.engine is None:
+            return
+        params = dict(self.named_parameters())
+        sig = tuple((p.data_ptr(), p._version) for p in params.values())
+        if force or self.auto_refresh or sig != rt.sig:
+            rt.engine.set_weights(MOD_RSSM, params)
+            for mod, m in self.head_modules.items():
+                rt.engine.set_weights(mod, dict(m.named_parameters()))
+            rt.sig = sig
+
+    def _uniform(self, *shape):
+        dev = next(self.parameters()).device
+        if self.noise_source is not None:
+            return self.noise_source(shape, dev)
+        return torch.rand(*shape, device=dev, dtype=torch.float32).clamp_(_U_LO, 1.0 - _U_LO)
+
+    # ------------------------------------------------------------------ reference API
+    def initial(self, batch_size):
+        """rssm.py:133-138."""
+        dev = next(self.parameters()).device
+        deter = torch.zeros(batch_size, self._deter, dtype=torch.float32, device=dev)
+        stoch = torch.zeros(batch_size, self._stoch, self._discrete, dtype=torch.float32, device=dev)
+        return stoch, deter
+
+    def observe(self, embed, action, initial, reset):
+        """rssm.py:140-156: (B,T,E),(B,T,A),((B,S,K),(B,D)),(B,T[,1]) -> stochs, deters, logits."""
+        B, T = action.shape[:2]
+        stoch, deter = initial
+        u = self._uniform(B, T, self._stoch, self._discrete)
+        needs_grad = torch.is_grad_enabled() and (
+            embed.requires_grad or stoch.requires_grad or deter.requires_grad
+            or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            return _ObserveFn.apply(self, embed.float(), action, stoch.float(), deter.float(), reset, u,
+                                    *self.parameters())
+        eng = self._get_engine(B, T)
+        return eng.observe(embed, action, stoch, deter, reset, u, flags=self._flags())
+
+    def obs_step(self, stoch, deter, prev_action, embed, reset):
+        """rssm.py:158-178 (single posterior step; reset is (B,) or (B,1))."""
+        B = deter.shape[0]
+        st, dt, lg = self.observe(embed.unsqueeze(1), prev_action.unsqueeze(1), (stoch, deter), reset.reshape(B, 1))
+        return st[:, 0], dt[:, 0], lg[:, 0]
+
+    def img_step(self, stoch, deter, prev_action):
+        """rssm.py:180-187."""
+        st, dt = self.imagine_with_action(stoch, deter, prev_action.unsqueeze(1))
+        return st[:, 0], dt[:, 0]
+
+    def prior(self, deter):
+        """rssm.py:189-195; also called batched on (B,T,D) (dreamer.py:485)."""
+        lead = deter.shape[:-1]
+        rows = int(math.prod(lead))
+        eng = self._get_engine(min(rows, self.max_rows), 1)
+        if rows > eng.cfg.max_rows * eng.cfg.max_steps:
+            eng = self._get_engine(self.max_rows, -(-rows // self.max_rows))
+        u = self._uniform(*lead, self._stoch, self._discrete)
+        if torch.is_grad_enabled() and (deter.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("RSSM.prior backward is not available in this build (forward-only entry)")
+        return eng.prior(deter, u, flags=self._flags())
+
+    def imagine_with_action(self, stoch, deter, actions):
+        """rssm.py:197-209."""
+        R, T = actions.shape[:2]
+        eng = self._get_engine(R, T)
+        u = self._uniform(R, T, self._stoch, self._discrete)
+        return eng.imagine_with_action(stoch, deter, actions, u, flags=self._flags())
+
+    def get_feat(self, stoch, deter):
+        """rssm.py:211-217."""
+        stoch = stoch.reshape(*stoch.shape[:-2], self._stoch * self._discrete)
+        return torch.cat([stoch, deter], -1)
+
+    def get_dist(self, logit):
+        """rssm.py:219-220."""
+        from .distributions import OneHotDist
+        return torch.distributions.independent.Independent(OneHotDist(logit, unimix_ratio=self._unimix_ratio), 1)
+
+    def kl_loss(self, post_logit, prior_logit, free):
+        """rssm.py:222-230 (differentiable; the fused value-only kernel is Engine.kl_loss)."""
+        from .distributions import kl
+        rep_loss = kl(post_logit, prior_logit.detach()).sum(-1)
+        dyn_loss = kl(post_logit.detach(), prior_logit).sum(-1)
+        return torch.clip(dyn_loss, min=free), torch.clip(rep_loss, min=free)
