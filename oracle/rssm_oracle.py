@@ -531,3 +531,178 @@ def clamp_u(u):
 
 def cast_params(P, dtype):
     return {m: {k: v.astype(dtype) for k, v in d.items()} for m, d in P.items()}
+
+
+# --------------------------------------------------------------------------- backward (manual autograd)
+# Restates what torch.autograd computes for the reference modules; pinned against
+# autograd of the real reference by tests/golden (keys bwd_* / imag_bwd_*).
+def normact_bwd(dout, v, w):
+    """out = silu(rms_norm(v, w)).  Returns dv, dw."""
+    dt = v.dtype.type
+    rho = dt(1.0) / np.sqrt(np.mean(v * v, axis=-1, keepdims=True) + dt(RMS_EPS))
+    n = v * rho
+    m = n * w
+    sig = sigmoid(m)
+    dm = dout * (sig * (dt(1.0) + m * (dt(1.0) - sig)))
+    dw = (dm * n).sum(0)
+    dn = dm * w
+    dv = rho * (dn - n * np.mean(dn * n, axis=-1, keepdims=True))
+    return dv, dw
+
+
+def linear_bwd(dy, x, w):
+    return dy @ w, dy.T @ x, dy.sum(0)
+
+
+def block_linear_bwd(dy, x, w, G):
+    R = x.shape[0]
+    xg, dyg = x.reshape(R, G, -1), dy.reshape(R, G, -1)
+    dx = np.stack([dyg[:, g] @ w[:, :, g] for g in range(G)], 1).reshape(R, -1)
+    dw = np.stack([dyg[:, g].T @ xg[:, g] for g in range(G)], -1)
+    return dx, dw, dy.sum(0)
+
+
+def sample_bwd(dz, logit, y, unimix):
+    """Gradient of the straight-through sample w.r.t. the raw logits (only the +y term carries grad)."""
+    dt = logit.dtype.type
+    K = logit.shape[-1]
+    dl = y * (dz - (dz * y).sum(-1, keepdims=True))
+    p = softmax(logit)
+    pt = p * (dt(1.0) - dt(unimix)) + dt(unimix) / dt(K)
+    dlp = dl - pt * dl.sum(-1, keepdims=True)
+    dp = dlp / pt * (dt(1.0) - dt(unimix))
+    return p * (dp - (dp * p).sum(-1, keepdims=True))
+
+
+def _acc(G, k, v):
+    G[k] = v if k not in G else G[k] + v
+
+
+def mlp_logits_bwd(dlogit, P, G, acts, last_in, lin, norm, last):
+    """Backward of [Linear->RMS->SiLU]*n -> Linear.  acts = [(x_in, v)], returns d(input of layer 0)."""
+    dx, dw, db = linear_bwd(dlogit, last_in, P[last + ".weight"])
+    if G is not None:
+        _acc(G, last + ".weight", dw); _acc(G, last + ".bias", db)
+    for i in reversed(range(len(acts))):
+        x_in, v = acts[i]
+        dv, dg = normact_bwd(dx, v, P[f"{norm}{i}.weight"])
+        dx, dw, db = linear_bwd(dv, x_in, P[f"{lin}{i}.weight"])
+        if G is not None:
+            _acc(G, f"{norm}{i}.weight", dg); _acc(G, f"{lin}{i}.weight", dw); _acc(G, f"{lin}{i}.bias", db)
+    return dx
+
+
+def deter_step_bwd(c: Cfg, P, G, tp, g_d):
+    """Backward of deter_step given grad of its output.  Returns d_stoch(z flat), d_deter_in, d_action_raw."""
+    pre = "_deter_net."
+    dt = g_d.dtype.type
+    R = g_d.shape[0]
+    Dg = c.D // c.G
+    q, d_in = tp["q"], tp["deter_in"]
+    qg = q.reshape(R, c.G, 3, Dg)
+    r_, c_, u_ = (qg[:, :, j, :].reshape(R, -1) for j in range(3))
+    Rg = sigmoid(r_); C = np.tanh(Rg * c_); Uu = sigmoid(u_ - dt(1.0))
+    dUu = g_d * (C - d_in); dC = g_d * Uu; dd = g_d * (dt(1.0) - Uu)
+    du = dUu * Uu * (dt(1.0) - Uu)
+    dtn = dC * (dt(1.0) - C * C)
+    dc = dtn * Rg; dR = dtn * c_
+    dr = dR * Rg * (dt(1.0) - Rg)
+    dq = np.stack([dr.reshape(R, c.G, Dg), dc.reshape(R, c.G, Dg), du.reshape(R, c.G, Dg)], 2).reshape(R, -1)
+    dh, dw, db = block_linear_bwd(dq, tp["h"], P[pre + "_dyn_gru.weight"], c.G)
+    if G is not None:
+        _acc(G, pre + "_dyn_gru.weight", dw); _acc(G, pre + "_dyn_gru.bias", db)
+    dhpre, dg = normact_bwd(dh, tp["hpre"], P[pre + "_dyn_hid.norm_0.weight"])
+    x = tp["x"]
+    xin = np.concatenate([d_in.reshape(R, c.G, Dg), np.broadcast_to(x[:, None, :], (R, c.G, x.shape[-1]))], -1).reshape(R, -1)
+    dxin, dw, db = block_linear_bwd(dhpre, xin, P[pre + "_dyn_hid.dyn_hid_0.weight"], c.G)
+    if G is not None:
+        _acc(G, pre + "_dyn_hid.norm_0.weight", dg)
+        _acc(G, pre + "_dyn_hid.dyn_hid_0.weight", dw); _acc(G, pre + "_dyn_hid.dyn_hid_0.bias", db)
+    dxin = dxin.reshape(R, c.G, -1)
+    dd = dd + dxin[:, :, :Dg].reshape(R, -1)
+    dx = dxin[:, :, Dg:].sum(1)
+    U = c.U
+    outs = []
+    for j, (name, inp) in enumerate((("_dyn_in0", d_in), ("_dyn_in1", tp["z"]), ("_dyn_in2", tp["a"]))):
+        dv, dgj = normact_bwd(dx[:, j * U:(j + 1) * U], tp[f"v{j}"], P[pre + name + ".1.weight"])
+        dxi, dw, db = linear_bwd(dv, inp, P[pre + name + ".0.weight"])
+        if G is not None:
+            _acc(G, pre + name + ".1.weight", dgj); _acc(G, pre + name + ".0.weight", dw); _acc(G, pre + name + ".0.bias", db)
+        outs.append(dxi)
+    dd = dd + outs[0]
+    d_act = outs[2] / np.maximum(np.abs(tp["act_raw"]), dt(1.0))
+    return outs[1], dd, d_act
+
+
+def observe_bwd(c: Cfg, P, tapes, d_stochs, d_deters, d_logits):
+    """Reverse-time backward of observe().  Returns (param grads dict, d_embed, d_init_stoch, d_init_deter)."""
+    T = len(tapes)
+    B = tapes[0]["deter_in"].shape[0]
+    G = {}
+    d_embed = np.zeros((B, T, c.E), d_deters.dtype)
+    g_z = np.zeros((B, c.S, c.K), d_deters.dtype)
+    g_d = np.zeros((B, c.D), d_deters.dtype)
+    for t in reversed(range(T)):
+        tp = tapes[t]
+        g_z = g_z + d_stochs[:, t]
+        g_d = g_d + d_deters[:, t]
+        g_l = d_logits[:, t] + sample_bwd(g_z, tp["logit"], tp["y"], c.unimix)
+        dxe = mlp_logits_bwd(g_l.reshape(B, -1), P, G, tp["obs_acts"], tp["obs_last_in"], "_obs_net.obs_net_",
+                             "_obs_net.obs_net_n_", "_obs_net.obs_net_logit")
+        g_d = g_d + dxe[:, :c.D]
+        d_embed[:, t] = dxe[:, c.D:]
+        dz, dd, _ = deter_step_bwd(c, P, G, tp, g_d)
+        keep = (~tp["reset"])[:, None].astype(dd.dtype)
+        g_z = (dz * keep).reshape(B, c.S, c.K)
+        g_d = dd * keep
+    for k, shp in rssm_param_shapes(c).items():
+        if k not in G:
+            G[k] = np.zeros(shp, d_deters.dtype)
+    return G, d_embed, g_z, g_d
+
+
+def actor_bwd(c: Cfg, PA, tp, d_action):
+    """dgrad-only backward of actor_sample w.r.t. feat."""
+    dt = d_action.dtype.type
+    if c.act_kind == "cont":
+        std, tm, eps = tp["act_std"], tp["act_tm"], tp["act_noise"].astype(d_action.dtype)
+        dmean = d_action * (dt(1.0) - tm * tm)
+        dstd = d_action * eps
+        sg = (std - dt(c.min_std)) / dt(c.max_std - c.min_std)
+        dsraw = dstd * dt(c.max_std - c.min_std) * sg * (dt(1.0) - sg)
+        dout = np.concatenate([dmean, dsraw], -1)
+    else:
+        dout = sample_bwd(d_action, tp["act_out"], tp["act_y"], c.act_unimix)
+    feat = tp["feat"]
+    # recompute trunk activations
+    acts, x = [], feat
+    for i in range(c.actor_layers):
+        v = linear(x, PA[f"mlp.layers.actor_linear{i}.weight"], PA[f"mlp.layers.actor_linear{i}.bias"])
+        acts.append((x, v))
+        x = silu(rms_norm(v, PA[f"mlp.layers.actor_norm{i}.weight"]))
+    return mlp_logits_bwd(dout, {**PA}, None, acts, x, "mlp.layers.actor_linear", "mlp.layers.actor_norm", "last")
+
+
+def imagine_bwd(c: Cfg, P, PA, tapes, d_feats, d_actions):
+    """dgrad-only backward of imagine() (frozen weights): returns d_stoch0 (N,S,K), d_deter0 (N,D)."""
+    H = len(tapes)
+    N = d_feats.shape[0]
+    SK = c.SK
+    g_z = np.zeros((N, SK), d_feats.dtype)   # grad w.r.t. stoch entering step t+1 (output of img_step t)
+    g_d = np.zeros((N, c.D), d_feats.dtype)
+    for t in reversed(range(H)):
+        tp = tapes[t]
+        d_act = d_actions[:, t].copy()
+        if t < H - 1:
+            # g_z/g_d currently hold grads of (stoch_{t+1}, deter_{t+1}) = outputs of img_step at step t
+            g_l = sample_bwd(g_z.reshape(N, c.S, c.K), tp["logit"], tp["y"], c.unimix)
+            dd_img = mlp_logits_bwd(g_l.reshape(N, -1), P, None, tp["img_acts"], tp["img_last_in"], "_img_net.img_net_",
+                                    "_img_net.img_net_n_", "_img_net.img_net_logit")
+            dz, dd, da = deter_step_bwd(c, P, None, tp, g_d + dd_img)
+            d_act = d_act + da
+        else:
+            dz = np.zeros((N, SK), d_feats.dtype); dd = np.zeros((N, c.D), d_feats.dtype)
+        dfeat = actor_bwd(c, PA, tp, d_act) + d_feats[:, t]
+        g_z = dz + dfeat[:, :SK]
+        g_d = dd + dfeat[:, SK:]
+    return g_z.reshape(N, c.S, c.K), g_d

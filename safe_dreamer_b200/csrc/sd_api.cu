@@ -188,16 +188,16 @@ struct LinCall {  // one dense layer applied to (up to) two concatenated operand
   float* C; int ldc; int c_gstride;
 };
 
-template <int BN>
+template <int BN, int NST>
 static void launch_tc(Ctx& cx, const sd::tc::Batch& b, int ntiles_n, int R) {
-  using L = sd::tc::SmemLayout<BN>;
+  using L = sd::tc::SmemLayout<BN, NST>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<BN, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     attr_done = true;
   }
   dim3 grid(ntiles_n, (R + sd::tc::BM - 1) / sd::tc::BM, b.count);
-  sd::tc::gemm_bf16_tc_kernel<BN><<<grid, sd::tc::THREADS, L::kTotal, cx.st>>>(b);
+  sd::tc::gemm_bf16_tc_kernel<BN, NST><<<grid, sd::tc::THREADS, L::kTotal, cx.st>>>(b);
   cx.check("gemm_bf16_tc_kernel");
 }
 
@@ -231,8 +231,11 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
     tb.count = ntc;
     tb.R = R;
     // small-N problems: 64-wide tiles spread the work over more SMs; wide ones use 256.
-    if (batch_wide) launch_tc<256>(cx, tb, (max_n_tc + 255) / 256, R);
-    else launch_tc<64>(cx, tb, (max_n_tc + 63) / 64, R);
+    int max_kb = 0;
+    for (int i = 0; i < ntc; ++i) max_kb = tb.p[i].K / sd::tc::BK > max_kb ? tb.p[i].K / sd::tc::BK : max_kb;
+    if (batch_wide) launch_tc<256, 4>(cx, tb, (max_n_tc + 255) / 256, R);
+    else if (max_kb <= 4) launch_tc<64, 4>(cx, tb, (max_n_tc + 63) / 64, R);  // short K: 96 KB smem, 2 CTAs/SM
+    else launch_tc<64, 8>(cx, tb, (max_n_tc + 63) / 64, R);
     ntc = 0; nmaps = 0; max_n_tc = 0;
   };
   for (int ci = 0; ci < ncalls && !cx.err; ++ci) {
@@ -753,9 +756,15 @@ static void sample(Ctx& cx, int R, const float* lg, const float* u, int ld_u, fl
                    int ld_bf, float* logit_copy, int ld_c) {
   if (cx.err) return;
   sd_handle& h = *cx.h;
-  const int n = R * h.c.S;
-  sd::sample_kernel<<<(n + 127) / 128, 128, 0, cx.st>>>(lg, h.SK, u, ld_u, R, h.c.S, h.c.K, h.c.unimix, stoch, ld_o,
-                                                        stoch_bf, ld_bf, logit_copy, ld_c, nullptr);
+  const int K = h.c.K;
+  const int gs = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+  const long long n = (long long)R * h.c.S * gs;
+  const int blocks = (int)((n + 255) / 256);
+#define SD_SAMPLE(GS)                                                                                              \
+  sd::sample_kernel<GS><<<blocks, 256, 0, cx.st>>>(lg, h.SK, u, ld_u, R, h.c.S, K, h.c.unimix, stoch, ld_o, stoch_bf, \
+                                                   ld_bf, logit_copy, ld_c, nullptr)
+  if (gs == 8) SD_SAMPLE(8); else if (gs == 16) SD_SAMPLE(16); else SD_SAMPLE(32);
+#undef SD_SAMPLE
   cx.check("sample_kernel");
 }
 

@@ -40,7 +40,7 @@ struct GemmBatch {
   GemmP p[kMaxBatch];
 };
 
-constexpr int GB_KC = 512;           // K chunk staged in shared memory
+constexpr int GB_KC = 512;           // K chunk staged in shared memory (the i >> 9 fast path assumes 512)
 constexpr int GB_XLD = GB_KC + 4;    // padded row stride of the staged activations
 constexpr int GB_RLD = 16 * 16 + 4;  // padded stride of the split-K reduction buffer
 constexpr int GB_SMEM = (64 * GB_RLD > 16 * GB_XLD ? 64 * GB_RLD : 16 * GB_XLD) * 4;
@@ -61,13 +61,40 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
 
   for (int kc = 0; kc < p.K; kc += GB_KC) {
     const int kw = min(GB_KC, (p.K - kc + 3) & ~3);
-    for (int i = tid; i < 16 * kw; i += 256) {
-      const int r = i / kw, k = i - r * kw;
-      const int kk = kc + k, row = r0 + r;
-      float v = 0.f;
-      if (row < b.R && kk < p.K)
-        v = (kk < p.K1) ? p.A[(size_t)row * p.lda + kk] : p.A2[(size_t)row * p.lda2 + (kk - p.K1)];
-      xs[r * GB_XLD + k] = v;
+    // Issue every global load of this chunk before anything is stored to shared memory: the weight
+    // quads of this thread (8 x float4) and its share of the activation chunk (32 scalars).  Loads through
+    // generic pointers may alias shared memory as far as the compiler knows, so interleaving them with the
+    // shared stores would serialise one L2 round trip per element; this way a chunk costs one round trip.
+    float4 w[GB_KC / 4 / 64][4];
+#pragma unroll
+    for (int i = 0; i < GB_KC / 4 / 64; ++i) {
+      const int kbase = kc + (ty + 64 * i) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kbase + j;
+        w[i][j] = (k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + n0 + tx * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int i = j * 256 + tid;
+      v[j] = 0.f;
+      if (i < 16 * kw) {
+        const int r = (kw == GB_KC) ? (i >> 9) : i / kw, k = i - r * kw;
+        const int kk = kc + k, row = r0 + r;
+        if (row < b.R && kk < p.K)
+          v[j] = (kk < p.K1) ? __ldg(p.A + (size_t)row * p.lda + kk) : __ldg(p.A2 + (size_t)row * p.lda2 + (kk - p.K1));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int i = j * 256 + tid;
+      if (i < 16 * kw) {
+        const int r = (kw == GB_KC) ? (i >> 9) : i / kw, k = i - r * kw;
+        xs[r * GB_XLD + k] = v[j];
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -75,24 +102,17 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
       const int kq = ty + 64 * i;
       const int kbase = kc + kq * 4;
       if (kq * 4 < kw) {
-        float4 w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = kbase + j;
-          w[j] = (k < p.K) ? *reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + n0 + tx * 4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const float4 x = *reinterpret_cast<const float4*>(xs + r * GB_XLD + kq * 4);
-          acc[r][0] = fmaf(x.x, w[0].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[0].y, acc[r][1]);
-          acc[r][2] = fmaf(x.x, w[0].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[0].w, acc[r][3]);
-          acc[r][0] = fmaf(x.y, w[1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[1].y, acc[r][1]);
-          acc[r][2] = fmaf(x.y, w[1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[1].w, acc[r][3]);
-          acc[r][0] = fmaf(x.z, w[2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[2].y, acc[r][1]);
-          acc[r][2] = fmaf(x.z, w[2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[2].w, acc[r][3]);
-          acc[r][0] = fmaf(x.w, w[3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[3].y, acc[r][1]);
-          acc[r][2] = fmaf(x.w, w[3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[3].w, acc[r][3]);
+          acc[r][0] = fmaf(x.x, w[i][0].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[i][0].y, acc[r][1]);
+          acc[r][2] = fmaf(x.x, w[i][0].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[i][0].w, acc[r][3]);
+          acc[r][0] = fmaf(x.y, w[i][1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[i][1].y, acc[r][1]);
+          acc[r][2] = fmaf(x.y, w[i][1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[i][1].w, acc[r][3]);
+          acc[r][0] = fmaf(x.z, w[i][2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[i][2].y, acc[r][1]);
+          acc[r][2] = fmaf(x.z, w[i][2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[i][2].w, acc[r][3]);
+          acc[r][0] = fmaf(x.w, w[i][3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[i][3].y, acc[r][1]);
+          acc[r][2] = fmaf(x.w, w[i][3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[i][3].w, acc[r][3]);
         }
       }
     }
@@ -329,32 +349,76 @@ __device__ __forceinline__ int sample_category(const float* lg, const float* u, 
   return best;
 }
 
+// Lane-per-class variant of sample_category for the hot kernels: the group of `GS` lanes (GS = pow2 >= K)
+// that shares a category reduces with shuffles.  Same operation sequence per element as above.
+template <int GS>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int GS>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// returns the first-max class index of y = softmax(l + g) for this lane's category (valid on all lanes)
+template <int GS>
+__device__ __forceinline__ int sample_group(float lg, float u, bool valid, int k, int K, float unimix, float* y_out) {
+  const float NEG = -INFINITY;
+  const float m = group_max<GS>(valid ? lg : NEG);
+  float e = valid ? expf(lg - m) : 0.f;
+  const float s = group_sum<GS>(e);
+  float l = valid ? logf((e / s) * (1.f - unimix) + unimix / (float)K) : NEG;
+  const float m2 = group_max<GS>(l);
+  const float s2 = group_sum<GS>(valid ? expf(l - m2) : 0.f);
+  const float lse = m2 + logf(s2);
+  float z = valid ? (l - lse) + (-logf(-logf(u))) : NEG;
+  const float m3 = group_max<GS>(z);
+  const float ez = valid ? expf(z - m3) : 0.f;
+  const float s3 = group_sum<GS>(ez);
+  const float y = valid ? ez / s3 : NEG;
+  if (y_out) *y_out = y;
+  // arg-first-max over the group: max value, ties -> smallest index
+  float bv = y;
+  int bi = valid ? k : 0x7fffffff;
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  return bi;
+}
+
 // Sample all S categories of R rows.  logits (R, S*K) row stride ld_l; u (R, S*K) row stride ld_u.
 // Writes exact one-hot fp32 (row stride ld_o), optional bf16 copy, optional copy of the logits
-// (the `logits` output of observe) and the indices.
+// (the `logits` output of observe) and the indices.  One lane per class.
+template <int GS>
 __global__ void sample_kernel(const float* __restrict__ logits, int ld_l, const float* __restrict__ u, int ld_u,
                               int R, int S, int K, float unimix, float* stoch, int ld_o, __nv_bfloat16* stoch_bf,
                               int ld_bf, float* logit_copy, int ld_c, int* idx_out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * S) return;
-  const size_t row = i / S;
-  const int s = i - (int)row * S;
-  float lg[32], uu[32];
-  const float* lp = logits + row * ld_l + s * K;
-  const float* up = u + row * ld_u + s * K;
-#pragma unroll
-  for (int k = 0; k < 32; ++k)
-    if (k < K) { lg[k] = lp[k]; uu[k] = up[k]; }
-  const int best = sample_category(lg, uu, K, unimix, nullptr);
-  if (idx_out) idx_out[i] = best;
-#pragma unroll
-  for (int k = 0; k < 32; ++k)
-    if (k < K) {
-      const float v = (k == best) ? 1.f : 0.f;
-      if (stoch) stoch[row * ld_o + s * K + k] = v;
-      if (stoch_bf) stoch_bf[row * ld_bf + s * K + k] = __float2bfloat16(v);
-      if (logit_copy) logit_copy[row * ld_c + s * K + k] = lg[k];
-    }
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long cat = t / GS;          // (row, s)
+  const int k = (int)(t % GS);
+  const bool in_range = cat < (long long)R * S;
+  const size_t row = in_range ? (size_t)(cat / S) : 0;
+  const int sidx = in_range ? (int)(cat - (long long)row * S) : 0;
+  const bool valid = in_range && k < K;
+  float lg = 0.f, uu = 0.5f;
+  if (valid) {
+    lg = logits[row * ld_l + sidx * K + k];
+    uu = u[row * ld_u + sidx * K + k];
+  }
+  const int best = sample_group<GS>(lg, uu, valid, k, K, unimix, nullptr);
+  if (valid) {
+    const float v = (k == best) ? 1.f : 0.f;
+    if (stoch) stoch[row * ld_o + sidx * K + k] = v;
+    if (stoch_bf) stoch_bf[row * ld_bf + sidx * K + k] = __float2bfloat16(v);
+    if (logit_copy) logit_copy[row * ld_c + sidx * K + k] = lg;
+    if (idx_out && k == 0) idx_out[cat] = best;
+  }
 }
 
 // obs_step prologue (rssm.py:161-165 + :44): zero stoch/deter/action where is_first, normalise the

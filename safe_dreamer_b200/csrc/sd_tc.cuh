@@ -26,7 +26,6 @@ namespace tc {
 
 constexpr int BM = 128;      // UMMA M (rows of the output tile == TMEM lanes)
 constexpr int BK = 64;       // K elements per stage: 64 bf16 = 128 B = one swizzle atom row
-constexpr int STAGES = 4;
 constexpr int THREADS = 192;
 constexpr int kMaxProblems = 8;
 constexpr int kMaxMaps = 12;
@@ -119,19 +118,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int BN>
+template <int BN, int NSTAGES>
 struct SmemLayout {
+  static constexpr int STAGES = NSTAGES;  // skinny-N, long-K tiles are latency bound: deeper TMA ring
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStage = kABytes + kBBytes;
   static constexpr int kBarOff = STAGES * kStage;
-  static constexpr int kTotal = kBarOff + 128 + 1024;  // barriers + tmem slot, + 1 KB alignment slack
+  static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + tmem slot, + 1 KB alignment slack
 };
 
-template <int BN>
+template <int BN, int NSTAGES>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ Batch batch) {
   static_assert(BN == 64 || BN == 128 || BN == 256, "TMEM allocation must be a power of two >= 32 columns");
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, NSTAGES>;
+  constexpr int STAGES = L::STAGES;
   const Problem& pr = batch.p[blockIdx.z];
   const int n0 = blockIdx.x * BN;
   if (n0 >= pr.N) return;  // whole CTA exits before any barrier/TMEM use
