@@ -153,12 +153,14 @@ def run_gpu(args):
     g = torch.Generator(device="cpu").manual_seed(100 + rank)   # each rank scans its own replay slice
     emb_np = emb_np + 0.01 * torch.randn(emb_np.shape, generator=g).numpy().astype(np.float32) * (rank > 0)
     cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
-    embed, action, reset, u, ui, noise = cu(emb_np), cu(act_np), cu(rst_np), cu(u_np), cu(ui_np), cu(nz_np)
+    embed, action, reset, u, ui, noise = cu(emb_np), cu(act_np), cu(rst_np.astype(np.uint8)), cu(u_np), cu(ui_np), cu(nz_np)
     s0 = torch.zeros(B, c.S, c.K, device=dev)
     d0 = torch.zeros(B, c.D, device=dev)
     feats = torch.empty(N, H, c.F, device=dev)
     actions = torch.empty(N, H, c.A, device=dev)
     outs = tuple(torch.empty(N, H, 1, device=dev) for _ in range(5)) + (torch.empty(N, H - 1, 1, device=dev),)
+    obs_out = (torch.empty(B, T, c.S, c.K, device=dev), torch.empty(B, T, c.D, device=dev), torch.empty(B, T, c.S, c.K, device=dev))
+    eng.static_outputs = True
     disc = 1 - 1 / c.horizon
     GRAPH, BF16, TAPE = 4, 1, 2
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -170,7 +172,7 @@ def run_gpu(args):
         wgrads = {n: torch.zeros(P["rssm"][n].shape, device=dev) for n in eng.weight_names(0)}
 
     def hot_path():
-        st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | (TAPE if have_bwd else 0))
+        st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | (TAPE if have_bwd else 0), out=obs_out)
         if have_bwd:
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
             if world > 1:   # DP: one bucketed all-reduce of the RSSM weight grads, overlapped with imagination
@@ -209,15 +211,15 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     # dominant kernel sequence: the imagination scan alone (CUDA events on the launching stream)
-    st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH)
+    st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out)
     st, dt = st.reshape(N, c.S, c.K), dt.reshape(N, c.D)
     ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions)), args.steps)
-    ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH), args.steps)
+    ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out), args.steps)
     ms_heads = timed(lambda: eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs), args.steps)
     ms_obs_fb = None
     if have_bwd:
         def fb():
-            eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | TAPE)
+            eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | TAPE, out=obs_out)
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
         ms_obs_fb = timed(fb, args.steps)
     # ---- end-to-end through the public module API with HOST buffers (pinned) and a D2H result read
@@ -237,7 +239,7 @@ def run_gpu(args):
         m.load_state_dict({k: cu(v) for k, v in P[key].items()})
         heads[key] = m
     dreamer_ops.attach_heads(rssm, **heads)
-    rssm.use_graph, rssm.auto_refresh = True, False
+    rssm.use_graph, rssm.auto_refresh, rssm.static_outputs = True, False, True
     rssm.max_rows, rssm.max_steps = N, max(T, H)
     h_embed = torch.from_numpy(emb_np).pin_memory()
     h_action = torch.from_numpy(act_np).pin_memory()

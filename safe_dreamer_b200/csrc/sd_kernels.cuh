@@ -76,26 +76,26 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    // activation chunk: thread `tid` owns columns tid and tid+256 of all 16 rows (coalesced per row).
+    // The K segment (A or A2) depends on the column only, so it is resolved once per half.
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int i = j * 256 + tid;
-      v[j] = 0.f;
-      if (i < 16 * kw) {
-        const int r = (kw == GB_KC) ? (i >> 9) : i / kw, k = i - r * kw;
-        const int kk = kc + k, row = r0 + r;
-        if (row < b.R && kk < p.K)
-          v[j] = (kk < p.K1) ? __ldg(p.A + (size_t)row * p.lda + kk) : __ldg(p.A2 + (size_t)row * p.lda2 + (kk - p.K1));
+    for (int hf = 0; hf < 2; ++hf) {
+      const int kk = kc + hf * 256 + tid;
+      const bool in1 = kk < p.K1;
+      const float* src = in1 ? p.A + kk : p.A2 + (kk - p.K1);
+      const size_t ld = in1 ? p.lda : p.lda2;
+      const bool kok = kk < p.K;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int row = r0 + r;
+        v[r * 2 + hf] = (kok && row < b.R) ? __ldg(src + (size_t)row * ld) : 0.f;
       }
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int i = j * 256 + tid;
-      if (i < 16 * kw) {
-        const int r = (kw == GB_KC) ? (i >> 9) : i / kw, k = i - r * kw;
-        xs[r * GB_XLD + k] = v[j];
-      }
-    }
+    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+      for (int r = 0; r < 16; ++r) xs[r * GB_XLD + hf * 256 + tid] = v[r * 2 + hf];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < GB_KC / 4 / 64; ++i) {

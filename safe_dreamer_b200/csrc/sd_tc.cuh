@@ -68,6 +68,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: ~seconds of polling, then trap (turns a protocol bug into an error, never a hang).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 26); ++i)
     if (mbar_try_wait(bar, parity)) return;
   __trap();

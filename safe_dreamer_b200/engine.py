@@ -50,6 +50,11 @@ class Engine:
             _lib.check(self.lib.sd_create(C.byref(self.cfg), C.byref(h)), "sd_create")
         self.h = h
         self._keep = {}
+        # static_outputs=True: outputs live in engine-owned buffers that the next call of the same entry
+        # point and shape overwrites.  Pointer-stable outputs keep the CUDA-graph cache (keyed on pointers)
+        # hot; with fresh tensors per call the cache only hits when the allocator returns the same blocks.
+        self.static_outputs = False
+        self._outs = {}
 
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
@@ -87,18 +92,28 @@ class Engine:
         _lib.check(self.lib.sd_set_weights(self.h, module, arr, len(ts), self.stream), "sd_set_weights")
         self._keep[module] = ts  # keep sources alive until the async repack has been enqueued and run
 
-    def _new(self, *shape):
+    def _new(self, *shape, tag=None):
+        if self.static_outputs and tag is not None:
+            key = (tag, tuple(shape))
+            t = self._outs.get(key)
+            if t is None:
+                t = self._outs[key] = torch.empty(*shape, dtype=torch.float32, device=self.device)
+            return t
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ entry points
-    def observe(self, embed, action, init_stoch, init_deter, is_first, u, flags=0):
+    def observe(self, embed, action, init_stoch, init_deter, is_first, u, flags=0, out=None):
         B, T = action.shape[:2]
         embed, action, u = _f32c(embed, "embed"), _f32c(action, "action"), _f32c(u, "u")
         init_stoch, init_deter = _f32c(init_stoch, "init_stoch"), _f32c(init_deter, "init_deter")
         first = is_first.reshape(B, T).to(torch.uint8).contiguous()
         c = self.cfg
         assert embed.shape == (B, T, c.E) and action.shape == (B, T, c.A) and u.numel() == B * T * self.SK
-        stochs, deters, logits = self._new(B, T, c.S, c.K), self._new(B, T, c.D), self._new(B, T, c.S, c.K)
+        if out is not None:
+            stochs, deters, logits = out
+        else:
+            stochs, deters, logits = (self._new(B, T, c.S, c.K, tag="obs_s"), self._new(B, T, c.D, tag="obs_d"),
+                                      self._new(B, T, c.S, c.K, tag="obs_l"))
         _lib.check(self.lib.sd_observe_fwd(self.h, B, T, _ptr(embed), _ptr(action), _ptr(init_stoch), _ptr(init_deter),
                                            _ptr(first), _ptr(u), _ptr(stochs), _ptr(deters), _ptr(logits), flags,
                                            self.stream), "sd_observe_fwd")
@@ -110,9 +125,9 @@ class Engine:
         ds = None if d_stochs is None else _f32c(d_stochs, "d_stochs")
         dd = None if d_deters is None else _f32c(d_deters, "d_deters")
         dl = None if d_logits is None else _f32c(d_logits, "d_logits")
-        d_embed = self._new(B, T, c.E) if want_embed else None
-        d_is = self._new(B, c.S, c.K) if want_init else None
-        d_id = self._new(B, c.D) if want_init else None
+        d_embed = self._new(B, T, c.E, tag="ob_de") if want_embed else None
+        d_is = self._new(B, c.S, c.K, tag="ob_dis") if want_init else None
+        d_id = self._new(B, c.D, tag="ob_did") if want_init else None
         if weight_grads is not None:
             names = self.weight_names(MOD_RSSM)
             arr = (C.c_void_p * len(names))(*[0 if weight_grads.get(n) is None else weight_grads[n].data_ptr()
@@ -152,7 +167,7 @@ class Engine:
         stoch0, deter0, u, act_noise = (_f32c(stoch0, "stoch0"), _f32c(deter0, "deter0"), _f32c(u, "u"),
                                         _f32c(act_noise, "act_noise"))
         assert u.numel() == N * H * self.SK and act_noise.numel() == N * H * c.A
-        feats, actions = out if out is not None else (self._new(N, H, self.F), self._new(N, H, c.A))
+        feats, actions = out if out is not None else (self._new(N, H, self.F, tag="im_f"), self._new(N, H, c.A, tag="im_a"))
         _lib.check(self.lib.sd_imagine_fwd(self.h, N, H, _ptr(stoch0), _ptr(deter0), _ptr(u), _ptr(act_noise),
                                            _ptr(feats), _ptr(actions), flags, self.stream), "sd_imagine_fwd")
         return feats, actions
@@ -170,9 +185,9 @@ class Engine:
         N, H = feats.shape[:2]
         feats = _f32c(feats, "feats")
         if out is None:
-            rew, cont, val, wgt = (self._new(N, H, 1) for _ in range(4))
-            sval = self._new(N, H, 1) if slow else None
-            ret = self._new(N, H - 1, 1)
+            rew, cont, val, wgt = (self._new(N, H, 1, tag=f"hl{i}") for i in range(4))
+            sval = self._new(N, H, 1, tag="hl_sv") if slow else None
+            ret = self._new(N, H - 1, 1, tag="hl_ret")
         else:
             rew, cont, val, sval, wgt, ret = out
         _lib.check(self.lib.sd_heads_lambda_fwd(self.h, N, H, _ptr(feats), float(disc), float(lamb), _ptr(rew),

@@ -174,6 +174,7 @@ class RSSM(nn.Module):
         self.precision = "fp32"        # "bf16" => tcgen05 path when rows >= 128
         self.use_graph = False         # replay scans as cached CUDA graphs
         self.auto_refresh = True       # repack weights on every call (safe with in-place optimizers)
+        self.static_outputs = False    # reuse engine-owned output buffers (next same-shape call overwrites them)
         self.noise_source = None       # callable(shape, device) -> uniforms, for injected-noise parity
         self.max_rows, self.max_steps = 1024, 64
         self.head_modules = {}         # module id -> nn.Module (actor / reward / cont / value / slow value)
@@ -200,6 +201,7 @@ class RSSM(nn.Module):
             rt.engine = _engine.Engine(max_rows=max(need[0], 1), max_steps=max(need[1], 1), max_tape_rows=need[2],
                                        device=next(self.parameters()).device, **kw)
             rt.limits, rt.sig = need, None
+        rt.engine.static_outputs = self.static_outputs
         self.refresh_weights(force=False)
         return rt.engine
 
