@@ -17,6 +17,7 @@
 
 #include "../../include/safedreamer.h"
 #include "sd_kernels.cuh"
+#include "sd_bwd.cuh"
 #include "sd_tc.cuh"
 
 using bf16 = __nv_bfloat16;
@@ -83,7 +84,18 @@ struct StepBufs {
   float* vobs[4];
   float* o[4];
   float *va[4], *ao[4], *aout;  // actor pre-activations / activations / last-layer output
+  float *dnew, *emb, *keep, *feat, *act;  // tape only: deter' / embed_t / 1-is_first / imagination feat + action
   size_t stride;                 // floats between consecutive steps (0 = reuse)
+};
+
+// Gradients produced by the reverse scan and consumed by the batched weight-gradient pass (one slot per
+// taped row-step), plus per-step temporaries of the backward.
+struct BwdBufs {
+  float *d_lg, *d_q, *d_hpre, *d_vin, *dmn_h, *dmn_in;
+  float* d_v[4];    // grads of the obs/img/actor pre-norm activations
+  float* dmn_v[4];
+  // temporaries (one step)
+  float *t_do, *t_dxe, *gd, *dd, *t_dh, *t_dxin, *dx, *t_din0, *t_dz, *carry_z, *carry_d, *d_abar, *t_dfeat, *t_daout;
 };
 
 struct GraphEntry {
@@ -105,6 +117,8 @@ struct sd_handle {
   // activations
   StepBufs sb;        // non-taped (max_rows)
   StepBufs tape;      // taped (max_tape_rows x max_steps)
+  BwdBufs bw;
+  int tape_kind = 0;  // 1 = observe, 2 = imagine
   int tape_B = 0, tape_T = 0;
   bool tape_valid = false;
   // bf16 staging for the tcgen05 path
@@ -358,6 +372,42 @@ static void alloc_stepbufs(Arena& a, StepBufs& sb, const sd_handle& h, size_t ro
     sb.ao[i] = (with_actor && i < c.actor_layers) ? a.take<float>(n * c.units) : nullptr;
   }
   sb.aout = with_actor ? a.take<float>(n * up(h.act_out, 4)) : nullptr;
+  const bool tp = steps > 1;
+  sb.dnew = tp ? a.take<float>(n * c.D) : nullptr;
+  sb.emb = tp ? a.take<float>(n * c.E) : nullptr;
+  sb.keep = a.take<float>(n);
+  sb.feat = tp ? a.take<float>(n * h.F) : nullptr;
+  sb.act = tp ? a.take<float>(n * c.A) : nullptr;
+}
+
+static void alloc_bwd(Arena& a, BwdBufs& b, const sd_handle& h, size_t rows, size_t steps) {
+  const sd_config& c = h.c;
+  const size_t n = rows * steps;
+  const int U = c.U > c.units ? c.U : c.units;
+  b.d_lg = a.take<float>(n * h.SK);
+  b.d_q = a.take<float>(n * 3 * c.D);
+  b.d_hpre = a.take<float>(n * c.D);
+  b.d_vin = a.take<float>(n * 3 * c.U);
+  b.dmn_h = a.take<float>(n * c.D);
+  b.dmn_in = a.take<float>(n * 3 * c.U);
+  for (int i = 0; i < 4; ++i) {
+    b.d_v[i] = a.take<float>(n * U);
+    b.dmn_v[i] = a.take<float>(n * U);
+  }
+  b.t_do = a.take<float>(rows * U);
+  b.t_dxe = a.take<float>(rows * (size_t)(c.D + c.E > h.F ? c.D + c.E : h.F));
+  b.gd = a.take<float>(rows * c.D);
+  b.dd = a.take<float>(rows * c.D);
+  b.t_dh = a.take<float>(rows * c.D);
+  b.t_dxin = a.take<float>(rows * (size_t)c.G * (h.Dg + 3 * c.U));
+  b.dx = a.take<float>(rows * 3 * c.U);
+  b.t_din0 = a.take<float>(rows * c.D);
+  b.t_dz = a.take<float>(rows * h.SK);
+  b.carry_z = a.take<float>(rows * h.SK);
+  b.carry_d = a.take<float>(rows * c.D);
+  b.d_abar = a.take<float>(rows * c.A);
+  b.t_dfeat = a.take<float>(rows * h.F);
+  b.t_daout = a.take<float>(rows * up(h.act_out, 4));
 }
 
 static void layout(sd_handle& h, Arena& a) {
@@ -384,7 +434,10 @@ static void layout(sd_handle& h, Arena& a) {
   h.bins = a.take<float>(c.bins);
   const size_t R = c.max_rows, T = c.max_steps;
   alloc_stepbufs(a, h.sb, h, R, 1, true);
-  if (c.max_tape_rows > 0) alloc_stepbufs(a, h.tape, h, c.max_tape_rows, T, true);
+  if (c.max_tape_rows > 0) {
+    alloc_stepbufs(a, h.tape, h, c.max_tape_rows, T > 1 ? T : 2, true);
+    alloc_bwd(a, h.bw, h, c.max_tape_rows, T > 1 ? T : 2);
+  }
   h.feat_bf = a.take<bf16>(R * F);
   h.x_bf = a.take<bf16>(R * 3 * c.U);
   h.h_bf = a.take<bf16>(R * c.D);
@@ -702,6 +755,11 @@ static StepBufs at_step(const StepBufs& s, size_t t, size_t rows, const sd_handl
     if (r.ao[i]) r.ao[i] += o * c.units;
   }
   if (r.aout) r.aout += o * up(h.act_out, 4);
+  if (r.dnew) r.dnew += o * c.D;
+  if (r.emb) r.emb += o * c.E;
+  if (r.keep) r.keep += o;
+  if (r.feat) r.feat += o * h.F;
+  if (r.act) r.act += o * c.A;
   return r;
 }
 
@@ -816,7 +874,8 @@ extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, co
       const float* pd = t == 0 ? init_deter : deters + (size_t)(t - 1) * D;
       const int lds = t == 0 ? SK : T * SK, ldd = t == 0 ? D : T * D;
       sd::prep_obs_kernel<<<grid1d((long long)B * (SK + D + A), 256), 256, 0, cx.st>>>(
-          ps, lds, pd, ldd, action + (size_t)t * A, T * A, is_first + t, T, B, SK, D, A, sb.zin, sb.din, sb.ain);
+          ps, lds, pd, ldd, action + (size_t)t * A, T * A, is_first + t, T, B, SK, D, A, sb.zin, sb.din, sb.ain,
+          sb.keep, nullptr);
       cx.check("prep_obs_kernel");
       if (cx.tc) {
         cast_bf(cx, sb.zin, SK, h->feat_bf, h->F, B, SK);
@@ -834,8 +893,14 @@ extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, co
              logits + (size_t)t * SK, T * SK);
       if (tape) copy_f32(cx, u + (size_t)t * SK, T * SK, sb.ucopy, SK, B, SK);
     }
+    if (tape && !cx.err) {  // deter' and embed in step-major layout for the batched weight-gradient pass
+      sd::bt_to_tb_kernel<<<grid1d((long long)B * T * D, 256), 256, 0, cx.st>>>(deters, h->tape.dnew, B, T, D);
+      cx.check("bt_to_tb_kernel");
+      sd::bt_to_tb_kernel<<<grid1d((long long)B * T * E, 256), 256, 0, cx.st>>>(embed, h->tape.emb, B, T, E);
+      cx.check("bt_to_tb_kernel");
+    }
   });
-  if (rc == 0 && tape) { h->tape_valid = true; h->tape_B = B; h->tape_T = T; }
+  if (rc == 0 && tape) { h->tape_valid = true; h->tape_B = B; h->tape_T = T; h->tape_kind = 1; }
   return rc;
 }
 
@@ -884,7 +949,8 @@ extern "C" int sd_imagine_with_action(sd_handle* h, int R, int T, const float* s
       const float* pd = t == 0 ? deter : deters + (size_t)(t - 1) * D;
       const int lds = t == 0 ? SK : T * SK, ldd = t == 0 ? D : T * D;
       sd::prep_obs_kernel<<<grid1d((long long)R * (SK + D + A), 256), 256, 0, cx.st>>>(
-          ps, lds, pd, ldd, actions + (size_t)t * A, T * A, nullptr, 0, R, SK, D, A, sb.zin, sb.din, sb.ain);
+          ps, lds, pd, ldd, actions + (size_t)t * A, T * A, nullptr, 0, R, SK, D, A, sb.zin, sb.din, sb.ain, nullptr,
+          nullptr);
       cx.check("prep_obs_kernel");
       if (cx.tc) {
         cast_bf(cx, sb.zin, SK, h->feat_bf, h->F, R, SK);
@@ -966,12 +1032,216 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
   });
 }
 
+// ------------------------------------------------------------------------------------------------ backward pieces
+static void normact_bwd(Ctx& cx, int R, const sd::NormActBwdP* ps, int n) {
+  if (cx.err) return;
+  sd::NormActBwdBatch b;
+  b.count = n;
+  for (int i = 0; i < n; ++i) b.p[i] = ps[i];
+  sd::normact_bwd_kernel<<<dim3(R, n), 256, 0, cx.st>>>(b);
+  cx.check("normact_bwd_kernel");
+}
+static sd::NormActBwdP nbp(const float* dout, int ld_dout, const float* v, int ld_v, const float* w, int width, float* dv,
+                           int ld_dv, float* dmn, int ld_dmn) {
+  sd::NormActBwdP p;
+  p.dout = dout; p.ld_dout = ld_dout; p.v = v; p.ld_v = ld_v; p.w = w; p.dv = dv; p.ld_dv = ld_dv; p.dmn = dmn;
+  p.ld_dmn = ld_dmn; p.width = width;
+  return p;
+}
+// dx[R x K] = dy[R x N] * W[N x K] with the k-contiguous fp32 copy (per block g: column offsets via gstride).
+static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, int dy_gstride, float* dx, int ld_dx,
+                  int dx_gstride) {
+  if (cx.err) return;
+  sd::GemmBatch gb;
+  memset(&gb, 0, sizeof(gb));
+  gb.R = R;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
+    attr_done = true;
+  }
+  for (int g = 0; g < L.G; ++g) {
+    sd::GemmP& p = gb.p[gb.count++];
+    p.A = dy + (size_t)g * dy_gstride; p.lda = ld_dy; p.A2 = nullptr; p.lda2 = 0;
+    p.K1 = L.N; p.K = L.N;
+    p.Wt = L.wn + (size_t)g * L.N * L.ldk; p.ldw = L.ldk;
+    p.bias = nullptr;
+    p.C = dx + (size_t)g * dx_gstride; p.ldc = ld_dx; p.N = L.K;
+  }
+  dim3 grid((L.K + 15) / 16, (R + 15) / 16, gb.count);
+  sd::gemm_f32_kernel<<<grid, 256, sd::GB_SMEM, cx.st>>>(gb);
+  cx.check("gemm_f32_kernel(dgrad)");
+}
+template <int GS>
+static void launch_sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
+                              const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
+                              float* d_logit, int ld_d) {
+  const long long n = (long long)R * S * GS;
+  sd::sample_bwd_kernel<GS><<<(int)((n + 255) / 256), 256, 0, cx.st>>>(lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul,
+                                                                       R, S, K, unimix, d_logit, ld_d);
+}
+static void sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
+                       const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
+                       float* d_logit, int ld_d) {
+  if (cx.err) return;
+  if (K <= 8) launch_sample_bwd<8>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d);
+  else if (K <= 16) launch_sample_bwd<16>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d);
+  else launch_sample_bwd<32>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d);
+  cx.check("sample_bwd_kernel");
+}
+// Backward of latent_logits: d(logits) -> d(layer-0 input) [R x K0] in `dx0`; fills the d-tape slots.
+static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, const LinearW* layers,
+                              int nl, const LinearW& last, const float* d_lg, float* dx0) {
+  sd_handle& h = *cx.h;
+  const int U = h.c.U;
+  dgrad(cx, R, last, d_lg, h.SK, 0, bw.t_do, U, 0);
+  for (int i = nl - 1; i >= 0; --i) {
+    float* dv = bw.d_v[i] + slot * U;
+    sd::NormActBwdP p = nbp(bw.t_do, U, sb.vobs[i], U, layers[i].gain, U, dv, U, bw.dmn_v[i] + slot * U, U);
+    normact_bwd(cx, R, &p, 1);
+    if (i > 0) dgrad(cx, R, layers[i], dv, U, 0, bw.t_do, U, 0);
+    else dgrad(cx, R, layers[0], dv, U, 0, dx0, layers[0].K, 0);
+  }
+}
+// Backward of deter_core given g = d(deter') in bw.gd: leaves d(deter_in) parts in bw.dd (+ bw.t_din0),
+// d(stoch) in bw.t_dz and, when want_act, d(abar) in bw.d_abar.
+static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, bool want_act) {
+  sd_handle& h = *cx.h;
+  const sd_config& c = h.c;
+  const int U = c.U, D = c.D, Dg = h.Dg, Kb = Dg + 3 * U;
+  float* d_q = bw.d_q + slot * 3 * D;
+  float* d_hpre = bw.d_hpre + slot * D;
+  float* d_vin = bw.d_vin + slot * 3 * U;
+  if (cx.err) return;
+  sd::gates_bwd_kernel<<<grid1d((long long)R * D, 256), 256, 0, cx.st>>>(bw.gd, D, sb.q, sb.din, D, d_q, bw.dd, R, D, Dg);
+  cx.check("gates_bwd_kernel");
+  dgrad(cx, R, h.gru, d_q, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
+  sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D);
+  normact_bwd(cx, R, &ph, 1);
+  dgrad(cx, R, h.hid, d_hpre, D, Dg, bw.t_dxin, c.G * Kb, Kb);
+  if (cx.err) return;
+  sd::hid_reduce_kernel<<<grid1d((long long)R * (D + 3 * U), 256), 256, 0, cx.st>>>(bw.t_dxin, bw.dd, bw.dx, R, c.G, Dg, 3 * U);
+  cx.check("hid_reduce_kernel");
+  sd::NormActBwdP pin[3];
+  const float* gains[3] = {h.in0.gain, h.in1.gain, h.in2.gain};
+  for (int j = 0; j < 3; ++j)
+    pin[j] = nbp(bw.dx + j * U, 3 * U, sb.vin + j * U, 3 * U, gains[j], U, d_vin + j * U, 3 * U,
+                 bw.dmn_in + slot * 3 * U + j * U, 3 * U);
+  normact_bwd(cx, R, pin, 3);
+  dgrad(cx, R, h.in0, d_vin, 3 * U, 0, bw.t_din0, D, 0);
+  dgrad(cx, R, h.in1, d_vin + U, 3 * U, 0, bw.t_dz, h.SK, 0);
+  if (want_act) dgrad(cx, R, h.in2, d_vin + 2 * U, 3 * U, 0, bw.d_abar, c.A, 0);
+}
+
+static void wgrad_run(Ctx& cx, int R, sd::WgradBatch& wb, int max_n, int max_k) {
+  if (cx.err || wb.count == 0) return;
+  wb.R = R;
+  dim3 grid((max_n + 63) / 64, (max_k + 63) / 64, wb.count);
+  sd::wgrad_f32_kernel<<<grid, 256, 0, cx.st>>>(wb);
+  cx.check("wgrad_f32_kernel");
+  wb.count = 0;
+}
+// dW (+)= dY^T [X | X2] for a Linear (reference layout (N,K)) or the G blocks of a BlockLinear ((O/G, I/G, G)).
+static void wgrad_linear(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride,
+                         const float* X, int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* dW) {
+  if (!dW || cx.err) return;
+  sd::WgradBatch wb;
+  memset(&wb, 0, sizeof(wb));
+  for (int g = 0; g < L.G; ++g) {
+    sd::WgradP& p = wb.p[wb.count++];
+    p.dY = dY + (size_t)g * dy_gstride; p.ldy = ldy;
+    p.X = X + (size_t)g * x_gstride; p.ldx = ldx;
+    p.X2 = X2; p.ldx2 = ldx2;
+    p.K1 = K1; p.K = L.K; p.N = L.N;
+    p.dW = dW + (block ? g : 0);
+    p.sn = block ? (long long)L.K * L.G : L.K;
+    p.sk = block ? L.G : 1;
+  }
+  wgrad_run(cx, R, wb, L.N, L.K);
+}
+static void colsum(Ctx& cx, const float* in, int ld, int R, int W, float* out) {
+  if (!out || cx.err) return;
+  sd::colsum_kernel<<<(W + 127) / 128, 128, 0, cx.st>>>(in, ld, R, W, out);
+  cx.check("colsum_kernel");
+}
+
+extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs, const float* d_deters,
+                              const float* d_logits, float* d_embed, float* d_init_stoch, float* d_init_deter,
+                              float* const* wg, uint32_t flags, void* stream) {
+  if (!h) return fail(SD_ERR_INVALID, "sd_observe_bwd: null handle");
+  if (!h->tape_valid || h->tape_kind != 1 || h->tape_B != B || h->tape_T != T)
+    return fail(SD_ERR_NO_TAPE, "sd_observe_bwd: no matching SD_FLAG_SAVE_TAPE sd_observe_fwd(B=%d,T=%d)", B, T);
+  const sd_config& c = h->c;
+  const int SK = h->SK, D = c.D, E = c.E, U = c.U;
+  Key key;
+  key.add(11).add(B).add(T).add(d_stochs).add(d_deters).add(d_logits).add(d_embed).add(d_init_stoch).add(d_init_deter).add(flags);
+  const int nw = (int)h->wdesc[SD_MOD_RSSM].size();
+  for (int i = 0; i < nw; ++i) key.add(wg ? wg[i] : nullptr);
+  std::vector<float*> W(nw, nullptr);
+  if (wg) for (int i = 0; i < nw; ++i) W[i] = wg[i];
+  return run(h, key.v, flags, (cudaStream_t)stream, false, [&](Ctx& cx) {
+    const BwdBufs& bw = h->bw;
+    StepBufs base = h->tape;
+    base.stride = 1;
+    cudaMemsetAsync(bw.carry_z, 0, (size_t)B * SK * sizeof(float), cx.st);
+    cudaMemsetAsync(bw.carry_d, 0, (size_t)B * D * sizeof(float), cx.st);
+    for (int t = T - 1; t >= 0 && !cx.err; --t) {
+      StepBufs sb = at_step(base, t, B, *h);
+      const size_t slot = (size_t)t * B;
+      float* d_lg = bw.d_lg + slot * SK;
+      sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, d_stochs ? d_stochs + (size_t)t * SK : nullptr, T * SK,
+                 d_logits ? d_logits + (size_t)t * SK : nullptr, T * SK, B, c.S, c.K, c.unimix, d_lg, SK);
+      latent_logits_bwd(cx, sb, bw, slot, B, h->obs, c.obs_layers, h->obs_logit, d_lg, bw.t_dxe);
+      if (cx.err) return;
+      sd::obs_combine_kernel<<<grid1d((long long)B * (D + E), 256), 256, 0, cx.st>>>(
+          bw.carry_d, d_deters ? d_deters + (size_t)t * D : nullptr, T * D, bw.t_dxe, B, D, E, bw.gd,
+          d_embed ? d_embed + (size_t)t * E : nullptr, T * E);
+      cx.check("obs_combine_kernel");
+      deter_core_bwd(cx, sb, bw, slot, B, false);
+      if (cx.err) return;
+      // reset cut (rssm.py:161-165): carry = d(step inputs) * (1 - is_first)
+      sd::carry_kernel<<<grid1d((long long)B * (SK + D), 256), 256, 0, cx.st>>>(bw.dd, bw.t_din0, bw.t_dz, sb.keep, nullptr,
+                                                                              0, B, SK, D, bw.carry_z, bw.carry_d);
+      cx.check("carry_kernel");
+    }
+    if (cx.err) return;
+    if (d_init_stoch) cudaMemcpyAsync(d_init_stoch, bw.carry_z, (size_t)B * SK * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+    if (d_init_deter) cudaMemcpyAsync(d_init_deter, bw.carry_d, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+    if (!wg) return;
+    // ---- weight gradients: one contraction over all T*B taped row-steps per layer (fixed order)
+    const int RT = B * T;
+    const StepBufs& tp = h->tape;
+    const int Dg = h->Dg;
+    int i = 0;
+    wgrad_linear(cx, RT, h->in0, false, bw.d_vin, 3 * U, 0, tp.din, D, 0, D, nullptr, 0, W[0]);
+    colsum(cx, bw.d_vin, 3 * U, RT, U, W[1]);
+    colsum(cx, bw.dmn_in, 3 * U, RT, U, W[2]);
+    wgrad_linear(cx, RT, h->in1, false, bw.d_vin + U, 3 * U, 0, tp.zin, SK, 0, SK, nullptr, 0, W[3]);
+    colsum(cx, bw.d_vin + U, 3 * U, RT, U, W[4]);
+    colsum(cx, bw.dmn_in + U, 3 * U, RT, U, W[5]);
+    wgrad_linear(cx, RT, h->in2, false, bw.d_vin + 2 * U, 3 * U, 0, tp.ain, c.A, 0, c.A, nullptr, 0, W[6]);
+    colsum(cx, bw.d_vin + 2 * U, 3 * U, RT, U, W[7]);
+    colsum(cx, bw.dmn_in + 2 * U, 3 * U, RT, U, W[8]);
+    wgrad_linear(cx, RT, h->hid, true, bw.d_hpre, D, Dg, tp.din, D, Dg, Dg, tp.x, 3 * U, W[9]);
+    colsum(cx, bw.d_hpre, D, RT, D, W[10]);
+    colsum(cx, bw.dmn_h, D, RT, D, W[11]);
+    wgrad_linear(cx, RT, h->gru, true, bw.d_q, 3 * D, 3 * Dg, tp.h, D, Dg, Dg, nullptr, 0, W[12]);
+    colsum(cx, bw.d_q, 3 * D, RT, 3 * D, W[13]);
+    i = 14;
+    for (int l = 0; l < c.obs_layers; ++l, i += 3) {
+      if (l == 0) wgrad_linear(cx, RT, h->obs[0], false, bw.d_v[0], U, 0, tp.dnew, D, 0, D, tp.emb, E, W[i]);
+      else wgrad_linear(cx, RT, h->obs[l], false, bw.d_v[l], U, 0, tp.o[l - 1], U, 0, U, nullptr, 0, W[i]);
+      colsum(cx, bw.d_v[l], U, RT, U, W[i + 1]);
+      colsum(cx, bw.dmn_v[l], U, RT, U, W[i + 2]);
+    }
+    wgrad_linear(cx, RT, h->obs_logit, false, bw.d_lg, SK, 0, tp.o[c.obs_layers - 1], U, 0, U, nullptr, 0, W[i]);
+    colsum(cx, bw.d_lg, SK, RT, SK, W[i + 1]);
+    // _img_net takes no part in observe(): its gradient slots are left untouched.
+  });
+}
+
 extern "C" int sd_imagine_bwd(sd_handle*, int, int, const float*, const float*, float*, float*, uint32_t, void*) {
   return fail(SD_ERR_INVALID, "sd_imagine_bwd: not implemented in this build");
-}
-extern "C" int sd_observe_bwd(sd_handle*, int, int, const float*, const float*, const float*, float*, float*, float*,
-                              float* const*, uint32_t, void*) {
-  return fail(SD_ERR_INVALID, "sd_observe_bwd: not implemented in this build");
 }
 
 // ------------------------------------------------------------------------------------------------ heads + returns

@@ -1,0 +1,242 @@
+// sd_bwd.cuh -- row-wise kernels of the reverse-time backward scans (K2: observe, K4: imagine).
+//
+// Math: SURVEY.md Appendix A (checked there against autograd in fp64); restated in
+// oracle/rssm_oracle.py:{normact_bwd, sample_bwd, deter_step_bwd} which the tests compare against.
+// Dense transposes (dgrad) reuse gemm_f32_kernel with the k-contiguous weight copy; weight gradients are
+// ONE batched contraction over all T*B rows after the scan (wgrad_f32_kernel), fed by the per-step
+// "d-tape" these kernels write.  All reductions have a fixed order (deterministic gradients).
+#pragma once
+#include "sd_kernels.cuh"
+
+namespace sd {
+
+// d(out)/d(v) of out = SiLU(RMSNorm_width(v) * w)  (networks.py:325-327 / rssm.py:16-31).
+//   dv   = rho * (dn - n * mean(dn * n)),  dn = dm * w,  dm = dout * silu'(m),  m = n * w,  n = v * rho
+//   dmn  = dm * n  (per-row contribution to the RMS scale gradient; column-summed after the scan)
+struct NormActBwdP {
+  const float* dout; int ld_dout;  // grad w.r.t. the activation output
+  const float* v;    int ld_v;     // saved pre-norm values
+  const float* w;                  // [width]
+  float* dv;  int ld_dv;
+  float* dmn; int ld_dmn;          // nullable (dgrad-only)
+  int width;
+};
+struct NormActBwdBatch {
+  int count;
+  NormActBwdP p[4];
+};
+__global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch b) {
+  __shared__ float sh[32];
+  const NormActBwdP& p = b.p[blockIdx.y];
+  const size_t row = blockIdx.x;
+  const float* v = p.v + row * p.ld_v;
+  const float* dout = p.dout + row * p.ld_dout;
+  float vv[8], dn[8], nn[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    vv[i] = (c < p.width) ? v[c] : 0.f;
+    ss = fmaf(vv[i], vv[i], ss);
+  }
+  ss = block_sum(ss, sh);
+  const float rho = 1.f / sqrtf(ss / (float)p.width + kRmsEps);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    dn[i] = 0.f; nn[i] = 0.f;
+    if (c < p.width) {
+      const float w = p.w[c];
+      const float n = vv[i] * rho;
+      const float m = n * w;
+      const float sg = sigmoidf_(m);
+      const float dm = dout[c] * (sg * (1.f + m * (1.f - sg)));
+      if (p.dmn) p.dmn[row * p.ld_dmn + c] = dm * n;
+      nn[i] = n;
+      dn[i] = dm * w;
+      dot = fmaf(dn[i], n, dot);
+    }
+  }
+  dot = block_sum(dot, sh) / (float)p.width;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < p.width) p.dv[row * p.ld_dv + c] = rho * (dn[i] - nn[i] * dot);
+  }
+}
+
+// Backward of the straight-through unimix Gumbel sample w.r.t. the raw logits (oracle: sample_bwd),
+// recomputing p = softmax(logit) and y = softmax(l + g) from the saved logits and uniforms.
+//   gz = carry (+ upstream): grad w.r.t. the sampled one-hot;  d_logit = upstream_logit + p*(dp - <dp,p>)
+template <int GS>
+__global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, const float* __restrict__ u, int ld_u,
+                                  const float* __restrict__ gz_a, int ld_a, const float* __restrict__ gz_b, int ld_b,
+                                  const float* __restrict__ up_logit, int ld_ul, int R, int S, int K, float unimix,
+                                  float* d_logit, int ld_d) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long cat = t / GS;
+  const int k = (int)(t % GS);
+  const bool in_range = cat < (long long)R * S;
+  const size_t row = in_range ? (size_t)(cat / S) : 0;
+  const int sidx = in_range ? (int)(cat - (long long)row * S) : 0;
+  const bool valid = in_range && k < K;
+  const int col = sidx * K + k;
+  float lg = 0.f, uu = 0.5f, gz = 0.f;
+  if (valid) {
+    lg = logits[row * ld_l + col];
+    uu = u[row * ld_u + col];
+    if (gz_a) gz += gz_a[row * ld_a + col];
+    if (gz_b) gz += gz_b[row * ld_b + col];
+  }
+  float y;
+  (void)sample_group<GS>(lg, uu, valid, k, K, unimix, &y);
+  if (!valid) y = 0.f;
+  // dl = y * (gz - <gz, y>)
+  const float gy = group_sum<GS>(gz * y);
+  const float dl = y * (gz - gy);
+  // p, p~ (unimix), d(log p~) = dl - p~ * sum(dl), dp = d(log p~)/p~ * (1-unimix), d_logit = p*(dp - <dp,p>)
+  const float m = group_max<GS>(valid ? lg : -INFINITY);
+  const float e = valid ? expf(lg - m) : 0.f;
+  const float s = group_sum<GS>(e);
+  const float p = e / s;
+  const float pt = p * (1.f - unimix) + unimix / (float)K;
+  const float sdl = group_sum<GS>(dl);
+  const float dlp = dl - pt * sdl;
+  const float dp = valid ? dlp / pt * (1.f - unimix) : 0.f;
+  const float dpp = group_sum<GS>(dp * p);
+  if (valid) {
+    float out = p * (dp - dpp);
+    if (up_logit) out += up_logit[row * ld_ul + col];
+    d_logit[row * ld_d + col] = out;
+  }
+}
+
+// Backward of the GRU-style gates (rssm.py:63-75): given g = d(deter'), the saved gate pre-activations q
+// (R, 3D) [g][reset|cand|update][Dg] and the step's input deter, emit dq (same layout) and the direct
+// path dd = g * (1 - update).
+__global__ void gates_bwd_kernel(const float* __restrict__ g, int ld_g, const float* __restrict__ q,
+                                 const float* __restrict__ deter_in, int ld_in, float* dq, float* dd, int R, int D,
+                                 int Dg) {
+  const long long total = (long long)R * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const size_t row = (size_t)(i / D);
+    const int gi = d / Dg, o = d - gi * Dg;
+    const size_t qo = row * 3 * D + (size_t)gi * 3 * Dg + o;
+    const float r = q[qo], c = q[qo + Dg], uu = q[qo + 2 * Dg];
+    const float Rg = sigmoidf_(r), C = tanhf(Rg * c), Uu = sigmoidf_(uu - 1.f);
+    const float gd = g[row * ld_g + d];
+    const float dUu = gd * (C - deter_in[row * ld_in + d]);
+    const float dC = gd * Uu;
+    const float dtn = dC * (1.f - C * C);
+    dq[qo] = (dtn * c) * Rg * (1.f - Rg);
+    dq[qo + Dg] = dtn * Rg;
+    dq[qo + 2 * Dg] = dUu * Uu * (1.f - Uu);
+    dd[row * D + d] = gd * (1.f - Uu);
+  }
+}
+
+// g_d(t) = carry + upstream d_deters[:, t] + d[deter'|embed][:, :D];  d_embed[:, t] = d[deter'|embed][:, D:].
+__global__ void obs_combine_kernel(const float* __restrict__ carry, const float* __restrict__ up, int ld_up,
+                                   const float* __restrict__ dxe, int R, int D, int E, float* gd, float* d_embed,
+                                   int ld_e) {
+  const int W = D + E;
+  const long long total = (long long)R * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const size_t row = (size_t)(i / W);
+    const int c = (int)(i - (long long)row * W);
+    const float v = dxe ? dxe[row * W + c] : 0.f;
+    if (c < D) {
+      gd[row * D + c] = carry[row * D + c] + (up ? up[row * ld_up + c] : 0.f) + v;
+    } else if (d_embed) {
+      d_embed[row * ld_e + (c - D)] = v;
+    }
+  }
+}
+
+// After the block dgrad of dyn_hid: dxin (R, G, Dg + 3U).  dd += dxin[:, g, :Dg];  dx = sum_g dxin[:, g, Dg:].
+__global__ void hid_reduce_kernel(const float* __restrict__ dxin, float* dd, float* dx, int R, int G, int Dg, int U3) {
+  const int W = G * Dg + U3;
+  const int Kb = Dg + U3;
+  const long long total = (long long)R * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const size_t row = (size_t)(i / W);
+    const int c = (int)(i - (long long)row * W);
+    const float* base = dxin + row * (size_t)G * Kb;
+    if (c < G * Dg) {
+      const int g = c / Dg, o = c - g * Dg;
+      dd[row * (size_t)(G * Dg) + c] += base[(size_t)g * Kb + o];
+    } else {
+      const int j = c - G * Dg;
+      float s = 0.f;
+      for (int g = 0; g < G; ++g) s += base[(size_t)g * Kb + Dg + j];
+      dx[row * U3 + j] = s;
+    }
+  }
+}
+
+// End of a reverse step: carry_d = (dd + d_din0) * keep, carry_z = dz * keep, keep = 1 - is_first saved by the
+// forward (rssm.py:161-165).
+// `extra_z/extra_d` (nullable) are added before masking (imagination: grads through the actor's feat input).
+__global__ void carry_kernel(const float* __restrict__ dd, const float* __restrict__ d_din0,
+                             const float* __restrict__ dz, const float* __restrict__ keep_mask,
+                             const float* __restrict__ extra, int ld_x, int R, int SK, int D, float* carry_z,
+                             float* carry_d) {
+  const int W = SK + D;
+  const long long total = (long long)R * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const size_t row = (size_t)(i / W);
+    const int c = (int)(i - (long long)row * W);
+    const float keep = keep_mask ? keep_mask[row] : 1.f;
+    const float ex = extra ? extra[row * ld_x + c] : 0.f;
+    if (c < SK) carry_z[row * SK + c] = ((dz ? dz[row * SK + c] : 0.f) + ex) * keep;
+    else {
+      const int d = c - SK;
+      carry_d[row * D + d] = ((dd ? dd[row * D + d] : 0.f) + (d_din0 ? d_din0[row * D + d] : 0.f) + ex) * keep;
+    }
+  }
+}
+
+// out[c] (+)= sum_r in[r][c]: fixed-order column sums for bias / RMS-scale gradients.
+// One thread per column (coalesced across the warp), rows summed sequentially => deterministic.
+__global__ void colsum_kernel(const float* __restrict__ in, int ld, int R, int W, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= W) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = 0;
+  for (; r + 4 <= R; r += 4) {
+    s0 += in[(size_t)r * ld + c];
+    s1 += in[(size_t)(r + 1) * ld + c];
+    s2 += in[(size_t)(r + 2) * ld + c];
+    s3 += in[(size_t)(r + 3) * ld + c];
+  }
+  for (; r < R; ++r) s0 += in[(size_t)r * ld + c];
+  out[c] += (s0 + s1) + (s2 + s3);
+}
+
+// Backward of the bounded-normal actor sample (distributions.py:217-222): action = tanh(mean) + std*eps,
+// std = (max-min)*sigmoid(sraw+2)+min.  d_act = upstream + d(abar)/max(|a|,1) (rssm.py:44, detached clip).
+__global__ void actor_sample_bwd_kernel(const float* __restrict__ out, const float* __restrict__ eps, int ld_n,
+                                        const float* __restrict__ action, int ld_act, const float* __restrict__ d_up,
+                                        int ld_up, const float* __restrict__ d_abar, int R, int A, float min_std,
+                                        float max_std, float* d_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * A) return;
+  const size_t row = i / A;
+  const int a = i - (int)row * A;
+  const float act = action[row * ld_act + a];
+  float da = d_up ? d_up[row * ld_up + a] : 0.f;
+  if (d_abar) da += d_abar[row * A + a] / fmaxf(fabsf(act), 1.f);
+  const float mean = out[row * 2 * A + a], sraw = out[row * 2 * A + A + a];
+  const float tm = tanhf(mean);
+  const float sg = sigmoidf_(sraw + 2.f);
+  d_out[row * 2 * A + a] = da * (1.f - tm * tm);
+  d_out[row * 2 * A + A + a] = da * eps[row * ld_n + a] * (max_std - min_std) * sg * (1.f - sg);
+}
+
+}  // namespace sd

@@ -425,7 +425,8 @@ __global__ void sample_kernel(const float* __restrict__ logits, int ld_l, const 
 // action magnitude, and stage the three step inputs contiguously (they are also the backward tape).
 __global__ void prep_obs_kernel(const float* __restrict__ stoch, int ld_s, const float* __restrict__ deter, int ld_d,
                                 const float* __restrict__ action, int ld_a, const uint8_t* __restrict__ is_first,
-                                int ld_f, int R, int SK, int D, int A, float* zin, float* din, float* ain) {
+                                int ld_f, int R, int SK, int D, int A, float* zin, float* din, float* ain,
+                                float* keep_out, float* araw_out) {
   const int W = SK + D + A;
   const long long total = (long long)R * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -433,6 +434,7 @@ __global__ void prep_obs_kernel(const float* __restrict__ stoch, int ld_s, const
     const size_t row = (size_t)(i / W);
     const int c = (int)(i - (long long)row * W);
     const bool rs = is_first ? (is_first[row * ld_f] != 0) : false;
+    if (c == 0 && keep_out) keep_out[row] = rs ? 0.f : 1.f;
     if (c < SK) {
       zin[row * SK + c] = rs ? 0.f : stoch[row * ld_s + c];
     } else if (c < SK + D) {
@@ -442,7 +444,20 @@ __global__ void prep_obs_kernel(const float* __restrict__ stoch, int ld_s, const
       const int a = c - SK - D;
       const float v = rs ? 0.f : action[row * ld_a + a];
       ain[row * A + a] = v / fmaxf(fabsf(v), 1.f);
+      if (araw_out) araw_out[row * A + a] = v;
     }
+  }
+}
+
+// (B, T, W) -> (T, B, W): puts user-layout tensors into the step-major tape layout.
+__global__ void bt_to_tb_kernel(const float* __restrict__ in, float* out, int B, int T, int W) {
+  const long long total = (long long)B * T * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const long long bt = i / W;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    out[((size_t)t * B + b) * W + w] = in[i];
   }
 }
 
