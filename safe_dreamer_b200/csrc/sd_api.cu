@@ -990,14 +990,17 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
   if (int e = check_rows(h, "sd_imagine_fwd", N, H)) return e;
   if (!stoch0 || !deter0 || !u || !act_noise || !feats || !actions) return fail(SD_ERR_INVALID, "sd_imagine_fwd: null tensor");
   if (!h->rssm_set || !h->heads[SD_MOD_ACTOR].set) return fail(SD_ERR_WEIGHTS, "sd_imagine_fwd: RSSM/actor weights not set");
-  if (flags & SD_FLAG_SAVE_TAPE) return fail(SD_ERR_INVALID, "sd_imagine_fwd: tape (backward) not available yet");
+  const bool tape = flags & SD_FLAG_SAVE_TAPE;
+  if (tape && N > h->c.max_tape_rows) return fail(SD_ERR_WORKSPACE, "sd_imagine_fwd: N=%d > max_tape_rows=%d", N, h->c.max_tape_rows);
+  if (tape) h->tape_valid = false;
   const sd_config& c = h->c;
   const int SK = h->SK, D = c.D, A = c.A, F = h->F;
   const bool tc = (flags & SD_FLAG_BF16) && N >= 128;
   Key key;
   key.add(4).add(N).add(H).add(stoch0).add(deter0).add(u).add(act_noise).add(feats).add(actions).add(flags);
-  return run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
-    const StepBufs& sb = h->sb;
+  int rc = run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
+    StepBufs base = tape ? h->tape : h->sb;
+    base.stride = tape ? 1 : 0;
     const HeadW& actor = h->heads[SD_MOD_ACTOR];
     const int ldf = H * F;
     // feats[:, 0] = [stoch0 | deter0] (rssm.py:211-217)
@@ -1005,6 +1008,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     copy_f32(cx, deter0, D, feats + SK, ldf, N, D);
     if (cx.tc) cast_bf(cx, feats, ldf, h->feat_bf, F, N, F);
     for (int t = 0; t < H && !cx.err; ++t) {
+      const StepBufs sb = at_step(base, t, N, *h);
       float* ft = feats + (size_t)t * F;
       Operand feat = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
       // action = actor(feat).rsample() (dreamer.py:684)
@@ -1016,6 +1020,13 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
                                                                     c.act_unimix, act_noise + (size_t)t * A, H * A,
                                                                     actions + (size_t)t * A, H * A, h->abar);
         cx.check("actor_sample_kernel");
+      }
+      if (tape) {  // what the dgrad-only backward needs beyond the pre-activations: deter_t, action_t, noise_t
+        copy_f32(cx, ft, ldf, sb.feat, F, N, F);
+        copy_f32(cx, actions + (size_t)t * A, H * A, sb.act, A, N, A);
+        copy_f32(cx, act_noise + (size_t)t * A, H * A, sb.emb, A, N, A);
+        copy_f32(cx, h->abar, A, sb.ain, A, N, A);
+        if (t < H - 1) copy_f32(cx, u + (size_t)t * SK, H * SK, sb.ucopy, SK, N, SK);
       }
       // stoch, deter = img_step(stoch, deter, action) (dreamer.py:688).  The H-th img_step result is
       // dropped by the reference and nothing downstream consumes it, so it is not computed.
@@ -1030,6 +1041,8 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
       sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, cx.tc ? h->feat_bf : nullptr, F, nullptr, 0);
     }
   });
+  if (rc == 0 && tape) { h->tape_valid = true; h->tape_B = N; h->tape_T = H; h->tape_kind = 2; }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ backward pieces
@@ -1105,7 +1118,8 @@ static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, si
 }
 // Backward of deter_core given g = d(deter') in bw.gd: leaves d(deter_in) parts in bw.dd (+ bw.t_din0),
 // d(stoch) in bw.t_dz and, when want_act, d(abar) in bw.d_abar.
-static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, bool want_act) {
+static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, bool want_act,
+                           const float* deter_in, int ld_in) {
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
   const int U = c.U, D = c.D, Dg = h.Dg, Kb = Dg + 3 * U;
@@ -1113,7 +1127,7 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   float* d_hpre = bw.d_hpre + slot * D;
   float* d_vin = bw.d_vin + slot * 3 * U;
   if (cx.err) return;
-  sd::gates_bwd_kernel<<<grid1d((long long)R * D, 256), 256, 0, cx.st>>>(bw.gd, D, sb.q, sb.din, D, d_q, bw.dd, R, D, Dg);
+  sd::gates_bwd_kernel<<<grid1d((long long)R * D, 256), 256, 0, cx.st>>>(bw.gd, D, sb.q, deter_in, ld_in, d_q, bw.dd, R, D, Dg);
   cx.check("gates_bwd_kernel");
   dgrad(cx, R, h.gru, d_q, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
   sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D);
@@ -1197,11 +1211,11 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
           bw.carry_d, d_deters ? d_deters + (size_t)t * D : nullptr, T * D, bw.t_dxe, B, D, E, bw.gd,
           d_embed ? d_embed + (size_t)t * E : nullptr, T * E);
       cx.check("obs_combine_kernel");
-      deter_core_bwd(cx, sb, bw, slot, B, false);
+      deter_core_bwd(cx, sb, bw, slot, B, false, sb.din, D);
       if (cx.err) return;
       // reset cut (rssm.py:161-165): carry = d(step inputs) * (1 - is_first)
       sd::carry_kernel<<<grid1d((long long)B * (SK + D), 256), 256, 0, cx.st>>>(bw.dd, bw.t_din0, bw.t_dz, sb.keep, nullptr,
-                                                                              0, B, SK, D, bw.carry_z, bw.carry_d);
+                                                                              0, nullptr, 0, B, SK, D, bw.carry_z, bw.carry_d);
       cx.check("carry_kernel");
     }
     if (cx.err) return;
@@ -1240,8 +1254,73 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
   });
 }
 
-extern "C" int sd_imagine_bwd(sd_handle*, int, int, const float*, const float*, float*, float*, uint32_t, void*) {
-  return fail(SD_ERR_INVALID, "sd_imagine_bwd: not implemented in this build");
+// dgrad of an MLPHead trunk + last layer (frozen weights): d(last-layer output) -> d(feat) [R x F].
+static void head_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, int R, const HeadW& hw, const float* d_out, int ld_o,
+                     float* d_feat, int F) {
+  sd_handle& h = *cx.h;
+  const int units = h.c.units;
+  dgrad(cx, R, hw.last, d_out, ld_o, 0, bw.t_do, units, 0);
+  for (int i = hw.layers - 1; i >= 0; --i) {
+    sd::NormActBwdP p = nbp(bw.t_do, units, sb.va[i], units, hw.l[i].gain, units, bw.d_v[0], units, nullptr, 0);
+    normact_bwd(cx, R, &p, 1);
+    if (i > 0) dgrad(cx, R, hw.l[i], bw.d_v[0], units, 0, bw.t_do, units, 0);
+    else dgrad(cx, R, hw.l[0], bw.d_v[0], units, 0, d_feat, F, 0);
+  }
+}
+
+extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, const float* d_actions,
+                              float* d_stoch0, float* d_deter0, uint32_t flags, void* stream) {
+  if (!h) return fail(SD_ERR_INVALID, "sd_imagine_bwd: null handle");
+  if (!h->tape_valid || h->tape_kind != 2 || h->tape_B != N || h->tape_T != H)
+    return fail(SD_ERR_NO_TAPE, "sd_imagine_bwd: no matching SD_FLAG_SAVE_TAPE sd_imagine_fwd(N=%d,H=%d)", N, H);
+  if (!d_stoch0 || !d_deter0) return fail(SD_ERR_INVALID, "sd_imagine_bwd: null output");
+  const sd_config& c = h->c;
+  const int SK = h->SK, D = c.D, A = c.A, F = h->F;
+  Key key;
+  key.add(12).add(N).add(H).add(d_feats).add(d_actions).add(d_stoch0).add(d_deter0).add(flags);
+  return run(h, key.v, flags, (cudaStream_t)stream, false, [&](Ctx& cx) {
+    const BwdBufs& bw = h->bw;
+    StepBufs base = h->tape;
+    base.stride = 1;
+    const HeadW& actor = h->heads[SD_MOD_ACTOR];
+    cudaMemsetAsync(bw.carry_z, 0, (size_t)N * SK * sizeof(float), cx.st);
+    cudaMemsetAsync(bw.carry_d, 0, (size_t)N * D * sizeof(float), cx.st);
+    for (int t = H - 1; t >= 0 && !cx.err; --t) {
+      const StepBufs sb = at_step(base, t, N, *h);
+      const bool stepped = t < H - 1;  // the H-th img_step is never computed (dreamer.py:688 result dropped)
+      if (stepped) {
+        // carry = grads of (stoch_{t+1}, deter_{t+1}), the outputs of img_step at step t
+        sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, nullptr, 0, nullptr, 0, N, c.S, c.K, c.unimix, bw.d_lg, SK);
+        latent_logits_bwd(cx, sb, bw, 0, N, h->img, c.img_layers, h->img_logit, bw.d_lg, bw.t_dxe);
+        if (cx.err) return;
+        sd::obs_combine_kernel<<<grid1d((long long)N * D, 256), 256, 0, cx.st>>>(bw.carry_d, nullptr, 0, bw.t_dxe, N, D, 0,
+                                                                               bw.gd, nullptr, 0);
+        cx.check("obs_combine_kernel");
+        deter_core_bwd(cx, sb, bw, 0, N, true, sb.feat + SK, F);
+        if (cx.err) return;
+      }
+      // through action = actor(feat_t).rsample()
+      const float* d_up = d_actions ? d_actions + (size_t)t * A : nullptr;
+      if (c.act_kind == 0) {
+        sd::actor_sample_bwd_kernel<<<(N * A + 127) / 128, 128, 0, cx.st>>>(sb.aout, sb.emb, A, sb.act, A, d_up, H * A,
+                                                                            stepped ? bw.d_abar : nullptr, N, A, c.min_std,
+                                                                            c.max_std, bw.t_daout);
+        cx.check("actor_sample_bwd_kernel");
+      } else {
+        sample_bwd(cx, sb.aout, A, sb.emb, A, d_up, H * A, stepped ? bw.d_abar : nullptr, A, nullptr, 0, N, 1, A,
+                   c.act_unimix, bw.t_daout, A);
+      }
+      head_bwd(cx, sb, bw, N, actor, bw.t_daout, h->act_out, bw.t_dfeat, F);
+      if (cx.err) return;
+      sd::carry_kernel<<<grid1d((long long)N * F, 256), 256, 0, cx.st>>>(
+          stepped ? bw.dd : nullptr, stepped ? bw.t_din0 : nullptr, stepped ? bw.t_dz : nullptr, nullptr, bw.t_dfeat, F,
+          d_feats ? d_feats + (size_t)t * F : nullptr, H * F, N, SK, D, bw.carry_z, bw.carry_d);
+      cx.check("carry_kernel");
+    }
+    if (cx.err) return;
+    cudaMemcpyAsync(d_stoch0, bw.carry_z, (size_t)N * SK * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+    cudaMemcpyAsync(d_deter0, bw.carry_d, (size_t)N * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ heads + returns

@@ -184,8 +184,8 @@ __global__ void hid_reduce_kernel(const float* __restrict__ dxin, float* dd, flo
 // `extra_z/extra_d` (nullable) are added before masking (imagination: grads through the actor's feat input).
 __global__ void carry_kernel(const float* __restrict__ dd, const float* __restrict__ d_din0,
                              const float* __restrict__ dz, const float* __restrict__ keep_mask,
-                             const float* __restrict__ extra, int ld_x, int R, int SK, int D, float* carry_z,
-                             float* carry_d) {
+                             const float* __restrict__ extra, int ld_x, const float* __restrict__ extra2, int ld_x2,
+                             int R, int SK, int D, float* carry_z, float* carry_d) {
   const int W = SK + D;
   const long long total = (long long)R * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -193,7 +193,7 @@ __global__ void carry_kernel(const float* __restrict__ dd, const float* __restri
     const size_t row = (size_t)(i / W);
     const int c = (int)(i - (long long)row * W);
     const float keep = keep_mask ? keep_mask[row] : 1.f;
-    const float ex = extra ? extra[row * ld_x + c] : 0.f;
+    const float ex = (extra ? extra[row * ld_x + c] : 0.f) + (extra2 ? extra2[row * ld_x2 + c] : 0.f);
     if (c < SK) carry_z[row * SK + c] = ((dz ? dz[row * SK + c] : 0.f) + ex) * keep;
     else {
       const int d = c - SK;

@@ -87,3 +87,25 @@ def test_module_autograd_matches_reference_grads():
             continue
         np.testing.assert_allclose(_np(p.grad), z["bwd_g/" + name], rtol=3e-3,
                                    atol=3e-5 * max(1.0, float(z["bwd_gn/" + name])), err_msg=name)
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_imagine_bwd(tag):
+    """dgrad-only backward through the imagination rollout (frozen weights; the attack shape)."""
+    c, z = load_golden(tag)
+    P = golden_params(c, z)
+    N, H = int(z["N"]), int(z["H"])
+    eng = make_engine(c, P, max_rows=16, max_steps=8, max_tape_rows=8)
+    st0, dt0, u, noise = O.synth_imagine_inputs(c, N, H, seed=3)
+    g2 = np.random.Generator(np.random.Philox(17))
+    c_f = g2.standard_normal((N, H, c.F), dtype=np.float32) * np.float32(0.1)
+    c_a = g2.standard_normal((N, H, c.A), dtype=np.float32)
+    for flags in (0, 4, 4):
+        feats, acts = eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=2 | flags)
+        ds, dd = eng.imagine_bwd(N, H, cu(c_f), cu(c_a), flags=flags)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(_np(feats)[..., c.SK:], z["imag_deter"], atol=5e-5, rtol=0)
+        np.testing.assert_allclose(_np(ds), z["imag_bwd_d_stoch"], rtol=3e-3, atol=3e-5)
+        np.testing.assert_allclose(_np(dd), z["imag_bwd_d_deter"], rtol=3e-3, atol=3e-5)
+    with pytest.raises(RuntimeError, match="SAVE_TAPE"):
+        eng.imagine_bwd(N, H + 1, cu(c_f), cu(c_a))
