@@ -169,19 +169,21 @@ def run_gpu(args):
         gst = torch.randn(B, T, c.S, c.K, device=dev) * 0.01
         gdt = torch.randn(B, T, c.D, device=dev) * 0.01
         glg = torch.randn(B, T, c.S, c.K, device=dev) * 0.01
-        wgrads = {n: torch.zeros(P["rssm"][n].shape, device=dev) for n in eng.weight_names(0)}
+        from safe_dreamer_b200.parallel import GradBucket
+        bucket = GradBucket({n: P["rssm"][n].shape for n in eng.weight_names(0)}, dev)
+        wgrads = bucket.views
 
     def hot_path():
+        if have_bwd:
+            bucket.zero_()
         st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | (TAPE if have_bwd else 0), out=obs_out)
         if have_bwd:
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
-            if world > 1:   # DP: one bucketed all-reduce of the RSSM weight grads, overlapped with imagination
-                flat = torch.cat([w.reshape(-1) for w in wgrads.values()])
-                work = dist.all_reduce(flat, async_op=True)
+            bucket.allreduce_async()   # DP: ONE flat NCCL all-reduce of the RSSM grads, overlapped with imagination
         eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions))
         eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
-        if have_bwd and world > 1:
-            work.wait()
+        if have_bwd:
+            bucket.wait()
         return outs[-1]
 
     def timed(fn, iters, do_flush=True):
@@ -248,15 +250,29 @@ def run_gpu(args):
     h2d = sum(x.numel() * x.element_size() for x in (h_embed, h_action, h_first, h_s0, h_d0))
 
     def e2e_step():
-        with torch.no_grad():
-            e_, a_, f_ = h_embed.to(dev, non_blocking=True), h_action.to(dev, non_blocking=True), h_first.to(dev, non_blocking=True)
-            s_, d_ = h_s0.to(dev, non_blocking=True), h_d0.to(dev, non_blocking=True)
-            rssm.refresh_weights(force=True)            # weights change once per update in training
-            rssm.precision = "fp32"
+        e_, a_, f_ = h_embed.to(dev, non_blocking=True), h_action.to(dev, non_blocking=True), h_first.to(dev, non_blocking=True)
+        s_, d_ = h_s0.to(dev, non_blocking=True), h_d0.to(dev, non_blocking=True)
+        rssm.refresh_weights(force=True)            # weights change once per update in training
+        rssm.precision = "fp32"
+        work = None
+        if have_bwd:                                    # posterior fwd+bwd through autograd (sd_observe_bwd)
+            for p_ in rssm.parameters():
+                p_.grad = None
+            e_.requires_grad_(True)
             st_, dt_, lg_ = rssm.observe(e_, a_, (s_, d_), f_)
+            torch.autograd.backward((st_, dt_, lg_), (gst, gdt, glg))
+            if world > 1:
+                flat = torch.cat([p_.grad.reshape(-1) for p_ in rssm.parameters() if p_.grad is not None])
+                work = dist.all_reduce(flat, async_op=True)
+        else:
+            with torch.no_grad():
+                st_, dt_, lg_ = rssm.observe(e_, a_, (s_, d_), f_)
+        with torch.no_grad():
             rssm.precision = "bf16"
-            ft_, ac_ = dreamer_ops.imagine(rssm, (st_.reshape(N, c.S, c.K), dt_.reshape(N, c.D)), H)
+            ft_, ac_ = dreamer_ops.imagine(rssm, (st_.detach().reshape(N, c.S, c.K), dt_.detach().reshape(N, c.D)), H)
             r_ = dreamer_ops.heads_lambda(rssm, ft_, c.horizon, c.lamb)
+            if work is not None:
+                work.wait()
             return float(r_[-1].mean().item())           # D2H read of the step's result
 
     for _ in range(3):

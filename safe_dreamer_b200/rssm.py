@@ -192,7 +192,8 @@ class RSSM(nn.Module):
 
     def _get_engine(self, rows, steps, tape=False, extra=None):
         rt = self._rt
-        need = (max(rows, rt.limits[0]), max(steps, rt.limits[1]), max(rows if tape else 0, rt.limits[2]))
+        need = (max(rows, rt.limits[0], self.max_rows), max(steps, rt.limits[1], self.max_steps),
+                max(rows if tape else 0, rt.limits[2]))
         if rt.engine is None or need != rt.limits:
             kw = self.engine_dims()
             kw.update(getattr(self, "_head_dims", {}))
