@@ -141,6 +141,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     c = O.Cfg(E=E, A=A)

@@ -11,7 +11,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -177,6 +179,33 @@ struct Ctx {
   }
 };
 
+
+// Every kernel is launched with programmatic dependent launch (PDL) enabled: the kernels call
+// griddepcontrol.launch_dependents + griddepcontrol.wait first thing, so the next kernel's CTAs are
+// scheduled while the current one still runs and only its memory accesses wait for completion.  This hides
+// most of the ~3 us launch gap between the many small dependent kernels of a scan (also inside CUDA graphs,
+// where the edges become programmatic dependencies).  SD_PDL=0 disables it.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SD_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <class... KArgs, class... Args>
+static void launch_k(cudaStream_t st, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
 // An activation matrix: fp32 view and (tcgen05 path) bf16 view; gstride = per-block column offset.
 struct Operand {
   const float* f = nullptr; int ldf = 0;
@@ -211,7 +240,7 @@ static void launch_tc(Ctx& cx, const sd::tc::Batch& b, int ntiles_n, int R) {
     attr_done = true;
   }
   dim3 grid(ntiles_n, (R + sd::tc::BM - 1) / sd::tc::BM, b.count);
-  sd::tc::gemm_bf16_tc_kernel<BN, NST><<<grid, sd::tc::THREADS, L::kTotal, cx.st>>>(b);
+  launch_k(cx.st, sd::tc::gemm_bf16_tc_kernel<BN, NST>, dim3(grid), dim3(sd::tc::THREADS), L::kTotal, b);
   cx.check("gemm_bf16_tc_kernel");
 }
 
@@ -235,7 +264,7 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
       attr_done = true;
     }
     dim3 grid((max_n_f + 15) / 16, (R + 15) / 16, gb.count);
-    sd::gemm_f32_kernel<<<grid, 256, sd::GB_SMEM, cx.st>>>(gb);
+    launch_k(cx.st, sd::gemm_f32_kernel, dim3(grid), dim3(256), sd::GB_SMEM, gb);
     cx.check("gemm_f32_kernel");
     gb.count = 0;
     max_n_f = 0;
@@ -310,7 +339,7 @@ static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
   sd::NormActBatch b;
   b.count = n;
   for (int i = 0; i < n; ++i) b.p[i] = ps[i];
-  sd::normact_kernel<<<dim3(R, n), 256, 0, cx.st>>>(b);
+  launch_k(cx.st, sd::normact_kernel, dim3(dim3(R, n)), dim3(256), 0, b);
   cx.check("normact_kernel");
 }
 static sd::NormActP nap(const float* in, int ld_in, const float* w, int width, float* out, int ld_out, bf16* ob, int ld_bf) {
@@ -626,7 +655,7 @@ static void pack_linear(Ctx& cx, LinearW& L, const float* w, const float* bias, 
   const long long s_g = block_layout ? 1 : 0;
   const long long s_n = block_layout ? (long long)L.K * L.G : L.K;
   const long long s_k = block_layout ? L.G : 1;
-  sd::pack_weight_kernel<<<grid1d((long long)L.G * L.N * L.K, 256), 256, 0, cx.st>>>(
+  launch_k(cx.st, sd::pack_weight_kernel, dim3(grid1d((long long)L.G * L.N * L.K, 256)), dim3(256), 0, 
       w, L.G, L.N, L.K, s_g, s_n, s_k, L.wt, L.ldw, L.wn, L.ldk, L.w_bf, nullptr);
   cx.check("pack_weight_kernel");
   if (L.w_bf == nullptr) { /* K not a multiple of 64: SIMT only */ }
@@ -640,7 +669,7 @@ static void pack_linear_bf(Ctx& cx, LinearW& L, const float* w, bool block_layou
   const long long s_n = block_layout ? (long long)L.K * L.G : L.K;
   const long long s_k = block_layout ? L.G : 1;
   for (int g = 0; g < L.G; ++g) {
-    sd::pack_weight_kernel<<<grid1d((long long)L.N * L.K, 256), 256, 0, cx.st>>>(
+    launch_k(cx.st, sd::pack_weight_kernel, dim3(grid1d((long long)L.N * L.K, 256)), dim3(256), 0, 
         w + (block_layout ? g : 0), 1, L.N, L.K, 0, s_n, s_k, nullptr, 0, nullptr, L.K,
         L.w_bf + (size_t)g * L.npad * L.K, nullptr);
     cx.check("pack_weight_kernel(bf16)");
@@ -787,7 +816,7 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
   normact(cx, R, &nh, 1);
   linear(cx, R, h.gru, opfb(sb.h, D, cx.tc ? h.h_bf : nullptr, D, Dg), Dg, Operand(), sb.q, 3 * D, 3 * Dg);
   if (cx.err) return;
-  sd::gates_kernel<<<grid1d((long long)R * D, 256), 256, 0, cx.st>>>(sb.q, d.f, d.ldf, deter_out, ld_out, out_bf, ld_bf,
+  launch_k(cx.st, sd::gates_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, sb.q, d.f, d.ldf, deter_out, ld_out, out_bf, ld_bf,
                                                                   R, D, Dg);
   cx.check("gates_kernel");
 }
@@ -819,7 +848,7 @@ static void sample(Ctx& cx, int R, const float* lg, const float* u, int ld_u, fl
   const long long n = (long long)R * h.c.S * gs;
   const int blocks = (int)((n + 255) / 256);
 #define SD_SAMPLE(GS)                                                                                              \
-  sd::sample_kernel<GS><<<blocks, 256, 0, cx.st>>>(lg, h.SK, u, ld_u, R, h.c.S, K, h.c.unimix, stoch, ld_o, stoch_bf, \
+  launch_k(cx.st, sd::sample_kernel<GS>, dim3(blocks), dim3(256), 0, lg, h.SK, u, ld_u, R, h.c.S, K, h.c.unimix, stoch, ld_o, stoch_bf, \
                                                    ld_bf, logit_copy, ld_c, nullptr)
   if (gs == 8) SD_SAMPLE(8); else if (gs == 16) SD_SAMPLE(16); else SD_SAMPLE(32);
 #undef SD_SAMPLE
@@ -828,12 +857,12 @@ static void sample(Ctx& cx, int R, const float* lg, const float* u, int ld_u, fl
 
 static void cast_bf(Ctx& cx, const float* in, int ld_in, bf16* out, int ld_out, int R, int W) {
   if (cx.err) return;
-  sd::cast_bf16_kernel<<<grid1d((long long)R * W, 256), 256, 0, cx.st>>>(in, ld_in, out, ld_out, R, W);
+  launch_k(cx.st, sd::cast_bf16_kernel, dim3(grid1d((long long)R * W, 256)), dim3(256), 0, in, ld_in, out, ld_out, R, W);
   cx.check("cast_bf16_kernel");
 }
 static void copy_f32(Ctx& cx, const float* in, int ld_in, float* out, int ld_out, int R, int W) {
   if (cx.err) return;
-  sd::copy_f32_kernel<<<grid1d((long long)R * W, 256), 256, 0, cx.st>>>(in, ld_in, out, ld_out, R, W);
+  launch_k(cx.st, sd::copy_f32_kernel, dim3(grid1d((long long)R * W, 256)), dim3(256), 0, in, ld_in, out, ld_out, R, W);
   cx.check("copy_f32_kernel");
 }
 
@@ -873,7 +902,7 @@ extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, co
       const float* ps = t == 0 ? init_stoch : stochs + (size_t)(t - 1) * SK;
       const float* pd = t == 0 ? init_deter : deters + (size_t)(t - 1) * D;
       const int lds = t == 0 ? SK : T * SK, ldd = t == 0 ? D : T * D;
-      sd::prep_obs_kernel<<<grid1d((long long)B * (SK + D + A), 256), 256, 0, cx.st>>>(
+      launch_k(cx.st, sd::prep_obs_kernel, dim3(grid1d((long long)B * (SK + D + A), 256)), dim3(256), 0, 
           ps, lds, pd, ldd, action + (size_t)t * A, T * A, is_first + t, T, B, SK, D, A, sb.zin, sb.din, sb.ain,
           sb.keep, nullptr);
       cx.check("prep_obs_kernel");
@@ -894,9 +923,9 @@ extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, co
       if (tape) copy_f32(cx, u + (size_t)t * SK, T * SK, sb.ucopy, SK, B, SK);
     }
     if (tape && !cx.err) {  // deter' and embed in step-major layout for the batched weight-gradient pass
-      sd::bt_to_tb_kernel<<<grid1d((long long)B * T * D, 256), 256, 0, cx.st>>>(deters, h->tape.dnew, B, T, D);
+      launch_k(cx.st, sd::bt_to_tb_kernel, dim3(grid1d((long long)B * T * D, 256)), dim3(256), 0, deters, h->tape.dnew, B, T, D);
       cx.check("bt_to_tb_kernel");
-      sd::bt_to_tb_kernel<<<grid1d((long long)B * T * E, 256), 256, 0, cx.st>>>(embed, h->tape.emb, B, T, E);
+      launch_k(cx.st, sd::bt_to_tb_kernel, dim3(grid1d((long long)B * T * E, 256)), dim3(256), 0, embed, h->tape.emb, B, T, E);
       cx.check("bt_to_tb_kernel");
     }
   });
@@ -948,7 +977,7 @@ extern "C" int sd_imagine_with_action(sd_handle* h, int R, int T, const float* s
       const float* ps = t == 0 ? stoch : stochs + (size_t)(t - 1) * SK;
       const float* pd = t == 0 ? deter : deters + (size_t)(t - 1) * D;
       const int lds = t == 0 ? SK : T * SK, ldd = t == 0 ? D : T * D;
-      sd::prep_obs_kernel<<<grid1d((long long)R * (SK + D + A), 256), 256, 0, cx.st>>>(
+      launch_k(cx.st, sd::prep_obs_kernel, dim3(grid1d((long long)R * (SK + D + A), 256)), dim3(256), 0, 
           ps, lds, pd, ldd, actions + (size_t)t * A, T * A, nullptr, 0, R, SK, D, A, sb.zin, sb.din, sb.ain, nullptr,
           nullptr);
       cx.check("prep_obs_kernel");
@@ -1016,7 +1045,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
       if (cx.err) return;
       {
         const int n = c.act_kind == 0 ? N * A : N;
-        sd::actor_sample_kernel<<<(n + 127) / 128, 128, 0, cx.st>>>(sb.aout, N, A, c.act_kind, c.min_std, c.max_std,
+        launch_k(cx.st, sd::actor_sample_kernel, dim3((n + 127) / 128), dim3(128), 0, sb.aout, N, A, c.act_kind, c.min_std, c.max_std,
                                                                     c.act_unimix, act_noise + (size_t)t * A, H * A,
                                                                     actions + (size_t)t * A, H * A, h->abar);
         cx.check("actor_sample_kernel");
@@ -1051,7 +1080,7 @@ static void normact_bwd(Ctx& cx, int R, const sd::NormActBwdP* ps, int n) {
   sd::NormActBwdBatch b;
   b.count = n;
   for (int i = 0; i < n; ++i) b.p[i] = ps[i];
-  sd::normact_bwd_kernel<<<dim3(R, n), 256, 0, cx.st>>>(b);
+  launch_k(cx.st, sd::normact_bwd_kernel, dim3(dim3(R, n)), dim3(256), 0, b);
   cx.check("normact_bwd_kernel");
 }
 static sd::NormActBwdP nbp(const float* dout, int ld_dout, const float* v, int ld_v, const float* w, int width, float* dv,
@@ -1082,7 +1111,7 @@ static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, 
     p.C = dx + (size_t)g * dx_gstride; p.ldc = ld_dx; p.N = L.K;
   }
   dim3 grid((L.K + 15) / 16, (R + 15) / 16, gb.count);
-  sd::gemm_f32_kernel<<<grid, 256, sd::GB_SMEM, cx.st>>>(gb);
+  launch_k(cx.st, sd::gemm_f32_kernel, dim3(grid), dim3(256), sd::GB_SMEM, gb);
   cx.check("gemm_f32_kernel(dgrad)");
 }
 template <int GS>
@@ -1090,7 +1119,7 @@ static void launch_sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u
                               const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
                               float* d_logit, int ld_d) {
   const long long n = (long long)R * S * GS;
-  sd::sample_bwd_kernel<GS><<<(int)((n + 255) / 256), 256, 0, cx.st>>>(lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul,
+  launch_k(cx.st, sd::sample_bwd_kernel<GS>, dim3((int)((n + 255) / 256)), dim3(256), 0, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul,
                                                                        R, S, K, unimix, d_logit, ld_d);
 }
 static void sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
@@ -1127,14 +1156,14 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   float* d_hpre = bw.d_hpre + slot * D;
   float* d_vin = bw.d_vin + slot * 3 * U;
   if (cx.err) return;
-  sd::gates_bwd_kernel<<<grid1d((long long)R * D, 256), 256, 0, cx.st>>>(bw.gd, D, sb.q, deter_in, ld_in, d_q, bw.dd, R, D, Dg);
+  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, bw.gd, D, sb.q, deter_in, ld_in, d_q, bw.dd, R, D, Dg);
   cx.check("gates_bwd_kernel");
   dgrad(cx, R, h.gru, d_q, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
   sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D);
   normact_bwd(cx, R, &ph, 1);
   dgrad(cx, R, h.hid, d_hpre, D, Dg, bw.t_dxin, c.G * Kb, Kb);
   if (cx.err) return;
-  sd::hid_reduce_kernel<<<grid1d((long long)R * (D + 3 * U), 256), 256, 0, cx.st>>>(bw.t_dxin, bw.dd, bw.dx, R, c.G, Dg, 3 * U);
+  launch_k(cx.st, sd::hid_reduce_kernel, dim3(grid1d((long long)R * (D + 3 * U), 256)), dim3(256), 0, bw.t_dxin, bw.dd, bw.dx, R, c.G, Dg, 3 * U);
   cx.check("hid_reduce_kernel");
   sd::NormActBwdP pin[3];
   const float* gains[3] = {h.in0.gain, h.in1.gain, h.in2.gain};
@@ -1151,7 +1180,7 @@ static void wgrad_run(Ctx& cx, int R, sd::WgradBatch& wb, int max_n, int max_k) 
   if (cx.err || wb.count == 0) return;
   wb.R = R;
   dim3 grid((max_n + 63) / 64, (max_k + 63) / 64, wb.count);
-  sd::wgrad_f32_kernel<<<grid, 256, 0, cx.st>>>(wb);
+  launch_k(cx.st, sd::wgrad_f32_kernel, dim3(grid), dim3(256), 0, wb);
   cx.check("wgrad_f32_kernel");
   wb.count = 0;
 }
@@ -1175,7 +1204,7 @@ static void wgrad_linear(Ctx& cx, int R, const LinearW& L, bool block, const flo
 }
 static void colsum(Ctx& cx, const float* in, int ld, int R, int W, float* out) {
   if (!out || cx.err) return;
-  sd::colsum_kernel<<<(W + 127) / 128, 128, 0, cx.st>>>(in, ld, R, W, out);
+  launch_k(cx.st, sd::colsum_kernel, dim3((W + 127) / 128), dim3(128), 0, in, ld, R, W, out);
   cx.check("colsum_kernel");
 }
 
@@ -1207,14 +1236,14 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
                  d_logits ? d_logits + (size_t)t * SK : nullptr, T * SK, B, c.S, c.K, c.unimix, d_lg, SK);
       latent_logits_bwd(cx, sb, bw, slot, B, h->obs, c.obs_layers, h->obs_logit, d_lg, bw.t_dxe);
       if (cx.err) return;
-      sd::obs_combine_kernel<<<grid1d((long long)B * (D + E), 256), 256, 0, cx.st>>>(
+      launch_k(cx.st, sd::obs_combine_kernel, dim3(grid1d((long long)B * (D + E), 256)), dim3(256), 0, 
           bw.carry_d, d_deters ? d_deters + (size_t)t * D : nullptr, T * D, bw.t_dxe, B, D, E, bw.gd,
           d_embed ? d_embed + (size_t)t * E : nullptr, T * E);
       cx.check("obs_combine_kernel");
       deter_core_bwd(cx, sb, bw, slot, B, false, sb.din, D);
       if (cx.err) return;
       // reset cut (rssm.py:161-165): carry = d(step inputs) * (1 - is_first)
-      sd::carry_kernel<<<grid1d((long long)B * (SK + D), 256), 256, 0, cx.st>>>(bw.dd, bw.t_din0, bw.t_dz, sb.keep, nullptr,
+      launch_k(cx.st, sd::carry_kernel, dim3(grid1d((long long)B * (SK + D), 256)), dim3(256), 0, bw.dd, bw.t_din0, bw.t_dz, sb.keep, nullptr,
                                                                               0, nullptr, 0, B, SK, D, bw.carry_z, bw.carry_d);
       cx.check("carry_kernel");
     }
@@ -1293,7 +1322,7 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
         sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, nullptr, 0, nullptr, 0, N, c.S, c.K, c.unimix, bw.d_lg, SK);
         latent_logits_bwd(cx, sb, bw, 0, N, h->img, c.img_layers, h->img_logit, bw.d_lg, bw.t_dxe);
         if (cx.err) return;
-        sd::obs_combine_kernel<<<grid1d((long long)N * D, 256), 256, 0, cx.st>>>(bw.carry_d, nullptr, 0, bw.t_dxe, N, D, 0,
+        launch_k(cx.st, sd::obs_combine_kernel, dim3(grid1d((long long)N * D, 256)), dim3(256), 0, bw.carry_d, nullptr, 0, bw.t_dxe, N, D, 0,
                                                                                bw.gd, nullptr, 0);
         cx.check("obs_combine_kernel");
         deter_core_bwd(cx, sb, bw, 0, N, true, sb.feat + SK, F);
@@ -1302,7 +1331,7 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
       // through action = actor(feat_t).rsample()
       const float* d_up = d_actions ? d_actions + (size_t)t * A : nullptr;
       if (c.act_kind == 0) {
-        sd::actor_sample_bwd_kernel<<<(N * A + 127) / 128, 128, 0, cx.st>>>(sb.aout, sb.emb, A, sb.act, A, d_up, H * A,
+        launch_k(cx.st, sd::actor_sample_bwd_kernel, dim3((N * A + 127) / 128), dim3(128), 0, sb.aout, sb.emb, A, sb.act, A, d_up, H * A,
                                                                             stepped ? bw.d_abar : nullptr, N, A, c.min_std,
                                                                             c.max_std, bw.t_daout);
         cx.check("actor_sample_bwd_kernel");
@@ -1312,7 +1341,7 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
       }
       head_bwd(cx, sb, bw, N, actor, bw.t_daout, h->act_out, bw.t_dfeat, F);
       if (cx.err) return;
-      sd::carry_kernel<<<grid1d((long long)N * F, 256), 256, 0, cx.st>>>(
+      launch_k(cx.st, sd::carry_kernel, dim3(grid1d((long long)N * F, 256)), dim3(256), 0, 
           stepped ? bw.dd : nullptr, stepped ? bw.t_din0 : nullptr, stepped ? bw.t_dz : nullptr, nullptr, bw.t_dfeat, F,
           d_feats ? d_feats + (size_t)t * F : nullptr, H * F, N, SK, D, bw.carry_z, bw.carry_d);
       cx.check("carry_kernel");
@@ -1355,10 +1384,10 @@ extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feat
       head_forward(cx, R, hw, feat, F, v, o, ob, h->hl, up(hw.out, 4));
       if (cx.err) return;
       if (twohot) {
-        sd::twohot_mode_kernel<<<(R * 32 + 255) / 256, 256, 0, cx.st>>>(h->hl, up(hw.out, 4), h->bins, c.bins, R, rew_like);
+        launch_k(cx.st, sd::twohot_mode_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, h->hl, up(hw.out, 4), h->bins, c.bins, R, rew_like);
         cx.check("twohot_mode_kernel");
       } else {
-        sd::sigmoid_kernel<<<(R + 255) / 256, 256, 0, cx.st>>>(h->hl, up(hw.out, 4), rew_like, R);
+        launch_k(cx.st, sd::sigmoid_kernel, dim3((R + 255) / 256), dim3(256), 0, h->hl, up(hw.out, 4), rew_like, R);
         cx.check("sigmoid_kernel");
       }
     };
@@ -1372,7 +1401,7 @@ extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feat
     cx.tc = tc_saved;
     if (cx.err) return;
     if (weight || ret) {
-      sd::imag_weight_ret_kernel<<<(N + 127) / 128, 128, 0, cx.st>>>(N, H, rw, ct, vl, disc, lamb, weight, ret);
+      launch_k(cx.st, sd::imag_weight_ret_kernel, dim3((N + 127) / 128), dim3(128), 0, N, H, rw, ct, vl, disc, lamb, weight, ret);
       cx.check("imag_weight_ret_kernel");
     }
   });
@@ -1384,7 +1413,7 @@ extern "C" int sd_lambda_return(int N, int T, const float* last, const float* te
   if (N < 1 || T < 2) return fail(SD_ERR_INVALID, "sd_lambda_return: need N >= 1, T >= 2");
   if (!term || !reward || !value || !boot || !out) return fail(SD_ERR_INVALID, "sd_lambda_return: null tensor");
   (void)value;  // the reference signature carries `value` but only `boot` enters the recursion (dreamer.py:701-706)
-  sd::lambda_return_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, T, last, term, reward, value, boot, disc,
+  launch_k((cudaStream_t)stream, sd::lambda_return_kernel, dim3((N + 127) / 128), dim3(128), 0, N, T, last, term, reward, value, boot, disc,
                                                                             lamb, out);
   ++g_launches;
   CUDA_TRY(cudaPeekAtLastError());
@@ -1399,9 +1428,9 @@ extern "C" int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const fl
   if (!post_logit || !prior_logit) return fail(SD_ERR_INVALID, "sd_kl_loss: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   const int n = R * h->c.S;
-  sd::kl_entropy_kernel<<<(n + 127) / 128, 128, 0, st>>>(post_logit, prior_logit, R, h->c.S, h->c.K, h->c.unimix, h->kl_a,
+  launch_k(st, sd::kl_entropy_kernel, dim3((n + 127) / 128), dim3(128), 0, post_logit, prior_logit, R, h->c.S, h->c.K, h->c.unimix, h->kl_a,
                                                         post_entropy ? h->kl_b : nullptr, prior_entropy ? h->kl_c : nullptr);
-  sd::kl_finish_kernel<<<(R + 127) / 128, 128, 0, st>>>(h->kl_a, h->kl_b, h->kl_c, R, h->c.S, free_nats, dyn_loss, rep_loss,
+  launch_k(st, sd::kl_finish_kernel, dim3((R + 127) / 128), dim3(128), 0, h->kl_a, h->kl_b, h->kl_c, R, h->c.S, free_nats, dyn_loss, rep_loss,
                                                        post_entropy, prior_entropy);
   g_launches += 2;
   CUDA_TRY(cudaPeekAtLastError());

@@ -26,6 +26,7 @@ struct NormActBwdBatch {
   NormActBwdP p[4];
 };
 __global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch b) {
+  pdl_prologue();
   __shared__ float sh[32];
   const NormActBwdP& p = b.p[blockIdx.y];
   const size_t row = blockIdx.x;
@@ -74,6 +75,7 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
                                   const float* __restrict__ gz_a, int ld_a, const float* __restrict__ gz_b, int ld_b,
                                   const float* __restrict__ up_logit, int ld_ul, int R, int S, int K, float unimix,
                                   float* d_logit, int ld_d) {
+  pdl_prologue();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long cat = t / GS;
   const int k = (int)(t % GS);
@@ -118,6 +120,7 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
 __global__ void gates_bwd_kernel(const float* __restrict__ g, int ld_g, const float* __restrict__ q,
                                  const float* __restrict__ deter_in, int ld_in, float* dq, float* dd, int R, int D,
                                  int Dg) {
+  pdl_prologue();
   const long long total = (long long)R * D;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -142,6 +145,7 @@ __global__ void gates_bwd_kernel(const float* __restrict__ g, int ld_g, const fl
 __global__ void obs_combine_kernel(const float* __restrict__ carry, const float* __restrict__ up, int ld_up,
                                    const float* __restrict__ dxe, int R, int D, int E, float* gd, float* d_embed,
                                    int ld_e) {
+  pdl_prologue();
   const int W = D + E;
   const long long total = (long long)R * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -159,6 +163,7 @@ __global__ void obs_combine_kernel(const float* __restrict__ carry, const float*
 
 // After the block dgrad of dyn_hid: dxin (R, G, Dg + 3U).  dd += dxin[:, g, :Dg];  dx = sum_g dxin[:, g, Dg:].
 __global__ void hid_reduce_kernel(const float* __restrict__ dxin, float* dd, float* dx, int R, int G, int Dg, int U3) {
+  pdl_prologue();
   const int W = G * Dg + U3;
   const int Kb = Dg + U3;
   const long long total = (long long)R * W;
@@ -186,6 +191,7 @@ __global__ void carry_kernel(const float* __restrict__ dd, const float* __restri
                              const float* __restrict__ dz, const float* __restrict__ keep_mask,
                              const float* __restrict__ extra, int ld_x, const float* __restrict__ extra2, int ld_x2,
                              int R, int SK, int D, float* carry_z, float* carry_d) {
+  pdl_prologue();
   const int W = SK + D;
   const long long total = (long long)R * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -205,6 +211,7 @@ __global__ void carry_kernel(const float* __restrict__ dd, const float* __restri
 // out[c] (+)= sum_r in[r][c]: fixed-order column sums for bias / RMS-scale gradients.
 // One thread per column (coalesced across the warp), rows summed sequentially => deterministic.
 __global__ void colsum_kernel(const float* __restrict__ in, int ld, int R, int W, float* out) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= W) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -225,6 +232,7 @@ __global__ void actor_sample_bwd_kernel(const float* __restrict__ out, const flo
                                         const float* __restrict__ action, int ld_act, const float* __restrict__ d_up,
                                         int ld_up, const float* __restrict__ d_abar, int R, int A, float min_std,
                                         float max_std, float* d_out) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * A) return;
   const size_t row = i / A;

@@ -18,6 +18,13 @@ namespace sd {
 
 constexpr float kRmsEps = 1e-4f;
 
+// Programmatic dependent launch prologue: let the next kernel in the stream get scheduled now, then wait
+// until every prerequisite grid has completed and its writes are visible.  No-ops without the PDL attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Batched skinny GEMM:  C[R x N] = [A | A2][R x K] * Wt[K x N] + bias, fp32.
 // A CTA owns a 16-row x 16-column output tile and splits K over its 64 thread groups (intra-CTA
@@ -46,6 +53,7 @@ constexpr int GB_RLD = 16 * 16 + 4;  // padded stride of the split-K reduction b
 constexpr int GB_SMEM = (64 * GB_RLD > 16 * GB_XLD ? 64 * GB_RLD : 16 * GB_XLD) * 4;
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
+  pdl_prologue();
   const GemmP& p = b.p[blockIdx.z];
   const int n0 = blockIdx.x * 16;
   if (n0 >= p.N) return;
@@ -151,6 +159,7 @@ struct WgradBatch {
 };
 
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
+  pdl_prologue();
   const WgradP& p = b.p[blockIdx.z];
   const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
   if (n0 >= p.N || k0 >= p.K) return;
@@ -206,6 +215,7 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
 __global__ void pack_weight_kernel(const float* __restrict__ src, int G, int N, int K, long long s_g,
                                    long long s_n, long long s_k, float* wt, int ldw, float* wn, int ldk,
                                    __nv_bfloat16* wn_bf, __nv_bfloat16* wt_bf) {
+  pdl_prologue();
   const long long total = (long long)G * N * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -261,6 +271,7 @@ struct NormActBatch {
   NormActP p[4];
 };
 __global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
+  pdl_prologue();
   __shared__ float sh[32];
   const NormActP& p = b.p[blockIdx.y];
   const size_t row = blockIdx.x;
@@ -290,6 +301,7 @@ __global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
 __global__ void gates_kernel(const float* __restrict__ q, const float* __restrict__ deter_in, int ld_in,
                              float* __restrict__ deter_out, int ld_out, __nv_bfloat16* out_bf, int ld_bf,
                              int R, int D, int Dg) {
+  pdl_prologue();
   const long long total = (long long)R * D;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -399,6 +411,7 @@ template <int GS>
 __global__ void sample_kernel(const float* __restrict__ logits, int ld_l, const float* __restrict__ u, int ld_u,
                               int R, int S, int K, float unimix, float* stoch, int ld_o, __nv_bfloat16* stoch_bf,
                               int ld_bf, float* logit_copy, int ld_c, int* idx_out) {
+  pdl_prologue();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long cat = t / GS;          // (row, s)
   const int k = (int)(t % GS);
@@ -427,6 +440,7 @@ __global__ void prep_obs_kernel(const float* __restrict__ stoch, int ld_s, const
                                 const float* __restrict__ action, int ld_a, const uint8_t* __restrict__ is_first,
                                 int ld_f, int R, int SK, int D, int A, float* zin, float* din, float* ain,
                                 float* keep_out, float* araw_out) {
+  pdl_prologue();
   const int W = SK + D + A;
   const long long total = (long long)R * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -451,6 +465,7 @@ __global__ void prep_obs_kernel(const float* __restrict__ stoch, int ld_s, const
 
 // (B, T, W) -> (T, B, W): puts user-layout tensors into the step-major tape layout.
 __global__ void bt_to_tb_kernel(const float* __restrict__ in, float* out, int B, int T, int W) {
+  pdl_prologue();
   const long long total = (long long)B * T * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -464,6 +479,7 @@ __global__ void bt_to_tb_kernel(const float* __restrict__ in, float* out, int B,
 // fp32 -> bf16 copy of a strided (R x W) matrix.
 __global__ void cast_bf16_kernel(const float* __restrict__ in, int ld_in, __nv_bfloat16* out, int ld_out, int R,
                                  int W) {
+  pdl_prologue();
   const long long total = (long long)R * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -474,6 +490,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, int ld_in, __nv_b
 }
 // strided (R x W) fp32 copy.
 __global__ void copy_f32_kernel(const float* __restrict__ in, int ld_in, float* out, int ld_out, int R, int W) {
+  pdl_prologue();
   const long long total = (long long)R * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -490,6 +507,7 @@ __global__ void copy_f32_kernel(const float* __restrict__ in, int ld_in, float* 
 __global__ void actor_sample_kernel(const float* __restrict__ out, int R, int A, int act_kind, float min_std,
                                     float max_std, float unimix, const float* __restrict__ noise, int ld_n,
                                     float* action, int ld_act, float* abar) {
+  pdl_prologue();
   if (act_kind == 0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R * A) return;
@@ -522,6 +540,7 @@ __global__ void actor_sample_kernel(const float* __restrict__ out, int R, int A,
 // pairing sum_j (p[m-1-j]*b[m-1-j] + p[m+1+j]*b[m+1+j]) + p[m]*b[m].  One warp per row.
 __global__ void twohot_mode_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ bins, int n,
                                    int R, float* out) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= R) return;
   const float* lp = logits + (size_t)warp * ld;
@@ -555,6 +574,7 @@ __global__ void twohot_mode_kernel(const float* __restrict__ logits, int ld, con
 
 // cont head mean = sigmoid(logit) (distributions.py:238-239, Bernoulli.mean).
 __global__ void sigmoid_kernel(const float* __restrict__ in, int ld, float* out, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = sigmoidf_(in[(size_t)i * ld]);
 }
@@ -564,6 +584,7 @@ __global__ void sigmoid_kernel(const float* __restrict__ in, int ld, float* out,
 __global__ void lambda_return_kernel(int N, int T, const float* __restrict__ last, const float* __restrict__ term,
                                      const float* __restrict__ reward, const float* __restrict__ value,
                                      const float* __restrict__ boot, float disc, float lamb, float* out) {
+  pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const size_t o = (size_t)n * T;
@@ -579,6 +600,7 @@ __global__ void lambda_return_kernel(int N, int T, const float* __restrict__ las
 __global__ void imag_weight_ret_kernel(int N, int H, const float* __restrict__ reward, const float* __restrict__ cont,
                                        const float* __restrict__ value, float disc, float lamb, float* weight,
                                        float* ret) {
+  pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const size_t o = (size_t)n * H;
@@ -605,6 +627,7 @@ __global__ void imag_weight_ret_kernel(int N, int H, const float* __restrict__ r
 // One thread per (row, category); per-row sums are reduced in a fixed order by the last stage.
 __global__ void kl_entropy_kernel(const float* __restrict__ post, const float* __restrict__ prior, int R, int S, int K,
                                   float unimix, float* kl_sk, float* ent_post_sk, float* ent_prior_sk) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * S) return;
   const float* a = post + (size_t)i * K;
@@ -637,6 +660,7 @@ __global__ void kl_entropy_kernel(const float* __restrict__ post, const float* _
 __global__ void kl_finish_kernel(const float* __restrict__ kl_sk, const float* __restrict__ ep_sk,
                                  const float* __restrict__ eq_sk, int R, int S, float free_nats, float* dyn, float* rep,
                                  float* ent_post, float* ent_prior) {
+  pdl_prologue();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   float k = 0.f, ep = 0.f, eq = 0.f;

@@ -167,6 +167,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // PDL: barrier init / TMEM allocation above overlap the previous kernel; global memory is touched below.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {

@@ -92,6 +92,19 @@ class Engine:
         _lib.check(self.lib.sd_set_weights(self.h, module, arr, len(ts), self.stream), "sd_set_weights")
         self._keep[module] = ts  # keep sources alive until the async repack has been enqueued and run
 
+    def _stage(self, t, tag):
+        """static mode: copy an input into an engine-owned buffer so the pointers seen by the C ABI (and the
+        CUDA-graph cache keyed on them) never change between calls."""
+        if not self.static_outputs or t is None:
+            return t
+        key = ("in_" + tag, tuple(t.shape), t.dtype)
+        buf = self._outs.get(key)
+        if buf is None:
+            buf = self._outs[key] = torch.empty_like(t)
+        if buf.data_ptr() != t.data_ptr():
+            buf.copy_(t)
+        return buf
+
     def _new(self, *shape, tag=None):
         if self.static_outputs and tag is not None:
             key = (tag, tuple(shape))
@@ -107,6 +120,9 @@ class Engine:
         embed, action, u = _f32c(embed, "embed"), _f32c(action, "action"), _f32c(u, "u")
         init_stoch, init_deter = _f32c(init_stoch, "init_stoch"), _f32c(init_deter, "init_deter")
         first = is_first.reshape(B, T).to(torch.uint8).contiguous()
+        embed, action, u, first = (self._stage(embed, "emb"), self._stage(action, "act"), self._stage(u, "u"),
+                                   self._stage(first, "first"))
+        init_stoch, init_deter = self._stage(init_stoch, "is"), self._stage(init_deter, "id")
         c = self.cfg
         assert embed.shape == (B, T, c.E) and action.shape == (B, T, c.A) and u.numel() == B * T * self.SK
         if out is not None:
@@ -125,6 +141,7 @@ class Engine:
         ds = None if d_stochs is None else _f32c(d_stochs, "d_stochs")
         dd = None if d_deters is None else _f32c(d_deters, "d_deters")
         dl = None if d_logits is None else _f32c(d_logits, "d_logits")
+        ds, dd, dl = self._stage(ds, "ds"), self._stage(dd, "dd"), self._stage(dl, "dl")
         d_embed = self._new(B, T, c.E, tag="ob_de") if want_embed else None
         d_is = self._new(B, c.S, c.K, tag="ob_dis") if want_init else None
         d_id = self._new(B, c.D, tag="ob_did") if want_init else None
@@ -167,6 +184,8 @@ class Engine:
         stoch0, deter0, u, act_noise = (_f32c(stoch0, "stoch0"), _f32c(deter0, "deter0"), _f32c(u, "u"),
                                         _f32c(act_noise, "act_noise"))
         assert u.numel() == N * H * self.SK and act_noise.numel() == N * H * c.A
+        stoch0, deter0, u, act_noise = (self._stage(stoch0, "s0"), self._stage(deter0, "d0"), self._stage(u, "iu"),
+                                        self._stage(act_noise, "an"))
         feats, actions = out if out is not None else (self._new(N, H, self.F, tag="im_f"), self._new(N, H, c.A, tag="im_a"))
         _lib.check(self.lib.sd_imagine_fwd(self.h, N, H, _ptr(stoch0), _ptr(deter0), _ptr(u), _ptr(act_noise),
                                            _ptr(feats), _ptr(actions), flags, self.stream), "sd_imagine_fwd")
@@ -183,7 +202,7 @@ class Engine:
 
     def heads_lambda(self, feats, disc, lamb, flags=0, slow=True, out=None):
         N, H = feats.shape[:2]
-        feats = _f32c(feats, "feats")
+        feats = _f32c(feats, "feats")  # (N,H,F) is large: not staged; imagine()'s static output keeps it stable
         if out is None:
             rew, cont, val, wgt = (self._new(N, H, 1, tag=f"hl{i}") for i in range(4))
             sval = self._new(N, H, 1, tag="hl_sv") if slow else None

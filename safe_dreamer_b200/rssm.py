@@ -95,6 +95,7 @@ class _Runtime:
         self.engine = None
         self.sig = None
         self.limits = (0, 0, 0)
+        self.bucket = None
 
     def __deepcopy__(self, memo):
         return _Runtime()
@@ -128,9 +129,19 @@ class _ObserveFn(torch.autograd.Function):
         names = eng.weight_names(MOD_RSSM)
         wg = None
         if need_w:
-            wg = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in rssm.named_parameters()}
+            if rssm.static_outputs:   # pointer-stable gradient buffers keep the CUDA-graph cache hot
+                from .parallel import GradBucket
+                if rssm._rt.bucket is None:
+                    rssm._rt.bucket = GradBucket({n: p.shape for n, p in rssm.named_parameters()}, d_dt.device)
+                rssm._rt.bucket.zero_()
+                wg = rssm._rt.bucket.views
+            else:
+                wg = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in rssm.named_parameters()}
         d_embed, d_is, d_id = eng.observe_bwd(ctx.B, ctx.T, d_st, d_dt, d_lg, need_embed, need_init, wg, ctx.flags)
-        pg = [None if wg is None else wg[n] for n, _ in rssm.named_parameters()]
+        pg = [None if wg is None else (wg[n].clone() if rssm.static_outputs else wg[n])
+              for n, _ in rssm.named_parameters()]
+        if rssm.static_outputs:
+            d_embed = None if d_embed is None else d_embed.clone()
         assert set(names) == set(n for n, _ in rssm.named_parameters())
         return (None, d_embed, None, d_is, d_id, None, None, *pg)
 
