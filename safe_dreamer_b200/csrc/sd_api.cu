@@ -129,6 +129,8 @@ struct sd_handle {
   // heads workspace
   float *hv, *ho, *hl, *h_rew, *h_cont, *h_val, *kl_a, *kl_b, *kl_c;
   std::vector<GraphEntry> graphs;
+  float* wg_scratch = nullptr;         // row-slice partials of the weight-gradient pass
+  size_t wg_scratch_elems = 0;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
   bf16* trunk_bf = nullptr;
 };
@@ -466,6 +468,14 @@ static void layout(sd_handle& h, Arena& a) {
   if (c.max_tape_rows > 0) {
     alloc_stepbufs(a, h.tape, h, c.max_tape_rows, T > 1 ? T : 2, true);
     alloc_bwd(a, h.bw, h, c.max_tape_rows, T > 1 ? T : 2);
+    // largest weight tensor x 8 row slices
+    size_t big = (size_t)c.U * (c.D + c.E);
+    const size_t hidw = (size_t)c.D * (h.Dg + 3 * c.U), gruw = (size_t)3 * c.D * h.Dg;
+    if (hidw > big) big = hidw;
+    if (gruw > big) big = gruw;
+    if ((size_t)c.units * F > big) big = (size_t)c.units * F;
+    h.wg_scratch_elems = big * 8;
+    h.wg_scratch = a.take<float>(h.wg_scratch_elems);
   }
   h.feat_bf = a.take<bf16>(R * F);
   h.x_bf = a.take<bf16>(R * 3 * c.U);
@@ -1176,35 +1186,44 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   if (want_act) dgrad(cx, R, h.in2, d_vin + 2 * U, 3 * U, 0, bw.d_abar, c.A, 0);
 }
 
-static void wgrad_run(Ctx& cx, int R, sd::WgradBatch& wb, int max_n, int max_k) {
-  if (cx.err || wb.count == 0) return;
-  wb.R = R;
-  dim3 grid((max_n + 63) / 64, (max_k + 63) / 64, wb.count);
-  launch_k(cx.st, sd::wgrad_f32_kernel, dim3(grid), dim3(256), 0, wb);
-  cx.check("wgrad_f32_kernel");
-  wb.count = 0;
-}
 // dW (+)= dY^T [X | X2] for a Linear (reference layout (N,K)) or the G blocks of a BlockLinear ((O/G, I/G, G)).
+// Rows are cut into fixed slices (more CTAs, short dependent chains); partials land in the scratch and are
+// added to dW in slice order.
 static void wgrad_linear(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride,
                          const float* X, int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* dW) {
   if (!dW || cx.err) return;
+  sd_handle& h = *cx.h;
+  const long long numel = (long long)L.G * L.N * L.K;
+  const int rows_per_slice = 128;
+  int slices = (R + rows_per_slice - 1) / rows_per_slice;
+  const int max_slices = (int)(h.wg_scratch_elems / numel);
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) { cx.err = fail(SD_ERR_WORKSPACE, "wgrad scratch too small"); return; }
   sd::WgradBatch wb;
   memset(&wb, 0, sizeof(wb));
+  wb.R = R;
+  wb.rows_per_slice = (R + slices - 1) / slices;
   for (int g = 0; g < L.G; ++g) {
     sd::WgradP& p = wb.p[wb.count++];
     p.dY = dY + (size_t)g * dy_gstride; p.ldy = ldy;
     p.X = X + (size_t)g * x_gstride; p.ldx = ldx;
     p.X2 = X2; p.ldx2 = ldx2;
     p.K1 = K1; p.K = L.K; p.N = L.N;
-    p.dW = dW + (block ? g : 0);
+    p.dW = h.wg_scratch + (block ? g : 0);
     p.sn = block ? (long long)L.K * L.G : L.K;
     p.sk = block ? L.G : 1;
+    p.slice_stride = numel;
   }
-  wgrad_run(cx, R, wb, L.N, L.K);
+  dim3 grid((L.N + 63) / 64, (L.K + 63) / 64, wb.count * slices);
+  launch_k(cx.st, sd::wgrad_f32_kernel, grid, dim3(256), 0, wb);
+  cx.check("wgrad_f32_kernel");
+  launch_k(cx.st, sd::wgrad_reduce_kernel, dim3(grid1d(numel, 256)), dim3(256), 0, (const float*)h.wg_scratch, numel,
+           slices, numel, dW);
+  cx.check("wgrad_reduce_kernel");
 }
 static void colsum(Ctx& cx, const float* in, int ld, int R, int W, float* out) {
   if (!out || cx.err) return;
-  launch_k(cx.st, sd::colsum_kernel, dim3((W + 127) / 128), dim3(128), 0, in, ld, R, W, out);
+  launch_k(cx.st, sd::colsum_kernel, dim3((W + 31) / 32), dim3(32, 32), 0, in, ld, R, W, out);
   cx.check("colsum_kernel");
 }
 

@@ -208,22 +208,24 @@ __global__ void carry_kernel(const float* __restrict__ dd, const float* __restri
   }
 }
 
-// out[c] (+)= sum_r in[r][c]: fixed-order column sums for bias / RMS-scale gradients.
-// One thread per column (coalesced across the warp), rows summed sequentially => deterministic.
-__global__ void colsum_kernel(const float* __restrict__ in, int ld, int R, int W, float* out) {
+// out[c] += sum_r in[r][c]: column sums for bias / RMS-scale gradients in a fixed order.
+// Block = 32 columns x 32 row lanes; each lane sums rows lane, lane+32, ... then the 32 lane partials are
+// added in ascending lane order => deterministic.
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ in, int ld, int R, int W, float* out) {
   pdl_prologue();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= W) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int r = 0;
-  for (; r + 4 <= R; r += 4) {
-    s0 += in[(size_t)r * ld + c];
-    s1 += in[(size_t)(r + 1) * ld + c];
-    s2 += in[(size_t)(r + 2) * ld + c];
-    s3 += in[(size_t)(r + 3) * ld + c];
+  __shared__ float sh[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < W)
+    for (int r = threadIdx.y; r < R; r += 32) s += in[(size_t)r * ld + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < W) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += sh[j][threadIdx.x];
+    out[c] += t;
   }
-  for (; r < R; ++r) s0 += in[(size_t)r * ld + c];
-  out[c] += (s0 + s1) + (s2 + s3);
 }
 
 // Backward of the bounded-normal actor sample (distributions.py:217-222): action = tanh(mean) + std*eps,

@@ -150,41 +150,61 @@ struct WgradP {
   const float* X;  int ldx;   // [R x K1]
   const float* X2; int ldx2;  // [R x (K-K1)]
   int K1, K, N;
-  float* dW; long long sn, sk; // dW[n*sn + k*sk]
+  float* dW; long long sn, sk; // partial slice s lives at dW + s*slice_stride; element (n,k) at n*sn + k*sk
+  long long slice_stride;
 };
 struct WgradBatch {
   int count;
   int R;
+  int rows_per_slice;          // rows are cut into gridDim.z / count slices (fixed assignment => deterministic)
   WgradP p[kMaxBatch];
 };
 
+// Each CTA owns a 64x64 (n,k) tile of one row slice; partial tiles are summed in slice order by
+// wgrad_reduce_kernel.  Next chunk's loads are issued before the current chunk's FMAs (register prefetch).
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
   pdl_prologue();
-  const WgradP& p = b.p[blockIdx.z];
+  const int prob = blockIdx.z % b.count, slice = blockIdx.z / b.count;
+  const WgradP& p = b.p[prob];
   const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
   if (n0 >= p.N || k0 >= p.K) return;
-  __shared__ float ys[16][64 + 4];
-  __shared__ float xs[16][64 + 4];
+  __shared__ __align__(16) float ys[16][64 + 4];
+  __shared__ __align__(16) float xs[16][64 + 4];
   const int tid = threadIdx.x, tn = tid & 15, tk = tid >> 4;
+  const int r_begin = slice * b.rows_per_slice;
+  const int r_end = min(b.R, r_begin + b.rows_per_slice);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int rc = 0; rc < b.R; rc += 16) {
-    for (int i = tid; i < 16 * 64; i += 256) {
-      const int r = i >> 6, c = i & 63;
-      const int row = rc + r;
-      float yv = 0.f, xv = 0.f;
-      if (row < b.R) {
-        if (n0 + c < p.N) yv = p.dY[(size_t)row * p.ldy + n0 + c];
-        const int k = k0 + c;
-        if (k < p.K) xv = (k < p.K1) ? p.X[(size_t)row * p.ldx + k] : p.X2[(size_t)row * p.ldx2 + (k - p.K1)];
-      }
-      ys[r][c] = yv;
-      xs[r][c] = xv;
+  // element e (0..3) of this thread: row (tid>>6) + 4e of the chunk, column tid&63
+  const int lc = tid & 63, lr = tid >> 6;
+  const bool nok = n0 + lc < p.N;
+  const int kk = k0 + lc;
+  const bool kok = kk < p.K;
+  const bool in1 = kk < p.K1;
+  const float* xsrc = in1 ? p.X + kk : p.X2 + (kk - p.K1);
+  const size_t xld = in1 ? p.ldx : p.ldx2;
+  float yv[4], xv[4];
+  auto load = [&](int rc) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int row = rc + lr + 4 * e;
+      const bool rok = row < r_end;
+      yv[e] = (rok && nok) ? __ldg(p.dY + (size_t)row * p.ldy + n0 + lc) : 0.f;
+      xv[e] = (rok && kok) ? __ldg(xsrc + (size_t)row * xld) : 0.f;
+    }
+  };
+  load(r_begin);
+  for (int rc = r_begin; rc < r_end; rc += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ys[lr + 4 * e][lc] = yv[e];
+      xs[lr + 4 * e][lc] = xv[e];
     }
     __syncthreads();
+    if (rc + 16 < r_end) load(rc + 16);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const float4 y = *reinterpret_cast<const float4*>(&ys[r][tn * 4]);
@@ -197,13 +217,25 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
     }
     __syncthreads();
   }
+  float* out = p.dW + (long long)slice * p.slice_stride;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tn * 4 + i, k = k0 + tk * 4 + j;
-      if (n < p.N && k < p.K) p.dW[n * p.sn + k * p.sk] += acc[i][j];
+      if (n < p.N && k < p.K) out[n * p.sn + k * p.sk] = acc[i][j];
     }
+}
+// dst[i] += sum_s partial[s*stride + i], s ascending.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, long long stride, int slices, long long numel,
+                                    float* dst) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < slices; ++k) s += partial[k * stride + i];
+    dst[i] += s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
