@@ -195,6 +195,33 @@ static bool pdl_enabled() {
   }
   return v == 1;
 }
+// fp32 skinny GEMM launch: K is split over a thread-block cluster along grid.y (see gemm_f32_kernel).
+static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n, int max_k, int R) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
+    attr_done = true;
+  }
+  int ksplit = 1;
+  while (ksplit < sd::GB_MAXSPLIT && (max_k + ksplit - 1) / ksplit > sd::GB_KC) ksplit *= 2;
+  int kslice = ((max_k + ksplit - 1) / ksplit + 3) & ~3;
+  if (kslice > sd::GB_KC) kslice = sd::GB_KC;  // K > 4096 is rejected by validate()
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((max_n + 15) / 16, ksplit, gb.count * ((R + 15) / 16));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = sd::GB_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ksplit; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, sd::gemm_f32_kernel, gb, ksplit, kslice);
+}
+
 template <class... KArgs, class... Args>
 static void launch_k(cudaStream_t st, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
   cudaLaunchConfig_t cfg;
@@ -258,18 +285,14 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
   memset(&gb, 0, sizeof(gb));
   gb.R = R;
   int max_n_f = 0;
+  int max_k_f = 0;
   auto flush_f = [&]() {
     if (gb.count == 0) return;
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
-      attr_done = true;
-    }
-    dim3 grid((max_n_f + 15) / 16, (R + 15) / 16, gb.count);
-    launch_k(cx.st, sd::gemm_f32_kernel, dim3(grid), dim3(256), sd::GB_SMEM, gb);
+    launch_gemm_f32(cx.st, gb, max_n_f, max_k_f, R);
     cx.check("gemm_f32_kernel");
     gb.count = 0;
     max_n_f = 0;
+    max_k_f = 0;
   };
   auto flush_tc = [&]() {
     if (ntc == 0) return;
@@ -325,6 +348,7 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
         p.bias = L.bias ? L.bias + (size_t)g * L.N : nullptr;
         p.C = c.C + (size_t)g * c.c_gstride; p.ldc = c.ldc; p.N = L.N;
         if (L.N > max_n_f) max_n_f = L.N;
+        if (L.K > max_k_f) max_k_f = L.K;
       }
     }
   }
@@ -366,6 +390,8 @@ static int validate(const sd_config& c) {
   if (c.act_kind == 1 && c.A > 32) return fail(SD_ERR_INVALID, "sd_config: one-hot actor with A > 32 unsupported");
   if (c.max_rows < 1 || c.max_steps < 1) return fail(SD_ERR_INVALID, "sd_config: max_rows/max_steps must be >= 1");
   if (c.bins < 2 || c.bins > 1024) return fail(SD_ERR_INVALID, "sd_config: bins out of range");
+  if (c.D + c.E > 4096 || c.S * c.K + c.D > 4096 || 3 * (c.D / c.G) > 4096 || c.D / c.G + 3 * c.U > 4096)
+    return fail(SD_ERR_INVALID, "sd_config: a contraction dimension exceeds 4096 (fp32 cluster split-K limit)");
   return 0;
 }
 
@@ -1107,11 +1133,6 @@ static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, 
   sd::GemmBatch gb;
   memset(&gb, 0, sizeof(gb));
   gb.R = R;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
-    attr_done = true;
-  }
   for (int g = 0; g < L.G; ++g) {
     sd::GemmP& p = gb.p[gb.count++];
     p.A = dy + (size_t)g * dy_gstride; p.lda = ld_dy; p.A2 = nullptr; p.lda2 = 0;
@@ -1120,8 +1141,7 @@ static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, 
     p.bias = nullptr;
     p.C = dx + (size_t)g * dx_gstride; p.ldc = ld_dx; p.N = L.K;
   }
-  dim3 grid((L.K + 15) / 16, (R + 15) / 16, gb.count);
-  launch_k(cx.st, sd::gemm_f32_kernel, dim3(grid), dim3(256), sd::GB_SMEM, gb);
+  launch_gemm_f32(cx.st, gb, L.K, L.N, R);
   cx.check("gemm_f32_kernel(dgrad)");
 }
 template <int GS>

@@ -47,32 +47,49 @@ struct GemmBatch {
   GemmP p[kMaxBatch];
 };
 
-constexpr int GB_KC = 512;           // K chunk staged in shared memory (the i >> 9 fast path assumes 512)
+constexpr int GB_KC = 512;           // largest K slice one CTA handles (staged in shared memory)
 constexpr int GB_XLD = GB_KC + 4;    // padded row stride of the staged activations
 constexpr int GB_RLD = 16 * 16 + 4;  // padded stride of the split-K reduction buffer
-constexpr int GB_SMEM = (64 * GB_RLD > 16 * GB_XLD ? 64 * GB_RLD : 16 * GB_XLD) * 4;
+constexpr int GB_MAXSPLIT = 8;       // cluster size along K (portable maximum)
+constexpr int GB_SMEM = (64 * GB_RLD > 16 * GB_XLD ? 64 * GB_RLD : 16 * GB_XLD) * 4 + GB_MAXSPLIT * 256 * 4;
 
-__global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// grid = (ceil(N/16), ksplit, problems * row_tiles), cluster = (1, ksplit, 1).
+// K is cut into `ksplit` slices of `kslice` (<= 512) elements, one per CTA of the cluster: every CTA does ONE
+// global round trip (its weight quads + its activation slice are all in flight together), reduces its 64
+// thread-group partials through shared memory, and ships its 16x16 partial tile to the cluster leader through
+// distributed shared memory; the leader adds the slices in rank order (deterministic) and stores.
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ksplit, int kslice) {
   pdl_prologue();
-  const GemmP& p = b.p[blockIdx.z];
+  const int prob = blockIdx.z % b.count, rtile = blockIdx.z / b.count;
+  const GemmP& p = b.p[prob];
   const int n0 = blockIdx.x * 16;
-  if (n0 >= p.N) return;
-  const int r0 = blockIdx.y * 16;
+  const bool active = n0 < p.N;           // whole clusters are inactive together (same blockIdx.x / z)
+  const int r0 = rtile * 16;
+  const int rank = (int)blockIdx.y;        // == cluster rank (cluster spans gridDim.y)
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;
+  float* slots = smem + (GB_SMEM / 4 - GB_MAXSPLIT * 256);   // leader: one 16x16 tile per rank
   const int tid = threadIdx.x, tx = tid & 3, ty = tid >> 2;
-  float acc[16][4];
+  const int kc = rank * kslice;
+  const int kend = min(p.K, kc + kslice);
+  float s = 0.f;
+  if (active && kc < kend) {
+    float acc[16][4];
 #pragma unroll
-  for (int r = 0; r < 16; ++r)
+    for (int r = 0; r < 16; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-
-  for (int kc = 0; kc < p.K; kc += GB_KC) {
-    const int kw = min(GB_KC, (p.K - kc + 3) & ~3);
-    // Issue every global load of this chunk before anything is stored to shared memory: the weight
-    // quads of this thread (8 x float4) and its share of the activation chunk (32 scalars).  Loads through
-    // generic pointers may alias shared memory as far as the compiler knows, so interleaving them with the
-    // shared stores would serialise one L2 round trip per element; this way a chunk costs one round trip.
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    // all global loads of this CTA are issued before anything is stored to shared memory
     float4 w[GB_KC / 4 / 64][4];
 #pragma unroll
     for (int i = 0; i < GB_KC / 4 / 64; ++i) {
@@ -80,12 +97,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = kbase + j;
-        w[i][j] = (k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + n0 + tx * 4))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        w[i][j] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + n0 + tx * 4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    // activation chunk: thread `tid` owns columns tid and tid+256 of all 16 rows (coalesced per row).
-    // The K segment (A or A2) depends on the column only, so it is resolved once per half.
     float v[32];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
@@ -93,7 +108,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
       const bool in1 = kk < p.K1;
       const float* src = in1 ? p.A + kk : p.A2 + (kk - p.K1);
       const size_t ld = in1 ? p.lda : p.lda2;
-      const bool kok = kk < p.K;
+      const bool kok = kk < kend;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const int row = r0 + r;
@@ -108,8 +123,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
 #pragma unroll
     for (int i = 0; i < GB_KC / 4 / 64; ++i) {
       const int kq = ty + 64 * i;
-      const int kbase = kc + kq * 4;
-      if (kq * 4 < kw) {
+      if (kc + kq * 4 < kend) {
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const float4 x = *reinterpret_cast<const float4*>(xs + r * GB_XLD + kq * 4);
@@ -125,18 +139,28 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b) {
       }
     }
     __syncthreads();
-  }
-  float* red = smem;
+    float* red = smem;
 #pragma unroll
-  for (int r = 0; r < 16; ++r)
-    *reinterpret_cast<float4*>(red + ty * GB_RLD + r * 16 + tx * 4) =
-        make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-  __syncthreads();
-  float s = 0.f;
+    for (int r = 0; r < 16; ++r)
+      *reinterpret_cast<float4*>(red + ty * GB_RLD + r * 16 + tx * 4) =
+          make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    __syncthreads();
 #pragma unroll 8
-  for (int t = 0; t < 64; ++t) s += red[t * GB_RLD + tid];
+    for (int t = 0; t < 64; ++t) s += red[t * GB_RLD + tid];
+  }
+  if (ksplit > 1) {
+    // ship the partial tile into slot `rank` of the leader's shared memory (DSMEM), then cluster barrier
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(slots + rank * 256 + tid);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(s) : "memory");
+    cluster_sync_all();
+    if (rank != 0) return;
+    s = 0.f;
+    for (int r = 0; r < ksplit; ++r) s += slots[r * 256 + tid];
+  }
   const int row = r0 + (tid >> 4), n = n0 + (tid & 15);
-  if (row < b.R && n < p.N) p.C[(size_t)row * p.ldc + n] = s + (p.bias ? p.bias[n] : 0.f);
+  if (active && row < b.R && n < p.N) p.C[(size_t)row * p.ldc + n] = s + (p.bias ? p.bias[n] : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
