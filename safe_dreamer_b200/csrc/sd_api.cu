@@ -129,6 +129,8 @@ struct sd_handle {
   // heads workspace
   float *hv, *ho, *hl, *h_rew, *h_cont, *h_val, *kl_a, *kl_b, *kl_c;
   std::vector<GraphEntry> graphs;
+  float* part = nullptr;               // split-K partial slices of the tcgen05 GEMMs (kMaxParts x part_stride)
+  size_t part_stride = 0;
   float* wg_scratch = nullptr;         // row-slice partials of the weight-gradient pass
   size_t wg_scratch_elems = 0;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
@@ -164,14 +166,36 @@ static bool make_map(CUtensorMap* m, const bf16* ptr, uint64_t rows, uint64_t co
 }
 
 // ------------------------------------------------------------------------------------------------ launch ctx
+// SD_TRACE=1: record a CUDA event after every launch of a direct (non-graph) run and print per-kernel
+// in-stream time (launch gap + execution) when the call ends.  Diagnostic only (adds event overhead).
+static bool trace_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SD_TRACE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+struct TraceRec {
+  const char* what;
+  cudaEvent_t ev;
+};
 struct Ctx {
   sd_handle* h;
   cudaStream_t st;
   bool tc;        // tcgen05 path requested and eligible (rows >= 128)
   int err = 0;
   uint64_t launches = 0;
+  int last_ksplit = 1;   // split-K factor the most recent tcgen05 batch used (its consumer sums the slices)
+  std::vector<TraceRec>* trace = nullptr;
   void check(const char* what) {
     ++launches;
+    if (trace) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, st);
+      trace->push_back({what, e});
+    }
     if (err) return;
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
@@ -195,6 +219,22 @@ static bool pdl_enabled() {
   }
   return v == 1;
 }
+// All kernels ask for the same (maximum) shared-memory carve-out: consecutive kernels of a scan alternate
+// between 0 B and ~200 KB of dynamic shared memory, and an SM can only change its L1/shared split when it is
+// idle, which would serialise every kernel boundary.  SD_CARVEOUT=0 disables (for A/B measurements).
+static void prefer_max_smem(const void* kernel) {
+  static std::vector<const void*> done;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SD_CARVEOUT");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return;
+  for (const void* k : done) if (k == kernel) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  done.push_back(kernel);
+}
+
 // fp32 skinny GEMM launch: K is split over a thread-block cluster along grid.y (see gemm_f32_kernel).
 static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n, int max_k, int R) {
   static bool attr_done = false;
@@ -219,6 +259,7 @@ static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  prefer_max_smem((const void*)sd::gemm_f32_kernel);
   cudaLaunchKernelEx(&cfg, sd::gemm_f32_kernel, gb, ksplit, kslice);
 }
 
@@ -232,6 +273,7 @@ static void launch_k(cudaStream_t st, void (*kernel)(KArgs...), dim3 grid, dim3 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  prefer_max_smem((const void*)kernel);
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
 }
 
@@ -258,7 +300,17 @@ struct LinCall {  // one dense layer applied to (up to) two concatenated operand
   Operand a1; int K1;
   Operand a2;
   float* C; int ldc; int c_gstride;
+  float* parts = nullptr;  // split-K partial buffer mirroring C's layout (the consumer sums the slices); null = no split
 };
+constexpr int kMaxParts = 7;  // extra split-K slices the partial buffer can hold
+
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// measured on B200 (bench.py, N=1024): 64-wide tiles + split-K beat 256-wide tiles for rows < 4096 (2.47 vs 2.58 ms)
+static bool tc_wide_enabled() { static int v = env_flag("SD_TC_WIDE", 0); return v != 0; }
+static bool tc_split_enabled() { static int v = env_flag("SD_TC_SPLIT", 1); return v != 0; }
 
 template <int BN, int NST>
 static void launch_tc(Ctx& cx, const sd::tc::Batch& b, int ntiles_n, int R) {
@@ -268,13 +320,42 @@ static void launch_tc(Ctx& cx, const sd::tc::Batch& b, int ntiles_n, int R) {
     cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<BN, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     attr_done = true;
   }
-  dim3 grid(ntiles_n, (R + sd::tc::BM - 1) / sd::tc::BM, b.count);
+  dim3 grid(ntiles_n, (R + sd::tc::BM - 1) / sd::tc::BM, b.count * b.ksplit);
+  static long long* timing_dev = nullptr;
+  static int timing_budget = 40;
+  const bool timing = cx.trace && getenv("SD_TRACE_TC") && timing_budget > 0;
+  if (timing) {
+    if (!timing_dev) cudaMalloc(&timing_dev, 16 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 16 * sizeof(long long), cx.st);
+    sd::tc::Batch b2 = b;
+    b2.timing = timing_dev;
+    launch_k(cx.st, sd::tc::gemm_bf16_tc_kernel<BN, NST>, dim3(grid), dim3(sd::tc::THREADS), L::kTotal, b2);
+    cudaStreamSynchronize(cx.st);
+    long long t[16];
+    cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[SD_TRACE_TC] tc<%d,%d> grid=(%d,%d,%d) K=%d ksplit=%d cycles: alloc=%lld pdlwait=%lld tma0_issued=%lld "
+                    "first_full=%lld last_full=%lld acc_ready=%lld epi_done=%lld total=%lld\n",
+            BN, NST, grid.x, grid.y, grid.z, b.p[0].K, b.ksplit, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[2], t[5] - t[2],
+            t[6] - t[2], t[7] - t[6], t[8] - t[0]);
+    --timing_budget;
+  } else
   launch_k(cx.st, sd::tc::gemm_bf16_tc_kernel<BN, NST>, dim3(grid), dim3(sd::tc::THREADS), L::kTotal, b);
-  cx.check("gemm_bf16_tc_kernel");
+  if (cx.trace) {
+    static std::vector<std::string*> pool;  // trace labels must outlive the call (diagnostic mode only)
+    char buf[96];
+    snprintf(buf, sizeof(buf), "tc<%d,%d> grid=(%d,%d,%d) K=%d ksplit=%d", BN, NST, grid.x, grid.y, grid.z, b.p[0].K, b.ksplit);
+    std::string* found = nullptr;
+    for (auto* q : pool) if (*q == buf) found = q;
+    if (!found) { found = new std::string(buf); pool.push_back(found); }
+    cx.check(found->c_str());
+  } else {
+    cx.check("gemm_bf16_tc_kernel");
+  }
 }
 
 // Run a set of independent dense layers (same row count) as ONE launch per backend.
 static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
+  cx.last_ksplit = 1;
   if (cx.err) return;
   // ---- tcgen05 problems
   sd::tc::Batch tb;
@@ -286,6 +367,7 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
   gb.R = R;
   int max_n_f = 0;
   int max_k_f = 0;
+  size_t part_stride_elems = 0;
   auto flush_f = [&]() {
     if (gb.count == 0) return;
     launch_gemm_f32(cx.st, gb, max_n_f, max_k_f, R);
@@ -299,8 +381,26 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
     tb.count = ntc;
     tb.R = R;
     // small-N problems: 64-wide tiles spread the work over more SMs; wide ones use 256.
-    int max_kb = 0;
-    for (int i = 0; i < ntc; ++i) max_kb = tb.p[i].K / sd::tc::BK > max_kb ? tb.p[i].K / sd::tc::BK : max_kb;
+    int max_kb = 0, min_kb = 1 << 30;
+    bool can_split = true;
+    for (int i = 0; i < ntc; ++i) {
+      const int kb = tb.p[i].K / sd::tc::BK;
+      max_kb = kb > max_kb ? kb : max_kb;
+      min_kb = kb < min_kb ? kb : min_kb;
+      can_split = can_split && tb.p[i].Cpart != nullptr;
+    }
+    // split-K: when the tile grid cannot fill the machine and K is long, cut K into slices (more CTAs, shorter
+    // dependent TMA->MMA chains); the consumer (normact) adds the partial slices in a fixed order.
+    const int bn = batch_wide ? 256 : 64;
+    const int ctas = ((max_n_tc + bn - 1) / bn) * ((R + sd::tc::BM - 1) / sd::tc::BM) * ntc;
+    int ksplit = 1;
+    if (can_split && tc_split_enabled())
+      while (ksplit < kMaxParts + 1 && ctas * ksplit * 2 <= 160 && max_kb / (ksplit * 2) >= 4 && min_kb / (ksplit * 2) >= 1)
+        ksplit *= 2;
+    cx.last_ksplit = ksplit;
+    tb.ksplit = ksplit;
+    tb.part_stride = (long long)part_stride_elems;
+    if (ksplit > 1) max_kb = (max_kb + ksplit - 1) / ksplit;
     if (batch_wide) launch_tc<256, 4>(cx, tb, (max_n_tc + 255) / 256, R);
     else if (max_kb <= 4) launch_tc<64, 4>(cx, tb, (max_n_tc + 63) / 64, R);  // short K: 96 KB smem, 2 CTAs/SM
     else launch_tc<64, 8>(cx, tb, (max_n_tc + 63) / 64, R);
@@ -313,7 +413,11 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
     const bool use_tc = cx.tc && L.tc_ok() && (c.K1 % 64) == 0 && L.N >= 64 && c.a1.b && (K2 == 0 || c.a2.b);
     if (use_tc) {
       // maps: a1, (a2), w  -- one set per call, shared by its G block problems
-      const bool wide = (R >= 4096 && L.N >= 256);  // a batch never mixes tile widths
+      // 256-wide tiles when the layer is wide and either the row count is large, the layer is block-diagonal
+      // (many problems already fill the machine) or split-K will provide the parallelism; a batch never
+      // mixes tile widths.
+      const bool wide = L.N >= 256 && (L.N % 256) == 0 && (R >= 4096 || tc_wide_enabled()) &&
+                        (R >= 4096 || L.G > 1 || (c.parts && L.K >= 1024) || (ntc > 0 && batch_wide && c.parts));
       if (ntc > 0 && (wide != batch_wide || ntc + L.G > sd::tc::kMaxProblems || nmaps + 3 > sd::tc::kMaxMaps)) flush_tc();
       batch_wide = wide;
       const int m_a1 = nmaps++;
@@ -333,8 +437,10 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
         p.w_map = m_w;   p.w_row = g * L.npad;
         p.K1 = c.K1; p.K = L.K; p.N = L.N; p.ldc = c.ldc;
         p.C = c.C + (size_t)g * c.c_gstride;
+        p.Cpart = c.parts ? c.parts + (size_t)g * c.c_gstride : nullptr;
         p.bias = L.bias ? L.bias + (size_t)g * L.N : nullptr;
       }
+      part_stride_elems = cx.h->part_stride;
       if (L.N > max_n_tc) max_n_tc = L.N;
     } else {
       if (!c.a1.f || (K2 > 0 && !c.a2.f)) { cx.err = fail(SD_ERR_INVALID, "linear: fp32 operand missing"); return; }
@@ -355,9 +461,18 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
   flush_tc();
   flush_f();
 }
-static void linear(Ctx& cx, int R, const LinearW& L, Operand a1, int K1, Operand a2, float* C, int ldc, int c_gstride = 0) {
+static void linear(Ctx& cx, int R, const LinearW& L, Operand a1, int K1, Operand a2, float* C, int ldc, int c_gstride = 0,
+                   float* parts = nullptr) {
   LinCall c{&L, a1, K1, a2, C, ldc, c_gstride};
+  c.parts = (R <= cx.h->c.max_rows) ? parts : nullptr;
   linear_multi(cx, R, &c, 1);
+}
+// normact whose input may be the sum of split-K slices left by the preceding linear()
+static sd::NormActP with_parts(Ctx& cx, sd::NormActP p, const float* parts) {
+  p.parts = parts;
+  p.nparts = cx.last_ksplit - 1;
+  p.part_stride = (long long)cx.h->part_stride;
+  return p;
 }
 
 static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
@@ -368,8 +483,10 @@ static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
   launch_k(cx.st, sd::normact_kernel, dim3(dim3(R, n)), dim3(256), 0, b);
   cx.check("normact_kernel");
 }
-static sd::NormActP nap(const float* in, int ld_in, const float* w, int width, float* out, int ld_out, bf16* ob, int ld_bf) {
+static sd::NormActP nap(float* in, int ld_in, const float* w, int width, float* out, int ld_out, bf16* ob, int ld_bf,
+                        const float* parts = nullptr) {
   sd::NormActP p;
+  p.parts = parts; p.nparts = 0; p.part_stride = 0;
   p.in = in; p.ld_in = ld_in; p.w = w; p.out = out; p.ld_out = ld_out; p.out_bf = ob; p.ld_bf = ld_bf; p.width = width;
   return p;
 }
@@ -512,6 +629,13 @@ static void layout(sd_handle& h, Arena& a) {
   }
   h.emb_bf = a.take<bf16>(R * T * c.E);
   h.big_bf = a.take<bf16>(R * T * F);  // heads: bf16 copy of (N*H, F) feats
+  {
+    size_t w = 3 * (size_t)c.U;
+    if ((size_t)c.D > w) w = c.D;
+    if ((size_t)c.units > w) w = c.units;
+    h.part_stride = R * w;
+    h.part = a.take<float>(h.part_stride * 7);
+  }
   h.scratch_stoch = a.take<float>(R * SK);
   h.scratch_deter = a.take<float>(R * c.D);
   h.abar = a.take<float>(R * c.A);
@@ -766,8 +890,32 @@ template <class F>
 static int run(sd_handle* h, uint64_t key, uint32_t flags, cudaStream_t st, bool tc, F&& body) {
   auto direct = [&]() -> int {
     Ctx cx{h, st, tc};
+    std::vector<TraceRec> recs;
+    if (trace_enabled()) {
+      cx.trace = &recs;
+      cx.check("<begin>");
+    }
     body(cx);
     g_launches += cx.launches;
+    if (cx.trace && !recs.empty()) {
+      cudaStreamSynchronize(st);
+      std::vector<std::pair<std::string, std::pair<int, float>>> agg;
+      float total = 0.f;
+      for (size_t i = 1; i < recs.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, recs[i - 1].ev, recs[i].ev);
+        total += ms;
+        bool found = false;
+        for (auto& a : agg)
+          if (a.first == recs[i].what) { a.second.first++; a.second.second += ms; found = true; break; }
+        if (!found) agg.push_back({recs[i].what, {1, ms}});
+      }
+      fprintf(stderr, "[SD_TRACE] call key=%llx launches=%zu total=%.3f ms\n", (unsigned long long)key, recs.size() - 1, total);
+      for (auto& a : agg)
+        fprintf(stderr, "[SD_TRACE]   %-32s n=%5d total=%9.3f ms avg=%8.2f us\n", a.first.c_str(), a.second.first,
+                a.second.second, 1e3f * a.second.second / a.second.first);
+      for (auto& r : recs) cudaEventDestroy(r.ev);
+    }
     return cx.err;
   };
   if (!(flags & SD_FLAG_GRAPH)) return direct();
@@ -831,7 +979,7 @@ static StepBufs at_step(const StepBufs& s, size_t t, size_t rows, const sd_handl
 // Deter.forward (rssm.py:36-75).  z/d: stoch (R,SK) and deter (R,D) operands; abar: magnitude-normalised
 // action (R,A) fp32.  Writes the new deter (fp32, + bf16 copy on the tcgen05 path).
 static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d, const float* abar, float* deter_out,
-                       int ld_out, bf16* out_bf, int ld_bf) {
+                       int ld_out, bf16* out_bf, int ld_bf, bool v2_done = false) {
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
   const int U = c.U, D = c.D, Dg = h.Dg;
@@ -840,15 +988,18 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
       {&h.in1, z, h.SK, Operand(), sb.vin + U, 3 * U, 0},
       {&h.in2, opf(abar, c.A), c.A, Operand(), sb.vin + 2 * U, 3 * U, 0},
   };
-  linear_multi(cx, R, in, 3);
+  if (R <= c.max_rows) { in[0].parts = h.part; in[1].parts = h.part + U; }
+  linear_multi(cx, R, in, v2_done ? 2 : 3);  // the fused actor tail already wrote vin[:, 2U:3U]
   sd::NormActP na[3];
   const float* gains[3] = {h.in0.gain, h.in1.gain, h.in2.gain};
-  for (int j = 0; j < 3; ++j)
+  for (int j = 0; j < 3; ++j) {
     na[j] = nap(sb.vin + j * U, 3 * U, gains[j], U, sb.x + j * U, 3 * U, cx.tc ? h.x_bf + j * U : nullptr, 3 * U);
+    if (j < 2) na[j] = with_parts(cx, na[j], h.part + j * U);
+  }
   normact(cx, R, na, 3);
   Operand dg = d; dg.gstride = Dg;
-  linear(cx, R, h.hid, dg, Dg, opfb(sb.x, 3 * U, cx.tc ? h.x_bf : nullptr, 3 * U), sb.hpre, D, Dg);
-  sd::NormActP nh = nap(sb.hpre, D, h.hid.gain, D, sb.h, D, cx.tc ? h.h_bf : nullptr, D);
+  linear(cx, R, h.hid, dg, Dg, opfb(sb.x, 3 * U, cx.tc ? h.x_bf : nullptr, 3 * U), sb.hpre, D, Dg, h.part);
+  sd::NormActP nh = with_parts(cx, nap(sb.hpre, D, h.hid.gain, D, sb.h, D, cx.tc ? h.h_bf : nullptr, D), h.part);
   normact(cx, R, &nh, 1);
   linear(cx, R, h.gru, opfb(sb.h, D, cx.tc ? h.h_bf : nullptr, D, Dg), Dg, Operand(), sb.q, 3 * D, 3 * Dg);
   if (cx.err) return;
@@ -865,8 +1016,8 @@ static void latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* lay
   Operand cur1 = a1, cur2 = a2;
   int k1 = K1;
   for (int i = 0; i < nl; ++i) {
-    linear(cx, R, layers[i], cur1, k1, cur2, sb.vobs[i], U);
-    sd::NormActP p = nap(sb.vobs[i], U, layers[i].gain, U, sb.o[i], U, cx.tc ? h.o_bf[i] : nullptr, U);
+    linear(cx, R, layers[i], cur1, k1, cur2, sb.vobs[i], U, 0, h.part);
+    sd::NormActP p = with_parts(cx, nap(sb.vobs[i], U, layers[i].gain, U, sb.o[i], U, cx.tc ? h.o_bf[i] : nullptr, U), h.part);
     normact(cx, R, &p, 1);
     cur1 = opfb(sb.o[i], U, cx.tc ? h.o_bf[i] : nullptr, U);
     cur2 = Operand();
@@ -1041,8 +1192,8 @@ static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, f
   Operand cur = feat;
   int k = F;
   for (int i = 0; i < hw.layers; ++i) {
-    linear(cx, R, hw.l[i], cur, k, Operand(), v[i], units);
-    sd::NormActP p = nap(v[i], units, hw.l[i].gain, units, o[i], units, cx.tc ? o_bf[i] : nullptr, units);
+    linear(cx, R, hw.l[i], cur, k, Operand(), v[i], units, 0, h.part);
+    sd::NormActP p = with_parts(cx, nap(v[i], units, hw.l[i].gain, units, o[i], units, cx.tc ? o_bf[i] : nullptr, units), h.part);
     normact(cx, R, &p, 1);
     cur = opfb(o[i], units, cx.tc ? o_bf[i] : nullptr, units);
     k = units;
@@ -1077,13 +1228,33 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
       float* ft = feats + (size_t)t * F;
       Operand feat = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
       // action = actor(feat).rsample() (dreamer.py:684)
-      head_forward(cx, N, actor, feat, F, sb.va, sb.ao, h->a_bf, sb.aout, h->act_out);
-      if (cx.err) return;
-      {
+      const size_t tail_smem = sd::actor_tail_smem(h->act_out, c.units, A, c.U);
+      const bool fused_tail = h->act_out <= sd::kTailMaxOut && A <= 32 && c.units <= 256 && tail_smem <= 48 * 1024;
+      if (fused_tail) {
+        // trunk only; last layer + sampling + action normalisation + dyn_in2 projection run in one kernel
+        Operand cur = feat;
+        int k = F;
+        for (int i = 0; i < actor.layers; ++i) {
+          linear(cx, N, actor.l[i], cur, k, Operand(), sb.va[i], c.units, 0, h->part);
+          sd::NormActP p = with_parts(cx, nap(sb.va[i], c.units, actor.l[i].gain, c.units, sb.ao[i], c.units,
+                                              cx.tc ? h->a_bf[i] : nullptr, c.units), h->part);
+          normact(cx, N, &p, 1);
+          cur = opfb(sb.ao[i], c.units, cx.tc ? h->a_bf[i] : nullptr, c.units);
+          k = c.units;
+        }
+        if (cx.err) return;
+        launch_k(cx.st, sd::actor_tail_kernel, dim3((N * 32 + 255) / 256), dim3(256), tail_smem,
+                 (const float*)sb.ao[actor.layers - 1], c.units, c.units, (const float*)actor.last.wn, actor.last.ldk,
+                 (const float*)actor.last.bias, h->act_out, A, c.act_kind, c.min_std, c.max_std, c.act_unimix,
+                 act_noise + (size_t)t * A, H * A, (const float*)h->in2.wt, h->in2.ldw, (const float*)h->in2.bias, c.U, N,
+                 sb.aout, actions + (size_t)t * A, H * A, h->abar, sb.vin + 2 * c.U, 3 * c.U);
+        cx.check("actor_tail_kernel");
+      } else {
+        head_forward(cx, N, actor, feat, F, sb.va, sb.ao, h->a_bf, sb.aout, h->act_out);
+        if (cx.err) return;
         const int n = c.act_kind == 0 ? N * A : N;
-        launch_k(cx.st, sd::actor_sample_kernel, dim3((n + 127) / 128), dim3(128), 0, sb.aout, N, A, c.act_kind, c.min_std, c.max_std,
-                                                                    c.act_unimix, act_noise + (size_t)t * A, H * A,
-                                                                    actions + (size_t)t * A, H * A, h->abar);
+        launch_k(cx.st, sd::actor_sample_kernel, dim3((n + 127) / 128), dim3(128), 0, (const float*)sb.aout, N, A, c.act_kind,
+                 c.min_std, c.max_std, c.act_unimix, act_noise + (size_t)t * A, H * A, actions + (size_t)t * A, H * A, h->abar);
         cx.check("actor_sample_kernel");
       }
       if (tape) {  // what the dgrad-only backward needs beyond the pre-activations: deter_t, action_t, noise_t
@@ -1100,7 +1271,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
       const int ldn = ldf;
       Operand z = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
       Operand d = opfb(ft + SK, ldf, cx.tc ? h->feat_bf + SK : nullptr, F);
-      deter_core(cx, sb, N, z, d, h->abar, dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F);
+      deter_core(cx, sb, N, z, d, h->abar, dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F, fused_tail);
       latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit, opfb(dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F), D,
                     Operand(), sb.lg);
       sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, cx.tc ? h->feat_bf : nullptr, F, nullptr, 0);

@@ -316,7 +316,8 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 // y = SiLU(RMSNorm_width(v) * w): one CTA per (row, segment).  rssm.py:16-31,106-130; networks.py:325-327.
 struct NormActP {
-  const float* in; int ld_in;   // segment base (row 0), row stride
+  float* in; int ld_in;         // segment base (row 0), row stride; rewritten with the summed value when nparts > 0
+  const float* parts; int nparts; long long part_stride;  // split-K partial slices 1..nparts (same ld as `in`)
   const float* w;               // [width]
   float* out; int ld_out;       // nullable
   __nv_bfloat16* out_bf; int ld_bf; // nullable
@@ -331,13 +332,17 @@ __global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
   __shared__ float sh[32];
   const NormActP& p = b.p[blockIdx.y];
   const size_t row = blockIdx.x;
-  const float* in = p.in + row * p.ld_in;
+  float* in = p.in + row * p.ld_in;
   float v[8];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 256;
     v[i] = (c < p.width) ? in[c] : 0.f;
+    if (p.nparts > 0 && c < p.width) {   // fixed slice order => deterministic
+      for (int s = 0; s < p.nparts; ++s) v[i] += p.parts[s * p.part_stride + row * p.ld_in + c];
+      in[c] = v[i];
+    }
     ss = fmaf(v[i], v[i], ss);
   }
   ss = block_sum(ss, sh);
@@ -589,6 +594,105 @@ __global__ void actor_sample_kernel(const float* __restrict__ out, int R, int A,
         action[(size_t)row * ld_act + k] = v;
         abar[(size_t)row * A + k] = v;  // |v| <= 1: normalisation is the identity
       }
+  }
+}
+
+// Fused actor tail for the imagination rollout (dreamer.py:684 + rssm.py:44,48), one warp per row:
+//   out = W_last * a3 + b  (units -> act_out)          [networks.py:374-377]
+//   action = tanh(mean) + std * eps  |  one-hot Gumbel sample                [distributions.py:217-231]
+//   abar = action / max(|action|, 1)
+//   v2 = W_in2 * abar + b_in2  (A -> U), the pre-norm input projection of the action.
+// Replaces two skinny GEMM launches and the sampling kernel; fp32 throughout.
+constexpr int kTailMaxOut = 36;
+// dynamic shared memory: W_last [act_out][units] | b_last [act_out] | W_in2^T [A][U] | b_in2 [U]
+__host__ __device__ inline size_t actor_tail_smem(int act_out, int units, int A, int U) {
+  return ((size_t)act_out * units + act_out + (size_t)A * U + U) * sizeof(float);
+}
+__global__ void __launch_bounds__(256) actor_tail_kernel(const float* __restrict__ a3, int ld_a3, int units,
+                                                         const float* __restrict__ wl_n, int ldk_l,
+                                                         const float* __restrict__ bl, int act_out, int A, int act_kind,
+                                                         float min_std, float max_std, float unimix,
+                                                         const float* __restrict__ noise, int ld_n,
+                                                         const float* __restrict__ w2_t, int ldw_2,
+                                                         const float* __restrict__ b2, int U, int R, float* aout,
+                                                         float* action, int ld_act, float* abar, float* v2, int ld_v2) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float tsm[];
+  float* wl_s = tsm;                          // [act_out][units]
+  float* bl_s = wl_s + act_out * units;       // [act_out]
+  float* w2_s = bl_s + act_out;               // [A][U]
+  float* b2_s = w2_s + A * U;                 // [U]
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  // one global round trip: this row's activations and the CTA's share of the (tiny) weights are all in flight
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = lane + 32 * i;
+    x[i] = (row < R && k < units) ? a3[(size_t)row * ld_a3 + k] : 0.f;
+  }
+  const float nz = (row < R && lane < A) ? noise[(size_t)row * ld_n + lane] : 0.5f;
+  for (int i = threadIdx.x; i < act_out * units; i += blockDim.x) {
+    const int j = i / units, k = i - j * units;
+    wl_s[i] = __ldg(wl_n + (size_t)j * ldk_l + k);
+  }
+  for (int i = threadIdx.x; i < A * U; i += blockDim.x) {
+    const int a = i / U, n = i - a * U;
+    w2_s[i] = __ldg(w2_t + (size_t)a * ldw_2 + n);
+  }
+  for (int i = threadIdx.x; i < act_out; i += blockDim.x) bl_s[i] = bl[i];
+  for (int i = threadIdx.x; i < U; i += blockDim.x) b2_s[i] = b2[i];
+  __syncthreads();
+  if (row >= R) return;
+  float acc[kTailMaxOut];
+#pragma unroll
+  for (int j = 0; j < kTailMaxOut; ++j) {
+    acc[j] = 0.f;
+    if (j < act_out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = lane + 32 * i;
+        if (k < units) acc[j] = fmaf(x[i], wl_s[j * units + k], acc[j]);
+      }
+      acc[j] = warp_sum(acc[j]) + bl_s[j];
+    }
+  }
+  if (aout && lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kTailMaxOut; ++j)
+      if (j < act_out) aout[(size_t)row * act_out + j] = acc[j];
+  }
+  // action of this lane (lane < A)
+  float act = 0.f;
+  if (act_kind == 0) {
+    float mean = 0.f, sraw = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTailMaxOut; ++j) {
+      if (j == lane) mean = acc[j];
+      if (j == lane + A) sraw = acc[j];
+    }
+    if (lane < A) {
+      const float std = (max_std - min_std) * sigmoidf_(sraw + 2.f) + min_std;
+      act = tanhf(mean) + std * nz;
+    }
+  } else {
+    float lg = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTailMaxOut; ++j)
+      if (j == lane) lg = acc[j];
+    const bool valid = lane < A;
+    const int best = sample_group<32>(lg, nz, valid, lane, A, unimix, nullptr);
+    act = (valid && lane == best) ? 1.f : 0.f;
+  }
+  const float ab = act / fmaxf(fabsf(act), 1.f);
+  if (lane < A) {
+    action[(size_t)row * ld_act + lane] = act;
+    abar[(size_t)row * A + lane] = ab;
+  }
+  // v2[n] = sum_a W2t[a][n] * abar[a] + b2[n]
+  for (int n = lane; n < U; n += 32) {
+    float v = 0.f;
+    for (int a = 0; a < A; ++a) v = fmaf(__shfl_sync(0xffffffffu, ab, a), w2_s[a * U + n], v);
+    v2[(size_t)row * ld_v2 + n] = v + b2_s[n];
   }
 }
 

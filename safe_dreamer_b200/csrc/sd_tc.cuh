@@ -5,7 +5,8 @@
 // sm_100a only.  One CTA computes one 128 x BN output tile of one problem of the batch:
 //   warp 0    : TMA producer  (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4-stage mbarrier ring)
 //   warp 1    : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, kind::f16, M=128,N=BN,K=16)
-//   warps 2-5 : epilogue (tcgen05.ld 32x32b -> +bias -> fp32 global store), one TMEM lane quadrant each
+//   warps 2-9 : epilogue (tcgen05.ld 32x32b -> smem transpose -> +bias -> coalesced float4 stores), two warps per
+//               TMEM lane quadrant
 // Both operands are K-major (activations row-major [R x K], weights in nn.Linear [N x K] layout), so the
 // shared-memory tiles are the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect
 // (8-row x 128-byte swizzle atoms, SBO = 1024 B); K advances inside an atom by bumping the descriptor
@@ -26,7 +27,7 @@ namespace tc {
 
 constexpr int BM = 128;      // UMMA M (rows of the output tile == TMEM lanes)
 constexpr int BK = 64;       // K elements per stage: 64 bf16 = 128 B = one swizzle atom row
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;  // warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quadrant)
 constexpr int kMaxProblems = 8;
 constexpr int kMaxMaps = 12;
 
@@ -38,6 +39,7 @@ struct Problem {
   int N;               // logical output columns (store guard); tiles cover ceil(N/BN)*BN
   int ldc;
   float* C;
+  float* Cpart;        // split-K: slice s >= 1 writes to Cpart + (s-1)*part_stride (same ldc, no bias)
   const float* bias;   // nullable
 };
 struct alignas(64) Batch {
@@ -45,7 +47,11 @@ struct alignas(64) Batch {
   Problem p[kMaxProblems];
   int count;
   int R;
+  int ksplit;             // K is cut into `ksplit` slices over blockIdx.z / count (partials summed by the consumer)
+  long long part_stride;  // floats between partial slices
+  long long* timing;      // diagnostic (SD_TRACE=2): clock64 stamps of CTA (0,0,0); null in production
 };
+#define SD_TC_STAMP(i) do { if (batch.timing && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) batch.timing[i] = clock64(); } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -134,7 +140,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   static_assert(BN == 64 || BN == 128 || BN == 256, "TMEM allocation must be a power of two >= 32 columns");
   using L = SmemLayout<BN, NSTAGES>;
   constexpr int STAGES = L::STAGES;
-  const Problem& pr = batch.p[blockIdx.z];
+  const int prob = blockIdx.z % batch.count, slice = blockIdx.z / batch.count;
+  const Problem pr = batch.p[prob];  // by value: keeps the fields in registers instead of re-reading the param bank
   const int n0 = blockIdx.x * BN;
   if (n0 >= pr.N) return;  // whole CTA exits before any barrier/TMEM use
   const int m0 = blockIdx.y * BM;
@@ -149,7 +156,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen_base + L::kBarOff + STAGES * 16 + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = pr.K / BK;
+  if (threadIdx.x == 0) SD_TC_STAMP(0);
+  const int num_kb_all = pr.K / BK;
+  const int kb_per = (num_kb_all + batch.ksplit - 1) / batch.ksplit;
+  const int kb0 = slice * kb_per;
+  const int kb1 = min(num_kb_all, kb0 + kb_per);
+  const int num_kb = kb1 > kb0 ? kb1 - kb0 : 0;   // an empty slice just stores zeros
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -167,77 +179,117 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if (threadIdx.x == 0) SD_TC_STAMP(1);
   // PDL: barrier init / TMEM allocation above overlap the previous kernel; global memory is touched below.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) SD_TC_STAMP(2);
 
   if (warp == 0) {
     if (lane == 0) {
       const CUtensorMap* ma1 = &batch.maps[pr.a1_map];
       const CUtensorMap* ma2 = &batch.maps[pr.a2_map];
       const CUtensorMap* mw = &batch.maps[pr.w_map];
-      const int kb1 = pr.K1 / BK;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      const int kbA = pr.K1 / BK;  // k-blocks that come from A segment 1
+      for (int it = 0; it < num_kb; ++it) {
+        const int kb = kb0 + it;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(bar_empty + s * 8, ph ^ 1u);
         const uint32_t sa = base + s * L::kStage, sb = sa + L::kABytes;
         mbar_expect_tx(bar_full + s * 8, L::kStage);
-        if (kb < kb1) tma_load_2d(sa, ma1, pr.a1_col + kb * BK, m0, bar_full + s * 8);
-        else          tma_load_2d(sa, ma2, pr.a2_col + (kb - kb1) * BK, m0, bar_full + s * 8);
+        if (kb < kbA) tma_load_2d(sa, ma1, pr.a1_col + kb * BK, m0, bar_full + s * 8);
+        else          tma_load_2d(sa, ma2, pr.a2_col + (kb - kbA) * BK, m0, bar_full + s * 8);
         tma_load_2d(sb, mw, kb * BK, pr.w_row + n0, bar_full + s * 8);
+        if (it == 0) SD_TC_STAMP(3);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(bar_full + s * 8, ph);
+        if (it == 0) SD_TC_STAMP(4);
+        if (it == num_kb - 1) SD_TC_STAMP(5);
         tc_fence_after();
         const uint32_t sa = base + s * L::kStage, sb = sa + L::kABytes;
         const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sb);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)  // +32 B per UMMA_K inside the 128 B swizzle row => +2 in the >>4 field
-          tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
         tc_commit(bar_empty + s * 8);  // frees the smem stage once these MMAs have read it
       }
-      tc_commit(bar_acc);              // accumulator complete
+      if (num_kb > 0) tc_commit(bar_acc);  // accumulator complete
     }
   } else {
     // epilogue: warp w owns TMEM lanes [32*(w%4), +32) == output rows m0 + 32*(w%4) + lane
     const int quad = warp & 3;
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const int row = m0 + quad * 32 + lane;
-    float* crow = pr.C + (size_t)row * pr.ldc;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (row < batch.R) {
-        const int nb = n0 + c0;
-        if (nb + 32 <= pr.N && (pr.ldc & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (pr.bias) {
-              const float4 bb = *reinterpret_cast<const float4*>(pr.bias + nb + j);
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            *reinterpret_cast<float4*>(crow + nb + j) = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < pr.N) crow[nb + j] = v[j] + (pr.bias ? pr.bias[nb + j] : 0.f);
-        }
-      }
+    if (num_kb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
     }
+    if (threadIdx.x == 64) SD_TC_STAMP(6);
+    float* cbase = slice == 0 ? pr.C : pr.Cpart + (long long)(slice - 1) * batch.part_stride;
+    const float* bias = slice == 0 ? pr.bias : nullptr;
+    // Coalesced, vectorised epilogue.  tcgen05.ld hands each thread one ROW (32 consecutive columns); storing
+    // that directly issues 32 scattered 16-byte requests per instruction.  Each warp instead transposes its
+    // 32x32 block through a padded staging tile in the (now idle) pipeline shared memory and stores float4s
+    // so that every store instruction writes four full 128-byte row segments.  Two warps share each TMEM
+    // lane quadrant and split the tile's columns (a lone warp per SMSP is issue-latency bound).
+    const int half = (warp - 2) >> 2;                 // 0 or 1
+    constexpr int SLD = 36;                           // staging row stride in floats (16 B aligned, conflict free)
+    float* stage = reinterpret_cast<float*>(gen_base) + (warp - 2) * (32 * SLD);
+    const int row_base = m0 + quad * 32;
+    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
+    const bool vec_ok = (pr.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(cbase) & 15) == 0;
+#pragma unroll 1
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+      float v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stage + lane * SLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      const int col = n0 + c0 + c4;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) {
+        if (col + 0 < pr.N) bv.x = bias[col + 0];
+        if (col + 1 < pr.N) bv.y = bias[col + 1];
+        if (col + 2 < pr.N) bv.z = bias[col + 2];
+        if (col + 3 < pr.N) bv.w = bias[col + 3];
+      }
+      float* cptr = cbase + (size_t)(row_base + sub_r) * pr.ldc + col;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + sub_r;
+        float4 o = *reinterpret_cast<const float4*>(stage + rr * SLD + c4);
+        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+        if (row_base + rr < batch.R) {
+          if (vec_ok && col + 3 < pr.N) {
+            *reinterpret_cast<float4*>(cptr) = o;
+          } else {
+            if (col + 0 < pr.N) cptr[0] = o.x;
+            if (col + 1 < pr.N) cptr[1] = o.y;
+            if (col + 2 < pr.N) cptr[2] = o.z;
+            if (col + 3 < pr.N) cptr[3] = o.w;
+          }
+        }
+        cptr += (size_t)4 * pr.ldc;
+      }
+      __syncwarp();
+    }
+    if (threadIdx.x == 64) SD_TC_STAMP(7);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SD_TC_STAMP(8);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
