@@ -236,7 +236,7 @@ static void prefer_max_smem(const void* kernel) {
 }
 
 // fp32 skinny GEMM launch: K is split over a thread-block cluster along grid.y (see gemm_f32_kernel).
-static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n, int max_k, int R) {
+static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n, int max_k, int R, bool gates = false) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
@@ -248,18 +248,35 @@ static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n,
   if (kslice > sd::GB_KC) kslice = sd::GB_KC;  // K > 4096 is rejected by validate()
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((max_n + 15) / 16, ksplit, gb.count * ((R + 15) / 16));
+  cfg.gridDim = dim3((gates ? 3 : 1) * ((max_n + 15) / 16), ksplit, gb.count * ((R + 15) / 16));
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = sd::GB_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ksplit; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = gates ? 3 : 1; attr[0].val.clusterDim.y = ksplit; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   prefer_max_smem((const void*)sd::gemm_f32_kernel);
+  static long long* timing_dev = nullptr;
+  static int timing_budget = 24;
+  if (getenv("SD_TRACE_G") && timing_budget > 0) {
+    if (!timing_dev) cudaMalloc(&timing_dev, 16 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 16 * sizeof(long long), st);
+    sd::GemmBatch g2 = gb;
+    g2.timing = timing_dev;
+    cudaLaunchKernelEx(&cfg, sd::gemm_f32_kernel, g2, ksplit, kslice);
+    cudaStreamSynchronize(st);
+    long long t[16];
+    cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[SD_TRACE_G] grid=(%d,%d,%d) K=%d ksplit=%d epi=%d cycles: pdlwait=%lld loads+sts=%lld fma=%lld reduce=%lld "
+                    "cluster=%lld tail=%lld total=%lld\n", cfg.gridDim.x, cfg.gridDim.y, cfg.gridDim.z, max_k, ksplit, gb.p[0].epi,
+            t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] ? t[5] - t[4] : 0, t[6] - (t[5] ? t[5] : t[4]), t[6] - t[0]);
+    --timing_budget;
+    return;
+  }
   cudaLaunchKernelEx(&cfg, sd::gemm_f32_kernel, gb, ksplit, kslice);
 }
 
@@ -310,6 +327,7 @@ static int env_flag(const char* name, int dflt) {
 }
 // measured on B200 (bench.py, N=1024): 64-wide tiles + split-K beat 256-wide tiles for rows < 4096 (2.47 vs 2.58 ms)
 static bool tc_wide_enabled() { static int v = env_flag("SD_TC_WIDE", 0); return v != 0; }
+static bool fused_epi_enabled() { static int v = env_flag("SD_FUSED_EPI", 1); return v != 0; }
 static bool tc_split_enabled() { static int v = env_flag("SD_TC_SPLIT", 1); return v != 0; }
 
 template <int BN, int NST>
@@ -1001,6 +1019,25 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
   linear(cx, R, h.hid, dg, Dg, opfb(sb.x, 3 * U, cx.tc ? h.x_bf : nullptr, 3 * U), sb.hpre, D, Dg, h.part);
   sd::NormActP nh = with_parts(cx, nap(sb.hpre, D, h.hid.gain, D, sb.h, D, cx.tc ? h.h_bf : nullptr, D), h.part);
   normact(cx, R, &nh, 1);
+  if (!cx.tc && Dg <= sd::GB_KC && c.G <= sd::kMaxBatch && !out_bf && fused_epi_enabled()) {
+    // fp32 path: gate projection + GRU gate math in ONE launch (cluster of 3 CTAs per 16 units, see EPI_GATES)
+    sd::GemmBatch gb;
+    memset(&gb, 0, sizeof(gb));
+    gb.R = R;
+    for (int g = 0; g < c.G; ++g) {
+      sd::GemmP& p = gb.p[gb.count++];
+      p.A = sb.h + (size_t)g * Dg; p.lda = D; p.A2 = nullptr; p.lda2 = 0; p.K1 = Dg; p.K = Dg;
+      p.Wt = h.gru.wt + (size_t)g * Dg * h.gru.ldw; p.ldw = h.gru.ldw;
+      p.bias = h.gru.bias + (size_t)g * 3 * Dg;
+      p.C = sb.q + (size_t)g * 3 * Dg; p.ldc = 3 * D; p.N = Dg;
+      p.epi = sd::EPI_GATES; p.e_k = Dg;
+      p.e_in = d.f + (size_t)g * Dg; p.e_ld_in = d.ldf;
+      p.e_out = deter_out + (size_t)g * Dg; p.e_ld_out = ld_out;
+    }
+    launch_gemm_f32(cx.st, gb, Dg, Dg, R, true);
+    cx.check("gemm_f32_kernel(gru+gates)");
+    return;
+  }
   linear(cx, R, h.gru, opfb(sb.h, D, cx.tc ? h.h_bf : nullptr, D, Dg), Dg, Operand(), sb.q, 3 * D, 3 * Dg);
   if (cx.err) return;
   launch_k(cx.st, sd::gates_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, sb.q, d.f, d.ldf, deter_out, ld_out, out_bf, ld_bf,
@@ -1009,8 +1046,13 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
 }
 
 // [Linear -> RMSNorm -> SiLU] x layers -> Linear(SK) (rssm.py:106-130).  Returns raw logits in `lg`.
-static void latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* layers, int nl, const LinearW& last,
-                          Operand a1, int K1, Operand a2, float* lg) {
+struct SampleOut {  // when given (and the fp32 path is used) the last layer samples in its epilogue
+  const float* u; int ld_u;
+  float* stoch; int ld_st;
+  float* logits; int ld_lg;  // nullable copy of the logits (the `logits` output of observe)
+};
+static bool latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* layers, int nl, const LinearW& last,
+                          Operand a1, int K1, Operand a2, float* lg, const SampleOut* so = nullptr) {
   sd_handle& h = *cx.h;
   const int U = h.c.U;
   Operand cur1 = a1, cur2 = a2;
@@ -1023,7 +1065,26 @@ static void latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* lay
     cur2 = Operand();
     k1 = U;
   }
+  if (so && !cx.tc && cur2.f == nullptr && k1 <= sd::GB_KC && (16 % h.c.K) == 0 && fused_epi_enabled()) {
+    sd::GemmBatch gb;
+    memset(&gb, 0, sizeof(gb));
+    gb.R = R;
+    sd::GemmP& p = gb.p[gb.count++];
+    p.A = cur1.f; p.lda = cur1.ldf; p.A2 = nullptr; p.lda2 = 0; p.K1 = k1; p.K = k1;
+    p.Wt = last.wt; p.ldw = last.ldw; p.bias = last.bias;
+    p.C = lg; p.ldc = h.SK; p.N = h.SK;
+    p.epi = sd::EPI_SAMPLE; p.e_k = h.c.K; p.e_f = h.c.unimix;
+    p.e_in = so->u; p.e_ld_in = so->ld_u;
+    p.e_out = so->stoch; p.e_ld_out = so->ld_st;
+    p.e_out2 = so->logits; p.e_ld_out2 = so->ld_lg;
+    if (!cx.err) {
+      launch_gemm_f32(cx.st, gb, h.SK, k1, R);
+      cx.check("gemm_f32_kernel(logit+sample)");
+    }
+    return true;   // sampled
+  }
   linear(cx, R, last, cur1, k1, cur2, lg, h.SK);
+  return false;
 }
 
 static void sample(Ctx& cx, int R, const float* lg, const float* u, int ld_u, float* stoch, int ld_o, bf16* stoch_bf,
@@ -1103,13 +1164,18 @@ extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, co
                  cx.tc ? h->h_bf : nullptr, D);
       // posterior logits on [deter' | embed_t] (rssm.py:171-173); h_bf is free again after the gru GEMM,
       // so it carries the bf16 copy of deter' on the tcgen05 path.
-      latent_logits(cx, sb, B, h->obs, c.obs_layers, h->obs_logit, opfb(dout, T * D, cx.tc ? h->h_bf : nullptr, D), D,
-                    opfb(embed + (size_t)t * E, T * E, cx.tc ? h->emb_bf + (size_t)t * E : nullptr, T * E), sb.lg);
-      sample(cx, B, sb.lg, u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, nullptr, 0,
-             logits + (size_t)t * SK, T * SK);
-      if (tape) copy_f32(cx, u + (size_t)t * SK, T * SK, sb.ucopy, SK, B, SK);
+      SampleOut so{u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, logits + (size_t)t * SK, T * SK};
+      const bool sampled = latent_logits(cx, sb, B, h->obs, c.obs_layers, h->obs_logit,
+                                         opfb(dout, T * D, cx.tc ? h->h_bf : nullptr, D), D,
+                                         opfb(embed + (size_t)t * E, T * E, cx.tc ? h->emb_bf + (size_t)t * E : nullptr, T * E),
+                                         sb.lg, &so);
+      if (!sampled)
+        sample(cx, B, sb.lg, u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, nullptr, 0,
+               logits + (size_t)t * SK, T * SK);
     }
-    if (tape && !cx.err) {  // deter' and embed in step-major layout for the batched weight-gradient pass
+    if (tape && !cx.err) {  // u, deter' and embed in step-major layout for the backward / weight-gradient pass
+      launch_k(cx.st, sd::bt_to_tb_kernel, dim3(grid1d((long long)B * T * SK, 256)), dim3(256), 0, u, h->tape.ucopy, B, T, SK);
+      cx.check("bt_to_tb_kernel");
       launch_k(cx.st, sd::bt_to_tb_kernel, dim3(grid1d((long long)B * T * D, 256)), dim3(256), 0, deters, h->tape.dnew, B, T, D);
       cx.check("bt_to_tb_kernel");
       launch_k(cx.st, sd::bt_to_tb_kernel, dim3(grid1d((long long)B * T * E, 256)), dim3(256), 0, embed, h->tape.emb, B, T, E);
@@ -1176,9 +1242,10 @@ extern "C" int sd_imagine_with_action(sd_handle* h, int R, int T, const float* s
       deter_core(cx, sb, R, opfb(sb.zin, SK, cx.tc ? h->feat_bf : nullptr, h->F),
                  opfb(sb.din, D, cx.tc ? h->feat_bf + SK : nullptr, h->F), sb.ain, dout, T * D,
                  cx.tc ? h->h_bf : nullptr, D);
-      latent_logits(cx, sb, R, h->img, c.img_layers, h->img_logit, opfb(dout, T * D, cx.tc ? h->h_bf : nullptr, D), D,
-                    Operand(), sb.lg);
-      sample(cx, R, sb.lg, u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, nullptr, 0, nullptr, 0);
+      SampleOut so{u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, nullptr, 0};
+      if (!latent_logits(cx, sb, R, h->img, c.img_layers, h->img_logit, opfb(dout, T * D, cx.tc ? h->h_bf : nullptr, D), D,
+                         Operand(), sb.lg, &so))
+        sample(cx, R, sb.lg, u + (size_t)t * SK, T * SK, stochs + (size_t)t * SK, T * SK, nullptr, 0, nullptr, 0);
     }
   });
 }
@@ -1272,9 +1339,10 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
       Operand z = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
       Operand d = opfb(ft + SK, ldf, cx.tc ? h->feat_bf + SK : nullptr, F);
       deter_core(cx, sb, N, z, d, h->abar, dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F, fused_tail);
-      latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit, opfb(dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F), D,
-                    Operand(), sb.lg);
-      sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, cx.tc ? h->feat_bf : nullptr, F, nullptr, 0);
+      SampleOut so{u + (size_t)t * SK, H * SK, ft + F, ldf, nullptr, 0};
+      if (!latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit,
+                         opfb(dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F), D, Operand(), sb.lg, &so))
+        sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, cx.tc ? h->feat_bf : nullptr, F, nullptr, 0);
     }
   });
   if (rc == 0 && tape) { h->tape_valid = true; h->tape_B = N; h->tape_T = H; h->tape_kind = 2; }

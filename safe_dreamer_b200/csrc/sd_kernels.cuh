@@ -25,6 +25,53 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x / (1.f + expf(-x)); }
+
+
+// Lane-per-class variant of sample_category for the hot kernels: the group of `GS` lanes (GS = pow2 >= K)
+// that shares a category reduces with shuffles.  Same operation sequence per element as above.
+template <int GS>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int GS>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// returns the first-max class index of y = softmax(l + g) for this lane's category (valid on all lanes)
+template <int GS>
+__device__ __forceinline__ int sample_group(float lg, float u, bool valid, int k, int K, float unimix, float* y_out) {
+  const float NEG = -INFINITY;
+  const float m = group_max<GS>(valid ? lg : NEG);
+  float e = valid ? expf(lg - m) : 0.f;
+  const float s = group_sum<GS>(e);
+  float l = valid ? logf((e / s) * (1.f - unimix) + unimix / (float)K) : NEG;
+  const float m2 = group_max<GS>(l);
+  const float s2 = group_sum<GS>(valid ? expf(l - m2) : 0.f);
+  const float lse = m2 + logf(s2);
+  float z = valid ? (l - lse) + (-logf(-logf(u))) : NEG;
+  const float m3 = group_max<GS>(z);
+  const float ez = valid ? expf(z - m3) : 0.f;
+  const float s3 = group_sum<GS>(ez);
+  const float y = valid ? ez / s3 : NEG;
+  if (y_out) *y_out = y;
+  // arg-first-max over the group: max value, ties -> smallest index
+  float bv = y;
+  int bi = valid ? k : 0x7fffffff;
+#pragma unroll
+  for (int o = GS / 2; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  return bi;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Batched skinny GEMM:  C[R x N] = [A | A2][R x K] * Wt[K x N] + bias, fp32.
 // A CTA owns a 16-row x 16-column output tile and splits K over its 64 thread groups (intra-CTA
@@ -37,15 +84,31 @@ struct GemmP {
   const float* A2;   // [R x (K-K1)], row stride lda2 (second K segment; may be null when K1 == K)
   const float* Wt;   // [K x ldw] (n contiguous, ldw % 16 == 0, zero padded)
   const float* bias; // [N] or null
-  float* C;          // [R x N], row stride ldc
+  float* C;          // [R x N], row stride ldc (nullable for the fused epilogues when no tape is kept)
   int lda, lda2, K1, K, ldw, ldc, N;
+  // fused epilogues (K <= 512 only, i.e. no split-K cluster along y):
+  //  EPI_GATES : the problem is one block of the gate projection, N = Dg; a cluster of 3 CTAs computes the
+  //              reset / cand / update tiles of the same 16 units and the leader applies the GRU gate math
+  //              (rssm.py:63-75) writing deter' (e_out); C receives q in the reference layout [r|c|u].
+  //  EPI_SAMPLE: N = S*Kc logits; each 16-column tile holds 16/Kc whole categories; the CTA samples them
+  //              (distributions.py:16-36) from uniforms e_in, writes the one-hot (e_out), the logits (e_out2)
+  //              and C (raw logits for the backward tape).
+  int epi;
+  const float* e_in; int e_ld_in;
+  float* e_out; int e_ld_out;
+  float* e_out2; int e_ld_out2;
+  int e_k;           // Dg (gates) or Kc (sample)
+  float e_f;         // unimix (sample)
 };
+enum { EPI_STORE = 0, EPI_GATES = 1, EPI_SAMPLE = 2 };
 constexpr int kMaxBatch = 8;
 struct GemmBatch {
   int count;
   int R;
+  long long* timing;   // diagnostic (SD_TRACE_TC): clock64 stamps of CTA 0; null in production
   GemmP p[kMaxBatch];
 };
+#define SD_G_STAMP(i) do { if (b.timing && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) b.timing[i] = clock64(); } while (0)
 
 constexpr int GB_KC = 512;           // largest K slice one CTA handles (staged in shared memory)
 constexpr int GB_XLD = GB_KC + 4;    // padded row stride of the staged activations
@@ -69,18 +132,23 @@ __device__ __forceinline__ void cluster_sync_all() {
 // thread-group partials through shared memory, and ships its 16x16 partial tile to the cluster leader through
 // distributed shared memory; the leader adds the slices in rank order (deterministic) and stores.
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ksplit, int kslice) {
+  SD_G_STAMP(0);
   pdl_prologue();
+  SD_G_STAMP(1);
   const int prob = blockIdx.z % b.count, rtile = blockIdx.z / b.count;
   const GemmP& p = b.p[prob];
-  const int n0 = blockIdx.x * 16;
-  const bool active = n0 < p.N;           // whole clusters are inactive together (same blockIdx.x / z)
+  const bool gates = p.epi == EPI_GATES;   // cluster = (3,1,1): blockIdx.x = tile*3 + gate
+  const int gate = gates ? (int)(blockIdx.x % 3) : 0;
+  const int n0 = gates ? (int)(blockIdx.x / 3) * 16 : blockIdx.x * 16;
+  const bool active = n0 < p.N;           // whole clusters are inactive together
   const int r0 = rtile * 16;
-  const int rank = (int)blockIdx.y;        // == cluster rank (cluster spans gridDim.y)
+  const int rank = gates ? gate : (int)blockIdx.y;   // == cluster rank
+  const int wcol = gates ? gate * p.e_k + n0 : n0;   // first weight column of this CTA's tile
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;
   float* slots = smem + (GB_SMEM / 4 - GB_MAXSPLIT * 256);   // leader: one 16x16 tile per rank
   const int tid = threadIdx.x, tx = tid & 3, ty = tid >> 2;
-  const int kc = rank * kslice;
+  const int kc = gates ? 0 : rank * kslice;
   const int kend = min(p.K, kc + kslice);
   float s = 0.f;
   if (active && kc < kend) {
@@ -97,29 +165,63 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = kbase + j;
-        w[i][j] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + n0 + tx * 4))
+        w[i][j] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + wcol + tx * 4))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    float v[32];
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int kk = kc + hf * 256 + tid;
+    // activation slice -> shared memory.  Fast path: 16-byte loads/stores (thread owns 8 float4 = 2 rows x 4
+    // quads... precisely: quad q = tid & 127 of rows 2*i + (tid >> 7)); needs 16 B aligned rows and a segment
+    // boundary on a multiple of 4.  Otherwise scalar (thread owns columns tid and tid+256 of all 16 rows).
+    const bool vec = ((p.lda & 3) == 0) && ((p.K1 & 3) == 0) && ((kc & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
+                     (p.K1 == p.K || (((p.lda2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A2) & 15) == 0)));
+    if (vec) {
+      float4 v4[8];
+      const int q = tid & 127, rsel = tid >> 7;
+      const int kk = kc + q * 4;
       const bool in1 = kk < p.K1;
       const float* src = in1 ? p.A + kk : p.A2 + (kk - p.K1);
       const size_t ld = in1 ? p.lda : p.lda2;
-      const bool kok = kk < kend;
+      const bool kok = kk < kend;   // kend and K1 are multiples of 4 on this path or the tail quad is zero-padded below
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const int row = r0 + r;
-        v[r * 2 + hf] = (kok && row < b.R) ? __ldg(src + (size_t)row * ld) : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        const int row = r0 + 2 * i + rsel;
+        v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kok && row < b.R) {
+          if (kk + 3 < kend) {
+            v4[i] = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * ld));
+          } else {  // ragged tail of the slice
+            const float* s1 = src + (size_t)row * ld;
+            v4[i].x = s1[0];
+            if (kk + 1 < kend) v4[i].y = s1[1];
+            if (kk + 2 < kend) v4[i].z = s1[2];
+          }
+        }
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(xs + (2 * i + rsel) * GB_XLD + q * 4) = v4[i];
+    } else {
+      float v[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int kk = kc + hf * 256 + tid;
+        const bool in1 = kk < p.K1;
+        const float* src = in1 ? p.A + kk : p.A2 + (kk - p.K1);
+        const size_t ld = in1 ? p.lda : p.lda2;
+        const bool kok = kk < kend;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int row = r0 + r;
+          v[r * 2 + hf] = (kok && row < b.R) ? __ldg(src + (size_t)row * ld) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int r = 0; r < 16; ++r) xs[r * GB_XLD + hf * 256 + tid] = v[r * 2 + hf];
     }
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-      for (int r = 0; r < 16; ++r) xs[r * GB_XLD + hf * 256 + tid] = v[r * 2 + hf];
     __syncthreads();
+    SD_G_STAMP(2);
 #pragma unroll
     for (int i = 0; i < GB_KC / 4 / 64; ++i) {
       const int kq = ty + 64 * i;
@@ -139,14 +241,48 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
       }
     }
     __syncthreads();
+    SD_G_STAMP(3);
     float* red = smem;
 #pragma unroll
     for (int r = 0; r < 16; ++r)
       *reinterpret_cast<float4*>(red + ty * GB_RLD + r * 16 + tx * 4) =
           make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
     __syncthreads();
-#pragma unroll 8
-    for (int t = 0; t < 64; ++t) s += red[t * GB_RLD + tid];
+    {  // 64 k-group partials per output: four interleaved chains (fixed order => deterministic), then combine
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 64; t += 4) {
+        s0 += red[(t + 0) * GB_RLD + tid];
+        s1 += red[(t + 1) * GB_RLD + tid];
+        s2 += red[(t + 2) * GB_RLD + tid];
+        s3 += red[(t + 3) * GB_RLD + tid];
+      }
+      s = (s0 + s1) + (s2 + s3);
+    }
+    SD_G_STAMP(4);
+  }
+  const int row = r0 + (tid >> 4), cc = tid & 15, n = n0 + cc;
+  if (gates) {
+    // slots of the leader: [gate][256]; every CTA ships its full-K tile, the leader applies the gate math
+    const uint32_t local = (uint32_t)__cvta_generic_to_shared(slots + gate * 256 + tid);
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(s) : "memory");
+    cluster_sync_all();
+    if (gate != 0 || !active || row >= b.R || n >= p.N) return;
+    const int Dg = p.e_k;
+    const float qr = slots[tid] + (p.bias ? p.bias[n] : 0.f);
+    const float qc = slots[256 + tid] + (p.bias ? p.bias[Dg + n] : 0.f);
+    const float qu = slots[512 + tid] + (p.bias ? p.bias[2 * Dg + n] : 0.f);
+    if (p.C) {
+      float* q = p.C + (size_t)row * p.ldc;
+      q[n] = qr; q[Dg + n] = qc; q[2 * Dg + n] = qu;
+    }
+    const float reset = sigmoidf_(qr);
+    const float cand = tanhf(reset * qc);
+    const float upd = sigmoidf_(qu - 1.f);
+    p.e_out[(size_t)row * p.e_ld_out + n] = upd * cand + (1.f - upd) * p.e_in[(size_t)row * p.e_ld_in + n];
+    return;
   }
   if (ksplit > 1) {
     // ship the partial tile into slot `rank` of the leader's shared memory (DSMEM), then cluster barrier
@@ -155,12 +291,32 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(s) : "memory");
     cluster_sync_all();
+    SD_G_STAMP(5);
     if (rank != 0) return;
     s = 0.f;
     for (int r = 0; r < ksplit; ++r) s += slots[r * 256 + tid];
   }
-  const int row = r0 + (tid >> 4), n = n0 + (tid & 15);
-  if (active && row < b.R && n < p.N) p.C[(size_t)row * p.ldc + n] = s + (p.bias ? p.bias[n] : 0.f);
+  const bool ok = active && row < b.R && n < p.N;
+  const float val = s + ((p.bias && ok) ? p.bias[n] : 0.f);
+  if (p.epi == EPI_SAMPLE) {
+    // 16 consecutive threads own the 16 logits of one (row, tile): 16/Kc whole categories
+    const int Kc = p.e_k;
+    const int kcls = cc % Kc;
+    const float uu = ok ? p.e_in[(size_t)row * p.e_ld_in + n] : 0.5f;
+    int best;
+    if (Kc == 16) best = sample_group<16>(val, uu, ok, kcls, Kc, p.e_f, nullptr);
+    else if (Kc == 8) best = sample_group<8>(val, uu, ok, kcls, Kc, p.e_f, nullptr);
+    else if (Kc == 4) best = sample_group<4>(val, uu, ok, kcls, Kc, p.e_f, nullptr);
+    else best = sample_group<2>(val, uu, ok, kcls, Kc, p.e_f, nullptr);
+    if (ok) {
+      if (p.C) p.C[(size_t)row * p.ldc + n] = val;
+      if (p.e_out2) p.e_out2[(size_t)row * p.e_ld_out2 + n] = val;
+      p.e_out[(size_t)row * p.e_ld_out + n] = (kcls == best) ? 1.f : 0.f;
+    }
+    return;
+  }
+  if (ok) p.C[(size_t)row * p.ldc + n] = val;
+  SD_G_STAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,9 +445,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int G, int N, 
 // ------------------------------------------------------------------------------------------------
 // Row-wise helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float siluf_(float x) { return x / (1.f + expf(-x)); }
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -420,49 +573,6 @@ __device__ __forceinline__ int sample_category(const float* lg, const float* u, 
       if (y > bv) { bv = y; best = k; }
     }
   return best;
-}
-
-// Lane-per-class variant of sample_category for the hot kernels: the group of `GS` lanes (GS = pow2 >= K)
-// that shares a category reduces with shuffles.  Same operation sequence per element as above.
-template <int GS>
-__device__ __forceinline__ float group_max(float v) {
-#pragma unroll
-  for (int o = GS / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-template <int GS>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-  for (int o = GS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// returns the first-max class index of y = softmax(l + g) for this lane's category (valid on all lanes)
-template <int GS>
-__device__ __forceinline__ int sample_group(float lg, float u, bool valid, int k, int K, float unimix, float* y_out) {
-  const float NEG = -INFINITY;
-  const float m = group_max<GS>(valid ? lg : NEG);
-  float e = valid ? expf(lg - m) : 0.f;
-  const float s = group_sum<GS>(e);
-  float l = valid ? logf((e / s) * (1.f - unimix) + unimix / (float)K) : NEG;
-  const float m2 = group_max<GS>(l);
-  const float s2 = group_sum<GS>(valid ? expf(l - m2) : 0.f);
-  const float lse = m2 + logf(s2);
-  float z = valid ? (l - lse) + (-logf(-logf(u))) : NEG;
-  const float m3 = group_max<GS>(z);
-  const float ez = valid ? expf(z - m3) : 0.f;
-  const float s3 = group_sum<GS>(ez);
-  const float y = valid ? ez / s3 : NEG;
-  if (y_out) *y_out = y;
-  // arg-first-max over the group: max value, ties -> smallest index
-  float bv = y;
-  int bi = valid ? k : 0x7fffffff;
-#pragma unroll
-  for (int o = GS / 2; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-  }
-  return bi;
 }
 
 // Sample all S categories of R rows.  logits (R, S*K) row stride ld_l; u (R, S*K) row stride ld_u.
