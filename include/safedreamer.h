@@ -123,6 +123,11 @@ int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs, const floa
 /* RSSM.prior (rssm.py:189-195) on R rows: logit = _img_net(deter); stoch = rsample. */
 int sd_prior(sd_handle* h, int R, const float* deter, const float* u, float* stoch, float* logit,
              uint32_t flags, void* stream);
+/* Backward of the last SD_FLAG_SAVE_TAPE sd_prior (autograd of rssm.py:189-195 as used at dreamer.py:485-486):
+ *   d_stoch (R,S,K) nullable, d_logit (R,S,K) nullable (not both) -> d_deter (R,D) nullable; weight_grads as in
+ *   sd_observe_bwd (only the _img_net slots are touched; accumulated). */
+int sd_prior_bwd(sd_handle* h, int R, const float* d_stoch, const float* d_logit, float* d_deter,
+                 float* const* weight_grads, uint32_t flags, void* stream);
 /* RSSM.imagine_with_action (rssm.py:197-209); T == 1 is RSSM.img_step (rssm.py:180-187).
  *   stoch (R,S,K) deter (R,D) actions (R,T,A) u (R,T,S,K) -> stochs (R,T,S,K) deters (R,T,D) */
 int sd_imagine_with_action(sd_handle* h, int R, int T, const float* stoch, const float* deter,

@@ -71,6 +71,7 @@ _SIGS = {
     "sd_observe_fwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 9 + [C.c_uint32, _P]),
     "sd_observe_bwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 6 + [C.POINTER(_P), C.c_uint32, _P]),
     "sd_prior": (C.c_int, [_P, C.c_int] + [_P] * 4 + [C.c_uint32, _P]),
+    "sd_prior_bwd": (C.c_int, [_P, C.c_int] + [_P] * 3 + [C.POINTER(_P), C.c_uint32, _P]),
     "sd_imagine_with_action": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 6 + [C.c_uint32, _P]),
     "sd_imagine_fwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 6 + [C.c_uint32, _P]),
     "sd_imagine_bwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 4 + [C.c_uint32, _P]),

@@ -121,6 +121,9 @@ struct sd_handle {
   StepBufs tape;      // taped (max_tape_rows x max_steps)
   BwdBufs bw;
   int tape_kind = 0;  // 1 = observe, 2 = imagine
+  StepBufs pt;        // batched prior (dreamer.py:485): activations over up to max_rows*max_steps rows
+  BwdBufs pbw;
+  int ptape_R = 0;
   int tape_B = 0, tape_T = 0;
   bool tape_valid = false;
   // bf16 staging for the tcgen05 path
@@ -670,6 +673,25 @@ static void layout(sd_handle& h, Arena& a) {
   h.kl_a = a.take<float>(NH * c.S);
   h.kl_b = a.take<float>(NH * c.S);
   h.kl_c = a.take<float>(NH * c.S);
+  // batched prior: only the fields latent_logits / latent_logits_bwd touch
+  memset(&h.pt, 0, sizeof(h.pt));
+  memset(&h.pbw, 0, sizeof(h.pbw));
+  for (int i = 0; i < c.img_layers; ++i) {
+    h.pt.vobs[i] = a.take<float>(NH * c.U);
+    h.pt.o[i] = a.take<float>(NH * c.U);
+  }
+  h.pt.lg = a.take<float>(NH * SK);
+  if (c.max_tape_rows > 0) {
+    h.pt.ucopy = a.take<float>(NH * SK);
+    h.pt.dnew = a.take<float>(NH * c.D);
+    h.pbw.d_lg = a.take<float>(NH * SK);
+    for (int i = 0; i < c.img_layers; ++i) {
+      h.pbw.d_v[i] = a.take<float>(NH * c.U);
+      h.pbw.dmn_v[i] = a.take<float>(NH * c.U);
+    }
+    h.pbw.t_do = a.take<float>(NH * c.U);
+    h.pbw.t_dxe = a.take<float>(NH * c.D);
+  }
 }
 
 static void describe_weights(sd_handle& h) {
@@ -1052,16 +1074,17 @@ struct SampleOut {  // when given (and the fp32 path is used) the last layer sam
   float* logits; int ld_lg;  // nullable copy of the logits (the `logits` output of observe)
 };
 static bool latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* layers, int nl, const LinearW& last,
-                          Operand a1, int K1, Operand a2, float* lg, const SampleOut* so = nullptr) {
+                          Operand a1, int K1, Operand a2, float* lg, const SampleOut* so = nullptr, bf16* obf = nullptr) {
   sd_handle& h = *cx.h;
   const int U = h.c.U;
+  bf16* obfs[4] = {obf ? obf : h.o_bf[0], obf ? obf : h.o_bf[1], obf ? obf : h.o_bf[2], obf ? obf : h.o_bf[3]};
   Operand cur1 = a1, cur2 = a2;
   int k1 = K1;
   for (int i = 0; i < nl; ++i) {
     linear(cx, R, layers[i], cur1, k1, cur2, sb.vobs[i], U, 0, h.part);
-    sd::NormActP p = with_parts(cx, nap(sb.vobs[i], U, layers[i].gain, U, sb.o[i], U, cx.tc ? h.o_bf[i] : nullptr, U), h.part);
+    sd::NormActP p = with_parts(cx, nap(sb.vobs[i], U, layers[i].gain, U, sb.o[i], U, cx.tc ? obfs[i] : nullptr, U), h.part);
     normact(cx, R, &p, 1);
-    cur1 = opfb(sb.o[i], U, cx.tc ? h.o_bf[i] : nullptr, U);
+    cur1 = opfb(sb.o[i], U, cx.tc ? obfs[i] : nullptr, U);
     cur2 = Operand();
     k1 = U;
   }
@@ -1195,22 +1218,26 @@ extern "C" int sd_prior(sd_handle* h, int R, const float* deter, const float* u,
   if (!deter || !u || !stoch || !logit) return fail(SD_ERR_INVALID, "sd_prior: null tensor");
   if (!h->rssm_set) return fail(SD_ERR_WEIGHTS, "sd_prior: RSSM weights not set");
   const sd_config& c = h->c;
-  // batched over (B,T) rows (dreamer.py:485): chunk by max_rows so the step buffers suffice
+  const bool tape = flags & SD_FLAG_SAVE_TAPE;
+  if (tape && c.max_tape_rows <= 0) return fail(SD_ERR_WORKSPACE, "sd_prior: handle was created without a tape (max_tape_rows=0)");
+  if (tape) h->ptape_R = 0;
+  // batched over all (B,T) rows in one pass (dreamer.py:485)
   Key key;
   key.add(2).add(R).add(deter).add(u).add(stoch).add(logit).add(flags);
-  const bool tc_req = (flags & SD_FLAG_BF16) != 0;
-  return run(h, key.v, flags, (cudaStream_t)stream, tc_req, [&](Ctx& cx) {
-    for (int r0 = 0; r0 < R && !cx.err; r0 += c.max_rows) {
-      const int n = (R - r0) < c.max_rows ? (R - r0) : c.max_rows;
-      cx.tc = tc_req && n >= 128;
-      const float* d = deter + (size_t)r0 * c.D;
-      if (cx.tc) cast_bf(cx, d, c.D, h->h_bf, c.D, n, c.D);
-      latent_logits(cx, h->sb, n, h->img, c.img_layers, h->img_logit, opfb(d, c.D, cx.tc ? h->h_bf : nullptr, c.D), c.D,
-                    Operand(), h->sb.lg);
-      sample(cx, n, h->sb.lg, u + (size_t)r0 * h->SK, h->SK, stoch + (size_t)r0 * h->SK, h->SK, nullptr, 0,
-             logit + (size_t)r0 * h->SK, h->SK);
+  const bool tc = (flags & SD_FLAG_BF16) && R >= 128 && c.U <= c.units;
+  int rc = run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
+    if (cx.tc) cast_bf(cx, deter, c.D, h->big_bf, c.D, R, c.D);
+    SampleOut so{u, h->SK, stoch, h->SK, logit, h->SK};
+    if (!latent_logits(cx, h->pt, R, h->img, c.img_layers, h->img_logit, opfb(deter, c.D, cx.tc ? h->big_bf : nullptr, c.D),
+                       c.D, Operand(), h->pt.lg, &so, h->trunk_bf))
+      sample(cx, R, h->pt.lg, u, h->SK, stoch, h->SK, nullptr, 0, logit, h->SK);
+    if (tape) {
+      copy_f32(cx, u, h->SK, h->pt.ucopy, h->SK, R, h->SK);
+      copy_f32(cx, deter, c.D, h->pt.dnew, c.D, R, c.D);
     }
   });
+  if (rc == 0 && tape) h->ptape_R = R;
+  return rc;
 }
 
 extern "C" int sd_imagine_with_action(sd_handle* h, int R, int T, const float* stoch, const float* deter,
@@ -1627,6 +1654,45 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
     if (cx.err) return;
     cudaMemcpyAsync(d_stoch0, bw.carry_z, (size_t)N * SK * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
     cudaMemcpyAsync(d_deter0, bw.carry_d, (size_t)N * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+  });
+}
+
+// Backward of the last SD_FLAG_SAVE_TAPE sd_prior: d_logit (+ optional d_stoch through the straight-through
+// sample) -> d_deter and the _img_net weight gradients (accumulated into the RSSM gradient slots).
+extern "C" int sd_prior_bwd(sd_handle* h, int R, const float* d_stoch, const float* d_logit, float* d_deter,
+                            float* const* wg, uint32_t flags, void* stream) {
+  if (!h) return fail(SD_ERR_INVALID, "sd_prior_bwd: null handle");
+  if (h->ptape_R != R || R < 1) return fail(SD_ERR_NO_TAPE, "sd_prior_bwd: no matching SD_FLAG_SAVE_TAPE sd_prior(R=%d)", R);
+  if (!d_stoch && !d_logit) return fail(SD_ERR_INVALID, "sd_prior_bwd: no upstream gradient");
+  const sd_config& c = h->c;
+  const int SK = h->SK, D = c.D, U = c.U;
+  Key key;
+  key.add(13).add(R).add(d_stoch).add(d_logit).add(d_deter).add(flags);
+  const int nw = (int)h->wdesc[SD_MOD_RSSM].size();
+  for (int i = 0; i < nw; ++i) key.add(wg ? wg[i] : nullptr);
+  std::vector<float*> W(nw, nullptr);
+  if (wg) for (int i = 0; i < nw; ++i) W[i] = wg[i];
+  return run(h, key.v, flags, (cudaStream_t)stream, false, [&](Ctx& cx) {
+    const BwdBufs& bw = h->pbw;
+    const StepBufs& pt = h->pt;
+    const float* d_lg = d_logit;
+    if (d_stoch) {
+      sample_bwd(cx, pt.lg, SK, pt.ucopy, SK, d_stoch, SK, nullptr, 0, d_logit, SK, R, c.S, c.K, c.unimix, bw.d_lg, SK);
+      d_lg = bw.d_lg;
+    }
+    latent_logits_bwd(cx, pt, bw, 0, R, h->img, c.img_layers, h->img_logit, d_lg, bw.t_dxe);
+    if (cx.err) return;
+    if (d_deter) cudaMemcpyAsync(d_deter, bw.t_dxe, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
+    if (!wg) return;
+    int i = 14 + 3 * c.obs_layers + 2;
+    for (int l = 0; l < c.img_layers; ++l, i += 3) {
+      if (l == 0) wgrad_linear(cx, R, h->img[0], false, bw.d_v[0], U, 0, pt.dnew, D, 0, D, nullptr, 0, W[i]);
+      else wgrad_linear(cx, R, h->img[l], false, bw.d_v[l], U, 0, pt.o[l - 1], U, 0, U, nullptr, 0, W[i]);
+      colsum(cx, bw.d_v[l], U, R, U, W[i + 1]);
+      colsum(cx, bw.dmn_v[l], U, R, U, W[i + 2]);
+    }
+    wgrad_linear(cx, R, h->img_logit, false, d_lg, SK, 0, pt.o[c.img_layers - 1], U, 0, U, nullptr, 0, W[i]);
+    colsum(cx, d_lg, SK, R, SK, W[i + 1]);
   });
 }
 

@@ -161,10 +161,25 @@ class Engine:
         deter, u = _f32c(deter, "deter").reshape(-1, c.D), _f32c(u, "u")
         R = deter.shape[0]
         assert u.numel() == R * self.SK
-        stoch, logit = self._new(R, c.S, c.K), self._new(R, c.S, c.K)
+        deter, u = self._stage(deter, "pr_d"), self._stage(u, "pr_u")
+        stoch, logit = self._new(R, c.S, c.K, tag="pr_s"), self._new(R, c.S, c.K, tag="pr_l")
         _lib.check(self.lib.sd_prior(self.h, R, _ptr(deter), _ptr(u), _ptr(stoch), _ptr(logit), flags, self.stream),
                    "sd_prior")
         return stoch.reshape(*lead, c.S, c.K), logit.reshape(*lead, c.S, c.K)
+
+    def prior_bwd(self, R, d_stoch, d_logit, want_deter=True, weight_grads=None, flags=0):
+        c = self.cfg
+        ds = None if d_stoch is None else self._stage(_f32c(d_stoch, "d_stoch"), "pds")
+        dl = None if d_logit is None else self._stage(_f32c(d_logit, "d_logit"), "pdl")
+        d_deter = self._new(R, c.D, tag="pr_dd") if want_deter else None
+        arr = None
+        if weight_grads is not None:
+            names = self.weight_names(MOD_RSSM)
+            arr = (C.c_void_p * len(names))(*[0 if weight_grads.get(n) is None else weight_grads[n].data_ptr()
+                                              for n in names])
+        _lib.check(self.lib.sd_prior_bwd(self.h, R, _ptr(ds), _ptr(dl), _ptr(d_deter), arr, flags, self.stream),
+                   "sd_prior_bwd")
+        return d_deter
 
     def imagine_with_action(self, stoch, deter, actions, u, flags=0):
         c = self.cfg

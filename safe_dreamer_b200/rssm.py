@@ -146,6 +146,36 @@ class _ObserveFn(torch.autograd.Function):
         return (None, d_embed, None, d_is, d_id, None, None, *pg)
 
 
+class _PriorFn(torch.autograd.Function):
+    """batched prior forward/backward through the C ABI (sd_prior / sd_prior_bwd)."""
+
+    @staticmethod
+    def forward(ctx, rssm, deter, u, *params):
+        lead = deter.shape[:-1]
+        rows = int(math.prod(lead))
+        eng = rssm._get_engine(min(rows, rssm.max_rows), 1, tape=True, tape_rows=1)
+        stoch, logit = eng.prior(deter, u, flags=rssm._flags() | SD_FLAG_SAVE_TAPE)
+        ctx.rssm, ctx.rows, ctx.lead = rssm, rows, lead
+        ctx.need = (ctx.needs_input_grad[1], any(ctx.needs_input_grad[3:]))
+        ctx.flags = rssm._flags()
+        return stoch, logit
+
+    @staticmethod
+    def backward(ctx, d_stoch, d_logit):
+        rssm = ctx.rssm
+        eng = rssm._rt.engine
+        need_deter, need_w = ctx.need
+        wg = None
+        if need_w:
+            wg = {n: (torch.zeros_like(p, dtype=torch.float32) if n.startswith("_img_net") else None)
+                  for n, p in rssm.named_parameters()}
+        d_deter = eng.prior_bwd(ctx.rows, d_stoch, d_logit, need_deter, wg, ctx.flags)
+        if d_deter is not None:
+            d_deter = d_deter.reshape(*ctx.lead, -1).clone()
+        pg = [None if wg is None else wg[n] for n, _ in rssm.named_parameters()]
+        return (None, d_deter, None, *pg)
+
+
 class RSSM(nn.Module):
     """world_model/rssm.py:78-230 with the scans in CUDA."""
 
@@ -201,10 +231,10 @@ class RSSM(nn.Module):
                     E=self._embed_size, A=self._act_dim, obs_layers=self._obs_layers, img_layers=self._img_layers,
                     unimix=self._unimix_ratio)
 
-    def _get_engine(self, rows, steps, tape=False, extra=None):
+    def _get_engine(self, rows, steps, tape=False, extra=None, tape_rows=None):
         rt = self._rt
         need = (max(rows, rt.limits[0], self.max_rows), max(steps, rt.limits[1], self.max_steps),
-                max(rows if tape else 0, rt.limits[2]))
+                max((rows if tape_rows is None else tape_rows) if tape else 0, rt.limits[2]))
         if rt.engine is None or need != rt.limits:
             kw = self.engine_dims()
             kw.update(getattr(self, "_head_dims", {}))
@@ -278,7 +308,7 @@ class RSSM(nn.Module):
             eng = self._get_engine(self.max_rows, -(-rows // self.max_rows))
         u = self._uniform(*lead, self._stoch, self._discrete)
         if torch.is_grad_enabled() and (deter.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("RSSM.prior backward is not available in this build (forward-only entry)")
+            return _PriorFn.apply(self, deter.float(), u, *self.parameters())
         return eng.prior(deter, u, flags=self._flags())
 
     def imagine_with_action(self, stoch, deter, actions):
