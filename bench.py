@@ -219,12 +219,28 @@ def run_gpu(args):
     ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions)), args.steps)
     ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out), args.steps)
     ms_heads = timed(lambda: eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs), args.steps)
-    ms_obs_fb = None
+    ms_obs_fb = ms_wm = None
     if have_bwd:
         def fb():
             eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | TAPE, out=obs_out)
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
         ms_obs_fb = timed(fb, args.steps)
+        # one world-model update: observe fwd + batched prior + kl values + backward of all of them
+        up = torch.rand(N, c.S, c.K, device=dev).clamp_(1e-6, 1 - 1e-6)
+        gpl = torch.randn(N, c.S, c.K, device=dev) * 0.01
+
+        def wm():
+            bucket.zero_()
+            st_, dt_, lg_ = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | TAPE, out=obs_out)
+            pst, plog = eng.prior(dt_.reshape(N, c.D), up, flags=GRAPH | TAPE | BF16)
+            eng.kl_loss(lg_, plog, 1.0)
+            d_dt = eng.prior_bwd(N, None, gpl, True, wgrads, flags=GRAPH)
+            eng.observe_bwd(B, T, gst, d_dt.reshape(B, T, c.D), glg, True, True, wgrads, flags=GRAPH)
+            bucket.allreduce_async()
+            bucket.wait()
+        for _ in range(3):
+            wm()
+        ms_wm = timed(wm, args.steps)
     # ---- end-to-end through the public module API with HOST buffers (pinned) and a D2H result read
     from types import SimpleNamespace as NS
     from safe_dreamer_b200 import dreamer_ops
@@ -318,7 +334,9 @@ def run_gpu(args):
                        "l2": "256 MB flush write between timed iterations (outside the event pairs)",
                        "multi_gpu": "each rank scans its own replay slice; RSSM grad all-reduce (NCCL) overlapped with imagination" if have_bwd else "replicas only"},
             "gpu_launches": int(launches),
-            "breakdown_ms": {"observe_fwd": ms_obs / args.steps, "observe_fwd_bwd": None if ms_obs_fb is None else ms_obs_fb / args.steps,
+            "world_model_updates_per_s": None if ms_wm is None else world * args.steps / (ms_wm * 1e-3),
+            "posterior_steps_per_s_fwd_bwd": None if ms_obs_fb is None else world * N * args.steps / (ms_obs_fb * 1e-3),
+            "breakdown_ms": {"observe_fwd": ms_obs / args.steps, "world_model_update": None if ms_wm is None else ms_wm / args.steps, "observe_fwd_bwd": None if ms_obs_fb is None else ms_obs_fb / args.steps,
                              "imagine_fwd": ms_imag / args.steps, "heads_lambda": ms_heads / args.steps},
             "roofline": {"bound": "tensor", "achieved": imag_tflops, "peak": sus, "unit": "TFLOP/s", "frac": imag_tflops / sus,
                          "traffic": None, "kernel": "sd_imagine_fwd scan (tcgen05 GEMMs + fused row kernels, one CUDA graph)",
