@@ -1062,6 +1062,38 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
     cx.check("gemm_f32_kernel(gru+gates)");
     return;
   }
+  if (cx.tc && sb.stride == 0 && (Dg % 64) == 0 && c.G <= sd::tc::kMaxProblems && h.gru.tc_ok() && fused_epi_enabled() &&
+      out_bf != h.h_bf /* the bf16 output must not alias this GEMM's A operand */) {
+    // tcgen05 path, no tape: gate projection with the GRU gate math fused in the epilogue (192-wide tiles =
+    // reset|cand|update of 64 units); q is never materialised.
+    sd::tc::Batch tb;
+    memset(&tb, 0, sizeof(tb));
+    bool ok = make_map(&tb.maps[0], h.h_bf, (uint64_t)R, (uint64_t)D, (uint64_t)D, 128);
+    ok = ok && make_map(&tb.maps[1], h.gru.w_bf, (uint64_t)c.G * h.gru.npad, (uint64_t)Dg, (uint64_t)Dg, 64);
+    if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed"); return; }
+    for (int g = 0; g < c.G; ++g) {
+      sd::tc::Problem& p = tb.p[g];
+      p.a1_map = 0; p.a1_col = g * Dg; p.a2_map = 0; p.a2_col = 0;
+      p.w_map = 1; p.w_row = g * h.gru.npad;
+      p.K1 = Dg; p.K = Dg; p.N = Dg; p.ldc = 0; p.C = nullptr; p.Cpart = nullptr;
+      p.bias = h.gru.bias + (size_t)g * 3 * Dg;
+      p.e_in = d.f + (size_t)g * Dg; p.e_ld_in = d.ldf;
+      p.e_out = deter_out + (size_t)g * Dg; p.e_ld_out = ld_out;
+      p.e_out_bf = out_bf ? out_bf + (size_t)g * Dg : nullptr; p.e_ld_bf = ld_bf;
+      p.e_dg = Dg;
+    }
+    tb.count = c.G; tb.R = R; tb.ksplit = 1; tb.part_stride = 0; tb.timing = nullptr;
+    using LG = sd::tc::SmemLayout<192, 4>;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<192, 4, sd::tc::EPI_GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG::kTotal);
+      attr_done = true;
+    }
+    launch_k(cx.st, sd::tc::gemm_bf16_tc_kernel<192, 4, sd::tc::EPI_GATES>, dim3(Dg / 64, (R + 127) / 128, c.G),
+             dim3(sd::tc::THREADS), LG::kTotal, tb);
+    cx.check("tc<192,4,gates>");
+    return;
+  }
   linear(cx, R, h.gru, opfb(sb.h, D, cx.tc ? h.h_bf : nullptr, D, Dg), Dg, Operand(), sb.q, 3 * D, 3 * Dg);
   if (cx.err) return;
   launch_k(cx.st, sd::gates_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, sb.q, d.f, d.ldf, deter_out, ld_out, out_bf, ld_bf,

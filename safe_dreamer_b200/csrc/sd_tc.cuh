@@ -41,7 +41,13 @@ struct Problem {
   float* C;
   float* Cpart;        // split-K: slice s >= 1 writes to Cpart + (s-1)*part_stride (same ldc, no bias)
   const float* bias;   // nullable
+  // EPI_GATES (BN = 192 = reset|cand|update of 64 units): GRU gate math in the epilogue (rssm.py:63-75)
+  const float* e_in; int e_ld_in;         // deter entering the step
+  float* e_out; int e_ld_out;             // deter' fp32
+  __nv_bfloat16* e_out_bf; int e_ld_bf;   // deter' bf16 (next tcgen05 operand), nullable
+  int e_dg;                               // units per block (weight rows of one gate)
 };
+enum { EPI_STORE = 0, EPI_GATES = 1 };
 struct alignas(64) Batch {
   CUtensorMap maps[kMaxMaps];
   Problem p[kMaxProblems];
@@ -135,14 +141,16 @@ struct SmemLayout {
   static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + tmem slot, + 1 KB alignment slack
 };
 
-template <int BN, int NSTAGES>
+template <int BN, int NSTAGES, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ Batch batch) {
-  static_assert(BN == 64 || BN == 128 || BN == 256, "TMEM allocation must be a power of two >= 32 columns");
+  static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported tile width");
+  static_assert(EPI == EPI_STORE || BN == 192, "the gate epilogue uses 192-wide tiles (3 gates x 64 units)");
+  constexpr int TMEM_COLS = BN == 192 ? 256 : BN;   // allocations are powers of two >= 32 columns
   using L = SmemLayout<BN, NSTAGES>;
   constexpr int STAGES = L::STAGES;
   const int prob = blockIdx.z % batch.count, slice = blockIdx.z / batch.count;
   const Problem pr = batch.p[prob];  // by value: keeps the fields in registers instead of re-reading the param bank
-  const int n0 = blockIdx.x * BN;
+  const int n0 = blockIdx.x * (EPI == EPI_GATES ? 64 : BN);   // gates: first of this tile's 64 units
   if (n0 >= pr.N) return;  // whole CTA exits before any barrier/TMEM use
   const int m0 = blockIdx.y * BM;
 
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -200,7 +208,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
         mbar_expect_tx(bar_full + s * 8, L::kStage);
         if (kb < kbA) tma_load_2d(sa, ma1, pr.a1_col + kb * BK, m0, bar_full + s * 8);
         else          tma_load_2d(sa, ma2, pr.a2_col + (kb - kbA) * BK, m0, bar_full + s * 8);
-        tma_load_2d(sb, mw, kb * BK, pr.w_row + n0, bar_full + s * 8);
+        if (EPI == EPI_GATES) {  // three 64-row boxes: the reset / cand / update rows of this tile's units
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            tma_load_2d(sb + j * (64 * BK * 2), mw, kb * BK, pr.w_row + j * pr.e_dg + n0, bar_full + s * 8);
+        } else {
+          tma_load_2d(sb, mw, kb * BK, pr.w_row + n0, bar_full + s * 8);
+        }
         if (it == 0) SD_TC_STAMP(3);
       }
     }
@@ -231,6 +245,48 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       tc_fence_after();
     }
     if (threadIdx.x == 64) SD_TC_STAMP(6);
+    if (EPI == EPI_GATES) {
+      // warp (quad, half) owns rows [32*quad, +32) and units [n0 + 32*half, +32): its reset / cand / update
+      // pre-activations are TMEM columns 32*half, 64 + 32*half, 128 + 32*half.
+      const int halfg = (warp - 2) >> 2;
+      constexpr int SLDG = 33;
+      float* stg = reinterpret_cast<float*>(gen_base) + (warp - 2) * (32 * SLDG);
+      const int rb = m0 + quad * 32;
+      const int u0 = n0 + halfg * 32;
+      // stage deter_in[32 rows][32 units] with coalesced loads (lane = unit), then read it row-wise
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr)
+        stg[rr * SLDG + lane] = (rb + rr < batch.R) ? pr.e_in[(size_t)(rb + rr) * pr.e_ld_in + u0 + lane] : 0.f;
+      __syncwarp();
+      float qr[32], qc[32], qu[32];
+      const uint32_t tb = tmem_base + ((uint32_t)(quad * 32) << 16);
+      tmem_ld32(tb + (uint32_t)(halfg * 32), qr);
+      tmem_ld32(tb + (uint32_t)(64 + halfg * 32), qc);
+      tmem_ld32(tb + (uint32_t)(128 + halfg * 32), qu);
+      float outv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float br = pr.bias ? pr.bias[u0 + j] : 0.f;
+        const float bc = pr.bias ? pr.bias[pr.e_dg + u0 + j] : 0.f;
+        const float bu = pr.bias ? pr.bias[2 * pr.e_dg + u0 + j] : 0.f;
+        const float reset = 1.f / (1.f + expf(-(qr[j] + br)));
+        const float cand = tanhf(reset * (qc[j] + bc));
+        const float upd = 1.f / (1.f + expf(-((qu[j] + bu) - 1.f)));
+        outv[j] = upd * cand + (1.f - upd) * stg[lane * SLDG + j];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * SLDG + j] = outv[j];
+      __syncwarp();
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        if (rb + rr < batch.R) {
+          const float o = stg[rr * SLDG + lane];
+          pr.e_out[(size_t)(rb + rr) * pr.e_ld_out + u0 + lane] = o;
+          if (pr.e_out_bf) pr.e_out_bf[(size_t)(rb + rr) * pr.e_ld_bf + u0 + lane] = __float2bfloat16(o);
+        }
+      }
+    } else {
     float* cbase = slice == 0 ? pr.C : pr.Cpart + (long long)(slice - 1) * batch.part_stride;
     const float* bias = slice == 0 ? pr.bias : nullptr;
     // Coalesced, vectorised epilogue.  tcgen05.ld hands each thread one ROW (32 consecutive columns); storing
@@ -285,6 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
       }
       __syncwarp();
     }
+    }  // EPI_STORE
     if (threadIdx.x == 64) SD_TC_STAMP(7);
   }
   tc_fence_before();
@@ -292,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_c
   if (threadIdx.x == 0) SD_TC_STAMP(8);
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
