@@ -1444,6 +1444,35 @@ static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, 
   launch_gemm_f32(cx.st, gb, L.K, L.N, R);
   cx.check("gemm_f32_kernel(dgrad)");
 }
+// Several independent single-block dgrads (same row count) in one launch; `col0`/`ncols` select a range of the
+// layer's input columns so one layer can scatter its input gradient to two destinations.
+struct DgradCall {
+  const LinearW* L;
+  const float* dy; int ld_dy;
+  float* dx; int ld_dx;
+  int col0, ncols;   // input-column range [col0, col0+ncols) of L (ncols = 0 => all)
+};
+static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n) {
+  if (cx.err) return;
+  sd::GemmBatch gb;
+  memset(&gb, 0, sizeof(gb));
+  gb.R = R;
+  int max_n = 0, max_k = 0;
+  for (int i = 0; i < n; ++i) {
+    const LinearW& L = *calls[i].L;
+    const int nc = calls[i].ncols ? calls[i].ncols : L.K;
+    sd::GemmP& p = gb.p[gb.count++];
+    p.A = calls[i].dy; p.lda = calls[i].ld_dy; p.A2 = nullptr; p.lda2 = 0;
+    p.K1 = L.N; p.K = L.N;
+    p.Wt = L.wn + calls[i].col0; p.ldw = L.ldk;
+    p.bias = nullptr;
+    p.C = calls[i].dx; p.ldc = calls[i].ld_dx; p.N = nc;
+    if (nc > max_n) max_n = nc;
+    if (L.N > max_k) max_k = L.N;
+  }
+  launch_gemm_f32(cx.st, gb, max_n, max_k, R);
+  cx.check("gemm_f32_kernel(dgrad)");
+}
 template <int GS>
 static void launch_sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
                               const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
@@ -1463,7 +1492,8 @@ static void sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int l
 }
 // Backward of latent_logits: d(logits) -> d(layer-0 input) [R x K0] in `dx0`; fills the d-tape slots.
 static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, const LinearW* layers,
-                              int nl, const LinearW& last, const float* d_lg, float* dx0) {
+                              int nl, const LinearW& last, const float* d_lg, float* dx0, int k_first = 0,
+                              float* dx0_b = nullptr, int ld_b = 0) {
   sd_handle& h = *cx.h;
   const int U = h.c.U;
   dgrad(cx, R, last, d_lg, h.SK, 0, bw.t_do, U, 0);
@@ -1472,13 +1502,20 @@ static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, si
     sd::NormActBwdP p = nbp(bw.t_do, U, sb.vobs[i], U, layers[i].gain, U, dv, U, bw.dmn_v[i] + slot * U, U);
     normact_bwd(cx, R, &p, 1);
     if (i > 0) dgrad(cx, R, layers[i], dv, U, 0, bw.t_do, U, 0);
-    else dgrad(cx, R, layers[0], dv, U, 0, dx0, layers[0].K, 0);
+    else if (k_first > 0) {
+      // input gradient split in two column ranges: [0, k_first) -> dx0 (row stride k_first), the rest -> dx0_b
+      // (e.g. straight into d_embed[:, t]); the second range is skipped when nobody wants it
+      DgradCall dc[2] = {{&layers[0], dv, U, dx0, k_first, 0, k_first},
+                         {&layers[0], dv, U, dx0_b, ld_b, k_first, layers[0].K - k_first}};
+      dgrad_multi(cx, R, dc, dx0_b ? 2 : 1);
+    } else dgrad(cx, R, layers[0], dv, U, 0, dx0, layers[0].K, 0);
   }
 }
 // Backward of deter_core given g = d(deter') in bw.gd: leaves d(deter_in) parts in bw.dd (+ bw.t_din0),
 // d(stoch) in bw.t_dz and, when want_act, d(abar) in bw.d_abar.
 static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, bool want_act,
-                           const float* deter_in, int ld_in) {
+                           const float* deter_in, int ld_in, const float* ga, int ld_a, const float* gb, int ld_b,
+                           const float* gc, int ld_c) {
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
   const int U = c.U, D = c.D, Dg = h.Dg, Kb = Dg + 3 * U;
@@ -1486,7 +1523,7 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   float* d_hpre = bw.d_hpre + slot * D;
   float* d_vin = bw.d_vin + slot * 3 * U;
   if (cx.err) return;
-  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, bw.gd, D, sb.q, deter_in, ld_in, d_q, bw.dd, R, D, Dg);
+  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, ga, ld_a, gb, ld_b, gc, ld_c, (const float*)sb.q, deter_in, ld_in, d_q, bw.dd, R, D, Dg);
   cx.check("gates_bwd_kernel");
   dgrad(cx, R, h.gru, d_q, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
   sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D);
@@ -1501,9 +1538,10 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
     pin[j] = nbp(bw.dx + j * U, 3 * U, sb.vin + j * U, 3 * U, gains[j], U, d_vin + j * U, 3 * U,
                  bw.dmn_in + slot * 3 * U + j * U, 3 * U);
   normact_bwd(cx, R, pin, 3);
-  dgrad(cx, R, h.in0, d_vin, 3 * U, 0, bw.t_din0, D, 0);
-  dgrad(cx, R, h.in1, d_vin + U, 3 * U, 0, bw.t_dz, h.SK, 0);
-  if (want_act) dgrad(cx, R, h.in2, d_vin + 2 * U, 3 * U, 0, bw.d_abar, c.A, 0);
+  DgradCall dc[3] = {{&h.in0, d_vin, 3 * U, bw.t_din0, D, 0, 0},
+                     {&h.in1, d_vin + U, 3 * U, bw.t_dz, h.SK, 0, 0},
+                     {&h.in2, d_vin + 2 * U, 3 * U, bw.d_abar, c.A, 0, 0}};
+  dgrad_multi(cx, R, dc, want_act ? 3 : 2);
 }
 
 // dW (+)= dY^T [X | X2] for a Linear (reference layout (N,K)) or the G blocks of a BlockLinear ((O/G, I/G, G)).
@@ -1573,13 +1611,12 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
       float* d_lg = bw.d_lg + slot * SK;
       sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, d_stochs ? d_stochs + (size_t)t * SK : nullptr, T * SK,
                  d_logits ? d_logits + (size_t)t * SK : nullptr, T * SK, B, c.S, c.K, c.unimix, d_lg, SK);
-      latent_logits_bwd(cx, sb, bw, slot, B, h->obs, c.obs_layers, h->obs_logit, d_lg, bw.t_dxe);
+      // d[deter' | embed]: the deter' part goes to a scratch, the embed part straight into d_embed[:, t]
+      latent_logits_bwd(cx, sb, bw, slot, B, h->obs, c.obs_layers, h->obs_logit, d_lg, bw.t_dxe, D,
+                        d_embed ? d_embed + (size_t)t * E : nullptr, T * E);
       if (cx.err) return;
-      launch_k(cx.st, sd::obs_combine_kernel, dim3(grid1d((long long)B * (D + E), 256)), dim3(256), 0, 
-          bw.carry_d, d_deters ? d_deters + (size_t)t * D : nullptr, T * D, bw.t_dxe, B, D, E, bw.gd,
-          d_embed ? d_embed + (size_t)t * E : nullptr, T * E);
-      cx.check("obs_combine_kernel");
-      deter_core_bwd(cx, sb, bw, slot, B, false, sb.din, D);
+      deter_core_bwd(cx, sb, bw, slot, B, false, sb.din, D, bw.carry_d, D, d_deters ? d_deters + (size_t)t * D : nullptr, T * D,
+                     bw.t_dxe, D);
       if (cx.err) return;
       // reset cut (rssm.py:161-165): carry = d(step inputs) * (1 - is_first)
       launch_k(cx.st, sd::carry_kernel, dim3(grid1d((long long)B * (SK + D), 256)), dim3(256), 0, bw.dd, bw.t_din0, bw.t_dz, sb.keep, nullptr,
@@ -1661,10 +1698,7 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
         sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, nullptr, 0, nullptr, 0, N, c.S, c.K, c.unimix, bw.d_lg, SK);
         latent_logits_bwd(cx, sb, bw, 0, N, h->img, c.img_layers, h->img_logit, bw.d_lg, bw.t_dxe);
         if (cx.err) return;
-        launch_k(cx.st, sd::obs_combine_kernel, dim3(grid1d((long long)N * D, 256)), dim3(256), 0, bw.carry_d, nullptr, 0, bw.t_dxe, N, D, 0,
-                                                                               bw.gd, nullptr, 0);
-        cx.check("obs_combine_kernel");
-        deter_core_bwd(cx, sb, bw, 0, N, true, sb.feat + SK, F);
+        deter_core_bwd(cx, sb, bw, 0, N, true, sb.feat + SK, F, bw.carry_d, D, nullptr, 0, bw.t_dxe, D);
         if (cx.err) return;
       }
       // through action = actor(feat_t).rsample()

@@ -117,7 +117,10 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
 // Backward of the GRU-style gates (rssm.py:63-75): given g = d(deter'), the saved gate pre-activations q
 // (R, 3D) [g][reset|cand|update][Dg] and the step's input deter, emit dq (same layout) and the direct
 // path dd = g * (1 - update).
-__global__ void gates_bwd_kernel(const float* __restrict__ g, int ld_g, const float* __restrict__ q,
+// g = ga + gb + gc (gb, gc nullable): carry from step t+1, upstream d_deters[:, t] and the gradient coming back
+// through the posterior / prior net, summed here instead of in a separate kernel.
+__global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const float* __restrict__ gb, int ld_b,
+                                 const float* __restrict__ gc, int ld_c, const float* __restrict__ q,
                                  const float* __restrict__ deter_in, int ld_in, float* dq, float* dd, int R, int D,
                                  int Dg) {
   pdl_prologue();
@@ -130,7 +133,7 @@ __global__ void gates_bwd_kernel(const float* __restrict__ g, int ld_g, const fl
     const size_t qo = row * 3 * D + (size_t)gi * 3 * Dg + o;
     const float r = q[qo], c = q[qo + Dg], uu = q[qo + 2 * Dg];
     const float Rg = sigmoidf_(r), C = tanhf(Rg * c), Uu = sigmoidf_(uu - 1.f);
-    const float gd = g[row * ld_g + d];
+    const float gd = ga[row * ld_a + d] + (gb ? gb[row * ld_b + d] : 0.f) + (gc ? gc[row * ld_c + d] : 0.f);
     const float dUu = gd * (C - deter_in[row * ld_in + d]);
     const float dC = gd * Uu;
     const float dtn = dC * (1.f - C * C);
@@ -138,26 +141,6 @@ __global__ void gates_bwd_kernel(const float* __restrict__ g, int ld_g, const fl
     dq[qo + Dg] = dtn * Rg;
     dq[qo + 2 * Dg] = dUu * Uu * (1.f - Uu);
     dd[row * D + d] = gd * (1.f - Uu);
-  }
-}
-
-// g_d(t) = carry + upstream d_deters[:, t] + d[deter'|embed][:, :D];  d_embed[:, t] = d[deter'|embed][:, D:].
-__global__ void obs_combine_kernel(const float* __restrict__ carry, const float* __restrict__ up, int ld_up,
-                                   const float* __restrict__ dxe, int R, int D, int E, float* gd, float* d_embed,
-                                   int ld_e) {
-  pdl_prologue();
-  const int W = D + E;
-  const long long total = (long long)R * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const size_t row = (size_t)(i / W);
-    const int c = (int)(i - (long long)row * W);
-    const float v = dxe ? dxe[row * W + c] : 0.f;
-    if (c < D) {
-      gd[row * D + c] = carry[row * D + c] + (up ? up[row * ld_up + c] : 0.f) + v;
-    } else if (d_embed) {
-      d_embed[row * ld_e + (c - D)] = v;
-    }
   }
 }
 
