@@ -85,7 +85,7 @@ def oracle_step(c, P, inputs, rows_frac=1.0):
 
 
 def make_np_inputs(c):
-    from oracle import rssm_oracle as O
+    from safe_dreamer_b200 import synth as O
     embed, action, reset, u = O.synth_observe_inputs(c, B, T, seed=2)
     _, _, ui, noise = O.synth_imagine_inputs(c, N, H, seed=3)
     return embed, action, reset, u, ui, noise
@@ -132,9 +132,9 @@ def run_gpu(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from oracle import rssm_oracle as O          # cpu_baseline leg + synthetic weights/inputs only
     from safe_dreamer_b200 import _lib
-    from tests.helpers import make_engine
+    from safe_dreamer_b200 import synth as O     # seeded synthetic sizes / weights / inputs (no compute)
+    from safe_dreamer_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -149,7 +149,7 @@ def run_gpu(args):
     lib = _lib.load()
     lib.sd_observe_bwd(None, 1, 1, None, None, None, None, None, None, None, 0, None)  # probes the build
     have_bwd = (not args.no_bwd) and b"not implemented" not in lib.sd_last_error_string()
-    eng = make_engine(c, P, max_rows=N, max_steps=max(T, H), max_tape_rows=B if have_bwd else 0)
+    eng = Engine.from_cfg(c, N, max(T, H), B if have_bwd else 0, P)
     emb_np, act_np, rst_np, u_np, ui_np, nz_np = make_np_inputs(c)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)   # each rank scans its own replay slice
     emb_np = emb_np + 0.01 * torch.randn(emb_np.shape, generator=g).numpy().astype(np.float32) * (rank > 0)

@@ -1422,6 +1422,7 @@ static void normact_bwd(Ctx& cx, int R, const sd::NormActBwdP* ps, int n) {
 static sd::NormActBwdP nbp(const float* dout, int ld_dout, const float* v, int ld_v, const float* w, int width, float* dv,
                            int ld_dv, float* dmn, int ld_dmn) {
   sd::NormActBwdP p;
+  p.nsum = 0; p.sum_stride = 0;
   p.dout = dout; p.ld_dout = ld_dout; p.v = v; p.ld_v = ld_v; p.w = w; p.dv = dv; p.ld_dv = ld_dv; p.dmn = dmn;
   p.ld_dmn = ld_dmn; p.width = width;
   return p;
@@ -1530,13 +1531,14 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   normact_bwd(cx, R, &ph, 1);
   dgrad(cx, R, h.hid, d_hpre, D, Dg, bw.t_dxin, c.G * Kb, Kb);
   if (cx.err) return;
-  launch_k(cx.st, sd::hid_reduce_kernel, dim3(grid1d((long long)R * (D + 3 * U), 256)), dim3(256), 0, bw.t_dxin, bw.dd, bw.dx, R, c.G, Dg, 3 * U);
-  cx.check("hid_reduce_kernel");
   sd::NormActBwdP pin[3];
   const float* gains[3] = {h.in0.gain, h.in1.gain, h.in2.gain};
-  for (int j = 0; j < 3; ++j)
-    pin[j] = nbp(bw.dx + j * U, 3 * U, sb.vin + j * U, 3 * U, gains[j], U, d_vin + j * U, 3 * U,
+  // d(x_j) = sum over the G blocks of the x-part of the block-input gradient (read in place, no reduce kernel)
+  for (int j = 0; j < 3; ++j) {
+    pin[j] = nbp(bw.t_dxin + Dg + j * U, c.G * Kb, sb.vin + j * U, 3 * U, gains[j], U, d_vin + j * U, 3 * U,
                  bw.dmn_in + slot * 3 * U + j * U, 3 * U);
+    pin[j].nsum = c.G; pin[j].sum_stride = Kb;
+  }
   normact_bwd(cx, R, pin, 3);
   DgradCall dc[3] = {{&h.in0, d_vin, 3 * U, bw.t_din0, D, 0, 0},
                      {&h.in1, d_vin + U, 3 * U, bw.t_dz, h.SK, 0, 0},
@@ -1619,8 +1621,9 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
                      bw.t_dxe, D);
       if (cx.err) return;
       // reset cut (rssm.py:161-165): carry = d(step inputs) * (1 - is_first)
-      launch_k(cx.st, sd::carry_kernel, dim3(grid1d((long long)B * (SK + D), 256)), dim3(256), 0, bw.dd, bw.t_din0, bw.t_dz, sb.keep, nullptr,
-                                                                              0, nullptr, 0, B, SK, D, bw.carry_z, bw.carry_d);
+      launch_k(cx.st, sd::carry_kernel, dim3(grid1d((long long)B * (SK + D), 256)), dim3(256), 0, (const float*)bw.dd,
+               (const float*)bw.t_din0, (const float*)bw.t_dz, (const float*)sb.keep, (const float*)nullptr, 0,
+               (const float*)nullptr, 0, (const float*)bw.t_dxin, c.G, h->Dg, h->Dg + 3 * c.U, B, SK, D, bw.carry_z, bw.carry_d);
       cx.check("carry_kernel");
     }
     if (cx.err) return;
@@ -1715,8 +1718,10 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
       head_bwd(cx, sb, bw, N, actor, bw.t_daout, h->act_out, bw.t_dfeat, F);
       if (cx.err) return;
       launch_k(cx.st, sd::carry_kernel, dim3(grid1d((long long)N * F, 256)), dim3(256), 0, 
-          stepped ? bw.dd : nullptr, stepped ? bw.t_din0 : nullptr, stepped ? bw.t_dz : nullptr, nullptr, bw.t_dfeat, F,
-          d_feats ? d_feats + (size_t)t * F : nullptr, H * F, N, SK, D, bw.carry_z, bw.carry_d);
+          (const float*)(stepped ? bw.dd : nullptr), (const float*)(stepped ? bw.t_din0 : nullptr),
+          (const float*)(stepped ? bw.t_dz : nullptr), (const float*)nullptr, (const float*)bw.t_dfeat, F,
+          d_feats ? d_feats + (size_t)t * F : (const float*)nullptr, H * F,
+          (const float*)(stepped ? bw.t_dxin : nullptr), c.G, h->Dg, h->Dg + 3 * c.U, N, SK, D, bw.carry_z, bw.carry_d);
       cx.check("carry_kernel");
     }
     if (cx.err) return;

@@ -15,6 +15,7 @@ namespace sd {
 //   dmn  = dm * n  (per-row contribution to the RMS scale gradient; column-summed after the scan)
 struct NormActBwdP {
   const float* dout; int ld_dout;  // grad w.r.t. the activation output
+  int nsum; long long sum_stride;  // dout[c] = sum_{g < nsum} dout[g*sum_stride + c] (block-diagonal consumers); 0/1 = plain
   const float* v;    int ld_v;     // saved pre-norm values
   const float* w;                  // [width]
   float* dv;  int ld_dv;
@@ -52,7 +53,9 @@ __global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch 
       const float n = vv[i] * rho;
       const float m = n * w;
       const float sg = sigmoidf_(m);
-      const float dm = dout[c] * (sg * (1.f + m * (1.f - sg)));
+      float dy = dout[c];
+      for (int g = 1; g < p.nsum; ++g) dy += dout[g * p.sum_stride + c];
+      const float dm = dy * (sg * (1.f + m * (1.f - sg)));
       if (p.dmn) p.dmn[row * p.ld_dmn + c] = dm * n;
       nn[i] = n;
       dn[i] = dm * w;
@@ -144,35 +147,13 @@ __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const f
   }
 }
 
-// After the block dgrad of dyn_hid: dxin (R, G, Dg + 3U).  dd += dxin[:, g, :Dg];  dx = sum_g dxin[:, g, Dg:].
-__global__ void hid_reduce_kernel(const float* __restrict__ dxin, float* dd, float* dx, int R, int G, int Dg, int U3) {
-  pdl_prologue();
-  const int W = G * Dg + U3;
-  const int Kb = Dg + U3;
-  const long long total = (long long)R * W;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const size_t row = (size_t)(i / W);
-    const int c = (int)(i - (long long)row * W);
-    const float* base = dxin + row * (size_t)G * Kb;
-    if (c < G * Dg) {
-      const int g = c / Dg, o = c - g * Dg;
-      dd[row * (size_t)(G * Dg) + c] += base[(size_t)g * Kb + o];
-    } else {
-      const int j = c - G * Dg;
-      float s = 0.f;
-      for (int g = 0; g < G; ++g) s += base[(size_t)g * Kb + Dg + j];
-      dx[row * U3 + j] = s;
-    }
-  }
-}
-
 // End of a reverse step: carry_d = (dd + d_din0) * keep, carry_z = dz * keep, keep = 1 - is_first saved by the
 // forward (rssm.py:161-165).
 // `extra_z/extra_d` (nullable) are added before masking (imagination: grads through the actor's feat input).
 __global__ void carry_kernel(const float* __restrict__ dd, const float* __restrict__ d_din0,
                              const float* __restrict__ dz, const float* __restrict__ keep_mask,
                              const float* __restrict__ extra, int ld_x, const float* __restrict__ extra2, int ld_x2,
+                             const float* __restrict__ dxin, int G, int Dg, int Kb,
                              int R, int SK, int D, float* carry_z, float* carry_d) {
   pdl_prologue();
   const int W = SK + D;
@@ -186,7 +167,9 @@ __global__ void carry_kernel(const float* __restrict__ dd, const float* __restri
     if (c < SK) carry_z[row * SK + c] = ((dz ? dz[row * SK + c] : 0.f) + ex) * keep;
     else {
       const int d = c - SK;
-      carry_d[row * D + d] = ((dd ? dd[row * D + d] : 0.f) + (d_din0 ? d_din0[row * D + d] : 0.f) + ex) * keep;
+      // dxin (R, G, Kb): gradient of the block input [deter_g | x]; its deter part belongs to unit d = g*Dg + o
+      const float dh = dxin ? dxin[(row * G + d / Dg) * (size_t)Kb + (d % Dg)] : 0.f;
+      carry_d[row * D + d] = ((dd ? dd[row * D + d] : 0.f) + (d_din0 ? d_din0[row * D + d] : 0.f) + dh + ex) * keep;
     }
   }
 }

@@ -56,6 +56,20 @@ class Engine:
         self.static_outputs = False
         self._outs = {}
 
+    @classmethod
+    def from_cfg(cls, c, max_rows, max_steps, max_tape_rows=0, params=None):
+        """Engine for a `synth.Cfg`-like size object; `params` = {module: {state_dict name: ndarray}} to load."""
+        eng = cls(D=c.D, U=c.U, S=c.S, K=c.K, G=c.G, E=c.E, A=c.A, obs_layers=c.obs_layers, img_layers=c.img_layers,
+                  act_kind=0 if c.act_kind == "cont" else 1, units=c.units, actor_layers=c.actor_layers,
+                  value_layers=c.value_layers, reward_layers=c.reward_layers, cont_layers=c.cont_layers, bins=c.bins,
+                  unimix=c.unimix, act_unimix=c.act_unimix, min_std=c.min_std, max_std=c.max_std, max_rows=max_rows,
+                  max_steps=max_steps, max_tape_rows=max_tape_rows)
+        if params is not None:
+            for mod, key in enumerate(["rssm", "actor", "reward", "cont", "value", "slow_value"]):
+                eng.set_weights(mod, {k: torch.from_numpy(v).to(eng.device) for k, v in params[key].items()})
+            torch.cuda.synchronize(eng.device)
+        return eng
+
     def __del__(self):
         h, self.h = getattr(self, "h", None), None
         if h:

@@ -60,19 +60,9 @@ def index_mismatch_report(idx_a, idx_b, score, tol):
 
 # ----------------------------------------------------------------------------- GPU-side helpers
 def make_engine(c, P, max_rows, max_steps, max_tape_rows=0):
-    """Engine for oracle config `c` with oracle weights `P` loaded (CUDA only)."""
-    import torch
+    """Engine for config `c` with weights `P` loaded (CUDA only)."""
     from safe_dreamer_b200.engine import Engine
-    eng = Engine(D=c.D, U=c.U, S=c.S, K=c.K, G=c.G, E=c.E, A=c.A, obs_layers=c.obs_layers,
-                 img_layers=c.img_layers, act_kind=0 if c.act_kind == "cont" else 1, units=c.units,
-                 actor_layers=c.actor_layers, value_layers=c.value_layers, reward_layers=c.reward_layers,
-                 cont_layers=c.cont_layers, bins=c.bins, unimix=c.unimix, act_unimix=c.act_unimix,
-                 min_std=c.min_std, max_std=c.max_std, max_rows=max_rows, max_steps=max_steps,
-                 max_tape_rows=max_tape_rows)
-    for mod, key in enumerate(["rssm", "actor", "reward", "cont", "value", "slow_value"]):
-        eng.set_weights(mod, {k: torch.from_numpy(v).cuda() for k, v in P[key].items()})
-    torch.cuda.synchronize()
-    return eng
+    return Engine.from_cfg(c, max_rows, max_steps, max_tape_rows, P)
 
 
 def cu(x):
