@@ -298,10 +298,15 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
+    e2e_iter = []
     for _ in range(args.steps):
+        ti = time.perf_counter()
         e2e_step()
+        e2e_iter.append(1e3 * (time.perf_counter() - ti))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("SD_BENCH_VERBOSE"):
+        print("e2e per-iteration ms:", [round(x, 2) for x in e2e_iter], file=sys.stderr)
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
