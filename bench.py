@@ -174,15 +174,34 @@ def run_gpu(args):
         bucket = GradBucket({n: P["rssm"][n].shape for n in eng.weight_names(0)}, dev)
         wgrads = bucket.views
 
+    # The imagination rollout + heads only depend on the posterior FORWARD (dreamer.py:580-602 detaches the
+    # start states), so they run on a second stream concurrently with the posterior backward scan and the
+    # gradient all-reduce; both are latency bound and use disjoint workspace regions.
+    side = torch.cuda.Stream(device=dev)
+    ev_fwd, ev_side = torch.cuda.Event(), torch.cuda.Event()
+    overlap = have_bwd and not args.no_overlap
+
     def hot_path():
+        nonlocal overlap
+        main = torch.cuda.current_stream(dev)
         if have_bwd:
             bucket.zero_()
         st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | (TAPE if have_bwd else 0), out=obs_out)
+        if overlap:
+            ev_fwd.record(main)
+            side.wait_event(ev_fwd)
+            with torch.cuda.stream(side):
+                eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions))
+                eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
+                ev_side.record(side)
         if have_bwd:
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
-            bucket.allreduce_async()   # DP: ONE flat NCCL all-reduce of the RSSM grads, overlapped with imagination
-        eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions))
-        eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
+            bucket.allreduce_async()   # DP: ONE flat NCCL all-reduce of the RSSM grads
+        if overlap:
+            main.wait_event(ev_side)
+        else:
+            eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions))
+            eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
         if have_bwd:
             bucket.wait()
         return outs[-1]
@@ -200,6 +219,15 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         hot_path()
     torch.cuda.synchronize()
+    if overlap:  # the two-stream schedule must produce exactly what the single-stream one does
+        ref_ret, ref_w = outs[-1].clone(), bucket.flat.clone()
+        overlap = False
+        hot_path()
+        torch.cuda.synchronize()
+        assert torch.equal(ref_ret, outs[-1]) and torch.equal(ref_w, bucket.flat), "stream overlap changed the results"
+        overlap = True
+        hot_path()
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -277,20 +305,36 @@ def run_gpu(args):
                 p_.grad = None
             e_.requires_grad_(True)
             st_, dt_, lg_ = rssm.observe(e_, a_, (s_, d_), f_)
+        else:
+            with torch.no_grad():
+                st_, dt_, lg_ = rssm.observe(e_, a_, (s_, d_), f_)
+
+        def imag():
+            with torch.no_grad():
+                rssm.precision = "bf16"
+                ft_, ac_ = dreamer_ops.imagine(rssm, (st_.detach().reshape(N, c.S, c.K), dt_.detach().reshape(N, c.D)), H)
+                out_ = dreamer_ops.heads_lambda(rssm, ft_, c.horizon, c.lamb)
+                rssm.precision = "fp32"
+                return out_
+        main = torch.cuda.current_stream(dev)
+        if overlap:   # imagination on the side stream while autograd runs the posterior backward on the main one
+            ev_fwd.record(main)
+            side.wait_event(ev_fwd)
+            with torch.cuda.stream(side):
+                r_ = imag()
+                ev_side.record(side)
+        if have_bwd:
             torch.autograd.backward((st_, dt_, lg_), (gst, gdt, glg))
             if world > 1:
                 flat = torch.cat([p_.grad.reshape(-1) for p_ in rssm.parameters() if p_.grad is not None])
                 work = dist.all_reduce(flat, async_op=True)
+        if overlap:
+            main.wait_event(ev_side)
         else:
-            with torch.no_grad():
-                st_, dt_, lg_ = rssm.observe(e_, a_, (s_, d_), f_)
-        with torch.no_grad():
-            rssm.precision = "bf16"
-            ft_, ac_ = dreamer_ops.imagine(rssm, (st_.detach().reshape(N, c.S, c.K), dt_.detach().reshape(N, c.D)), H)
-            r_ = dreamer_ops.heads_lambda(rssm, ft_, c.horizon, c.lamb)
-            if work is not None:
-                work.wait()
-            return float(r_[-1].mean().item())           # D2H read of the step's result
+            r_ = imag()
+        if work is not None:
+            work.wait()
+        return float(r_[-1].mean().item())               # D2H read of the step's result
 
     for _ in range(3):
         e2e_step()
@@ -337,7 +381,8 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "rows": N, "horizon": H, "posterior_bwd": bool(have_bwd),
                        "l2": "256 MB flush write between timed iterations (outside the event pairs)",
-                       "multi_gpu": "each rank scans its own replay slice; RSSM grad all-reduce (NCCL) overlapped with imagination" if have_bwd else "replicas only"},
+                       "multi_gpu": "each rank scans its own replay slice; RSSM grad all-reduce (NCCL) overlapped with imagination" if have_bwd else "replicas only",
+                       "streams": "imagination+heads on a second stream concurrent with the posterior backward" if overlap else "single stream"},
             "gpu_launches": int(launches),
             "world_model_updates_per_s": None if ms_wm is None else world * args.steps / (ms_wm * 1e-3),
             "posterior_steps_per_s_fwd_bwd": None if ms_obs_fb is None else world * N * args.steps / (ms_obs_fb * 1e-3),
@@ -366,7 +411,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-bwd", action="store_true", help="time the forward-only hot path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run imagination after (not concurrently with) the posterior backward")
+    ap.add_argument("--batch", type=int, default=16, help="replay batch B per GPU (default: base.yaml's 16; the headline config)")
     args = ap.parse_args()
+    global B, N, WORKLOAD
+    if args.batch != B:
+        B, N = args.batch, args.batch * T
+        WORKLOAD = WORKLOAD.replace("B=16", f"B={B}").replace("N=1024", f"N={N}") + " [non-headline batch]"
     if args.impl == "reference":
         run_reference(args)
     else:
