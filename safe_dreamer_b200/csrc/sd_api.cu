@@ -50,6 +50,8 @@ struct LinearW {
   float* wt = nullptr;    // [G][K][ldw]   forward operand (n contiguous)
   float* wn = nullptr;    // [G][N][ldk]   dgrad operand (k contiguous)
   bf16* w_bf = nullptr;   // [G][npad][K]  tcgen05 forward operand (K-major rows)
+  bf16* wT_bf = nullptr;  // [G][kpad][N]  tcgen05 dgrad operand (transposed: rows = input unit, N-major)
+  int kpad = 0;
   float* bias = nullptr;  // [G*N]
   float* gain = nullptr;  // RMSNorm scale that follows this layer (nullable)
   bool tc_ok() const { return (K % 64) == 0; }
@@ -98,6 +100,8 @@ struct BwdBufs {
   float* dmn_v[4];
   // temporaries (one step)
   float *t_do, *t_dxe, *gd, *dd, *t_dh, *t_dxin, *dx, *t_din0, *t_dz, *carry_z, *carry_d, *d_abar, *t_dfeat, *t_daout;
+  // bf16 copies of one step's gradients (tcgen05 dgrad operands of the large-row backward)
+  bf16 *d_lg_bf, *d_q_bf, *d_hpre_bf, *d_vin_bf, *d_v_bf;
 };
 
 struct GraphEntry {
@@ -543,6 +547,8 @@ static void alloc_linear(Arena& a, LinearW& L, int G, int N, int K, bool has_bia
   L.wt = a.take<float>((size_t)G * K * L.ldw);
   L.wn = a.take<float>((size_t)G * N * L.ldk);
   L.w_bf = (K % 64 == 0) ? a.take<bf16>((size_t)G * L.npad * K) : nullptr;
+  L.kpad = up(K, 256);
+  L.wT_bf = (N % 64 == 0 && K >= 64) ? a.take<bf16>((size_t)G * L.kpad * N) : nullptr;
   L.bias = has_bias ? a.take<float>((size_t)G * N) : nullptr;
   L.gain = has_gain ? a.take<float>((size_t)gain_n) : nullptr;
 }
@@ -605,6 +611,11 @@ static void alloc_bwd(Arena& a, BwdBufs& b, const sd_handle& h, size_t rows, siz
   b.d_abar = a.take<float>(rows * c.A);
   b.t_dfeat = a.take<float>(rows * h.F);
   b.t_daout = a.take<float>(rows * up(h.act_out, 4));
+  b.d_lg_bf = a.take<bf16>(rows * h.SK);
+  b.d_q_bf = a.take<bf16>(rows * 3 * c.D);
+  b.d_hpre_bf = a.take<bf16>(rows * c.D);
+  b.d_vin_bf = a.take<bf16>(rows * 3 * c.U);
+  b.d_v_bf = a.take<bf16>(rows * U);
 }
 
 static void layout(sd_handle& h, Arena& a) {
@@ -875,6 +886,12 @@ static void pack_linear_bf(Ctx& cx, LinearW& L, const float* w, bool block_layou
         w + (block_layout ? g : 0), 1, L.N, L.K, 0, s_n, s_k, nullptr, 0, nullptr, L.K,
         L.w_bf + (size_t)g * L.npad * L.K, nullptr);
     cx.check("pack_weight_kernel(bf16)");
+    if (L.wT_bf) {
+      launch_k(cx.st, sd::pack_weight_kernel, dim3(grid1d((long long)L.N * L.K, 256)), dim3(256), 0,
+               w + (block_layout ? g : 0), 1, L.N, L.K, 0, s_n, s_k, nullptr, L.N, nullptr, 0, nullptr,
+               L.wT_bf + (size_t)g * L.kpad * L.N);
+      cx.check("pack_weight_kernel(bf16 T)");
+    }
   }
 }
 
@@ -1420,8 +1437,9 @@ static void normact_bwd(Ctx& cx, int R, const sd::NormActBwdP* ps, int n) {
   cx.check("normact_bwd_kernel");
 }
 static sd::NormActBwdP nbp(const float* dout, int ld_dout, const float* v, int ld_v, const float* w, int width, float* dv,
-                           int ld_dv, float* dmn, int ld_dmn) {
+                           int ld_dv, float* dmn, int ld_dmn, bf16* dv_bf = nullptr) {
   sd::NormActBwdP p;
+  p.dv_bf = dv_bf;
   p.nsum = 0; p.sum_stride = 0;
   p.dout = dout; p.ld_dout = ld_dout; p.v = v; p.ld_v = ld_v; p.w = w; p.dv = dv; p.ld_dv = ld_dv; p.dmn = dmn;
   p.ld_dmn = ld_dmn; p.width = width;
@@ -1445,6 +1463,20 @@ static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, 
   launch_gemm_f32(cx.st, gb, L.K, L.N, R);
   cx.check("gemm_f32_kernel(dgrad)");
 }
+// dgrad on the tcgen05 path when the transposed bf16 weights exist and a bf16 copy of dy is available
+// (large-row backward of the imagination rollout), else the fp32 cluster GEMM.
+static void dgrad_any(Ctx& cx, int R, const LinearW& L, const float* dy, const bf16* dy_bf, int ld_dy, int dy_gstride,
+                      float* dx, int ld_dx, int dx_gstride) {
+  if (cx.tc && dy_bf && L.wT_bf && (L.N % 64) == 0 && L.K >= 64) {
+    LinearW LT;   // transposed view: contraction over the layer's outputs
+    LT.G = L.G; LT.N = L.K; LT.K = L.N; LT.npad = L.kpad; LT.w_bf = L.wT_bf; LT.bias = nullptr;
+    Operand a; a.b = dy_bf; a.ldb = ld_dy; a.gstride = dy_gstride; a.f = dy; a.ldf = ld_dy;
+    linear(cx, R, LT, a, LT.K, Operand(), dx, ld_dx, dx_gstride);
+    return;
+  }
+  dgrad(cx, R, L, dy, ld_dy, dy_gstride, dx, ld_dx, dx_gstride);
+}
+
 // Several independent single-block dgrads (same row count) in one launch; `col0`/`ncols` select a range of the
 // layer's input columns so one layer can scatter its input gradient to two destinations.
 struct DgradCall {
@@ -1477,32 +1509,34 @@ static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n) {
 template <int GS>
 static void launch_sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
                               const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
-                              float* d_logit, int ld_d) {
+                              float* d_logit, int ld_d, bf16* d_logit_bf) {
   const long long n = (long long)R * S * GS;
   launch_k(cx.st, sd::sample_bwd_kernel<GS>, dim3((int)((n + 255) / 256)), dim3(256), 0, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul,
-                                                                       R, S, K, unimix, d_logit, ld_d);
+                                                                       R, S, K, unimix, d_logit, ld_d, d_logit_bf);
 }
 static void sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
                        const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
-                       float* d_logit, int ld_d) {
+                       float* d_logit, int ld_d, bf16* d_logit_bf = nullptr) {
   if (cx.err) return;
-  if (K <= 8) launch_sample_bwd<8>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d);
-  else if (K <= 16) launch_sample_bwd<16>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d);
-  else launch_sample_bwd<32>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d);
+  if (K <= 8) launch_sample_bwd<8>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf);
+  else if (K <= 16) launch_sample_bwd<16>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf);
+  else launch_sample_bwd<32>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf);
   cx.check("sample_bwd_kernel");
 }
 // Backward of latent_logits: d(logits) -> d(layer-0 input) [R x K0] in `dx0`; fills the d-tape slots.
 static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, const LinearW* layers,
                               int nl, const LinearW& last, const float* d_lg, float* dx0, int k_first = 0,
-                              float* dx0_b = nullptr, int ld_b = 0) {
+                              float* dx0_b = nullptr, int ld_b = 0, const bf16* d_lg_bf = nullptr) {
   sd_handle& h = *cx.h;
   const int U = h.c.U;
-  dgrad(cx, R, last, d_lg, h.SK, 0, bw.t_do, U, 0);
+  bf16* dvb = cx.tc ? bw.d_v_bf : nullptr;   // one step's bf16 copy (tcgen05 dgrad; slot 0 callers only)
+  dgrad_any(cx, R, last, d_lg, d_lg_bf, h.SK, 0, bw.t_do, U, 0);
   for (int i = nl - 1; i >= 0; --i) {
     float* dv = bw.d_v[i] + slot * U;
-    sd::NormActBwdP p = nbp(bw.t_do, U, sb.vobs[i], U, layers[i].gain, U, dv, U, bw.dmn_v[i] + slot * U, U);
+    sd::NormActBwdP p = nbp(bw.t_do, U, sb.vobs[i], U, layers[i].gain, U, dv, U, bw.dmn_v[i] + slot * U, U, dvb);
     normact_bwd(cx, R, &p, 1);
-    if (i > 0) dgrad(cx, R, layers[i], dv, U, 0, bw.t_do, U, 0);
+    if (i > 0) dgrad_any(cx, R, layers[i], dv, dvb, U, 0, bw.t_do, U, 0);
+    else if (k_first == 0 && dvb) dgrad_any(cx, R, layers[0], dv, dvb, U, 0, dx0, layers[0].K, 0);
     else if (k_first > 0) {
       // input gradient split in two column ranges: [0, k_first) -> dx0 (row stride k_first), the rest -> dx0_b
       // (e.g. straight into d_embed[:, t]); the second range is skipped when nobody wants it
@@ -1524,22 +1558,31 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   float* d_hpre = bw.d_hpre + slot * D;
   float* d_vin = bw.d_vin + slot * 3 * U;
   if (cx.err) return;
-  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, ga, ld_a, gb, ld_b, gc, ld_c, (const float*)sb.q, deter_in, ld_in, d_q, bw.dd, R, D, Dg);
+  const bool tcb = cx.tc;   // large-row backward: bf16 copies of the gradients feed the tcgen05 dgrads
+  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, ga, ld_a, gb, ld_b, gc, ld_c,
+           (const float*)sb.q, deter_in, ld_in, d_q, tcb ? bw.d_q_bf : (bf16*)nullptr, bw.dd, R, D, Dg);
   cx.check("gates_bwd_kernel");
-  dgrad(cx, R, h.gru, d_q, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
-  sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D);
+  dgrad_any(cx, R, h.gru, d_q, tcb ? bw.d_q_bf : nullptr, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
+  sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D,
+                           tcb ? bw.d_hpre_bf : nullptr);
   normact_bwd(cx, R, &ph, 1);
-  dgrad(cx, R, h.hid, d_hpre, D, Dg, bw.t_dxin, c.G * Kb, Kb);
+  dgrad_any(cx, R, h.hid, d_hpre, tcb ? bw.d_hpre_bf : nullptr, D, Dg, bw.t_dxin, c.G * Kb, Kb);
   if (cx.err) return;
   sd::NormActBwdP pin[3];
   const float* gains[3] = {h.in0.gain, h.in1.gain, h.in2.gain};
   // d(x_j) = sum over the G blocks of the x-part of the block-input gradient (read in place, no reduce kernel)
   for (int j = 0; j < 3; ++j) {
     pin[j] = nbp(bw.t_dxin + Dg + j * U, c.G * Kb, sb.vin + j * U, 3 * U, gains[j], U, d_vin + j * U, 3 * U,
-                 bw.dmn_in + slot * 3 * U + j * U, 3 * U);
+                 bw.dmn_in + slot * 3 * U + j * U, 3 * U, tcb ? bw.d_vin_bf + j * U : nullptr);
     pin[j].nsum = c.G; pin[j].sum_stride = Kb;
   }
   normact_bwd(cx, R, pin, 3);
+  if (tcb) {
+    dgrad_any(cx, R, h.in0, d_vin, bw.d_vin_bf, 3 * U, 0, bw.t_din0, D, 0);
+    dgrad_any(cx, R, h.in1, d_vin + U, bw.d_vin_bf + U, 3 * U, 0, bw.t_dz, h.SK, 0);
+    if (want_act) dgrad(cx, R, h.in2, d_vin + 2 * U, 3 * U, 0, bw.d_abar, c.A, 0);
+    return;
+  }
   DgradCall dc[3] = {{&h.in0, d_vin, 3 * U, bw.t_din0, D, 0, 0},
                      {&h.in1, d_vin + U, 3 * U, bw.t_dz, h.SK, 0, 0},
                      {&h.in2, d_vin + 2 * U, 3 * U, bw.d_abar, c.A, 0, 0}};
@@ -1669,10 +1712,11 @@ static void head_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, int R, cons
   const int units = h.c.units;
   dgrad(cx, R, hw.last, d_out, ld_o, 0, bw.t_do, units, 0);
   for (int i = hw.layers - 1; i >= 0; --i) {
-    sd::NormActBwdP p = nbp(bw.t_do, units, sb.va[i], units, hw.l[i].gain, units, bw.d_v[0], units, nullptr, 0);
+    bf16* dvb = cx.tc ? bw.d_v_bf : nullptr;
+    sd::NormActBwdP p = nbp(bw.t_do, units, sb.va[i], units, hw.l[i].gain, units, bw.d_v[0], units, nullptr, 0, dvb);
     normact_bwd(cx, R, &p, 1);
-    if (i > 0) dgrad(cx, R, hw.l[i], bw.d_v[0], units, 0, bw.t_do, units, 0);
-    else dgrad(cx, R, hw.l[0], bw.d_v[0], units, 0, d_feat, F, 0);
+    if (i > 0) dgrad_any(cx, R, hw.l[i], bw.d_v[0], dvb, units, 0, bw.t_do, units, 0);
+    else dgrad_any(cx, R, hw.l[0], bw.d_v[0], dvb, units, 0, d_feat, F, 0);
   }
 }
 
@@ -1686,7 +1730,8 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
   const int SK = h->SK, D = c.D, A = c.A, F = h->F;
   Key key;
   key.add(12).add(N).add(H).add(d_feats).add(d_actions).add(d_stoch0).add(d_deter0).add(flags);
-  return run(h, key.v, flags, (cudaStream_t)stream, false, [&](Ctx& cx) {
+  const bool tc = (flags & SD_FLAG_BF16) && N >= 128;   // dgrads on tcgen05 with bf16 copies of the gradients
+  return run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
     const BwdBufs& bw = h->bw;
     StepBufs base = h->tape;
     base.stride = 1;
@@ -1698,8 +1743,10 @@ extern "C" int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, 
       const bool stepped = t < H - 1;  // the H-th img_step is never computed (dreamer.py:688 result dropped)
       if (stepped) {
         // carry = grads of (stoch_{t+1}, deter_{t+1}), the outputs of img_step at step t
-        sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, nullptr, 0, nullptr, 0, N, c.S, c.K, c.unimix, bw.d_lg, SK);
-        latent_logits_bwd(cx, sb, bw, 0, N, h->img, c.img_layers, h->img_logit, bw.d_lg, bw.t_dxe);
+        sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, nullptr, 0, nullptr, 0, N, c.S, c.K, c.unimix, bw.d_lg, SK,
+                   cx.tc ? bw.d_lg_bf : nullptr);
+        latent_logits_bwd(cx, sb, bw, 0, N, h->img, c.img_layers, h->img_logit, bw.d_lg, bw.t_dxe, 0, nullptr, 0,
+                          cx.tc ? bw.d_lg_bf : nullptr);
         if (cx.err) return;
         deter_core_bwd(cx, sb, bw, 0, N, true, sb.feat + SK, F, bw.carry_d, D, nullptr, 0, bw.t_dxe, D);
         if (cx.err) return;

@@ -19,6 +19,7 @@ struct NormActBwdP {
   const float* v;    int ld_v;     // saved pre-norm values
   const float* w;                  // [width]
   float* dv;  int ld_dv;
+  __nv_bfloat16* dv_bf;            // nullable bf16 copy of dv (same row stride) for the tcgen05 dgrad
   float* dmn; int ld_dmn;          // nullable (dgrad-only)
   int width;
 };
@@ -66,7 +67,11 @@ __global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 256;
-    if (c < p.width) p.dv[row * p.ld_dv + c] = rho * (dn[i] - nn[i] * dot);
+    if (c < p.width) {
+      const float o = rho * (dn[i] - nn[i] * dot);
+      p.dv[row * p.ld_dv + c] = o;
+      if (p.dv_bf) p.dv_bf[row * p.ld_dv + c] = __float2bfloat16(o);
+    }
   }
 }
 
@@ -77,7 +82,7 @@ template <int GS>
 __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, const float* __restrict__ u, int ld_u,
                                   const float* __restrict__ gz_a, int ld_a, const float* __restrict__ gz_b, int ld_b,
                                   const float* __restrict__ up_logit, int ld_ul, int R, int S, int K, float unimix,
-                                  float* d_logit, int ld_d) {
+                                  float* d_logit, int ld_d, __nv_bfloat16* d_logit_bf) {
   pdl_prologue();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long cat = t / GS;
@@ -114,6 +119,7 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
     float out = p * (dp - dpp);
     if (up_logit) out += up_logit[row * ld_ul + col];
     d_logit[row * ld_d + col] = out;
+    if (d_logit_bf) d_logit_bf[row * ld_d + col] = __float2bfloat16(out);
   }
 }
 
@@ -124,8 +130,8 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
 // through the posterior / prior net, summed here instead of in a separate kernel.
 __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const float* __restrict__ gb, int ld_b,
                                  const float* __restrict__ gc, int ld_c, const float* __restrict__ q,
-                                 const float* __restrict__ deter_in, int ld_in, float* dq, float* dd, int R, int D,
-                                 int Dg) {
+                                 const float* __restrict__ deter_in, int ld_in, float* dq, __nv_bfloat16* dq_bf, float* dd,
+                                 int R, int D, int Dg) {
   pdl_prologue();
   const long long total = (long long)R * D;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -140,9 +146,15 @@ __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const f
     const float dUu = gd * (C - deter_in[row * ld_in + d]);
     const float dC = gd * Uu;
     const float dtn = dC * (1.f - C * C);
-    dq[qo] = (dtn * c) * Rg * (1.f - Rg);
-    dq[qo + Dg] = dtn * Rg;
-    dq[qo + 2 * Dg] = dUu * Uu * (1.f - Uu);
+    const float o_r = (dtn * c) * Rg * (1.f - Rg), o_c = dtn * Rg, o_u = dUu * Uu * (1.f - Uu);
+    dq[qo] = o_r;
+    dq[qo + Dg] = o_c;
+    dq[qo + 2 * Dg] = o_u;
+    if (dq_bf) {
+      dq_bf[qo] = __float2bfloat16(o_r);
+      dq_bf[qo + Dg] = __float2bfloat16(o_c);
+      dq_bf[qo + 2 * Dg] = __float2bfloat16(o_u);
+    }
     dd[row * D + d] = gd * (1.f - Uu);
   }
 }

@@ -198,3 +198,30 @@ def test_world_model_update_autograd():
         ref = G.get(name, 0) + G2[name]
         gn = float(np.sqrt((ref.astype(np.float64) ** 2).sum()))
         np.testing.assert_allclose(_np(p.grad), ref, rtol=5e-3, atol=5e-5 * max(gn, 1e-3), err_msg=name)
+
+
+def test_imagine_bwd_tcgen05_dgrad():
+    """Large-row imagination backward with the dgrads on tcgen05 (bf16 copies of the gradients, fp32
+    accumulate): fp32 forward (so the sampled path equals the oracle's), bf16 backward.
+    Tolerance: relative L2 error <= 3 %, cosine >= 0.999 against the fp32 oracle gradients."""
+    c, z = load_golden("base_cont")
+    P = golden_params(c, z)
+    N, H = 128, 3
+    eng = make_engine(c, P, max_rows=N, max_steps=4, max_tape_rows=N)
+    st0, dt0, u, noise = O.synth_imagine_inputs(c, N, H, seed=33)
+    g2 = np.random.Generator(np.random.Philox(34))
+    c_f = g2.standard_normal((N, H, c.F), dtype=np.float32) * np.float32(0.1)
+    c_a = g2.standard_normal((N, H, c.A), dtype=np.float32)
+    tapes = []
+    feats_o, acts_o = O.imagine(c, P["rssm"], P["actor"], (st0, dt0), H, u, noise, tapes)
+    ds_o, dd_o = O.imagine_bwd(c, P["rssm"], P["actor"], tapes, c_f, c_a)
+    feats, acts = eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=2)
+    np.testing.assert_array_equal(_np(feats)[..., :c.SK], feats_o[..., :c.SK])
+    for flags, tol in ((0, 3e-3), (1, 3e-2)):
+        ds, dd = eng.imagine_bwd(N, H, cu(c_f), cu(c_a), flags=flags)
+        torch.cuda.synchronize()
+        for got, ref, name in ((_np(ds), ds_o, "d_stoch0"), (_np(dd), dd_o, "d_deter0")):
+            rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+            cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref)))
+            print(f"imagine_bwd flags={flags} {name}: rel L2 err {rel:.2e}, cosine {cos:.6f}")
+            assert rel <= tol and cos >= 0.999, (flags, name, rel, cos)
