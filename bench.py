@@ -269,6 +269,22 @@ def run_gpu(args):
         for _ in range(3):
             wm()
         ms_wm = timed(wm, args.steps)
+    # ---- grad-enabled imagination (attack shape: frozen weights, dgrad-only; README.md:68-116): fwd + bwd scans
+    ms_imag_fb = None
+    if have_bwd and not args.no_imagine_bwd:
+        eng2 = Engine.from_cfg(c, N, H, N, P)
+        d_feats = torch.randn(N, H, c.F, device=dev) * 0.01
+        d_acts = torch.randn(N, H, c.A, device=dev) * 0.01
+        out2 = (torch.empty(N, H, c.F, device=dev), torch.empty(N, H, c.A, device=dev))
+        eng2.static_outputs = True
+
+        def imag_fb():
+            eng2.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | TAPE, out=out2)
+            eng2.imagine_bwd(N, H, d_feats, d_acts, flags=BF16 | GRAPH)
+        for _ in range(3):
+            imag_fb()
+        ms_imag_fb = timed(imag_fb, args.steps)
+        del eng2
     # ---- end-to-end through the public module API with HOST buffers (pinned) and a D2H result read
     from types import SimpleNamespace as NS
     from safe_dreamer_b200 import dreamer_ops
@@ -385,9 +401,10 @@ def run_gpu(args):
                        "streams": "imagination+heads on a second stream concurrent with the posterior backward" if overlap else "single stream"},
             "gpu_launches": int(launches),
             "world_model_updates_per_s": None if ms_wm is None else world * args.steps / (ms_wm * 1e-3),
+            "imagined_steps_per_s_fwd_bwd_dgrad": None if ms_imag_fb is None else world * N * H * args.steps / (ms_imag_fb * 1e-3),
             "posterior_steps_per_s_fwd_bwd": None if ms_obs_fb is None else world * N * args.steps / (ms_obs_fb * 1e-3),
             "breakdown_ms": {"observe_fwd": ms_obs / args.steps, "world_model_update": None if ms_wm is None else ms_wm / args.steps, "observe_fwd_bwd": None if ms_obs_fb is None else ms_obs_fb / args.steps,
-                             "imagine_fwd": ms_imag / args.steps, "heads_lambda": ms_heads / args.steps},
+                             "imagine_fwd": ms_imag / args.steps, "imagine_fwd_bwd_dgrad": None if ms_imag_fb is None else ms_imag_fb / args.steps, "heads_lambda": ms_heads / args.steps},
             "roofline": {"bound": "tensor", "achieved": imag_tflops, "peak": sus, "unit": "TFLOP/s", "frac": imag_tflops / sus,
                          "traffic": None, "kernel": "sd_imagine_fwd scan (tcgen05 GEMMs + fused row kernels, one CUDA graph)",
                          "peak_source": f"{how} bf16_tflops_sustained (burst {burst})",
@@ -411,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-bwd", action="store_true", help="time the forward-only hot path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-imagine-bwd", action="store_true", help="skip the grad-enabled imagination (attack shape) measurement")
     ap.add_argument("--no-overlap", action="store_true", help="run imagination after (not concurrently with) the posterior backward")
     ap.add_argument("--batch", type=int, default=16, help="replay batch B per GPU (default: base.yaml's 16; the headline config)")
     args = ap.parse_args()
