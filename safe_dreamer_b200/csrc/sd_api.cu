@@ -427,7 +427,7 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
     tb.part_stride = (long long)part_stride_elems;
     if (ksplit > 1) max_kb = (max_kb + ksplit - 1) / ksplit;
     if (batch_wide) launch_tc<256, 4>(cx, tb, (max_n_tc + 255) / 256, R);
-    else if (max_kb <= 4) launch_tc<64, 4>(cx, tb, (max_n_tc + 63) / 64, R);  // short K: 96 KB smem, 2 CTAs/SM
+    else if (max_kb <= 4 || ctas * ksplit > 148) launch_tc<64, 4>(cx, tb, (max_n_tc + 63) / 64, R);  // 96 KB smem: 2 CTAs/SM
     else launch_tc<64, 8>(cx, tb, (max_n_tc + 63) / 64, R);
     ntc = 0; nmaps = 0; max_n_tc = 0;
   };
@@ -1100,15 +1100,16 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
       p.e_dg = Dg;
     }
     tb.count = c.G; tb.R = R; tb.ksplit = 1; tb.part_stride = 0; tb.timing = nullptr;
-    using LG = sd::tc::SmemLayout<192, 4>;
+    // 2 stages (80 KB): two CTAs per SM, so the 256 tiles of the base config run as one wave; K = Dg is short
+    using LG = sd::tc::SmemLayout<192, 2>;
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<192, 4, sd::tc::EPI_GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG::kTotal);
+      cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<192, 2, sd::tc::EPI_GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG::kTotal);
       attr_done = true;
     }
-    launch_k(cx.st, sd::tc::gemm_bf16_tc_kernel<192, 4, sd::tc::EPI_GATES>, dim3(Dg / 64, (R + 127) / 128, c.G),
+    launch_k(cx.st, sd::tc::gemm_bf16_tc_kernel<192, 2, sd::tc::EPI_GATES>, dim3(Dg / 64, (R + 127) / 128, c.G),
              dim3(sd::tc::THREADS), LG::kTotal, tb);
-    cx.check("tc<192,4,gates>");
+    cx.check("tc<192,2,gates>");
     return;
   }
   linear(cx, R, h.gru, opfb(sb.h, D, cx.tc ? h.h_bf : nullptr, D, Dg), Dg, Operand(), sb.q, 3 * D, 3 * Dg);

@@ -142,7 +142,7 @@ struct SmemLayout {
 };
 
 template <int BN, int NSTAGES, int EPI = EPI_STORE>
-__global__ void __launch_bounds__(THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ Batch batch) {
+__global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_kernel(const __grid_constant__ Batch batch) {
   static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported tile width");
   static_assert(EPI == EPI_STORE || BN == 192, "the gate epilogue uses 192-wide tiles (3 gates x 64 units)");
   constexpr int TMEM_COLS = BN == 192 ? 256 : BN;   // allocations are powers of two >= 32 columns
