@@ -269,9 +269,11 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
         const float br = pr.bias ? pr.bias[u0 + j] : 0.f;
         const float bc = pr.bias ? pr.bias[pr.e_dg + u0 + j] : 0.f;
         const float bu = pr.bias ? pr.bias[2 * pr.e_dg + u0 + j] : 0.f;
-        const float reset = 1.f / (1.f + expf(-(qr[j] + br)));
-        const float cand = tanhf(reset * (qc[j] + bc));
-        const float upd = 1.f / (1.f + expf(-((qu[j] + bu) - 1.f)));
+        // bf16-operand path (tolerance ~1e-2): hardware exp2-based intrinsics instead of the accurate libm
+        // routines the fp32 parity path uses; tanh(x) = 1 - 2 / (1 + e^{2x})
+        const float reset = __fdividef(1.f, 1.f + __expf(-(qr[j] + br)));
+        const float cand = 1.f - __fdividef(2.f, 1.f + __expf(2.f * (reset * (qc[j] + bc))));
+        const float upd = __fdividef(1.f, 1.f + __expf(-((qu[j] + bu) - 1.f)));
         outv[j] = upd * cand + (1.f - upd) * stg[lane * SLDG + j];
       }
       __syncwarp();
