@@ -518,6 +518,50 @@ static sd::NormActP nap(float* in, int ld_in, const float* w, int width, float* 
   return p;
 }
 
+// Dense layer + RMSNorm + SiLU in ONE tcgen05 launch (EPI_NORM: cluster of four 64-wide tiles exchanging row
+// statistics through DSMEM).  Applies to the U x U / units x units layers (N = 256, K <= 256, single block)
+// on the tcgen05 path when no tape is kept.  Returns false when the caller must run linear() + normact().
+static bool linear_norm_tc(Ctx& cx, int R, const LinearW& L, Operand a, const StepBufs& sb, float* out_f, int ld_f,
+                           bf16* out_bf, int ld_bf) {
+  if (!cx.tc || sb.stride != 0 || !fused_epi_enabled() || L.G != 1 || L.N != 256 || L.K > 256 || (L.K % 64) != 0 ||
+      !L.w_bf || !a.b || !L.gain || cx.err)
+    return false;
+  sd::tc::Batch tb;
+  memset(&tb, 0, sizeof(tb));
+  bool ok = make_map(&tb.maps[0], a.b, (uint64_t)R, (uint64_t)a.ldb, (uint64_t)a.ldb, 128);
+  ok = ok && make_map(&tb.maps[1], L.w_bf, (uint64_t)L.npad, (uint64_t)L.K, (uint64_t)L.K, 64);
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed"); return true; }
+  sd::tc::Problem& p = tb.p[0];
+  p.a1_map = 0; p.a1_col = 0; p.a2_map = 0; p.a2_col = 0; p.w_map = 1; p.w_row = 0;
+  p.K1 = L.K; p.K = L.K; p.N = L.N; p.bias = L.bias; p.e_gain = L.gain;
+  p.e_out = out_f; p.e_ld_out = ld_f; p.e_out_bf = out_bf; p.e_ld_bf = ld_bf;
+  tb.count = 1; tb.R = R; tb.ksplit = 1;
+  using LN = sd::tc::SmemLayout<64, 4>;
+  auto kern = sd::tc::gemm_bf16_tc_kernel<64, 4, sd::tc::EPI_NORM>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LN::kTotal);
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(4, (R + 127) / 128, 1);
+  cfg.blockDim = dim3(sd::tc::THREADS);
+  cfg.dynamicSmemBytes = LN::kTotal;
+  cfg.stream = cx.st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  prefer_max_smem((const void*)kern);
+  cudaLaunchKernelEx(&cfg, kern, tb);
+  cx.check("tc<64,4,norm>");
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ config / layout
 static int validate(const sd_config& c) {
   if (c.D <= 0 || c.U <= 0 || c.S <= 0 || c.K <= 0 || c.G <= 0 || c.E <= 0 || c.A <= 0)
@@ -1133,6 +1177,12 @@ static bool latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* lay
   Operand cur1 = a1, cur2 = a2;
   int k1 = K1;
   for (int i = 0; i < nl; ++i) {
+    if (cur2.f == nullptr && cur2.b == nullptr && k1 == layers[i].K &&
+        linear_norm_tc(cx, R, layers[i], cur1, sb, sb.o[i], U, obfs[i], U)) {
+      cur1 = opfb(sb.o[i], U, obfs[i], U);
+      k1 = U;
+      continue;
+    }
     linear(cx, R, layers[i], cur1, k1, cur2, sb.vobs[i], U, 0, h.part);
     sd::NormActP p = with_parts(cx, nap(sb.vobs[i], U, layers[i].gain, U, sb.o[i], U, cx.tc ? obfs[i] : nullptr, U), h.part);
     normact(cx, R, &p, 1);
@@ -1338,6 +1388,13 @@ static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, f
   Operand cur = feat;
   int k = F;
   for (int i = 0; i < hw.layers; ++i) {
+    // (in-place bf16 input/output is safe for the fused kernel: tiles of different clusters touch different
+    //  rows, and inside a cluster every store happens after the cluster barrier that follows all MMAs)
+    if (k == hw.l[i].K && linear_norm_tc(cx, R, hw.l[i], cur, h.sb, o[i], units, o_bf[i], units)) {
+      cur = opfb(o[i], units, o_bf[i], units);
+      k = units;
+      continue;
+    }
     linear(cx, R, hw.l[i], cur, k, Operand(), v[i], units, 0, h.part);
     sd::NormActP p = with_parts(cx, nap(v[i], units, hw.l[i].gain, units, o[i], units, cx.tc ? o_bf[i] : nullptr, units), h.part);
     normact(cx, R, &p, 1);
@@ -1381,6 +1438,11 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
         Operand cur = feat;
         int k = F;
         for (int i = 0; i < actor.layers; ++i) {
+          if (k == actor.l[i].K && linear_norm_tc(cx, N, actor.l[i], cur, sb, sb.ao[i], c.units, h->a_bf[i], c.units)) {
+            cur = opfb(sb.ao[i], c.units, h->a_bf[i], c.units);
+            k = c.units;
+            continue;
+          }
           linear(cx, N, actor.l[i], cur, k, Operand(), sb.va[i], c.units, 0, h->part);
           sd::NormActP p = with_parts(cx, nap(sb.va[i], c.units, actor.l[i].gain, c.units, sb.ao[i], c.units,
                                               cx.tc ? h->a_bf[i] : nullptr, c.units), h->part);

@@ -46,8 +46,13 @@ struct Problem {
   float* e_out; int e_ld_out;             // deter' fp32
   __nv_bfloat16* e_out_bf; int e_ld_bf;   // deter' bf16 (next tcgen05 operand), nullable
   int e_dg;                               // units per block (weight rows of one gate)
+  const float* e_gain;                    // EPI_NORM: RMS scale
 };
-enum { EPI_STORE = 0, EPI_GATES = 1 };
+// EPI_NORM (BN = 64, N = 256, cluster of 4 CTAs along N): RMSNorm(1e-4)*gain -> SiLU fused in the epilogue.  The
+// four CTAs of a cluster own the four 64-column tiles of the same 128 rows; per-row partial sums of squares are
+// exchanged through distributed shared memory (st.shared::cluster + barrier.cluster) so every CTA can normalise
+// its tile.  e_gain = RMS scale [N]; e_out / e_out_bf = activation fp32 / bf16.
+enum { EPI_STORE = 0, EPI_GATES = 1, EPI_NORM = 2 };
 struct alignas(64) Batch {
   CUtensorMap maps[kMaxMaps];
   Problem p[kMaxProblems];
@@ -138,13 +143,15 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStage = kABytes + kBBytes;
   static constexpr int kBarOff = STAGES * kStage;
-  static constexpr int kTotal = kBarOff + 256 + 1024;  // barriers + tmem slot, + 1 KB alignment slack
+  static constexpr int kNormOff = kBarOff + 256;           // EPI_NORM: [8][128] partial sums written by cluster peers
+  static constexpr int kTotal = kNormOff + 4096 + 1024;    // barriers + tmem slot + norm slots + 1 KB alignment slack  // barriers + tmem slot, + 1 KB alignment slack
 };
 
 template <int BN, int NSTAGES, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_kernel(const __grid_constant__ Batch batch) {
   static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported tile width");
-  static_assert(EPI == EPI_STORE || BN == 192, "the gate epilogue uses 192-wide tiles (3 gates x 64 units)");
+  static_assert(EPI != EPI_GATES || BN == 192, "the gate epilogue uses 192-wide tiles (3 gates x 64 units)");
+  static_assert(EPI != EPI_NORM || BN == 64, "the fused-norm epilogue uses four 64-wide tiles per cluster");
   constexpr int TMEM_COLS = BN == 192 ? 256 : BN;   // allocations are powers of two >= 32 columns
   using L = SmemLayout<BN, NSTAGES>;
   constexpr int STAGES = L::STAGES;
@@ -218,6 +225,11 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
         if (it == 0) SD_TC_STAMP(3);
       }
     }
+    if (EPI == EPI_NORM) {  // every thread of the cluster takes part in the epilogue's cluster barrier
+      __syncwarp();
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
@@ -236,6 +248,11 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
         tc_commit(bar_empty + s * 8);  // frees the smem stage once these MMAs have read it
       }
       if (num_kb > 0) tc_commit(bar_acc);  // accumulator complete
+    }
+    if (EPI == EPI_NORM) {
+      __syncwarp();
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
   } else {
     // epilogue: warp w owns TMEM lanes [32*(w%4), +32) == output rows m0 + 32*(w%4) + lane
@@ -286,6 +303,52 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
           const float o = stg[rr * SLDG + lane];
           pr.e_out[(size_t)(rb + rr) * pr.e_ld_out + u0 + lane] = o;
           if (pr.e_out_bf) pr.e_out_bf[(size_t)(rb + rr) * pr.e_ld_bf + u0 + lane] = __float2bfloat16(o);
+        }
+      }
+    } else if (EPI == EPI_NORM) {
+      // warp (quad, half) owns rows [32*quad, +32) x columns [n0 + 32*half, +32) of this CTA's 64-wide tile
+      const int halfn = (warp - 2) >> 2;
+      constexpr int SLDN = 33;
+      float* stg = reinterpret_cast<float*>(gen_base) + (warp - 2) * (32 * SLDN);
+      float* ssq = reinterpret_cast<float*>(gen_base + L::kNormOff);       // [8 partials][128 rows], never touched by TMA
+      const int rb = m0 + quad * 32;
+      const int c0 = n0 + halfn * 32;
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(halfn * 32), v);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] += pr.bias ? pr.bias[c0 + j] : 0.f;
+        ss = fmaf(v[j], v[j], ss);
+      }
+      // partial (cluster rank, half) of row (quad*32 + lane) -> slot of every CTA in the cluster
+      uint32_t my_rank;
+      asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(my_rank));
+      const uint32_t local = (uint32_t)__cvta_generic_to_shared(ssq + (my_rank * 2 + halfn) * 128 + quad * 32 + lane);
+#pragma unroll
+      for (uint32_t r = 0; r < 4; ++r) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(ss) : "memory");
+      }
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      float tot = 0.f;
+#pragma unroll
+      for (int pidx = 0; pidx < 8; ++pidx) tot += ssq[pidx * 128 + quad * 32 + lane];   // fixed order
+      const float rs = 1.f / sqrtf(tot / (float)pr.N + 1e-4f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float y = (v[j] * rs) * pr.e_gain[c0 + j];
+        stg[lane * SLDN + j] = __fdividef(y, 1.f + __expf(-y));
+      }
+      __syncwarp();
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        if (rb + rr < batch.R) {
+          const float o = stg[rr * SLDN + lane];
+          if (pr.e_out) pr.e_out[(size_t)(rb + rr) * pr.e_ld_out + c0 + lane] = o;
+          if (pr.e_out_bf) pr.e_out_bf[(size_t)(rb + rr) * pr.e_ld_bf + c0 + lane] = __float2bfloat16(o);
         }
       }
     } else {
