@@ -1572,18 +1572,18 @@ static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n) {
 template <int GS>
 static void launch_sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
                               const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
-                              float* d_logit, int ld_d, bf16* d_logit_bf) {
+                              float* d_logit, int ld_d, bf16* d_logit_bf, const float* a_scale) {
   const long long n = (long long)R * S * GS;
   launch_k(cx.st, sd::sample_bwd_kernel<GS>, dim3((int)((n + 255) / 256)), dim3(256), 0, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul,
-                                                                       R, S, K, unimix, d_logit, ld_d, d_logit_bf);
+                                                                       R, S, K, unimix, d_logit, ld_d, d_logit_bf, a_scale);
 }
 static void sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
                        const float* gb_, int ld_b, const float* ul, int ld_ul, int R, int S, int K, float unimix,
-                       float* d_logit, int ld_d, bf16* d_logit_bf = nullptr) {
+                       float* d_logit, int ld_d, bf16* d_logit_bf = nullptr, const float* a_scale = nullptr) {
   if (cx.err) return;
-  if (K <= 8) launch_sample_bwd<8>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf);
-  else if (K <= 16) launch_sample_bwd<16>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf);
-  else launch_sample_bwd<32>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf);
+  if (K <= 8) launch_sample_bwd<8>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf, a_scale);
+  else if (K <= 16) launch_sample_bwd<16>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf, a_scale);
+  else launch_sample_bwd<32>(cx, lg, ld_l, u, ld_u, ga, ld_a, gb_, ld_b, ul, ld_ul, R, S, K, unimix, d_logit, ld_d, d_logit_bf, a_scale);
   cx.check("sample_bwd_kernel");
 }
 // Backward of latent_logits: d(logits) -> d(layer-0 input) [R x K0] in `dx0`; fills the d-tape slots.
@@ -1613,7 +1613,8 @@ static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, si
 // d(stoch) in bw.t_dz and, when want_act, d(abar) in bw.d_abar.
 static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, bool want_act,
                            const float* deter_in, int ld_in, const float* ga, int ld_a, const float* gb, int ld_b,
-                           const float* gc, int ld_c) {
+                           const float* gc, int ld_c, const float* ga2 = nullptr, const float* dxin_prev = nullptr,
+                           const float* a_scale = nullptr) {
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
   const int U = c.U, D = c.D, Dg = h.Dg, Kb = Dg + 3 * U;
@@ -1622,8 +1623,8 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   float* d_vin = bw.d_vin + slot * 3 * U;
   if (cx.err) return;
   const bool tcb = cx.tc;   // large-row backward: bf16 copies of the gradients feed the tcgen05 dgrads
-  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, ga, ld_a, gb, ld_b, gc, ld_c,
-           (const float*)sb.q, deter_in, ld_in, d_q, tcb ? bw.d_q_bf : (bf16*)nullptr, bw.dd, R, D, Dg);
+  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, ga, ld_a, gb, ld_b, gc, ld_c, ga2,
+           dxin_prev, c.G, Kb, a_scale, (const float*)sb.q, deter_in, ld_in, d_q, tcb ? bw.d_q_bf : (bf16*)nullptr, bw.dd, R, D, Dg);
   cx.check("gates_bwd_kernel");
   dgrad_any(cx, R, h.gru, d_q, tcb ? bw.d_q_bf : nullptr, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
   sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D,
@@ -1713,26 +1714,35 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
     base.stride = 1;
     cudaMemsetAsync(bw.carry_z, 0, (size_t)B * SK * sizeof(float), cx.st);
     cudaMemsetAsync(bw.carry_d, 0, (size_t)B * D * sizeof(float), cx.st);
+    // The carry (grads of a step's input state, cut where is_first) is never materialised inside the loop:
+    // the first consumers of step t (sample_bwd, gates_bwd) assemble it from step t+1's pieces
+    // (t_dz | dd + t_din0 + dxin[:, g, :Dg]) and step t+1's keep mask.
     for (int t = T - 1; t >= 0 && !cx.err; --t) {
       StepBufs sb = at_step(base, t, B, *h);
+      const bool has_next = t + 1 < T;
+      const float* keep_next = has_next ? at_step(base, t + 1, B, *h).keep : nullptr;
       const size_t slot = (size_t)t * B;
       float* d_lg = bw.d_lg + slot * SK;
-      sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, bw.carry_z, SK, d_stochs ? d_stochs + (size_t)t * SK : nullptr, T * SK,
-                 d_logits ? d_logits + (size_t)t * SK : nullptr, T * SK, B, c.S, c.K, c.unimix, d_lg, SK);
+      sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, has_next ? bw.t_dz : nullptr, SK,
+                 d_stochs ? d_stochs + (size_t)t * SK : nullptr, T * SK, d_logits ? d_logits + (size_t)t * SK : nullptr, T * SK,
+                 B, c.S, c.K, c.unimix, d_lg, SK, nullptr, keep_next);
       // d[deter' | embed]: the deter' part goes to a scratch, the embed part straight into d_embed[:, t]
       latent_logits_bwd(cx, sb, bw, slot, B, h->obs, c.obs_layers, h->obs_logit, d_lg, bw.t_dxe, D,
                         d_embed ? d_embed + (size_t)t * E : nullptr, T * E);
       if (cx.err) return;
-      deter_core_bwd(cx, sb, bw, slot, B, false, sb.din, D, bw.carry_d, D, d_deters ? d_deters + (size_t)t * D : nullptr, T * D,
-                     bw.t_dxe, D);
+      deter_core_bwd(cx, sb, bw, slot, B, false, sb.din, D, has_next ? bw.dd : nullptr, D,
+                     d_deters ? d_deters + (size_t)t * D : nullptr, T * D, bw.t_dxe, D, has_next ? bw.t_din0 : nullptr,
+                     has_next ? bw.t_dxin : nullptr, keep_next);
       if (cx.err) return;
-      // reset cut (rssm.py:161-165): carry = d(step inputs) * (1 - is_first)
+    }
+    if (cx.err) return;
+    {  // grads of the initial state: step 0's pieces with step 0's reset cut (rssm.py:161-165)
+      StepBufs sb0 = at_step(base, 0, B, *h);
       launch_k(cx.st, sd::carry_kernel, dim3(grid1d((long long)B * (SK + D), 256)), dim3(256), 0, (const float*)bw.dd,
-               (const float*)bw.t_din0, (const float*)bw.t_dz, (const float*)sb.keep, (const float*)nullptr, 0,
+               (const float*)bw.t_din0, (const float*)bw.t_dz, (const float*)sb0.keep, (const float*)nullptr, 0,
                (const float*)nullptr, 0, (const float*)bw.t_dxin, c.G, h->Dg, h->Dg + 3 * c.U, B, SK, D, bw.carry_z, bw.carry_d);
       cx.check("carry_kernel");
     }
-    if (cx.err) return;
     if (d_init_stoch) cudaMemcpyAsync(d_init_stoch, bw.carry_z, (size_t)B * SK * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
     if (d_init_deter) cudaMemcpyAsync(d_init_deter, bw.carry_d, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
     if (!wg) return;

@@ -82,7 +82,7 @@ template <int GS>
 __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, const float* __restrict__ u, int ld_u,
                                   const float* __restrict__ gz_a, int ld_a, const float* __restrict__ gz_b, int ld_b,
                                   const float* __restrict__ up_logit, int ld_ul, int R, int S, int K, float unimix,
-                                  float* d_logit, int ld_d, __nv_bfloat16* d_logit_bf) {
+                                  float* d_logit, int ld_d, __nv_bfloat16* d_logit_bf, const float* __restrict__ a_scale) {
   pdl_prologue();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long cat = t / GS;
@@ -96,7 +96,7 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
   if (valid) {
     lg = logits[row * ld_l + col];
     uu = u[row * ld_u + col];
-    if (gz_a) gz += gz_a[row * ld_a + col];
+    if (gz_a) gz += gz_a[row * ld_a + col] * (a_scale ? a_scale[row] : 1.f);  // a_scale: reset cut of the later step
     if (gz_b) gz += gz_b[row * ld_b + col];
   }
   float y;
@@ -128,8 +128,12 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
 // path dd = g * (1 - update).
 // g = ga + gb + gc (gb, gc nullable): carry from step t+1, upstream d_deters[:, t] and the gradient coming back
 // through the posterior / prior net, summed here instead of in a separate kernel.
+// When `ga2` / `dxin` are given the carry is assembled here instead of by carry_kernel:
+//   carry = (ga + ga2 + dxin[row][g][o]) * a_scale[row]   (d(deter_in) pieces of step t+1 and its reset cut).
 __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const float* __restrict__ gb, int ld_b,
-                                 const float* __restrict__ gc, int ld_c, const float* __restrict__ q,
+                                 const float* __restrict__ gc, int ld_c, const float* __restrict__ ga2,
+                                 const float* __restrict__ dxin, int G, int Kb, const float* __restrict__ a_scale,
+                                 const float* __restrict__ q,
                                  const float* __restrict__ deter_in, int ld_in, float* dq, __nv_bfloat16* dq_bf, float* dd,
                                  int R, int D, int Dg) {
   pdl_prologue();
@@ -142,7 +146,11 @@ __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const f
     const size_t qo = row * 3 * D + (size_t)gi * 3 * Dg + o;
     const float r = q[qo], c = q[qo + Dg], uu = q[qo + 2 * Dg];
     const float Rg = sigmoidf_(r), C = tanhf(Rg * c), Uu = sigmoidf_(uu - 1.f);
-    const float gd = ga[row * ld_a + d] + (gb ? gb[row * ld_b + d] : 0.f) + (gc ? gc[row * ld_c + d] : 0.f);
+    float carry = ga ? ga[row * ld_a + d] : 0.f;
+    if (ga2) carry += ga2[row * D + d];
+    if (dxin) carry += dxin[(row * G + gi) * (size_t)Kb + o];
+    if (a_scale) carry *= a_scale[row];
+    const float gd = carry + (gb ? gb[row * ld_b + d] : 0.f) + (gc ? gc[row * ld_c + d] : 0.f);
     const float dUu = gd * (C - deter_in[row * ld_in + d]);
     const float dC = gd * Uu;
     const float dtn = dC * (1.f - C * C);
