@@ -18,11 +18,16 @@ namespace sd {
 
 constexpr float kRmsEps = 1e-4f;
 
-// Programmatic dependent launch prologue: let the next kernel in the stream get scheduled now, then wait
-// until every prerequisite grid has completed and its writes are visible.  No-ops without the PDL attribute.
+// Programmatic dependent launch prologue: wait until every prerequisite grid has completed and its writes are
+// visible, then let the next kernel in the stream get scheduled (it will block in its own wait until this grid
+// is done).  Triggering only AFTER the wait keeps the look-ahead at depth one: a kernel that runs early can
+// overlap with its immediate predecessor only, which is what makes the weight prefetch in gemm_f32_kernel
+// safe (weights are written by pack_weight_kernel, which never triggers early).  No-ops without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_wait();
+  pdl_trigger();
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -133,8 +138,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 // distributed shared memory; the leader adds the slices in rank order (deterministic) and stores.
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ksplit, int kslice) {
   SD_G_STAMP(0);
-  pdl_prologue();
-  SD_G_STAMP(1);
   const int prob = blockIdx.z % b.count, rtile = blockIdx.z / b.count;
   const GemmP& p = b.p[prob];
   const bool gates = p.epi == EPI_GATES;   // cluster = (3,1,1): blockIdx.x = tile*3 + gate
@@ -151,6 +154,21 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
   const int kc = gates ? 0 : rank * kslice;
   const int kend = min(p.K, kc + kslice);
   float s = 0.f;
+  // Weight prefetch BEFORE the PDL wait: the packed weights do not depend on the preceding kernel, so their
+  // L2 round trip overlaps its execution; only the activations have to wait.
+  float4 w[GB_KC / 4 / 64][4];
+#pragma unroll
+  for (int i = 0; i < GB_KC / 4 / 64; ++i) {
+    const int kbase = kc + (ty + 64 * i) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kbase + j;
+      w[i][j] = (active && k < kend) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + wcol + tx * 4))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  pdl_prologue();
+  SD_G_STAMP(1);
   if (active && kc < kend) {
     float acc[16][4];
 #pragma unroll
@@ -158,17 +176,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
     // all global loads of this CTA are issued before anything is stored to shared memory
-    float4 w[GB_KC / 4 / 64][4];
-#pragma unroll
-    for (int i = 0; i < GB_KC / 4 / 64; ++i) {
-      const int kbase = kc + (ty + 64 * i) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kbase + j;
-        w[i][j] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + wcol + tx * 4))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+    // (weights were prefetched into w[][] before the PDL wait, see below)
     // activation slice -> shared memory.  Fast path: 16-byte loads/stores (thread owns 8 float4 = 2 rows x 4
     // quads... precisely: quad q = tid & 127 of rows 2*i + (tid >> 7)); needs 16 B aligned rows and a segment
     // boundary on a multiple of 4.  Otherwise scalar (thread owns columns tid and tid+256 of all 16 rows).
@@ -427,7 +435,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, long long
 __global__ void pack_weight_kernel(const float* __restrict__ src, int G, int N, int K, long long s_g,
                                    long long s_n, long long s_k, float* wt, int ldw, float* wn, int ldk,
                                    __nv_bfloat16* wn_bf, __nv_bfloat16* wt_bf) {
-  pdl_prologue();
+  pdl_wait();   // no early trigger: consumers may prefetch packed weights before their own wait
   const long long total = (long long)G * N * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {

@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
   const uint32_t tmem_base = *tmem_slot_gen;
   if (threadIdx.x == 0) SD_TC_STAMP(1);
   // PDL: barrier init / TMEM allocation above overlap the previous kernel; global memory is touched below.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) SD_TC_STAMP(2);
 
   if (warp == 0) {
