@@ -195,7 +195,24 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   if (threadIdx.x == 0) SD_TC_STAMP(1);
-  // PDL: barrier init / TMEM allocation above overlap the previous kernel; global memory is touched below.
+  // PDL: barrier init / TMEM allocation above overlap the previous kernel.  The weight tiles do not depend on
+  // it either, so the producer arms the first ring stages and issues their weight TMA loads BEFORE the wait;
+  // activations (A tiles), bias-free outputs etc. are only touched after it.
+  const int n_pref = num_kb < STAGES ? num_kb : STAGES;
+  if (warp == 0 && lane == 0) {
+    const CUtensorMap* mw = &batch.maps[pr.w_map];
+    for (int it = 0; it < n_pref; ++it) {
+      const uint32_t sb = base + it * L::kStage + L::kABytes;
+      mbar_expect_tx(bar_full + it * 8, L::kStage);
+      if (EPI == EPI_GATES) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          tma_load_2d(sb + j * (64 * BK * 2), mw, (kb0 + it) * BK, pr.w_row + j * pr.e_dg + n0, bar_full + it * 8);
+      } else {
+        tma_load_2d(sb, mw, (kb0 + it) * BK, pr.w_row + n0, bar_full + it * 8);
+      }
+    }
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) SD_TC_STAMP(2);
@@ -212,10 +229,12 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(bar_empty + s * 8, ph ^ 1u);
         const uint32_t sa = base + s * L::kStage, sb = sa + L::kABytes;
-        mbar_expect_tx(bar_full + s * 8, L::kStage);
+        if (it >= n_pref) mbar_expect_tx(bar_full + s * 8, L::kStage);   // first ring round was armed before the wait
         if (kb < kbA) tma_load_2d(sa, ma1, pr.a1_col + kb * BK, m0, bar_full + s * 8);
         else          tma_load_2d(sa, ma2, pr.a2_col + (kb - kbA) * BK, m0, bar_full + s * 8);
-        if (EPI == EPI_GATES) {  // three 64-row boxes: the reset / cand / update rows of this tile's units
+        if (it < n_pref) {
+          // weight tile already in flight
+        } else if (EPI == EPI_GATES) {  // three 64-row boxes: the reset / cand / update rows of this tile's units
 #pragma unroll
           for (int j = 0; j < 3; ++j)
             tma_load_2d(sb + j * (64 * BK * 2), mw, kb * BK, pr.w_row + j * pr.e_dg + n0, bar_full + s * 8);
