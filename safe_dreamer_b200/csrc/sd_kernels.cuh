@@ -734,21 +734,13 @@ __global__ void __launch_bounds__(256) actor_tail_kernel(const float* __restrict
                                                          const float* __restrict__ w2_t, int ldw_2,
                                                          const float* __restrict__ b2, int U, int R, float* aout,
                                                          float* action, int ld_act, float* abar, float* v2, int ld_v2) {
-  pdl_prologue();
   extern __shared__ __align__(16) float tsm[];
   float* wl_s = tsm;                          // [act_out][units]
   float* bl_s = wl_s + act_out * units;       // [act_out]
   float* w2_s = bl_s + act_out;               // [A][U]
   float* b2_s = w2_s + A * U;                 // [U]
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  // one global round trip: this row's activations and the CTA's share of the (tiny) weights are all in flight
-  float x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = lane + 32 * i;
-    x[i] = (row < R && k < units) ? a3[(size_t)row * ld_a3 + k] : 0.f;
-  }
-  const float nz = (row < R && lane < A) ? noise[(size_t)row * ld_n + lane] : 0.5f;
+  // packed weights and the injected noise do not depend on the preceding kernel: stage them before the PDL wait
   for (int i = threadIdx.x; i < act_out * units; i += blockDim.x) {
     const int j = i / units, k = i - j * units;
     wl_s[i] = __ldg(wl_n + (size_t)j * ldk_l + k);
@@ -759,6 +751,14 @@ __global__ void __launch_bounds__(256) actor_tail_kernel(const float* __restrict
   }
   for (int i = threadIdx.x; i < act_out; i += blockDim.x) bl_s[i] = bl[i];
   for (int i = threadIdx.x; i < U; i += blockDim.x) b2_s[i] = b2[i];
+  const float nz = (row < R && lane < A) ? noise[(size_t)row * ld_n + lane] : 0.5f;
+  pdl_prologue();
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = lane + 32 * i;
+    x[i] = (row < R && k < units) ? a3[(size_t)row * ld_a3 + k] : 0.f;
+  }
   __syncthreads();
   if (row >= R) return;
   float acc[kTailMaxOut];
