@@ -28,20 +28,23 @@ struct NormActBwdBatch {
   NormActBwdP p[4];
 };
 __global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch b) {
-  pdl_prologue();
   __shared__ float sh[32];
   const NormActBwdP& p = b.p[blockIdx.y];
   const size_t row = blockIdx.x;
   const float* v = p.v + row * p.ld_v;
   const float* dout = p.dout + row * p.ld_dout;
-  float vv[8], dn[8], nn[8];
+  float vv[8], dn[8], nn[8], gw[8];
   float ss = 0.f;
+  // the saved pre-norm values (forward tape) and the RMS scale do not depend on the preceding kernel of the
+  // reverse scan: fetch them before the PDL wait; only `dout` has to wait
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 256;
-    vv[i] = (c < p.width) ? v[c] : 0.f;
+    vv[i] = (c < p.width) ? __ldg(v + c) : 0.f;
+    gw[i] = (c < p.width) ? __ldg(p.w + c) : 0.f;
     ss = fmaf(vv[i], vv[i], ss);
   }
+  pdl_prologue();
   ss = block_sum(ss, sh);
   const float rho = 1.f / sqrtf(ss / (float)p.width + kRmsEps);
   float dot = 0.f;
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch 
     const int c = threadIdx.x + i * 256;
     dn[i] = 0.f; nn[i] = 0.f;
     if (c < p.width) {
-      const float w = p.w[c];
+      const float w = gw[i];
       const float n = vv[i] * rho;
       const float m = n * w;
       const float sg = sigmoidf_(m);

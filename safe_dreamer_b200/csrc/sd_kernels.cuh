@@ -167,6 +167,13 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  // bias of this thread's output element(s) (packed weights too)
+  const int pre_n = n0 + (tid & 15);
+  float pb0 = 0.f, pb1 = 0.f, pb2 = 0.f;
+  if (p.bias && active && pre_n < p.N) {
+    pb0 = __ldg(p.bias + pre_n);
+    if (gates) { pb1 = __ldg(p.bias + p.e_k + pre_n); pb2 = __ldg(p.bias + 2 * p.e_k + pre_n); }
+  }
   pdl_prologue();
   SD_G_STAMP(1);
   if (active && kc < kend) {
@@ -279,9 +286,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
     cluster_sync_all();
     if (gate != 0 || !active || row >= b.R || n >= p.N) return;
     const int Dg = p.e_k;
-    const float qr = slots[tid] + (p.bias ? p.bias[n] : 0.f);
-    const float qc = slots[256 + tid] + (p.bias ? p.bias[Dg + n] : 0.f);
-    const float qu = slots[512 + tid] + (p.bias ? p.bias[2 * Dg + n] : 0.f);
+    const float qr = slots[tid] + pb0;
+    const float qc = slots[256 + tid] + pb1;
+    const float qu = slots[512 + tid] + pb2;
     if (p.C) {
       float* q = p.C + (size_t)row * p.ldc;
       q[n] = qr; q[Dg + n] = qc; q[2 * Dg + n] = qu;
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
     for (int r = 0; r < ksplit; ++r) s += slots[r * 256 + tid];
   }
   const bool ok = active && row < b.R && n < p.N;
-  const float val = s + ((p.bias && ok) ? p.bias[n] : 0.f);
+  const float val = s + pb0;
   if (p.epi == EPI_SAMPLE) {
     // 16 consecutive threads own the 16 logits of one (row, tile): 16/Kc whole categories
     const int Kc = p.e_k;
@@ -489,12 +496,18 @@ struct NormActBatch {
   NormActP p[4];
 };
 __global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
-  pdl_prologue();
   __shared__ float sh[32];
   const NormActP& p = b.p[blockIdx.y];
   const size_t row = blockIdx.x;
   float* in = p.in + row * p.ld_in;
-  float v[8];
+  float v[8], g[8];
+  // the RMS scale is a packed weight: fetch it before the PDL wait (off the post-reduction critical path)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    g[i] = (c < p.width) ? __ldg(p.w + c) : 0.f;
+  }
+  pdl_prologue();
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 256;
     if (c < p.width) {
-      const float y = siluf_((v[i] * rs) * p.w[c]);
+      const float y = siluf_((v[i] * rs) * g[i]);
       if (p.out) p.out[row * p.ld_out + c] = y;
       if (p.out_bf) p.out_bf[row * p.ld_bf + c] = __float2bfloat16(y);
     }
