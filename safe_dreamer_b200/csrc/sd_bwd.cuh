@@ -86,7 +86,6 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
                                   const float* __restrict__ gz_a, int ld_a, const float* __restrict__ gz_b, int ld_b,
                                   const float* __restrict__ up_logit, int ld_ul, int R, int S, int K, float unimix,
                                   float* d_logit, int ld_d, __nv_bfloat16* d_logit_bf, const float* __restrict__ a_scale) {
-  pdl_prologue();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long cat = t / GS;
   const int k = (int)(t % GS);
@@ -95,25 +94,30 @@ __global__ void sample_bwd_kernel(const float* __restrict__ logits, int ld_l, co
   const int sidx = in_range ? (int)(cat - (long long)row * S) : 0;
   const bool valid = in_range && k < K;
   const int col = sidx * K + k;
-  float lg = 0.f, uu = 0.5f, gz = 0.f;
+  // Everything that only needs the forward tape (saved logits, uniforms) is done BEFORE the PDL wait: the
+  // re-sampling softmaxes y and p are most of this kernel's arithmetic.
+  float lg = 0.f, uu = 0.5f;
   if (valid) {
-    lg = logits[row * ld_l + col];
-    uu = u[row * ld_u + col];
-    if (gz_a) gz += gz_a[row * ld_a + col] * (a_scale ? a_scale[row] : 1.f);  // a_scale: reset cut of the later step
-    if (gz_b) gz += gz_b[row * ld_b + col];
+    lg = __ldg(logits + row * ld_l + col);
+    uu = __ldg(u + row * ld_u + col);
   }
   float y;
   (void)sample_group<GS>(lg, uu, valid, k, K, unimix, &y);
   if (!valid) y = 0.f;
-  // dl = y * (gz - <gz, y>)
-  const float gy = group_sum<GS>(gz * y);
-  const float dl = y * (gz - gy);
-  // p, p~ (unimix), d(log p~) = dl - p~ * sum(dl), dp = d(log p~)/p~ * (1-unimix), d_logit = p*(dp - <dp,p>)
   const float m = group_max<GS>(valid ? lg : -INFINITY);
   const float e = valid ? expf(lg - m) : 0.f;
   const float s = group_sum<GS>(e);
   const float p = e / s;
   const float pt = p * (1.f - unimix) + unimix / (float)K;
+  pdl_prologue();
+  float gz = 0.f;
+  if (valid) {
+    if (gz_a) gz += gz_a[row * ld_a + col] * (a_scale ? a_scale[row] : 1.f);  // a_scale: reset cut of the later step
+    if (gz_b) gz += gz_b[row * ld_b + col];
+  }
+  // dl = y * (gz - <gz, y>);  d(log p~) = dl - p~ * sum(dl);  dp = d(log p~)/p~ * (1-unimix);  d_logit = p*(dp - <dp,p>)
+  const float gy = group_sum<GS>(gz * y);
+  const float dl = y * (gz - gy);
   const float sdl = group_sum<GS>(dl);
   const float dlp = dl - pt * sdl;
   const float dp = valid ? dlp / pt * (1.f - unimix) : 0.f;

@@ -603,7 +603,6 @@ template <int GS>
 __global__ void sample_kernel(const float* __restrict__ logits, int ld_l, const float* __restrict__ u, int ld_u,
                               int R, int S, int K, float unimix, float* stoch, int ld_o, __nv_bfloat16* stoch_bf,
                               int ld_bf, float* logit_copy, int ld_c, int* idx_out) {
-  pdl_prologue();
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long cat = t / GS;          // (row, s)
   const int k = (int)(t % GS);
@@ -612,10 +611,9 @@ __global__ void sample_kernel(const float* __restrict__ logits, int ld_l, const 
   const int sidx = in_range ? (int)(cat - (long long)row * S) : 0;
   const bool valid = in_range && k < K;
   float lg = 0.f, uu = 0.5f;
-  if (valid) {
-    lg = logits[row * ld_l + sidx * K + k];
-    uu = u[row * ld_u + sidx * K + k];
-  }
+  if (valid) uu = __ldg(u + row * ld_u + sidx * K + k);   // injected noise: independent of the preceding kernel
+  pdl_prologue();
+  if (valid) lg = logits[row * ld_l + sidx * K + k];
   const int best = sample_group<GS>(lg, uu, valid, k, K, unimix, nullptr);
   if (valid) {
     const float v = (k == best) ? 1.f : 0.f;
