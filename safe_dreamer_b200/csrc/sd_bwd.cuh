@@ -143,22 +143,34 @@ __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const f
                                  const float* __restrict__ q,
                                  const float* __restrict__ deter_in, int ld_in, float* dq, __nv_bfloat16* dq_bf, float* dd,
                                  int R, int D, int Dg) {
-  pdl_prologue();
   const long long total = (long long)R * D;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // first element's taped operands (gate pre-activations, step input) are fetched before the PDL wait
+  float pr_ = 0.f, pc_ = 0.f, pu_ = 0.f, pd_ = 0.f;
+  if (i < total) {
     const int d = (int)(i % D);
     const size_t row = (size_t)(i / D);
     const int gi = d / Dg, o = d - gi * Dg;
     const size_t qo = row * 3 * D + (size_t)gi * 3 * Dg + o;
-    const float r = q[qo], c = q[qo + Dg], uu = q[qo + 2 * Dg];
+    pr_ = __ldg(q + qo); pc_ = __ldg(q + qo + Dg); pu_ = __ldg(q + qo + 2 * Dg);
+    pd_ = __ldg(deter_in + row * ld_in + d);
+  }
+  pdl_prologue();
+  for (bool first = true; i < total; i += stride, first = false) {
+    const int d = (int)(i % D);
+    const size_t row = (size_t)(i / D);
+    const int gi = d / Dg, o = d - gi * Dg;
+    const size_t qo = row * 3 * D + (size_t)gi * 3 * Dg + o;
+    const float r = first ? pr_ : q[qo], c = first ? pc_ : q[qo + Dg], uu = first ? pu_ : q[qo + 2 * Dg];
+    const float din = first ? pd_ : deter_in[row * ld_in + d];
     const float Rg = sigmoidf_(r), C = tanhf(Rg * c), Uu = sigmoidf_(uu - 1.f);
     float carry = ga ? ga[row * ld_a + d] : 0.f;
     if (ga2) carry += ga2[row * D + d];
     if (dxin) carry += dxin[(row * G + gi) * (size_t)Kb + o];
     if (a_scale) carry *= a_scale[row];
     const float gd = carry + (gb ? gb[row * ld_b + d] : 0.f) + (gc ? gc[row * ld_c + d] : 0.f);
-    const float dUu = gd * (C - deter_in[row * ld_in + d]);
+    const float dUu = gd * (C - din);
     const float dC = gd * Uu;
     const float dtn = dC * (1.f - C * C);
     const float o_r = (dtn * c) * Rg * (1.f - Rg), o_c = dtn * Rg, o_u = dUu * Uu * (1.f - Uu);
