@@ -21,6 +21,7 @@
 #include "sd_kernels.cuh"
 #include "sd_bwd.cuh"
 #include "sd_tc.cuh"
+#include "sd_chain.cuh"
 
 using bf16 = __nv_bfloat16;
 
@@ -562,6 +563,146 @@ static bool linear_norm_tc(Ctx& cx, int R, const LinearW& L, Operand a, const St
   return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------ chain kernels
+// SD_CHAIN=1 selects the row-tile resident chain kernels (sd_chain.cuh).  Measured on B200 at N = 1024 they tie with
+// the layer-by-layer path (8 CTAs own all the element-wise work of a 1024 x 256 layer: MUFU / TMEM-read bound, see
+// profiles/r01b_chain_phase_stamps.txt), so the default is the 13-launch variant below; the chain pays at larger N.
+static bool chain_enabled() { static int v = env_flag("SD_CHAIN", 0); return v != 0; }
+static bool wide_in_enabled() { static int v = env_flag("SD_WIDE_IN", 1); return v != 0; }
+
+static void launch_chain(Ctx& cx, const sd::chain::Params& P, int side_ctas, const char* what) {
+  if (cx.err) return;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(sd::chain::mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::chain::kSmemBytes);
+    attr_done = true;
+  }
+  static long long* timing_dev = nullptr;
+  static int timing_budget = 12;
+  if (cx.trace && getenv("SD_TRACE_CHAIN") && timing_budget > 0) {
+    if (!timing_dev) cudaMalloc(&timing_dev, 16 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 16 * sizeof(long long), cx.st);
+    sd::chain::Params P2 = P;
+    P2.timing = timing_dev;
+    launch_k(cx.st, sd::chain::mlp_chain_kernel, dim3(P.n_tiles + side_ctas), dim3(sd::chain::THREADS),
+             (size_t)sd::chain::kSmemBytes, P2);
+    cudaStreamSynchronize(cx.st);
+    long long t[16];
+    cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[SD_TRACE_CHAIN] %s cycles from start: prewait=%lld pdlwait=%lld prologue=%lld | acc0=%lld epi0=%lld acc1=%lld "
+                    "epi1=%lld | accF=%lld tail_sampled=%lld fin_done=%lld end=%lld\n", what, t[1] - t[0], t[2] - t[0], t[3] - t[0],
+            t[4] ? t[4] - t[0] : 0, t[5] ? t[5] - t[0] : 0, t[6] ? t[6] - t[0] : 0, t[7] ? t[7] - t[0] : 0, t[8] - t[0],
+            t[9] ? t[9] - t[0] : 0, t[10] - t[0], t[11] - t[0]);
+    --timing_budget;
+  } else
+  launch_k(cx.st, sd::chain::mlp_chain_kernel, dim3(P.n_tiles + side_ctas), dim3(sd::chain::THREADS),
+           (size_t)sd::chain::kSmemBytes, P);
+  cx.check(what);
+}
+static bool chain_add_layer(sd::chain::Params& P, const LinearW& L, int box_rows) {
+  const int i = P.n_layers;
+  if (i >= sd::chain::kMaxLayers || !L.w_bf || L.K != sd::chain::HID) return false;
+  if (!make_map(&P.maps[i], L.w_bf, (uint64_t)L.npad, (uint64_t)L.K, (uint64_t)L.K, (uint32_t)box_rows)) return false;
+  P.layer[i].w_map = i; P.layer[i].N = L.N; P.layer[i].box_rows = box_rows; P.layer[i].bias = L.bias; P.layer[i].gain = L.gain;
+  P.n_layers = i + 1;
+  return true;
+}
+// The chain kernels cover the base architecture (256-wide hidden layers); anything else keeps the layer-by-layer path.
+static bool imagine_chain_ok(const sd_handle& h) {
+  const sd_config& c = h.c;
+  const HeadW& actor = h.heads[SD_MOD_ACTOR];
+  return chain_enabled() && fused_epi_enabled() && c.U == sd::chain::HID && c.units == sd::chain::HID && actor.layers >= 1 &&
+         actor.layers <= 3 && h.act_out <= sd::chain::kTailMaxOut && c.A <= 32 && c.img_layers >= 1 && c.img_layers <= 3 &&
+         h.SK <= 512 && (h.SK % 64) == 0 && (c.D % 64) == 0 && (h.Dg % 64) == 0 && c.G <= sd::tc::kMaxProblems;
+}
+static int ks_for(int K) {   // split-K factor giving ~8-10 k-blocks of 64 per CTA (at most 4 slices)
+  const int kb = K / 64;
+  int ks = (kb + 4) / 9;
+  return ks < 1 ? 1 : (ks > 4 ? 4 : ks);
+}
+// First launch of an imagination step: the three wide layers that read feat = [stoch | deter] --
+// actor layer 0 (F -> units), dyn_in0 (deter -> U), dyn_in1 (stoch -> U) -- as one split-K tcgen05 batch.
+// Pre-norm outputs land in sb.va[0] / sb.vin (+ partial slices); ks[] returns the per-layer split factors.
+static void imagine_wide_in(Ctx& cx, int N, const StepBufs& sb, int* ks) {
+  if (cx.err) return;
+  sd_handle& h = *cx.h;
+  const sd_config& c = h.c;
+  const HeadW& actor = h.heads[SD_MOD_ACTOR];
+  const int SK = h.SK, D = c.D, F = h.F, U = c.U;
+  sd::tc::Batch tb;
+  memset(&tb, 0, sizeof(tb));
+  bool ok = make_map(&tb.maps[0], h.feat_bf, (uint64_t)N, (uint64_t)F, (uint64_t)F, 128);
+  ok = ok && make_map(&tb.maps[1], actor.l[0].w_bf, (uint64_t)actor.l[0].npad, (uint64_t)F, (uint64_t)F, 64);
+  ok = ok && make_map(&tb.maps[2], h.in0.w_bf, (uint64_t)h.in0.npad, (uint64_t)D, (uint64_t)D, 64);
+  ok = ok && make_map(&tb.maps[3], h.in1.w_bf, (uint64_t)h.in1.npad, (uint64_t)SK, (uint64_t)SK, 64);
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed"); return; }
+  ks[0] = ks_for(F); ks[1] = ks_for(D); ks[2] = ks_for(SK);
+  sd::tc::Problem* p = tb.p;
+  p[0].a1_map = 0; p[0].a1_col = 0;  p[0].a2_map = 0; p[0].w_map = 1; p[0].K1 = F;  p[0].K = F;  p[0].N = c.units; p[0].ldc = c.units;
+  p[0].C = sb.va[0]; p[0].Cpart = h.part + 3 * h.part_stride; p[0].bias = actor.l[0].bias; p[0].ksplit = ks[0];
+  p[1].a1_map = 0; p[1].a1_col = SK; p[1].a2_map = 0; p[1].w_map = 2; p[1].K1 = D;  p[1].K = D;  p[1].N = U; p[1].ldc = 3 * U;
+  p[1].C = sb.vin; p[1].Cpart = h.part; p[1].bias = h.in0.bias; p[1].ksplit = ks[1];
+  p[2].a1_map = 0; p[2].a1_col = 0;  p[2].a2_map = 0; p[2].w_map = 3; p[2].K1 = SK; p[2].K = SK; p[2].N = U; p[2].ldc = 3 * U;
+  p[2].C = sb.vin + U; p[2].Cpart = h.part + U; p[2].bias = h.in1.bias; p[2].ksplit = ks[2];
+  tb.count = 3; tb.R = N;
+  tb.ksplit = ks[0] > ks[1] ? ks[0] : ks[1];
+  if (ks[2] > tb.ksplit) tb.ksplit = ks[2];
+  tb.part_stride = (long long)h.part_stride;
+  launch_tc<64, 4>(cx, tb, (U + 63) / 64, N);
+}
+// Second launch: actor layers 1.. -> head -> action sample -> dyn_in2 (+ the dyn_in0 / dyn_in1 norms as a side job).
+static void imagine_actor_chain(Ctx& cx, int N, int H, int t, const StepBufs& sb, const int* ks, const float* act_noise,
+                                float* actions) {
+  if (cx.err) return;
+  sd_handle& h = *cx.h;
+  const sd_config& c = h.c;
+  const HeadW& actor = h.heads[SD_MOD_ACTOR];
+  const int U = c.U, A = c.A;
+  sd::chain::Params P;
+  memset(&P, 0, sizeof(P));
+  bool ok = true;
+  for (int i = 1; i < actor.layers; ++i) ok = ok && chain_add_layer(P, actor.l[i], 256);
+  ok = ok && chain_add_layer(P, actor.last, 64);
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "chain: tensor map / layer setup failed (actor)"); return; }
+  P.R = N; P.n_tiles = (N + 127) / 128;
+  P.in = sb.va[0]; P.ld_in = c.units; P.parts = h.part + 3 * h.part_stride; P.nparts = ks[0] - 1;
+  P.in_gain = actor.l[0].gain; P.part_stride = (long long)h.part_stride;
+  P.fin_mode = 2;
+  P.act_out = h.act_out; P.A = A; P.act_kind = c.act_kind; P.min_std = c.min_std; P.max_std = c.max_std; P.unimix = c.act_unimix;
+  P.noise = act_noise + (size_t)t * A; P.ld_n = H * A;
+  P.w2_t = h.in2.wt; P.ldw_2 = h.in2.ldw; P.b2 = h.in2.bias; P.g2 = h.in2.gain;
+  P.aout = nullptr; P.action = actions + (size_t)t * A; P.ld_act = H * A; P.abar = h.abar;
+  P.x2_bf = h.x_bf + 2 * U; P.ld_x2 = 3 * U;
+  P.side[0].in = sb.vin;     P.side[0].ld_in = 3 * U; P.side[0].parts = h.part;     P.side[0].nparts = ks[1] - 1;
+  P.side[0].gain = h.in0.gain; P.side[0].out_bf = h.x_bf;     P.side[0].ld_bf = 3 * U;
+  P.side[1].in = sb.vin + U; P.side[1].ld_in = 3 * U; P.side[1].parts = h.part + U; P.side[1].nparts = ks[2] - 1;
+  P.side[1].gain = h.in1.gain; P.side[1].out_bf = h.x_bf + U; P.side[1].ld_bf = 3 * U;
+  P.n_side = 2;
+  int side_ctas = (2 * N + 35) / 36;   // ~2 rows per warp
+  if (side_ctas > 140 - P.n_tiles) side_ctas = 140 - P.n_tiles;
+  if (side_ctas < 1) side_ctas = 1;
+  launch_chain(cx, P, side_ctas, "chain(actor)");
+}
+// img_net layers 1.. -> logits (fp32) on the pre-norm output of img_net layer 0 (+ split-K slices).
+static void imagine_img_chain(Ctx& cx, int N, const StepBufs& sb, int nparts, float* lg) {
+  if (cx.err) return;
+  sd_handle& h = *cx.h;
+  const sd_config& c = h.c;
+  sd::chain::Params P;
+  memset(&P, 0, sizeof(P));
+  bool ok = true;
+  for (int i = 1; i < c.img_layers; ++i) ok = ok && chain_add_layer(P, h.img[i], 256);
+  ok = ok && chain_add_layer(P, h.img_logit, 256);
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "chain: tensor map / layer setup failed (img)"); return; }
+  P.R = N; P.n_tiles = (N + 127) / 128;
+  P.in = sb.vobs[0]; P.ld_in = c.U; P.parts = h.part; P.nparts = nparts; P.in_gain = h.img[0].gain;
+  P.part_stride = (long long)h.part_stride;
+  P.fin_mode = 1; P.out = lg; P.ld_out = h.SK;
+  P.n_side = 0;
+  launch_chain(cx, P, 0, "chain(img)");
+}
+
 // ------------------------------------------------------------------------------------------------ config / layout
 static int validate(const sd_config& c) {
   if (c.D <= 0 || c.U <= 0 || c.S <= 0 || c.K <= 0 || c.G <= 0 || c.E <= 0 || c.A <= 0)
@@ -1082,10 +1223,11 @@ static StepBufs at_step(const StepBufs& s, size_t t, size_t rows, const sd_handl
 // Deter.forward (rssm.py:36-75).  z/d: stoch (R,SK) and deter (R,D) operands; abar: magnitude-normalised
 // action (R,A) fp32.  Writes the new deter (fp32, + bf16 copy on the tcgen05 path).
 static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d, const float* abar, float* deter_out,
-                       int ld_out, bf16* out_bf, int ld_bf, bool v2_done = false) {
+                       int ld_out, bf16* out_bf, int ld_bf, bool v2_done = false, bool x_done = false) {
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
   const int U = c.U, D = c.D, Dg = h.Dg;
+  if (!x_done) {   // x_done: the chain kernel already left x = [x0|x1|x2] (bf16) in h.x_bf
   LinCall in[3] = {
       {&h.in0, d, D, Operand(), sb.vin, 3 * U, 0},
       {&h.in1, z, h.SK, Operand(), sb.vin + U, 3 * U, 0},
@@ -1100,6 +1242,7 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
     if (j < 2) na[j] = with_parts(cx, na[j], h.part + j * U);
   }
   normact(cx, R, na, 3);
+  }
   Operand dg = d; dg.gstride = Dg;
   linear(cx, R, h.hid, dg, Dg, opfb(sb.x, 3 * U, cx.tc ? h.x_bf : nullptr, 3 * U), sb.hpre, D, Dg, h.part);
   sd::NormActP nh = with_parts(cx, nap(sb.hpre, D, h.hid.gain, D, sb.h, D, cx.tc ? h.h_bf : nullptr, D), h.part);
@@ -1426,10 +1569,70 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     copy_f32(cx, stoch0, SK, feats, ldf, N, SK);
     copy_f32(cx, deter0, D, feats + SK, ldf, N, D);
     if (cx.tc) cast_bf(cx, feats, ldf, h->feat_bf, F, N, F);
+    const bool use_chain = cx.tc && !tape && imagine_chain_ok(*h);
+    const size_t tsm = sd::actor_tail_smem(h->act_out, c.units, A, c.U);
+    const bool use_wide = cx.tc && !tape && wide_in_enabled() && fused_epi_enabled() && c.U == 256 && c.units == 256 &&
+                          actor.layers >= 1 && h->act_out <= sd::kTailMaxOut && A <= 32 && tsm <= 48 * 1024 &&
+                          (h->SK % 64) == 0 && (c.D % 64) == 0;
     for (int t = 0; t < H && !cx.err; ++t) {
       const StepBufs sb = at_step(base, t, N, *h);
       float* ft = feats + (size_t)t * F;
       Operand feat = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
+      if (use_wide && !use_chain) {
+        // 13 launches per step: the three wide feat layers in one split-K launch, their three norms in one launch,
+        // actor layers 1.. (norm fused), actor tail (+ dyn_in2 and its norm), then the block-GRU / img_net as below
+        int ks[3];
+        imagine_wide_in(cx, N, sb, ks);
+        sd::NormActP na[3];
+        na[0] = nap(sb.va[0], c.units, actor.l[0].gain, c.units, sb.ao[0], c.units, h->a_bf[0], c.units);
+        na[0].parts = h->part + 3 * h->part_stride; na[0].nparts = ks[0] - 1; na[0].part_stride = (long long)h->part_stride;
+        na[1] = nap(sb.vin, 3 * c.U, h->in0.gain, c.U, nullptr, 0, h->x_bf, 3 * c.U);
+        na[1].parts = h->part; na[1].nparts = ks[1] - 1; na[1].part_stride = (long long)h->part_stride;
+        na[2] = nap(sb.vin + c.U, 3 * c.U, h->in1.gain, c.U, nullptr, 0, h->x_bf + c.U, 3 * c.U);
+        na[2].parts = h->part + c.U; na[2].nparts = ks[2] - 1; na[2].part_stride = (long long)h->part_stride;
+        normact(cx, N, na, 3);
+        Operand cur = opfb(sb.ao[0], c.units, h->a_bf[0], c.units);
+        for (int i = 1; i < actor.layers && !cx.err; ++i) {
+          if (!linear_norm_tc(cx, N, actor.l[i], cur, sb, sb.ao[i], c.units, h->a_bf[i], c.units)) {
+            cx.err = fail(SD_ERR_INVALID, "imagine: fused actor layer %d not eligible", i);
+            return;
+          }
+          cur = opfb(sb.ao[i], c.units, h->a_bf[i], c.units);
+        }
+        if (cx.err) return;
+        const size_t tail_smem2 = sd::actor_tail_smem(h->act_out, c.units, A, c.U);
+        launch_k(cx.st, sd::actor_tail_kernel, dim3((N * 32 + 255) / 256), dim3(256), tail_smem2,
+                 (const float*)sb.ao[actor.layers - 1], c.units, c.units, (const float*)actor.last.wn, actor.last.ldk,
+                 (const float*)actor.last.bias, h->act_out, A, c.act_kind, c.min_std, c.max_std, c.act_unimix,
+                 act_noise + (size_t)t * A, H * A, (const float*)h->in2.wt, h->in2.ldw, (const float*)h->in2.bias, c.U, N,
+                 (float*)nullptr, actions + (size_t)t * A, H * A, h->abar, (float*)nullptr, 0, (const float*)h->in2.gain,
+                 h->x_bf + 2 * c.U, 3 * c.U);
+        cx.check("actor_tail_kernel(+x2)");
+        if (t == H - 1) break;
+        float* dnext = ft + F + SK;
+        deter_core(cx, sb, N, opfb(ft, ldf, h->feat_bf, F), opfb(ft + SK, ldf, h->feat_bf + SK, F), h->abar, dnext, ldf,
+                   h->feat_bf + SK, F, true, true);
+        SampleOut so{u + (size_t)t * SK, H * SK, ft + F, ldf, nullptr, 0};
+        if (!latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit, opfb(dnext, ldf, h->feat_bf + SK, F), D, Operand(),
+                           sb.lg, &so))
+          sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, h->feat_bf, F, nullptr, 0);
+        continue;
+      }
+      if (use_chain) {
+        // 8 launches per step: wide feat layers | actor chain (+ input norms) | block-GRU hidden | its norm |
+        // gate projection + gates | img_net layer 0 | img chain -> logits | sample
+        int ks[3];
+        imagine_wide_in(cx, N, sb, ks);
+        imagine_actor_chain(cx, N, H, t, sb, ks, act_noise, actions);
+        if (t == H - 1) break;
+        float* dnext = ft + F + SK;
+        deter_core(cx, sb, N, opfb(ft, ldf, h->feat_bf, F), opfb(ft + SK, ldf, h->feat_bf + SK, F), h->abar, dnext, ldf,
+                   h->feat_bf + SK, F, true, true);
+        linear(cx, N, h->img[0], opfb(dnext, ldf, h->feat_bf + SK, F), D, Operand(), sb.vobs[0], c.U, 0, h->part);
+        imagine_img_chain(cx, N, sb, cx.last_ksplit - 1, sb.lg);
+        sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, h->feat_bf, F, nullptr, 0);
+        continue;
+      }
       // action = actor(feat).rsample() (dreamer.py:684)
       const size_t tail_smem = sd::actor_tail_smem(h->act_out, c.units, A, c.U);
       const bool fused_tail = h->act_out <= sd::kTailMaxOut && A <= 32 && c.units <= 256 && tail_smem <= 48 * 1024;
@@ -1455,7 +1658,8 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
                  (const float*)sb.ao[actor.layers - 1], c.units, c.units, (const float*)actor.last.wn, actor.last.ldk,
                  (const float*)actor.last.bias, h->act_out, A, c.act_kind, c.min_std, c.max_std, c.act_unimix,
                  act_noise + (size_t)t * A, H * A, (const float*)h->in2.wt, h->in2.ldw, (const float*)h->in2.bias, c.U, N,
-                 sb.aout, actions + (size_t)t * A, H * A, h->abar, sb.vin + 2 * c.U, 3 * c.U);
+                 sb.aout, actions + (size_t)t * A, H * A, h->abar, sb.vin + 2 * c.U, 3 * c.U, (const float*)nullptr,
+                 (bf16*)nullptr, 0);
         cx.check("actor_tail_kernel");
       } else {
         head_forward(cx, N, actor, feat, F, sb.va, sb.ao, h->a_bf, sb.aout, h->act_out);

@@ -744,7 +744,9 @@ __global__ void __launch_bounds__(256) actor_tail_kernel(const float* __restrict
                                                          const float* __restrict__ noise, int ld_n,
                                                          const float* __restrict__ w2_t, int ldw_2,
                                                          const float* __restrict__ b2, int U, int R, float* aout,
-                                                         float* action, int ld_act, float* abar, float* v2, int ld_v2) {
+                                                         float* action, int ld_act, float* abar, float* v2, int ld_v2,
+                                                         const float* __restrict__ g2 = nullptr,
+                                                         __nv_bfloat16* x2_bf = nullptr, int ld_x2 = 0) {
   extern __shared__ __align__(16) float tsm[];
   float* wl_s = tsm;                          // [act_out][units]
   float* bl_s = wl_s + act_out * units;       // [act_out]
@@ -818,6 +820,31 @@ __global__ void __launch_bounds__(256) actor_tail_kernel(const float* __restrict
     abar[(size_t)row * A + lane] = ab;
   }
   // v2[n] = sum_a W2t[a][n] * abar[a] + b2[n]
+  if (x2_bf != nullptr && U <= 256) {
+    // x2 = SiLU(RMSNorm(v2) * g2) (rssm.py:48) finished here: the row is already in this warp's registers
+    float vv[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = lane + 32 * i;
+      float v = 0.f;
+      if (n < U) {
+        for (int a = 0; a < A; ++a) v = fmaf(__shfl_sync(0xffffffffu, ab, a), w2_s[a * U + n], v);
+        v += b2_s[n];
+        if (v2) v2[(size_t)row * ld_v2 + n] = v;
+      }
+      vv[i] = v;
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float rs = 1.f / sqrtf(ss / (float)U + kRmsEps);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = lane + 32 * i;
+      if (n < U) x2_bf[(size_t)row * ld_x2 + n] = __float2bfloat16(siluf_((vv[i] * rs) * __ldg(g2 + n)));
+    }
+    return;
+  }
   for (int n = lane; n < U; n += 32) {
     float v = 0.f;
     for (int a = 0; a < A; ++a) v = fmaf(__shfl_sync(0xffffffffu, ab, a), w2_s[a * U + n], v);

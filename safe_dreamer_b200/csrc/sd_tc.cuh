@@ -47,6 +47,7 @@ struct Problem {
   __nv_bfloat16* e_out_bf; int e_ld_bf;   // deter' bf16 (next tcgen05 operand), nullable
   int e_dg;                               // units per block (weight rows of one gate)
   const float* e_gain;                    // EPI_NORM: RMS scale
+  int ksplit;                             // per-problem split-K factor (0 = the batch's); CTAs of slices >= it exit
 };
 // EPI_NORM (BN = 64, N = 256, cluster of 4 CTAs along N): RMSNorm(1e-4)*gain -> SiLU fused in the epilogue.  The
 // four CTAs of a cluster own the four 64-column tiles of the same 128 rows; per-row partial sums of squares are
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
   const int prob = blockIdx.z % batch.count, slice = blockIdx.z / batch.count;
   const Problem pr = batch.p[prob];  // by value: keeps the fields in registers instead of re-reading the param bank
   const int n0 = blockIdx.x * (EPI == EPI_GATES ? 64 : BN);   // gates: first of this tile's 64 units
-  if (n0 >= pr.N) return;  // whole CTA exits before any barrier/TMEM use
+  const int ks = pr.ksplit > 0 ? pr.ksplit : batch.ksplit;
+  if (n0 >= pr.N || slice >= ks) return;  // whole CTA exits before any barrier/TMEM use
   const int m0 = blockIdx.y * BM;
 
   extern __shared__ uint8_t smem_raw[];
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) SD_TC_STAMP(0);
   const int num_kb_all = pr.K / BK;
-  const int kb_per = (num_kb_all + batch.ksplit - 1) / batch.ksplit;
+  const int kb_per = (num_kb_all + ks - 1) / ks;
   const int kb0 = slice * kb_per;
   const int kb1 = min(num_kb_all, kb0 + kb_per);
   const int num_kb = kb1 > kb0 ? kb1 - kb0 : 0;   // an empty slice just stores zeros

@@ -86,3 +86,50 @@ def test_imagine_tc_first_step_and_shape(base):
     np.testing.assert_allclose(_np(cont), cont_o, atol=0.02)
     np.testing.assert_allclose(_np(rew), rew_o, rtol=0.1, atol=0.05)
     np.testing.assert_allclose(_np(val), val_o, rtol=0.1, atol=0.05)
+
+
+def test_imagine_tc_step1_indices(base):
+    """Step-1 stoch of the tcgen05 rollout (img chain: img_net -> logits -> sample) against the oracle's
+    img_step fed with the oracle's own step-0 action: every index mismatch must be a near tie."""
+    c, P, eng = base
+    N, H = 384, 2
+    st0, dt0, u, noise = O.synth_imagine_inputs(c, N, H, seed=27)
+    feat0 = O.get_feat(st0, dt0)
+    act_o = O.actor_sample(c, P["actor"], feat0, noise[:, 0])
+    st_o, dt_o, lg_o, idx_o = O.img_step(c, P["rssm"], st0, dt0, act_o, u[:, 0])
+    feats, acts = eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=BF16)
+    torch.cuda.synchronize()
+    feats, acts = _np(feats), _np(acts)
+    assert np.abs(acts[:, 0] - act_o).max() <= 0.03
+    assert np.abs(feats[:, 1, c.SK:] - dt_o).max() <= 0.04
+    idx = feats[:, 1, :c.SK].reshape(N, c.S, c.K).argmax(-1)
+    assert_indices(idx, idx_o, perturbed_scores(lg_o, u[:, 0], c.unimix), 0.25, 0.04, "imagine tc step 1")
+    # ragged row count (not a multiple of the 128-row tile) must give the same rows
+    M = 200
+    feats2, acts2 = eng.imagine(cu(st0[:M]), cu(dt0[:M]), cu(u[:M]), cu(noise[:M]), H, flags=BF16)
+    torch.cuda.synchronize()
+    # step 0 does not depend on the row count at all; later steps may differ in the last bf16 bit because the
+    # split-K factor of the wide layers (hence the fp32 summation order) is chosen from the CTA count
+    np.testing.assert_array_equal(_np(acts2)[:, 0], acts[:M, 0])
+    np.testing.assert_array_equal(_np(feats2)[:, 0], feats[:M, 0])
+    assert np.abs(_np(feats2)[:, 1, c.SK:] - feats[:M, 1, c.SK:]).max() <= 0.02
+    assert np.abs(_np(acts2)[:, 1] - acts[:M, 1]).max() <= 0.03
+
+
+def test_imagine_tc_onehot_actor():
+    """Atari-like 18-way one-hot actor on the tcgen05 path: actions are exact one-hots and agree with the
+    oracle except at near ties of the actor's perturbed logits."""
+    c, z = load_golden("base_onehot18")
+    P = golden_params(c, z)
+    eng = make_engine(c, P, max_rows=256, max_steps=2)
+    N, H = 256, 2
+    st0, dt0, u, noise = O.synth_imagine_inputs(c, N, H, seed=29)
+    feat0 = O.get_feat(st0, dt0)
+    out_o = O.head_logits(P["actor"], "actor", c.actor_layers, feat0)
+    act_o = O.actor_sample(c, P["actor"], feat0, noise[:, 0])
+    feats, acts = eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=BF16)
+    torch.cuda.synchronize()
+    acts = _np(acts)
+    assert np.all(acts.sum(-1) == 1.0) and np.all((acts == 0) | (acts == 1))
+    assert_indices(acts[:, 0].argmax(-1)[:, None], act_o.argmax(-1)[:, None],
+                   perturbed_scores(out_o[:, None, :], noise[:, 0][:, None, :], c.act_unimix), 0.25, 0.04, "onehot actor tc")
