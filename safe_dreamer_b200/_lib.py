@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libsafedreamer.so")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "safedreamer.h")
-_SOURCES = ["sd_api.cu", "sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh"]
+_SOURCES = ["sd_api.cu", "sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

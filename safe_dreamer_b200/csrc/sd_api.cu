@@ -22,6 +22,7 @@
 #include "sd_bwd.cuh"
 #include "sd_tc.cuh"
 #include "sd_chain.cuh"
+#include "sd_scan.cuh"
 
 using bf16 = __nv_bfloat16;
 
@@ -143,6 +144,10 @@ struct sd_handle {
   size_t wg_scratch_elems = 0;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
   bf16* trunk_bf = nullptr;
+  // persistent posterior scan (sd_scan.cuh): input-only precomputations and cross-CTA exchange
+  float *ps_x2 = nullptr, *ps_eproj = nullptr, *ps_ssq = nullptr;
+  int* ps_idx = nullptr;
+  unsigned int* ps_bar = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------ TMA maps
@@ -855,6 +860,11 @@ static void layout(sd_handle& h, Arena& a) {
     h.part_stride = R * w;
     h.part = a.take<float>(h.part_stride * 7);
   }
+  h.ps_x2 = a.take<float>((size_t)16 * T * c.U);
+  h.ps_eproj = a.take<float>((size_t)16 * T * c.U);
+  h.ps_ssq = a.take<float>((size_t)sd::scan::NCTA * 16);
+  h.ps_idx = a.take<int>((size_t)16 * c.S);
+  h.ps_bar = a.take<unsigned int>(64);
   h.scratch_stoch = a.take<float>(R * SK);
   h.scratch_deter = a.take<float>(R * c.D);
   h.abar = a.take<float>(R * c.A);
@@ -1391,6 +1401,95 @@ static int check_rows(sd_handle* h, const char* fn, long long rows, long long st
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent posterior scan
+static bool pscan_enabled() { static int v = env_flag("SD_PSCAN", 1); return v != 0; }
+// The persistent kernel covers the base architecture at small batch (rssm.py:140-178 with base.yaml sizes).
+static bool pscan_ok(const sd_handle& h, int B, int T) {
+  const sd_config& c = h.c;
+  return pscan_enabled() && B >= 1 && B <= 16 && T >= 1 && c.U == sd::scan::HW && h.Dg == sd::scan::HW && c.G == 8 &&
+         c.D == 4 * sd::scan::KC && (h.SK % 16) == 0 && h.SK <= 512 && (16 % c.K) == 0 && c.K >= 2 && c.obs_layers == 1 &&
+         c.A <= 32 && (c.E % 4) == 0 && T <= c.max_steps;
+}
+static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const float* action, const float* init_stoch,
+                               const float* init_deter, const uint8_t* is_first, const float* u, float* stochs,
+                               float* deters, float* logits, bool tape) {
+  sd_handle& h = *cx.h;
+  const sd_config& c = h.c;
+  const int SK = h.SK, D = c.D, E = c.E, A = c.A, U = c.U;
+  StepBufs base = tape ? h.tape : h.sb;
+  // step 0: masked initial state and its two input projections (the layer-by-layer kernels; init_stoch need not be one-hot)
+  launch_k(cx.st, sd::prep_obs_kernel, dim3(grid1d((long long)B * (SK + D + A), 256)), dim3(256), 0, init_stoch, SK, init_deter, D,
+           action, T * A, is_first, T, B, SK, D, A, base.zin, base.din, base.ain, base.keep, (float*)nullptr);
+  cx.check("prep_obs_kernel");
+  LinCall in[2] = {{&h.in0, opf(base.din, D), D, Operand(), base.vin, 3 * U, 0},
+                   {&h.in1, opf(base.zin, SK), SK, Operand(), base.vin + U, 3 * U, 0}};
+  linear_multi(cx, B, in, 2);
+  if (cx.err) return;
+  // all steps: action branch (keep mask, normalised action, dyn_in2 + norm)
+  launch_k(cx.st, sd::scan::obs_prep_kernel, dim3((B * T * 32 + 255) / 256), dim3(256), 0, action, is_first, B, T, A, U,
+           (const float*)h.in2.wt, h.in2.ldw, (const float*)h.in2.bias, (const float*)h.in2.gain, h.ps_x2,
+           tape ? base.ain : (float*)nullptr, tape ? base.keep : (float*)nullptr, tape ? base.vin : (float*)nullptr,
+           tape ? base.x : (float*)nullptr);
+  cx.check("obs_prep_kernel");
+  // all steps: embed part of obs_net_0 (rows (b, t)), no bias
+  {
+    sd::GemmBatch gb;
+    memset(&gb, 0, sizeof(gb));
+    gb.R = B * T;
+    sd::GemmP& p = gb.p[gb.count++];
+    p.A = embed; p.lda = E; p.A2 = nullptr; p.lda2 = 0; p.K1 = E; p.K = E;
+    p.Wt = h.obs[0].wt + (size_t)D * h.obs[0].ldw; p.ldw = h.obs[0].ldw; p.bias = nullptr;
+    p.C = h.ps_eproj; p.ldc = U; p.N = U;
+    launch_gemm_f32(cx.st, gb, U, E, B * T);
+    cx.check("gemm_f32_kernel(embed proj)");
+  }
+  if (cx.err) return;
+  cudaMemsetAsync(h.ps_bar, 0, 64 * sizeof(unsigned int), cx.st);
+  sd::scan::Params P;
+  memset(&P, 0, sizeof(P));
+  P.B = B; P.T = T; P.D = D; P.SK = SK; P.S = c.S; P.K = c.K; P.G = c.G; P.E = E; P.A = A; P.unimix = c.unimix;
+  P.w_in0 = h.in0.wt; P.b_in0 = h.in0.bias; P.g_in0 = h.in0.gain; P.ld_in0 = h.in0.ldw;
+  P.w_in1 = h.in1.wt; P.b_in1 = h.in1.bias; P.g_in1 = h.in1.gain; P.ld_in1 = h.in1.ldw;
+  P.w_hid = h.hid.wt; P.b_hid = h.hid.bias; P.g_hid = h.hid.gain; P.ld_hid = h.hid.ldw;
+  P.w_gru = h.gru.wt; P.b_gru = h.gru.bias; P.ld_gru = h.gru.ldw;
+  P.w_obs = h.obs[0].wt; P.b_obs = h.obs[0].bias; P.g_obs = h.obs[0].gain; P.ld_obs = h.obs[0].ldw;
+  P.w_lg = h.obs_logit.wt; P.b_lg = h.obs_logit.bias; P.ld_lg = h.obs_logit.ldw;
+  P.init_stoch = init_stoch; P.init_deter = init_deter; P.is_first = is_first; P.u = u;
+  P.eproj = h.ps_eproj; P.x2 = h.ps_x2;
+  P.stochs = stochs; P.deters = deters; P.logits = logits;
+  P.zin = base.zin; P.din = base.din; P.vin = base.vin; P.x = base.x; P.hpre = base.hpre; P.h = base.h; P.q = base.q;
+  P.lg = base.lg; P.vobs = base.vobs[0]; P.o = base.o[0];
+  P.step = tape ? 1 : 0;
+  P.ssq_h = h.ps_ssq; P.idx = h.ps_idx; P.bar = h.ps_bar;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(sd::scan::observe_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::scan::kSmemBytes);
+    attr_done = true;
+  }
+  // no PDL attribute: all 128 CTAs must become resident together (they spin on a grid barrier)
+  static long long* timing_dev = nullptr;
+  if (cx.trace && getenv("SD_TRACE_SCAN")) {
+    if (!timing_dev) cudaMalloc(&timing_dev, 32 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 32 * sizeof(long long), cx.st);
+    P.timing = timing_dev;
+  }
+  sd::scan::observe_scan_kernel<<<sd::scan::NCTA, sd::scan::THREADS, sd::scan::kSmemBytes, cx.st>>>(P);
+  cx.check("observe_scan_kernel");
+  if (P.timing) {
+    cudaStreamSynchronize(cx.st);
+    long long tt[32];
+    cudaMemcpy(tt, timing_dev, sizeof(tt), cudaMemcpyDeviceToHost);
+    for (int c0 = 0; c0 < 32; c0 += 16)
+      fprintf(stderr, "[SD_TRACE_SCAN] cta %d step 2 cycles: P1=%lld bar=%lld | P2=%lld bar=%lld | P3=%lld bar=%lld | P4=%lld bar=%lld | "
+                      "P5=%lld bar=%lld | step=%lld\n", c0 ? 40 : 0, tt[c0 + 1] - tt[c0 + 0], tt[c0 + 2] - tt[c0 + 1], tt[c0 + 3] - tt[c0 + 2],
+              tt[c0 + 4] - tt[c0 + 3], tt[c0 + 5] - tt[c0 + 4], tt[c0 + 6] - tt[c0 + 5], tt[c0 + 7] - tt[c0 + 6], tt[c0 + 8] - tt[c0 + 7],
+              tt[c0 + 9] - tt[c0 + 8], tt[c0 + 10] - tt[c0 + 9], tt[c0 + 10] - tt[c0 + 0]);
+    fprintf(stderr, "[SD_TRACE_SCAN] cta 0 P3 detail: loads+stage=%lld product=%lld dsmem+cluster=%lld tail=%lld\n", tt[11] - tt[4],
+            tt[12] - tt[11], tt[13] - tt[12], tt[5] - tt[13]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ observe
 extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, const float* action,
                               const float* init_stoch, const float* init_deter, const uint8_t* is_first,
@@ -1413,7 +1512,9 @@ extern "C" int sd_observe_fwd(sd_handle* h, int B, int T, const float* embed, co
     StepBufs base = tape ? h->tape : h->sb;
     base.stride = tape ? 1 : 0;
     if (cx.tc) cast_bf(cx, embed, E, h->emb_bf, E, B * T, E);
-    for (int t = 0; t < T && !cx.err; ++t) {
+    const bool persistent = !cx.tc && pscan_ok(*h, B, T);
+    if (persistent) observe_persistent(cx, B, T, embed, action, init_stoch, init_deter, is_first, u, stochs, deters, logits, tape);
+    for (int t = 0; t < T && !cx.err && !persistent; ++t) {
       StepBufs sb = at_step(base, t, B, *h);
       const float* ps = t == 0 ? init_stoch : stochs + (size_t)(t - 1) * SK;
       const float* pd = t == 0 ? init_deter : deters + (size_t)(t - 1) * D;
