@@ -212,6 +212,40 @@ __device__ __forceinline__ void normact16(const float4 (&v)[4], float rs, const 
   for (int i = 0; i < 4; ++i) y[i] = normact4(v[i], rs, *reinterpret_cast<const float4*>(g_s + i * 64 + seg * 4));
 }
 
+// First half of the block-GRU hidden layer of step tt: s_a = W_hid[g][:, 0:512] . [keep * d_g | x0], x0 = SiLU(RMSNorm(v_in0)).
+// Neither operand depends on the sample of the previous step (v_in0 is produced two phases earlier, in P3), so this
+// runs in the otherwise idle P4 / P5 slot and only its 16x16 partial tile (one float per thread) is carried into P1.
+__device__ __noinline__ float hid_first_half(const float* dsrc, float keep, const float* v0src, bool rok, float* A_s,
+                                             const float* W1, float* red, const float* G_s, int row, int seg, float* din_t,
+                                             float* x_t) {
+  float4 dv[4], v0[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = i * 64 + seg * 4;
+    dv[i] = rok ? ldcg4(dsrc + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v0[i] = rok ? ldcg4(v0src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float ss0 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ss0 += sq4(v0[i]);
+  ss0 = sum16(ss0);
+  const float rs0 = 1.f / sqrtf(ss0 / (float)HW + kRmsEps);
+  float4 x0[4];
+  normact16(v0, rs0, G_s, seg, x0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    dv[i].x *= keep; dv[i].y *= keep; dv[i].z *= keep; dv[i].w *= keep;
+    *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = dv[i];
+    *reinterpret_cast<float4*>(A_s + row * ALD + HW + i * 64 + seg * 4) = x0[i];
+    if (din_t) *reinterpret_cast<float4*>(din_t + i * 64 + seg * 4) = dv[i];   // backward tape: masked deter input
+    if (x_t) *reinterpret_cast<float4*>(x_t + i * 64 + seg * 4) = x0[i];       // backward tape: x0
+  }
+  __syncthreads();
+  float s;
+  tile_product<1>(A_s, W1, 0, KC / 4, red, &s);
+  return s;
+}
+
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) observe_scan_kernel(const Params P) {
   extern __shared__ __align__(16) float sm[];
   float* W1 = sm + kW1;
@@ -255,6 +289,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   const float bias_5 = do5 ? __ldg(P.b_in1 + j5 * 16 + col) : 0.f;
   unsigned int epoch = 0;
   __syncthreads();
+  // first half of step 0's hidden layer (v_in0 of step 0 comes from the host-side launches)
+  float s_a = hid_first_half(P.init_deter + (size_t)row * D + g * HW, (rok && P.is_first[(size_t)row * T]) ? 0.f : 1.f,
+                             P.vin + (size_t)row * (3 * HW), rok, A_s, W1, red, G_s, row, seg,
+                             (P.step && rok && jt == 0) ? P.din + (size_t)row * D + g * HW : nullptr,
+                             (P.step && rok && cta == 0) ? P.x + (size_t)row * (3 * HW) : nullptr);
 
   for (int t = 0; t < T; ++t) {
     const float keep_t = (rok && P.is_first[(size_t)row * T + t]) ? 0.f : 1.f;
@@ -269,62 +308,39 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     SD_SC_STAMP(0);
     // ================================================================ P1: hidden layer of the block GRU
     {
-      float4 dv[4], v0[4], v1[4], xv2[4];
-      const float* dsrc = t == 0 ? P.init_deter + (size_t)row * D : P.deters + ((size_t)row * T + (t - 1)) * D;
+      float4 v1[4], xv2[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int k = i * 64 + seg * 4;
-        dv[i] = rok ? ldcg4(dsrc + g * HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v0[i] = rok ? ldcg4(vin_t + (size_t)row * (3 * HW) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         v1[i] = rok ? ldcg4(vin_t + (size_t)row * (3 * HW) + HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         xv2[i] = rok ? __ldg(reinterpret_cast<const float4*>(P.x2 + ((size_t)t * B + row) * HW + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float ss0 = 0.f, ss1 = 0.f;
+      float ss1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { ss0 += sq4(v0[i]); ss1 += sq4(v1[i]); }
-      ss0 = sum16(ss0); ss1 = sum16(ss1);
-      const float rs0 = 1.f / sqrtf(ss0 / (float)HW + kRmsEps), rs1 = 1.f / sqrtf(ss1 / (float)HW + kRmsEps);
-      float4 x0[4], x1[4];
-      normact16(v0, rs0, G_s, seg, x0);
+      for (int i = 0; i < 4; ++i) ss1 += sq4(v1[i]);
+      ss1 = sum16(ss1);
+      const float rs1 = 1.f / sqrtf(ss1 / (float)HW + kRmsEps);
+      float4 x1[4];
       normact16(v1, rs1, G_s + 256, seg, x1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        dv[i].x *= keep_t; dv[i].y *= keep_t; dv[i].z *= keep_t; dv[i].w *= keep_t;
-        *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = dv[i];
-        *reinterpret_cast<float4*>(A_s + row * ALD + HW + i * 64 + seg * 4) = x0[i];
-      }
-      if (P.step && rok) {   // backward tape: masked deter input and x = [x0 | x1 | (x2 by obs_prep_kernel)]
-        if (jt == 0) {
-          float* dt = P.din + ((size_t)t * sstep + row) * D + g * HW + seg * 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(dt + i * 64) = dv[i];
-        }
-        if (cta == 0) {
-          float* xt = P.x + ((size_t)t * sstep + row) * (3 * HW) + seg * 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            *reinterpret_cast<float4*>(xt + i * 64) = x0[i];
-            *reinterpret_cast<float4*>(xt + HW + i * 64) = x1[i];
-          }
-        }
-      }
-      __syncthreads();
-      float s, s2;
-      tile_product<1>(A_s, W1, 0, KC / 4, red, &s);
-      __syncthreads();
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = x1[i];
         *reinterpret_cast<float4*>(A_s + row * ALD + HW + i * 64 + seg * 4) = xv2[i];
       }
+      if (P.step && rok && cta == 0) {   // backward tape: x1 (x0 by hid_first_half, x2 by obs_prep_kernel)
+        float* xt = P.x + ((size_t)t * sstep + row) * (3 * HW) + HW + seg * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(xt + i * 64) = x1[i];
+      }
       __syncthreads();
+      float s2;
       tile_product<1>(A_s, W1 + (KC / 4) * 64, 0, KC / 4, red, &s2);
-      s += s2;
+      const float s = s_a + s2;
       const int n = g * HW + jt * 16 + col;
       const float hp = s + bias_h;
       if (rok) hpre_t[(size_t)row * D + n] = hp;
       const float ssr = sum16(hp * hp);
-      if (col == 0) P.ssq_h[cta * 16 + row] = ssr;
+      if (col == 0) P.ssq_h[row * NCTA + cta] = ssr;
     }
     SD_SC_STAMP(1);
     grid_sync(P.bar, epoch);
@@ -338,7 +354,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
         hv[i] = rok ? ldcg4(hpre_t + (size_t)row * D + g * HW + i * 64 + seg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       float tot = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) tot += ldcg(P.ssq_h + (seg * 8 + i) * 16 + row);   // 128 tile partials per row
+      for (int i = 0; i < 8; ++i) tot += ldcg(P.ssq_h + row * NCTA + seg * 8 + i);   // 128 tile partials per row
       tot = sum16(tot);
       const float rs = 1.f / sqrtf(tot / (float)D + kRmsEps);
       float4 hh[4];
@@ -410,7 +426,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     grid_sync(P.bar, epoch);
     SD_SC_STAMP(6);
 
-    // ================================================================ P4: logits + sample
+    // ================================================================ P4: logits + sample (other CTAs: first half of the next hidden layer)
+    if (!do4 && t + 1 < T) s_a = hid_first_half(P.deters + ((size_t)row * T + t) * D + g * HW, keep_n, P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW),
+                           rok, A_s, W1, red, G_s, row, seg,
+                           (P.step && rok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + row) * D + g * HW : nullptr,
+                           (P.step && rok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + row) * (3 * HW) : nullptr);
     if (do4) {
       float4 vv[4];
 #pragma unroll
@@ -458,6 +478,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     SD_SC_STAMP(8);
 
     // ================================================================ P5: next step's dyn_in1 (gather-sum of one-hot rows)
+    if (do4 && t + 1 < T) s_a = hid_first_half(P.deters + ((size_t)row * T + t) * D + g * HW, keep_n, P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW),
+                           rok, A_s, W1, red, G_s, row, seg,
+                           (P.step && rok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + row) * D + g * HW : nullptr,
+                           (P.step && rok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + row) * (3 * HW) : nullptr);
     if (do5 && t + 1 < T) {
       float v = 0.f;
       if (rok) {
