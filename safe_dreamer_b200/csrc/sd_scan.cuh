@@ -25,7 +25,7 @@
 namespace sd {
 namespace scan {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;          // 16 warps: four per scheduler (every phase is latency bound)
 constexpr int NCTA = 128;
 constexpr int CLUSTER = 4;
 constexpr int HW = 256;            // U == Dg == 256 (checked on the host)
@@ -36,9 +36,8 @@ constexpr int kW1 = 0;                         // P1: [1024][16]
 constexpr int kW2 = kW1 + 1024 * 16;           // P2: 3 x [256][16]
 constexpr int kW3 = kW2 + 3 * 256 * 16;        // P3: [512][16]
 constexpr int kW45 = kW3 + 512 * 16;           // P4: [256][16] (CTAs < SK/16) | P5: [SK][16] (CTAs 32..47)
-constexpr int kAs = kW45 + 512 * 16;           // [16][ALD]
-constexpr int kRed = kAs + 16 * ALD;           // [8 warps][256]
-constexpr int kSlots = kRed + 8 * 256;         // [4 ranks][256] (cluster leader)
+constexpr int kAs = kW45 + 512 * 16;           // [16][ALD]; after the FMA loop of a tile it is the [16 warps][256] reduction buffer
+constexpr int kSlots = kAs + 16 * ALD;         // [4 ranks][256] (cluster leader)
 constexpr int kGain = kSlots + CLUSTER * 256;  // RMS scales: g_in0 | g_in1 | g_hid[block] | g_obs (4 x 256)
 constexpr int kSmemFloats = kGain + 4 * 256;
 constexpr int kSmemBytes = kSmemFloats * 4;
@@ -110,87 +109,82 @@ __device__ __forceinline__ void stage_w(float* dst, const float* w, int ld, int 
 }
 
 // NG 16x16 output tiles that share the A operand: s_g(row, col) = sum_k A_s[row][k] * W_g[k][col], W_g = W + g*wstride,
-// over the nkq staged k-quads.  Thread (kg = tid >> 4, ty = (tid >> 2) & 3, tx = tid & 3) owns rows 4ty..4ty+3 x
-// columns 4tx..4tx+3 for the k-quads kg, kg + 16, ...; the operands of the next k-quad are fetched from shared memory
-// while the current one is multiplied (two warps per scheduler cannot hide the LDS latency otherwise).  The 16
-// k-group partials are summed by ONE shuffle (the two k-groups of a warp), then the 8 warps in order through shared
-// memory (fixed order => deterministic).  out[g] = element (row = tid >> 4, col = tid & 15) of tile g.
-// Deliberately not inlined: the persistent kernel runs every phase once per step, its code has to stay small.
+// over the nkq staged k-quads (nkq*4 = K elements, a multiple of 128).
+// The 16 batch rows are exactly the M of mma.sync.m16n8k8, so the contraction runs on the tensor pipe with the
+// 3xTF32 split (x = hi + lo, hi = tf32(x), lo = tf32(x - hi); hi*hi + hi*lo + lo*hi in fp32 accumulators): the dropped
+// lo*lo term is 2^-22 relative, i.e. fp32-class accuracy -- the SIMT version of this tile was shared-memory bandwidth
+// bound (2048 LDS wavefronts per K=512, 3.3k cycles; this one needs ~1/8 of the shared-memory traffic).
+// Warp w owns the k-range [w*K/16, (w+1)*K/16); the 16 per-warp partial tiles are summed in warp order through shared
+// memory (fixed order => deterministic).  The reduction buffer ALIASES the A tile (every thread is past its last A
+// read at the first barrier); callers must barrier before they overwrite A_s again.
+// out[g] = element (row = tid >> 4, col = tid & 15) of tile g, valid for tid < 256.  Deliberately not inlined.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 template <int NG>
-__device__ __noinline__ void tile_product(const float* A_s, const float* W, int wstride, int nkq, float* red, float* out) {
-  const int tx = threadIdx.x & 3, ty = (threadIdx.x >> 2) & 3, kg = threadIdx.x >> 4;
-  float acc[NG][4][4];
+__device__ __noinline__ void tile_product(float* A_s, const float* W, int wstride, int nkq, float* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, tq = lane & 3;   // mma fragment coordinates: groupID, threadID_in_group
+  float acc[NG][2][4];
 #pragma unroll
   for (int g = 0; g < NG; ++g)
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[g][r][c] = 0.f;
-  const float* ap = A_s + (ty * 4) * ALD;
-  float4 xa[4], wa[NG][4];
-  {
-    const int kq = kg < nkq ? kg : 0;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) xa[r] = *reinterpret_cast<const float4*>(ap + r * ALD + kq * 4);
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wa[g][j] = *reinterpret_cast<const float4*>(W + g * wstride + kq * 64 + j * 16 + tx * 4);
-  }
+      for (int c = 0; c < 4; ++c) acc[g][nt][c] = 0.f;
+  const int ksteps = nkq / (2 * (THREADS / 32));   // k-steps of 8 per warp
 #pragma unroll 1
-  for (int kq = kg; kq < nkq; kq += 16) {
-    float4 x[4], w[NG][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) x[r] = xa[r];
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) w[g][j] = wa[g][j];
-    const int kn = kq + 16 < nkq ? kq + 16 : kq;   // prefetch (re-reads the last one harmlessly)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) xa[r] = *reinterpret_cast<const float4*>(ap + r * ALD + kn * 4);
-#pragma unroll
-    for (int g = 0; g < NG; ++g)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wa[g][j] = *reinterpret_cast<const float4*>(W + g * wstride + kn * 64 + j * 16 + tx * 4);
+  for (int s = 0; s < ksteps; ++s) {
+    const int k0 = (warp * ksteps + s) * 8;
+    // A fragment: a0 (gq, tq), a1 (gq+8, tq), a2 (gq, tq+4), a3 (gq+8, tq+4)
+    uint32_t ah[4], al[4];
+    split_tf32(A_s[gq * ALD + k0 + tq], ah[0], al[0]);
+    split_tf32(A_s[(gq + 8) * ALD + k0 + tq], ah[1], al[1]);
+    split_tf32(A_s[gq * ALD + k0 + tq + 4], ah[2], al[2]);
+    split_tf32(A_s[(gq + 8) * ALD + k0 + tq + 4], ah[3], al[3]);
+    // B fragment of n-tile nt: b0 (k = tq, n = gq), b1 (k = tq + 4, n = gq); W is [k/4][k%4][16]
+    const float* w0 = W + ((k0 >> 2) * 64) + tq * 16 + gq;   // k0 + tq      -> k-quad k0/4, j = tq
+    const float* w1 = w0 + 64;                                // k0 + tq + 4  -> next k-quad
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        acc[g][r][0] = fmaf(x[r].x, w[g][0].x, acc[g][r][0]); acc[g][r][1] = fmaf(x[r].x, w[g][0].y, acc[g][r][1]);
-        acc[g][r][2] = fmaf(x[r].x, w[g][0].z, acc[g][r][2]); acc[g][r][3] = fmaf(x[r].x, w[g][0].w, acc[g][r][3]);
-        acc[g][r][0] = fmaf(x[r].y, w[g][1].x, acc[g][r][0]); acc[g][r][1] = fmaf(x[r].y, w[g][1].y, acc[g][r][1]);
-        acc[g][r][2] = fmaf(x[r].y, w[g][1].z, acc[g][r][2]); acc[g][r][3] = fmaf(x[r].y, w[g][1].w, acc[g][r][3]);
-        acc[g][r][0] = fmaf(x[r].z, w[g][2].x, acc[g][r][0]); acc[g][r][1] = fmaf(x[r].z, w[g][2].y, acc[g][r][1]);
-        acc[g][r][2] = fmaf(x[r].z, w[g][2].z, acc[g][r][2]); acc[g][r][3] = fmaf(x[r].z, w[g][2].w, acc[g][r][3]);
-        acc[g][r][0] = fmaf(x[r].w, w[g][3].x, acc[g][r][0]); acc[g][r][1] = fmaf(x[r].w, w[g][3].y, acc[g][r][1]);
-        acc[g][r][2] = fmaf(x[r].w, w[g][3].z, acc[g][r][2]); acc[g][r][3] = fmaf(x[r].w, w[g][3].w, acc[g][r][3]);
+      for (int nt = 0; nt < 2; ++nt) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(w0[g * wstride + nt * 8], bh0, bl0);
+        split_tf32(w1[g * wstride + nt * 8], bh1, bl1);
+        mma_tf32(acc[g][nt], al, bh0, bh1);   // small terms first
+        mma_tf32(acc[g][nt], ah, bl0, bl1);
+        mma_tf32(acc[g][nt], ah, bh0, bh1);
       }
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int g = 0; g < NG; ++g)
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[g][r][c] += __shfl_xor_sync(0xffffffffu, acc[g][r][c], 16);
+  float* red = A_s;
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    __syncthreads();   // red may still be read by the previous reduction
-    if (lane < 16) {
+    __syncthreads();   // every thread is done reading A_s / the previous reduction
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        *reinterpret_cast<float4*>(red + warp * 256 + (ty * 4 + r) * 16 + tx * 4) =
-            make_float4(acc[g][r][0], acc[g][r][1], acc[g][r][2], acc[g][r][3]);
+    for (int nt = 0; nt < 2; ++nt) {
+      // C fragment: c0 (gq, 2tq), c1 (gq, 2tq+1), c2 (gq+8, 2tq), c3 (gq+8, 2tq+1)
+      float* r0 = red + warp * 256 + gq * 16 + nt * 8 + 2 * tq;
+      *reinterpret_cast<float2*>(r0) = make_float2(acc[g][nt][0], acc[g][nt][1]);
+      *reinterpret_cast<float2*>(r0 + 8 * 16) = make_float2(acc[g][nt][2], acc[g][nt][3]);
     }
     __syncthreads();
     float s = 0.f;
+    if (threadIdx.x < 256) {
 #pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 256 + threadIdx.x];
+      for (int w16 = 0; w16 < THREADS / 32; ++w16) s += red[w16 * 256 + threadIdx.x];
+    }
     out[g] = s;
   }
 }
-__device__ __forceinline__ float sum16(float v) {   // over the 16 lanes that share a row
+__device__ __forceinline__ float sum16(float v) {   // over the 16 lanes that share a tile row
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -206,43 +200,40 @@ __device__ __noinline__ float4 normact4(float4 v, float rs, float4 gg) {
   y.z = siluf_((v.z * rs) * gg.z); y.w = siluf_((v.w * rs) * gg.w);
   return y;
 }
-// the thread's i-th float4 of a 256-wide row sits at columns 64*i + 4*seg (conflict-free stores, 256 B coalesced loads)
-__device__ __forceinline__ void normact16(const float4 (&v)[4], float rs, const float* g_s, int seg, float4 (&y)[4]) {
+// Load mapping: one warp per batch row (lrow = tid >> 5); lane ls owns columns 128*i + 4*ls, i = 0, 1 of a 256-wide row
+// (512 B coalesced loads, conflict-free float4 stores into the A tile).
+__device__ __forceinline__ void normact8(const float4 (&v)[2], float rs, const float* g_s, int ls, float4 (&y)[2]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) y[i] = normact4(v[i], rs, *reinterpret_cast<const float4*>(g_s + i * 64 + seg * 4));
+  for (int i = 0; i < 2; ++i) y[i] = normact4(v[i], rs, *reinterpret_cast<const float4*>(g_s + i * 128 + ls * 4));
 }
 
 // First half of the block-GRU hidden layer of step tt: s_a = W_hid[g][:, 0:512] . [keep * d_g | x0], x0 = SiLU(RMSNorm(v_in0)).
 // Neither operand depends on the sample of the previous step (v_in0 is produced two phases earlier, in P3), so this
 // runs in the otherwise idle P4 / P5 slot and only its 16x16 partial tile (one float per thread) is carried into P1.
-__device__ __noinline__ float hid_first_half(const float* dsrc, float keep, const float* v0src, bool rok, float* A_s,
-                                             const float* W1, float* red, const float* G_s, int row, int seg, float* din_t,
-                                             float* x_t) {
-  float4 dv[4], v0[4];
+__device__ __noinline__ float hid_first_half(const float* dsrc, float keep, const float* v0src, bool lok, float* A_s,
+                                             const float* W1, const float* G_s, int lrow, int ls, float* din_t, float* x_t) {
+  float4 dv[2], v0[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = i * 64 + seg * 4;
-    dv[i] = rok ? ldcg4(dsrc + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    v0[i] = rok ? ldcg4(v0src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 2; ++i) {
+    const int k = i * 128 + ls * 4;
+    dv[i] = lok ? ldcg4(dsrc + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v0[i] = lok ? ldcg4(v0src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  float ss0 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) ss0 += sq4(v0[i]);
-  ss0 = sum16(ss0);
+  const float ss0 = warp_sum(sq4(v0[0]) + sq4(v0[1]));
   const float rs0 = 1.f / sqrtf(ss0 / (float)HW + kRmsEps);
-  float4 x0[4];
-  normact16(v0, rs0, G_s, seg, x0);
+  float4 x0[2];
+  normact8(v0, rs0, G_s, ls, x0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     dv[i].x *= keep; dv[i].y *= keep; dv[i].z *= keep; dv[i].w *= keep;
-    *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = dv[i];
-    *reinterpret_cast<float4*>(A_s + row * ALD + HW + i * 64 + seg * 4) = x0[i];
-    if (din_t) *reinterpret_cast<float4*>(din_t + i * 64 + seg * 4) = dv[i];   // backward tape: masked deter input
-    if (x_t) *reinterpret_cast<float4*>(x_t + i * 64 + seg * 4) = x0[i];       // backward tape: x0
+    *reinterpret_cast<float4*>(A_s + lrow * ALD + i * 128 + ls * 4) = dv[i];
+    *reinterpret_cast<float4*>(A_s + lrow * ALD + HW + i * 128 + ls * 4) = x0[i];
+    if (din_t) *reinterpret_cast<float4*>(din_t + i * 128 + ls * 4) = dv[i];   // backward tape: masked deter input
+    if (x_t) *reinterpret_cast<float4*>(x_t + i * 128 + ls * 4) = x0[i];       // backward tape: x0
   }
   __syncthreads();
   float s;
-  tile_product<1>(A_s, W1, 0, KC / 4, red, &s);
+  tile_product<1>(A_s, W1, 0, KC / 4, &s);
   return s;
 }
 
@@ -253,13 +244,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   float* W3 = sm + kW3;
   float* W45 = sm + kW45;
   float* A_s = sm + kAs;
-  float* red = sm + kRed;
   float* slots = sm + kSlots;
   float* G_s = sm + kGain;
   const int cta = blockIdx.x, tid = threadIdx.x;
-  const int row = tid >> 4, seg = tid & 15, col = tid & 15;
   const int B = P.B, T = P.T, D = P.D, SK = P.SK;
-  const bool rok = row < B;
+  // load mapping (all 512 threads): one warp per batch row
+  const int lrow = tid >> 5, ls = tid & 31;
+  const bool lok = lrow < B;
+  // tile mapping (threads < 256): output element (row, col) of the CTA's 16x16 tile
+  const bool et = tid < 256;
+  const int row = (tid >> 4) & 15, col = tid & 15;
+  const bool rok = et && row < B;
   const int g = cta >> 4, jt = cta & 15;                       // P1 / P2: block and 16-column (16-unit) tile
   const int p3 = cta >> 6, j3 = (cta & 63) >> 2, r3 = cta & 3; // P3: problem, column tile, k-slice (= cluster rank)
   const int n4tiles = SK / 16;
@@ -276,10 +271,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   if (do5) stage_w(W45, P.w_in1, P.ld_in1, 0, SK, j5 * 16, false);
   // RMS scales -> shared memory, per-thread biases -> registers (the acquire of every grid barrier invalidates L1, so
   // anything re-read from global each phase would pay an L2 round trip on the critical path)
-  G_s[tid] = __ldg(P.g_in0 + tid);
-  G_s[256 + tid] = __ldg(P.g_in1 + tid);
-  G_s[512 + tid] = __ldg(P.g_hid + g * HW + tid);
-  G_s[768 + tid] = __ldg(P.g_obs + tid);
+  if (et) {
+    G_s[tid] = __ldg(P.g_in0 + tid);
+    G_s[256 + tid] = __ldg(P.g_in1 + tid);
+    G_s[512 + tid] = __ldg(P.g_hid + g * HW + tid);
+    G_s[768 + tid] = __ldg(P.g_obs + tid);
+  }
   const float bias_h = __ldg(P.b_hid + g * HW + jt * 16 + col);
   const float bias_qr = __ldg(P.b_gru + (size_t)g * 3 * HW + jt * 16 + col);
   const float bias_qc = __ldg(P.b_gru + (size_t)g * 3 * HW + HW + jt * 16 + col);
@@ -290,14 +287,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   unsigned int epoch = 0;
   __syncthreads();
   // first half of step 0's hidden layer (v_in0 of step 0 comes from the host-side launches)
-  float s_a = hid_first_half(P.init_deter + (size_t)row * D + g * HW, (rok && P.is_first[(size_t)row * T]) ? 0.f : 1.f,
-                             P.vin + (size_t)row * (3 * HW), rok, A_s, W1, red, G_s, row, seg,
-                             (P.step && rok && jt == 0) ? P.din + (size_t)row * D + g * HW : nullptr,
-                             (P.step && rok && cta == 0) ? P.x + (size_t)row * (3 * HW) : nullptr);
+  float s_a = hid_first_half(P.init_deter + (size_t)lrow * D + g * HW, (lok && P.is_first[(size_t)lrow * T]) ? 0.f : 1.f,
+                             P.vin + (size_t)lrow * (3 * HW), lok, A_s, W1, G_s, lrow, ls,
+                             (P.step && lok && jt == 0) ? P.din + (size_t)lrow * D + g * HW : nullptr,
+                             (P.step && lok && cta == 0) ? P.x + (size_t)lrow * (3 * HW) : nullptr);
 
   for (int t = 0; t < T; ++t) {
+    // reset masks (rssm.py:161-165) in both mappings
     const float keep_t = (rok && P.is_first[(size_t)row * T + t]) ? 0.f : 1.f;
     const float keep_n = (t + 1 < T && rok && P.is_first[(size_t)row * T + t + 1]) ? 0.f : 1.f;
+    const float lkeep_n = (t + 1 < T && lok && P.is_first[(size_t)lrow * T + t + 1]) ? 0.f : 1.f;
     float* vin_t = P.vin + (size_t)t * sstep * (3 * HW);
     float* hpre_t = P.hpre + (size_t)t * sstep * D;
     float* vobs_t = P.vobs + (size_t)t * sstep * HW;
@@ -306,41 +305,39 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     const float uu_t = (do4 && rok) ? __ldg(P.u + ((size_t)row * T + t) * SK + cta * 16 + col) : 0.5f;
 
     SD_SC_STAMP(0);
-    // ================================================================ P1: hidden layer of the block GRU
+    // ================================================================ P1: hidden layer of the block GRU (second half)
     {
-      float4 v1[4], xv2[4];
+      float4 v1[2], xv2[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = i * 64 + seg * 4;
-        v1[i] = rok ? ldcg4(vin_t + (size_t)row * (3 * HW) + HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        xv2[i] = rok ? __ldg(reinterpret_cast<const float4*>(P.x2 + ((size_t)t * B + row) * HW + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 2; ++i) {
+        const int k = i * 128 + ls * 4;
+        v1[i] = lok ? ldcg4(vin_t + (size_t)lrow * (3 * HW) + HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv2[i] = lok ? __ldg(reinterpret_cast<const float4*>(P.x2 + ((size_t)t * B + lrow) * HW + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float ss1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ss1 += sq4(v1[i]);
-      ss1 = sum16(ss1);
+      const float ss1 = warp_sum(sq4(v1[0]) + sq4(v1[1]));
       const float rs1 = 1.f / sqrtf(ss1 / (float)HW + kRmsEps);
-      float4 x1[4];
-      normact16(v1, rs1, G_s + 256, seg, x1);
+      float4 x1[2];
+      normact8(v1, rs1, G_s + 256, ls, x1);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = x1[i];
-        *reinterpret_cast<float4*>(A_s + row * ALD + HW + i * 64 + seg * 4) = xv2[i];
+      for (int i = 0; i < 2; ++i) {
+        *reinterpret_cast<float4*>(A_s + lrow * ALD + i * 128 + ls * 4) = x1[i];
+        *reinterpret_cast<float4*>(A_s + lrow * ALD + HW + i * 128 + ls * 4) = xv2[i];
       }
-      if (P.step && rok && cta == 0) {   // backward tape: x1 (x0 by hid_first_half, x2 by obs_prep_kernel)
-        float* xt = P.x + ((size_t)t * sstep + row) * (3 * HW) + HW + seg * 4;
+      if (P.step && lok && cta == 0) {   // backward tape: x1 (x0 by hid_first_half, x2 by obs_prep_kernel)
+        float* xt = P.x + ((size_t)t * sstep + lrow) * (3 * HW) + HW + ls * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(xt + i * 64) = x1[i];
+        for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(xt + i * 128) = x1[i];
       }
       __syncthreads();
       float s2;
-      tile_product<1>(A_s, W1 + (KC / 4) * 64, 0, KC / 4, red, &s2);
-      const float s = s_a + s2;
-      const int n = g * HW + jt * 16 + col;
-      const float hp = s + bias_h;
-      if (rok) hpre_t[(size_t)row * D + n] = hp;
-      const float ssr = sum16(hp * hp);
-      if (col == 0) P.ssq_h[row * NCTA + cta] = ssr;
+      tile_product<1>(A_s, W1 + (KC / 4) * 64, 0, KC / 4, &s2);
+      if (et) {
+        const int n = g * HW + jt * 16 + col;
+        const float hp = (s_a + s2) + bias_h;
+        if (rok) hpre_t[(size_t)row * D + n] = hp;
+        const float ssr = sum16(hp * hp);
+        if (col == 0) P.ssq_h[row * NCTA + cta] = ssr;
+      }
     }
     SD_SC_STAMP(1);
     grid_sync(P.bar, epoch);
@@ -348,34 +345,32 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
 
     // ================================================================ P2: gate projection + GRU gates
     {
-      float4 hv[4];
+      float4 hv[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        hv[i] = rok ? ldcg4(hpre_t + (size_t)row * D + g * HW + i * 64 + seg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float tot = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tot += ldcg(P.ssq_h + row * NCTA + seg * 8 + i);   // 128 tile partials per row
-      tot = sum16(tot);
+      for (int i = 0; i < 2; ++i)
+        hv[i] = lok ? ldcg4(hpre_t + (size_t)lrow * D + g * HW + i * 128 + ls * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 pq = ldcg4(P.ssq_h + lrow * NCTA + ls * 4);   // 128 tile partials per row, 4 per lane
+      const float tot = warp_sum((pq.x + pq.y) + (pq.z + pq.w));
       const float rs = 1.f / sqrtf(tot / (float)D + kRmsEps);
-      float4 hh[4];
-      normact16(hv, rs, G_s + 512, seg, hh);
+      float4 hh[2];
+      normact8(hv, rs, G_s + 512, ls, hh);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = hh[i];
-      if (P.step && rok && jt == 0) {
-        float* ht = P.h + ((size_t)t * sstep + row) * D + g * HW + seg * 4;
+      for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(A_s + lrow * ALD + i * 128 + ls * 4) = hh[i];
+      if (P.step && lok && jt == 0) {
+        float* ht = P.h + ((size_t)t * sstep + lrow) * D + g * HW + ls * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(ht + i * 64) = hh[i];
+        for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(ht + i * 128) = hh[i];
       }
       const int n = g * HW + jt * 16 + col;   // unit
       const float* dsrc = t == 0 ? P.init_deter + (size_t)row * D : P.deters + ((size_t)row * T + (t - 1)) * D;
       const float dprev = rok ? keep_t * ldcg(dsrc + n) : 0.f;
       __syncthreads();
       float q3[3];
-      tile_product<3>(A_s, W2, HW * 16, HW / 4, red, q3);   // reset | cand | update tiles share the A operand
-      const float qr = q3[0] + bias_qr;
-      const float qc = q3[1] + bias_qc;
-      const float qu = q3[2] + bias_qu;
+      tile_product<3>(A_s, W2, HW * 16, HW / 4, q3);   // reset | cand | update tiles share the A operand
       if (rok) {
+        const float qr = q3[0] + bias_qr;
+        const float qc = q3[1] + bias_qc;
+        const float qu = q3[2] + bias_qu;
         if (P.step) {
           float* qt = P.q + ((size_t)t * sstep + row) * (3 * D) + (size_t)g * 3 * HW + jt * 16 + col;
           qt[0] = qr; qt[HW] = qc; qt[2 * HW] = qu;
@@ -392,20 +387,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
 
     // ================================================================ P3: obs_net_0 (deter part) and next step's dyn_in0
     {
-      const float* dsrc = P.deters + ((size_t)row * T + t) * D + r3 * KC + seg * 4;
-      float4 a[8];
+      const float* dsrc = P.deters + ((size_t)lrow * T + t) * D + r3 * KC + ls * 4;
+      float4 a[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = rok ? ldcg4(dsrc + i * 64) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int n = j3 * 16 + col;
-      const float extra = bias_3 + ep_t;   // leader: bias (+ embed part of obs_net_0)
+      for (int i = 0; i < 4; ++i) a[i] = lok ? ldcg4(dsrc + i * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = a[i];
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(A_s + lrow * ALD + i * 128 + ls * 4) = a[i];
       __syncthreads();
       SD_SC_STAMP(11);
       float s;
-      tile_product<1>(A_s, W3, 0, KC / 4, red, &s);
+      tile_product<1>(A_s, W3, 0, KC / 4, &s);
       SD_SC_STAMP(12);
-      {
+      if (et) {
         const uint32_t local = (uint32_t)__cvta_generic_to_shared(slots + r3 * 256 + tid);
         uint32_t remote;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
@@ -414,6 +407,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
       cluster_sync_all();
       SD_SC_STAMP(13);
       if (r3 == 0 && rok) {
+        const int n = j3 * 16 + col;
+        const float extra = bias_3 + ep_t;   // bias (+ embed part of obs_net_0)
         const float tot = ((slots[tid] + slots[256 + tid]) + slots[512 + tid]) + slots[768 + tid];
         if (p3 == 0) {
           if (t + 1 < T) P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + n] = extra + keep_n * tot;
@@ -427,50 +422,49 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     SD_SC_STAMP(6);
 
     // ================================================================ P4: logits + sample (other CTAs: first half of the next hidden layer)
-    if (!do4 && t + 1 < T) s_a = hid_first_half(P.deters + ((size_t)row * T + t) * D + g * HW, keep_n, P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW),
-                           rok, A_s, W1, red, G_s, row, seg,
-                           (P.step && rok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + row) * D + g * HW : nullptr,
-                           (P.step && rok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + row) * (3 * HW) : nullptr);
+    if (!do4 && t + 1 < T)
+      s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
+                           P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), lok, A_s, W1, G_s, lrow, ls,
+                           (P.step && lok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + g * HW : nullptr,
+                           (P.step && lok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + lrow) * (3 * HW) : nullptr);
     if (do4) {
-      float4 vv[4];
+      float4 vv[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) vv[i] = rok ? ldcg4(vobs_t + (size_t)row * HW + i * 64 + seg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int n = cta * 16 + col;
-      const float uu = uu_t;
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ss += sq4(vv[i]);
-      ss = sum16(ss);
+      for (int i = 0; i < 2; ++i) vv[i] = lok ? ldcg4(vobs_t + (size_t)lrow * HW + i * 128 + ls * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float ss = warp_sum(sq4(vv[0]) + sq4(vv[1]));
       const float rs = 1.f / sqrtf(ss / (float)HW + kRmsEps);
-      float4 oo[4];
-      normact16(vv, rs, G_s + 768, seg, oo);
+      float4 oo[2];
+      normact8(vv, rs, G_s + 768, ls, oo);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(A_s + row * ALD + i * 64 + seg * 4) = oo[i];
-      if (P.step && rok && cta == 0) {
-        float* ot = P.o + ((size_t)t * sstep + row) * HW + seg * 4;
+      for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(A_s + lrow * ALD + i * 128 + ls * 4) = oo[i];
+      if (P.step && lok && cta == 0) {
+        float* ot = P.o + ((size_t)t * sstep + lrow) * HW + ls * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(ot + i * 64) = oo[i];
+        for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(ot + i * 128) = oo[i];
       }
       __syncthreads();
       float lgv;
-      tile_product<1>(A_s, W45, 0, HW / 4, red, &lgv);
-      lgv += bias_lg;
-      const int Kc = P.K, kcls = col % Kc;
-      int best;
-      if (Kc == 16) best = sample_group<16>(lgv, uu, true, kcls, Kc, P.unimix, nullptr);
-      else if (Kc == 8) best = sample_group<8>(lgv, uu, true, kcls, Kc, P.unimix, nullptr);
-      else if (Kc == 4) best = sample_group<4>(lgv, uu, true, kcls, Kc, P.unimix, nullptr);
-      else best = sample_group<2>(lgv, uu, true, kcls, Kc, P.unimix, nullptr);
-      if (rok) {
-        const float oh = (kcls == best) ? 1.f : 0.f;
-        const size_t off = ((size_t)row * T + t) * SK + n;
-        P.stochs[off] = oh;
-        P.logits[off] = lgv;
-        if (P.step) {
-          P.lg[((size_t)t * sstep + row) * SK + n] = lgv;
-          if (t + 1 < T) P.zin[((size_t)(t + 1) * sstep + row) * SK + n] = keep_n * oh;
+      tile_product<1>(A_s, W45, 0, HW / 4, &lgv);
+      if (et) {   // warps 0-7: one thread per (row, class)
+        lgv += bias_lg;
+        const int n = cta * 16 + col;
+        const int Kc = P.K, kcls = col % Kc;
+        int best;
+        if (Kc == 16) best = sample_group<16>(lgv, uu_t, true, kcls, Kc, P.unimix, nullptr);
+        else if (Kc == 8) best = sample_group<8>(lgv, uu_t, true, kcls, Kc, P.unimix, nullptr);
+        else if (Kc == 4) best = sample_group<4>(lgv, uu_t, true, kcls, Kc, P.unimix, nullptr);
+        else best = sample_group<2>(lgv, uu_t, true, kcls, Kc, P.unimix, nullptr);
+        if (rok) {
+          const float oh = (kcls == best) ? 1.f : 0.f;
+          const size_t off = ((size_t)row * T + t) * SK + n;
+          P.stochs[off] = oh;
+          P.logits[off] = lgv;
+          if (P.step) {
+            P.lg[((size_t)t * sstep + row) * SK + n] = lgv;
+            if (t + 1 < T) P.zin[((size_t)(t + 1) * sstep + row) * SK + n] = keep_n * oh;
+          }
+          if (kcls == 0) P.idx[row * P.S + n / Kc] = best;
         }
-        if (kcls == 0) P.idx[row * P.S + n / Kc] = best;
       }
     }
     SD_SC_STAMP(7);
@@ -478,21 +472,20 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     SD_SC_STAMP(8);
 
     // ================================================================ P5: next step's dyn_in1 (gather-sum of one-hot rows)
-    if (do4 && t + 1 < T) s_a = hid_first_half(P.deters + ((size_t)row * T + t) * D + g * HW, keep_n, P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW),
-                           rok, A_s, W1, red, G_s, row, seg,
-                           (P.step && rok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + row) * D + g * HW : nullptr,
-                           (P.step && rok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + row) * (3 * HW) : nullptr);
-    if (do5 && t + 1 < T) {
+    if (do4 && t + 1 < T)
+      s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
+                           P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), lok, A_s, W1, G_s, lrow, ls,
+                           (P.step && lok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + g * HW : nullptr,
+                           (P.step && lok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + lrow) * (3 * HW) : nullptr);
+    if (do5 && t + 1 < T && rok) {
       float v = 0.f;
-      if (rok) {
-        const int Kc = P.K;
-        for (int s = 0; s < P.S; ++s) {
-          const int id = __ldcg(P.idx + row * P.S + s);
-          v += W45[(s * Kc + id) * 16 + col];
-        }
+      const int Kc = P.K;
+      for (int s = 0; s < P.S; ++s) {
+        const int id = __ldcg(P.idx + row * P.S + s);
+        v += W45[(s * Kc + id) * 16 + col];
       }
       const int n = j5 * 16 + col;
-      if (rok) P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = bias_5 + keep_n * v;
+      P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = bias_5 + keep_n * v;
     }
     SD_SC_STAMP(9);
     if (t + 1 < T) grid_sync(P.bar, epoch);
