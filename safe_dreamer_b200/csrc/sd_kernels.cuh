@@ -33,6 +33,20 @@ __device__ __forceinline__ void pdl_prologue() {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x / (1.f + expf(-x)); }
 
+// 3xTF32 on mma.sync (m16n8k8): x = hi + lo with hi = tf32(x), lo = tf32(x - hi); A*B ~ hi*hi + hi*lo + lo*hi accumulated
+// in fp32.  The dropped lo*lo term is 2^-22 relative, so the result is fp32-class (all fp32 parity tolerances hold),
+// while the 16-row skinny tiles of the small-batch path stop being shared-memory / FMA-issue bound.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 
 // Lane-per-class variant of sample_category for the hot kernels: the group of `GS` lanes (GS = pow2 >= K)
 // that shares a category reduces with shuffles.  Same operation sequence per element as above.
@@ -79,8 +93,9 @@ __device__ __forceinline__ int sample_group(float lg, float u, bool valid, int k
 
 // ------------------------------------------------------------------------------------------------
 // Batched skinny GEMM:  C[R x N] = [A | A2][R x K] * Wt[K x N] + bias, fp32.
-// A CTA owns a 16-row x 16-column output tile and splits K over its 64 thread groups (intra-CTA
-// split-K, reduced through shared memory in a fixed order => deterministic).  Built for the
+// A CTA owns a 16-row x 16-column output tile: the 16 rows are the M of mma.sync.m16n8k8 (3xTF32 split, fp32-class
+// accuracy), K is split over the 8 warps and the partial tiles are summed in warp order through shared memory
+// (fixed order => deterministic).  Built for the
 // latency-bound regime of the posterior scan (R = 16): the grid spreads N over many SMs and every
 // thread does <= ~2k FMAs.  Rows are tiled by 16, so it is also the fp32 parity path for large R.
 // ------------------------------------------------------------------------------------------------
@@ -119,7 +134,7 @@ constexpr int GB_KC = 512;           // largest K slice one CTA handles (staged 
 constexpr int GB_XLD = GB_KC + 4;    // padded row stride of the staged activations
 constexpr int GB_RLD = 16 * 16 + 4;  // padded stride of the split-K reduction buffer
 constexpr int GB_MAXSPLIT = 8;       // cluster size along K (portable maximum)
-constexpr int GB_SMEM = (64 * GB_RLD > 16 * GB_XLD ? 64 * GB_RLD : 16 * GB_XLD) * 4 + GB_MAXSPLIT * 256 * 4;
+constexpr int GB_SMEM = (16 * GB_XLD) * 4 + GB_MAXSPLIT * 256 * 4;   // staged activations (reused as the [8][256] reduction buffer) + cluster slots
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -155,17 +170,22 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
   const int kend = min(p.K, kc + kslice);
   float s = 0.f;
   // Weight prefetch BEFORE the PDL wait: the packed weights do not depend on the preceding kernel, so their
-  // L2 round trip overlaps its execution; only the activations have to wait.
-  float4 w[GB_KC / 4 / 64][4];
+  // L2 round trip overlaps its execution; only the activations have to wait.  They are fetched straight into the
+  // mma.sync B-fragment layout: warp w owns the k-steps (of 8) w, w + 8, ... of this CTA's slice; lane (gq, tq) holds
+  // W[k0 + tq][n] and W[k0 + tq + 4][n] for n = 8*nt + gq.
+  const int lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+  constexpr int KSTEPS = GB_KC / 8 / 8;   // k-steps per warp when the slice is full
+  float wb[KSTEPS][2][2];
 #pragma unroll
-  for (int i = 0; i < GB_KC / 4 / 64; ++i) {
-    const int kbase = kc + (ty + 64 * i) * 4;
+  for (int i = 0; i < KSTEPS; ++i) {
+    const int k0 = kc + (i * 8 + warp) * 8;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = kbase + j;
-      w[i][j] = (active && k < kend) ? __ldg(reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.ldw + wcol + tx * 4))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + tq + 4 * h;
+        wb[i][nt][h] = (active && k < kend) ? __ldg(p.Wt + (size_t)k * p.ldw + wcol + nt * 8 + gq) : 0.f;
+      }
   }
   // bias of this thread's output element(s) (packed weights too)
   const int pre_n = n0 + (tid & 15);
@@ -177,11 +197,6 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
   pdl_prologue();
   SD_G_STAMP(1);
   if (active && kc < kend) {
-    float acc[16][4];
-#pragma unroll
-    for (int r = 0; r < 16; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
     // all global loads of this CTA are issued before anything is stored to shared memory
     // (weights were prefetched into w[][] before the PDL wait, see below)
     // activation slice -> shared memory.  Fast path: 16-byte loads/stores (thread owns 8 float4 = 2 rows x 4
@@ -237,43 +252,43 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
     }
     __syncthreads();
     SD_G_STAMP(2);
+    float acc[2][4];
 #pragma unroll
-    for (int i = 0; i < GB_KC / 4 / 64; ++i) {
-      const int kq = ty + 64 * i;
-      if (kc + kq * 4 < kend) {
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const float4 x = *reinterpret_cast<const float4*>(xs + r * GB_XLD + kq * 4);
-          acc[r][0] = fmaf(x.x, w[i][0].x, acc[r][0]); acc[r][1] = fmaf(x.x, w[i][0].y, acc[r][1]);
-          acc[r][2] = fmaf(x.x, w[i][0].z, acc[r][2]); acc[r][3] = fmaf(x.x, w[i][0].w, acc[r][3]);
-          acc[r][0] = fmaf(x.y, w[i][1].x, acc[r][0]); acc[r][1] = fmaf(x.y, w[i][1].y, acc[r][1]);
-          acc[r][2] = fmaf(x.y, w[i][1].z, acc[r][2]); acc[r][3] = fmaf(x.y, w[i][1].w, acc[r][3]);
-          acc[r][0] = fmaf(x.z, w[i][2].x, acc[r][0]); acc[r][1] = fmaf(x.z, w[i][2].y, acc[r][1]);
-          acc[r][2] = fmaf(x.z, w[i][2].z, acc[r][2]); acc[r][3] = fmaf(x.z, w[i][2].w, acc[r][3]);
-          acc[r][0] = fmaf(x.w, w[i][3].x, acc[r][0]); acc[r][1] = fmaf(x.w, w[i][3].y, acc[r][1]);
-          acc[r][2] = fmaf(x.w, w[i][3].z, acc[r][2]); acc[r][3] = fmaf(x.w, w[i][3].w, acc[r][3]);
+      for (int c = 0; c < 4; ++c) acc[nt][c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KSTEPS; ++i) {
+      const int kl = (i * 8 + warp) * 8;   // offset inside the staged slice (zero filled beyond kend)
+      if (kc + kl < kend) {                // warp-uniform
+        uint32_t ah[4], al[4];
+        split_tf32(xs[gq * GB_XLD + kl + tq], ah[0], al[0]);
+        split_tf32(xs[(gq + 8) * GB_XLD + kl + tq], ah[1], al[1]);
+        split_tf32(xs[gq * GB_XLD + kl + tq + 4], ah[2], al[2]);
+        split_tf32(xs[(gq + 8) * GB_XLD + kl + tq + 4], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32(wb[i][nt][0], bh0, bl0);
+          split_tf32(wb[i][nt][1], bh1, bl1);
+          mma_tf32(acc[nt], al, bh0, bh1);   // small terms first
+          mma_tf32(acc[nt], ah, bl0, bl1);
+          mma_tf32(acc[nt], ah, bh0, bh1);
         }
       }
     }
     __syncthreads();
     SD_G_STAMP(3);
-    float* red = smem;
+    float* red = smem;   // [8 warps][256]: C fragment c0 (gq, 2tq), c1 (gq, 2tq+1), c2 (gq+8, 2tq), c3 (gq+8, 2tq+1)
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
-      *reinterpret_cast<float4*>(red + ty * GB_RLD + r * 16 + tx * 4) =
-          make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-    __syncthreads();
-    {  // 64 k-group partials per output: four interleaved chains (fixed order => deterministic), then combine
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int t = 0; t < 64; t += 4) {
-        s0 += red[(t + 0) * GB_RLD + tid];
-        s1 += red[(t + 1) * GB_RLD + tid];
-        s2 += red[(t + 2) * GB_RLD + tid];
-        s3 += red[(t + 3) * GB_RLD + tid];
-      }
-      s = (s0 + s1) + (s2 + s3);
+    for (int nt = 0; nt < 2; ++nt) {
+      float* r0p = red + warp * 256 + gq * 16 + nt * 8 + 2 * tq;
+      *reinterpret_cast<float2*>(r0p) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(r0p + 8 * 16) = make_float2(acc[nt][2], acc[nt][3]);
     }
+    __syncthreads();
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 256 + tid];   // fixed warp order => deterministic
     SD_G_STAMP(4);
   }
   const int row = r0 + (tid >> 4), cc = tid & 15, n = n0 + cc;

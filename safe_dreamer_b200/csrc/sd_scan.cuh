@@ -118,16 +118,6 @@ __device__ __forceinline__ void stage_w(float* dst, const float* w, int ld, int 
 // memory (fixed order => deterministic).  The reduction buffer ALIASES the A tile (every thread is past its last A
 // read at the first barrier); callers must barrier before they overwrite A_s again.
 // out[g] = element (row = tid >> 4, col = tid & 15) of tile g, valid for tid < 256.  Deliberately not inlined.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 template <int NG>
 __device__ __noinline__ void tile_product(float* A_s, const float* W, int wstride, int nkq, float* out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
