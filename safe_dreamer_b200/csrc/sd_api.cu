@@ -1814,8 +1814,28 @@ static sd::NormActBwdP nbp(const float* dout, int ld_dout, const float* v, int l
   return p;
 }
 // dx[R x K] = dy[R x N] * W[N x K] with the k-contiguous fp32 copy (per block g: column offsets via gstride).
+// Fused prologue descriptor: the dgrad's dy operand is produced on the fly from d(activation) (PRE_NORMBWD).
+struct PreNB {
+  const float* dout; int ld_dout;   // grad w.r.t. the layer's activation output
+  const float* v; int ld_v;         // saved pre-norm values
+  const float* w;                   // RMS scale
+  float* dv; int ld_dv;             // d-tape: grad w.r.t. the pre-norm values (what dy would have been)
+  float* dmn; int ld_dmn;           // d-tape: dm * n (RMS-scale gradient term), nullable
+};
+static bool fuse_bwd_enabled() { static int v = env_flag("SD_FUSE_BWD", 1); return v != 0; }
+static bool pre_nb_ok(const Ctx& cx, int width, const PreNB& q) {
+  return fuse_bwd_enabled() && !cx.tc && width <= 256 && (width % 4) == 0 && (q.ld_dout % 4) == 0 && (q.ld_v % 4) == 0 &&
+         (q.ld_dv % 4) == 0 && (q.ld_dmn % 4) == 0 && ((reinterpret_cast<uintptr_t>(q.dout) | reinterpret_cast<uintptr_t>(q.v) |
+          reinterpret_cast<uintptr_t>(q.w) | reinterpret_cast<uintptr_t>(q.dv) | reinterpret_cast<uintptr_t>(q.dmn)) & 15) == 0;
+}
+static void set_pre(sd::GemmP& p, const PreNB& q, bool write) {
+  p.pre = sd::PRE_NORMBWD; p.pre_write = write ? 1 : 0;
+  p.A = q.dout; p.lda = q.ld_dout;
+  p.pre_v = q.v; p.pre_ldv = q.ld_v; p.pre_w = q.w;
+  p.pre_dv = q.dv; p.pre_lddv = q.ld_dv; p.pre_dmn = q.dmn; p.pre_lddmn = q.ld_dmn;
+}
 static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, int dy_gstride, float* dx, int ld_dx,
-                  int dx_gstride) {
+                  int dx_gstride, const PreNB* pre = nullptr) {
   if (cx.err) return;
   sd::GemmBatch gb;
   memset(&gb, 0, sizeof(gb));
@@ -1827,9 +1847,10 @@ static void dgrad(Ctx& cx, int R, const LinearW& L, const float* dy, int ld_dy, 
     p.Wt = L.wn + (size_t)g * L.N * L.ldk; p.ldw = L.ldk;
     p.bias = nullptr;
     p.C = dx + (size_t)g * dx_gstride; p.ldc = ld_dx; p.N = L.K;
+    if (pre) set_pre(p, *pre, g == 0);
   }
   launch_gemm_f32(cx.st, gb, L.K, L.N, R);
-  cx.check("gemm_f32_kernel(dgrad)");
+  cx.check(pre ? "gemm_f32_kernel(normact_bwd+dgrad)" : "gemm_f32_kernel(dgrad)");
 }
 // dgrad on the tcgen05 path when the transposed bf16 weights exist and a bf16 copy of dy is available
 // (large-row backward of the imagination rollout), else the fp32 cluster GEMM.
@@ -1853,7 +1874,7 @@ struct DgradCall {
   float* dx; int ld_dx;
   int col0, ncols;   // input-column range [col0, col0+ncols) of L (ncols = 0 => all)
 };
-static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n) {
+static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n, const PreNB* pre = nullptr) {
   if (cx.err) return;
   sd::GemmBatch gb;
   memset(&gb, 0, sizeof(gb));
@@ -1868,11 +1889,12 @@ static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n) {
     p.Wt = L.wn + calls[i].col0; p.ldw = L.ldk;
     p.bias = nullptr;
     p.C = calls[i].dx; p.ldc = calls[i].ld_dx; p.N = nc;
+    if (pre) set_pre(p, *pre, i == 0);
     if (nc > max_n) max_n = nc;
     if (L.N > max_k) max_k = L.N;
   }
   launch_gemm_f32(cx.st, gb, max_n, max_k, R);
-  cx.check("gemm_f32_kernel(dgrad)");
+  cx.check(pre ? "gemm_f32_kernel(normact_bwd+dgrad)" : "gemm_f32_kernel(dgrad)");
 }
 template <int GS>
 static void launch_sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int ld_u, const float* ga, int ld_a,
@@ -1901,6 +1923,17 @@ static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, si
   dgrad_any(cx, R, last, d_lg, d_lg_bf, h.SK, 0, bw.t_do, U, 0);
   for (int i = nl - 1; i >= 0; --i) {
     float* dv = bw.d_v[i] + slot * U;
+    // fp32 path: the norm backward runs as the prologue of the layer's dgrad (one launch less per layer)
+    const PreNB pre{bw.t_do, U, sb.vobs[i], U, layers[i].gain, dv, U, bw.dmn_v[i] + slot * U, U};
+    // (first layer only: its dgrad writes dx0, so reading t_do in the prologue cannot race with the output tiles)
+    if (i == 0 && !dvb && pre_nb_ok(cx, U, pre) && layers[0].N == U) {
+      if (k_first > 0) {
+        DgradCall dc[2] = {{&layers[0], dv, U, dx0, k_first, 0, k_first},
+                           {&layers[0], dv, U, dx0_b, ld_b, k_first, layers[0].K - k_first}};
+        dgrad_multi(cx, R, dc, dx0_b ? 2 : 1, &pre);
+      } else dgrad(cx, R, layers[0], dv, U, 0, dx0, layers[0].K, 0, &pre);
+      continue;
+    }
     sd::NormActBwdP p = nbp(bw.t_do, U, sb.vobs[i], U, layers[i].gain, U, dv, U, bw.dmn_v[i] + slot * U, U, dvb);
     normact_bwd(cx, R, &p, 1);
     if (i > 0) dgrad_any(cx, R, layers[i], dv, dvb, U, 0, bw.t_do, U, 0);

@@ -119,7 +119,18 @@ struct GemmP {
   float* e_out2; int e_ld_out2;
   int e_k;           // Dg (gates) or Kc (sample)
   float e_f;         // unimix (sample)
+  // fused A-operand prologue (reverse scans; single k-slice, K <= 256, 16-byte aligned rows):
+  //  PRE_NORMBWD: A is d(out) of a [Linear -> RMSNorm -> SiLU] layer; the CTA turns it into d(pre-norm) on the fly
+  //               (dv = rho*(dn - n*mean(dn*n)), dn = dout*silu'(m)*w) from the saved pre-norm values
+  //               pre_v and the RMS scale pre_w, instead of a separate normact_bwd launch.  The CTA of column tile 0 of a
+  //               problem with pre_write also stores dv / dm*n (the d-tape the weight-gradient pass reads).
+  int pre, pre_write;
+  const float* pre_v; int pre_ldv;
+  const float* pre_w;
+  float* pre_dv; int pre_lddv;
+  float* pre_dmn; int pre_lddmn;
 };
+enum { PRE_NONE = 0, PRE_NORMBWD = 1 };
 enum { EPI_STORE = 0, EPI_GATES = 1, EPI_SAMPLE = 2 };
 constexpr int kMaxBatch = 8;
 struct GemmBatch {
@@ -194,6 +205,42 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
     pb0 = __ldg(p.bias + pre_n);
     if (gates) { pb1 = __ldg(p.bias + p.e_k + pre_n); pb2 = __ldg(p.bias + 2 * p.e_k + pre_n); }
   }
+  // PRE_NORMBWD: the saved pre-norm values and the RMS scale are forward-tape data: fetch them and finish everything
+  // that only depends on them (rho, n, silu') before the PDL wait.  Lane layout: 16 lanes per row, float4 i of a lane
+  // sits at columns 64*i + 4*(tid & 15).
+  const int prow = tid >> 4, pseg = tid & 15;
+  float4 pn[4], pc[4], pre_w4[4];   // n = v*rho, c = silu'(m) and the RMS scale w per element
+  float prho = 0.f;
+  if (p.pre == PRE_NORMBWD && active) {
+    float4 pv[4], pw[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 64 + pseg * 4;
+      const bool ok = c < p.K && r0 + prow < b.R;
+      pv[i] = ok ? __ldg(reinterpret_cast<const float4*>(p.pre_v + (size_t)(r0 + prow) * p.pre_ldv + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pw[i] = c < p.K ? __ldg(reinterpret_cast<const float4*>(p.pre_w + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss += pv[i].x * pv[i].x + pv[i].y * pv[i].y + pv[i].z * pv[i].z + pv[i].w * pv[i].w;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    prho = 1.f / sqrtf(ss / (float)p.K + kRmsEps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float vv[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w}, ww[4] = {pw[i].x, pw[i].y, pw[i].z, pw[i].w};
+      float nn[4], cc[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        nn[e] = vv[e] * prho;
+        const float m = nn[e] * ww[e];
+        const float sg = sigmoidf_(m);
+        cc[e] = sg * (1.f + m * (1.f - sg));
+      }
+      pn[i] = make_float4(nn[0], nn[1], nn[2], nn[3]);
+      pc[i] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+      pre_w4[i] = pw[i];
+    }
+  }
   pdl_prologue();
   SD_G_STAMP(1);
   if (active && kc < kend) {
@@ -205,7 +252,37 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
     const bool vec = ((p.lda & 3) == 0) && ((p.K1 & 3) == 0) && ((kc & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) &&
                      (p.K1 == p.K || (((p.lda2 & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A2) & 15) == 0)));
-    if (vec) {
+    if (p.pre == PRE_NORMBWD) {
+      // dv = rho * (dn - n * mean(dn * n)), dn = dm * w, dm = dout * silu'(m); dm * n is the RMS-scale gradient term
+      float4 dn4[4];
+      float dot = 0.f;
+      const bool wr = p.pre_write && blockIdx.x == 0 && r0 + prow < b.R;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = i * 64 + pseg * 4;
+        const bool ok = c < p.K && r0 + prow < b.R;
+        const float4 dy = ok ? __ldg(reinterpret_cast<const float4*>(p.A + (size_t)(r0 + prow) * p.lda + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 dm = make_float4(dy.x * pc[i].x, dy.y * pc[i].y, dy.z * pc[i].z, dy.w * pc[i].w);
+        if (wr && ok && p.pre_dmn)
+          *reinterpret_cast<float4*>(p.pre_dmn + (size_t)(r0 + prow) * p.pre_lddmn + c) =
+              make_float4(dm.x * pn[i].x, dm.y * pn[i].y, dm.z * pn[i].z, dm.w * pn[i].w);
+        dn4[i] = make_float4(dm.x * pre_w4[i].x, dm.y * pre_w4[i].y, dm.z * pre_w4[i].z, dm.w * pre_w4[i].w);
+        dot = fmaf(dn4[i].x, pn[i].x, dot); dot = fmaf(dn4[i].y, pn[i].y, dot);
+        dot = fmaf(dn4[i].z, pn[i].z, dot); dot = fmaf(dn4[i].w, pn[i].w, dot);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      dot /= (float)p.K;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = i * 64 + pseg * 4;
+        const float4 o4 = make_float4(prho * (dn4[i].x - pn[i].x * dot), prho * (dn4[i].y - pn[i].y * dot),
+                                      prho * (dn4[i].z - pn[i].z * dot), prho * (dn4[i].w - pn[i].w * dot));
+        *reinterpret_cast<float4*>(xs + prow * GB_XLD + c) = (c < p.K) ? o4 : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wr && c < p.K) *reinterpret_cast<float4*>(p.pre_dv + (size_t)(r0 + prow) * p.pre_lddv + c) = o4;
+      }
+      // columns [256, 512) of the staged slice are never read: kend <= 256 on this path
+    } else if (vec) {
       float4 v4[8];
       const int q = tid & 127, rsel = tid >> 7;
       const int kk = kc + q * 4;
