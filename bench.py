@@ -141,9 +141,21 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout must carry ONE JSON line: NCCL prints its version banner to stdout when the communicator is created, so
+        # stdout is pointed at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     c = O.Cfg(E=E, A=A)
     P = O.init_params(c, seed=0)
     lib = _lib.load()

@@ -55,6 +55,10 @@ typedef enum sd_module {
 #define SD_FLAG_SAVE_TAPE  2u  /* keep per-step activations for the matching *_bwd call */
 #define SD_FLAG_GRAPH      4u  /* replay the step sequence as a cached CUDA graph (ignored while the stream is
                                   already being captured, e.g. under torch.compile reduce-overhead) */
+#define SD_FLAG_FEATS_FROM_IMAGINE 8u /* sd_heads_lambda_fwd only: `feats` is the UNMODIFIED feats output of the preceding
+                                  SD_FLAG_BF16 sd_imagine_fwd on this handle (same N, H), so its bf16 copy, written step by
+                                  step during the rollout, is reused instead of re-casting 168 MB; SD_ERR_INVALID when the
+                                  pointer / sizes do not match that call */
 
 /* Sizes of the path: configs/base.yaml:117-127,252-276,340-420. */
 typedef struct sd_config {

@@ -148,6 +148,9 @@ struct sd_handle {
   float *ps_x2 = nullptr, *ps_eproj = nullptr, *ps_ssq = nullptr;
   int* ps_idx = nullptr;
   unsigned int* ps_bar = nullptr;
+  // big_bf holds the bf16 copy of this sd_imagine_fwd feats output (SD_FLAG_FEATS_FROM_IMAGINE), else null
+  const float* bigbf_feats = nullptr;
+  int bigbf_N = 0, bigbf_H = 0;
 };
 
 // ------------------------------------------------------------------------------------------------ TMA maps
@@ -629,7 +632,7 @@ static int ks_for(int K) {   // split-K factor giving ~8-10 k-blocks of 64 per C
 // First launch of an imagination step: the three wide layers that read feat = [stoch | deter] --
 // actor layer 0 (F -> units), dyn_in0 (deter -> U), dyn_in1 (stoch -> U) -- as one split-K tcgen05 batch.
 // Pre-norm outputs land in sb.va[0] / sb.vin (+ partial slices); ks[] returns the per-layer split factors.
-static void imagine_wide_in(Ctx& cx, int N, const StepBufs& sb, int* ks) {
+static void imagine_wide_in(Ctx& cx, int N, const StepBufs& sb, int* ks, const bf16* fb, int ldfb) {
   if (cx.err) return;
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
@@ -637,7 +640,7 @@ static void imagine_wide_in(Ctx& cx, int N, const StepBufs& sb, int* ks) {
   const int SK = h.SK, D = c.D, F = h.F, U = c.U;
   sd::tc::Batch tb;
   memset(&tb, 0, sizeof(tb));
-  bool ok = make_map(&tb.maps[0], h.feat_bf, (uint64_t)N, (uint64_t)F, (uint64_t)F, 128);
+  bool ok = make_map(&tb.maps[0], fb, (uint64_t)N, (uint64_t)F, (uint64_t)ldfb, 128);
   ok = ok && make_map(&tb.maps[1], actor.l[0].w_bf, (uint64_t)actor.l[0].npad, (uint64_t)F, (uint64_t)F, 64);
   ok = ok && make_map(&tb.maps[2], h.in0.w_bf, (uint64_t)h.in0.npad, (uint64_t)D, (uint64_t)D, 64);
   ok = ok && make_map(&tb.maps[3], h.in1.w_bf, (uint64_t)h.in1.npad, (uint64_t)SK, (uint64_t)SK, 64);
@@ -1572,7 +1575,7 @@ extern "C" int sd_prior(sd_handle* h, int R, const float* deter, const float* u,
   key.add(2).add(R).add(deter).add(u).add(stoch).add(logit).add(flags);
   const bool tc = (flags & SD_FLAG_BF16) && R >= 128 && c.U <= c.units;
   int rc = run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
-    if (cx.tc) cast_bf(cx, deter, c.D, h->big_bf, c.D, R, c.D);
+    if (cx.tc) { cast_bf(cx, deter, c.D, h->big_bf, c.D, R, c.D); h->bigbf_feats = nullptr; }
     SampleOut so{u, h->SK, stoch, h->SK, logit, h->SK};
     if (!latent_logits(cx, h->pt, R, h->img, c.img_layers, h->img_logit, opfb(deter, c.D, cx.tc ? h->big_bf : nullptr, c.D),
                        c.D, Operand(), h->pt.lg, &so, h->trunk_bf))
@@ -1669,7 +1672,12 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     // feats[:, 0] = [stoch0 | deter0] (rssm.py:211-217)
     copy_f32(cx, stoch0, SK, feats, ldf, N, SK);
     copy_f32(cx, deter0, D, feats + SK, ldf, N, D);
-    if (cx.tc) cast_bf(cx, feats, ldf, h->feat_bf, F, N, F);
+    // bf16 operand copies of feat_t: without a tape every step writes into its own slot of big_bf laid out like feats
+    // ((N, H, F), row stride H*F), which the heads reuse (SD_FLAG_FEATS_FROM_IMAGINE); with a tape one slot is reused
+    const bool bigbf = cx.tc && !tape;
+    const int ldfb = bigbf ? H * F : F;
+    auto fbt = [&](int t) -> bf16* { return bigbf ? h->big_bf + (size_t)t * F : h->feat_bf; };
+    if (cx.tc) cast_bf(cx, feats, ldf, fbt(0), ldfb, N, F);
     const bool use_chain = cx.tc && !tape && imagine_chain_ok(*h);
     const size_t tsm = sd::actor_tail_smem(h->act_out, c.units, A, c.U);
     const bool use_wide = cx.tc && !tape && wide_in_enabled() && fused_epi_enabled() && c.U == 256 && c.units == 256 &&
@@ -1678,12 +1686,14 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     for (int t = 0; t < H && !cx.err; ++t) {
       const StepBufs sb = at_step(base, t, N, *h);
       float* ft = feats + (size_t)t * F;
-      Operand feat = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
+      bf16* fb = fbt(t);
+      bf16* fbn = fbt(t + 1 < H ? t + 1 : t);   // next step's slot (unused after the last step)
+      Operand feat = opfb(ft, ldf, cx.tc ? fb : nullptr, ldfb);
       if (use_wide && !use_chain) {
         // 13 launches per step: the three wide feat layers in one split-K launch, their three norms in one launch,
         // actor layers 1.. (norm fused), actor tail (+ dyn_in2 and its norm), then the block-GRU / img_net as below
         int ks[3];
-        imagine_wide_in(cx, N, sb, ks);
+        imagine_wide_in(cx, N, sb, ks, fb, ldfb);
         sd::NormActP na[3];
         na[0] = nap(sb.va[0], c.units, actor.l[0].gain, c.units, sb.ao[0], c.units, h->a_bf[0], c.units);
         na[0].parts = h->part + 3 * h->part_stride; na[0].nparts = ks[0] - 1; na[0].part_stride = (long long)h->part_stride;
@@ -1711,27 +1721,27 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
         cx.check("actor_tail_kernel(+x2)");
         if (t == H - 1) break;
         float* dnext = ft + F + SK;
-        deter_core(cx, sb, N, opfb(ft, ldf, h->feat_bf, F), opfb(ft + SK, ldf, h->feat_bf + SK, F), h->abar, dnext, ldf,
-                   h->feat_bf + SK, F, true, true);
+        deter_core(cx, sb, N, opfb(ft, ldf, fb, ldfb), opfb(ft + SK, ldf, fb + SK, ldfb), h->abar, dnext, ldf,
+                   fbn + SK, ldfb, true, true);
         SampleOut so{u + (size_t)t * SK, H * SK, ft + F, ldf, nullptr, 0};
-        if (!latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit, opfb(dnext, ldf, h->feat_bf + SK, F), D, Operand(),
+        if (!latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit, opfb(dnext, ldf, fbn + SK, ldfb), D, Operand(),
                            sb.lg, &so))
-          sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, h->feat_bf, F, nullptr, 0);
+          sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, fbn, ldfb, nullptr, 0);
         continue;
       }
       if (use_chain) {
         // 8 launches per step: wide feat layers | actor chain (+ input norms) | block-GRU hidden | its norm |
         // gate projection + gates | img_net layer 0 | img chain -> logits | sample
         int ks[3];
-        imagine_wide_in(cx, N, sb, ks);
+        imagine_wide_in(cx, N, sb, ks, fb, ldfb);
         imagine_actor_chain(cx, N, H, t, sb, ks, act_noise, actions);
         if (t == H - 1) break;
         float* dnext = ft + F + SK;
-        deter_core(cx, sb, N, opfb(ft, ldf, h->feat_bf, F), opfb(ft + SK, ldf, h->feat_bf + SK, F), h->abar, dnext, ldf,
-                   h->feat_bf + SK, F, true, true);
-        linear(cx, N, h->img[0], opfb(dnext, ldf, h->feat_bf + SK, F), D, Operand(), sb.vobs[0], c.U, 0, h->part);
+        deter_core(cx, sb, N, opfb(ft, ldf, fb, ldfb), opfb(ft + SK, ldf, fb + SK, ldfb), h->abar, dnext, ldf,
+                   fbn + SK, ldfb, true, true);
+        linear(cx, N, h->img[0], opfb(dnext, ldf, fbn + SK, ldfb), D, Operand(), sb.vobs[0], c.U, 0, h->part);
         imagine_img_chain(cx, N, sb, cx.last_ksplit - 1, sb.lg);
-        sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, h->feat_bf, F, nullptr, 0);
+        sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, fbn, ldfb, nullptr, 0);
         continue;
       }
       // action = actor(feat).rsample() (dreamer.py:684)
@@ -1782,16 +1792,18 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
       if (t == H - 1) break;
       float* dnext = ft + F + SK;
       const int ldn = ldf;
-      Operand z = opfb(ft, ldf, cx.tc ? h->feat_bf : nullptr, F);
-      Operand d = opfb(ft + SK, ldf, cx.tc ? h->feat_bf + SK : nullptr, F);
-      deter_core(cx, sb, N, z, d, h->abar, dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F, fused_tail);
+      Operand z = opfb(ft, ldf, cx.tc ? fb : nullptr, ldfb);
+      Operand d = opfb(ft + SK, ldf, cx.tc ? fb + SK : nullptr, ldfb);
+      deter_core(cx, sb, N, z, d, h->abar, dnext, ldn, cx.tc ? fbn + SK : nullptr, ldfb, fused_tail);
       SampleOut so{u + (size_t)t * SK, H * SK, ft + F, ldf, nullptr, 0};
       if (!latent_logits(cx, sb, N, h->img, c.img_layers, h->img_logit,
-                         opfb(dnext, ldn, cx.tc ? h->feat_bf + SK : nullptr, F), D, Operand(), sb.lg, &so))
-        sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, cx.tc ? h->feat_bf : nullptr, F, nullptr, 0);
+                         opfb(dnext, ldn, cx.tc ? fbn + SK : nullptr, ldfb), D, Operand(), sb.lg, &so))
+        sample(cx, N, sb.lg, u + (size_t)t * SK, H * SK, ft + F, ldf, cx.tc ? fbn : nullptr, ldfb, nullptr, 0);
     }
   });
   if (rc == 0 && tape) { h->tape_valid = true; h->tape_B = N; h->tape_T = H; h->tape_kind = 2; }
+  h->bigbf_feats = (rc == 0 && tc && !tape) ? feats : nullptr;
+  h->bigbf_N = N; h->bigbf_H = H;
   return rc;
 }
 
@@ -2240,12 +2252,17 @@ extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feat
   const int F = h->F;
   const long long NH = (long long)N * H;
   const bool tc = (flags & SD_FLAG_BF16) && NH >= 128;
+  const bool reuse = (flags & SD_FLAG_FEATS_FROM_IMAGINE) != 0;
+  if (reuse && (!tc || h->bigbf_feats != feats || h->bigbf_N != N || h->bigbf_H != H))
+    return fail(SD_ERR_INVALID, "sd_heads_lambda_fwd: SD_FLAG_FEATS_FROM_IMAGINE but feats is not the output of the preceding "
+                                "SD_FLAG_BF16 sd_imagine_fwd(N=%d,H=%d) on this handle", N, H);
+  if (tc && !reuse) h->bigbf_feats = nullptr;   // the cast below overwrites big_bf
   Key key;
   key.add(5).add(N).add(H).add(feats).add(disc).add(lamb).add(reward).add(cont).add(value).add(slow_value).add(weight)
       .add(ret).add(flags);
   return run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
     const int R = (int)NH;
-    if (cx.tc) cast_bf(cx, feats, F, h->big_bf, F, R, F);
+    if (cx.tc && !reuse) cast_bf(cx, feats, F, h->big_bf, F, R, F);
     Operand feat = opfb(feats, F, cx.tc ? h->big_bf : nullptr, F);
     // the MLP trunks reuse two (N*H, units) buffers; bf16 copies alias the per-step actor staging only
     // when rows fit, so the heads keep their own: hv (pre-norm), ho (post-act) and big bf16 views.

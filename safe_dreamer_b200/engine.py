@@ -177,6 +177,8 @@ class Engine:
         assert u.numel() == R * self.SK
         deter, u = self._stage(deter, "pr_d"), self._stage(u, "pr_u")
         stoch, logit = self._new(R, c.S, c.K, tag="pr_s"), self._new(R, c.S, c.K, tag="pr_l")
+        if flags & SD_FLAG_BF16:
+            self._imag_feats = None   # sd_prior stages its bf16 operand in the same buffer
         _lib.check(self.lib.sd_prior(self.h, R, _ptr(deter), _ptr(u), _ptr(stoch), _ptr(logit), flags, self.stream),
                    "sd_prior")
         return stoch.reshape(*lead, c.S, c.K), logit.reshape(*lead, c.S, c.K)
@@ -218,6 +220,9 @@ class Engine:
         feats, actions = out if out is not None else (self._new(N, H, self.F, tag="im_f"), self._new(N, H, c.A, tag="im_a"))
         _lib.check(self.lib.sd_imagine_fwd(self.h, N, H, _ptr(stoch0), _ptr(deter0), _ptr(u), _ptr(act_noise),
                                            _ptr(feats), _ptr(actions), flags, self.stream), "sd_imagine_fwd")
+        # the library kept a bf16 copy of feats (tcgen05 path, no tape): heads_lambda() may reuse it while feats is unmodified
+        self._imag_feats = (feats.data_ptr(), feats._version, N, H) if (flags & SD_FLAG_BF16 and not flags & SD_FLAG_SAVE_TAPE
+                                                                       and N >= 128) else None
         return feats, actions
 
     def imagine_bwd(self, N, H, d_feats, d_actions, flags=0):
@@ -238,6 +243,11 @@ class Engine:
             ret = self._new(N, H - 1, 1, tag="hl_ret")
         else:
             rew, cont, val, sval, wgt, ret = out
+        tag = getattr(self, "_imag_feats", None)
+        if (flags & SD_FLAG_BF16) and tag == (feats.data_ptr(), feats._version, N, H):
+            flags |= _lib.SD_FLAG_FEATS_FROM_IMAGINE   # same, unmodified tensor: skip the 168 MB re-cast
+        else:
+            self._imag_feats = None                    # the library's bf16 staging gets overwritten by this call
         _lib.check(self.lib.sd_heads_lambda_fwd(self.h, N, H, _ptr(feats), float(disc), float(lamb), _ptr(rew),
                                                 _ptr(cont), _ptr(val), _ptr(sval), _ptr(wgt), _ptr(ret), flags,
                                                 self.stream), "sd_heads_lambda_fwd")
