@@ -572,6 +572,36 @@ static bool linear_norm_tc(Ctx& cx, int R, const LinearW& L, Operand a, const St
 }
 
 
+// Same for the long-K first layers on many rows (heads on the N*H imagined feats): one CTA per 128 rows owns the whole
+// 256-wide row (BN = 256), so the norm needs no cluster (EPI_NORMW).  Only bf16 (+ optional fp32) activations are
+// written; the pre-norm values are never materialised (no tape on this path).
+static bool linear_norm_tc_wide(Ctx& cx, int R, const LinearW& L, Operand a, const StepBufs& sb, float* out_f, int ld_f,
+                                bf16* out_bf, int ld_bf) {
+  if (!cx.tc || sb.stride != 0 || !fused_epi_enabled() || L.G != 1 || L.N != 256 || L.K <= 256 || (L.K % 64) != 0 ||
+      R < 4096 || !L.w_bf || !a.b || !L.gain || cx.err || (ld_bf % 8) != 0 || (out_f && (ld_f % 4) != 0))
+    return false;
+  sd::tc::Batch tb;
+  memset(&tb, 0, sizeof(tb));
+  bool ok = make_map(&tb.maps[0], a.b, (uint64_t)R, (uint64_t)a.ldb, (uint64_t)a.ldb, 128);
+  ok = ok && make_map(&tb.maps[1], L.w_bf, (uint64_t)L.npad, (uint64_t)L.K, (uint64_t)L.K, 256);
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed"); return true; }
+  sd::tc::Problem& p = tb.p[0];
+  p.a1_map = 0; p.a1_col = 0; p.a2_map = 0; p.a2_col = 0; p.w_map = 1; p.w_row = 0;
+  p.K1 = L.K; p.K = L.K; p.N = L.N; p.bias = L.bias; p.e_gain = L.gain;
+  p.e_out = out_f; p.e_ld_out = ld_f; p.e_out_bf = out_bf; p.e_ld_bf = ld_bf;
+  tb.count = 1; tb.R = R; tb.ksplit = 1;
+  using LW = sd::tc::SmemLayout<256, 4>;
+  auto kern = sd::tc::gemm_bf16_tc_kernel<256, 4, sd::tc::EPI_NORMW>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LW::kTotal);
+    attr_done = true;
+  }
+  launch_k(cx.st, kern, dim3(1, (R + 127) / 128, 1), dim3(sd::tc::THREADS), (size_t)LW::kTotal, tb);
+  cx.check("tc<256,4,normw>");
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ chain kernels
 // SD_CHAIN=1 selects the row-tile resident chain kernels (sd_chain.cuh).  Measured on B200 at N = 1024 they tie with
 // the layer-by-layer path (8 CTAs own all the element-wise work of a 1024 x 256 layer: MUFU / TMEM-read bound, see
@@ -1637,7 +1667,10 @@ static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, f
   for (int i = 0; i < hw.layers; ++i) {
     // (in-place bf16 input/output is safe for the fused kernel: tiles of different clusters touch different
     //  rows, and inside a cluster every store happens after the cluster barrier that follows all MMAs)
-    if (k == hw.l[i].K && linear_norm_tc(cx, R, hw.l[i], cur, h.sb, o[i], units, o_bf[i], units)) {
+    if (k == hw.l[i].K && (linear_norm_tc(cx, R, hw.l[i], cur, h.sb, o[i], units, o_bf[i], units) ||
+                           linear_norm_tc_wide(cx, R, hw.l[i], cur, h.sb,
+                                               (i == hw.layers - 1 && hw.last.N < 64) ? o[i] : nullptr,   // fp32 only when the
+                                               units, o_bf[i], units))) {                                 // last layer is SIMT
       cur = opfb(o[i], units, o_bf[i], units);
       k = units;
       continue;

@@ -53,7 +53,10 @@ struct Problem {
 // four CTAs of a cluster own the four 64-column tiles of the same 128 rows; per-row partial sums of squares are
 // exchanged through distributed shared memory (st.shared::cluster + barrier.cluster) so every CTA can normalise
 // its tile.  e_gain = RMS scale [N]; e_out / e_out_bf = activation fp32 / bf16.
-enum { EPI_STORE = 0, EPI_GATES = 1, EPI_NORM = 2 };
+// EPI_NORMW (BN = 256 = N): the CTA owns whole rows, so RMSNorm -> SiLU needs no cluster: two epilogue warps share a
+// TMEM lane quadrant (128 columns each) and exchange their partial row sums through shared memory.  Writes bf16 (and
+// optionally fp32) activations; used for the K = 2560 first layers of the heads on 16 384 rows.
+enum { EPI_STORE = 0, EPI_GATES = 1, EPI_NORM = 2, EPI_NORMW = 3 };
 struct alignas(64) Batch {
   CUtensorMap maps[kMaxMaps];
   Problem p[kMaxProblems];
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
   static_assert(BN == 64 || BN == 128 || BN == 192 || BN == 256, "unsupported tile width");
   static_assert(EPI != EPI_GATES || BN == 192, "the gate epilogue uses 192-wide tiles (3 gates x 64 units)");
   static_assert(EPI != EPI_NORM || BN == 64, "the fused-norm epilogue uses four 64-wide tiles per cluster");
+  static_assert(EPI != EPI_NORMW || BN == 256, "the wide fused-norm epilogue needs the whole 256-wide row in one tile");
   constexpr int TMEM_COLS = BN == 192 ? 256 : BN;   // allocations are powers of two >= 32 columns
   using L = SmemLayout<BN, NSTAGES>;
   constexpr int STAGES = L::STAGES;
@@ -370,6 +374,57 @@ __global__ void __launch_bounds__(THREADS, NSTAGES <= 4 ? 2 : 1) gemm_bf16_tc_ke
           const float o = stg[rr * SLDN + lane];
           if (pr.e_out) pr.e_out[(size_t)(rb + rr) * pr.e_ld_out + c0 + lane] = o;
           if (pr.e_out_bf) pr.e_out_bf[(size_t)(rb + rr) * pr.e_ld_bf + c0 + lane] = __float2bfloat16(o);
+        }
+      }
+    } else if (EPI == EPI_NORMW) {
+      // warp (quad, half): rows [32*quad, +32) (thread = row), columns [128*half, +128) of the 256-wide row
+      const int halfw = (warp - 2) >> 2;
+      float* ssq = reinterpret_cast<float*>(gen_base + L::kNormOff);   // [2 halves][128 rows]
+      const int rb = m0 + quad * 32;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(halfw * 128);
+      float v[32];
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        tmem_ld32(trow + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float t = v[j] + (pr.bias ? __ldg(pr.bias + halfw * 128 + c0 + j) : 0.f);
+          ss = fmaf(t, t, ss);
+        }
+      }
+      ssq[halfw * 128 + quad * 32 + lane] = ss;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps
+      const float tot = ssq[quad * 32 + lane] + ssq[128 + quad * 32 + lane];
+      const float rs = 1.f / sqrtf(tot / (float)pr.N + 1e-4f);
+      const bool rowok = rb + lane < batch.R;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        tmem_ld32(trow + (uint32_t)c0, v);
+        const int cb = halfw * 128 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float y = ((v[j] + (pr.bias ? __ldg(pr.bias + cb + j) : 0.f)) * rs) * __ldg(pr.e_gain + cb + j);
+          v[j] = __fdividef(y, 1.f + __expf(-y));
+        }
+        if (rowok) {
+          if (pr.e_out_bf) {
+            __nv_bfloat16* ob = pr.e_out_bf + (size_t)(rb + lane) * pr.e_ld_bf + cb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(ob + j) = pk;
+            }
+          }
+          if (pr.e_out) {
+            float* of = pr.e_out + (size_t)(rb + lane) * pr.e_ld_out + cb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(of + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
         }
       }
     } else {

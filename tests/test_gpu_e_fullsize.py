@@ -103,7 +103,27 @@ def test_imagine_heads_properties(full):
     assert np.all(oh.sum(-1) == 1.0) and set(np.unique(oh)) == {0.0, 1.0}
     assert np.isfinite(feats).all() and np.isfinite(acts).all()
     disc, lamb = 1 - 1 / c.horizon, c.lamb
-    rew, cont, val, sval, wgt, ret = [_np(x).astype(np.float64) for x in eng.heads_lambda(cu(feats), disc, lamb, flags=1)]
+    # (a) heads straight on imagine()'s output tensor: the library reuses the bf16 copy the rollout wrote step by step
+    #     (SD_FLAG_FEATS_FROM_IMAGINE); (b) on a copy: re-cast path.  Both must be bit-identical.
+    feats_t, _ = eng.imagine(cu(st0), cu(dt0), cu(ui), cu(noise), H, flags=1)
+    assert eng._imag_feats is not None
+    outs_a = [x.clone() for x in eng.heads_lambda(feats_t, disc, lamb, flags=1)]
+    outs_b = eng.heads_lambda(cu(feats), disc, lamb, flags=1)
+    for xa, xb in zip(outs_a, outs_b):
+        assert torch.equal(xa, xb)
+    feats_t.add_(0.0)   # an in-place op bumps the tensor version: the copy may be stale, the wrapper must re-cast
+    outs_c = eng.heads_lambda(feats_t, disc, lamb, flags=1)
+    assert eng._imag_feats is None
+    for xa, xc in zip(outs_a, outs_c):
+        assert torch.equal(xa, xc)
+    rew, cont, val, sval, wgt, ret = [_np(x).astype(np.float64) for x in outs_b]
+    # value parity of the 16 384-row head evaluation (wide fused-norm tcgen05 first layers) on the first 256 trajectories
+    M = 256
+    rew_o, cont_o, val_o, sval_o, wgt_o, ret_o = O.heads_lambda(c, P["reward"], P["cont"], P["value"], P["slow_value"], feats[:M])
+    np.testing.assert_allclose(cont[:M], cont_o, atol=0.02)
+    np.testing.assert_allclose(rew[:M], rew_o, rtol=0.1, atol=0.05)
+    np.testing.assert_allclose(val[:M], val_o, rtol=0.1, atol=0.05)
+    np.testing.assert_allclose(sval[:M], sval_o, rtol=0.1, atol=0.05)
     assert ((cont > 0) & (cont < 1)).all()
     np.testing.assert_allclose(wgt, np.cumprod(cont * disc, axis=1), rtol=1e-5)
     # R_t = r_{t+1} + cont_{t+1}*disc*((1-lamb) v_{t+1} + lamb R_{t+1}),  R_{H-1} = v_{H-1}
