@@ -450,7 +450,12 @@ static void linear_multi(Ctx& cx, int R, const LinCall* calls, int ncalls) {
       // 256-wide tiles when the layer is wide and either the row count is large, the layer is block-diagonal
       // (many problems already fill the machine) or split-K will provide the parallelism; a batch never
       // mixes tile widths.
-      const bool wide = L.N >= 256 && (L.N % 256) == 0 && (R >= 4096 || tc_wide_enabled()) &&
+      // SD_TC_WIDE_BLOCK=1 (default off): 256-wide tiles + split-K 2 for the block-GRU hidden layer (8 x (K = 1024 -> 256))
+      // at small row counts.  Measured on B200, N = 1024: slower (imagination scan 1.79 vs 1.69 ms) -- 128 CTAs with 8
+      // k-blocks of 48 KB each lose to 256 CTAs (2 per SM) with 16 k-blocks of 24 KB.
+      static const int wide_block = env_flag("SD_TC_WIDE_BLOCK", 0);
+      const bool wide_blk = wide_block && L.G > 1 && L.K >= 1024 && c.parts != nullptr;
+      const bool wide = L.N >= 256 && (L.N % 256) == 0 && (R >= 4096 || tc_wide_enabled() || wide_blk) &&
                         (R >= 4096 || L.G > 1 || (c.parts && L.K >= 1024) || (ntc > 0 && batch_wide && c.parts));
       if (ntc > 0 && (wide != batch_wide || ntc + L.G > sd::tc::kMaxProblems || nmaps + 3 > sd::tc::kMaxMaps)) flush_tc();
       batch_wide = wide;
