@@ -1095,39 +1095,6 @@ extern "C" int64_t sd_weight_numel(const sd_handle* h, int module, int i) {
 }
 
 // ------------------------------------------------------------------------------------------------ weights
-static void pack_linear(Ctx& cx, LinearW& L, const float* w, const float* bias, const float* gain, int gain_n,
-                        bool block_layout) {
-  if (cx.err) return;
-  const long long s_g = block_layout ? 1 : 0;
-  const long long s_n = block_layout ? (long long)L.K * L.G : L.K;
-  const long long s_k = block_layout ? L.G : 1;
-  launch_k(cx.st, sd::pack_weight_kernel, dim3(grid1d((long long)L.G * L.N * L.K, 256)), dim3(256), 0, 
-      w, L.G, L.N, L.K, s_g, s_n, s_k, L.wt, L.ldw, L.wn, L.ldk, L.w_bf, nullptr);
-  cx.check("pack_weight_kernel");
-  if (L.w_bf == nullptr) { /* K not a multiple of 64: SIMT only */ }
-  if (bias && L.bias) cudaMemcpyAsync(L.bias, bias, (size_t)L.G * L.N * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
-  if (gain && L.gain) cudaMemcpyAsync(L.gain, gain, (size_t)gain_n * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
-}
-// bf16 rows are addressed [G][npad][K] but pack_weight_kernel writes [g][n][ldk]: for the bf16 copy the row
-// stride must be K and the block stride npad*K, so it gets its own call below.
-static void pack_linear_bf(Ctx& cx, LinearW& L, const float* w, bool block_layout) {
-  if (cx.err || !L.w_bf) return;
-  const long long s_n = block_layout ? (long long)L.K * L.G : L.K;
-  const long long s_k = block_layout ? L.G : 1;
-  for (int g = 0; g < L.G; ++g) {
-    launch_k(cx.st, sd::pack_weight_kernel, dim3(grid1d((long long)L.N * L.K, 256)), dim3(256), 0, 
-        w + (block_layout ? g : 0), 1, L.N, L.K, 0, s_n, s_k, nullptr, 0, nullptr, L.K,
-        L.w_bf + (size_t)g * L.npad * L.K, nullptr);
-    cx.check("pack_weight_kernel(bf16)");
-    if (L.wT_bf) {
-      launch_k(cx.st, sd::pack_weight_kernel, dim3(grid1d((long long)L.N * L.K, 256)), dim3(256), 0,
-               w + (block_layout ? g : 0), 1, L.N, L.K, 0, s_n, s_k, nullptr, L.N, nullptr, 0, nullptr,
-               L.wT_bf + (size_t)g * L.kpad * L.N);
-      cx.check("pack_weight_kernel(bf16 T)");
-    }
-  }
-}
-
 extern "C" int sd_set_weights(sd_handle* h, int module, const float* const* t, int count, void* stream) {
   if (!h || !t) return fail(SD_ERR_INVALID, "sd_set_weights: null argument");
   if (module < 0 || module >= SD_MOD_COUNT) return fail(SD_ERR_INVALID, "sd_set_weights: bad module %d", module);
@@ -1137,11 +1104,25 @@ extern "C" int sd_set_weights(sd_handle* h, int module, const float* const* t, i
     if (!t[i]) return fail(SD_ERR_INVALID, "sd_set_weights: tensor %d (%s) is null", i, h->wdesc[module][i].name.c_str());
   Ctx cx{h, (cudaStream_t)stream, false};
   const sd_config& c = h->c;
+  // one launch per module: every layer is an entry of the pack table (sd_kernels.cuh: pack_module_kernel)
+  sd::PackTable tbl;
+  memset(&tbl, 0, sizeof(tbl));
+  int nblocks = 0;
   auto pack = [&](LinearW& L, const float* w, const float* b, const float* g, int gn, bool blk) {
-    LinearW tmp = L;
-    tmp.w_bf = nullptr;  // fp32 layouts first (the generic kernel's bf16 strides differ)
-    pack_linear(cx, tmp, w, b, g, gn, blk);
-    pack_linear_bf(cx, L, w, blk);
+    if (tbl.n >= sd::kMaxPack) { cx.err = fail(SD_ERR_INVALID, "sd_set_weights: too many layers in one module"); return; }
+    sd::PackEntry& e = tbl.e[tbl.n++];
+    e.src = w; e.G = L.G; e.N = L.N; e.K = L.K;
+    e.s_g = blk ? 1 : 0; e.s_n = blk ? (long long)L.K * L.G : L.K; e.s_k = blk ? L.G : 1;
+    e.wt = L.wt; e.ldw = L.ldw; e.wn = L.wn; e.ldk = L.ldk;
+    e.w_bf = L.w_bf; e.npad = L.npad; e.wT_bf = L.wT_bf; e.kpad = L.kpad;
+    e.bias_src = b; e.bias_dst = L.bias; e.nbias = L.G * L.N;
+    e.gain_src = g; e.gain_dst = L.gain; e.ngain = gn;
+    const long long total = (long long)L.G * L.N * L.K;
+    long long nb = (total + 2047) / 2048;
+    if (nb < 1) nb = 1;
+    if (nb > 592) nb = 592;
+    e.blk0 = nblocks; e.nblk = (int)nb;
+    nblocks += (int)nb;
   };
   int i = 0;
   if (module == SD_MOD_RSSM) {
@@ -1161,6 +1142,10 @@ extern "C" int sd_set_weights(sd_handle* h, int module, const float* const* t, i
     for (int l = 0; l < hw.layers; ++l, i += 3) pack(hw.l[l], t[i], t[i + 1], t[i + 2], c.units, false);
     pack(hw.last, t[i], t[i + 1], nullptr, 0, false);
     hw.set = true;
+  }
+  if (!cx.err) {
+    launch_k(cx.st, sd::pack_module_kernel, dim3(nblocks), dim3(256), 0, tbl);
+    cx.check("pack_module_kernel");
   }
   g_launches += cx.launches;
   if (cx.err) return cx.err;

@@ -549,6 +549,48 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int G, int N, 
   }
 }
 
+// All layers of one module in ONE launch (sd_set_weights is on the critical path of every training step: the weights
+// change once per update): a table of layers in the kernel parameters, a contiguous range of blocks per layer.  Writes
+// the four packed layouts (fp32 Wt / Wn, bf16 [g][npad][K] and its transpose [g][kpad][N]) and copies bias / RMS scale.
+struct PackEntry {
+  const float* src; int G, N, K; long long s_g, s_n, s_k;
+  float* wt; int ldw; float* wn; int ldk;
+  __nv_bfloat16* w_bf; int npad;
+  __nv_bfloat16* wT_bf; int kpad;
+  const float* bias_src; float* bias_dst; int nbias;
+  const float* gain_src; float* gain_dst; int ngain;
+  int blk0, nblk;
+};
+constexpr int kMaxPack = 16;
+struct PackTable {
+  int n;
+  PackEntry e[kMaxPack];
+};
+__global__ void __launch_bounds__(256) pack_module_kernel(const PackTable t) {
+  pdl_wait();   // no early trigger: consumers may prefetch packed weights before their own wait
+  int ei = 0;
+  while (ei + 1 < t.n && (int)blockIdx.x >= t.e[ei + 1].blk0) ++ei;
+  const PackEntry& e = t.e[ei];
+  const int lb = blockIdx.x - e.blk0;
+  const long long total = (long long)e.G * e.N * e.K;
+  for (long long i = lb * 256ll + threadIdx.x; i < total; i += e.nblk * 256ll) {
+    const int k = (int)(i % e.K);
+    const int n = (int)((i / e.K) % e.N);
+    const int g = (int)(i / ((long long)e.K * e.N));
+    const float v = e.src[g * e.s_g + n * e.s_n + k * e.s_k];
+    if (e.wt) e.wt[((size_t)g * e.K + k) * e.ldw + n] = v;
+    if (e.wn) e.wn[((size_t)g * e.N + n) * e.ldk + k] = v;
+    if (e.w_bf) e.w_bf[((size_t)g * e.npad + n) * e.K + k] = __float2bfloat16(v);
+    if (e.wT_bf) e.wT_bf[((size_t)g * e.kpad + k) * e.N + n] = __float2bfloat16(v);
+  }
+  if (lb == 0) {
+    if (e.bias_src && e.bias_dst)
+      for (int i = threadIdx.x; i < e.nbias; i += 256) e.bias_dst[i] = e.bias_src[i];
+    if (e.gain_src && e.gain_dst)
+      for (int i = threadIdx.x; i < e.ngain; i += 256) e.gain_dst[i] = e.gain_src[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row-wise helpers
 // ------------------------------------------------------------------------------------------------

@@ -87,20 +87,27 @@ class Engine:
         return int(self.lib.sd_workspace_bytes(C.byref(self.cfg)))
 
     def weight_names(self, module):
-        n = self.lib.sd_weight_count(self.h, module)
-        return [self.lib.sd_weight_name(self.h, module, i).decode() for i in range(n)]
+        return list(self._weight_meta(module)[0])
+
+    def _weight_meta(self, module):
+        """(names, numels) of a module's tensors; cached (set_weights runs once per training step)."""
+        cache = self.__dict__.setdefault("_wmeta", {})
+        if module not in cache:
+            n = self.lib.sd_weight_count(self.h, module)
+            cache[module] = ([self.lib.sd_weight_name(self.h, module, i).decode() for i in range(n)],
+                             [int(self.lib.sd_weight_numel(self.h, module, i)) for i in range(n)])
+        return cache[module]
 
     def set_weights(self, module, named):
         """named: mapping state_dict-name -> fp32 CUDA tensor (reference layouts)."""
-        names = self.weight_names(module)
+        names, numels = self._weight_meta(module)
         ts = []
-        for i, n in enumerate(names):
+        for n, want in zip(names, numels):
             if n not in named:
                 raise KeyError(f"set_weights(module={module}): missing tensor '{n}'")
             t = _f32c(named[n].detach(), n)
-            if t.numel() != self.lib.sd_weight_numel(self.h, module, i):
-                raise ValueError(f"set_weights: '{n}' has {t.numel()} elements, expected "
-                                 f"{self.lib.sd_weight_numel(self.h, module, i)}")
+            if t.numel() != want:
+                raise ValueError(f"set_weights: '{n}' has {t.numel()} elements, expected {want}")
             ts.append(t)
         arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         _lib.check(self.lib.sd_set_weights(self.h, module, arr, len(ts), self.stream), "sd_set_weights")
