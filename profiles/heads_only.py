@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from safe_dreamer_b200 import synth as S
-from tests.helpers import cu, make_engine
+from profiles._common import O, cu, make_engine
 N, H = 1024, 16
 c = S.Cfg(); P = S.init_params(c, seed=0)
 eng = make_engine(c, P, max_rows=N, max_steps=H)

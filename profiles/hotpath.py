@@ -10,8 +10,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from oracle import rssm_oracle as O
-from tests.helpers import cu, make_engine
+from profiles._common import O, cu, make_engine
 
 T_OBS = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 H_IMAG = int(sys.argv[2]) if len(sys.argv) > 2 else 3

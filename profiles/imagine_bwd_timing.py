@@ -3,7 +3,6 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from safe_dreamer_b200 import synth as O
 from safe_dreamer_b200.engine import Engine
 H = 16
 c = O.Cfg(); P = O.init_params(c, seed=0)

@@ -3,8 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from safe_dreamer_b200 import synth as O
-from tests.helpers import cu, make_engine
+from profiles._common import O, cu, make_engine
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 N = 1024
 c = O.Cfg(); P = O.init_params(c, seed=0)

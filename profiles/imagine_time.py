@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from safe_dreamer_b200 import synth as S
-from tests.helpers import cu, make_engine
+from profiles._common import O, cu, make_engine
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20

@@ -3,8 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from oracle import rssm_oracle as O
-from tests.helpers import cu, make_engine
+from profiles._common import O, cu, make_engine
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 B = 16
 c = O.Cfg(); P = O.init_params(c, seed=0)

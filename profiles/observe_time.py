@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 from safe_dreamer_b200 import synth as S
-from tests.helpers import cu, make_engine
+from profiles._common import O, cu, make_engine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 c = S.Cfg(); P = S.init_params(c, seed=0)

@@ -3,8 +3,9 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from safe_dreamer_b200 import synth as S, _lib
-from tests.helpers import cu, make_engine
+from safe_dreamer_b200 import _lib
+from safe_dreamer_b200 import synth as S
+from profiles._common import O, cu, make_engine
 c = S.Cfg(); P = S.init_params(c, seed=0)
 eng = make_engine(c, P, max_rows=1024, max_steps=64, max_tape_rows=16)
 Pd = {m: {k: cu(v) for k, v in P[m].items()} for m in P}

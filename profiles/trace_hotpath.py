@@ -10,8 +10,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from oracle import rssm_oracle as O
-from tests.helpers import cu, make_engine
+from profiles._common import O, cu, make_engine
 
 B, T, N, H = 16, 64, 1024, 16
 c = O.Cfg()
