@@ -573,14 +573,22 @@ __global__ void __launch_bounds__(256) pack_module_kernel(const PackTable t) {
   const PackEntry& e = t.e[ei];
   const int lb = blockIdx.x - e.blk0;
   const long long total = (long long)e.G * e.N * e.K;
+  // two passes so that every WRITE is coalesced: k fastest for the k-contiguous layouts, n fastest for the n-contiguous
+  // ones (the strided reads of the second pass hit L2: a module's weights are a few MB)
   for (long long i = lb * 256ll + threadIdx.x; i < total; i += e.nblk * 256ll) {
     const int k = (int)(i % e.K);
     const int n = (int)((i / e.K) % e.N);
     const int g = (int)(i / ((long long)e.K * e.N));
     const float v = e.src[g * e.s_g + n * e.s_n + k * e.s_k];
-    if (e.wt) e.wt[((size_t)g * e.K + k) * e.ldw + n] = v;
     if (e.wn) e.wn[((size_t)g * e.N + n) * e.ldk + k] = v;
     if (e.w_bf) e.w_bf[((size_t)g * e.npad + n) * e.K + k] = __float2bfloat16(v);
+  }
+  for (long long i = lb * 256ll + threadIdx.x; i < total; i += e.nblk * 256ll) {
+    const int n = (int)(i % e.N);
+    const int k = (int)((i / e.N) % e.K);
+    const int g = (int)(i / ((long long)e.K * e.N));
+    const float v = e.src[g * e.s_g + n * e.s_n + k * e.s_k];
+    if (e.wt) e.wt[((size_t)g * e.K + k) * e.ldw + n] = v;
     if (e.wT_bf) e.wT_bf[((size_t)g * e.kpad + k) * e.N + n] = __float2bfloat16(v);
   }
   if (lb == 0) {

@@ -101,6 +101,13 @@ class Engine:
     def set_weights(self, module, named):
         """named: mapping state_dict-name -> fp32 CUDA tensor (reference layouts)."""
         names, numels = self._weight_meta(module)
+        # fast path (once per training step): the same parameter tensors as last time, updated in place by the optimizer
+        fast = self.__dict__.setdefault("_wfast", {}).get(module)
+        if fast is not None:
+            srcs, ptrs, arr = fast
+            if len(srcs) == len(names) and all(named.get(n) is s_ and s_.data_ptr() == p_ for n, s_, p_ in zip(names, srcs, ptrs)):
+                _lib.check(self.lib.sd_set_weights(self.h, module, arr, len(srcs), self.stream), "sd_set_weights")
+                return
         ts = []
         for n, want in zip(names, numels):
             if n not in named:
@@ -112,6 +119,11 @@ class Engine:
         arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         _lib.check(self.lib.sd_set_weights(self.h, module, arr, len(ts), self.stream), "sd_set_weights")
         self._keep[module] = ts  # keep sources alive until the async repack has been enqueued and run
+        srcs = [named[n] for n in names]
+        if all(t.data_ptr() == s_.data_ptr() for t, s_ in zip(ts, srcs)):   # no dtype / layout conversion happened
+            self._wfast[module] = (srcs, [t.data_ptr() for t in ts], arr)
+        else:
+            self._wfast.pop(module, None)
 
     def _stage(self, t, tag):
         """static mode: copy an input into an engine-owned buffer so the pointers seen by the C ABI (and the
