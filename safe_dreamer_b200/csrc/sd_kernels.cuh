@@ -448,16 +448,21 @@ struct WgradBatch {
 };
 
 // Each CTA owns a 64x64 (n,k) tile of one row slice; partial tiles are summed in slice order by
-// wgrad_reduce_kernel.  Next chunk's loads are issued before the current chunk's FMAs (register prefetch).
+// wgrad_reduce_kernel.  The contraction over the rows runs on mma.sync.m16n8k8 with the 3xTF32 split (fp32-class
+// accuracy): M = 64 output features (4 m-tiles), N = 64 input features (8 n-tiles), K = 16 rows per staged chunk.
+// Warp w owns m-tile (w & 3) and the n-tiles 4*(w >> 2) .. +3.  Next chunk's loads are issued before the current
+// chunk's MMAs (register prefetch).
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
   pdl_prologue();
   const int prob = blockIdx.z % b.count, slice = blockIdx.z / b.count;
   const WgradP& p = b.p[prob];
   const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
   if (n0 >= p.N || k0 >= p.K) return;
-  __shared__ __align__(16) float ys[16][64 + 4];
-  __shared__ __align__(16) float xs[16][64 + 4];
-  const int tid = threadIdx.x, tn = tid & 15, tk = tid >> 4;
+  constexpr int LD = 64 + 8;   // row r of a chunk at bank offset 8r: the fragment reads (4 rows x 8 columns) are conflict free
+  __shared__ __align__(16) float ys[16][LD];
+  __shared__ __align__(16) float xs[16][LD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+  const int mt = warp & 3, nh = warp >> 2;
   const int r_begin = slice * b.rows_per_slice;
   const int r_end = min(b.R, r_begin + b.rows_per_slice);
   float acc[4][4];
@@ -493,24 +498,34 @@ __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
     __syncthreads();
     if (rc + 16 < r_end) load(rc + 16);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const float4 y = *reinterpret_cast<const float4*>(&ys[r][tn * 4]);
-      const float4 x = *reinterpret_cast<const float4*>(&xs[r][tk * 4]);
-      const float yy[4] = {y.x, y.y, y.z, y.w}, xx[4] = {x.x, x.y, x.z, x.w};
+    for (int ks = 0; ks < 2; ++ks) {
+      // A[m][kr] = dY[row kr][feature m]: a0 (gq, tq), a1 (gq+8, tq), a2 (gq, tq+4), a3 (gq+8, tq+4)
+      uint32_t ah[4], al[4];
+      split_tf32(ys[ks * 8 + tq][mt * 16 + gq], ah[0], al[0]);
+      split_tf32(ys[ks * 8 + tq][mt * 16 + gq + 8], ah[1], al[1]);
+      split_tf32(ys[ks * 8 + tq + 4][mt * 16 + gq], ah[2], al[2]);
+      split_tf32(ys[ks * 8 + tq + 4][mt * 16 + gq + 8], ah[3], al[3]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(yy[i], xx[j], acc[i][j]);
+      for (int nt = 0; nt < 4; ++nt) {
+        // B[kr][n] = X[row kr][feature n]: b0 (k = tq, n = gq), b1 (k = tq + 4, n = gq)
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(xs[ks * 8 + tq][nh * 32 + nt * 8 + gq], bh0, bl0);
+        split_tf32(xs[ks * 8 + tq + 4][nh * 32 + nt * 8 + gq], bh1, bl1);
+        mma_tf32(acc[nt], al, bh0, bh1);   // small terms first
+        mma_tf32(acc[nt], ah, bl0, bl1);
+        mma_tf32(acc[nt], ah, bh0, bh1);
+      }
     }
     __syncthreads();
   }
   float* out = p.dW + (long long)slice * p.slice_stride;
+  // C fragment: c0 (gq, 2tq), c1 (gq, 2tq+1), c2 (gq+8, 2tq), c3 (gq+8, 2tq+1)
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tn * 4 + i, k = k0 + tk * 4 + j;
-      if (n < p.N && k < p.K) out[n * p.sn + k * p.sk] = acc[i][j];
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + mt * 16 + gq + (c >> 1) * 8, kq = k0 + nh * 32 + nt * 8 + 2 * tq + (c & 1);
+      if (n < p.N && kq < p.K) out[n * p.sn + kq * p.sk] = acc[nt][c];
     }
 }
 // dst[i] += sum_s partial[s*stride + i], s ascending.
