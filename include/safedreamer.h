@@ -168,6 +168,11 @@ int sd_lambda_return(int N, int T, const float* last, const float* term, const f
 int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
                float* dyn_loss, float* rep_loss, float* post_entropy, float* prior_entropy, void* stream);
 
+/* ReturnEMA.__call__ (networks.py:416-422): q05/q95 = torch.quantile(ret.flatten(), [0.05, 0.95]) (linear interpolation),
+ * ema_vals[2] (device, in/out) <- alpha * q + (1 - alpha) * ema_vals, offset = ema_vals[0],
+ * scale = max(ema_vals[1] - ema_vals[0], 1).  `ret` holds n device floats; offset / scale are device scalars (nullable). */
+int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale, void* stream);
+
 /* Kernels launched by this library since process start (all handles): bench.py's gpu_launches. */
 uint64_t sd_launch_count(void);
 

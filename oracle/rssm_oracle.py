@@ -300,6 +300,30 @@ def imagine_with_action(c: Cfg, P, stoch, deter, actions, u):
     return np.stack(S_, 1), np.stack(D_, 1)
 
 
+def return_ema(x, ema_vals, alpha=1e-2):
+    """ReturnEMA.__call__ (networks.py:416-422): returns (new ema_vals, offset, scale), all float32.
+
+    torch.quantile(flat, [0.05, 0.95]) with linear interpolation computes, in float32: rank = q * (n - 1),
+    below = floor(rank), above = ceil(rank), w = rank - below, lerp(v[below], v[above], w) with torch's lerp
+    (w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)); then alpha * q + (1 - alpha) * ema with the two Python-float
+    scalars rounded to float32 and no fused multiply-add."""
+    f = np.float32
+    v = np.sort(np.asarray(x, np.float32).reshape(-1))
+    n = v.size
+    qv = []
+    for q in (f(0.05), f(0.95)):
+        rank = f(q * f(n - 1))
+        lo, hi = int(np.floor(rank)), int(np.ceil(rank))
+        w = f(rank - f(np.floor(rank)))
+        a, b = v[lo], v[hi]
+        d = f(b - a)
+        qv.append(f(a + f(w * d)) if w < f(0.5) else f(b - f(d * f(f(1.0) - w))))
+    a32, b32 = f(alpha), f(1.0 - alpha)
+    ema = np.asarray(ema_vals, np.float32)
+    new = np.array([f(f(a32 * qv[0]) + f(b32 * ema[0])), f(f(a32 * qv[1]) + f(b32 * ema[1]))], np.float32)
+    return new, new[0], np.maximum(f(new[1] - new[0]), f(1.0))
+
+
 # --------------------------------------------------------------------------- heads
 def head_logits(p, name, layers, feat):
     """MLPHead.forward up to the distribution factory (networks.py:339-377)."""

@@ -2335,6 +2335,18 @@ extern "C" int sd_lambda_return(int N, int T, const float* last, const float* te
   return SD_OK;
 }
 
+extern "C" int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale,
+                             void* stream) {
+  if (!ret || !ema_vals || n < 1) return fail(SD_ERR_INVALID, "sd_return_ema: null tensor or n < 1");
+  if (!(alpha >= 0.0 && alpha <= 1.0)) return fail(SD_ERR_INVALID, "sd_return_ema: alpha must be in [0, 1]");
+  launch_k((cudaStream_t)stream, sd::return_ema_kernel, dim3(1), dim3(1024), 0, ret, (long long)n, (float)alpha,
+           (float)(1.0 - alpha), ema_vals, offset, scale);
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_return_ema: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+
 extern "C" int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
                           float* dyn_loss, float* rep_loss, float* post_entropy, float* prior_entropy, void* stream) {
   if (!h) return fail(SD_ERR_INVALID, "sd_kl_loss: null handle");

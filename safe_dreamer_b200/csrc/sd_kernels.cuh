@@ -1096,6 +1096,78 @@ __global__ void imag_weight_ret_kernel(int N, int H, const float* __restrict__ r
   }
 }
 
+// ReturnEMA.__call__ (networks.py:416-422): q05 / q95 of the flattened returns (torch.quantile, linear interpolation),
+// EMA(alpha) of the two, offset = ema[0], scale = max(ema[1] - ema[0], 1).
+// One CTA.  An order statistic is found by an MSB-first radix select (4 passes of 8 bits over order-preserving uint32
+// keys, shared-memory histogram) -- exact, any n, no sort.  The rank / interpolation arithmetic follows torch in fp32:
+// rank = q * (n - 1), below = floor, above = ceil, lerp(a, b, w) = w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w).
+__device__ __forceinline__ uint32_t f32_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void __launch_bounds__(1024) return_ema_kernel(const float* __restrict__ x, long long n, float a32, float b32,
+                                                         float* ema, float* offset, float* scale) {
+  pdl_prologue();
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sel_prefix;
+  __shared__ long long sel_k;
+  __shared__ float stat[4];
+  const float qs[2] = {0.05f, 0.95f};
+  for (int s = 0; s < 4; ++s) {
+    const float rank = qs[s >> 1] * (float)(n - 1);
+    long long kth = (long long)((s & 1) ? ceilf(rank) : floorf(rank));
+    if (kth < 0) kth = 0;
+    if (kth > n - 1) kth = n - 1;
+    unsigned int prefix = 0, mask = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t key = f32_key(x[i]);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        long long kk = kth;
+        int d = 0;
+        for (; d < 255; ++d) {
+          if (kk < (long long)hist[d]) break;
+          kk -= hist[d];
+        }
+        sel_prefix = prefix | ((unsigned int)d << shift);
+        sel_k = kk;
+      }
+      __syncthreads();
+      prefix = sel_prefix;
+      kth = sel_k;
+      mask |= 255u << shift;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) stat[s] = key_f32(prefix);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float qv[2];
+    for (int j = 0; j < 2; ++j) {
+      const float rank = qs[j] * (float)(n - 1);
+      const float w = rank - floorf(rank);
+      const float a = stat[2 * j], b = stat[2 * j + 1];
+      const float d = __fsub_rn(b, a);
+      qv[j] = (w < 0.5f) ? __fadd_rn(a, __fmul_rn(w, d)) : __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.f, w)));
+    }
+    const float e0 = __fadd_rn(__fmul_rn(a32, qv[0]), __fmul_rn(b32, ema[0]));
+    const float e1 = __fadd_rn(__fmul_rn(a32, qv[1]), __fmul_rn(b32, ema[1]));
+    ema[0] = e0; ema[1] = e1;
+    if (offset) *offset = e0;
+    if (scale) *scale = fmaxf(__fsub_rn(e1, e0), 1.f);
+  }
+}
+
+
 // RSSM.kl_loss values + unimix entropies (rssm.py:222-230; distributions.py:266-271; dreamer.py:575-576).
 // One thread per (row, category); per-row sums are reduced in a fixed order by the last stage.
 __global__ void kl_entropy_kernel(const float* __restrict__ post, const float* __restrict__ prior, int R, int S, int K,

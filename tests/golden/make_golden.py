@@ -240,8 +240,38 @@ def run_case(tag, c, B, T, N, H, rssm_mod, dists, networks, dreamer, store_input
     print(tag, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", "dreamer.py used:", dreamer is not None)
 
 
+def return_ema_inputs(case, call):
+    """Seeded return tensors for the ReturnEMA goldens (shape as dreamer.py:600-602: (N, H-1, 1)); shared with the tests."""
+    n_rows, scale, shift, ties = [(1024, 3.0, 1.0, False), (7, 1.0, 0.0, False), (1, 1.0, 2.0, False), (333, 50.0, -20.0, True),
+                                  (9001, 0.01, 0.0, False)][case]
+    rng = np.random.Generator(np.random.Philox(900 + 17 * case + call))
+    x = (rng.standard_normal((n_rows, 15, 1), dtype=np.float32) * np.float32(scale) + np.float32(shift + 0.5 * call)).astype(np.float32)
+    if ties:
+        x = np.round(x)          # many equal values
+    return x
+
+
+def run_return_ema(networks):
+    """ReturnEMA (networks.py:405-422), four consecutive calls per case (the buffer carries over)."""
+    out = {}
+    for case in range(5):
+        ema = networks.ReturnEMA(device="cpu")
+        for call in range(4):
+            x = return_ema_inputs(case, call)
+            off, scl = ema(t(x))
+            out[f"c{case}_{call}_ema"] = ema.ema_vals.numpy().copy()
+            out[f"c{case}_{call}_offset"] = np.float32(off.item())
+            out[f"c{case}_{call}_scale"] = np.float32(scl.item())
+    path = os.path.join(ROOT, "tests", "golden", "return_ema.npz")
+    np.savez_compressed(path, **out)
+    print("return_ema ->", path)
+
+
 def main():
     rssm_mod, dists, networks, dreamer = import_reference()
+    if "--return-ema-only" in sys.argv:
+        run_return_ema(networks)
+        return
     patch_noise(dists)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     tiny = dict(D=256, U=64, S=8, K=8, G=4, E=48, units=64)
@@ -249,6 +279,7 @@ def main():
     run_case("tiny_onehot", O.Cfg(A=5, act_kind="onehot", **tiny), 3, 6, 5, 4, rssm_mod, dists, networks, dreamer, True)
     run_case("base_cont", O.Cfg(), 2, 5, 4, 3, rssm_mod, dists, networks, dreamer, False)
     run_case("base_onehot18", O.Cfg(A=18, act_kind="onehot"), 2, 3, 3, 3, rssm_mod, dists, networks, dreamer, False)
+    run_return_ema(networks)
 
 
 if __name__ == "__main__":
