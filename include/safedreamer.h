@@ -168,6 +168,12 @@ int sd_lambda_return(int N, int T, const float* last, const float* term, const f
 int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
                float* dyn_loss, float* rep_loss, float* post_entropy, float* prior_entropy, void* stream);
 
+/* Backward of sd_kl_loss w.r.t. the raw logits (autograd of rssm.py:222-230 with its detach pattern): g_dyn / g_rep are the
+ * upstream gradients of the per-row dyn / rep losses (nullable = ones); d_post receives the rep term, d_prior the dyn term
+ * (each nullable); rows whose summed KL is below free_nats get zero gradient (the clip). */
+int sd_kl_loss_bwd(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
+                   const float* g_dyn, const float* g_rep, float* d_post_logit, float* d_prior_logit, void* stream);
+
 /* ReturnEMA.__call__ (networks.py:416-422): q05/q95 = torch.quantile(ret.flatten(), [0.05, 0.95]) (linear interpolation),
  * ema_vals[2] (device, in/out) <- alpha * q + (1 - alpha) * ema_vals, offset = ema_vals[0],
  * scale = max(ema_vals[1] - ema_vals[0], 1).  `ret` holds n device floats; offset / scale are device scalars (nullable). */

@@ -145,6 +145,20 @@ def kl_loss(post_logit, prior_logit, free):
     return v.copy(), v.copy()  # dyn_loss, rep_loss
 
 
+def kl_loss_bwd(post_logit, prior_logit, free, g_dyn, g_rep):
+    """Autograd of RSSM.kl_loss (rssm.py:222-230): returns (d_post_logit, d_prior_logit).
+
+    rep = clip(KL(post || sg(prior)).sum(-1), free) -> posterior logits; dyn = clip(KL(sg(post) || prior).sum(-1), free) ->
+    prior logits; torch.clip passes gradient where the clipped value >= free."""
+    lp, lq = log_softmax(post_logit), log_softmax(prior_logit)
+    p, q = np.exp(lp), np.exp(lq)
+    kls = (p * (lp - lq)).sum(-1, keepdims=True)                      # (..., S, 1)
+    act = (kls.sum(-2, keepdims=True) >= post_logit.dtype.type(free)).astype(post_logit.dtype)
+    gd = np.asarray(g_dyn, post_logit.dtype)[..., None, None] * act
+    gr = np.asarray(g_rep, post_logit.dtype)[..., None, None] * act
+    return gr * p * ((lp - lq) - kls), gd * (q - p)
+
+
 def torch_linspace_f32(start, end, steps):
     """torch.linspace's symmetric fp32 algorithm (front half from start, back half from end)."""
     start, end = np.float32(start), np.float32(end)

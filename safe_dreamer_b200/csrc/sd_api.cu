@@ -2335,6 +2335,23 @@ extern "C" int sd_lambda_return(int N, int T, const float* last, const float* te
   return SD_OK;
 }
 
+extern "C" int sd_kl_loss_bwd(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
+                              const float* g_dyn, const float* g_rep, float* d_post_logit, float* d_prior_logit, void* stream) {
+  if (!h || !post_logit || !prior_logit) return fail(SD_ERR_INVALID, "sd_kl_loss_bwd: null argument");
+  if (R < 1 || (long long)R > (long long)h->c.max_rows * h->c.max_steps)
+    return fail(SD_ERR_WORKSPACE, "sd_kl_loss_bwd: R=%d exceeds max_rows*max_steps", R);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = R * h->c.S;
+  launch_k(st, sd::kl_entropy_kernel, dim3((n + 127) / 128), dim3(128), 0, post_logit, prior_logit, R, h->c.S, h->c.K, h->c.unimix,
+           h->kl_a, (float*)nullptr, (float*)nullptr);
+  launch_k(st, sd::kl_grad_kernel, dim3((n + 127) / 128), dim3(128), 0, post_logit, prior_logit, (const float*)h->kl_a, R, h->c.S,
+           h->c.K, free_nats, g_dyn, g_rep, d_post_logit, d_prior_logit);
+  g_launches += 2;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_kl_loss_bwd: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+
 extern "C" int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale,
                              void* stream) {
   if (!ret || !ema_vals || n < 1) return fail(SD_ERR_INVALID, "sd_return_ema: null tensor or n < 1");

@@ -1221,4 +1221,35 @@ __global__ void kl_finish_kernel(const float* __restrict__ kl_sk, const float* _
   if (ent_prior) ent_prior[r] = eq;
 }
 
+// Backward of RSSM.kl_loss (rssm.py:222-230): rep = clip(KL(post || sg(prior)).sum_s, free) sends gradient to the posterior
+// logits only, dyn = clip(KL(sg(post) || prior).sum_s, free) to the prior logits only; the clip passes gradient where the
+// row's KL >= free (torch.clamp's mask).  Per category: dKL/d post_j = p_j ((log p_j - log q_j) - KL_s),
+// dKL/d prior_j = q_j - p_j.  One thread per (row, category); kl_sk = per-category KL from kl_entropy_kernel.
+__global__ void kl_grad_kernel(const float* __restrict__ post, const float* __restrict__ prior, const float* __restrict__ kl_sk,
+                               int R, int S, int K, float free_nats, const float* __restrict__ g_dyn,
+                               const float* __restrict__ g_rep, float* d_post, float* d_prior) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * S) return;
+  const int r = i / S;
+  float tot = 0.f;
+  for (int s = 0; s < S; ++s) tot += kl_sk[(size_t)r * S + s];   // same order as kl_finish_kernel
+  const float act = tot >= free_nats ? 1.f : 0.f;
+  const float gd = act * (g_dyn ? g_dyn[r] : 1.f), gr = act * (g_rep ? g_rep[r] : 1.f);
+  const float* a = post + (size_t)i * K;
+  const float* b = prior + (size_t)i * K;
+  float ma = -INFINITY, mb = -INFINITY;
+  for (int k = 0; k < K; ++k) { ma = fmaxf(ma, a[k]); mb = fmaxf(mb, b[k]); }
+  float sa = 0.f, sb = 0.f;
+  for (int k = 0; k < K; ++k) { sa += expf(a[k] - ma); sb += expf(b[k] - mb); }
+  const float lsa = ma + logf(sa), lsb = mb + logf(sb);
+  const float kls = kl_sk[i];
+  for (int k = 0; k < K; ++k) {
+    const float lp = a[k] - lsa, lq = b[k] - lsb;
+    const float pk = expf(lp), qk = expf(lq);
+    if (d_post) d_post[(size_t)i * K + k] = gr * pk * ((lp - lq) - kls);
+    if (d_prior) d_prior[(size_t)i * K + k] = gd * (qk - pk);
+  }
+}
+
 }  // namespace sd

@@ -294,3 +294,15 @@ class Engine:
         if entropies:
             outs += [ep.reshape(lead), eq.reshape(lead)]
         return tuple(outs)
+
+    def kl_loss_bwd(self, post_logit, prior_logit, free, g_dyn, g_rep, want_post=True, want_prior=True):
+        """Gradients of (dyn, rep) = kl_loss(...) w.r.t. the raw logits (rssm.py:222-230 detach pattern)."""
+        a, b = _f32c(post_logit, "post_logit"), _f32c(prior_logit, "prior_logit")
+        R = a.numel() // self.SK
+        gd = None if g_dyn is None else _f32c(g_dyn, "g_dyn").reshape(-1)
+        gr = None if g_rep is None else _f32c(g_rep, "g_rep").reshape(-1)
+        d_post = torch.empty_like(a) if want_post else None
+        d_prior = torch.empty_like(b) if want_prior else None
+        _lib.check(self.lib.sd_kl_loss_bwd(self.h, R, _ptr(a), _ptr(b), float(free), _ptr(gd), _ptr(gr), _ptr(d_post),
+                                           _ptr(d_prior), self.stream), "sd_kl_loss_bwd")
+        return d_post, d_prior

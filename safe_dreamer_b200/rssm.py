@@ -107,6 +107,31 @@ class _Runtime:
         self.__init__()
 
 
+class _KLFn(torch.autograd.Function):
+    """RSSM.kl_loss (rssm.py:222-230) through the C ABI: rep sends gradient to the posterior logits only, dyn to the prior
+    logits only, rows clipped at `free` send none."""
+
+    @staticmethod
+    def forward(ctx, rssm, post_logit, prior_logit, free):
+        lead = post_logit.shape[:-2]
+        rows = 1
+        for d in lead:
+            rows *= int(d)
+        eng = rssm._get_engine(max(rows, 1), 1)
+        dyn, rep = eng.kl_loss(post_logit, prior_logit, free)
+        ctx.save_for_backward(post_logit, prior_logit)
+        ctx.rssm, ctx.free, ctx.rows = rssm, free, rows
+        return dyn.reshape(lead).clone(), rep.reshape(lead).clone()
+
+    @staticmethod
+    def backward(ctx, g_dyn, g_rep):
+        post_logit, prior_logit = ctx.saved_tensors
+        eng = ctx.rssm._get_engine(max(ctx.rows, 1), 1)
+        d_post, d_prior = eng.kl_loss_bwd(post_logit, prior_logit, ctx.free, g_dyn.contiguous(), g_rep.contiguous(),
+                                          ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return None, d_post, d_prior, None
+
+
 class _ObserveFn(torch.autograd.Function):
     """observe forward/backward through the C ABI (sd_observe_fwd / sd_observe_bwd)."""
 
@@ -329,7 +354,10 @@ class RSSM(nn.Module):
         return torch.distributions.independent.Independent(OneHotDist(logit, unimix_ratio=self._unimix_ratio), 1)
 
     def kl_loss(self, post_logit, prior_logit, free):
-        """rssm.py:222-230 (differentiable; the fused value-only kernel is Engine.kl_loss)."""
+        """rssm.py:222-230 -> (dyn_loss, rep_loss).  CUDA tensors go through sd_kl_loss / sd_kl_loss_bwd (values and the
+        gradients of the reference's detach pattern); anything else through the torch restatement."""
+        if post_logit.is_cuda and prior_logit.is_cuda:
+            return _KLFn.apply(self, post_logit.float(), prior_logit.float(), float(free))
         from .distributions import kl
         rep_loss = kl(post_logit, prior_logit.detach()).sum(-1)
         dyn_loss = kl(post_logit.detach(), prior_logit).sum(-1)

@@ -251,6 +251,32 @@ def return_ema_inputs(case, call):
     return x
 
 
+def kl_grad_inputs():
+    """Seeded (R, S, K) posterior / prior logits and upstream row gradients for the kl_loss backward goldens; the scale
+    makes some rows fall under free = 1 (clipped: zero gradient) and some above.  Shared with the tests."""
+    rng = np.random.Generator(np.random.Philox(4242))
+    R, S, K = 12, 32, 16
+    post = rng.standard_normal((R, S, K), dtype=np.float32) * np.linspace(0.05, 1.5, R, dtype=np.float32)[:, None, None]
+    prior = rng.standard_normal((R, S, K), dtype=np.float32) * np.linspace(0.05, 1.5, R, dtype=np.float32)[:, None, None]
+    g_dyn = rng.standard_normal(R, dtype=np.float32)
+    g_rep = rng.standard_normal(R, dtype=np.float32)
+    return post.astype(np.float32), prior.astype(np.float32), g_dyn, g_rep
+
+
+def run_kl_grad(rssm_mod):
+    """Autograd of the reference RSSM.kl_loss (rssm.py:222-230) on seeded logits."""
+    c = O.Cfg()
+    R = rssm_mod.RSSM(rssm_cfg(c), c.E, c.A)
+    post, prior, g_dyn, g_rep = kl_grad_inputs()
+    a, b = t(post).requires_grad_(True), t(prior).requires_grad_(True)
+    dyn, rep = R.kl_loss(a, b, 1.0)
+    loss = (dyn * t(g_dyn)).sum() + (rep * t(g_rep)).sum()
+    da, db = torch.autograd.grad(loss, [a, b])
+    path = os.path.join(ROOT, "tests", "golden", "kl_grad.npz")
+    np.savez_compressed(path, dyn=dyn.detach().numpy(), rep=rep.detach().numpy(), d_post=da.numpy(), d_prior=db.numpy())
+    print("kl_grad ->", path, "rows clipped:", int((dyn.detach() <= 1.0).sum().item()), "of", post.shape[0])
+
+
 def run_return_ema(networks):
     """ReturnEMA (networks.py:405-422), four consecutive calls per case (the buffer carries over)."""
     out = {}
@@ -272,6 +298,9 @@ def main():
     if "--return-ema-only" in sys.argv:
         run_return_ema(networks)
         return
+    if "--kl-grad-only" in sys.argv:
+        run_kl_grad(rssm_mod)
+        return
     patch_noise(dists)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     tiny = dict(D=256, U=64, S=8, K=8, G=4, E=48, units=64)
@@ -280,6 +309,7 @@ def main():
     run_case("base_cont", O.Cfg(), 2, 5, 4, 3, rssm_mod, dists, networks, dreamer, False)
     run_case("base_onehot18", O.Cfg(A=18, act_kind="onehot"), 2, 3, 3, 3, rssm_mod, dists, networks, dreamer, False)
     run_return_ema(networks)
+    run_kl_grad(rssm_mod)
 
 
 if __name__ == "__main__":
