@@ -174,6 +174,14 @@ int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const float* prior_
 int sd_kl_loss_bwd(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
                    const float* g_dyn, const float* g_rep, float* d_post_logit, float* d_prior_logit, void* stream);
 
+/* TwoHot.log_prob (distributions.py:100-129) of R rows of `n` logits (row stride ld) against scalar targets and the bin
+ * positions `bins[n]` (ascending; symexp_twohot: distributions.py:242-251): out[r] = sum(two_hot(target_r) * log_softmax). */
+int sd_twohot_logprob(const float* logits, int ld, const float* bins, int n, const float* target, int R, float* out,
+                      void* stream);
+/* Its gradient w.r.t. the logits: d_logits[r][j] = g[r] * (two_hot_j - softmax_j)  (g nullable = ones). */
+int sd_twohot_logprob_bwd(const float* logits, int ld, const float* bins, int n, const float* target, const float* g, int R,
+                          float* d_logits, int ld_d, void* stream);
+
 /* ReturnEMA.__call__ (networks.py:416-422): q05/q95 = torch.quantile(ret.flatten(), [0.05, 0.95]) (linear interpolation),
  * ema_vals[2] (device, in/out) <- alpha * q + (1 - alpha) * ema_vals, offset = ema_vals[0],
  * scale = max(ema_vals[1] - ema_vals[0], 1).  `ret` holds n device floats; offset / scale are device scalars (nullable). */

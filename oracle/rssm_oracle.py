@@ -197,6 +197,31 @@ def twohot_mode(logit, bins):
     return pair.sum(-1, keepdims=True)
 
 
+def twohot_logprob(logit, bins, target):
+    """TwoHot.log_prob (distributions.py:100-129) with squash = identity: returns (log_prob, mixed_target)."""
+    f = logit.dtype.type
+    b = bins.astype(logit.dtype)
+    n = b.size
+    t = np.asarray(target, logit.dtype).reshape(logit.shape[:-1])
+    below = np.clip((b <= t[..., None]).sum(-1) - 1, 0, n - 1)
+    above = np.clip(n - (b > t[..., None]).sum(-1), 0, n - 1)
+    equal = below == above
+    db = np.where(equal, f(1.0), np.abs(b[below] - t)).astype(logit.dtype)
+    da = np.where(equal, f(1.0), np.abs(b[above] - t)).astype(logit.dtype)
+    total = db + da
+    wb, wa = da / total, db / total
+    mixed = np.zeros_like(logit)
+    np.add.at(mixed, tuple(np.indices(below.shape)) + (below,), wb)
+    np.add.at(mixed, tuple(np.indices(above.shape)) + (above,), wa)
+    log_pred = log_softmax(logit)
+    return (mixed * log_pred).sum(-1), mixed
+
+
+def twohot_logprob_bwd(logit, mixed, g):
+    """d(sum_r g_r * log_prob_r)/d(logit) = g * (mixed - softmax) (mixed sums to one)."""
+    return np.asarray(g, logit.dtype)[..., None] * (mixed - softmax(logit))
+
+
 # --------------------------------------------------------------------------- RSSM
 def get_feat(stoch, deter):
     """RSSM.get_feat (rssm.py:211-217): [stoch.flat | deter]."""

@@ -79,6 +79,8 @@ _SIGS = {
     "sd_lambda_return": (C.c_int, [C.c_int, C.c_int] + [_P] * 5 + [C.c_float, C.c_float, _P, _P]),
     "sd_kl_loss": (C.c_int, [_P, C.c_int, _P, _P, C.c_float] + [_P] * 4 + [_P]),
     "sd_kl_loss_bwd": (C.c_int, [_P, C.c_int, _P, _P, C.c_float] + [_P] * 4 + [_P]),
+    "sd_twohot_logprob": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
+    "sd_twohot_logprob_bwd": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
     "sd_return_ema": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, _P, _P]),
     "sd_launch_count": (C.c_uint64, []),
 }

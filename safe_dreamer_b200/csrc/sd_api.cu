@@ -2352,6 +2352,27 @@ extern "C" int sd_kl_loss_bwd(sd_handle* h, int R, const float* post_logit, cons
   return SD_OK;
 }
 
+extern "C" int sd_twohot_logprob(const float* logits, int ld, const float* bins, int n, const float* target, int R,
+                                 float* out, void* stream) {
+  if (!logits || !bins || !target || !out || R < 1 || n < 1 || ld < n) return fail(SD_ERR_INVALID, "sd_twohot_logprob: bad argument");
+  launch_k((cudaStream_t)stream, sd::twohot_logprob_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, logits, ld, bins, n, target, R, out);
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_twohot_logprob: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+extern "C" int sd_twohot_logprob_bwd(const float* logits, int ld, const float* bins, int n, const float* target,
+                                     const float* g, int R, float* d_logits, int ld_d, void* stream) {
+  if (!logits || !bins || !target || !d_logits || R < 1 || n < 1 || ld < n || ld_d < n)
+    return fail(SD_ERR_INVALID, "sd_twohot_logprob_bwd: bad argument");
+  launch_k((cudaStream_t)stream, sd::twohot_logprob_bwd_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, logits, ld, bins, n, target,
+           g, R, d_logits, ld_d);
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_twohot_logprob_bwd: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+
 extern "C" int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale,
                              void* stream) {
   if (!ret || !ema_vals || n < 1) return fail(SD_ERR_INVALID, "sd_return_ema: null tensor or n < 1");

@@ -1045,6 +1045,81 @@ __global__ void twohot_mode_kernel(const float* __restrict__ logits, int ld, con
   if (lane == 0) out[warp] = acc;
 }
 
+// TwoHot.log_prob (distributions.py:100-129), forward and backward w.r.t. the logits.  One warp per row.
+//   below = #(bins <= t) - 1, above = n - #(bins > t), both clamped to [0, n-1]; equal -> weights (1, 1)/2, else the
+//   distances to the two neighbouring bins; log_prob = w_below * log_softmax[below] + w_above * log_softmax[above];
+//   d(log_prob)/d(logit_j) = mixed_j - softmax_j  (mixed = the two-hot target, sums to one).
+__device__ __forceinline__ void twohot_target(const float* __restrict__ bins, int n, float t, int lane, int& below, int& above,
+                                              float& wb, float& wa) {
+  int le = 0, gt = 0;
+  for (int j = lane; j < n; j += 32) {
+    const float bj = __ldg(bins + j);
+    le += (bj <= t) ? 1 : 0;
+    gt += (bj > t) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    le += __shfl_xor_sync(0xffffffffu, le, o);
+    gt += __shfl_xor_sync(0xffffffffu, gt, o);
+  }
+  below = min(max(le - 1, 0), n - 1);
+  above = min(max(n - gt, 0), n - 1);
+  float db = 1.f, da = 1.f;
+  if (below != above) {
+    db = fabsf(__ldg(bins + below) - t);
+    da = fabsf(__ldg(bins + above) - t);
+  }
+  const float total = db + da;
+  wb = da / total;
+  wa = db / total;
+}
+__global__ void twohot_logprob_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ bins, int n,
+                                      const float* __restrict__ target, int R, float* out) {
+  pdl_prologue();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float* lp = logits + (size_t)warp * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < n; j += 32) m = fmaxf(m, lp[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s += expf(lp[j] - m);
+  s = warp_sum(s);
+  const float lse = m + logf(s);
+  int below, above;
+  float wb, wa;
+  twohot_target(bins, n, target[warp], lane, below, above, wb, wa);
+  if (lane == 0) {
+    // mixed_target * log_pred summed over the bins: only `below` and `above` are non-zero (added in index order)
+    const float lb = wb * (lp[below] - lse), la = wa * (lp[above] - lse);
+    out[warp] = below == above ? (wb + wa) * (lp[below] - lse) : lb + la;
+  }
+}
+__global__ void twohot_logprob_bwd_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ bins, int n,
+                                          const float* __restrict__ target, const float* __restrict__ g, int R, float* d_logits,
+                                          int ld_d) {
+  pdl_prologue();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float* lp = logits + (size_t)warp * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < n; j += 32) m = fmaxf(m, lp[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s += expf(lp[j] - m);
+  s = warp_sum(s);
+  int below, above;
+  float wb, wa;
+  twohot_target(bins, n, target[warp], lane, below, above, wb, wa);
+  const float gr = g ? g[warp] : 1.f;
+  for (int j = lane; j < n; j += 32) {
+    float mixed = 0.f;
+    if (j == below) mixed += wb;
+    if (j == above) mixed += wa;
+    d_logits[(size_t)warp * ld_d + j] = gr * (mixed - expf(lp[j] - m) / s);
+  }
+}
+
 // cont head mean = sigmoid(logit) (distributions.py:238-239, Bernoulli.mean).
 __global__ void sigmoid_kernel(const float* __restrict__ in, int ld, float* out, int n) {
   pdl_prologue();

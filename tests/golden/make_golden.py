@@ -277,6 +277,34 @@ def run_kl_grad(rssm_mod):
     print("kl_grad ->", path, "rows clipped:", int((dyn.detach() <= 1.0).sum().item()), "of", post.shape[0])
 
 
+def twohot_inputs(bins):
+    """Seeded logits (R, 255), targets and upstream gradients for the TwoHot.log_prob goldens: generic targets, exact bin
+    hits, values beyond both ends of the bin range.  Shared with the tests (restated there)."""
+    rng = np.random.Generator(np.random.Philox(777))
+    R, n = 96, len(bins)
+    logits = (rng.standard_normal((R, n), dtype=np.float32) * np.float32(2.0)).astype(np.float32)
+    target = (rng.standard_normal(R, dtype=np.float32) * np.float32(30.0)).astype(np.float32)
+    target[:8] = bins[[0, 1, n // 2, n // 2 + 1, n - 2, n - 1, 17, 200]]          # exact hits
+    target[8:12] = np.array([-1e9, 1e9, bins[0] * 2, bins[-1] * 2], np.float32)   # out of range
+    target[12:16] = np.array([0.0, 1e-6, -1e-6, 0.5], np.float32)
+    g = rng.standard_normal(R, dtype=np.float32)
+    return logits, target.astype(np.float32), g
+
+
+def run_twohot(dists):
+    """TwoHot.log_prob (distributions.py:100-129) built by symexp_twohot (distributions.py:242-251), with autograd."""
+    bins = dists.symexp_twohot(torch.zeros(1, 255), 255).bins.numpy().copy()   # the reference's own bin positions (torch
+    np.testing.assert_allclose(O.twohot_bins(255), bins, rtol=4e-6)             # expm1; numpy's differs by ~1 ulp)
+    logits, target, g = twohot_inputs(bins)
+    lg = t(logits).requires_grad_(True)
+    dist = dists.symexp_twohot(lg, 255)
+    lp = dist.log_prob(t(target)[..., None])
+    (dlg,) = torch.autograd.grad((lp * t(g)).sum(), [lg])
+    path = os.path.join(ROOT, "tests", "golden", "twohot_logprob.npz")
+    np.savez_compressed(path, bins=bins, log_prob=lp.detach().numpy(), d_logits=dlg.numpy(), mode=dist.mode().detach().numpy())
+    print("twohot_logprob ->", path)
+
+
 def run_return_ema(networks):
     """ReturnEMA (networks.py:405-422), four consecutive calls per case (the buffer carries over)."""
     out = {}
@@ -298,6 +326,9 @@ def main():
     if "--return-ema-only" in sys.argv:
         run_return_ema(networks)
         return
+    if "--twohot-only" in sys.argv:
+        run_twohot(dists)
+        return
     if "--kl-grad-only" in sys.argv:
         run_kl_grad(rssm_mod)
         return
@@ -310,6 +341,7 @@ def main():
     run_case("base_onehot18", O.Cfg(A=18, act_kind="onehot"), 2, 3, 3, 3, rssm_mod, dists, networks, dreamer, False)
     run_return_ema(networks)
     run_kl_grad(rssm_mod)
+    run_twohot(dists)
 
 
 if __name__ == "__main__":
