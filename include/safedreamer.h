@@ -187,6 +187,27 @@ int sd_twohot_logprob_bwd(const float* logits, int ld, const float* bins, int n,
  * scale = max(ema_vals[1] - ema_vals[0], 1).  `ret` holds n device floats; offset / scale are device scalars (nullable). */
 int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale, void* stream);
 
+/* Fused multi-tensor optimiser step = clip_grad_agc_ (utils/optim/agc.py:15-60) followed by LaProp.step
+ * (utils/optim/laprop.py:46-118, amsgrad = centered = False) for `count` fp32 tensors in three launches.
+ *   AGC    : per tensor scale = 1 / max(||g||_2 / (clip * max(||p||_2, pmin)), 1), g *= scale (clip <= 0: no clipping);
+ *   LaProp : g' = g * inv_scale (GradScaler's unscale, 1 when unused); v = beta2 v + one_minus_beta2 g'^2;
+ *            m = beta1 m + lr_term * g' / (sqrt(v / bias_correction2) + eps), lr_term = (1 - beta1) * lr;
+ *            p -= step_size * m (step_size = 1 / bias_correction1); p -= weight_decay * p.
+ * The scalar state (exp_avg_lr_1/2 -> step_size, bias_correction2) stays on the host as in the reference.
+ * `table_dev` / `scratch_dev`: device buffers of sd_opt_table_bytes(count) / sd_opt_scratch_bytes(tensors, count) bytes.
+ * found_inf (device int, nullable): set to 1 and the update skipped when a gradient norm is not finite.
+ * mode 0 = AGC + LaProp, 1 = AGC only (scales the gradients in place, nothing else). */
+typedef struct sd_opt_tensor {
+  float* param; float* grad; float* exp_avg; float* exp_avg_sq;
+  int64_t numel;
+} sd_opt_tensor;
+size_t sd_opt_table_bytes(int count);
+size_t sd_opt_scratch_bytes(const sd_opt_tensor* tensors, int count);
+int sd_agc_laprop_step(const sd_opt_tensor* tensors, int count, int mode, float clip, float pmin, float inv_scale,
+                       float beta1, float beta2, float one_minus_beta2, float lr_term, float step_size,
+                       float bias_correction2, float eps, float weight_decay, void* table_dev, void* scratch_dev,
+                       int* found_inf, void* stream);
+
 /* Kernels launched by this library since process start (all handles): bench.py's gpu_launches. */
 uint64_t sd_launch_count(void);
 

@@ -606,3 +606,31 @@ def imagine_bwd(c: Cfg, P, PA, tapes, d_feats, d_actions):
         g_z = dz + dfeat[:, :SK]
         g_d = dd + dfeat[:, SK:]
     return g_z.reshape(N, c.S, c.K), g_d
+
+
+# --------------------------------------------------------------------------- optimiser (section 8f rank 3)
+def agc_scale(p, g, clip, pmin):
+    """clip_grad_agc_ (utils/optim/agc.py:15-60): per-tensor factor 1 / max(||g|| / (clip * max(||p||, pmin)), 1)."""
+    f = np.float32
+    pn = np.sqrt(np.sum(p.astype(np.float32) ** 2, dtype=np.float32))
+    gn = np.sqrt(np.sum(g.astype(np.float32) ** 2, dtype=np.float32))
+    upper = f(np.maximum(pn, f(pmin)) * f(clip))
+    return f(1.0) / np.maximum(f(gn / upper), f(1.0))
+
+
+def laprop_step(p, g, m, v, st, lr, beta1=0.9, beta2=0.999, eps=1e-15, wd=0.0):
+    """LaProp.step for one tensor (utils/optim/laprop.py:83-118, amsgrad = centered = False); st = dict(step, lr1, lr2).
+    Returns the new (p, m, v); the Python-float state is updated in place."""
+    f = np.float32
+    st["step"] += 1
+    st["lr1"] = st["lr1"] * beta1 + (1 - beta1) * lr
+    st["lr2"] = st["lr2"] * beta2 + (1 - beta2)
+    bc1 = st["lr1"] / lr if lr != 0.0 else 1.0
+    step_size, bc2 = 1 / bc1, st["lr2"]
+    v = (v * f(beta2) + (f(1 - beta2) * g) * g).astype(np.float32)
+    denom = (np.sqrt(v / f(bc2)) + f(eps)).astype(np.float32)
+    m = (m * f(beta1) + f((1 - beta1) * lr) * (g / denom).astype(np.float32)).astype(np.float32)
+    p = (p + f(-step_size) * m).astype(np.float32)
+    if wd != 0:
+        p = (p + f(-wd) * p).astype(np.float32)
+    return p, m, v

@@ -24,6 +24,11 @@ SD_FLAG_BF16, SD_FLAG_SAVE_TAPE, SD_FLAG_GRAPH, SD_FLAG_FEATS_FROM_IMAGINE = 1, 
 MOD_RSSM, MOD_ACTOR, MOD_REWARD, MOD_CONT, MOD_VALUE, MOD_SLOW_VALUE = range(6)
 
 
+class sd_opt_tensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64)]
+
+
 class sd_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("D", "U", "S", "K", "G", "E", "A", "obs_layers", "img_layers", "act_kind", "units",
@@ -81,6 +86,9 @@ _SIGS = {
     "sd_kl_loss_bwd": (C.c_int, [_P, C.c_int, _P, _P, C.c_float] + [_P] * 4 + [_P]),
     "sd_twohot_logprob": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
     "sd_twohot_logprob_bwd": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
+    "sd_opt_table_bytes": (C.c_size_t, [C.c_int]),
+    "sd_opt_scratch_bytes": (C.c_size_t, [C.POINTER(sd_opt_tensor), C.c_int]),
+    "sd_agc_laprop_step": (C.c_int, [C.POINTER(sd_opt_tensor), C.c_int, C.c_int] + [C.c_float] * 11 + [_P, _P, _P, _P]),
     "sd_return_ema": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, _P, _P]),
     "sd_launch_count": (C.c_uint64, []),
 }

@@ -2373,6 +2373,50 @@ extern "C" int sd_twohot_logprob_bwd(const float* logits, int ld, const float* b
   return SD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ fused optimiser
+static int opt_blocks(long long n) { return (int)((n + sd::kOptChunk - 1) / sd::kOptChunk); }
+extern "C" size_t sd_opt_table_bytes(int count) { return count > 0 ? (size_t)count * sizeof(sd::OptTensor) : 0; }
+extern "C" size_t sd_opt_scratch_bytes(const sd_opt_tensor* tensors, int count) {
+  if (!tensors || count <= 0) return 0;
+  size_t blocks = 0;
+  for (int i = 0; i < count; ++i) blocks += (size_t)opt_blocks(tensors[i].numel > 0 ? tensors[i].numel : 1);
+  return (2 * blocks + (size_t)count) * sizeof(float);   // chunk partials (p^2, g^2) + per-tensor scale
+}
+extern "C" int sd_agc_laprop_step(const sd_opt_tensor* tensors, int count, int mode, float clip, float pmin, float inv_scale,
+                                  float beta1, float beta2, float one_minus_beta2, float lr_term, float step_size,
+                                  float bias_correction2, float eps, float weight_decay, void* table_dev, void* scratch_dev,
+                                  int* found_inf, void* stream) {
+  if (!tensors || count < 1 || !table_dev || !scratch_dev) return fail(SD_ERR_INVALID, "sd_agc_laprop_step: null argument");
+  if (mode != 0 && mode != 1) return fail(SD_ERR_INVALID, "sd_agc_laprop_step: mode must be 0 or 1");
+  std::vector<sd::OptTensor> tbl((size_t)count);
+  int blocks = 0;
+  for (int i = 0; i < count; ++i) {
+    const sd_opt_tensor& t = tensors[i];
+    if (!t.param || !t.grad || t.numel < 1 || (mode == 0 && (!t.exp_avg || !t.exp_avg_sq)))
+      return fail(SD_ERR_INVALID, "sd_agc_laprop_step: tensor %d has a null pointer or no elements", i);
+    tbl[i].p = t.param; tbl[i].g = t.grad; tbl[i].m = t.exp_avg; tbl[i].v = t.exp_avg_sq; tbl[i].n = t.numel;
+    tbl[i].blk0 = blocks; tbl[i].nblk = opt_blocks(t.numel);
+    blocks += tbl[i].nblk;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // the table is a few KB: staged by the driver, asynchronous with respect to the host
+  cudaMemcpyAsync(table_dev, tbl.data(), tbl.size() * sizeof(sd::OptTensor), cudaMemcpyHostToDevice, st);
+  const sd::OptTensor* td = static_cast<const sd::OptTensor*>(table_dev);
+  float* partial = static_cast<float*>(scratch_dev);
+  float* scale = partial + 2 * (size_t)blocks;
+  launch_k(st, sd::opt_norm_kernel, dim3(blocks), dim3(256), 0, td, count, partial);
+  launch_k(st, sd::opt_finalize_kernel, dim3(1), dim3(256), 0, td, count, (const float*)partial, clip, pmin, scale, found_inf);
+  if (mode == 0)
+    launch_k(st, sd::opt_update_kernel, dim3(blocks), dim3(256), 0, td, count, (const float*)scale, (const int*)found_inf, inv_scale,
+             beta1, beta2, one_minus_beta2, lr_term, step_size, bias_correction2, eps, weight_decay, 1);
+  else
+    launch_k(st, sd::opt_scale_grads_kernel, dim3(blocks), dim3(256), 0, td, count, (const float*)scale);
+  g_launches += 3;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_agc_laprop_step: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+
 extern "C" int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale,
                              void* stream) {
   if (!ret || !ema_vals || n < 1) return fail(SD_ERR_INVALID, "sd_return_ema: null tensor or n < 1");

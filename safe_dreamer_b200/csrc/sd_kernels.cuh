@@ -1327,4 +1327,97 @@ __global__ void kl_grad_kernel(const float* __restrict__ post, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused multi-tensor AGC + LaProp step (utils/optim/agc.py:15-60, utils/optim/laprop.py:46-118).
+// The reference runs two foreach norms, four foreach ops and then a Python loop of ~8 kernels per tensor; here the whole
+// update of every tensor is three launches over a device-resident tensor table:
+//   opt_norm_kernel     per 8192-element chunk: sum p^2, sum g^2                        (fixed tree => deterministic)
+//   opt_finalize_kernel per tensor: sums the chunk partials in order, scale = 1 / max(||g|| / (clip * max(||p||, pmin)), 1)
+//                       (1 when clip <= 0), raises found_inf when a gradient norm is not finite
+//   opt_update_kernel   g' = g * scale * inv_scale;  v = beta2 v + (1 - beta2) g'^2;  m = beta1 m + (1 - beta1) lr g' / (sqrt(v / bc2) + eps);
+//                       p -= step_size * m  (then p -= wd * p); skipped entirely when found_inf is set
+// ------------------------------------------------------------------------------------------------
+struct OptTensor {
+  float* p; float* g; float* m; float* v;
+  long long n;
+  int blk0, nblk;
+};
+constexpr int kOptChunk = 8192;
+__device__ __forceinline__ int opt_find(const OptTensor* __restrict__ t, int count, int b) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (t[mid].blk0 <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(256) opt_norm_kernel(const OptTensor* __restrict__ t, int count, float* partial) {
+  pdl_prologue();
+  __shared__ float sh[32];
+  const int ti = opt_find(t, count, blockIdx.x);
+  const OptTensor e = t[ti];
+  const long long i0 = (long long)(blockIdx.x - e.blk0) * kOptChunk;
+  const long long i1 = min(e.n, i0 + kOptChunk);
+  float sp = 0.f, sg = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const float pv = e.p[i], gv = e.g[i];
+    sp = fmaf(pv, pv, sp);
+    sg = fmaf(gv, gv, sg);
+  }
+  sp = block_sum(sp, sh);
+  sg = block_sum(sg, sh);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sp; partial[2 * blockIdx.x + 1] = sg; }
+}
+__global__ void __launch_bounds__(256) opt_finalize_kernel(const OptTensor* __restrict__ t, int count, const float* __restrict__ partial,
+                                                           float clip, float pmin, float* scale, int* found_inf) {
+  pdl_prologue();
+  for (int ti = threadIdx.x; ti < count; ti += 256) {
+    const OptTensor e = t[ti];
+    float sp = 0.f, sg = 0.f;
+    for (int b = 0; b < e.nblk; ++b) { sp += partial[2 * (e.blk0 + b)]; sg += partial[2 * (e.blk0 + b) + 1]; }
+    float s = 1.f;
+    if (clip > 0.f) {
+      const float upper = fmaxf(sqrtf(sp), pmin) * clip;
+      s = 1.f / fmaxf(sqrtf(sg) / upper, 1.f);
+    }
+    scale[ti] = s;
+    if (found_inf && !isfinite(sg)) atomicOr(found_inf, 1);
+  }
+}
+__global__ void __launch_bounds__(256) opt_update_kernel(const OptTensor* __restrict__ t, int count, const float* __restrict__ scale,
+                                                         const int* __restrict__ found_inf, float inv_scale, float beta1, float beta2,
+                                                         float omb2, float lr_term, float step_size, float bc2, float eps, float wd,
+                                                         int write_grads) {
+  pdl_prologue();
+  if (found_inf && *found_inf) return;   // GradScaler semantics: a non-finite gradient skips the whole step
+  const int ti = opt_find(t, count, blockIdx.x);
+  const OptTensor e = t[ti];
+  const float gs = scale[ti];
+  const long long i0 = (long long)(blockIdx.x - e.blk0) * kOptChunk;
+  const long long i1 = min(e.n, i0 + kOptChunk);
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    float g = __fmul_rn(e.g[i], gs);
+    if (write_grads) e.g[i] = g;                    // clip_grad_agc_ scales p.grad in place
+    g = __fmul_rn(g, inv_scale);
+    const float v = __fadd_rn(__fmul_rn(e.v[i], beta2), __fmul_rn(__fmul_rn(omb2, g), g));
+    e.v[i] = v;
+    const float denom = __fadd_rn(sqrtf(v / bc2), eps);
+    const float s = g / denom;
+    const float m = __fadd_rn(__fmul_rn(e.m[i], beta1), __fmul_rn(lr_term, s));
+    e.m[i] = m;
+    float pv = __fadd_rn(e.p[i], -__fmul_rn(step_size, m));
+    if (wd != 0.f) pv = __fadd_rn(pv, -__fmul_rn(wd, pv));
+    e.p[i] = pv;
+  }
+}
+__global__ void __launch_bounds__(256) opt_scale_grads_kernel(const OptTensor* __restrict__ t, int count, const float* __restrict__ scale) {
+  pdl_prologue();
+  const int ti = opt_find(t, count, blockIdx.x);
+  const OptTensor e = t[ti];
+  const float gs = scale[ti];
+  const long long i0 = (long long)(blockIdx.x - e.blk0) * kOptChunk;
+  const long long i1 = min(e.n, i0 + kOptChunk);
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) e.g[i] = __fmul_rn(e.g[i], gs);
+}
+
 }  // namespace sd

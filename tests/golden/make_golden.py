@@ -305,6 +305,47 @@ def run_twohot(dists):
     print("twohot_logprob ->", path)
 
 
+OPT_SHAPES = [(48, 200), (256,), (8, 12, 8), (12, 64), (1,), (255, 16), (3, 5, 7)]
+
+
+def optim_inputs(step):
+    """Seeded parameters (step < 0) / gradients of step `step` for the optimiser goldens; tensor 1's gradients are large
+    (AGC clips), tensor 4 is a single element, tensor 6 has a tiny parameter norm (pmin floor).  Shared with the tests."""
+    rng = np.random.Generator(np.random.Philox(31337 + (step if step >= 0 else 1000)))
+    out = []
+    for i, shp in enumerate(OPT_SHAPES):
+        x = rng.standard_normal(shp, dtype=np.float32)
+        if step < 0:
+            x = x * np.float32(1e-5 if i == 6 else 0.05)
+        else:
+            x = x * np.float32([1e-3, 5.0, 1e-2, 1e-4, 0.3, 2e-2, 1e-3][i])
+        out.append(x.astype(np.float32))
+    return out
+
+
+def run_optim():
+    """clip_grad_agc_ (utils/optim/agc.py) + LaProp.step (utils/optim/laprop.py) for three steps on seeded tensors."""
+    import utils.optim.laprop as laprop
+    import utils.optim.agc as agc
+    params = [torch.nn.Parameter(t(x.copy())) for x in optim_inputs(-1)]
+    opt = laprop.LaProp(params, lr=4e-5, betas=(0.9, 0.999), eps=1e-20)
+    out = {}
+    for step in range(3):
+        for p_, g_ in zip(params, optim_inputs(step)):
+            p_.grad = t(g_.copy())
+        agc.clip_grad_agc_(params, 0.3, 1e-3, foreach=True)
+        for i, p_ in enumerate(params):
+            out[f"s{step}_g{i}"] = p_.grad.detach().numpy().copy()
+        opt.step()
+        for i, p_ in enumerate(params):
+            out[f"s{step}_p{i}"] = p_.detach().numpy().copy()
+            out[f"s{step}_m{i}"] = opt.state[p_]["exp_avg"].numpy().copy()
+            out[f"s{step}_v{i}"] = opt.state[p_]["exp_avg_sq"].numpy().copy()
+    path = os.path.join(ROOT, "tests", "golden", "optim.npz")
+    np.savez_compressed(path, **out)
+    print("optim ->", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
+
+
 def run_return_ema(networks):
     """ReturnEMA (networks.py:405-422), four consecutive calls per case (the buffer carries over)."""
     out = {}
@@ -326,6 +367,9 @@ def main():
     if "--return-ema-only" in sys.argv:
         run_return_ema(networks)
         return
+    if "--optim-only" in sys.argv:
+        run_optim()
+        return
     if "--twohot-only" in sys.argv:
         run_twohot(dists)
         return
@@ -342,6 +386,7 @@ def main():
     run_return_ema(networks)
     run_kl_grad(rssm_mod)
     run_twohot(dists)
+    run_optim()
 
 
 if __name__ == "__main__":
