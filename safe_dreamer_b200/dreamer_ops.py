@@ -66,3 +66,31 @@ def heads_lambda(rssm, imag_feat, horizon=333, lamb=0.95, slow=True):
 def lambda_return(rssm, last, term, reward, value, boot, disc, lamb):
     eng = rssm._get_engine(1, 1)
     return eng.lambda_return(last, term, reward, value, boot, disc, lamb)
+
+
+@torch.no_grad()
+def act(rssm, embed, state, is_first, eval=False, u=None, act_noise=None):
+    """Dreamer.act after the encoder (dreamer.py:345-357): obs_step on the previous latent, then the frozen actor on the new
+    feat.  state = (stoch (B,S,K), deter (B,D), prev_action (B,A)); returns action (B,A) and the new (stoch, deter, action).
+    Two library calls (the single-step persistent posterior kernel and the actor), each one cached CUDA graph when
+    `rssm.use_graph`.  eval=True takes the distribution's mode: zero normal noise (tanh(mean)) for the bounded-normal actor,
+    constant uniforms (argmax of the logits) for the one-hot actor."""
+    prev_stoch, prev_deter, prev_action = state
+    B = prev_deter.shape[0]
+    dev = prev_deter.device
+    eng = rssm._get_engine(B, 1)
+    if u is None:
+        u = rssm._uniform(B, 1, rssm._stoch, rssm._discrete)
+    stoch, deter, _ = eng.observe(embed.reshape(B, 1, -1), prev_action.reshape(B, 1, -1), prev_stoch, prev_deter,
+                                  is_first.reshape(B, 1), u.reshape(B, 1, rssm._stoch, rssm._discrete), flags=rssm._flags() & ~1)
+    stoch, deter = stoch[:, 0], deter[:, 0]
+    if act_noise is None:
+        if eng.cfg.act_kind == 0:
+            act_noise = torch.zeros(B, 1, rssm._act_dim, device=dev) if eval else torch.randn(B, 1, rssm._act_dim, device=dev)
+        else:
+            act_noise = (torch.full((B, 1, rssm._act_dim), 0.5, device=dev) if eval
+                         else torch.rand(B, 1, rssm._act_dim, device=dev).clamp_(_U_LO, 1 - _U_LO))
+    iu = torch.full((B, 1, rssm._stoch, rssm._discrete), 0.5, device=dev)   # the prior sample of a 1-step rollout is never drawn
+    _, actions = eng.imagine(stoch, deter, iu, act_noise.reshape(B, 1, -1), 1, flags=rssm._flags() & ~1)
+    action = actions[:, 0]
+    return action, (stoch, deter, action)

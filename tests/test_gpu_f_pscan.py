@@ -93,3 +93,52 @@ def test_pscan_tape_feeds_backward(base):
             continue
         gn = float(np.sqrt((ref.astype(np.float64) ** 2).sum()))
         np.testing.assert_allclose(_np(wg[name]), ref, rtol=3e-3, atol=3e-5 * max(1.0, gn), err_msg=name)
+
+
+def test_act_step_matches_oracle():
+    """dreamer_ops.act == Dreamer.act after the encoder (dreamer.py:345-357): obs_step + frozen actor, sample and mode."""
+    from types import SimpleNamespace as NS
+    from safe_dreamer_b200 import dreamer_ops
+    from safe_dreamer_b200.networks import MLPHead
+    from safe_dreamer_b200.rssm import RSSM
+    for kind in ("cont", "onehot"):
+        c = O.Cfg() if kind == "cont" else O.Cfg(A=18, act_kind="onehot")
+        P = O.init_params(c, seed=0)
+        cfg = NS(stoch=c.S, deter=c.D, hidden=c.U, discrete=c.K, act="SiLU", unimix_ratio=c.unimix, initial="learned",
+                 device="cuda", obs_layers=c.obs_layers, img_layers=c.img_layers, dyn_layers=1, blocks=c.G)
+        rssm = RSSM(cfg, c.E, c.A).cuda()
+        rssm.load_state_dict({k: cu(v) for k, v in P["rssm"].items()})
+        actor = MLPHead("actor", c.actor_layers, c.units, c.F, 2 * c.A if kind == "cont" else c.A).cuda()
+        actor.load_state_dict({k: cu(v) for k, v in P["actor"].items()})
+        dreamer_ops.attach_heads(rssm, actor=actor, act_kind=kind)
+        B = 6
+        rng = np.random.Generator(np.random.Philox(91))
+        s0 = np.eye(c.K, dtype=np.float32)[rng.integers(0, c.K, size=(B, c.S))]
+        d0 = np.tanh(rng.standard_normal((B, c.D), dtype=np.float32)).astype(np.float32)
+        a0 = (rng.random((B, c.A), dtype=np.float32) * 2 - 1).astype(np.float32) if kind == "cont" else \
+            np.eye(c.A, dtype=np.float32)[rng.integers(0, c.A, size=B)]
+        emb = rng.standard_normal((B, c.E), dtype=np.float32)
+        first = np.array([True, False, False, True, False, False])
+        u = O.clamp_u(rng.random((B, c.S, c.K), dtype=np.float32))
+        noise = rng.standard_normal((B, c.A), dtype=np.float32) if kind == "cont" else O.clamp_u(rng.random((B, c.A), dtype=np.float32))
+        st_o, dt_o, lg_o, idx_o = O.obs_step(c, P["rssm"], s0, d0, a0, emb, first, u)
+        act_o = O.actor_sample(c, P["actor"], O.get_feat(st_o, dt_o), noise)
+        action, (st, dt, pa) = dreamer_ops.act(rssm, cu(emb), (cu(s0), cu(d0), cu(a0)), cu(first), u=cu(u), act_noise=cu(noise))
+        torch.cuda.synchronize()
+        assert_indices(_np(st).argmax(-1), idx_o, perturbed_scores(lg_o, u, c.unimix), 1e-4, 5e-3, f"act {kind}")
+        np.testing.assert_allclose(_np(dt), dt_o, atol=5e-5, rtol=0)
+        if (_np(st).argmax(-1) == idx_o).all():
+            if kind == "cont":
+                np.testing.assert_allclose(_np(action), act_o, atol=1e-4, rtol=0)
+            else:
+                assert (_np(action).argmax(-1) == act_o.argmax(-1)).mean() >= 0.8 and np.all(_np(action).sum(-1) == 1.0)
+        # eval: the mode of the action distribution
+        mode, _ = dreamer_ops.act(rssm, cu(emb), (cu(s0), cu(d0), cu(a0)), cu(first), eval=True, u=cu(u))
+        out_o = O.head_logits(P["actor"], "actor", c.actor_layers, O.get_feat(st_o, dt_o))
+        if (_np(st).argmax(-1) == idx_o).all():
+            if kind == "cont":
+                np.testing.assert_allclose(_np(mode), np.tanh(out_o[:, :c.A]), atol=1e-4, rtol=0)
+            else:
+                gap = np.sort(out_o, -1)
+                sure = (gap[:, -1] - gap[:, -2]) > 1e-3
+                assert (_np(mode).argmax(-1)[sure] == out_o.argmax(-1)[sure]).all()
