@@ -187,6 +187,14 @@ int sd_twohot_logprob_bwd(const float* logits, int ld, const float* bins, int n,
  * scale = max(ema_vals[1] - ema_vals[0], 1).  `ret` holds n device floats; offset / scale are device scalars (nullable). */
 int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale, void* stream);
 
+/* Barlow-twins redundancy loss of dreamer.py:525-532 between projected latents x1 (N, E) and (detached) embeddings x2 (N, E):
+ * columns standardised with the unbiased std (+1e-8), c = x1n^T x2n / N, loss = sum_i (c_ii - 1)^2 + lambd * sum_{i!=j} c_ij^2.
+ * Writes the scalar loss and (nullable) d(loss)/d(x1) (N, E).  E must be a multiple of 16, N >= 2.  `scratch`: device buffer
+ * of sd_barlow_scratch_bytes(N, E) bytes.  fp32 throughout (3xTF32 tensor tiles for the two contractions). */
+size_t sd_barlow_scratch_bytes(int N, int E);
+int sd_barlow_loss(const float* x1, const float* x2, int N, int E, float lambd, float* loss, float* d_x1, void* scratch,
+                   void* stream);
+
 /* Fused multi-tensor optimiser step = clip_grad_agc_ (utils/optim/agc.py:15-60) followed by LaProp.step
  * (utils/optim/laprop.py:46-118, amsgrad = centered = False) for `count` fp32 tensors in three launches.
  *   AGC    : per tensor scale = 1 / max(||g||_2 / (clip * max(||p||_2, pmin)), 1), g *= scale (clip <= 0: no clipping);

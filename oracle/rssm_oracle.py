@@ -634,3 +634,22 @@ def laprop_step(p, g, m, v, st, lr, beta1=0.9, beta2=0.999, eps=1e-15, wd=0.0):
     if wd != 0:
         p = (p + f(-wd) * p).astype(np.float32)
     return p, m, v
+
+
+# --------------------------------------------------------------------------- Barlow loss (section 8f rank 2)
+def barlow_loss(x1, x2, lambd):
+    """dreamer.py:525-532: returns (loss, d loss / d x1); x2 carries no gradient (detached at :522)."""
+    f = x1.dtype.type
+    n, e = x1.shape
+    mu1, mu2 = x1.mean(0), x2.mean(0)
+    s1 = x1.std(0, ddof=1) + f(1e-8)
+    s2 = x2.std(0, ddof=1) + f(1e-8)
+    x1n, x2n = (x1 - mu1) / s1, (x2 - mu2) / s2
+    c = (x1n.T @ x2n) / f(n)
+    eye = np.eye(e, dtype=bool)
+    loss = ((np.diag(c) - f(1.0)) ** 2).sum() + f(lambd) * (c[~eye] ** 2).sum()
+    dc = np.where(eye, f(2.0) * (c - f(1.0)), f(2.0) * f(lambd) * c).astype(x1.dtype)
+    g = (x2n @ dc.T) / f(n)                                            # d loss / d x1n
+    sigma = x1.std(0, ddof=1)
+    dx = (g - g.mean(0)) / s1 - x1n * ((g * x1n).sum(0) / (f(n - 1) * sigma))
+    return loss, dx.astype(x1.dtype)

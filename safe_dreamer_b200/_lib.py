@@ -86,6 +86,8 @@ _SIGS = {
     "sd_kl_loss_bwd": (C.c_int, [_P, C.c_int, _P, _P, C.c_float] + [_P] * 4 + [_P]),
     "sd_twohot_logprob": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
     "sd_twohot_logprob_bwd": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P]),
+    "sd_barlow_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "sd_barlow_loss": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
     "sd_opt_table_bytes": (C.c_size_t, [C.c_int]),
     "sd_opt_scratch_bytes": (C.c_size_t, [C.POINTER(sd_opt_tensor), C.c_int]),
     "sd_agc_laprop_step": (C.c_int, [C.POINTER(sd_opt_tensor), C.c_int, C.c_int] + [C.c_float] * 11 + [_P, _P, _P, _P]),

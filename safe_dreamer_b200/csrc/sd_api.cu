@@ -2373,6 +2373,61 @@ extern "C" int sd_twohot_logprob_bwd(const float* logits, int ld, const float* b
   return SD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ Barlow loss
+extern "C" size_t sd_barlow_scratch_bytes(int N, int E) {
+  if (N < 2 || E < 1) return 0;
+  const size_t ne = (size_t)N * E, ee = (size_t)E * E;
+  return (4 * (size_t)E + 3 * ne + 2 * ee + (ee + 255) / 256 + 64) * sizeof(float);
+}
+extern "C" int sd_barlow_loss(const float* x1, const float* x2, int N, int E, float lambd, float* loss, float* d_x1,
+                              void* scratch, void* stream) {
+  if (!x1 || !x2 || !loss || !scratch) return fail(SD_ERR_INVALID, "sd_barlow_loss: null argument");
+  if (N < 2 || E < 16 || (E % 16) != 0 || (N % 4) != 0)
+    return fail(SD_ERR_INVALID, "sd_barlow_loss: need N >= 2, N %% 4 == 0 and E a multiple of 16 (got N=%d, E=%d)", N, E);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ne = (size_t)N * E, ee = (size_t)E * E;
+  float* f = static_cast<float*>(scratch);
+  float *mean1 = f, *std1 = f + E, *mean2 = f + 2 * E, *std2 = f + 3 * E;
+  float* x1nT = f + 4 * (size_t)E;     // (E, N)
+  float* x2n = x1nT + ne;              // (N, E)
+  float* gx = x2n + ne;                // (N, E): d(loss)/d(x1n)
+  float* craw = gx + ne;               // (E, E)
+  float* dcT = craw + ee;              // (E, E), transposed dL/d(craw)
+  float* partial = dcT + ee;
+  const int nblk = (int)((ee + 255) / 256);
+  const dim3 cb(32, 32), cgrid((E + 31) / 32);
+  launch_k(st, sd::col_meanstd_kernel, cgrid, cb, 0, x1, E, N, E, mean1, std1);
+  launch_k(st, sd::col_meanstd_kernel, cgrid, cb, 0, x2, E, N, E, mean2, std2);
+  const dim3 tgrid((E + 31) / 32, (N + 31) / 32);
+  launch_k(st, sd::standardise_kernel, tgrid, cb, 0, x1, E, N, E, (const float*)mean1, (const float*)std1, (float*)nullptr, x1nT);
+  launch_k(st, sd::standardise_kernel, tgrid, cb, 0, x2, E, N, E, (const float*)mean2, (const float*)std2, x2n, (float*)nullptr);
+  {
+    sd::GemmBatch gb;
+    memset(&gb, 0, sizeof(gb));
+    gb.R = E;
+    sd::GemmP& p = gb.p[gb.count++];
+    p.A = x1nT; p.lda = N; p.K1 = N; p.K = N; p.Wt = x2n; p.ldw = E; p.C = craw; p.ldc = E; p.N = E;
+    launch_gemm_f32(st, gb, E, N, E);
+  }
+  launch_k(st, sd::barlow_loss_kernel, dim3(nblk), dim3(256), 0, (const float*)craw, E, N, lambd, partial, dcT);
+  launch_k(st, sd::sum_in_order_kernel, dim3(1), dim3(32), 0, (const float*)partial, nblk, loss);
+  int launches = 7;
+  if (d_x1) {
+    sd::GemmBatch gb;
+    memset(&gb, 0, sizeof(gb));
+    gb.R = N;
+    sd::GemmP& p = gb.p[gb.count++];
+    p.A = x2n; p.lda = E; p.K1 = E; p.K = E; p.Wt = dcT; p.ldw = E; p.C = gx; p.ldc = E; p.N = E;
+    launch_gemm_f32(st, gb, E, E, N);
+    launch_k(st, sd::standardise_bwd_kernel, cgrid, cb, 0, (const float*)gx, (const float*)x1nT, (const float*)std1, N, E, d_x1, E);
+    launches += 2;
+  }
+  g_launches += launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_barlow_loss: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ fused optimiser
 static int opt_blocks(long long n) { return (int)((n + sd::kOptChunk - 1) / sd::kOptChunk); }
 extern "C" size_t sd_opt_table_bytes(int count) { return count > 0 ? (size_t)count * sizeof(sd::OptTensor) : 0; }

@@ -1420,4 +1420,115 @@ __global__ void __launch_bounds__(256) opt_scale_grads_kernel(const OptTensor* _
   for (long long i = i0 + threadIdx.x; i < i1; i += 256) e.g[i] = __fmul_rn(e.g[i], gs);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Barlow-twins redundancy loss between projected latents x1 (N, E) and detached embeddings x2 (N, E)
+// (dreamer.py:525-532): columns standardised with the unbiased std (+1e-8), c = x1n^T x2n / N,
+// loss = sum_i (c_ii - 1)^2 + lambd * sum_{i != j} c_ij^2, and its gradient w.r.t. x1.
+// The two E x E x N contractions run on the fp32 skinny GEMM above (3xTF32 tensor tiles); these kernels do the column
+// statistics, the standardisation (writing x1n transposed so that both GEMM operands are K-major), the loss / dL/dc
+// epilogue and the backward of the standardisation.  All reductions have a fixed order.
+// ------------------------------------------------------------------------------------------------
+// mean / unbiased std of every column of x (R x W); block = 32 columns x 32 row lanes (same shape as colsum_kernel).
+__global__ void __launch_bounds__(1024) col_meanstd_kernel(const float* __restrict__ x, int ld, int R, int W, float* mean, float* stdv) {
+  pdl_prologue();
+  __shared__ float sh[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < W)
+    for (int r = threadIdx.y; r < R; r += 32) s += x[(size_t)r * ld + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  float mu = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mu += sh[j][threadIdx.x];
+  mu /= (float)R;
+  __syncthreads();
+  float q = 0.f;
+  if (c < W)
+    for (int r = threadIdx.y; r < R; r += 32) { const float d = x[(size_t)r * ld + c] - mu; q = fmaf(d, d, q); }
+  sh[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < W) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += sh[j][threadIdx.x];
+    mean[c] = mu;
+    stdv[c] = sqrtf(t / (float)(R - 1));
+  }
+}
+// xn = (x - mean) / (std + 1e-8): row-major copy xn (nullable) and transposed copy xnT (W x R, nullable) through a 32x32 tile.
+__global__ void __launch_bounds__(1024) standardise_kernel(const float* __restrict__ x, int ld, int R, int W,
+                                                           const float* __restrict__ mean, const float* __restrict__ stdv,
+                                                           float* xn, float* xnT) {
+  pdl_prologue();
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 32 + threadIdx.y;
+  float v = 0.f;
+  if (c < W && r < R) {
+    v = (x[(size_t)r * ld + c] - mean[c]) / (stdv[c] + 1e-8f);
+    if (xn) xn[(size_t)r * W + c] = v;
+  }
+  tile[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  const int ct = blockIdx.x * 32 + threadIdx.y, rt = blockIdx.y * 32 + threadIdx.x;
+  if (xnT && ct < W && rt < R) xnT[(size_t)ct * R + rt] = tile[threadIdx.x][threadIdx.y];
+}
+// craw = x1n^T x2n (E x E).  c = craw / N; per-block partial sums of the loss; dcT[j][i] = dL/d(craw)[i][j].
+__global__ void __launch_bounds__(256) barlow_loss_kernel(const float* __restrict__ craw, int E, int N, float lambd, float* partial,
+                                                          float* dcT) {
+  pdl_prologue();
+  __shared__ float sh[32];
+  const long long idx = blockIdx.x * 256ll + threadIdx.x;
+  float term = 0.f;
+  if (idx < (long long)E * E) {
+    const int i = (int)(idx / E), j = (int)(idx - (long long)i * E);
+    const float c = craw[idx] / (float)N;
+    float g;
+    if (i == j) { term = (c - 1.f) * (c - 1.f); g = 2.f * (c - 1.f); }
+    else { term = lambd * (c * c); g = 2.f * lambd * c; }
+    dcT[(size_t)j * E + i] = g / (float)N;
+  }
+  term = block_sum(term, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = term;
+}
+__global__ void sum_in_order_kernel(const float* __restrict__ partial, int n, float* out) {
+  pdl_prologue();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    *out = s;
+  }
+}
+// Backward of the standardisation: dx = (g - mean(g)) / s - xn * sum(g * xn) / ((N - 1) * s) * (s - 1e-8) ... written with
+// sigma = std, s = sigma + 1e-8:  dx_r = (g_r - gbar) / s - (x_r - mu) * sum_q(g_q xn_q) / ((N - 1) sigma s).
+// Column reductions as in col_meanstd_kernel; g = d(loss)/d(xn) (R x W), xnT is the transposed standardised copy.
+__global__ void __launch_bounds__(1024) standardise_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xnT,
+                                                               const float* __restrict__ stdv, int R, int W, float* dx, int ld_dx) {
+  pdl_prologue();
+  __shared__ float sh[32][33];
+  __shared__ float sh2[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float sg = 0.f, sgx = 0.f;
+  if (c < W)
+    for (int r = threadIdx.y; r < R; r += 32) {
+      const float gv = g[(size_t)r * W + c];
+      sg += gv;
+      sgx = fmaf(gv, xnT[(size_t)c * R + r], sgx);
+    }
+  sh[threadIdx.y][threadIdx.x] = sg;
+  sh2[threadIdx.y][threadIdx.x] = sgx;
+  __syncthreads();
+  float tg = 0.f, tgx = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { tg += sh[j][threadIdx.x]; tgx += sh2[j][threadIdx.x]; }
+  if (c < W) {
+    const float sigma = stdv[c], s = sigma + 1e-8f;
+    const float gbar = tg / (float)R;
+    // (x_r - mu) = xn_r * s
+    const float k2 = tgx / ((float)(R - 1) * sigma);
+    for (int r = threadIdx.y; r < R; r += 32)
+      dx[(size_t)r * ld_dx + c] = (g[(size_t)r * W + c] - gbar) / s - xnT[(size_t)c * R + r] * k2;
+  }
+}
+
 }  // namespace sd

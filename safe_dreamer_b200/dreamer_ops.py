@@ -94,3 +94,36 @@ def act(rssm, embed, state, is_first, eval=False, u=None, act_noise=None):
     _, actions = eng.imagine(stoch, deter, iu, act_noise.reshape(B, 1, -1), 1, flags=rssm._flags() & ~1)
     action = actions[:, 0]
     return action, (stoch, deter, action)
+
+
+class _BarlowFn(torch.autograd.Function):
+    """sd_barlow_loss: loss and d(loss)/d(x1) in one pass (x2 is detached, as at dreamer.py:522)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, lambd):
+        from . import _lib
+        lib = _lib.load()
+        N, E = x1.shape
+        a, b = x1.float().contiguous(), x2.detach().float().contiguous()
+        scratch = torch.empty(int(lib.sd_barlow_scratch_bytes(N, E)), dtype=torch.uint8, device=a.device)
+        loss = torch.empty((), dtype=torch.float32, device=a.device)
+        need = ctx.needs_input_grad[0]
+        d_x1 = torch.empty_like(a) if need else None
+        stream = torch.cuda.current_stream(a.device).cuda_stream
+        _lib.check(lib.sd_barlow_loss(a.data_ptr(), b.data_ptr(), N, E, float(lambd), loss.data_ptr(),
+                                      d_x1.data_ptr() if need else None, scratch.data_ptr(), stream), "sd_barlow_loss")
+        if need:
+            ctx.save_for_backward(d_x1)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_x1,) = ctx.saved_tensors
+        return d_x1 * g, None, None
+
+
+def barlow_loss(x1, x2, lambd):
+    """dreamer.py:525-532: Barlow-twins loss between projected latents x1 (B*T, E) and detached embeddings x2 (B*T, E)."""
+    if not x1.is_cuda:
+        raise RuntimeError("barlow_loss: expected CUDA tensors (no CPU implementation)")
+    return _BarlowFn.apply(x1, x2, lambd)

@@ -346,6 +346,38 @@ def run_optim():
     print("optim ->", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
 
 
+def barlow_inputs():
+    """Seeded projected latents x1 / embeddings x2 (N, E) for the Barlow goldens (correlated, so diag(c) is not ~0)."""
+    rng = np.random.Generator(np.random.Philox(2718))
+    N, E = 64, 48
+    z = rng.standard_normal((N, E), dtype=np.float32)
+    x1 = (z * np.float32(1.5) + np.float32(0.3) * rng.standard_normal((N, E), dtype=np.float32) + np.float32(0.7)).astype(np.float32)
+    x2 = (z @ (np.eye(E, dtype=np.float32) + np.float32(0.1) * rng.standard_normal((E, E), dtype=np.float32))
+          + np.float32(0.5) * rng.standard_normal((N, E), dtype=np.float32)).astype(np.float32)
+    return x1, x2
+
+
+def run_barlow():
+    """The Barlow block of Dreamer._cal_grad is inline code (dreamer.py:525-532), not a callable: the seven statements are
+    executed here verbatim on seeded tensors with torch autograd (x2 detached as at :522)."""
+    x1_np, x2_np = barlow_inputs()
+    x1 = t(x1_np).requires_grad_(True)
+    x2 = t(x2_np).detach()
+    B_T = x1.shape[0]
+    barlow_lambd = 5e-4                                   # configs/base.yaml:214
+    x1_norm = (x1 - x1.mean(0)) / (x1.std(0) + 1e-8)      # dreamer.py:525
+    x2_norm = (x2 - x2.mean(0)) / (x2.std(0) + 1e-8)      # :526
+    c = torch.mm(x1_norm.T, x2_norm) / B_T                # :528
+    invariance_loss = (torch.diagonal(c) - 1.0).pow(2).sum()                      # :529
+    off_diag_mask = ~torch.eye(x1.shape[-1], dtype=torch.bool, device=x1.device)  # :530
+    redundancy_loss = c[off_diag_mask].pow(2).sum()                               # :531
+    loss = invariance_loss + barlow_lambd * redundancy_loss                       # :532
+    (dx1,) = torch.autograd.grad(loss, [x1])
+    path = os.path.join(ROOT, "tests", "golden", "barlow.npz")
+    np.savez_compressed(path, loss=np.float32(loss.item()), d_x1=dx1.numpy(), lambd=np.float32(barlow_lambd))
+    print("barlow ->", path, "loss", float(loss))
+
+
 def run_return_ema(networks):
     """ReturnEMA (networks.py:405-422), four consecutive calls per case (the buffer carries over)."""
     out = {}
@@ -367,6 +399,9 @@ def main():
     if "--return-ema-only" in sys.argv:
         run_return_ema(networks)
         return
+    if "--barlow-only" in sys.argv:
+        run_barlow()
+        return
     if "--optim-only" in sys.argv:
         run_optim()
         return
@@ -387,6 +422,7 @@ def main():
     run_kl_grad(rssm_mod)
     run_twohot(dists)
     run_optim()
+    run_barlow()
 
 
 if __name__ == "__main__":
