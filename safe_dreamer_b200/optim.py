@@ -73,16 +73,14 @@ class LaProp(Optimizer):
                  agc=None, pmin=1e-3):
         if amsgrad or centered:
             raise NotImplementedError("LaProp(amsgrad/centered): not used by the reference configs, not implemented in CUDA")
-        if not 0.0 <= lr:
-            raise ValueError(f"Invalid learning rate: {lr}")
-        if not 0.0 <= eps:
-            raise ValueError(f"Invalid epsilon value: {eps}")
-        if not 0.0 <= betas[0] < 1.0:
-            raise ValueError(f"Invalid beta parameter at index 0: {betas[0]}")
-        if not 0.0 <= betas[1] < 1.0:
-            raise ValueError(f"Invalid beta parameter at index 1: {betas[1]}")
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad, centered=centered)
-        super().__init__(params, defaults)
+        # same argument checks and messages as the reference constructor (laprop.py:36-43)
+        for ok, msg in ((lr >= 0.0, f"Invalid learning rate: {lr}"), (eps >= 0.0, f"Invalid epsilon value: {eps}"),
+                        (0.0 <= betas[0] < 1.0, f"Invalid beta parameter at index 0: {betas[0]}"),
+                        (0.0 <= betas[1] < 1.0, f"Invalid beta parameter at index 1: {betas[1]}")):
+            if not ok:
+                raise ValueError(msg)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad,
+                                      centered=centered))
         self.agc, self.pmin = agc, pmin
         self._fused = _Fused()
 
