@@ -358,23 +358,21 @@ def barlow_inputs():
 
 
 def run_barlow():
-    """The Barlow block of Dreamer._cal_grad is inline code (dreamer.py:525-532), not a callable: the seven statements are
-    executed here verbatim on seeded tensors with torch autograd (x2 detached as at :522)."""
+    """The Barlow block of Dreamer._cal_grad is inline code (dreamer.py:525-532), not a callable: those source lines are read
+    from the reference checkout and executed as they are (dedented) on seeded tensors under torch autograd, with x2 detached
+    as at :522 and `self.barlow_lambd` = configs/base.yaml:214."""
+    import textwrap
     x1_np, x2_np = barlow_inputs()
     x1 = t(x1_np).requires_grad_(True)
     x2 = t(x2_np).detach()
-    B_T = x1.shape[0]
-    barlow_lambd = 5e-4                                   # configs/base.yaml:214
-    x1_norm = (x1 - x1.mean(0)) / (x1.std(0) + 1e-8)      # dreamer.py:525
-    x2_norm = (x2 - x2.mean(0)) / (x2.std(0) + 1e-8)      # :526
-    c = torch.mm(x1_norm.T, x2_norm) / B_T                # :528
-    invariance_loss = (torch.diagonal(c) - 1.0).pow(2).sum()                      # :529
-    off_diag_mask = ~torch.eye(x1.shape[-1], dtype=torch.bool, device=x1.device)  # :530
-    redundancy_loss = c[off_diag_mask].pow(2).sum()                               # :531
-    loss = invariance_loss + barlow_lambd * redundancy_loss                       # :532
+    src = open(os.path.join(REF, "world_model", "dreamer.py")).read().splitlines()[524:532]
+    assert src[0].strip().startswith("x1_norm") and src[-1].strip().startswith('losses["barlow"]'), src
+    ns = {"torch": torch, "x1": x1, "x2": x2, "B": x1.shape[0], "T": 1, "self": NS(barlow_lambd=5e-4), "losses": {}}
+    exec(textwrap.dedent("\n".join(src)), ns)
+    loss = ns["losses"]["barlow"]
     (dx1,) = torch.autograd.grad(loss, [x1])
     path = os.path.join(ROOT, "tests", "golden", "barlow.npz")
-    np.savez_compressed(path, loss=np.float32(loss.item()), d_x1=dx1.numpy(), lambd=np.float32(barlow_lambd))
+    np.savez_compressed(path, loss=np.float32(loss.item()), d_x1=dx1.numpy(), lambd=np.float32(5e-4))
     print("barlow ->", path, "loss", float(loss))
 
 
