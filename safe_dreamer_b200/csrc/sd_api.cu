@@ -344,6 +344,9 @@ static int env_flag(const char* name, int dflt) {
 // measured on B200 (bench.py, N=1024): 64-wide tiles + split-K beat 256-wide tiles for rows < 4096 (2.47 vs 2.58 ms)
 static bool tc_wide_enabled() { static int v = env_flag("SD_TC_WIDE", 0); return v != 0; }
 static bool fused_epi_enabled() { static int v = env_flag("SD_FUSED_EPI", 1); return v != 0; }
+// Diagnostic only (SD_ABLATE bitmask): drop one kernel of the imagination step to measure its contribution to the scan's
+// critical path (results are garbage).  1 actor tail, 2 sample, 4 norm(hid), 8 3-segment norm, 16 hid GEMM, 32 img layer 0.
+static int ablate() { static int v = env_flag("SD_ABLATE", 0); return v; }
 static bool tc_split_enabled() { static int v = env_flag("SD_TC_SPLIT", 1); return v != 0; }
 
 template <int BN, int NST>
@@ -514,12 +517,28 @@ static sd::NormActP with_parts(Ctx& cx, sd::NormActP p, const float* parts) {
   return p;
 }
 
+static bool normact_warp_enabled() { static int v = env_flag("SD_NORM_WARP", 1); return v != 0; }
 static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
   if (cx.err) return;
   sd::NormActBatch b;
   b.count = n;
   for (int i = 0; i < n; ++i) b.p[i] = ps[i];
-  // one CTA per (row, segment): measured faster than a warp-per-row variant (the kernel is latency bound; 256
+  // 256-wide segments with 16-byte aligned rows: one warp per (row, segment), every slice load in flight at once
+  bool warp_ok = normact_warp_enabled();
+  for (int i = 0; i < n && warp_ok; ++i) {
+    const sd::NormActP& p = ps[i];
+    warp_ok = p.width == 256 && p.nparts <= 7 && (p.ld_in % 4) == 0 && (p.part_stride % 4) == 0 &&
+              (reinterpret_cast<uintptr_t>(p.in) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.w) % 16) == 0 &&
+              (p.nparts == 0 || (reinterpret_cast<uintptr_t>(p.parts) % 16) == 0) &&
+              (!p.out || ((p.ld_out % 4) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16) == 0)) &&
+              (!p.out_bf || ((p.ld_bf % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out_bf) % 16) == 0));
+  }
+  if (warp_ok) {
+    launch_k(cx.st, sd::normact256_warp_kernel, dim3((R * n + 7) / 8), dim3(256), 0, b, R);
+    cx.check("normact256_warp_kernel");
+    return;
+  }
+  // otherwise one CTA per (row, segment): measured faster than a warp-per-row variant (the kernel is latency bound; 256
   // threads with one element each maximise memory-level parallelism)
   launch_k(cx.st, sd::normact_kernel, dim3(dim3(R, n)), dim3(256), 0, b);
   cx.check("normact_kernel");
@@ -529,6 +548,7 @@ static sd::NormActP nap(float* in, int ld_in, const float* w, int width, float* 
   sd::NormActP p;
   p.parts = parts; p.nparts = 0; p.part_stride = 0;
   p.in = in; p.ld_in = ld_in; p.w = w; p.out = out; p.ld_out = ld_out; p.out_bf = ob; p.ld_bf = ld_bf; p.width = width;
+  p.no_writeback = 0;
   return p;
 }
 
@@ -1277,9 +1297,15 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
   normact(cx, R, na, 3);
   }
   Operand dg = d; dg.gstride = Dg;
-  linear(cx, R, h.hid, dg, Dg, opfb(sb.x, 3 * U, cx.tc ? h.x_bf : nullptr, 3 * U), sb.hpre, D, Dg, h.part);
-  sd::NormActP nh = with_parts(cx, nap(sb.hpre, D, h.hid.gain, D, sb.h, D, cx.tc ? h.h_bf : nullptr, D), h.part);
-  normact(cx, R, &nh, 1);
+  if (!(ablate() & 16)) linear(cx, R, h.hid, dg, Dg, opfb(sb.x, 3 * U, cx.tc ? h.x_bf : nullptr, 3 * U), sb.hpre, D, Dg, h.part);
+  // no tape + tcgen05 gate projection below: only the bf16 h is read again, so the fp32 copy (8 MB at 1024 rows) and the
+  // summed pre-norm write-back are skipped
+  const bool gates_tc = cx.tc && sb.stride == 0 && (Dg % 64) == 0 && c.G <= sd::tc::kMaxProblems && h.gru.tc_ok() &&
+                        fused_epi_enabled() && out_bf != h.h_bf;
+  sd::NormActP nh = with_parts(cx, nap(sb.hpre, D, h.hid.gain, D, gates_tc ? nullptr : sb.h, D, cx.tc ? h.h_bf : nullptr, D),
+                               h.part);
+  nh.no_writeback = gates_tc ? 1 : 0;
+  if (!(ablate() & 4)) normact(cx, R, &nh, 1);
   if (!cx.tc && Dg <= sd::GB_KC && c.G <= sd::kMaxBatch && !out_bf && fused_epi_enabled()) {
     // fp32 path: gate projection + GRU gate math in ONE launch (cluster of 3 CTAs per 16 units, see EPI_GATES)
     sd::GemmBatch gb;
@@ -1299,8 +1325,7 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
     cx.check("gemm_f32_kernel(gru+gates)");
     return;
   }
-  if (cx.tc && sb.stride == 0 && (Dg % 64) == 0 && c.G <= sd::tc::kMaxProblems && h.gru.tc_ok() && fused_epi_enabled() &&
-      out_bf != h.h_bf /* the bf16 output must not alias this GEMM's A operand */) {
+  if (gates_tc /* the bf16 output must not alias this GEMM's A operand */) {
     // tcgen05 path, no tape: gate projection with the GRU gate math fused in the epilogue (192-wide tiles =
     // reset|cand|update of 64 units); q is never materialised.
     sd::tc::Batch tb;
@@ -1390,7 +1415,7 @@ static bool latent_logits(Ctx& cx, const StepBufs& sb, int R, const LinearW* lay
 
 static void sample(Ctx& cx, int R, const float* lg, const float* u, int ld_u, float* stoch, int ld_o, bf16* stoch_bf,
                    int ld_bf, float* logit_copy, int ld_c) {
-  if (cx.err) return;
+  if (cx.err || (ablate() & 2)) return;
   sd_handle& h = *cx.h;
   const int K = h.c.K;
   const int gs = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
@@ -1724,7 +1749,8 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
         na[1].parts = h->part; na[1].nparts = ks[1] - 1; na[1].part_stride = (long long)h->part_stride;
         na[2] = nap(sb.vin + c.U, 3 * c.U, h->in1.gain, c.U, nullptr, 0, h->x_bf + c.U, 3 * c.U);
         na[2].parts = h->part + c.U; na[2].nparts = ks[2] - 1; na[2].part_stride = (long long)h->part_stride;
-        normact(cx, N, na, 3);
+        na[0].no_writeback = na[1].no_writeback = na[2].no_writeback = 1;   // no tape on this path
+        if (!(ablate() & 8)) normact(cx, N, na, 3);
         Operand cur = opfb(sb.ao[0], c.units, h->a_bf[0], c.units);
         for (int i = 1; i < actor.layers && !cx.err; ++i) {
           if (!linear_norm_tc(cx, N, actor.l[i], cur, sb, sb.ao[i], c.units, h->a_bf[i], c.units)) {
@@ -1735,6 +1761,17 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
         }
         if (cx.err) return;
         const size_t tail_smem2 = sd::actor_tail_smem(h->act_out, c.units, A, c.U);
+        static const bool tail_regs = env_flag("SD_TAIL_REGS", 1) != 0;
+        if (ablate() & 1) {
+        } else if (tail_regs && h->act_out == 12 && A == 6 && c.act_kind == 0) {
+          // base continuous-control head: weights in registers, no staging / block barrier after the PDL wait
+          launch_k(cx.st, sd::actor_tail_x2_kernel<12, 6>, dim3((N * 32 + 255) / 256), dim3(256), 0,
+                   (const float*)sb.ao[actor.layers - 1], c.units, (const float*)actor.last.wn, actor.last.ldk,
+                   (const float*)actor.last.bias, c.act_kind, c.min_std, c.max_std, c.act_unimix,
+                   act_noise + (size_t)t * A, H * A, (const float*)h->in2.wt, h->in2.ldw, (const float*)h->in2.bias, N,
+                   actions + (size_t)t * A, H * A, h->abar, (const float*)h->in2.gain, h->x_bf + 2 * c.U, 3 * c.U);
+          cx.check("actor_tail_x2_kernel");
+        } else {
         launch_k(cx.st, sd::actor_tail_kernel, dim3((N * 32 + 255) / 256), dim3(256), tail_smem2,
                  (const float*)sb.ao[actor.layers - 1], c.units, c.units, (const float*)actor.last.wn, actor.last.ldk,
                  (const float*)actor.last.bias, h->act_out, A, c.act_kind, c.min_std, c.max_std, c.act_unimix,
@@ -1742,6 +1779,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
                  (float*)nullptr, actions + (size_t)t * A, H * A, h->abar, (float*)nullptr, 0, (const float*)h->in2.gain,
                  h->x_bf + 2 * c.U, 3 * c.U);
         cx.check("actor_tail_kernel(+x2)");
+        }
         if (t == H - 1) break;
         float* dnext = ft + F + SK;
         deter_core(cx, sb, N, opfb(ft, ldf, fb, ldfb), opfb(ft + SK, ldf, fb + SK, ldfb), h->abar, dnext, ldf,

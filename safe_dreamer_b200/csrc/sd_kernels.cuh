@@ -647,6 +647,7 @@ struct NormActP {
   float* out; int ld_out;       // nullable
   __nv_bfloat16* out_bf; int ld_bf; // nullable
   int width;
+  int no_writeback;             // nparts > 0: do not rewrite `in` with the summed value (no backward tape wanted)
 };
 struct NormActBatch {
   int count;
@@ -670,10 +671,19 @@ __global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 256;
     v[i] = (c < p.width) ? in[c] : 0.f;
-    if (p.nparts > 0 && c < p.width) {   // fixed slice order => deterministic
-      for (int s = 0; s < p.nparts; ++s) v[i] += p.parts[s * p.part_stride + row * p.ld_in + c];
-      in[c] = v[i];
+  }
+  for (int s = 0; s < p.nparts; ++s) {   // fixed slice order => deterministic; the 8 loads of a slice are independent
+    const float* ps = p.parts + s * p.part_stride + row * p.ld_in;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < p.width) v[i] += ps[c];
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (p.nparts > 0 && !p.no_writeback && c < p.width) in[c] = v[i];
     ss = fmaf(v[i], v[i], ss);
   }
   ss = block_sum(ss, sh);
@@ -686,6 +696,63 @@ __global__ void __launch_bounds__(256) normact_kernel(const NormActBatch b) {
       if (p.out) p.out[row * p.ld_out + c] = y;
       if (p.out_bf) p.out_bf[row * p.ld_bf + c] = __float2bfloat16(y);
     }
+  }
+}
+
+// Same for 256-wide segments (the U / units layers), one WARP per (row, segment): lane owns 8 consecutive columns, the
+// slice-0 value and every split-K partial are fetched as 16-byte loads that are all in flight together (the CTA-per-row
+// kernel above walks the partial slices one L2 round trip at a time and needs two block barriers), the row statistic is a
+// shuffle reduction, outputs are 16-byte stores.  Measured by ablation on B200 (N = 1024 imagination scan): the
+// 3-segment norm after the wide feat layers cost 10.5 us per step on the critical path with the CTA-per-row kernel.
+__global__ void __launch_bounds__(256) normact256_warp_kernel(const NormActBatch b, int R) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const bool live = item < R * b.count;
+  const int row = live ? item / b.count : 0, seg = live ? item - row * b.count : 0;
+  const NormActP& p = b.p[seg];
+  // the RMS scale is a packed weight: fetch it before the PDL wait
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.w + lane * 8));
+  const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.w + lane * 8 + 4));
+  pdl_prologue();
+  if (!live) return;
+  const size_t off = (size_t)row * p.ld_in + lane * 8;
+  float4 a = *reinterpret_cast<const float4*>(p.in + off), c = *reinterpret_cast<const float4*>(p.in + off + 4);
+  float4 pa[7], pc[7];
+#pragma unroll
+  for (int s = 0; s < 7; ++s) {
+    if (s < p.nparts) {
+      pa[s] = *reinterpret_cast<const float4*>(p.parts + s * p.part_stride + off);
+      pc[s] = *reinterpret_cast<const float4*>(p.parts + s * p.part_stride + off + 4);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 7; ++s) {   // fixed slice order => deterministic
+    if (s < p.nparts) {
+      a.x += pa[s].x; a.y += pa[s].y; a.z += pa[s].z; a.w += pa[s].w;
+      c.x += pc[s].x; c.y += pc[s].y; c.z += pc[s].z; c.w += pc[s].w;
+    }
+  }
+  if (p.nparts > 0 && !p.no_writeback) {   // the summed pre-norm value is the backward tape
+    *reinterpret_cast<float4*>(p.in + off) = a;
+    *reinterpret_cast<float4*>(p.in + off + 4) = c;
+  }
+  float ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + c.x * c.x + c.y * c.y + c.z * c.z + c.w * c.w;
+  ss = warp_sum(ss);
+  const float rs = 1.f / sqrtf(ss / 256.f + kRmsEps);
+  float y[8] = {siluf_((a.x * rs) * g0.x), siluf_((a.y * rs) * g0.y), siluf_((a.z * rs) * g0.z), siluf_((a.w * rs) * g0.w),
+                siluf_((c.x * rs) * g1.x), siluf_((c.y * rs) * g1.y), siluf_((c.z * rs) * g1.z), siluf_((c.w * rs) * g1.w)};
+  if (p.out) {
+    float* o = p.out + (size_t)row * p.ld_out + lane * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+  }
+  if (p.out_bf) {
+    __nv_bfloat162 q0 = __floats2bfloat162_rn(y[0], y[1]), q1 = __floats2bfloat162_rn(y[2], y[3]);
+    __nv_bfloat162 q2 = __floats2bfloat162_rn(y[4], y[5]), q3 = __floats2bfloat162_rn(y[6], y[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&q0); pk.y = *reinterpret_cast<uint32_t*>(&q1);
+    pk.z = *reinterpret_cast<uint32_t*>(&q2); pk.w = *reinterpret_cast<uint32_t*>(&q3);
+    *reinterpret_cast<uint4*>(p.out_bf + (size_t)row * p.ld_bf + lane * 8) = pk;
   }
 }
 
@@ -1007,6 +1074,100 @@ __global__ void __launch_bounds__(256) actor_tail_kernel(const float* __restrict
     for (int a = 0; a < A; ++a) v = fmaf(__shfl_sync(0xffffffffu, ab, a), w2_s[a * U + n], v);
     v2[(size_t)row * ld_v2 + n] = v + b2_s[n];
   }
+}
+
+// Register-resident variant of the fused tail for the 13-launch imagination step (units = U = 256, x2 output only).
+// The sizes are compile-time, so every loop unrolls and the AO row reductions interleave; all weights (W_last, W_in2,
+// b, g2) sit in REGISTERS, fetched before the PDL wait, so after the wait the warp only loads its activation row: no
+// shared-memory staging, no block barrier.  Same arithmetic order as actor_tail_kernel (results are bit-identical).
+// Measured by ablation (B200, N = 1024): the shared-memory tail cost 12 us per step on the critical path.
+template <int AO, int AA>
+__global__ void __launch_bounds__(256) actor_tail_x2_kernel(const float* __restrict__ a3, int ld_a3,
+                                                            const float* __restrict__ wl_n, int ldk_l,
+                                                            const float* __restrict__ bl, int act_kind, float min_std,
+                                                            float max_std, float unimix, const float* __restrict__ noise,
+                                                            int ld_n, const float* __restrict__ w2_t, int ldw_2,
+                                                            const float* __restrict__ b2, int R, float* action, int ld_act,
+                                                            float* abar, const float* __restrict__ g2,
+                                                            __nv_bfloat16* x2_bf, int ld_x2) {
+  static_assert(AO <= 32 && AA <= 32, "one lane per output");
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  float wl[AO][8], w2[AA][8], b2r[8], g2r[8], blr[AO];
+#pragma unroll
+  for (int j = 0; j < AO; ++j) {
+    blr[j] = __ldg(bl + j);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wl[j][i] = __ldg(wl_n + (size_t)j * ldk_l + lane + 32 * i);
+  }
+#pragma unroll
+  for (int a = 0; a < AA; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w2[a][i] = __ldg(w2_t + (size_t)a * ldw_2 + lane + 32 * i);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { b2r[i] = __ldg(b2 + lane + 32 * i); g2r[i] = __ldg(g2 + lane + 32 * i); }
+  const float nz = (row < R && lane < AA) ? noise[(size_t)row * ld_n + lane] : 0.5f;
+  pdl_prologue();
+  if (row >= R) return;
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = a3[(size_t)row * ld_a3 + lane + 32 * i];
+  float acc[AO];
+#pragma unroll
+  for (int j = 0; j < AO; ++j) {
+    acc[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[j] = fmaf(x[i], wl[j][i], acc[j]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int j = 0; j < AO; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+#pragma unroll
+  for (int j = 0; j < AO; ++j) acc[j] += blr[j];
+  float act = 0.f;
+  if (act_kind == 0) {
+    float mean = 0.f, sraw = 0.f;
+#pragma unroll
+    for (int j = 0; j < AO; ++j) {
+      if (j == lane) mean = acc[j];
+      if (j == lane + AA) sraw = acc[j];
+    }
+    if (lane < AA) {
+      const float std = (max_std - min_std) * sigmoidf_(sraw + 2.f) + min_std;
+      act = tanhf(mean) + std * nz;
+    }
+  } else {
+    float lg = 0.f;
+#pragma unroll
+    for (int j = 0; j < AO; ++j)
+      if (j == lane) lg = acc[j];
+    const bool valid = lane < AA;
+    const int best = sample_group<32>(lg, nz, valid, lane, AA, unimix, nullptr);
+    act = (valid && lane == best) ? 1.f : 0.f;
+  }
+  const float ab = act / fmaxf(fabsf(act), 1.f);
+  if (lane < AA) {
+    action[(size_t)row * ld_act + lane] = act;
+    abar[(size_t)row * AA + lane] = ab;
+  }
+  float abv[AA];
+#pragma unroll
+  for (int a = 0; a < AA; ++a) abv[a] = __shfl_sync(0xffffffffu, ab, a);
+  float vv[8], ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = 0.f;
+#pragma unroll
+    for (int a = 0; a < AA; ++a) v = fmaf(abv[a], w2[a][i], v);
+    v += b2r[i];
+    vv[i] = v;
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float rs = 1.f / sqrtf(ss / 256.f + kRmsEps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    x2_bf[(size_t)row * ld_x2 + lane + 32 * i] = __float2bfloat16(siluf_((vv[i] * rs) * g2r[i]));
 }
 
 // TwoHot.mode (distributions.py:78-98): softmax over `bins` logits, then the reference's symmetric
