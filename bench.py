@@ -176,6 +176,9 @@ def run_gpu(args):
     eng.static_outputs = True
     disc = 1 - 1 / c.horizon
     GRAPH, BF16, TAPE = 4, 1, 2
+    # imagination + heads run beside the latency-critical posterior backward: SD_FLAG_BACKGROUND (no PDL pre-launch, so
+    # only one of their kernels holds SM resources at a time) measured 5.91 -> 5.68 ms per step (profiles/overlap_probe.py)
+    BG = 0 if os.environ.get("SD_BENCH_BG", "1") == "0" else 16
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     # upstream cotangents for the posterior backward (what dreamer.py:486-573 would send back)
     if have_bwd:
@@ -203,8 +206,8 @@ def run_gpu(args):
             ev_fwd.record(main)
             side.wait_event(ev_fwd)
             with torch.cuda.stream(side):
-                eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions))
-                eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
+                eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH | BG, out=(feats, actions))
+                eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH | BG, out=outs)
                 ev_side.record(side)
         if have_bwd:
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
@@ -340,9 +343,11 @@ def run_gpu(args):
         def imag():
             with torch.no_grad():
                 rssm.precision = "bf16"
+                rssm.background = bool(overlap and BG)
                 ft_, ac_ = dreamer_ops.imagine(rssm, (st_.detach().reshape(N, c.S, c.K), dt_.detach().reshape(N, c.D)), H)
                 out_ = dreamer_ops.heads_lambda(rssm, ft_, c.horizon, c.lamb)
                 rssm.precision = "fp32"
+                rssm.background = False
                 return out_
         main = torch.cuda.current_stream(dev)
         if overlap:   # imagination on the side stream while autograd runs the posterior backward on the main one

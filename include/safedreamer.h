@@ -59,6 +59,10 @@ typedef enum sd_module {
                                   SD_FLAG_BF16 sd_imagine_fwd on this handle (same N, H), so its bf16 copy, written step by
                                   step during the rollout, is reused instead of re-casting 168 MB; SD_ERR_INVALID when the
                                   pointer / sizes do not match that call */
+#define SD_FLAG_BACKGROUND 16u /* with SD_FLAG_GRAPH: this call is off the caller's critical path; its kernel nodes are
+                                  captured WITHOUT programmatic dependent launch, so only one of its kernels holds SM
+                                  resources at a time and concurrent latency-critical work on another stream finds
+                                  room (two-stream schedule). */
 
 /* Sizes of the path: configs/base.yaml:117-127,252-276,340-420. */
 typedef struct sd_config {

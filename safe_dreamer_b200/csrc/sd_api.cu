@@ -296,16 +296,21 @@ static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n,
   cudaLaunchKernelEx(&cfg, sd::gemm_f32_kernel, gb, ksplit, kslice);
 }
 
+static thread_local bool tl_no_pdl = false;   // SD_FLAG_BACKGROUND
 template <class... KArgs, class... Args>
 static void launch_k(cudaStream_t st, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  int na = 0;
+  if (pdl_enabled() && !tl_no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = na;
   prefer_max_smem((const void*)kernel);
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
 }
@@ -1230,11 +1235,14 @@ static int run(sd_handle* h, uint64_t key, uint32_t flags, cudaStream_t st, bool
   // warm any lazily-set function attributes / driver entry points outside capture with a direct run
   // (results are identical; the captured replay below overwrites them).
   if (int e = direct()) return e;
-  CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-  Ctx cx{h, h->cap_stream, tc};
+  cudaStream_t cap = h->cap_stream;
+  CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+  Ctx cx{h, cap, tc};
+  tl_no_pdl = (flags & SD_FLAG_BACKGROUND) != 0;
   body(cx);
+  tl_no_pdl = false;
   cudaGraph_t graph = nullptr;
-  cudaError_t ee = cudaStreamEndCapture(h->cap_stream, &graph);
+  cudaError_t ee = cudaStreamEndCapture(cap, &graph);
   if (cx.err) { if (graph) cudaGraphDestroy(graph); return cx.err; }
   if (ee != cudaSuccess) return fail(SD_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ee));
   cudaGraphExec_t exec = nullptr;

@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from . import engine as _engine
+from ._lib import SD_FLAG_BACKGROUND
 from .engine import MOD_RSSM, SD_FLAG_BF16, SD_FLAG_GRAPH, SD_FLAG_SAVE_TAPE
 
 _U_LO = 2.0 ** -24
@@ -249,6 +250,8 @@ class RSSM(nn.Module):
     # ------------------------------------------------------------------ runtime plumbing
     def _flags(self):
         f = SD_FLAG_BF16 if self.precision == "bf16" else 0
+        if getattr(self, "background", False):   # calls issued beside latency-critical work on another stream
+            f |= SD_FLAG_BACKGROUND
         return f | (SD_FLAG_GRAPH if self.use_graph else 0)
 
     def engine_dims(self):

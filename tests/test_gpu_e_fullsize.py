@@ -90,7 +90,7 @@ def test_imagine_heads_properties(full):
     c, P, eng, *_ = full
     st0, dt0, ui, noise = O.synth_imagine_inputs(c, N, H, seed=3)
     runs = []
-    for f in (1, 1 | 4, 1 | 4):
+    for f in (1, 1 | 4, 1 | 4, 1 | 4 | 16, 1 | 4 | 16):   # 16 = SD_FLAG_BACKGROUND: graph captured without PDL, same results
         feats, acts = eng.imagine(cu(st0), cu(dt0), cu(ui), cu(noise), H, flags=f)
         runs.append((_np(feats).copy(), _np(acts).copy()))
     for fa in runs[1:]:
