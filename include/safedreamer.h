@@ -191,6 +191,25 @@ int sd_twohot_logprob_bwd(const float* logits, int ld, const float* bins, int n,
  * scale = max(ema_vals[1] - ema_vals[0], 1).  `ret` holds n device floats; offset / scale are device scalars (nullable). */
 int sd_return_ema(const float* ret, int64_t n, double alpha, float* ema_vals, float* offset, float* scale, void* stream);
 
+/* Replay latent write-back = Buffer.update (utils/buffer.py:44-53; call site dreamer.py:450): row i of the freshly
+ * inferred posterior (stoch (R, S, K) one-hot, deter (R, D)) is written to storage slot (time_idx[i], env_idx[i]) of a
+ * (n_time, n_env, ...) storage (the reference's LazyTensorStorage(ndim=2): length first, environments second).
+ *   store_idx   (n_time, n_env, S) uint8 : class index per categorical (first arg-max over K; K <= 256) -- 32 B per row
+ *                                          instead of the reference's 2 KB one-hot
+ *   store_stoch (n_time, n_env, S, K) f32: optional verbatim mirror in the reference's layout (nullable)
+ *   store_deter (n_time, n_env, D) f32
+ * When several rows of one call address the same slot (overlapping sampled slices) the row with the largest i wins, as
+ * sequential assignment would (deterministic).  Rows whose index is out of range are skipped and added to *n_bad (device
+ * int, nullable; the reference raises IndexError -- the host mirror checks it).  All pointers are device pointers. */
+int sd_latent_writeback(const int64_t* env_idx, const int64_t* time_idx, int R, const float* stoch, const float* deter,
+                        int S, int K, int D, int64_t n_time, int64_t n_env, uint8_t* store_idx, float* store_stoch,
+                        float* store_deter, int* n_bad, void* stream);
+/* Read side, Buffer.sample's `initial` (utils/buffer.py:40): gathers R rows from the storage written above; stoch comes
+ * back as exact one-hots decoded from the class indices.  Out-of-range rows are zero-filled and counted in *n_bad. */
+int sd_latent_gather(const int64_t* env_idx, const int64_t* time_idx, int R, int S, int K, int D, int64_t n_time,
+                     int64_t n_env, const uint8_t* store_idx, const float* store_deter, float* stoch, float* deter,
+                     int* n_bad, void* stream);
+
 /* Barlow-twins redundancy loss of dreamer.py:525-532 between projected latents x1 (N, E) and (detached) embeddings x2 (N, E):
  * columns standardised with the unbiased std (+1e-8), c = x1n^T x2n / N, loss = sum_i (c_ii - 1)^2 + lambd * sum_{i!=j} c_ij^2.
  * Writes the scalar loss and (nullable) d(loss)/d(x1) (N, E).  E must be a multiple of 16, N >= 2.  `scratch`: device buffer

@@ -653,3 +653,32 @@ def barlow_loss(x1, x2, lambd):
     sigma = x1.std(0, ddof=1)
     dx = (g - g.mean(0)) / s1 - x1n * ((g * x1n).sum(0) / (f(n - 1) * sigma))
     return loss, dx.astype(x1.dtype)
+
+
+# --------------------------------------------------------------------------- replay latent write-back (section 8f rank 4)
+def latent_writeback(index, stoch, deter, store_deter, store_idx=None, store_stoch=None):
+    """Buffer.update (utils/buffer.py:44-53; call site dreamer.py:450), in place: flatten (B, T, ...) -> (B*T, ...), then
+    storage[index[1], index[0]] <- row (storage is (length, envs, ...): index[1] addresses dim 0, index[0] dim 1).
+    Rows are assigned in order, so for a repeated slot the LAST row wins.  `store_stoch` is the reference's one-hot
+    storage; `store_idx` (length, envs, S) uint8 is the class-index form the B200 path keeps (first arg-max over K).
+    The storage itself lives in torchrl 's LazyTensorStorage (third-party, absent from the image): its published
+    behaviour for this call is plain index assignment, which is what is restated here."""
+    i0 = np.asarray(index[1]).reshape(-1)
+    i1 = np.asarray(index[0]).reshape(-1)
+    st = stoch.reshape(-1, *stoch.shape[2:])
+    dt = deter.reshape(-1, *deter.shape[2:])
+    for r in range(i0.shape[0]):
+        store_deter[i0[r], i1[r]] = dt[r]
+        if store_stoch is not None:
+            store_stoch[i0[r], i1[r]] = st[r]
+        if store_idx is not None:
+            store_idx[i0[r], i1[r]] = st[r].argmax(-1).astype(np.uint8)
+
+
+def latent_initial(index, store_idx, store_deter, K):
+    """Read side, `initial` of Buffer.sample (utils/buffer.py:40): (stoch one-hot (R, S, K), deter (R, D)) of the rows at
+    storage[index[1], index[0]], decoded from the class-index storage."""
+    i0 = np.asarray(index[1]).reshape(-1)
+    i1 = np.asarray(index[0]).reshape(-1)
+    idx = store_idx[i0, i1]
+    return np.eye(K, dtype=np.float32)[idx], store_deter[i0, i1].copy()

@@ -92,6 +92,8 @@ _SIGS = {
     "sd_opt_scratch_bytes": (C.c_size_t, [C.POINTER(sd_opt_tensor), C.c_int]),
     "sd_agc_laprop_step": (C.c_int, [C.POINTER(sd_opt_tensor), C.c_int, C.c_int] + [C.c_float] * 11 + [_P, _P, _P, _P]),
     "sd_return_ema": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, _P, _P]),
+    "sd_latent_writeback": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [_P] * 5),
+    "sd_latent_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [_P] * 6),
     "sd_launch_count": (C.c_uint64, []),
 }
 

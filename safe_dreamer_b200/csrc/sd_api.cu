@@ -2530,6 +2530,41 @@ extern "C" int sd_return_ema(const float* ret, int64_t n, double alpha, float* e
   return SD_OK;
 }
 
+static int latent_args_ok(const char* who, const void* a, const void* b, int R, int S, int K, int D, int64_t n_time,
+                          int64_t n_env) {
+  if (!a || !b) return fail(SD_ERR_INVALID, "%s: null index tensor", who);
+  if (R < 1 || S < 1 || K < 1 || K > 256 || D < 1 || n_time < 1 || n_env < 1)
+    return fail(SD_ERR_INVALID, "%s: bad sizes (R=%d S=%d K=%d D=%d n_time=%lld n_env=%lld; K <= 256)", who, R, S, K, D,
+                (long long)n_time, (long long)n_env);
+  return SD_OK;
+}
+extern "C" int sd_latent_writeback(const int64_t* env_idx, const int64_t* time_idx, int R, const float* stoch,
+                                   const float* deter, int S, int K, int D, int64_t n_time, int64_t n_env,
+                                   uint8_t* store_idx, float* store_stoch, float* store_deter, int* n_bad, void* stream) {
+  if (int e = latent_args_ok("sd_latent_writeback", env_idx, time_idx, R, S, K, D, n_time, n_env)) return e;
+  if (!stoch || !deter || !store_idx || !store_deter) return fail(SD_ERR_INVALID, "sd_latent_writeback: null tensor");
+  launch_k((cudaStream_t)stream, sd::latent_writeback_kernel, dim3(R), dim3(256), 0, (const long long*)env_idx,
+           (const long long*)time_idx, R, stoch, deter, S, K, D, (long long)n_time, (long long)n_env, store_idx, store_stoch,
+           store_deter, n_bad);
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_latent_writeback: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+extern "C" int sd_latent_gather(const int64_t* env_idx, const int64_t* time_idx, int R, int S, int K, int D, int64_t n_time,
+                                int64_t n_env, const uint8_t* store_idx, const float* store_deter, float* stoch,
+                                float* deter, int* n_bad, void* stream) {
+  if (int e = latent_args_ok("sd_latent_gather", env_idx, time_idx, R, S, K, D, n_time, n_env)) return e;
+  if (!stoch || !deter || !store_idx || !store_deter) return fail(SD_ERR_INVALID, "sd_latent_gather: null tensor");
+  launch_k((cudaStream_t)stream, sd::latent_gather_kernel, dim3(R), dim3(256), 0, (const long long*)env_idx,
+           (const long long*)time_idx, R, S, K, D, (long long)n_time, (long long)n_env, store_idx, store_deter, stoch, deter,
+           n_bad);
+  ++g_launches;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(SD_ERR_CUDA, "sd_latent_gather: %s", cudaGetErrorString(e)); }
+  return SD_OK;
+}
+
 extern "C" int sd_kl_loss(sd_handle* h, int R, const float* post_logit, const float* prior_logit, float free_nats,
                           float* dyn_loss, float* rep_loss, float* post_entropy, float* prior_entropy, void* stream) {
   if (!h) return fail(SD_ERR_INVALID, "sd_kl_loss: null handle");

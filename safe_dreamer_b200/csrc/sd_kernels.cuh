@@ -1170,6 +1170,76 @@ __global__ void __launch_bounds__(256) actor_tail_x2_kernel(const float* __restr
     x2_bf[(size_t)row * ld_x2 + lane + 32 * i] = __float2bfloat16(siluf_((vv[i] * rs) * g2r[i]));
 }
 
+// Replay latent write-back (utils/buffer.py:44-53, call site dreamer.py:450): row i of the freshly inferred posterior
+// (stoch (S,K) one-hot, deter (D)) goes to storage slot (time_idx[i], env_idx[i]).  The one-hot is stored as S class
+// indices (uint8: 32 B per row instead of 2 KB); an optional fp32 one-hot mirror keeps the reference's layout.
+// Duplicate slots inside one call (overlapping sampled slices): the row with the LARGEST i wins, as sequential assignment
+// would, so the result is deterministic.  Out-of-range indices are skipped and counted in *n_bad.  One CTA per row.
+__global__ void __launch_bounds__(256) latent_writeback_kernel(const long long* __restrict__ env_idx,
+                                                               const long long* __restrict__ time_idx, int R,
+                                                               const float* __restrict__ stoch,
+                                                               const float* __restrict__ deter, int S, int K, int D,
+                                                               long long n_time, long long n_env, uint8_t* store_idx,
+                                                               float* store_stoch, float* store_deter, int* n_bad) {
+  pdl_prologue();
+  const int row = blockIdx.x;
+  const long long e = env_idx[row], t = time_idx[row];
+  if (e < 0 || e >= n_env || t < 0 || t >= n_time) {
+    if (threadIdx.x == 0 && n_bad) atomicAdd(n_bad, 1);
+    return;
+  }
+  int later = 0;
+  for (int j = row + 1 + threadIdx.x; j < R; j += blockDim.x) later |= (env_idx[j] == e && time_idx[j] == t);
+  if (__syncthreads_or(later)) return;   // a later row owns this slot
+  const size_t slot = (size_t)t * n_env + e;
+  const float* dsrc = deter + (size_t)row * D;
+  float* ddst = store_deter + slot * D;
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(dsrc) | reinterpret_cast<uintptr_t>(ddst)) & 15) == 0) {
+    for (int i = threadIdx.x; i < D / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(ddst)[i] = reinterpret_cast<const float4*>(dsrc)[i];
+  } else {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) ddst[i] = dsrc[i];
+  }
+  const float* ssrc = stoch + (size_t)row * S * K;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {   // first arg-max over the K classes
+    float bv = ssrc[s * K];
+    int bi = 0;
+    for (int c = 1; c < K; ++c) {
+      const float v = ssrc[s * K + c];
+      if (v > bv) { bv = v; bi = c; }
+    }
+    store_idx[slot * S + s] = (uint8_t)bi;
+  }
+  if (store_stoch) {
+    float* sdst = store_stoch + slot * (size_t)S * K;
+    for (int i = threadIdx.x; i < S * K; i += blockDim.x) sdst[i] = ssrc[i];
+  }
+}
+
+// Read side (utils/buffer.py:40: `initial` = stored latents of the context step): gather rows from the storage, decoding the
+// class indices to exact one-hots.  One CTA per row; rows with an out-of-range index are zero-filled and counted.
+__global__ void __launch_bounds__(256) latent_gather_kernel(const long long* __restrict__ env_idx,
+                                                            const long long* __restrict__ time_idx, int R, int S, int K,
+                                                            int D, long long n_time, long long n_env,
+                                                            const uint8_t* __restrict__ store_idx,
+                                                            const float* __restrict__ store_deter, float* stoch,
+                                                            float* deter, int* n_bad) {
+  pdl_prologue();
+  const int row = blockIdx.x;
+  const long long e = env_idx[row], t = time_idx[row];
+  const bool bad = e < 0 || e >= n_env || t < 0 || t >= n_time;
+  if (bad && threadIdx.x == 0 && n_bad) atomicAdd(n_bad, 1);
+  const size_t slot = bad ? 0 : (size_t)t * n_env + e;
+  float* ddst = deter + (size_t)row * D;
+  const float* dsrc = store_deter + slot * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) ddst[i] = bad ? 0.f : dsrc[i];
+  float* sdst = stoch + (size_t)row * S * K;
+  for (int i = threadIdx.x; i < S * K; i += blockDim.x) {
+    const int s = i / K, c = i - s * K;
+    sdst[i] = (!bad && store_idx[slot * S + s] == c) ? 1.f : 0.f;
+  }
+}
+
 // TwoHot.mode (distributions.py:78-98): softmax over `bins` logits, then the reference's symmetric
 // pairing sum_j (p[m-1-j]*b[m-1-j] + p[m+1+j]*b[m+1+j]) + p[m]*b[m].  One warp per row.
 __global__ void twohot_mode_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ bins, int n,

@@ -376,6 +376,60 @@ def run_barlow():
     print("barlow ->", path, "loss", float(loss))
 
 
+def latent_store_inputs():
+    """Seeded inputs for the replay latent write-back (restated in tests/test_latent_store.py)."""
+    rng = np.random.Generator(np.random.Philox(4242))
+    B, T, S, K, D, n_len, n_env = 3, 5, 4, 8, 12, 20, 4
+    # B slices of T consecutive steps, distinct (time, env) slots (unique => index_put_ is deterministic)
+    env = np.array([0, 2, 3], np.int64)[:, None].repeat(T, 1)
+    t0 = np.array([1, 7, 13], np.int64)[:, None]
+    time = t0 + np.arange(T, dtype=np.int64)[None]
+    cls = rng.integers(0, K, size=(B, T, S))
+    stoch = np.eye(K, dtype=np.float32)[cls]
+    deter = rng.standard_normal((B, T, D), dtype=np.float32)
+    store_stoch = rng.standard_normal((n_len, n_env, S, K), dtype=np.float32)
+    store_deter = rng.standard_normal((n_len, n_env, D), dtype=np.float32)
+    return env, time, stoch, deter, store_stoch, store_deter
+
+
+def run_latent_store():
+    """Buffer.update (utils/buffer.py:44-53) executed from the reference checkout.  torchrl / tensordict (the storage the
+    reference delegates to; requirements pin torchrl, absent from this image) are replaced by a minimal stand-in whose
+    `storage[i0, i1].set_(key, value)` is torch's index assignment on plain tensors -- so the reference's own lines
+    (flattening, index ORDER index[1] -> dim 0, index[0] -> dim 1) are what runs."""
+    import types
+    for name in ("torchrl", "torchrl.data", "torchrl.data.replay_buffers", "torchrl.data.replay_buffers.samplers"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["torchrl.data.replay_buffers"].LazyTensorStorage = object
+    sys.modules["torchrl.data.replay_buffers"].ReplayBuffer = object
+    sys.modules["torchrl.data.replay_buffers.samplers"].SliceSampler = object
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_buffer", os.path.join(REF, "utils", "buffer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class View:
+        def __init__(self, store, key):
+            self.store, self.key = store, key
+
+        def set_(self, name, value):
+            self.store.t[name][self.key] = value
+
+    class Store:
+        def __init__(self, **t):
+            self.t = t
+
+        def __getitem__(self, key):
+            return View(self, key)
+
+    env, time, stoch, deter, store_stoch, store_deter = latent_store_inputs()
+    st = Store(stoch=t(store_stoch).clone(), deter=t(store_deter).clone())
+    holder = types.SimpleNamespace(_buffer=st)
+    mod.Buffer.update(holder, [t(env), t(time)], t(stoch), t(deter))
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "latent_store.npz"), store_stoch=st.t["stoch"].numpy(), store_deter=st.t["deter"].numpy())
+    print("wrote latent_store.npz")
+
+
 def run_return_ema(networks):
     """ReturnEMA (networks.py:405-422), four consecutive calls per case (the buffer carries over)."""
     out = {}
@@ -400,6 +454,9 @@ def main():
     if "--barlow-only" in sys.argv:
         run_barlow()
         return
+    if "--latent-store-only" in sys.argv:
+        run_latent_store()
+        return
     if "--optim-only" in sys.argv:
         run_optim()
         return
@@ -421,6 +478,7 @@ def main():
     run_twohot(dists)
     run_optim()
     run_barlow()
+    run_latent_store()
 
 
 if __name__ == "__main__":
