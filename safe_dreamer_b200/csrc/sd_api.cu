@@ -143,6 +143,11 @@ struct sd_handle {
   float* wg_scratch = nullptr;         // row-slice partials of the weight-gradient pass
   size_t wg_scratch_elems = 0;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
+  // early weight-gradient slices of sd_observe_bwd run on a forked stream beside the backward scan
+  cudaStream_t side_stream = nullptr, cap_side = nullptr;   // direct launches / inside graph capture
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* wg_early = nullptr;           // per layer x per row-slice partials (all layers live at once)
+  size_t wg_early_elems = 0;
   bf16* trunk_bf = nullptr;
   // persistent posterior scan (sd_scan.cuh): input-only precomputations and cross-CTA exchange
   float *ps_x2 = nullptr, *ps_eproj = nullptr, *ps_ssq = nullptr;
@@ -522,6 +527,7 @@ static sd::NormActP with_parts(Ctx& cx, sd::NormActP p, const float* parts) {
   return p;
 }
 
+static bool wgrad_early_enabled() { static int v = env_flag("SD_WGRAD_EARLY", 0); return v != 0; }
 static bool normact_warp_enabled() { static int v = env_flag("SD_NORM_WARP", 1); return v != 0; }
 static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
   if (cx.err) return;
@@ -906,6 +912,14 @@ static void layout(sd_handle& h, Arena& a) {
     if ((size_t)c.units * F > big) big = (size_t)c.units * F;
     h.wg_scratch_elems = big * 8;
     h.wg_scratch = a.take<float>(h.wg_scratch_elems);
+    // all posterior-path weight tensors x 8 row slices, live at once (early slices overlap the backward scan)
+    const size_t rssm_w = (size_t)c.U * c.D + (size_t)c.U * h.SK + (size_t)c.U * c.A + hidw + gruw +
+                          (size_t)c.U * (c.D + c.E) + (size_t)(c.obs_layers > 1 ? c.obs_layers - 1 : 0) * c.U * c.U +
+                          (size_t)h.SK * c.U;
+    // opt-in (SD_WGRAD_EARLY=1): measured on B200 it does NOT pay -- the saturating wgrad bursts delay the scan's small
+    // dependent launches by as much as they save (fwd+bwd 4.78 -> 4.85 ms, two-stream step 5.70 -> 5.76 ms)
+    h.wg_early_elems = wgrad_early_enabled() ? rssm_w * 8 : 0;
+    h.wg_early = a.take<float>(h.wg_early_elems);
   }
   h.feat_bf = a.take<bf16>(R * F);
   h.x_bf = a.take<bf16>(R * 3 * c.U);
@@ -1092,6 +1106,10 @@ extern "C" int sd_create(const sd_config* cfg, sd_handle** out) {
     cudaMemcpy(h->bins, b.data(), n * sizeof(float), cudaMemcpyHostToDevice);
   }
   CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_side, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CUDA_TRY(cudaDeviceSynchronize());
   *out = h;
   return SD_OK;
@@ -1101,6 +1119,10 @@ extern "C" int sd_destroy(sd_handle* h) {
   if (!h) return SD_OK;
   for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->cap_side) cudaStreamDestroy(h->cap_side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ws.base) cudaFree(h->ws.base);
   delete h;
   return SD_OK;
@@ -2075,37 +2097,58 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
 // dW (+)= dY^T [X | X2] for a Linear (reference layout (N,K)) or the G blocks of a BlockLinear ((O/G, I/G, G)).
 // Rows are cut into fixed slices (more CTAs, short dependent chains); partials land in the scratch and are
 // added to dW in slice order.
-static void wgrad_linear(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride,
-                         const float* X, int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* dW) {
-  if (!dW || cx.err) return;
-  sd_handle& h = *cx.h;
+// One row-slice range [s_lo, s_hi) of the weight-gradient partials of a layer into `scratch` (slice s at scratch + s*numel).
+static void wgrad_partial(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride,
+                          const float* X, int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* scratch,
+                          int rows_per_slice, int s_lo, int s_hi) {
+  if (cx.err || s_hi <= s_lo) return;
   const long long numel = (long long)L.G * L.N * L.K;
-  const int rows_per_slice = env_flag("SD_WGRAD_ROWS", 256);   // measured on B200 (T*B = 1024 rows): 64: 4.81, 128: 4.78, 256: 4.74, 512: 4.79 ms fwd+bwd
-  int slices = (R + rows_per_slice - 1) / rows_per_slice;
-  const int max_slices = (int)(h.wg_scratch_elems / numel);
-  if (slices > max_slices) slices = max_slices;
-  if (slices < 1) { cx.err = fail(SD_ERR_WORKSPACE, "wgrad scratch too small"); return; }
   sd::WgradBatch wb;
   memset(&wb, 0, sizeof(wb));
   wb.R = R;
-  wb.rows_per_slice = (R + slices - 1) / slices;
+  wb.rows_per_slice = rows_per_slice;
+  wb.slice0 = s_lo;
   for (int g = 0; g < L.G; ++g) {
     sd::WgradP& p = wb.p[wb.count++];
     p.dY = dY + (size_t)g * dy_gstride; p.ldy = ldy;
     p.X = X + (size_t)g * x_gstride; p.ldx = ldx;
     p.X2 = X2; p.ldx2 = ldx2;
     p.K1 = K1; p.K = L.K; p.N = L.N;
-    p.dW = h.wg_scratch + (block ? g : 0);
+    p.dW = scratch + (block ? g : 0);
     p.sn = block ? (long long)L.K * L.G : L.K;
     p.sk = block ? L.G : 1;
     p.slice_stride = numel;
   }
-  dim3 grid((L.N + 63) / 64, (L.K + 63) / 64, wb.count * slices);
+  dim3 grid((L.N + 63) / 64, (L.K + 63) / 64, wb.count * (s_hi - s_lo));
   launch_k(cx.st, sd::wgrad_f32_kernel, grid, dim3(256), 0, wb);
   cx.check("wgrad_f32_kernel");
-  launch_k(cx.st, sd::wgrad_reduce_kernel, dim3(grid1d(numel, 256)), dim3(256), 0, (const float*)h.wg_scratch, numel,
-           slices, numel, dW);
+}
+static void wgrad_finish(Ctx& cx, const LinearW& L, const float* scratch, int slices, float* dW) {
+  if (cx.err) return;
+  const long long numel = (long long)L.G * L.N * L.K;
+  launch_k(cx.st, sd::wgrad_reduce_kernel, dim3(grid1d(numel, 256)), dim3(256), 0, scratch, numel, slices, numel, dW);
   cx.check("wgrad_reduce_kernel");
+}
+// dW (+)= dY^T [X | X2] for a Linear (reference layout (N,K)) or the G blocks of a BlockLinear ((O/G, I/G, G)).
+// Rows are cut into fixed slices (more CTAs, short dependent chains); partials land in the scratch and are
+// added to dW in slice order.
+static int wgrad_rows_per_slice() {
+  static int v = env_flag("SD_WGRAD_ROWS", 256);   // measured on B200 (T*B = 1024 rows): 64: 4.81, 128: 4.78, 256: 4.74, 512: 4.79 ms fwd+bwd
+  return v;
+}
+static void wgrad_linear(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride,
+                         const float* X, int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* dW) {
+  if (!dW || cx.err) return;
+  sd_handle& h = *cx.h;
+  const long long numel = (long long)L.G * L.N * L.K;
+  const int rows_per_slice = wgrad_rows_per_slice();
+  int slices = (R + rows_per_slice - 1) / rows_per_slice;
+  const int max_slices = (int)(h.wg_scratch_elems / numel);
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) { cx.err = fail(SD_ERR_WORKSPACE, "wgrad scratch too small"); return; }
+  wgrad_partial(cx, R, L, block, dY, ldy, dy_gstride, X, ldx, x_gstride, K1, X2, ldx2, h.wg_scratch, (R + slices - 1) / slices,
+                0, slices);
+  wgrad_finish(cx, L, h.wg_scratch, slices, dW);
 }
 static void colsum(Ctx& cx, const float* in, int ld, int R, int W, float* out) {
   if (!out || cx.err) return;
@@ -2133,6 +2176,51 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
     base.stride = 1;
     cudaMemsetAsync(bw.carry_z, 0, (size_t)B * SK * sizeof(float), cx.st);
     cudaMemsetAsync(bw.carry_d, 0, (size_t)B * D * sizeof(float), cx.st);
+    // Weight-gradient work list (dW = dY^T X over all T*B taped rows, cut into row slices of whole time steps).  The scan
+    // runs t = T-1 .. 0, so slice s (steps [s*sl_steps, (s+1)*sl_steps)) is final once step s*sl_steps is done: its
+    // partial products are launched right then on a forked stream and overlap the rest of the latency-bound scan; only
+    // slice 0 and the in-order slice sums remain after the scan.  Same slices, same summation order as the unforked pass.
+    struct WgL {
+      const LinearW* L; bool block; const float* dY; int ldy, dyg; const float* X; int ldx, xg, K1; const float* X2; int ldx2;
+      float* dW; size_t off;
+    };
+    std::vector<WgL> wl;
+    const int RT = B * T;
+    const int Dg = h->Dg;
+    const int rows_per_slice = wgrad_rows_per_slice();
+    int nsl = 0, sl_steps = 0;
+    bool early = false;
+    cudaStream_t side = nullptr;
+    if (wg) {
+      const StepBufs& tp = h->tape;
+      auto add = [&](const LinearW& L, bool block, const float* dY, int ldy, int dyg, const float* X, int ldx, int xg, int K1,
+                     const float* X2, int ldx2, float* dW) {
+        if (dW) wl.push_back({&L, block, dY, ldy, dyg, X, ldx, xg, K1, X2, ldx2, dW, 0});
+      };
+      add(h->in0, false, bw.d_vin, 3 * U, 0, tp.din, D, 0, D, nullptr, 0, W[0]);
+      add(h->in1, false, bw.d_vin + U, 3 * U, 0, tp.zin, SK, 0, SK, nullptr, 0, W[3]);
+      add(h->in2, false, bw.d_vin + 2 * U, 3 * U, 0, tp.ain, c.A, 0, c.A, nullptr, 0, W[6]);
+      add(h->hid, true, bw.d_hpre, D, Dg, tp.din, D, Dg, Dg, tp.x, 3 * U, W[9]);
+      add(h->gru, true, bw.d_q, 3 * D, 3 * Dg, tp.h, D, Dg, Dg, nullptr, 0, W[12]);
+      int wi = 14;
+      for (int l = 0; l < c.obs_layers; ++l, wi += 3) {
+        if (l == 0) add(h->obs[0], false, bw.d_v[0], U, 0, tp.dnew, D, 0, D, tp.emb, E, W[wi]);
+        else add(h->obs[l], false, bw.d_v[l], U, 0, tp.o[l - 1], U, 0, U, nullptr, 0, W[wi]);
+      }
+      add(h->obs_logit, false, bw.d_lg, SK, 0, tp.o[c.obs_layers - 1], U, 0, U, nullptr, 0, W[wi]);
+      if (wgrad_early_enabled() && !cx.trace && B <= rows_per_slice && rows_per_slice % B == 0) {
+        sl_steps = rows_per_slice / B;
+        nsl = (T % sl_steps == 0) ? T / sl_steps : 0;
+        size_t need = 0;
+        for (WgL& l : wl) { l.off = need; need += (size_t)l.L->G * l.L->N * l.L->K * (size_t)(nsl > 0 ? nsl : 1); }
+        early = nsl >= 2 && nsl <= 8 && need <= h->wg_early_elems;
+      }
+      if (early) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(cx.st, &cs);
+        side = (cs == cudaStreamCaptureStatusActive) ? h->cap_side : h->side_stream;
+      }
+    }
     // The carry (grads of a step's input state, cut where is_first) is never materialised inside the loop:
     // the first consumers of step t (sample_bwd, gates_bwd) assemble it from step t+1's pieces
     // (t_dz | dd + t_din0 + dxin[:, g, :Dg]) and step t+1's keep mask.
@@ -2153,6 +2241,17 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
                      d_deters ? d_deters + (size_t)t * D : nullptr, T * D, bw.t_dxe, D, has_next ? bw.t_din0 : nullptr,
                      has_next ? bw.t_dxin : nullptr, keep_next);
       if (cx.err) return;
+      if (early && t > 0 && t % sl_steps == 0) {   // slice t / sl_steps is final: fork its partial products
+        const int sidx = t / sl_steps;
+        cudaEventRecord(h->ev_fork, cx.st);
+        cudaStreamWaitEvent(side, h->ev_fork, 0);
+        cudaStream_t main_st = cx.st;
+        cx.st = side;
+        for (const WgL& l : wl)
+          wgrad_partial(cx, RT, *l.L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2, h->wg_early + l.off,
+                        rows_per_slice, sidx, sidx + 1);
+        cx.st = main_st;
+      }
     }
     if (cx.err) return;
     {  // grads of the initial state: step 0's pieces with step 0's reset cut (rssm.py:161-165)
@@ -2166,32 +2265,33 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
     if (d_init_deter) cudaMemcpyAsync(d_init_deter, bw.carry_d, (size_t)B * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
     if (!wg) return;
     // ---- weight gradients: one contraction over all T*B taped row-steps per layer (fixed order)
-    const int RT = B * T;
-    const StepBufs& tp = h->tape;
-    const int Dg = h->Dg;
+    if (early) {
+      // slice 0 finishes with the scan; the other slices were launched on the forked stream as the scan passed them
+      for (const WgL& l : wl)
+        wgrad_partial(cx, RT, *l.L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2, h->wg_early + l.off,
+                      rows_per_slice, 0, 1);
+      cudaEventRecord(h->ev_join, side);
+      cudaStreamWaitEvent(cx.st, h->ev_join, 0);
+      for (const WgL& l : wl) wgrad_finish(cx, *l.L, h->wg_early + l.off, nsl, l.dW);   // slices summed in ascending order
+    } else {
+      for (const WgL& l : wl)
+        wgrad_linear(cx, RT, *l.L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2, l.dW);
+    }
     int i = 0;
-    wgrad_linear(cx, RT, h->in0, false, bw.d_vin, 3 * U, 0, tp.din, D, 0, D, nullptr, 0, W[0]);
     colsum(cx, bw.d_vin, 3 * U, RT, U, W[1]);
     colsum(cx, bw.dmn_in, 3 * U, RT, U, W[2]);
-    wgrad_linear(cx, RT, h->in1, false, bw.d_vin + U, 3 * U, 0, tp.zin, SK, 0, SK, nullptr, 0, W[3]);
     colsum(cx, bw.d_vin + U, 3 * U, RT, U, W[4]);
     colsum(cx, bw.dmn_in + U, 3 * U, RT, U, W[5]);
-    wgrad_linear(cx, RT, h->in2, false, bw.d_vin + 2 * U, 3 * U, 0, tp.ain, c.A, 0, c.A, nullptr, 0, W[6]);
     colsum(cx, bw.d_vin + 2 * U, 3 * U, RT, U, W[7]);
     colsum(cx, bw.dmn_in + 2 * U, 3 * U, RT, U, W[8]);
-    wgrad_linear(cx, RT, h->hid, true, bw.d_hpre, D, Dg, tp.din, D, Dg, Dg, tp.x, 3 * U, W[9]);
     colsum(cx, bw.d_hpre, D, RT, D, W[10]);
     colsum(cx, bw.dmn_h, D, RT, D, W[11]);
-    wgrad_linear(cx, RT, h->gru, true, bw.d_q, 3 * D, 3 * Dg, tp.h, D, Dg, Dg, nullptr, 0, W[12]);
     colsum(cx, bw.d_q, 3 * D, RT, 3 * D, W[13]);
     i = 14;
     for (int l = 0; l < c.obs_layers; ++l, i += 3) {
-      if (l == 0) wgrad_linear(cx, RT, h->obs[0], false, bw.d_v[0], U, 0, tp.dnew, D, 0, D, tp.emb, E, W[i]);
-      else wgrad_linear(cx, RT, h->obs[l], false, bw.d_v[l], U, 0, tp.o[l - 1], U, 0, U, nullptr, 0, W[i]);
       colsum(cx, bw.d_v[l], U, RT, U, W[i + 1]);
       colsum(cx, bw.dmn_v[l], U, RT, U, W[i + 2]);
     }
-    wgrad_linear(cx, RT, h->obs_logit, false, bw.d_lg, SK, 0, tp.o[c.obs_layers - 1], U, 0, U, nullptr, 0, W[i]);
     colsum(cx, bw.d_lg, SK, RT, SK, W[i + 1]);
     // _img_net takes no part in observe(): its gradient slots are left untouched.
   });

@@ -444,6 +444,7 @@ struct WgradBatch {
   int count;
   int R;
   int rows_per_slice;          // rows are cut into gridDim.z / count slices (fixed assignment => deterministic)
+  int slice0;                  // first slice this launch covers (a launch may handle a sub-range of the slices)
   WgradP p[kMaxBatch];
 };
 
@@ -454,7 +455,7 @@ struct WgradBatch {
 // chunk's MMAs (register prefetch).
 __global__ void __launch_bounds__(256) wgrad_f32_kernel(const WgradBatch b) {
   pdl_prologue();
-  const int prob = blockIdx.z % b.count, slice = blockIdx.z / b.count;
+  const int prob = blockIdx.z % b.count, slice = b.slice0 + blockIdx.z / b.count;
   const WgradP& p = b.p[prob];
   const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
   if (n0 >= p.N || k0 >= p.K) return;
