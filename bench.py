@@ -423,7 +423,7 @@ def run_gpu(args):
             "breakdown_ms": {"observe_fwd": ms_obs / args.steps, "world_model_update": None if ms_wm is None else ms_wm / args.steps, "observe_fwd_bwd": None if ms_obs_fb is None else ms_obs_fb / args.steps,
                              "imagine_fwd": ms_imag / args.steps, "imagine_fwd_bwd_dgrad": None if ms_imag_fb is None else ms_imag_fb / args.steps, "heads_lambda": ms_heads / args.steps},
             "roofline": {"bound": "tensor", "achieved": imag_tflops, "peak": sus, "unit": "TFLOP/s", "frac": imag_tflops / sus,
-                         "traffic": 1.10e9, "traffic_source": "ncu --cache-control none, dram__bytes_read+write summed over the launches of one sd_imagine_fwd call (profiles/r01b_imagine_warm_cache.txt); algorithmic HBM bytes 2.12e8",
+                         "traffic": 8.11e8, "traffic_source": "ncu --cache-control none, dram__bytes_read+write summed over the launches of one sd_imagine_fwd call (profiles/r01c_imagine_warm_cache.txt, minus the driver script's own at::reduce); algorithmic HBM bytes 2.12e8",
                          "kernel": "sd_imagine_fwd scan (tcgen05 GEMMs + fused row kernels, one CUDA graph of 13 launches per step)",
                          "peak_source": f"{how} bf16_tflops_sustained (burst {burst})",
                          "flop_per_unit": FLOP_IMAG_STEP, "units_per_launch": N * H},
