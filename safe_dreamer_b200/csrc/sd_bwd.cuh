@@ -33,10 +33,11 @@ __global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch 
   const size_t row = blockIdx.x;
   const float* v = p.v + row * p.ld_v;
   const float* dout = p.dout + row * p.ld_dout;
-  float vv[8], dn[8], nn[8], gw[8];
+  float vv[8], dn[8], nn[8], gw[8], dsl[8], dy[8];
   float ss = 0.f;
-  // the saved pre-norm values (forward tape) and the RMS scale do not depend on the preceding kernel of the
-  // reverse scan: fetch them before the PDL wait; only `dout` has to wait
+  // Everything that only needs the forward tape (saved pre-norm values, RMS scale) is done BEFORE the PDL wait: the row
+  // statistic (one block reduction), n = v * rho and silu'(m).  After the wait only `dout` is fetched -- all slices of all
+  // eight elements in flight together -- followed by the second reduction.
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 256;
@@ -44,26 +45,42 @@ __global__ void __launch_bounds__(256) normact_bwd_kernel(const NormActBwdBatch 
     gw[i] = (c < p.width) ? __ldg(p.w + c) : 0.f;
     ss = fmaf(vv[i], vv[i], ss);
   }
-  pdl_prologue();
   ss = block_sum(ss, sh);
   const float rho = 1.f / sqrtf(ss / (float)p.width + kRmsEps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float n = vv[i] * rho;
+    const float m = n * gw[i];
+    const float sg = sigmoidf_(m);
+    nn[i] = n;
+    dsl[i] = sg * (1.f + m * (1.f - sg));
+  }
+  pdl_prologue();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = threadIdx.x + i * 256;
+    dy[i] = (c < p.width) ? dout[c] : 0.f;
+  }
+  for (int g = 1; g < p.nsum; ++g) {   // fixed order => deterministic; the eight loads of a slice are independent
+    const float* ds = dout + g * p.sum_stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (c < p.width) dy[i] += ds[c];
+    }
+  }
   float dot = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = threadIdx.x + i * 256;
-    dn[i] = 0.f; nn[i] = 0.f;
+    dn[i] = 0.f;
     if (c < p.width) {
-      const float w = gw[i];
-      const float n = vv[i] * rho;
-      const float m = n * w;
-      const float sg = sigmoidf_(m);
-      float dy = dout[c];
-      for (int g = 1; g < p.nsum; ++g) dy += dout[g * p.sum_stride + c];
-      const float dm = dy * (sg * (1.f + m * (1.f - sg)));
-      if (p.dmn) p.dmn[row * p.ld_dmn + c] = dm * n;
-      nn[i] = n;
-      dn[i] = dm * w;
-      dot = fmaf(dn[i], n, dot);
+      const float dm = dy[i] * dsl[i];
+      if (p.dmn) p.dmn[row * p.ld_dmn + c] = dm * nn[i];
+      dn[i] = dm * gw[i];
+      dot = fmaf(dn[i], nn[i], dot);
+    } else {
+      nn[i] = 0.f;
     }
   }
   dot = block_sum(dot, sh) / (float)p.width;
