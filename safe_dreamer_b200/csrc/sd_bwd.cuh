@@ -173,6 +173,8 @@ __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const f
     pr_ = __ldg(q + qo); pc_ = __ldg(q + qo + Dg); pu_ = __ldg(q + qo + 2 * Dg);
     pd_ = __ldg(deter_in + row * ld_in + d);
   }
+  // ... and so are the gate activations recomputed from them
+  const float pRg = sigmoidf_(pr_), pC = tanhf(pRg * pc_), pUu = sigmoidf_(pu_ - 1.f);
   pdl_prologue();
   for (bool first = true; i < total; i += stride, first = false) {
     const int d = (int)(i % D);
@@ -181,7 +183,7 @@ __global__ void gates_bwd_kernel(const float* __restrict__ ga, int ld_a, const f
     const size_t qo = row * 3 * D + (size_t)gi * 3 * Dg + o;
     const float r = first ? pr_ : q[qo], c = first ? pc_ : q[qo + Dg], uu = first ? pu_ : q[qo + 2 * Dg];
     const float din = first ? pd_ : deter_in[row * ld_in + d];
-    const float Rg = sigmoidf_(r), C = tanhf(Rg * c), Uu = sigmoidf_(uu - 1.f);
+    const float Rg = first ? pRg : sigmoidf_(r), C = first ? pC : tanhf(Rg * c), Uu = first ? pUu : sigmoidf_(uu - 1.f);
     float carry = ga ? ga[row * ld_a + d] : 0.f;
     if (ga2) carry += ga2[row * D + d];
     if (dxin) carry += dxin[(row * G + gi) * (size_t)Kb + o];
