@@ -372,6 +372,14 @@ def run_gpu(args):
     for _ in range(3):
         e2e_step()
     torch.cuda.synchronize()
+    if os.environ.get("SD_BENCH_E2E_PROFILE") and rank == 0:   # diagnostic: where the end-to-end step spends GPU / CPU time
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                e2e_step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=60), file=sys.stderr)
+        prof.export_chrome_trace(os.environ["SD_BENCH_E2E_PROFILE"])
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()

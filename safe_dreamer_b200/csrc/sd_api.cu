@@ -2191,6 +2191,20 @@ static void wgrad_partial(Ctx& cx, int R, const LinearW& L, bool block, const fl
 static void wgrad_finish(Ctx& cx, const LinearW& L, const float* scratch, int slices, float* dW) {
   if (cx.err) return;
   const long long numel = (long long)L.G * L.N * L.K;
+  const bool vec = (numel % 4) == 0 && ((reinterpret_cast<uintptr_t>(scratch) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0 &&
+                   (slices == 1 || slices == 2 || slices == 4 || slices == 8);
+  if (vec) {
+    const long long n4 = numel / 4;
+    const dim3 grid(grid1d(n4, 256)), block(256);
+    const float4* p4 = reinterpret_cast<const float4*>(scratch);
+    float4* d4 = reinterpret_cast<float4*>(dW);
+    if (slices == 1) launch_k(cx.st, sd::wgrad_reduce4_kernel<1>, grid, block, 0, p4, n4, n4, d4);
+    else if (slices == 2) launch_k(cx.st, sd::wgrad_reduce4_kernel<2>, grid, block, 0, p4, n4, n4, d4);
+    else if (slices == 4) launch_k(cx.st, sd::wgrad_reduce4_kernel<4>, grid, block, 0, p4, n4, n4, d4);
+    else launch_k(cx.st, sd::wgrad_reduce4_kernel<8>, grid, block, 0, p4, n4, n4, d4);
+    cx.check("wgrad_reduce4_kernel");
+    return;
+  }
   launch_k(cx.st, sd::wgrad_reduce_kernel, dim3(grid1d(numel, 256)), dim3(256), 0, scratch, numel, slices, numel, dW);
   cx.check("wgrad_reduce_kernel");
 }
@@ -2220,6 +2234,26 @@ static void colsum(Ctx& cx, const float* in, int ld, int R, int W, float* out) {
   launch_k(cx.st, sd::colsum_kernel, dim3((W + 31) / 32), dim3(32, 32), 0, in, ld, R, W, out);
   cx.check("colsum_kernel");
 }
+
+struct ColsumList {
+  sd::ColsumBatch b;
+  int max_w = 0;
+  ColsumList() { memset(&b, 0, sizeof(b)); }
+  void flush(Ctx& cx, int R) {
+    if (b.count == 0 || cx.err) return;
+    b.R = R;
+    launch_k(cx.st, sd::colsum_batch_kernel, dim3((max_w + 31) / 32, b.count), dim3(32, 32), 0, b);
+    cx.check("colsum_batch_kernel");
+    b.count = 0;
+    max_w = 0;
+  }
+  void add(Ctx& cx, const float* in, int ld, int R, int W, float* out) {
+    if (!out || cx.err) return;
+    if (b.count == 16) flush(cx, R);
+    b.p[b.count++] = {in, ld, W, out};
+    if (W > max_w) max_w = W;
+  }
+};
 
 extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs, const float* d_deters,
                               const float* d_logits, float* d_embed, float* d_init_stoch, float* d_init_deter,
@@ -2343,21 +2377,23 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
         wgrad_linear(cx, RT, *l.L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2, l.dW);
     }
     int i = 0;
-    colsum(cx, bw.d_vin, 3 * U, RT, U, W[1]);
-    colsum(cx, bw.dmn_in, 3 * U, RT, U, W[2]);
-    colsum(cx, bw.d_vin + U, 3 * U, RT, U, W[4]);
-    colsum(cx, bw.dmn_in + U, 3 * U, RT, U, W[5]);
-    colsum(cx, bw.d_vin + 2 * U, 3 * U, RT, U, W[7]);
-    colsum(cx, bw.dmn_in + 2 * U, 3 * U, RT, U, W[8]);
-    colsum(cx, bw.d_hpre, D, RT, D, W[10]);
-    colsum(cx, bw.dmn_h, D, RT, D, W[11]);
-    colsum(cx, bw.d_q, 3 * D, RT, 3 * D, W[13]);
+    ColsumList cl;   // bias / RMS-scale gradients of every layer: one launch
+    cl.add(cx, bw.d_vin, 3 * U, RT, U, W[1]);
+    cl.add(cx, bw.dmn_in, 3 * U, RT, U, W[2]);
+    cl.add(cx, bw.d_vin + U, 3 * U, RT, U, W[4]);
+    cl.add(cx, bw.dmn_in + U, 3 * U, RT, U, W[5]);
+    cl.add(cx, bw.d_vin + 2 * U, 3 * U, RT, U, W[7]);
+    cl.add(cx, bw.dmn_in + 2 * U, 3 * U, RT, U, W[8]);
+    cl.add(cx, bw.d_hpre, D, RT, D, W[10]);
+    cl.add(cx, bw.dmn_h, D, RT, D, W[11]);
+    cl.add(cx, bw.d_q, 3 * D, RT, 3 * D, W[13]);
     i = 14;
     for (int l = 0; l < c.obs_layers; ++l, i += 3) {
-      colsum(cx, bw.d_v[l], U, RT, U, W[i + 1]);
-      colsum(cx, bw.dmn_v[l], U, RT, U, W[i + 2]);
+      cl.add(cx, bw.d_v[l], U, RT, U, W[i + 1]);
+      cl.add(cx, bw.dmn_v[l], U, RT, U, W[i + 2]);
     }
-    colsum(cx, bw.d_lg, SK, RT, SK, W[i + 1]);
+    cl.add(cx, bw.d_lg, SK, RT, SK, W[i + 1]);
+    cl.flush(cx, RT);
     // _img_net takes no part in observe(): its gradient slots are left untouched.
   });
 }

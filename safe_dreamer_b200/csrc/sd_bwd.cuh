@@ -252,6 +252,42 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ 
   }
 }
 
+// The same column sums for up to 16 matrices of R rows in ONE launch (blockIdx.y = matrix): the bias / RMS-scale gradients of
+// all layers after the reverse scan.  Eight row loads per lane are in flight at a time; the additions keep colsum_kernel's
+// order (rows lane, lane+32, ... then lanes ascending), so the results are bit-identical to 12 separate launches, which cost
+// 10 us each on the critical path (8-CTA grids, 32 dependent loads per lane).
+struct ColsumP { const float* in; int ld; int W; float* out; };
+struct ColsumBatch { int count; int R; ColsumP p[16]; };
+__global__ void __launch_bounds__(1024) colsum_batch_kernel(const ColsumBatch b) {
+  pdl_prologue();
+  __shared__ float sh[32][33];
+  const ColsumP& p = b.p[blockIdx.y];
+  if ((int)blockIdx.x * 32 >= p.W) return;   // block-uniform
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < p.W) {
+    for (int r0 = threadIdx.y; r0 < b.R; r0 += 32 * 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = r0 + 32 * j;
+        v[j] = r < b.R ? p.in[(size_t)r * p.ld + c] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r0 + 32 * j < b.R) s += v[j];
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < p.W) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += sh[j][threadIdx.x];
+    p.out[c] += t;
+  }
+}
+
 // Backward of the bounded-normal actor sample (distributions.py:217-222): action = tanh(mean) + std*eps,
 // std = (max-min)*sigmoid(sraw+2)+min.  d_act = upstream + d(abar)/max(|a|,1) (rssm.py:44, detached clip).
 __global__ void actor_sample_bwd_kernel(const float* __restrict__ out, const float* __restrict__ eps, int ld_n,

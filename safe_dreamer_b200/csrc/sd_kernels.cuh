@@ -541,6 +541,26 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, long long
   }
 }
 
+// Same sum, 16 bytes per thread and all S slice loads of an element group in flight together (the run-time loop above
+// issues them one L2/DRAM round trip at a time: 34 us per launch in the end-to-end profile).  Same order => same bits.
+template <int S>
+__global__ void __launch_bounds__(256) wgrad_reduce4_kernel(const float4* __restrict__ partial, long long stride4,
+                                                            long long numel4, float4* dst) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 v[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) v[k] = __ldg(partial + k * stride4 + i);
+    float4 d = dst[i];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < S; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+    d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+    dst[i] = d;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight repacking: reference layout -> Wt[g][k][ldw] fp32 (forward operand, n contiguous),
 // Wn[g][n][ldk] fp32 (dgrad operand, k contiguous) and bf16 copies of both for the tcgen05 path.
