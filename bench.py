@@ -193,7 +193,7 @@ def run_gpu(args):
     # start states), so they run on a second stream concurrently with the posterior backward scan and the
     # gradient all-reduce; both are latency bound and use disjoint workspace regions.
     side = torch.cuda.Stream(device=dev)
-    ev_fwd, ev_side = torch.cuda.Event(), torch.cuda.Event()
+    ev_fwd, ev_side, ev_w = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     overlap = have_bwd and not args.no_overlap
 
     def hot_path():
@@ -325,10 +325,18 @@ def run_gpu(args):
     h_s0, h_d0 = torch.zeros(B, c.S, c.K).pin_memory(), torch.zeros(B, c.D).pin_memory()
     h2d = sum(x.numel() * x.element_size() for x in (h_embed, h_action, h_first, h_s0, h_d0))
 
-    def e2e_step():
+    pin_res = [torch.zeros(1).pin_memory() for _ in range(2)]
+    ev_res = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_step(slot=None):
+        main0 = torch.cuda.current_stream(dev)
+        side.wait_stream(main0)
+        with torch.cuda.stream(side):                   # weight repack (weights change once per update in training) runs
+            rssm.refresh_weights(force=True)            # beside the host->device copies of the step's inputs
+            ev_w.record(side)
         e_, a_, f_ = h_embed.to(dev, non_blocking=True), h_action.to(dev, non_blocking=True), h_first.to(dev, non_blocking=True)
         s_, d_ = h_s0.to(dev, non_blocking=True), h_d0.to(dev, non_blocking=True)
-        rssm.refresh_weights(force=True)            # weights change once per update in training
+        main0.wait_event(ev_w)
         rssm.precision = "fp32"
         work = None
         if have_bwd:                                    # posterior fwd+bwd through autograd (sd_observe_bwd)
@@ -367,7 +375,11 @@ def run_gpu(args):
             r_ = imag()
         if work is not None:
             work.wait()
-        return float(r_[-1].mean().item())               # D2H read of the step's result
+        if slot is None:
+            return float(r_[-1].mean().item())           # D2H read of the step's result (blocking)
+        pin_res[slot].copy_(r_[-1].mean().reshape(1), non_blocking=True)   # async D2H read, consumed one step later
+        ev_res[slot].record(main)
+        return None
 
     for _ in range(3):
         e2e_step()
@@ -392,10 +404,32 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     if os.environ.get("SD_BENCH_VERBOSE"):
         print("e2e per-iteration ms:", [round(x, 2) for x in e2e_iter], file=sys.stderr)
+    # the same loop with the result read pipelined (what a training loop that logs asynchronously does): every step still
+    # copies its inputs from pinned memory and copies its result back, but the host looks at the value one step later, so
+    # the Python-side launch work of step k+1 overlaps the GPU work of step k.  Reported as an extra key, not as `e2e`.
+    e2e_step(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    seen = []
+    for k in range(args.steps):
+        e2e_step(k & 1)
+        if k > 0:
+            ev_res[(k - 1) & 1].synchronize()
+            seen.append(float(pin_res[(k - 1) & 1][0]))
+    ev_res[(args.steps - 1) & 1].synchronize()
+    seen.append(float(pin_res[(args.steps - 1) & 1][0]))
+    torch.cuda.synchronize()
+    e2e_async_s = time.perf_counter() - t1
+    assert len(seen) == args.steps and all(np.isfinite(seen))
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+        t = torch.tensor([e2e_async_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_async_s = float(t.item())
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -438,6 +472,8 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "e2e": {"value": N * H * args.steps * world / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e_async_read": {"value": N * H * args.steps * world / e2e_async_s, "unit": "steps/s", "ms_per_step": 1e3 * e2e_async_s / args.steps,
+                               "note": "same loop, the D2H result copy is consumed one step later (host launch work overlaps the previous step)"},
             "clocks": sampler.summary(),
         }
         print(json.dumps(line))
