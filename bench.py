@@ -318,6 +318,10 @@ def run_gpu(args):
         heads[key] = m
     dreamer_ops.attach_heads(rssm, **heads)
     rssm.use_graph, rssm.auto_refresh, rssm.static_outputs = True, False, True
+    # the step's inputs land in persistent device tensors (copy_ from pinned memory), so no staging copies are needed, and
+    # the optimizer would update the parameters in place, so the module tree is not re-walked on every call
+    rssm.stage_inputs, rssm.cache_params = False, True
+    rssm.static_grads = True    # p.grad is reset to None every step (no accumulation): it may alias the gradient bucket
     rssm.max_rows, rssm.max_steps = N, max(T, H)
     h_embed = torch.from_numpy(emb_np).pin_memory()
     h_action = torch.from_numpy(act_np).pin_memory()
@@ -325,6 +329,7 @@ def run_gpu(args):
     h_s0, h_d0 = torch.zeros(B, c.S, c.K).pin_memory(), torch.zeros(B, c.D).pin_memory()
     h2d = sum(x.numel() * x.element_size() for x in (h_embed, h_action, h_first, h_s0, h_d0))
 
+    dev_in = [torch.empty_like(x, device=dev) for x in (h_embed, h_action, h_first, h_s0, h_d0)]
     pin_res = [torch.zeros(1).pin_memory() for _ in range(2)]
     ev_res = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -334,13 +339,16 @@ def run_gpu(args):
         with torch.cuda.stream(side):                   # weight repack (weights change once per update in training) runs
             rssm.refresh_weights(force=True)            # beside the host->device copies of the step's inputs
             ev_w.record(side)
-        e_, a_, f_ = h_embed.to(dev, non_blocking=True), h_action.to(dev, non_blocking=True), h_first.to(dev, non_blocking=True)
-        s_, d_ = h_s0.to(dev, non_blocking=True), h_d0.to(dev, non_blocking=True)
+        with torch.no_grad():
+            for dst_, src_ in zip(dev_in, (h_embed, h_action, h_first, h_s0, h_d0)):   # host -> device, every step
+                dst_.copy_(src_, non_blocking=True)
+        e_, a_, f_, s_, d_ = dev_in
+        e_.grad = None
         main0.wait_event(ev_w)
         rssm.precision = "fp32"
         work = None
         if have_bwd:                                    # posterior fwd+bwd through autograd (sd_observe_bwd)
-            for p_ in rssm.parameters():
+            for p_ in rssm._params():
                 p_.grad = None
             e_.requires_grad_(True)
             st_, dt_, lg_ = rssm.observe(e_, a_, (s_, d_), f_)

@@ -47,10 +47,16 @@ def imagine(rssm, start, imag_horizon, act_noise=None, u=None):
     if u is None:
         u = rssm._uniform(N, imag_horizon, rssm._stoch, rssm._discrete)
     if act_noise is None:
-        if eng.cfg.act_kind == 0:
-            act_noise = torch.randn(N, imag_horizon, rssm._act_dim, device=dev)
+        shape = (N, imag_horizon, rssm._act_dim)
+        if rssm.static_outputs and not rssm.stage_inputs:   # pointer-stable noise buffer, regenerated in place
+            buf = rssm._rt.ubuf.get(("act",) + shape)
+            if buf is None or buf.device != dev:
+                buf = rssm._rt.ubuf[("act",) + shape] = torch.empty(*shape, device=dev)
+            act_noise = buf.normal_() if eng.cfg.act_kind == 0 else buf.uniform_().clamp_(_U_LO, 1 - _U_LO)
+        elif eng.cfg.act_kind == 0:
+            act_noise = torch.randn(*shape, device=dev)
         else:
-            act_noise = torch.rand(N, imag_horizon, rssm._act_dim, device=dev).clamp_(_U_LO, 1 - _U_LO)
+            act_noise = torch.rand(*shape, device=dev).clamp_(_U_LO, 1 - _U_LO)
     return eng.imagine(stoch, deter, u, act_noise, imag_horizon, flags=rssm._flags())
 
 

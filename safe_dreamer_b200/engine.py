@@ -54,6 +54,7 @@ class Engine:
         # point and shape overwrites.  Pointer-stable outputs keep the CUDA-graph cache (keyed on pointers)
         # hot; with fresh tensors per call the cache only hits when the allocator returns the same blocks.
         self.static_outputs = False
+        self.stage_inputs = True    # static mode: stage inputs in engine-owned buffers (False: the caller's are pointer-stable)
         self._outs = {}
 
     @classmethod
@@ -128,7 +129,7 @@ class Engine:
     def _stage(self, t, tag):
         """static mode: copy an input into an engine-owned buffer so the pointers seen by the C ABI (and the
         CUDA-graph cache keyed on them) never change between calls."""
-        if not self.static_outputs or t is None:
+        if not self.static_outputs or not self.stage_inputs or t is None:
             return t
         key = ("in_" + tag, tuple(t.shape), t.dtype)
         buf = self._outs.get(key)

@@ -97,6 +97,8 @@ class _Runtime:
         self.sig = None
         self.limits = (0, 0, 0)
         self.bucket = None
+        self.pcache = None     # cached (module id, name -> Parameter) lists (RSSM.cache_params)
+        self.ubuf = {}         # pointer-stable noise buffers (RSSM.stage_inputs = False)
 
     def __deepcopy__(self, memo):
         return _Runtime()
@@ -164,11 +166,19 @@ class _ObserveFn(torch.autograd.Function):
             else:
                 wg = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in rssm.named_parameters()}
         d_embed, d_is, d_id = eng.observe_bwd(ctx.B, ctx.T, d_st, d_dt, d_lg, need_embed, need_init, wg, ctx.flags)
-        pg = [None if wg is None else (wg[n].clone() if rssm.static_outputs else wg[n])
-              for n, _ in rssm.named_parameters()]
+        # static mode: gradients are copied out of the pointer-stable bucket -- unless static_grads is set: then p.grad
+        # ALIASES the bucket slices (fresh view objects, which autograd adopts without a copy) and is only valid until the
+        # next backward of this module (needs zero_grad(set_to_none=True) between backwards; no gradient accumulation)
+        pnames = [n for n, _ in rssm._param_dicts()[0][1].items()]
+        if wg is None:
+            pg = [None] * len(pnames)
+        elif rssm.static_outputs:
+            pg = [wg[n].view_as(wg[n]) if rssm.static_grads else wg[n].clone() for n in pnames]
+        else:
+            pg = [wg[n] for n in pnames]
         if rssm.static_outputs:
             d_embed = None if d_embed is None else d_embed.clone()
-        assert set(names) == set(n for n, _ in rssm.named_parameters())
+        assert set(names) == set(pnames)
         return (None, d_embed, None, d_is, d_id, None, None, *pg)
 
 
@@ -242,6 +252,12 @@ class RSSM(nn.Module):
         self.use_graph = False         # replay scans as cached CUDA graphs
         self.auto_refresh = True       # repack weights on every call (safe with in-place optimizers)
         self.static_outputs = False    # reuse engine-owned output buffers (next same-shape call overwrites them)
+        self.stage_inputs = True       # static_outputs: copy inputs into engine-owned buffers (pointer-stable graph keys).
+        #                                False = the caller's input tensors are already pointer-stable (persistent device
+        #                                buffers filled by copy_); a changed pointer only costs a graph re-capture
+        self.static_grads = False      # static_outputs: p.grad aliases engine-owned buffers (valid until the next backward)
+        self.cache_params = False      # True = Parameter OBJECTS never change (in-place optimizers): skip the module-tree
+        #                                walk (named_parameters) on every call
         self.noise_source = None       # callable(shape, device) -> uniforms, for injected-noise parity
         self.max_rows, self.max_steps = 1024, 64
         self.head_modules = {}         # module id -> nn.Module (actor / reward / cont / value / slow value)
@@ -272,26 +288,45 @@ class RSSM(nn.Module):
                                        device=next(self.parameters()).device, **kw)
             rt.limits, rt.sig = need, None
         rt.engine.static_outputs = self.static_outputs
+        rt.engine.stage_inputs = self.stage_inputs
         self.refresh_weights(force=False)
         return rt.engine
+
+    def _param_dicts(self):
+        """[(module id, {state_dict name: Parameter})] for the RSSM and the attached heads."""
+        rt = self._rt
+        pc = rt.pcache
+        if self.cache_params and pc is not None and len(pc) == 1 + len(self.head_modules):
+            return pc
+        pc = [(MOD_RSSM, dict(self.named_parameters()))] + [(mod, dict(m.named_parameters()))
+                                                             for mod, m in self.head_modules.items()]
+        rt.pcache = pc if self.cache_params else None
+        return pc
+
+    def _params(self):
+        return list(self._param_dicts()[0][1].values())
 
     def refresh_weights(self, force=True):
         """Repack the (possibly updated in place) parameters into the kernels' layouts."""
         rt = self._rt
         if rt.engine is None:
             return
-        params = dict(self.named_parameters())
-        sig = tuple((p.data_ptr(), p._version) for p in params.values())
+        pds = self._param_dicts()
+        sig = tuple((p.data_ptr(), p._version) for p in pds[0][1].values())
         if force or self.auto_refresh or sig != rt.sig:
-            rt.engine.set_weights(MOD_RSSM, params)
-            for mod, m in self.head_modules.items():
-                rt.engine.set_weights(mod, dict(m.named_parameters()))
+            for mod, named in pds:
+                rt.engine.set_weights(mod, named)
             rt.sig = sig
 
     def _uniform(self, *shape):
         dev = next(self.parameters()).device
         if self.noise_source is not None:
             return self.noise_source(shape, dev)
+        if self.static_outputs and not self.stage_inputs:   # pointer-stable noise: regenerate in place
+            buf = self._rt.ubuf.get(shape)
+            if buf is None or buf.device != dev:
+                buf = self._rt.ubuf[shape] = torch.empty(*shape, device=dev, dtype=torch.float32)
+            return buf.uniform_().clamp_(_U_LO, 1.0 - _U_LO)
         return torch.rand(*shape, device=dev, dtype=torch.float32).clamp_(_U_LO, 1.0 - _U_LO)
 
     # ------------------------------------------------------------------ reference API
@@ -309,10 +344,10 @@ class RSSM(nn.Module):
         u = self._uniform(B, T, self._stoch, self._discrete)
         needs_grad = torch.is_grad_enabled() and (
             embed.requires_grad or stoch.requires_grad or deter.requires_grad
-            or any(p.requires_grad for p in self.parameters()))
+            or any(p.requires_grad for p in self._params()))
         if needs_grad:
             return _ObserveFn.apply(self, embed.float(), action, stoch.float(), deter.float(), reset, u,
-                                    *self.parameters())
+                                    *self._params())
         eng = self._get_engine(B, T)
         return eng.observe(embed, action, stoch, deter, reset, u, flags=self._flags())
 

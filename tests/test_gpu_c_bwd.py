@@ -89,6 +89,59 @@ def test_module_autograd_matches_reference_grads():
                                    atol=3e-5 * max(1.0, float(z["bwd_gn/" + name])), err_msg=name)
 
 
+def test_module_static_fast_path_same_grads():
+    """The low-overhead module settings bench.py's end-to-end loop uses (CUDA graphs, engine-owned outputs, caller-owned
+    pointer-stable inputs, cached parameter dicts, p.grad aliasing the gradient bucket) give bit-identical outputs and
+    gradients to the default settings, step after step (second step with different inputs in the same buffers)."""
+    from types import SimpleNamespace as NS
+    from safe_dreamer_b200.rssm import RSSM
+    c, z = load_golden("tiny_cont")
+    P = golden_params(c, z)
+    B, T = int(z["B"]), int(z["T"])
+    cfg = NS(stoch=c.S, deter=c.D, hidden=c.U, discrete=c.K, act="SiLU", unimix_ratio=c.unimix, initial="learned",
+             device="cuda", obs_layers=c.obs_layers, img_layers=c.img_layers, dyn_layers=1, blocks=c.G)
+    mods = []
+    for fast in (False, True):
+        m = RSSM(cfg, c.E, c.A).cuda()
+        m.load_state_dict({k: cu(v) for k, v in P["rssm"].items()})
+        if fast:
+            m.use_graph, m.auto_refresh, m.static_outputs = True, False, True
+            m.stage_inputs, m.cache_params, m.static_grads = False, True, True
+        mods.append(m)
+    s0, d0 = golden_initial(c, B)
+    bufs = None
+    for step in range(3):
+        embed, action, reset, u = O.synth_observe_inputs(c, B, T, seed=20 + step)
+        g = np.random.Generator(np.random.Philox(90 + step))
+        cot = [g.standard_normal(sh, dtype=np.float32) * np.float32(0.1) for sh in ((B, T, c.S, c.K), (B, T, c.D), (B, T, c.S, c.K))]
+        outs = []
+        for fast, m in zip((False, True), mods):
+            m.noise_source = lambda shape, dev: cu(u).reshape(shape)
+            for p_ in m.parameters():
+                p_.grad = None
+            if fast:   # persistent device inputs, refilled in place
+                if bufs is None:
+                    bufs = [cu(embed), cu(action), cu(reset)[..., None].contiguous(), cu(s0), cu(d0)]
+                else:
+                    with torch.no_grad():
+                        bufs[0].copy_(cu(embed)); bufs[1].copy_(cu(action)); bufs[2].copy_(cu(reset)[..., None])
+                bufs[0].grad = None
+                e, a, r, si, di = bufs
+                m.refresh_weights(force=True)
+            else:
+                e, a, r, si, di = cu(embed), cu(action), cu(reset)[..., None], cu(s0), cu(d0)
+            e.requires_grad_(True)
+            st, dt, lg = m.observe(e, a, (si, di), r)
+            torch.autograd.backward((st, dt, lg), tuple(cu(x) for x in cot))
+            outs.append(([_np(st).copy(), _np(dt).copy(), _np(lg).copy(), _np(e.grad).copy()],
+                         {n: _np(p_.grad).copy() for n, p_ in m.named_parameters() if p_.grad is not None}))
+        for x, y in zip(outs[0][0], outs[1][0]):
+            np.testing.assert_array_equal(x, y)
+        assert outs[0][1].keys() == outs[1][1].keys()
+        for n in outs[0][1]:
+            np.testing.assert_array_equal(outs[0][1][n], outs[1][1][n], err_msg=n)
+
+
 @pytest.mark.parametrize("tag", CASES)
 def test_imagine_bwd(tag):
     """dgrad-only backward through the imagination rollout (frozen weights; the attack shape)."""
