@@ -430,6 +430,40 @@ def run_latent_store():
     print("wrote latent_store.npz")
 
 
+def cnn_encoder_inputs(hw, n):
+    """Seeded image batch (B, T, H, W, 3) in [0, 1] and an upstream gradient for the embedding (restated in tests/test_cnn_oracle.py)."""
+    rng = np.random.Generator(np.random.Philox(5150 + hw))
+    obs = rng.random((n, 2, hw, hw, 3), dtype=np.float32)
+    return obs, rng
+
+
+def run_cnn_encoder(networks):
+    """ConvEncoder (networks.py:192-234) of the reference, fp32 on CPU: forward embedding and autograd gradients for a tiny
+    (32x32, depth 4) and the base (64x64, depth 16, mults 2/3/4/4 -> E = 1024) configuration."""
+    from types import SimpleNamespace as NS
+    from oracle import cnn_oracle as CO
+    out = {}
+    for tag, hw, depth, n in (("tiny", 32, 4, 2), ("base", 64, 16, 1)):
+        mults = (2, 3, 4, 4)
+        cfg = NS(act="SiLU", norm=True, kernel_size=5, minres=4, depth=depth, mults=list(mults))
+        enc = networks.ConvEncoder(cfg, (hw, hw, 3))
+        P = CO.encoder_params([depth * m for m in mults], 3, 5, seed=77 + hw)
+        enc.load_state_dict({k: t(v) for k, v in P.items()})
+        obs, rng = cnn_encoder_inputs(hw, n)
+        x = t(obs).requires_grad_(True)
+        emb = enc(x)
+        g = rng.standard_normal(tuple(emb.shape), dtype=np.float32)
+        emb.backward(t(g))
+        out[f"{tag}/emb"] = emb.detach().numpy()
+        out[f"{tag}/g"] = g
+        out[f"{tag}/d_obs"] = x.grad.numpy()
+        for k, p_ in enc.named_parameters():
+            out[f"{tag}/grad/{k}"] = p_.grad.numpy()
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cnn_encoder.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items() if k.endswith("emb")})
+
+
 def run_return_ema(networks):
     """ReturnEMA (networks.py:405-422), four consecutive calls per case (the buffer carries over)."""
     out = {}
@@ -457,6 +491,9 @@ def main():
     if "--latent-store-only" in sys.argv:
         run_latent_store()
         return
+    if "--cnn-only" in sys.argv:
+        run_cnn_encoder(networks)
+        return
     if "--optim-only" in sys.argv:
         run_optim()
         return
@@ -479,6 +516,7 @@ def main():
     run_optim()
     run_barlow()
     run_latent_store()
+    run_cnn_encoder(networks)
 
 
 if __name__ == "__main__":
