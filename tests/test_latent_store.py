@@ -55,6 +55,15 @@ def test_oracle_repeated_slot_last_row_wins():
     np.testing.assert_array_equal(sd[2, 0], deter[0, 2]); np.testing.assert_array_equal(si[2, 0], [1, 1])
 
 
+def test_latent_store_has_no_cpu_fallback():
+    """The product path fails loudly off the GPU instead of falling back to torch indexing."""
+    from safe_dreamer_b200.replay import LatentStore
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        LatentStore(8, 2, 4, 8, 12, device="cpu")
+    with pytest.raises(ValueError, match="uint8"):
+        LatentStore(8, 2, 4, 300, 12, device="cpu")
+
+
 @pytest.mark.gpu
 def test_cuda_latent_store_golden_and_duplicates(golden):
     import torch
