@@ -6,6 +6,10 @@ One "step" = one pass of the hot path over one synthetic replay batch of the bas
 handle supports it]) -> imagination rollout Dreamer._imagine from all B*T posterior states
 (N=1024 rows, H=16, in-loop actor) -> frozen reward/cont/value/slow-value heads + lambda-return.
 metric = imagined RSSM steps/s (N*H row-steps per pass / device time), whole job over all ranks.
+`value`: inputs resident in HBM, C-ABI engine calls, CUDA events, L2 flushed between iterations.
+`e2e`: the same pass through the reference-facing module API (safe_dreamer_b200.rssm.RSSM + dreamer_ops, autograd backward):
+every step copies its inputs from pinned host memory, repacks the weights (they change once per update) and reads the
+step's result back with a blocking D2H copy.  `e2e_async_read` is that loop with the result consumed one step later.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 Under torchrun every rank runs the same per-GPU workload on its own replay slice (weak scaling).
