@@ -96,37 +96,39 @@ def make_np_inputs(c):
 
 
 def run_reference(args):
+    """--impl reference: the UNMODIFIED reference modules (baseline/_ref, copied by baseline/make_ref.py) on the host
+    cores, fp32 eager, all threads: observe fwd+bwd -> Dreamer._imagine -> frozen heads + Dreamer._lambda_return.
+    Falls back to the numpy port (oracle/) only when baseline/_ref did not travel."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np  # noqa: F401
-    from oracle import rssm_oracle as O
-    cores = os.cpu_count() or 1
+    from baseline import ref_harness as RH
+    from safe_dreamer_b200 import synth as O
     c = O.Cfg(E=E, A=A)
     P = O.init_params(c, seed=0)
-    inputs = make_np_inputs(c)
-    tw = time.perf_counter()
-    oracle_step(c, P, inputs)
-    t_full = time.perf_counter() - tw
-    # bounded sample: shrink the replay rows per step so K steps stay within ~2 minutes
-    frac = min(1.0, 120.0 / (args.steps * t_full))
-    frac = max(1, int(frac * B)) / B
-    for _ in range(max(0, args.warmup - 1)):
-        oracle_step(c, P, inputs, frac)
-    t0 = time.perf_counter()
-    units = 0
-    for _ in range(args.steps):
-        n, _ = oracle_step(c, P, inputs, frac)
-        units += n
-    dt = time.perf_counter() - t0
-    val = units / dt
+    if RH.available():
+        r = RH.time_cpu(c, P, B, T, H, args.steps, args.warmup, bwd=not args.no_bwd)
+        val, dt, cores, kind = r["units"] / r["seconds"], r["seconds"], r["cores"], "reference"
+        sample = (f"{r['rows']}/{B} of the replay rows per step x{args.steps} steps; unmodified reference torch modules "
+                  f"(baseline/_ref), fp32 eager, {cores} host threads, observe fwd{'+bwd' if not args.no_bwd else ''} + _imagine + heads/lambda-return")
+    else:
+        cores = os.cpu_count() or 1
+        inputs = make_np_inputs(c)
+        tw = time.perf_counter()
+        oracle_step(c, P, inputs)
+        t_full = time.perf_counter() - tw
+        frac = max(1, int(min(1.0, 120.0 / (args.steps * t_full)) * B)) / B
+        t0 = time.perf_counter()
+        units = sum(oracle_step(c, P, inputs, frac)[0] for _ in range(args.steps))
+        dt = time.perf_counter() - t0
+        val, kind = units / dt, "port"
+        sample = f"{int(frac * B)}/{B} of the replay rows per step x{args.steps} steps (numpy port, forward only; baseline/_ref missing)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rows": N, "horizon": H},
-        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{int(frac * B)}/{B} of the replay rows per step x{args.steps} steps (numpy/BLAS, all host threads)"},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -450,17 +452,51 @@ def run_gpu(args):
         units = N * H * args.steps * world
         imag_tflops = N * H * FLOP_IMAG_STEP / (ms_imag / args.steps * 1e-3) / 1e12
         cpu = None
+        gpu_ref = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            inputs = (emb_np, act_np, rst_np, u_np, ui_np, nz_np)
-            oracle_step(c, P, inputs, 0.25)
-            t1 = time.perf_counter()
-            reps, n_units = 0, 0
-            while time.perf_counter() - t1 < 10.0:
-                n_, _ = oracle_step(c, P, inputs)
-                n_units += n_; reps += 1
-            cpu = {"value": n_units / (time.perf_counter() - t1), "unit": "steps/s", "cores": cores, "kind": "port",
-                   "sample": f"full workload x{reps} on the host (numpy oracle port of the reference path)"}
+            from baseline import ref_harness as RH
+            if RH.available():
+                # the reference's own CPU path beside the GPU number: bounded sample (~15 s) of the same workload
+                r = RH.time_cpu(c, P, B, T, H, steps=2, warmup=1, bwd=bool(have_bwd), budget_s=15.0)
+                cpu = {"value": r["units"] / r["seconds"], "unit": "steps/s", "cores": r["cores"], "kind": "reference",
+                       "sample": f"{r['rows']}/{B} replay rows x2 steps: unmodified reference torch modules (baseline/_ref), fp32 eager, "
+                                 f"observe fwd{'+bwd' if have_bwd else ''} + _imagine + heads/lambda-return"}
+            else:
+                cores = os.cpu_count() or 1
+                inputs = (emb_np, act_np, rst_np, u_np, ui_np, nz_np)
+                oracle_step(c, P, inputs, 0.25)
+                t1 = time.perf_counter()
+                reps, n_units = 0, 0
+                while time.perf_counter() - t1 < 10.0:
+                    n_, _ = oracle_step(c, P, inputs)
+                    n_units += n_; reps += 1
+                cpu = {"value": n_units / (time.perf_counter() - t1), "unit": "steps/s", "cores": cores, "kind": "port",
+                       "sample": f"full workload x{reps} on the host (numpy port, forward only; baseline/_ref missing)"}
+        if world == 1 and not args.no_gpu_reference:
+            # like-for-like bar: the unmodified reference modules on THIS GPU, per stage.  Eager modes are
+            # measured in this run; torch.compile(mode="reduce-overhead") takes minutes to trace the unrolled T=64 scan, so
+            # it is measured by `--ref-compile` (profiles/r02_gpu_reference.json holds the committed run) and quoted here.
+            from baseline import ref_harness as RH
+            if RH.available():
+                modes = ("eager_fp16", "eager_fp32") + (("compiled_fp16",) if args.ref_compile else ())
+                gpu_ref = RH.time_gpu(c, P, B, T, H, dev, iters=3, modes=modes, flush=flush,
+                                      log=lambda m, r_: print(f"[gpu_reference] {m}: {r_}", file=sys.stderr))
+                gpu_ref["note"] = ("unmodified reference modules (baseline/_ref) on this GPU, ms per stage, CUDA events, L2 flushed; fp16 = the "
+                                   "reference's autocast(float16) (dreamer.py:420), fp32 = TF32 matmuls (train.py:38)")
+                saved = os.path.join(ROOT, "profiles", "r02_gpu_reference.json")
+                if "compiled_fp16" not in gpu_ref and os.path.exists(saved):
+                    try:
+                        prev = json.load(open(saved))
+                        gpu_ref["compiled_fp16"] = dict(prev.get("compiled_fp16", {}), source="profiles/r02_gpu_reference.json (bench.py --ref-compile, earlier run)")
+                    except Exception:
+                        pass
+                ours = ms_obs_fb / args.steps if ms_obs_fb else None
+                for m_, r_ in gpu_ref.items():
+                    if isinstance(r_, dict) and "imagine_fwd" in r_:
+                        r_["speedup_ours"] = {"imagine_fwd": r_["imagine_fwd"] / (ms_imag / args.steps),
+                                              "heads_lambda": r_["heads_lambda"] / (ms_heads / args.steps),
+                                              "observe_fwd": r_["observe_fwd"] / (ms_obs / args.steps),
+                                              "observe_fwd_bwd": None if ours is None else r_["observe_fwd_bwd"] / ours}
         line = {
             "metric": METRIC, "value": units / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -482,6 +518,7 @@ def run_gpu(args):
                          "peak_source": f"{how} bf16_tflops_sustained (burst {burst})",
                          "flop_per_unit": FLOP_IMAG_STEP, "units_per_launch": N * H},
             "cpu_baseline": cpu,
+            "gpu_reference": gpu_ref,
             "e2e": {"value": N * H * args.steps * world / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps},
             "e2e_async_read": {"value": N * H * args.steps * world / e2e_async_s, "unit": "steps/s", "ms_per_step": 1e3 * e2e_async_s / args.steps,
@@ -502,6 +539,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-bwd", action="store_true", help="time the forward-only hot path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the unmodified reference modules on this GPU")
+    ap.add_argument("--ref-compile", action="store_true", help="also time the reference under torch.compile(mode='reduce-overhead') (minutes)")
     ap.add_argument("--no-imagine-bwd", action="store_true", help="skip the grad-enabled imagination (attack shape) measurement")
     ap.add_argument("--no-overlap", action="store_true", help="run imagination after (not concurrently with) the posterior backward")
     ap.add_argument("--batch", type=int, default=16, help="replay batch B per GPU (default: base.yaml's 16; the headline config)")
