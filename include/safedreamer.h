@@ -63,6 +63,8 @@ typedef enum sd_module {
                                   captured WITHOUT programmatic dependent launch, so only one of its kernels holds SM
                                   resources at a time and concurrent latency-critical work on another stream finds
                                   room (two-stream schedule). */
+#define SD_FLAG_LAYERWISE  32u /* sd_imagine_fwd only: run the layer-by-layer launch sequence instead of the persistent
+                                  team-resident kernel (csrc/sd_pimg.cuh); for A/B measurements and cross-checks. */
 
 /* Sizes of the path: configs/base.yaml:117-127,252-276,340-420. */
 typedef struct sd_config {

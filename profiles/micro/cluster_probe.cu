@@ -154,6 +154,83 @@ __global__ void k_dsmem_bulk(long long* out, int nchunks) {
   cluster_sync_all();
 }
 
+
+// ---- 6. 2-D tiled TMA ingest (the GEMM operand path): boxes of 128 rows x 64 bf16 (16 KB, SWIZZLE_128B) from a
+// [rows][2048] bf16 matrix; `streams` producer threads (in different warps) each run their own ring of `depth` boxes.
+// same=1: the 16 CTAs of a team read the same boxes.
+#include <cuda.h>
+__device__ __forceinline__ void tma2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__global__ void k_tiled_ingest(const __grid_constant__ CUtensorMap map, int nrows, int nbox, int depth, int streams, int same, long long* out) {
+  extern __shared__ __align__(1024) uint8_t sm[];
+  __shared__ __align__(8) uint64_t full[2][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&full[s][i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  long long t0 = clock64();
+  if (warp < streams && lane == 0) {
+    const int who = same ? (int)(blockIdx.x / 16) : (int)blockIdx.x;
+    const int row_tiles = nrows / 128;
+    for (int i = 0; i < nbox + depth; ++i) {
+      if (i >= depth) mbar_wait(smem_u32(&full[warp][(i - depth) % depth]), (uint32_t)(((i - depth) / depth) & 1));
+      if (i < nbox) {
+        const int s = i % depth;
+        const int lin = who * 977 + warp * 331 + i;            // walk (row tile, k block) pairs
+        const int rt = (lin / 32) % row_tiles, kb = lin % 32;
+        mbar_expect_tx(smem_u32(&full[warp][s]), 16384);
+        tma2d(smem_u32(sm + (warp * depth + s) * 16384), &map, kb * 64, rt * 128, smem_u32(&full[warp][s]));
+      }
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+}
+
+// ---- 7. generic loads: every thread streams uint4 from L2 into shared memory (ILP 8)
+__global__ void k_ldg_ingest(const uint4* __restrict__ src, size_t n16, int iters, long long* out) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint4* s4 = reinterpret_cast<uint4*>(sm);
+  long long t0 = clock64();
+  size_t base = ((size_t)blockIdx.x * 131071) % (n16 - (size_t)iters * 8 * blockDim.x - 1);
+  for (int it = 0; it < iters; ++it) {
+    uint4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(src + base + ((size_t)it * 8 + j) * blockDim.x + threadIdx.x));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s4[(j * blockDim.x + threadIdx.x) % 4096] = v[j];
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+}
+
+// ---- 8. team sync through L2: 16 CTAs per team, red.release.gpu + relaxed poll + acquire fence, one line per team
+__global__ void k_flag_sync(unsigned int* flags, int iters, long long* out) {
+  unsigned int* f = flags + (blockIdx.x / 16) * 32;
+  __syncthreads();
+  long long t0 = clock64();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i <= iters; ++i) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+      unsigned int v = 0;
+      for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v >= (unsigned)i * 16u) break;
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = (t1 - t0) / iters;
+}
+
 template <class K, class... Args>
 static cudaError_t launch_cluster(K kernel, int grid, int block, size_t smem, int cluster, Args... args) {
   cudaLaunchConfig_t cfg;
@@ -246,6 +323,55 @@ int main() {
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost));
     printf("DSMEM cp.async.bulk push: cluster=%d 32 x 16KB per CTA: %lld cycles -> %.1f B/clk per CTA\n", cs, h[0], 32.0 * CHUNK / h[0]);
+  }
+
+  // ---- 2-D tiled TMA
+  {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
+    EncodeFn enc = (EncodeFn)fp;
+    const int nrows = 8192;                       // 8192 x 2048 bf16 = 32 MB: L2 resident
+    CUtensorMap map;
+    cuuint64_t dims[2] = {2048, (cuuint64_t)nrows}; cuuint64_t strides[1] = {4096}; cuuint32_t box[2] = {64, 128}; cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, src, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("tensor map encode: %d\n", (int)r);
+    CK(cudaFuncSetAttribute(k_tiled_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int grid : {16, 128, 148}) for (int same : {0, 1}) for (int streams : {1, 2}) for (int depth : {3, 6}) {
+      const int nbox = 256;
+      for (int rep = 0; rep < 2; ++rep) {
+        k_tiled_ingest<<<grid, 128, (size_t)streams * depth * 16384 + 1024>>>(map, nrows, nbox, depth, streams, same, out);
+        CK(cudaDeviceSynchronize());
+      }
+      CK(cudaMemcpy(h, out, grid * 8, cudaMemcpyDeviceToHost));
+      long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("tiled TMA ingest grid=%d same=%d streams=%d depth=%d: %d x 16KB per stream, max %lld cycles -> %.1f B/clk per CTA\n",
+             grid, same, streams, depth, nbox, mx, (double)streams * nbox * 16384 / mx);
+    }
+  }
+  // ---- generic loads
+  CK(cudaFuncSetAttribute(k_ldg_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  for (int grid : {16, 128}) for (int threads : {256, 512}) {
+    const int iters = 64;
+    for (int rep = 0; rep < 2; ++rep) { k_ldg_ingest<<<grid, threads, 65536>>>((const uint4*)src, SRC / 16, iters, out); CK(cudaDeviceSynchronize()); }
+    CK(cudaMemcpy(h, out, grid * 8, cudaMemcpyDeviceToHost));
+    long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("ld.global.cg.v4 ingest grid=%d threads=%d: %.0f KB per CTA, max %lld cycles -> %.1f B/clk per CTA\n", grid, threads,
+           iters * 8.0 * threads * 16 / 1024, mx, iters * 8.0 * threads * 16 / mx);
+  }
+  // ---- team sync through L2
+  {
+    unsigned int* flags; CK(cudaMalloc(&flags, 4096));
+    for (int grid : {16, 128}) {
+      CK(cudaMemset(flags, 0, 4096));
+      k_flag_sync<<<grid, 128>>>(flags, 1000, out);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(h, out, grid * 8, cudaMemcpyDeviceToHost));
+      long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("team sync through L2 (16 CTAs per team, red.release + poll + fence): grid=%d  %lld cycles per sync\n", grid, mx);
+    }
   }
   printf("done\n");
   return 0;

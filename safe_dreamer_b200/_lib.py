@@ -15,12 +15,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libsafedreamer.so")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "safedreamer.h")
-_SOURCES = ["sd_api.cu", "sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh"]
+_SOURCES = ["sd_api.cu", "sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh", "sd_pimg.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 SD_FLAG_BF16, SD_FLAG_SAVE_TAPE, SD_FLAG_GRAPH, SD_FLAG_FEATS_FROM_IMAGINE, SD_FLAG_BACKGROUND = 1, 2, 4, 8, 16
+SD_FLAG_LAYERWISE = 32
 MOD_RSSM, MOD_ACTOR, MOD_REWARD, MOD_CONT, MOD_VALUE, MOD_SLOW_VALUE = range(6)
 
 
@@ -46,16 +47,31 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU). Returns the .so path."""
+    """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU). Returns the .so path.
+
+    One process per GPU means several ranks may get here at once: the build runs under an exclusive file lock, writes to
+    a temporary file and renames it into place, so nobody ever loads a half-written library."""
     if not force and not _stale():
         return _SO
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(_CSRC, "sd_api.cu"), "-o", _SO]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    import fcntl
+    with open(_SO + ".lock", "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another rank built it while we waited
+                return _SO
+            nvcc = os.environ.get("NVCC", "nvcc")
+            tmp = f"{_SO}.tmp.{os.getpid()}"
+            cmd = [nvcc] + NVCC_FLAGS + [os.path.join(_CSRC, "sd_api.cu"), "-o", tmp]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, _SO)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     return _SO
 
 

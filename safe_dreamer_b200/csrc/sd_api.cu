@@ -23,6 +23,7 @@
 #include "sd_tc.cuh"
 #include "sd_chain.cuh"
 #include "sd_scan.cuh"
+#include "sd_pimg.cuh"
 
 using bf16 = __nv_bfloat16;
 
@@ -159,6 +160,11 @@ struct sd_handle {
   float *ps_x2 = nullptr, *ps_eproj = nullptr, *ps_ssq = nullptr;
   int* ps_idx = nullptr;
   unsigned int* ps_bar = nullptr;
+  // persistent imagination scan (sd_pimg.cuh): packed shared-slab weights, bf16 exchange buffer, team counters / row statistics
+  bf16 *pi_wp7 = nullptr, *pi_wz = nullptr, *pi_act = nullptr;
+  unsigned int* pi_flags = nullptr;
+  float2* pi_ssq = nullptr;
+  int pi_teams_max = 0;
   // big_bf holds the bf16 copy of this sd_imagine_fwd feats output (SD_FLAG_FEATS_FROM_IMAGINE), else null
   const float* bigbf_feats = nullptr;
   int bigbf_N = 0, bigbf_H = 0;
@@ -883,6 +889,13 @@ static void alloc_bwd(Arena& a, BwdBufs& b, const sd_handle& h, size_t rows, siz
   b.d_v_bf = a.take<bf16>(rows * U);
 }
 
+// The persistent imagination kernel is specialised for the base.yaml architecture (configs/base.yaml:117-127,252-276).
+static bool pimg_shape_ok(const sd_handle& h) {
+  const sd_config& c = h.c;
+  return c.D == sd::pimg::D && c.U == sd::pimg::U && c.units == sd::pimg::U && c.S * c.K == sd::pimg::SK && c.K == sd::pimg::KC &&
+         c.G == sd::pimg::G && c.img_layers == 2 && c.actor_layers == 3 && c.A <= 32 && h.act_out <= 32;
+}
+
 static void layout(sd_handle& h, Arena& a) {
   const sd_config& c = h.c;
   const int SK = h.SK, F = h.F, Dg = h.Dg;
@@ -948,6 +961,14 @@ static void layout(sd_handle& h, Arena& a) {
   h.ps_ssq = a.take<float>((size_t)sd::scan::NCTA * 16);
   h.ps_idx = a.take<int>((size_t)16 * c.S);
   h.ps_bar = a.take<unsigned int>(64);
+  if (pimg_shape_ok(h)) {
+    h.pi_wp7 = a.take<bf16>((size_t)768 * sd::pimg::D);
+    h.pi_wz = a.take<bf16>((size_t)512 * sd::pimg::SK);
+    h.pi_act = a.take<bf16>(R * (size_t)sd::pimg::ACT_LD);
+    h.pi_teams_max = 16;
+    h.pi_flags = a.take<unsigned int>((size_t)h.pi_teams_max * sd::pimg::flags_per_team());
+    h.pi_ssq = a.take<float2>((size_t)h.pi_teams_max * sd::pimg::ssq_per_team());
+  }
   h.scratch_stoch = a.take<float>(R * SK);
   h.scratch_deter = a.take<float>(R * c.D);
   h.abar = a.take<float>(R * c.A);
@@ -1794,6 +1815,83 @@ static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, f
   linear(cx, R, hw.last, cur, k, Operand(), out, ld_out);
 }
 
+// Persistent team-resident rollout (sd_pimg.cuh): prologue launches (feats[:, 0], its bf16 copy, weight re-pack, counter
+// reset) + ONE kernel for all H iterations.  SD_PIMG=0 selects the layer-by-layer path.
+static bool pimg_enabled() { static int v = env_flag("SD_PIMG", 1); return v != 0; }
+static bool make_map_box(CUtensorMap* m, const bf16* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_map(m, ptr, rows, cols, ld, box_rows);
+}
+static void imagine_persistent(Ctx& cx, int N, int H, const float* stoch0, const float* deter0, const float* u,
+                               const float* act_noise, float* feats, float* actions) {
+  namespace pi = sd::pimg;
+  sd_handle& h = *cx.h;
+  const sd_config& c = h.c;
+  const HeadW& actor = h.heads[SD_MOD_ACTOR];
+  const int F = h.F, SK = h.SK, ldf = H * F;
+  copy_f32(cx, stoch0, SK, feats, ldf, N, SK);
+  copy_f32(cx, deter0, c.D, feats + SK, ldf, N, c.D);
+  cast_bf(cx, feats, ldf, h.big_bf, ldf, N, F);
+  if (cx.err) return;
+  launch_k(cx.st, pi::pimg_pack_kernel, dim3(148), dim3(256), 0, (const bf16*)h.in0.w_bf, (const bf16*)h.img[0].w_bf,
+           (const bf16*)actor.l[0].w_bf, (const bf16*)h.in1.w_bf, h.pi_wp7, h.pi_wz);
+  cx.check("pimg_pack_kernel");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ngroups = (N + pi::BM - 1) / pi::BM;
+  int teams = sms / pi::CL;
+  if (teams > h.pi_teams_max) teams = h.pi_teams_max;
+  if (teams > ngroups) teams = ngroups;
+  cudaMemsetAsync(h.pi_flags, 0, (size_t)teams * pi::flags_per_team() * sizeof(unsigned int), cx.st);
+  pi::Params P;
+  memset(&P, 0, sizeof(P));
+  bool ok = make_map_box(&P.ma[pi::A_BIG], h.big_bf, (uint64_t)N, (uint64_t)ldf, (uint64_t)ldf, 128);
+  ok = ok && make_map_box(&P.ma[pi::A_ACT], h.pi_act, (uint64_t)N, pi::ACT_LD, pi::ACT_LD, 128);
+  ok = ok && make_map_box(&P.mw[pi::W_P7], h.pi_wp7, 768, pi::D, pi::D, 48);
+  ok = ok && make_map_box(&P.mw[pi::W_Z], h.pi_wz, 512, pi::SK, pi::SK, 16);
+  ok = ok && make_map_box(&P.mw[pi::W_A1], actor.l[1].w_bf, (uint64_t)actor.l[1].npad, 256, 256, 16);
+  ok = ok && make_map_box(&P.mw[pi::W_A2], actor.l[2].w_bf, (uint64_t)actor.l[2].npad, 256, 256, 16);
+  ok = ok && make_map_box(&P.mw[pi::W_I1], h.img[1].w_bf, (uint64_t)h.img[1].npad, 256, 256, 16);
+  ok = ok && make_map_box(&P.mw[pi::W_LG], h.img_logit.w_bf, (uint64_t)h.img_logit.npad, 256, 256, 32);
+  ok = ok && make_map_box(&P.mw[pi::W_HID], h.hid.w_bf, (uint64_t)c.G * h.hid.npad, (uint64_t)h.hid.K, (uint64_t)h.hid.K, 128);
+  ok = ok && make_map_box(&P.mw[pi::W_GRU], h.gru.w_bf, (uint64_t)c.G * h.gru.npad, (uint64_t)h.gru.K, (uint64_t)h.gru.K, 128);
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed (persistent imagination)"); return; }
+  P.N = N; P.H = H; P.ngroups = ngroups;
+  P.feats = feats; P.actions = actions; P.big_bf = h.big_bf; P.act = h.pi_act; P.u = u; P.act_noise = act_noise;
+  P.b_in0 = h.in0.bias; P.g_in0 = h.in0.gain; P.b_in1 = h.in1.bias; P.g_in1 = h.in1.gain; P.b_in2 = h.in2.bias; P.g_in2 = h.in2.gain;
+  P.b_hid = h.hid.bias; P.g_hid = h.hid.gain; P.b_gru = h.gru.bias;
+  P.b_i0 = h.img[0].bias; P.g_i0 = h.img[0].gain; P.b_i1 = h.img[1].bias; P.g_i1 = h.img[1].gain; P.b_lg = h.img_logit.bias;
+  P.b_a0 = actor.l[0].bias; P.g_a0 = actor.l[0].gain; P.b_a1 = actor.l[1].bias; P.g_a1 = actor.l[1].gain;
+  P.b_a2 = actor.l[2].bias; P.g_a2 = actor.l[2].gain; P.b_last = actor.last.bias;
+  P.w_last = actor.last.wn; P.ldk_last = actor.last.ldk;
+  P.w_in2 = h.in2.wt; P.ldw_in2 = h.in2.ldw;
+  P.A = c.A; P.act_out = h.act_out; P.act_kind = c.act_kind;
+  P.tail_in_smem = ((h.act_out + c.A) * 256 + 512 <= pi::kTailFloats && actor.last.ldk == 256 && h.in2.ldw == 256) ? 1 : 0;
+  P.flags = h.pi_flags; P.ssq = h.pi_ssq;
+  P.min_std = c.min_std; P.max_std = c.max_std; P.act_unimix = c.act_unimix; P.unimix = c.unimix;
+  static long long* timing_dev = nullptr;
+  const bool timing = cx.trace && getenv("SD_TRACE_PIMG");
+  if (timing) {
+    if (!timing_dev) cudaMalloc(&timing_dev, 1024 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 1024 * sizeof(long long), cx.st);
+    P.timing = timing_dev;
+  }
+  cudaFuncSetAttribute(pi::imagine_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pi::kSmemBytes);
+  launch_k(cx.st, pi::imagine_persistent_kernel, dim3(teams * pi::CL), dim3(pi::THREADS), (size_t)pi::kSmemBytes, P);
+  cx.check("imagine_persistent_kernel");
+  if (timing) {
+    cudaStreamSynchronize(cx.st);
+    long long t[1024];
+    cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
+    const char* names[12] = {"acc_p7", "sig_p7", "sig_o1", "sig_z", "sig_zin", "sig_a1", "sig_a2", "tail", "acc_hid", "sig_h", "acc_gru", "sig_d"};
+    for (int i = 0; i < H && i < 4; ++i) {
+      fprintf(stderr, "[SD_TRACE_PIMG] iter %d (cycles since acc_p7 of iter 0):", i);
+      for (int k = 0; k < 12; ++k) if (t[16 * i + k]) fprintf(stderr, " %s=%lld", names[k], t[16 * i + k] - t[0]);
+      fprintf(stderr, "\n");
+    }
+  }
+}
+
 extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, const float* deter0, const float* u,
                               const float* act_noise, float* feats, float* actions, uint32_t flags, void* stream) {
   if (int e = check_rows(h, "sd_imagine_fwd", N, H)) return e;
@@ -1812,6 +1910,10 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     base.stride = tape ? 1 : 0;
     const HeadW& actor = h->heads[SD_MOD_ACTOR];
     const int ldf = H * F;
+    if (cx.tc && !tape && !(flags & SD_FLAG_LAYERWISE) && pimg_enabled() && h->pi_wp7 && pimg_shape_ok(*h)) {
+      imagine_persistent(cx, N, H, stoch0, deter0, u, act_noise, feats, actions);
+      return;
+    }
     // feats[:, 0] = [stoch0 | deter0] (rssm.py:211-217)
     copy_f32(cx, stoch0, SK, feats, ldf, N, SK);
     copy_f32(cx, deter0, D, feats + SK, ldf, N, D);
