@@ -1816,8 +1816,8 @@ static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, f
 }
 
 // Persistent team-resident rollout (sd_pimg.cuh): prologue launches (feats[:, 0], its bf16 copy, weight re-pack, counter
-// reset) + ONE kernel for all H iterations.  SD_PIMG=0 selects the layer-by-layer path.
-static bool pimg_enabled() { static int v = env_flag("SD_PIMG", 1); return v != 0; }
+// reset) + ONE kernel for all H iterations.  Opt-in: SD_FLAG_PERSISTENT or SD_PIMG=1 (see include/safedreamer.h).
+static bool pimg_enabled() { static int v = env_flag("SD_PIMG", 0); return v != 0; }
 static bool make_map_box(CUtensorMap* m, const bf16* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   return make_map(m, ptr, rows, cols, ld, box_rows);
 }
@@ -1883,10 +1883,20 @@ static void imagine_persistent(Ctx& cx, int N, int H, const float* stoch0, const
     cudaStreamSynchronize(cx.st);
     long long t[1024];
     cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
-    const char* names[12] = {"acc_p7", "sig_p7", "sig_o1", "sig_z", "sig_zin", "sig_a1", "sig_a2", "tail", "acc_hid", "sig_h", "acc_gru", "sig_d"};
+    const char* names[16] = {"acc_p7", "sig_p7", "sig_o1", "sig_z", "sig_zin", "sig_a1", "sig_a2", "tail", "acc_hid", "sig_h", "acc_gru", "sig_d",
+                             "A:xd_seen", "A:xp7_seen", "M:p7_issued", "M:gru_issued"};
     for (int i = 0; i < H && i < 4; ++i) {
       fprintf(stderr, "[SD_TRACE_PIMG] iter %d (cycles since acc_p7 of iter 0):", i);
-      for (int k = 0; k < 12; ++k) if (t[16 * i + k]) fprintf(stderr, " %s=%lld", names[k], t[16 * i + k] - t[0]);
+      for (int k = 0; k < 16; ++k) if (t[16 * i + k]) fprintf(stderr, " %s=%lld", names[k], t[16 * i + k] - t[0]);
+      fprintf(stderr, "\n");
+    }
+    if (H >= 3) {   // iteration 2 of CTA 0, slab by slab / weight box by weight box (cycles since acc_p7 of iteration 0)
+      fprintf(stderr, "[SD_TRACE_PIMG] iter 2 A slabs (issued -> landed):");
+      for (int k = 0; k < 72; ++k) fprintf(stderr, " %d:%lld->%lld", k, t[336 + k] ? t[336 + k] - t[0] : 0, t[256 + k] ? t[256 + k] - t[0] : 0);
+      fprintf(stderr, "\n[SD_TRACE_PIMG] iter 2 W boxes (issued -> landed):");
+      for (int k = 0; k < 92; ++k) fprintf(stderr, " %d:%lld->%lld", k, t[512 + k] ? t[512 + k] - t[0] : 0, t[416 + k] ? t[416 + k] - t[0] : 0);
+      fprintf(stderr, "\n[SD_TRACE_PIMG] iter 2 MMA thread per weight box (w seen -> mmas issued -> commits issued):");
+      for (int k = 0; k < 32; ++k) fprintf(stderr, " %d:%lld->%lld->%lld", k, t[416 + k] - t[0], t[640 + 2 * k] - t[0], t[641 + 2 * k] - t[0]);
       fprintf(stderr, "\n");
     }
   }
@@ -1910,7 +1920,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     base.stride = tape ? 1 : 0;
     const HeadW& actor = h->heads[SD_MOD_ACTOR];
     const int ldf = H * F;
-    if (cx.tc && !tape && !(flags & SD_FLAG_LAYERWISE) && pimg_enabled() && h->pi_wp7 && pimg_shape_ok(*h)) {
+    if (cx.tc && !tape && ((flags & SD_FLAG_PERSISTENT) || pimg_enabled()) && h->pi_wp7 && pimg_shape_ok(*h)) {
       imagine_persistent(cx, N, H, stoch0, deter0, u, act_noise, feats, actions);
       return;
     }

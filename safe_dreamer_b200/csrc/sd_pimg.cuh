@@ -33,8 +33,12 @@ using tc::smem_u32;
 constexpr int CL = 16;          // CTAs per team
 constexpr int BM = 128, BK = 64;
 constexpr int NEPI = 8;         // epilogue warps (two per TMEM lane quadrant)
-constexpr int W_WARP = 8, A_WARP = 9, M_WARP = 10;
-constexpr int THREADS = 384;
+// Each producer role is NPW / NPA threads in different warps that take the boxes of the schedule round-robin (a lone
+// thread issues at most one 16 KB box per ~560 cycles).  Measured (profiles/r02_pimg_phase_stamps.txt): inside this kernel
+// the TMA unit delivers ~25 B/clk per SM in total however many threads issue (2+2 and 3+4 give the same slab cadence).
+constexpr int NPW = 2, NPA = 2;
+constexpr int W_WARP = NEPI, A_WARP = W_WARP + NPW, M_WARP = A_WARP + NPA;
+constexpr int THREADS = 32 * (M_WARP + 1);
 constexpr int NA = 6, NW = 5;   // activation-slab ring / weight ring depth
 constexpr int kSlab = BM * BK * 2;   // 16 KB: one A slab, one W ring slot
 
@@ -131,7 +135,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.f + __expf(-y)); }
+// one MUFU op each (tanh.approx.f32, |rel err| ~ 2^-11: below the bf16 rounding of every value these feed)
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ float silu_fast(float y) { return y * sigmoid_fast(y); }
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -225,45 +232,55 @@ struct Bars {
 };
 
 struct AProducer {
-  const Params& P; Bars b; uint32_t sA; const unsigned int* flags; uint32_t cnt = 0;
+  const Params& P; Bars b; uint32_t sA; const unsigned int* flags; uint32_t me; uint32_t cnt = 0;
   unsigned int xcnt[NX] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   __device__ __forceinline__ void wait(int x) {
     xcnt[x] += CL;
     flag_wait(flags + x * kFlagStride, xcnt[x]);
     fence_async_global();   // the TMA (async proxy) loads below read what the peers' generic-proxy stores wrote
+    if (P.timing && blockIdx.x == 0 && me == 0 && x == X_D) P.timing[16 * (xcnt[x] / CL) + 12] = clock64();
+    if (P.timing && blockIdx.x == 0 && me == 0 && x == X_P7) P.timing[16 * (xcnt[x] / CL - 1) + 13] = clock64();
   }
   __device__ __forceinline__ void a(int map, int col, int row) {
-    const uint32_t s = cnt % NA, ph = (cnt / NA) & 1u;
-    wait_local(b.a_empty + s * 8, ph ^ 1u);
-    tc::mbar_expect_tx(b.a_full + s * 8, kSlab);
-    tc::tma_load_2d(sA + s * kSlab, &P.ma[map], col, row, b.a_full + s * 8);
+    if (cnt % NPA == me) {
+      const uint32_t s = cnt % NA, ph = (cnt / NA) & 1u;
+      wait_local(b.a_empty + s * 8, ph ^ 1u);
+      tc::mbar_expect_tx(b.a_full + s * 8, kSlab);
+      tc::tma_load_2d(sA + s * kSlab, &P.ma[map], col, row, b.a_full + s * 8);
+      if (P.timing && blockIdx.x == 0 && cnt >= 136 && cnt < 208) P.timing[336 + cnt - 136] = clock64();
+    }
     ++cnt;
   }
   __device__ __forceinline__ void w(int, int, int, int, uint32_t, bool, bool, int) {}
 };
 struct WProducer {
-  const Params& P; Bars b; uint32_t sW; uint32_t cnt = 0;
+  const Params& P; Bars b; uint32_t sW; uint32_t me; uint32_t cnt = 0;
   __device__ __forceinline__ void wait(int) {}
   __device__ __forceinline__ void a(int, int, int) {}
   __device__ __forceinline__ void w(int map, int k, int row, int n, uint32_t, bool, bool, int) {
-    const uint32_t s = cnt % NW, ph = (cnt / NW) & 1u;
-    wait_local(b.w_empty + s * 8, ph ^ 1u);
-    tc::mbar_expect_tx(b.w_full + s * 8, (uint32_t)n * BK * 2);
-    tc::tma_load_2d(sW + s * kSlab, &P.mw[map], k, row, b.w_full + s * 8);
+    if (cnt % NPW == me) {
+      const uint32_t s = cnt % NW, ph = (cnt / NW) & 1u;
+      wait_local(b.w_empty + s * 8, ph ^ 1u);
+      tc::mbar_expect_tx(b.w_full + s * 8, (uint32_t)n * BK * 2);
+      tc::tma_load_2d(sW + s * kSlab, &P.mw[map], k, row, b.w_full + s * 8);
+      if (P.timing && blockIdx.x == 0 && cnt >= 176 && cnt < 268) P.timing[512 + cnt - 176] = clock64();
+    }
     ++cnt;
   }
 };
 struct MmaIssuer {
-  Bars b; uint32_t sA, sW, tmem; uint32_t acnt = 0, wcnt = 0, cur = 0;
+  Bars b; uint32_t sA, sW, tmem; long long* timing; uint32_t acnt = 0, wcnt = 0, cur = 0, n_p7 = 0, n_gru = 0;
   __device__ __forceinline__ void wait(int) {}
   __device__ __forceinline__ void a(int, int, int) {
     cur = acnt % NA;
     wait_local(b.a_full + cur * 8, (acnt / NA) & 1u);
+    if (timing && acnt >= 136 && acnt < 208) timing[256 + acnt - 136] = clock64();
     ++acnt;
   }
   __device__ __forceinline__ void w(int, int, int, int n, uint32_t tcol, bool accum, bool rel, int bar) {
     const uint32_t s = wcnt % NW;
     wait_local(b.w_full + s * 8, (wcnt / NW) & 1u);
+    if (timing && wcnt >= 176 && wcnt < 268) timing[416 + wcnt - 176] = clock64();
     ++wcnt;
     tc::tc_fence_after();
     const uint64_t da = tc::make_desc_sw128(sA + cur * kSlab), db = tc::make_desc_sw128(sW + s * kSlab);
@@ -271,9 +288,13 @@ struct MmaIssuer {
 #pragma unroll
     for (int k = 0; k < BK / 16; ++k)
       tc::tc_mma_f16(tmem + tcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (accum || k > 0) ? 1u : 0u);
+    if (timing && wcnt > 176 && wcnt <= 208) timing[640 + (wcnt - 177) * 2] = clock64();
     tc::tc_commit(b.w_empty + s * 8);
     if (rel) tc::tc_commit(b.a_empty + cur * 8);
     if (bar >= 0) tc::tc_commit(b.acc + bar * 8);
+    if (timing && wcnt > 176 && wcnt <= 208) timing[641 + (wcnt - 177) * 2] = clock64();
+    if (timing && bar == ACC_P7) timing[16 * (n_p7++) + 14] = clock64();
+    if (timing && bar == ACC_GRU) timing[16 * (n_gru++) + 15] = clock64();
   }
 };
 
@@ -432,19 +453,19 @@ __global__ void __launch_bounds__(THREADS, 1) imagine_persistent_kernel(const __
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == W_WARP) {
+  if (warp >= W_WARP && warp < A_WARP) {
     if (lane == 0) {
-      WProducer v{P, b, base + kOffW};
+      WProducer v{P, b, base + kOffW, (uint32_t)(warp - W_WARP)};
       walk(P, rank, v);
     }
-  } else if (warp == A_WARP) {
+  } else if (warp >= A_WARP && warp < M_WARP) {
     if (lane == 0) {
-      AProducer v{P, b, base + kOffA, P.flags + (size_t)team * flags_per_team()};
+      AProducer v{P, b, base + kOffA, P.flags + (size_t)team * flags_per_team(), (uint32_t)(warp - A_WARP)};
       walk(P, rank, v);
     }
   } else if (warp == M_WARP) {
     if (lane == 0) {
-      MmaIssuer v{b, base + kOffA, base + kOffW, tmem_base};
+      MmaIssuer v{b, base + kOffA, base + kOffW, tmem_base, blockIdx.x == 0 ? P.timing : nullptr};
       walk(P, rank, v);
     }
   } else if (warp < NEPI) {
@@ -600,28 +621,32 @@ __global__ void __launch_bounds__(THREADS, 1) imagine_persistent_kernel(const __
         {
           e.wait_acc(ACC_HID);
           SD_PI_STAMP(16 * i + 8);
-          float v[64];
-          tc::tmem_ld32(e.tmem + T_HID + (uint32_t)(half * 64), v);
-          tc::tmem_ld32(e.tmem + T_HID + (uint32_t)(half * 64 + 32), v + 32);
           float ss = 0.f;
+#pragma unroll 1
+          for (int c32 = 0; c32 < 2; ++c32) {
+            float v[32];
+            tc::tmem_ld32(e.tmem + T_HID + (uint32_t)(half * 64 + c32 * 32), v);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) { v[j] += cs[C_HB + half * 64 + j]; ss = fmaf(v[j], v[j], ss); }
+            for (int j = 0; j < 32; ++j) { const float t = v[j] + cs[C_HB + half * 64 + c32 * 32 + j]; ss = fmaf(t, t, ss); }
+          }
           float* hss = reinterpret_cast<float*>(gbase + kOffHss);
           hss[half * BM + e.row] = ss;
-          tc::tc_fence_before();
           epi_bar();
           const float mine = hss[e.row] + hss[BM + e.row];
           float tot, dummy;
           e.exchange(5, mine, 0.f, half == 0, tot, dummy);
           const float rs = 1.f / sqrtf(tot * (1.f / (float)D) + kRmsEps);
-          if (rowok) {
-            uint4* o = reinterpret_cast<uint4*>(P.act + (size_t)grow * ACT_LD + CH + rank * 128 + half * 64);
+          uint4* o = reinterpret_cast<uint4*>(P.act + (size_t)grow * ACT_LD + CH + rank * 128 + half * 64);
+#pragma unroll 1
+          for (int c32 = 0; c32 < 2; ++c32) {
+            float v[32];
+            tc::tmem_ld32(e.tmem + T_HID + (uint32_t)(half * 64 + c32 * 32), v);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float y[8];
+            for (int j = 0; j < 32; ++j)
+              v[j] = silu_fast(((v[j] + cs[C_HB + half * 64 + c32 * 32 + j]) * rs) * cs[C_HG + half * 64 + c32 * 32 + j]);
+            if (rowok) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) y[j] = silu_fast((v[q * 8 + j] * rs) * cs[C_HG + half * 64 + q * 8 + j]);
-              o[q] = pack_bf8(y);
+              for (int q = 0; q < 4; ++q) o[c32 * 4 + q] = pack_bf8(v + q * 8);
             }
           }
           e.signal(X_H);
@@ -636,36 +661,36 @@ __global__ void __launch_bounds__(THREADS, 1) imagine_persistent_kernel(const __
           float* dout = P.feats + (size_t)grow * ldf + (size_t)(i + 1) * F + col;
           __nv_bfloat16* dbf = P.big_bf + (size_t)grow * ldf + (size_t)(i + 1) * F + col;
 #pragma unroll 1
-          for (int c32 = 0; c32 < 2; ++c32) {
-            float qr[32], qc[32], qu[32], dold[32];
+          for (int c16 = 0; c16 < 4; ++c16) {
+            float qr[16], qc[16], qu[16], dold[16];
             if (rowok) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 t = *reinterpret_cast<const float4*>(din + c32 * 32 + q * 4);
+              for (int q = 0; q < 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(din + c16 * 16 + q * 4);
                 dold[4 * q] = t.x; dold[4 * q + 1] = t.y; dold[4 * q + 2] = t.z; dold[4 * q + 3] = t.w;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dold[j] = 0.f;
+              for (int j = 0; j < 16; ++j) dold[j] = 0.f;
             }
-            const uint32_t tb = e.tmem + T_GRU + (uint32_t)(half * 64 + c32 * 32);
-            tc::tmem_ld32(tb, qr);
-            tc::tmem_ld32(tb + 128u, qc);
-            tc::tmem_ld32(tb + 256u, qu);
-            const float* gb = cs + C_GB + half * 64 + c32 * 32;
+            const uint32_t tb = e.tmem + T_GRU + (uint32_t)(half * 64 + c16 * 16);
+            tmem_ld16(tb, qr);
+            tmem_ld16(tb + 128u, qc);
+            tmem_ld16(tb + 256u, qu);
+            const float* gb = cs + C_GB + half * 64 + c16 * 16;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float reset = __fdividef(1.f, 1.f + __expf(-(qr[j] + gb[j])));
-              const float cand = 1.f - __fdividef(2.f, 1.f + __expf(2.f * (reset * (qc[j] + gb[128 + j]))));
-              const float upd = __fdividef(1.f, 1.f + __expf(-((qu[j] + gb[256 + j]) - 1.f)));
-              dold[j] = upd * cand + (1.f - upd) * dold[j];
+            for (int j = 0; j < 16; ++j) {
+              const float reset = sigmoid_fast(qr[j] + gb[j]);
+              const float cand = tanh_fast(reset * (qc[j] + gb[128 + j]));
+              const float upd = sigmoid_fast((qu[j] + gb[256 + j]) - 1.f);
+              dold[j] = fmaf(upd, cand - dold[j], dold[j]);
             }
             if (rowok) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(dout + c32 * 32 + q * 4) = make_float4(dold[4 * q], dold[4 * q + 1], dold[4 * q + 2], dold[4 * q + 3]);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dbf + c32 * 32 + q * 8) = pack_bf8(dold + q * 8);
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(dout + c16 * 16 + q * 4) = make_float4(dold[4 * q], dold[4 * q + 1], dold[4 * q + 2], dold[4 * q + 3]);
+              *reinterpret_cast<uint4*>(dbf + c16 * 16) = pack_bf8(dold);
+              *reinterpret_cast<uint4*>(dbf + c16 * 16 + 8) = pack_bf8(dold + 8);
             }
           }
           e.signal(X_D);
