@@ -63,10 +63,12 @@ typedef enum sd_module {
                                   captured WITHOUT programmatic dependent launch, so only one of its kernels holds SM
                                   resources at a time and concurrent latency-critical work on another stream finds
                                   room (two-stream schedule). */
-#define SD_FLAG_PERSISTENT 32u /* sd_imagine_fwd only (with SD_FLAG_BF16, no tape, base.yaml architecture): run the whole rollout
-                                  as ONE persistent team-resident kernel (csrc/sd_pimg.cuh) instead of the layer-by-layer launch
-                                  sequence.  Same results up to bf16 rounding order; measured 8 % slower than the launch sequence
-                                  at N = 1024 on B200, so it is opt-in (SD_PIMG=1 makes it the default). */
+#define SD_FLAG_PERSISTENT 32u /* sd_imagine_fwd only: force the persistent team-resident kernel (csrc/sd_pimg.cuh: the whole
+                                  rollout is ONE launch).  It is already the default for SD_FLAG_BF16 calls without a tape on the
+                                  base.yaml architecture (D=2048, U=units=256, 32x16 latents, G=8, 2 img / 3 actor layers);
+                                  SD_PIMG=0 in the environment makes the launch sequence the default again. */
+#define SD_FLAG_LAYERWISE  64u /* sd_imagine_fwd only: force the layer-by-layer launch sequence (13 launches per step); for A/B
+                                  measurements and cross-checks.  Both paths agree up to bf16 rounding order. */
 
 /* Sizes of the path: configs/base.yaml:117-127,252-276,340-420. */
 typedef struct sd_config {

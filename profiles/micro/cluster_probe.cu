@@ -163,29 +163,43 @@ __device__ __forceinline__ void tma2d(uint32_t dst, const CUtensorMap* map, int 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__global__ void k_tiled_ingest(const __grid_constant__ CUtensorMap map, int nrows, int nbox, int depth, int streams, int same, long long* out) {
+struct Maps4 { CUtensorMap m[4]; };
+__global__ void k_tiled_ingest(const __grid_constant__ Maps4 maps, int nrows, int nbox, int depth, int streams, int same, int per_bar,
+                               int box_bytes, int distinct_maps, long long* out) {
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ __align__(8) uint64_t full[2][8];
+  __shared__ __align__(8) uint64_t full[4][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&full[s][i]), 1);
+    for (int s = 0; s < 4; ++s) for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&full[s][i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   long long t0 = clock64();
   if (warp < streams && lane == 0) {
+    const CUtensorMap* map = &maps.m[distinct_maps ? warp : 0];
     const int who = same ? (int)(blockIdx.x / 16) : (int)blockIdx.x;
     const int row_tiles = nrows / 128;
-    for (int i = 0; i < nbox + depth; ++i) {
+    const int ngroups = nbox / per_bar;
+    long long c_wait = 0, c_exp = 0, c_tma = 0;
+    for (int i = 0; i < ngroups + depth; ++i) {
+      long long a0 = clock64();
       if (i >= depth) mbar_wait(smem_u32(&full[warp][(i - depth) % depth]), (uint32_t)(((i - depth) / depth) & 1));
-      if (i < nbox) {
+      long long a1 = clock64();
+      c_wait += a1 - a0;
+      if (i < ngroups) {
         const int s = i % depth;
-        const int lin = who * 977 + warp * 331 + i;            // walk (row tile, k block) pairs
-        const int rt = (lin / 32) % row_tiles, kb = lin % 32;
-        mbar_expect_tx(smem_u32(&full[warp][s]), 16384);
-        tma2d(smem_u32(sm + (warp * depth + s) * 16384), &map, kb * 64, rt * 128, smem_u32(&full[warp][s]));
+        mbar_expect_tx(smem_u32(&full[warp][s]), (uint32_t)(box_bytes * per_bar));
+        long long a2 = clock64();
+        c_exp += a2 - a1;
+        for (int j = 0; j < per_bar; ++j) {
+          const int lin = who * 977 + warp * 331 + i * per_bar + j;
+          const int rt = (lin / 32) % row_tiles, kb = lin % 32;
+          tma2d(smem_u32(sm + ((warp * depth + s) * per_bar + j) * 16384), map, kb * 64, rt * 128, smem_u32(&full[warp][s]));
+        }
+        c_tma += clock64() - a2;
       }
     }
+    if (blockIdx.x == 0 && warp == 0) { out[200] = c_wait / ngroups; out[201] = c_exp / ngroups; out[202] = c_tma / ngroups; }
   }
   __syncthreads();
   long long t1 = clock64();
@@ -333,22 +347,31 @@ int main() {
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
     EncodeFn enc = (EncodeFn)fp;
     const int nrows = 8192;                       // 8192 x 2048 bf16 = 32 MB: L2 resident
-    CUtensorMap map;
-    cuuint64_t dims[2] = {2048, (cuuint64_t)nrows}; cuuint64_t strides[1] = {4096}; cuuint32_t box[2] = {64, 128}; cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, src, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    printf("tensor map encode: %d\n", (int)r);
+    Maps4 maps;
+    cuuint64_t dims[2] = {2048, (cuuint64_t)nrows}; cuuint64_t strides[1] = {4096}; cuuint32_t es[2] = {1, 1};
+    auto mk = [&](CUtensorMap* m, int box_rows, void* base) {
+      cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+      return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
     CK(cudaFuncSetAttribute(k_tiled_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    for (int grid : {16, 128, 148}) for (int same : {0, 1}) for (int streams : {1, 2}) for (int depth : {3, 6}) {
-      const int nbox = 256;
-      for (int rep = 0; rep < 2; ++rep) {
-        k_tiled_ingest<<<grid, 128, (size_t)streams * depth * 16384 + 1024>>>(map, nrows, nbox, depth, streams, same, out);
-        CK(cudaDeviceSynchronize());
+    for (int box_rows : {128, 16}) {
+      for (int i = 0; i < 4; ++i) { CUresult r = mk(&maps.m[i], box_rows, src); if (r) printf("encode failed %d\n", (int)r); }
+      for (int grid : {128}) for (int streams : {1, 2, 4}) for (int per_bar : {1, 2}) for (int dm : {0}) {
+        const int depth = 3;
+        if (box_rows != 128 && (per_bar == 2 || dm == 1 || grid == 16)) continue;
+        if ((size_t)streams * depth * per_bar * 16384 + 1024 > 200 * 1024) continue;
+        const int nbox = 240;
+        for (int rep = 0; rep < 2; ++rep) {
+          k_tiled_ingest<<<grid, 128, (size_t)streams * depth * per_bar * 16384 + 1024>>>(maps, nrows, nbox, depth, streams, 1, per_bar, box_rows * 128, dm, out);
+          CK(cudaDeviceSynchronize());
+        }
+        CK(cudaMemcpy(h, out, 203 * 8, cudaMemcpyDeviceToHost));
+        long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("[per iteration: wait %lld expect_tx %lld tma issue %lld cycles] ", h[200], h[201], h[202]);
+        printf("tiled TMA ingest box=%dx64 grid=%d streams=%d boxes/barrier=%d distinct_maps=%d depth=%d: %d boxes per stream, max %lld cycles -> %.1f B/clk per CTA, %.0f cycles per box per stream\n",
+               box_rows, grid, streams, per_bar, dm, depth, nbox, mx, (double)streams * nbox * box_rows * 128 / mx, (double)mx / nbox);
       }
-      CK(cudaMemcpy(h, out, grid * 8, cudaMemcpyDeviceToHost));
-      long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-      printf("tiled TMA ingest grid=%d same=%d streams=%d depth=%d: %d x 16KB per stream, max %lld cycles -> %.1f B/clk per CTA\n",
-             grid, same, streams, depth, nbox, mx, (double)streams * nbox * 16384 / mx);
     }
   }
   // ---- generic loads

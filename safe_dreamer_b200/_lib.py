@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 SD_FLAG_BF16, SD_FLAG_SAVE_TAPE, SD_FLAG_GRAPH, SD_FLAG_FEATS_FROM_IMAGINE, SD_FLAG_BACKGROUND = 1, 2, 4, 8, 16
-SD_FLAG_PERSISTENT = 32
+SD_FLAG_PERSISTENT, SD_FLAG_LAYERWISE = 32, 64
 MOD_RSSM, MOD_ACTOR, MOD_REWARD, MOD_CONT, MOD_VALUE, MOD_SLOW_VALUE = range(6)
 
 

@@ -162,8 +162,9 @@ struct sd_handle {
   unsigned int* ps_bar = nullptr;
   // persistent imagination scan (sd_pimg.cuh): packed shared-slab weights, bf16 exchange buffer, team counters / row statistics
   bf16 *pi_wp7 = nullptr, *pi_wz = nullptr, *pi_act = nullptr;
+  float* pi_raw = nullptr;
   unsigned int* pi_flags = nullptr;
-  float2* pi_ssq = nullptr;
+  float* pi_ssq = nullptr;
   int pi_teams_max = 0;
   // big_bf holds the bf16 copy of this sd_imagine_fwd feats output (SD_FLAG_FEATS_FROM_IMAGINE), else null
   const float* bigbf_feats = nullptr;
@@ -965,9 +966,10 @@ static void layout(sd_handle& h, Arena& a) {
     h.pi_wp7 = a.take<bf16>((size_t)768 * sd::pimg::D);
     h.pi_wz = a.take<bf16>((size_t)512 * sd::pimg::SK);
     h.pi_act = a.take<bf16>(R * (size_t)sd::pimg::ACT_LD);
+    h.pi_raw = a.take<float>(R * (size_t)sd::pimg::RAW_LD);
     h.pi_teams_max = 16;
     h.pi_flags = a.take<unsigned int>((size_t)h.pi_teams_max * sd::pimg::flags_per_team());
-    h.pi_ssq = a.take<float2>((size_t)h.pi_teams_max * sd::pimg::ssq_per_team());
+    h.pi_ssq = a.take<float>((size_t)h.pi_teams_max * sd::pimg::ssq_per_team());
   }
   h.scratch_stoch = a.take<float>(R * SK);
   h.scratch_deter = a.take<float>(R * c.D);
@@ -1816,8 +1818,8 @@ static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, f
 }
 
 // Persistent team-resident rollout (sd_pimg.cuh): prologue launches (feats[:, 0], its bf16 copy, weight re-pack, counter
-// reset) + ONE kernel for all H iterations.  Opt-in: SD_FLAG_PERSISTENT or SD_PIMG=1 (see include/safedreamer.h).
-static bool pimg_enabled() { static int v = env_flag("SD_PIMG", 0); return v != 0; }
+// reset) + ONE kernel for all H iterations.  Default for eligible calls; SD_FLAG_LAYERWISE / SD_PIMG=0 select the launch sequence.
+static bool pimg_enabled() { static int v = env_flag("SD_PIMG", 1); return v != 0; }
 static bool make_map_box(CUtensorMap* m, const bf16* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   return make_map(m, ptr, rows, cols, ld, box_rows);
 }
@@ -1848,16 +1850,16 @@ static void imagine_persistent(Ctx& cx, int N, int H, const float* stoch0, const
   bool ok = make_map_box(&P.ma[pi::A_BIG], h.big_bf, (uint64_t)N, (uint64_t)ldf, (uint64_t)ldf, 128);
   ok = ok && make_map_box(&P.ma[pi::A_ACT], h.pi_act, (uint64_t)N, pi::ACT_LD, pi::ACT_LD, 128);
   ok = ok && make_map_box(&P.mw[pi::W_P7], h.pi_wp7, 768, pi::D, pi::D, 48);
-  ok = ok && make_map_box(&P.mw[pi::W_Z], h.pi_wz, 512, pi::SK, pi::SK, 16);
-  ok = ok && make_map_box(&P.mw[pi::W_A1], actor.l[1].w_bf, (uint64_t)actor.l[1].npad, 256, 256, 16);
-  ok = ok && make_map_box(&P.mw[pi::W_A2], actor.l[2].w_bf, (uint64_t)actor.l[2].npad, 256, 256, 16);
-  ok = ok && make_map_box(&P.mw[pi::W_I1], h.img[1].w_bf, (uint64_t)h.img[1].npad, 256, 256, 16);
-  ok = ok && make_map_box(&P.mw[pi::W_LG], h.img_logit.w_bf, (uint64_t)h.img_logit.npad, 256, 256, 32);
+  ok = ok && make_map_box(&P.mw[pi::W_Z], h.pi_wz, 512, pi::SK, pi::SK, 32);
+  ok = ok && make_map_box(&P.mw[pi::W_A1], actor.l[1].w_bf, (uint64_t)actor.l[1].npad, 256, 256, 128);
+  ok = ok && make_map_box(&P.mw[pi::W_A2], actor.l[2].w_bf, (uint64_t)actor.l[2].npad, 256, 256, 128);
+  ok = ok && make_map_box(&P.mw[pi::W_I1], h.img[1].w_bf, (uint64_t)h.img[1].npad, 256, 256, 128);
+  ok = ok && make_map_box(&P.mw[pi::W_LG], h.img_logit.w_bf, (uint64_t)h.img_logit.npad, 256, 256, 128);
   ok = ok && make_map_box(&P.mw[pi::W_HID], h.hid.w_bf, (uint64_t)c.G * h.hid.npad, (uint64_t)h.hid.K, (uint64_t)h.hid.K, 128);
   ok = ok && make_map_box(&P.mw[pi::W_GRU], h.gru.w_bf, (uint64_t)c.G * h.gru.npad, (uint64_t)h.gru.K, (uint64_t)h.gru.K, 128);
   if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed (persistent imagination)"); return; }
   P.N = N; P.H = H; P.ngroups = ngroups;
-  P.feats = feats; P.actions = actions; P.big_bf = h.big_bf; P.act = h.pi_act; P.u = u; P.act_noise = act_noise;
+  P.feats = feats; P.actions = actions; P.big_bf = h.big_bf; P.act = h.pi_act; P.raw = h.pi_raw; P.u = u; P.act_noise = act_noise;
   P.b_in0 = h.in0.bias; P.g_in0 = h.in0.gain; P.b_in1 = h.in1.bias; P.g_in1 = h.in1.gain; P.b_in2 = h.in2.bias; P.g_in2 = h.in2.gain;
   P.b_hid = h.hid.bias; P.g_hid = h.hid.gain; P.b_gru = h.gru.bias;
   P.b_i0 = h.img[0].bias; P.g_i0 = h.img[0].gain; P.b_i1 = h.img[1].bias; P.g_i1 = h.img[1].gain; P.b_lg = h.img_logit.bias;
@@ -1883,20 +1885,12 @@ static void imagine_persistent(Ctx& cx, int N, int H, const float* stoch0, const
     cudaStreamSynchronize(cx.st);
     long long t[1024];
     cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
-    const char* names[16] = {"acc_p7", "sig_p7", "sig_o1", "sig_z", "sig_zin", "sig_a1", "sig_a2", "tail", "acc_hid", "sig_h", "acc_gru", "sig_d",
-                             "A:xd_seen", "A:xp7_seen", "M:p7_issued", "M:gru_issued"};
+    const char* names[32] = {"acc_p7", "sig_p7", "o1_ready", "sig_z", "sig_zin", "a1_ready", "a2_ready", "tail", "acc_hid", "sig_h", "acc_gru", "sig_d",
+                             "lg_acc", "xp7_seen", "o0_published", "i1_acc",
+                             "tail_dots", "tail_sampled", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-"};
     for (int i = 0; i < H && i < 4; ++i) {
       fprintf(stderr, "[SD_TRACE_PIMG] iter %d (cycles since acc_p7 of iter 0):", i);
-      for (int k = 0; k < 16; ++k) if (t[16 * i + k]) fprintf(stderr, " %s=%lld", names[k], t[16 * i + k] - t[0]);
-      fprintf(stderr, "\n");
-    }
-    if (H >= 3) {   // iteration 2 of CTA 0, slab by slab / weight box by weight box (cycles since acc_p7 of iteration 0)
-      fprintf(stderr, "[SD_TRACE_PIMG] iter 2 A slabs (issued -> landed):");
-      for (int k = 0; k < 72; ++k) fprintf(stderr, " %d:%lld->%lld", k, t[336 + k] ? t[336 + k] - t[0] : 0, t[256 + k] ? t[256 + k] - t[0] : 0);
-      fprintf(stderr, "\n[SD_TRACE_PIMG] iter 2 W boxes (issued -> landed):");
-      for (int k = 0; k < 92; ++k) fprintf(stderr, " %d:%lld->%lld", k, t[512 + k] ? t[512 + k] - t[0] : 0, t[416 + k] ? t[416 + k] - t[0] : 0);
-      fprintf(stderr, "\n[SD_TRACE_PIMG] iter 2 MMA thread per weight box (w seen -> mmas issued -> commits issued):");
-      for (int k = 0; k < 32; ++k) fprintf(stderr, " %d:%lld->%lld->%lld", k, t[416 + k] - t[0], t[640 + 2 * k] - t[0], t[641 + 2 * k] - t[0]);
+      for (int k = 0; k < 32; ++k) if (t[32 * i + k]) fprintf(stderr, " %s=%lld", names[k], t[32 * i + k] - t[0]);
       fprintf(stderr, "\n");
     }
   }
@@ -1920,7 +1914,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     base.stride = tape ? 1 : 0;
     const HeadW& actor = h->heads[SD_MOD_ACTOR];
     const int ldf = H * F;
-    if (cx.tc && !tape && ((flags & SD_FLAG_PERSISTENT) || pimg_enabled()) && h->pi_wp7 && pimg_shape_ok(*h)) {
+    if (cx.tc && !tape && !(flags & SD_FLAG_LAYERWISE) && ((flags & SD_FLAG_PERSISTENT) || pimg_enabled()) && h->pi_wp7 && pimg_shape_ok(*h)) {
       imagine_persistent(cx, N, H, stoch0, deter0, u, act_noise, feats, actions);
       return;
     }

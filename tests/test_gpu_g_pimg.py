@@ -1,10 +1,10 @@
 """GPU tests of the bf16 imagination rollout (Dreamer._imagine, dreamer.py:673-692) over the FULL horizon: the
-layer-by-layer tcgen05 launch sequence (default; the path the headline benchmark runs) and the persistent
-team-resident kernel (csrc/sd_pimg.cuh, SD_FLAG_PERSISTENT).
+persistent team-resident kernel (csrc/sd_pimg.cuh; the default for the base architecture and the path the headline
+benchmark runs) and the layer-by-layer tcgen05 launch sequence (SD_FLAG_LAYERWISE).
 
 Both are bf16-operand / fp32-accumulate, so element-wise parity is checked teacher-forced (test_gpu_b_tc.py and the
 first test below) and over the full horizon statistically:
-  * against the layer-by-layer tcgen05 path (default; the persistent kernel is selected with SD_FLAG_PERSISTENT) and the fp32 path of the same library:
+  * the two bf16 paths against each other and against the fp32 path of the same library:
     step-0 actions, step-1 deter, per-step index agreement, per-step action / deter statistics, and the
     mean / 5 % / 95 % quantiles of the lambda-return computed from the rolled-out features
   * structure: stoch rows exact one-hots, feats[:, 0] the start state, deter a convex mix (|d| <= 1)
@@ -19,7 +19,7 @@ from oracle import rssm_oracle as O
 from tests.helpers import cu, make_engine
 
 pytestmark = pytest.mark.gpu
-BF16, GRAPH, PERSIST = 1, 4, 32
+BF16, GRAPH, PERSIST, LAYERWISE = 1, 4, 32, 64
 
 
 def _np(t):
@@ -43,7 +43,7 @@ def test_pimg_matches_layerwise_and_oracle_first_steps(full):
     N, H = 384, 3
     st0, dt0, u, noise = O.synth_imagine_inputs(c, N, H, seed=31)
     fp, ap = [_np(x).copy() for x in eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=BF16 | PERSIST)]
-    fl, al = [_np(x).copy() for x in eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=BF16)]
+    fl, al = [_np(x).copy() for x in eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=BF16 | LAYERWISE)]
     torch.cuda.synchronize()
     np.testing.assert_array_equal(fp[:, 0], fl[:, 0])
     print("pimg vs layerwise: |dact0| =", np.abs(ap[:, 0] - al[:, 0]).max(), " |ddeter1| =", np.abs(fp[:, 1, c.SK:] - fl[:, 1, c.SK:]).max())
@@ -108,7 +108,7 @@ def test_pimg_h16_statistical_parity(full):
     ins = [cu(x) for x in (st0, dt0, u, noise)]
     f32, a32 = [_np(x).copy() for x in eng.imagine(*ins, H, flags=0)]
     fb, ab = [_np(x).copy() for x in eng.imagine(*ins, H, flags=BF16 | PERSIST)]
-    fw, aw = [_np(x).copy() for x in eng.imagine(*ins, H, flags=BF16)]
+    fw, aw = [_np(x).copy() for x in eng.imagine(*ins, H, flags=BF16 | LAYERWISE)]
     torch.cuda.synchronize()
     flip = [(_idx(fb[:, t], c) != _idx(f32[:, t], c)).mean() for t in range(H)]
     flip_w = [(_idx(fw[:, t], c) != _idx(f32[:, t], c)).mean() for t in range(H)]
