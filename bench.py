@@ -31,6 +31,7 @@ N = B * T
 FLOP_IMAG_STEP = 11_674_624       # fwd FLOP per imagined row-step (A=6 continuous)
 FLOP_POST_STEP = 10_488_832       # fwd FLOP per posterior row-step (E=1024)
 FLOP_HEADS_ROW = 6_159_360        # reward+cont+value+slow value per imagined row
+FLOP_ACTOR = 1_579_008            # actor MLP on one feat (part of FLOP_IMAG_STEP)
 METRIC = "imagined RSSM steps/s"
 WORKLOAD = "C2 dmc-vision r2dreamer base.yaml: observe B=16,T=64,E=1024 + imagine N=1024,H=16,A=6 + heads/lambda-return"
 
@@ -202,26 +203,39 @@ def run_gpu(args):
     ev_fwd, ev_side, ev_w = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     overlap = have_bwd and not args.no_overlap
 
+    PERSIST, LAYERWISE = 32, 64
+    # Schedules of one pass.  The imagination + heads only need the posterior FORWARD, so they may run on a second stream
+    # beside the posterior backward (the step's critical path).  The persistent rollout kernel is the fastest in isolation
+    # but holds its SMs for its whole duration; the launch sequence leaves gaps the backward's small kernels slip into.
+    #   overlap_layerwise   side stream: 13-launch-per-step sequence (SD_FLAG_BACKGROUND: no PDL pre-launch)
+    #   overlap_persistent  side stream: persistent kernel on SD_PIMG_BG_TEAMS (default 4) teams = 64 SMs
+    #   serial_persistent   one stream: backward, then the persistent kernel on all 8 teams, then the heads
+    SCHEDULES = {"overlap_layerwise": (True, LAYERWISE | BG), "overlap_persistent": (True, PERSIST | BG),
+                 "serial_persistent": (False, PERSIST)}
+    if not have_bwd or args.no_overlap:
+        SCHEDULES = {"serial_persistent": (False, PERSIST), "serial_layerwise": (False, LAYERWISE)}
+    sched = {"name": next(iter(SCHEDULES))}
+
     def hot_path():
-        nonlocal overlap
+        over, iflags = SCHEDULES[sched["name"]]
         main = torch.cuda.current_stream(dev)
         if have_bwd:
             bucket.zero_()
         st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | (TAPE if have_bwd else 0), out=obs_out)
-        if overlap:
+        if over:
             ev_fwd.record(main)
             side.wait_event(ev_fwd)
             with torch.cuda.stream(side):
-                eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH | BG, out=(feats, actions))
+                eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH | iflags, out=(feats, actions))
                 eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH | BG, out=outs)
                 ev_side.record(side)
         if have_bwd:
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
             bucket.allreduce_async()   # DP: ONE flat NCCL all-reduce of the RSSM grads
-        if overlap:
+        if over:
             main.wait_event(ev_side)
         else:
-            eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions))
+            eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH | iflags, out=(feats, actions))
             eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
         if have_bwd:
             bucket.wait()
@@ -237,18 +251,27 @@ def run_gpu(args):
             total += a.elapsed_time(b)
         return total
 
-    for _ in range(max(args.warmup, 3)):
-        hot_path()
+    # every schedule computes the same rows with the same kernels per path: warm each up, check that the overlapped launch
+    # sequence is bit-identical to its single-stream form, time each over a few steps and keep the fastest for the timed run
+    sched_ms, results = {}, {}
+    for name in SCHEDULES:
+        sched["name"] = name
+        for _ in range(max(args.warmup, 3)):
+            hot_path()
+        torch.cuda.synchronize()
+        results[name] = (outs[-1].clone(), bucket.flat.clone() if have_bwd else None)
+        sched_ms[name] = timed(hot_path, max(5, args.steps // 2)) / max(5, args.steps // 2)
+    if "overlap_persistent" in results and "serial_persistent" in results:
+        assert torch.equal(results["overlap_persistent"][0], results["serial_persistent"][0]), "stream overlap changed the results"
+        assert torch.equal(results["overlap_persistent"][1], results["serial_persistent"][1]), "stream overlap changed the gradients"
+    if world > 1:   # all ranks must agree on the schedule
+        tsel = torch.tensor([sched_ms[n] for n in SCHEDULES], device=dev)
+        dist.all_reduce(tsel, op=dist.ReduceOp.MAX)
+        sched_ms = {n: float(v) for n, v in zip(SCHEDULES, tsel.tolist())}
+    sched["name"] = args.schedule if args.schedule in SCHEDULES else min(sched_ms, key=sched_ms.get)
+    overlap = SCHEDULES[sched["name"]][0]
+    hot_path()
     torch.cuda.synchronize()
-    if overlap:  # the two-stream schedule must produce exactly what the single-stream one does
-        ref_ret, ref_w = outs[-1].clone(), bucket.flat.clone()
-        overlap = False
-        hot_path()
-        torch.cuda.synchronize()
-        assert torch.equal(ref_ret, outs[-1]) and torch.equal(ref_w, bucket.flat), "stream overlap changed the results"
-        overlap = True
-        hot_path()
-        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -265,7 +288,8 @@ def run_gpu(args):
     # dominant kernel sequence: the imagination scan alone (CUDA events on the launching stream)
     st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out)
     st, dt = st.reshape(N, c.S, c.K), dt.reshape(N, c.D)
-    ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH, out=(feats, actions)), args.steps)
+    ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | PERSIST, out=(feats, actions)), args.steps)
+    ms_imag_lw = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | LAYERWISE, out=(feats, actions)), args.steps)
     ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out), args.steps)
     ms_heads = timed(lambda: eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs), args.steps)
     ms_obs_fb = ms_wm = None
@@ -329,6 +353,7 @@ def run_gpu(args):
     rssm.stage_inputs, rssm.cache_params = False, True
     rssm.static_grads = True    # p.grad is reset to None every step (no accumulation): it may alias the gradient bucket
     rssm.max_rows, rssm.max_steps = N, max(T, H)
+    rssm.imagine_path = "layerwise" if "layerwise" in sched["name"] else "persistent"
     h_embed = torch.from_numpy(emb_np).pin_memory()
     h_action = torch.from_numpy(act_np).pin_memory()
     h_first = torch.from_numpy(rst_np.astype(np.uint8)).pin_memory()
@@ -336,7 +361,9 @@ def run_gpu(args):
     h2d = sum(x.numel() * x.element_size() for x in (h_embed, h_action, h_first, h_s0, h_d0))
 
     dev_in = [torch.empty_like(x, device=dev) for x in (h_embed, h_action, h_first, h_s0, h_d0)]
-    pin_res = [torch.zeros(1).pin_memory() for _ in range(2)]
+    # what the step hands back to the host: the lambda-returns of all imagined rows (dreamer.py:600-602 feeds them to the
+    # actor / critic losses and the logged metrics of dreamer.py:626-636), not just one scalar
+    pin_res = [torch.zeros(N, H - 1, 1).pin_memory() for _ in range(2)]
     ev_res = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_step(slot=None):
@@ -390,8 +417,10 @@ def run_gpu(args):
         if work is not None:
             work.wait()
         if slot is None:
-            return float(r_[-1].mean().item())           # D2H read of the step's result (blocking)
-        pin_res[slot].copy_(r_[-1].mean().reshape(1), non_blocking=True)   # async D2H read, consumed one step later
+            pin_res[0].copy_(r_[-1], non_blocking=True)   # D2H read of the step's result (blocking)
+            torch.cuda.current_stream(dev).synchronize()
+            return float(pin_res[0].mean())
+        pin_res[slot].copy_(r_[-1], non_blocking=True)   # async D2H read, consumed one step later
         ev_res[slot].record(main)
         return None
 
@@ -431,9 +460,9 @@ def run_gpu(args):
         e2e_step(k & 1)
         if k > 0:
             ev_res[(k - 1) & 1].synchronize()
-            seen.append(float(pin_res[(k - 1) & 1][0]))
+            seen.append(float(pin_res[(k - 1) & 1].mean()))
     ev_res[(args.steps - 1) & 1].synchronize()
-    seen.append(float(pin_res[(args.steps - 1) & 1][0]))
+    seen.append(float(pin_res[(args.steps - 1) & 1].mean()))
     torch.cuda.synchronize()
     e2e_async_s = time.perf_counter() - t1
     assert len(seen) == args.steps and all(np.isfinite(seen))
@@ -450,7 +479,15 @@ def run_gpu(args):
     if rank == 0:
         sus, burst, how = peaks()
         units = N * H * args.steps * world
-        imag_tflops = N * H * FLOP_IMAG_STEP / (ms_imag / args.steps * 1e-3) / 1e12
+        # FLOP actually executed by one rollout: H actor evaluations + (H - 1) Deter / prior evaluations per row (the H-th
+        # img_step is discarded by the reference, dreamer.py:680-688, and not computed)
+        flop_row = H * FLOP_ACTOR + (H - 1) * (FLOP_IMAG_STEP - FLOP_ACTOR)
+        imag_tflops = N * flop_row / (ms_imag / args.steps * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "r02_imagine_traffic.json")
+        if os.path.exists(tj) and N == 1024 and H == 16:
+            tjd = json.load(open(tj))
+            traffic, traffic_src = tjd["dram_bytes"], f"profiles/r02_imagine_traffic.json ({tjd['source']}; regenerate with profiles/ncu_traffic.py)"
         cpu = None
         gpu_ref = None
         if world == 1 and not args.no_cpu_baseline:
@@ -502,25 +539,32 @@ def run_gpu(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 (imagination/heads GEMMs, fp32 accumulate) + f32 (posterior scan, all sampling)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows": N, "horizon": H, "posterior_bwd": bool(have_bwd),
+            "config": {"workload": WORKLOAD, "rows": N, "horizon": H, "posterior_bwd": bool(have_bwd), "schedule": sched["name"],
                        "l2": "256 MB flush write between timed iterations (outside the event pairs)",
                        "multi_gpu": "each rank scans its own replay slice; RSSM grad all-reduce (NCCL) overlapped with imagination" if have_bwd else "replicas only",
                        "streams": "imagination+heads on a second stream concurrent with the posterior backward" if overlap else "single stream"},
+            "schedules_ms": sched_ms,
             "gpu_launches": int(launches),
             "world_model_updates_per_s": None if ms_wm is None else world * args.steps / (ms_wm * 1e-3),
             "imagined_steps_per_s_fwd_bwd_dgrad": None if ms_imag_fb is None else world * N * H * args.steps / (ms_imag_fb * 1e-3),
             "posterior_steps_per_s_fwd_bwd": None if ms_obs_fb is None else world * N * args.steps / (ms_obs_fb * 1e-3),
             "breakdown_ms": {"observe_fwd": ms_obs / args.steps, "world_model_update": None if ms_wm is None else ms_wm / args.steps, "observe_fwd_bwd": None if ms_obs_fb is None else ms_obs_fb / args.steps,
-                             "imagine_fwd": ms_imag / args.steps, "imagine_fwd_bwd_dgrad": None if ms_imag_fb is None else ms_imag_fb / args.steps, "heads_lambda": ms_heads / args.steps},
-            "roofline": {"bound": "tensor", "achieved": imag_tflops, "peak": sus, "unit": "TFLOP/s", "frac": imag_tflops / sus,
-                         "traffic": 8.11e8, "traffic_source": "ncu --cache-control none, dram__bytes_read+write summed over the launches of one sd_imagine_fwd call (profiles/r01c_imagine_warm_cache.txt, minus the driver script's own at::reduce); algorithmic HBM bytes 2.12e8",
-                         "kernel": "sd_imagine_fwd scan (tcgen05 GEMMs + fused row kernels, one CUDA graph of 13 launches per step)",
-                         "peak_source": f"{how} bf16_tflops_sustained (burst {burst})",
-                         "flop_per_unit": FLOP_IMAG_STEP, "units_per_launch": N * H},
+                             "imagine_fwd": ms_imag / args.steps, "imagine_fwd_layerwise": ms_imag_lw / args.steps, "imagine_fwd_bwd_dgrad": None if ms_imag_fb is None else ms_imag_fb / args.steps, "heads_lambda": ms_heads / args.steps},
+            "roofline": {"bound": "tensor", "achieved": imag_tflops, "peak": burst, "unit": "TFLOP/s", "frac": imag_tflops / burst,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_hbm_bytes": 2.12e8,
+                         "kernel": "sd::pimg::imagine_persistent_kernel: the whole sd_imagine_fwd rollout (H iterations) in ONE launch, timed alone",
+                         "peak_source": f"{how} bf16_tflops burst (kernel timed in isolation; sustained {sus})",
+                         "flop_per_unit": flop_row / H, "units_per_launch": N * H,
+                         "note": "flop_per_unit = executed FLOP per imagined row-step: H actor + (H-1) Deter/prior evaluations per row"},
+            "roofline_posterior": {"bound": "latency", "kernel": "observe_scan_kernel (persistent weight-stationary posterior scan, fp32 3xTF32 mma.sync)",
+                                   "us_per_step": 1e3 * ms_obs / args.steps / T, "grid_barriers_per_step": 5,
+                                   "achieved_tflops": B * T * FLOP_POST_STEP / (ms_obs / args.steps * 1e-3) / 1e12,
+                                   "note": "M = 16 rows per step: 168 MFLOP per step against 10.5 MB of resident weights; bounded by the 5 grid "
+                                           "barriers + dependent phases of a step, not by the tensor or HBM roofline"},
             "cpu_baseline": cpu,
             "gpu_reference": gpu_ref,
             "e2e": {"value": N * H * args.steps * world / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "d2h_bytes_per_step": int(pin_res[0].numel() * 4), "ms_per_step": 1e3 * e2e_s / args.steps},
             "e2e_async_read": {"value": N * H * args.steps * world / e2e_async_s, "unit": "steps/s", "ms_per_step": 1e3 * e2e_async_s / args.steps,
                                "note": "same loop, the D2H result copy is consumed one step later (host launch work overlaps the previous step)"},
             "clocks": sampler.summary(),
@@ -542,6 +586,7 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the unmodified reference modules on this GPU")
     ap.add_argument("--ref-compile", action="store_true", help="also time the reference under torch.compile(mode='reduce-overhead') (minutes)")
     ap.add_argument("--no-imagine-bwd", action="store_true", help="skip the grad-enabled imagination (attack shape) measurement")
+    ap.add_argument("--schedule", default="auto", help="hot-path schedule: auto (fastest of the measured ones) or a name from the JSON's schedules_ms")
     ap.add_argument("--no-overlap", action="store_true", help="run imagination after (not concurrently with) the posterior backward")
     ap.add_argument("--batch", type=int, default=16, help="replay batch B per GPU (default: base.yaml's 16; the headline config)")
     args = ap.parse_args()

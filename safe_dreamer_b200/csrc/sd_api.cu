@@ -1824,7 +1824,7 @@ static bool make_map_box(CUtensorMap* m, const bf16* ptr, uint64_t rows, uint64_
   return make_map(m, ptr, rows, cols, ld, box_rows);
 }
 static void imagine_persistent(Ctx& cx, int N, int H, const float* stoch0, const float* deter0, const float* u,
-                               const float* act_noise, float* feats, float* actions) {
+                               const float* act_noise, float* feats, float* actions, uint32_t flags) {
   namespace pi = sd::pimg;
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
@@ -1844,6 +1844,10 @@ static void imagine_persistent(Ctx& cx, int N, int H, const float* stoch0, const
   int teams = sms / pi::CL;
   if (teams > h.pi_teams_max) teams = h.pi_teams_max;
   if (teams > ngroups) teams = ngroups;
+  // SD_FLAG_BACKGROUND: the rollout runs beside latency-critical work on another stream; a persistent kernel keeps its SMs
+  // for its whole duration, so it takes only SD_PIMG_BG_TEAMS teams (16 SMs each) and walks the row groups in turn
+  static const int bg_teams = env_flag("SD_PIMG_BG_TEAMS", 4);
+  if ((flags & SD_FLAG_BACKGROUND) && bg_teams > 0 && teams > bg_teams) teams = bg_teams;
   cudaMemsetAsync(h.pi_flags, 0, (size_t)teams * pi::flags_per_team() * sizeof(unsigned int), cx.st);
   pi::Params P;
   memset(&P, 0, sizeof(P));
@@ -1915,7 +1919,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     const HeadW& actor = h->heads[SD_MOD_ACTOR];
     const int ldf = H * F;
     if (cx.tc && !tape && !(flags & SD_FLAG_LAYERWISE) && ((flags & SD_FLAG_PERSISTENT) || pimg_enabled()) && h->pi_wp7 && pimg_shape_ok(*h)) {
-      imagine_persistent(cx, N, H, stoch0, deter0, u, act_noise, feats, actions);
+      imagine_persistent(cx, N, H, stoch0, deter0, u, act_noise, feats, actions, flags);
       return;
     }
     // feats[:, 0] = [stoch0 | deter0] (rssm.py:211-217)

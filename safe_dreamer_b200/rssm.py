@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import engine as _engine
-from ._lib import SD_FLAG_BACKGROUND
+from ._lib import SD_FLAG_BACKGROUND, SD_FLAG_LAYERWISE, SD_FLAG_PERSISTENT
 from .engine import MOD_RSSM, SD_FLAG_BF16, SD_FLAG_GRAPH, SD_FLAG_SAVE_TAPE
 
 _U_LO = 2.0 ** -24
@@ -268,6 +268,12 @@ class RSSM(nn.Module):
         f = SD_FLAG_BF16 if self.precision == "bf16" else 0
         if getattr(self, "background", False):   # calls issued beside latency-critical work on another stream
             f |= SD_FLAG_BACKGROUND
+        # imagination rollout: None = library default (persistent kernel where eligible), "persistent" / "layerwise" force one
+        path = getattr(self, "imagine_path", None)
+        if path == "persistent":
+            f |= SD_FLAG_PERSISTENT
+        elif path == "layerwise":
+            f |= SD_FLAG_LAYERWISE
         return f | (SD_FLAG_GRAPH if self.use_graph else 0)
 
     def engine_dims(self):
