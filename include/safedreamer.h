@@ -226,14 +226,18 @@ int sd_barlow_loss(const float* x1, const float* x2, int N, int E, float lambd, 
 
 /* Fused multi-tensor optimiser step = clip_grad_agc_ (utils/optim/agc.py:15-60) followed by LaProp.step
  * (utils/optim/laprop.py:46-118, amsgrad = centered = False) for `count` fp32 tensors in three launches.
- *   AGC    : per tensor scale = 1 / max(||g||_2 / (clip * max(||p||_2, pmin)), 1), g *= scale (clip <= 0: no clipping);
- *   LaProp : g' = g * inv_scale (GradScaler's unscale, 1 when unused); v = beta2 v + one_minus_beta2 g'^2;
+ *   unscale: g' = g * inv_scale (GradScaler.unscale_, dreamer.py:422; 1 when unused) -- BEFORE the clip, as in the reference;
+ *   AGC    : per tensor scale = 1 / max(||g'||_2 / (clip * max(||p||_2, pmin)), 1), g' *= scale (clip <= 0: no clipping);
+ *            p.grad is left holding the unscaled, clipped gradient;
+ *   LaProp : v = beta2 v + one_minus_beta2 g'^2;
  *            m = beta1 m + lr_term * g' / (sqrt(v / bias_correction2) + eps), lr_term = (1 - beta1) * lr;
  *            p -= step_size * m (step_size = 1 / bias_correction1); p -= weight_decay * p.
  * The scalar state (exp_avg_lr_1/2 -> step_size, bias_correction2) stays on the host as in the reference.
  * `table_dev` / `scratch_dev`: device buffers of sd_opt_table_bytes(count) / sd_opt_scratch_bytes(tensors, count) bytes.
  * found_inf (device int, nullable): set to 1 and the update skipped when a gradient norm is not finite.
- * mode 0 = AGC + LaProp, 1 = AGC only (scales the gradients in place, nothing else). */
+ * mode 0 = AGC + LaProp, 1 = AGC only (scales the gradients in place, nothing else), 2 = finite check only (raises
+ * *found_inf when a gradient norm is not finite; nothing is written: run it over ALL tensors before a step that is
+ * split into several calls, so that an overflow skips every one of them). */
 typedef struct sd_opt_tensor {
   float* param; float* grad; float* exp_avg; float* exp_avg_sq;
   int64_t numel;

@@ -1732,7 +1732,7 @@ extern "C" int sd_prior(sd_handle* h, int R, const float* deter, const float* u,
   const sd_config& c = h->c;
   const bool tape = flags & SD_FLAG_SAVE_TAPE;
   if (tape && c.max_tape_rows <= 0) return fail(SD_ERR_WORKSPACE, "sd_prior: handle was created without a tape (max_tape_rows=0)");
-  if (tape) h->ptape_R = 0;
+  h->ptape_R = 0;   // the prior tape shares its buffers with every sd_prior call: an untaped call invalidates it too
   // batched over all (B,T) rows in one pass (dreamer.py:485)
   Key key;
   key.add(2).add(R).add(deter).add(u).add(stoch).add(logit).add(flags);
@@ -2799,7 +2799,7 @@ extern "C" int sd_agc_laprop_step(const sd_opt_tensor* tensors, int count, int m
                                   float bias_correction2, float eps, float weight_decay, void* table_dev, void* scratch_dev,
                                   int* found_inf, void* stream) {
   if (!tensors || count < 1 || !table_dev || !scratch_dev) return fail(SD_ERR_INVALID, "sd_agc_laprop_step: null argument");
-  if (mode != 0 && mode != 1) return fail(SD_ERR_INVALID, "sd_agc_laprop_step: mode must be 0 or 1");
+  if (mode < 0 || mode > 2) return fail(SD_ERR_INVALID, "sd_agc_laprop_step: mode must be 0, 1 or 2");
   std::vector<sd::OptTensor> tbl((size_t)count);
   int blocks = 0;
   for (int i = 0; i < count; ++i) {
@@ -2817,8 +2817,10 @@ extern "C" int sd_agc_laprop_step(const sd_opt_tensor* tensors, int count, int m
   float* partial = static_cast<float*>(scratch_dev);
   float* scale = partial + 2 * (size_t)blocks;
   launch_k(st, sd::opt_norm_kernel, dim3(blocks), dim3(256), 0, td, count, partial);
-  launch_k(st, sd::opt_finalize_kernel, dim3(1), dim3(256), 0, td, count, (const float*)partial, clip, pmin, scale, found_inf);
-  if (mode == 0)
+  launch_k(st, sd::opt_finalize_kernel, dim3(1), dim3(256), 0, td, count, (const float*)partial, clip, pmin,
+           mode == 0 ? inv_scale : 1.f, scale, found_inf);
+  if (mode == 2) {   // finite check only: raises *found_inf, touches nothing
+  } else if (mode == 0)
     launch_k(st, sd::opt_update_kernel, dim3(blocks), dim3(256), 0, td, count, (const float*)scale, (const int*)found_inf, inv_scale,
              beta1, beta2, one_minus_beta2, lr_term, step_size, bias_correction2, eps, weight_decay, 1);
   else

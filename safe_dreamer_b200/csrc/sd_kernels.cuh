@@ -1620,8 +1620,10 @@ __global__ void __launch_bounds__(256) opt_norm_kernel(const OptTensor* __restri
   sg = block_sum(sg, sh);
   if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sp; partial[2 * blockIdx.x + 1] = sg; }
 }
+// inv_scale: GradScaler's unscale factor.  The reference unscales the gradients first (scaler.unscale_, dreamer.py:422) and
+// clips the UNSCALED gradients (dreamer.py:432), so the gradient norm that enters the clip factor is ||g|| * inv_scale.
 __global__ void __launch_bounds__(256) opt_finalize_kernel(const OptTensor* __restrict__ t, int count, const float* __restrict__ partial,
-                                                           float clip, float pmin, float* scale, int* found_inf) {
+                                                           float clip, float pmin, float inv_scale, float* scale, int* found_inf) {
   pdl_prologue();
   for (int ti = threadIdx.x; ti < count; ti += 256) {
     const OptTensor e = t[ti];
@@ -1630,7 +1632,7 @@ __global__ void __launch_bounds__(256) opt_finalize_kernel(const OptTensor* __re
     float s = 1.f;
     if (clip > 0.f) {
       const float upper = fmaxf(sqrtf(sp), pmin) * clip;
-      s = 1.f / fmaxf(sqrtf(sg) / upper, 1.f);
+      s = 1.f / fmaxf((sqrtf(sg) * inv_scale) / upper, 1.f);
     }
     scale[ti] = s;
     if (found_inf && !isfinite(sg)) atomicOr(found_inf, 1);
@@ -1648,9 +1650,8 @@ __global__ void __launch_bounds__(256) opt_update_kernel(const OptTensor* __rest
   const long long i0 = (long long)(blockIdx.x - e.blk0) * kOptChunk;
   const long long i1 = min(e.n, i0 + kOptChunk);
   for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
-    float g = __fmul_rn(e.g[i], gs);
-    if (write_grads) e.g[i] = g;                    // clip_grad_agc_ scales p.grad in place
-    g = __fmul_rn(g, inv_scale);
+    const float g = __fmul_rn(__fmul_rn(e.g[i], inv_scale), gs);   // unscale, then clip (dreamer.py:422,432)
+    if (write_grads) e.g[i] = g;                    // scaler.unscale_ / clip_grad_agc_ both work on p.grad in place
     const float v = __fadd_rn(__fmul_rn(e.v[i], beta2), __fmul_rn(__fmul_rn(omb2, g), g));
     e.v[i] = v;
     const float denom = __fadd_rn(sqrtf(v / bc2), eps);

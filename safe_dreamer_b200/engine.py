@@ -149,6 +149,23 @@ class Engine:
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ entry points
+    # The library keeps ONE observe/imagine tape and ONE prior tape per handle (single slot).  `tape_gen` counts the taped
+    # forwards so that a backward can prove the tape it is about to consume is still the one its forward wrote.
+    tape_gen = {"scan": 0, "prior": 0}
+
+    def _bump(self, which):
+        if self.tape_gen is Engine.tape_gen:
+            self.tape_gen = {"scan": 0, "prior": 0}
+        self.tape_gen[which] += 1
+        return self.tape_gen[which]
+
+    def check_tape(self, which, gen, who):
+        if self.tape_gen.get(which, 0) != gen:
+            raise RuntimeError(
+                f"{who}: the {which} tape of this engine was overwritten by a later taped forward (generation {gen} -> "
+                f"{self.tape_gen.get(which, 0)}).  The library keeps one tape per handle: run each backward before the next "
+                f"grad-enabled forward of the same kind, or use a second RSSM module / engine for the second graph.")
+
     def observe(self, embed, action, init_stoch, init_deter, is_first, u, flags=0, out=None):
         B, T = action.shape[:2]
         embed, action, u = _f32c(embed, "embed"), _f32c(action, "action"), _f32c(u, "u")
@@ -167,6 +184,8 @@ class Engine:
         _lib.check(self.lib.sd_observe_fwd(self.h, B, T, _ptr(embed), _ptr(action), _ptr(init_stoch), _ptr(init_deter),
                                            _ptr(first), _ptr(u), _ptr(stochs), _ptr(deters), _ptr(logits), flags,
                                            self.stream), "sd_observe_fwd")
+        if flags & SD_FLAG_SAVE_TAPE:
+            self._bump("scan")
         return stochs, deters, logits
 
     def observe_bwd(self, B, T, d_stochs, d_deters, d_logits, want_embed=True, want_init=True, weight_grads=None,
@@ -201,6 +220,7 @@ class Engine:
             self._imag_feats = None   # sd_prior stages its bf16 operand in the same buffer
         _lib.check(self.lib.sd_prior(self.h, R, _ptr(deter), _ptr(u), _ptr(stoch), _ptr(logit), flags, self.stream),
                    "sd_prior")
+        self._bump("prior")   # taped or not: every sd_prior call rewrites the prior tape's buffers
         return stoch.reshape(*lead, c.S, c.K), logit.reshape(*lead, c.S, c.K)
 
     def prior_bwd(self, R, d_stoch, d_logit, want_deter=True, weight_grads=None, flags=0):
@@ -240,6 +260,8 @@ class Engine:
         feats, actions = out if out is not None else (self._new(N, H, self.F, tag="im_f"), self._new(N, H, c.A, tag="im_a"))
         _lib.check(self.lib.sd_imagine_fwd(self.h, N, H, _ptr(stoch0), _ptr(deter0), _ptr(u), _ptr(act_noise),
                                            _ptr(feats), _ptr(actions), flags, self.stream), "sd_imagine_fwd")
+        if flags & SD_FLAG_SAVE_TAPE:
+            self._bump("scan")
         # the library kept a bf16 copy of feats (tcgen05 path, no tape): heads_lambda() may reuse it while feats is unmodified
         self._imag_feats = (feats.data_ptr(), feats._version, N, H) if (flags & SD_FLAG_BF16 and not flags & SD_FLAG_SAVE_TAPE
                                                                        and N >= 128) else None

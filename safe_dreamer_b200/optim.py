@@ -82,12 +82,19 @@ class LaProp(Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad,
                                       centered=centered))
         self.agc, self.pmin = agc, pmin
-        self._fused = _Fused()
+        self._fused, self._check, self._more = _Fused(), _Fused(), {}
 
     @torch.no_grad()
-    def step(self, inv_scale=1.0, found_inf=None):
+    def step(self, inv_scale=1.0, found_inf=None, sync=False):
         """One optimisation step (laprop.py:46-118).  inv_scale / found_inf: GradScaler's unscale factor and (device int32)
-        overflow flag, for callers that fold `scaler.step` in; a raised flag skips the tensor updates."""
+        overflow flag, for callers that fold `scaler.unscale_` + `scaler.step` in (dreamer.py:422,433): gradients are unscaled
+        BEFORE the AGC clip, and a raised flag skips every tensor update of the step (the finite check runs over all
+        tensors before the first update launch).  The scalar state (`step`, `exp_avg_lr_1/2`) lives on the host as in the
+        reference: with sync=True the flag is read back after the launches and that state is rolled back when the step
+        was skipped (what GradScaler.step does by not calling optimizer.step()); with sync=False (no host sync) call
+        `rollback()` yourself once you have seen the flag."""
+        self._undo = []
+        todo = []
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             buckets = {}
@@ -103,6 +110,7 @@ class LaProp(Optimizer):
                     state["exp_avg_lr_1"] = 0.0
                     state["exp_avg_lr_2"] = 0.0
                     state["exp_avg_sq"] = torch.zeros_like(p.data)
+                self._undo.append((state, state["step"], state["exp_avg_lr_1"], state["exp_avg_lr_2"]))
                 state["step"] += 1
                 state["exp_avg_lr_1"] = state["exp_avg_lr_1"] * beta1 + (1 - beta1) * group["lr"]
                 state["exp_avg_lr_2"] = state["exp_avg_lr_2"] * beta2 + (1 - beta2)
@@ -110,5 +118,19 @@ class LaProp(Optimizer):
                 key = (1 / bc1, state["exp_avg_lr_2"])
                 buckets.setdefault(key, []).append((p.data, p.grad, state["exp_avg"], state["exp_avg_sq"]))
             for (step_size, bc2), entries in buckets.items():
-                self._fused.run(entries, 0, self.agc if self.agc else 0.0, self.pmin, inv_scale, beta1, beta2,
-                                (1 - beta1) * group["lr"], step_size, bc2, group["eps"], group["weight_decay"], found_inf)
+                todo.append((entries, beta1, beta2, (1 - beta1) * group["lr"], step_size, bc2, group["eps"], group["weight_decay"]))
+        if found_inf is not None and len(todo) > 1:   # several launches: no tensor may be updated if ANY gradient overflowed
+            every = [e for t in todo for e in t[0]]
+            self._check.run(every, 2, 0.0, self.pmin, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, found_inf)
+        for i, (entries, beta1, beta2, lr_term, step_size, bc2, eps, wd) in enumerate(todo):
+            fused = self._fused if i == 0 else self._more.setdefault(i, _Fused())
+            fused.run(entries, 0, self.agc if self.agc else 0.0, self.pmin, inv_scale, beta1, beta2, lr_term, step_size, bc2,
+                      eps, wd, found_inf)
+        if sync and found_inf is not None and int(found_inf.item()) != 0:
+            self.rollback()
+
+    def rollback(self):
+        """Undo the host-side scalar state of the last step() (call when its found_inf flag was raised)."""
+        for state, st, l1, l2 in getattr(self, "_undo", []):
+            state["step"], state["exp_avg_lr_1"], state["exp_avg_lr_2"] = st, l1, l2
+        self._undo = []

@@ -120,7 +120,8 @@ class _KLFn(torch.autograd.Function):
         rows = 1
         for d in lead:
             rows *= int(d)
-        eng = rssm._get_engine(max(rows, 1), 1)
+        # sd_kl_loss takes up to max_rows * max_steps rows: never grow (= rebuild) the engine here, its tapes may be live
+        eng = rssm._get_engine(min(max(rows, 1), rssm.max_rows), 1)
         dyn, rep = eng.kl_loss(post_logit, prior_logit, free)
         ctx.save_for_backward(post_logit, prior_logit)
         ctx.rssm, ctx.free, ctx.rows = rssm, free, rows
@@ -129,7 +130,7 @@ class _KLFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_dyn, g_rep):
         post_logit, prior_logit = ctx.saved_tensors
-        eng = ctx.rssm._get_engine(max(ctx.rows, 1), 1)
+        eng = ctx.rssm._get_engine(min(max(ctx.rows, 1), ctx.rssm.max_rows), 1)
         d_post, d_prior = eng.kl_loss_bwd(post_logit, prior_logit, ctx.free, g_dyn.contiguous(), g_rep.contiguous(),
                                           ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return None, d_post, d_prior, None
@@ -144,6 +145,7 @@ class _ObserveFn(torch.autograd.Function):
         flags = rssm._flags() | SD_FLAG_SAVE_TAPE
         stochs, deters, logits = eng.observe(embed, action, init_stoch, init_deter, reset, u, flags=flags)
         ctx.rssm, ctx.B, ctx.T = rssm, action.shape[0], action.shape[1]
+        ctx.eng, ctx.gen = eng, eng.tape_gen["scan"]
         ctx.need = (ctx.needs_input_grad[1], ctx.needs_input_grad[3] or ctx.needs_input_grad[4],
                     any(ctx.needs_input_grad[7:]))
         ctx.flags = rssm._flags()
@@ -153,6 +155,10 @@ class _ObserveFn(torch.autograd.Function):
     def backward(ctx, d_st, d_dt, d_lg):
         rssm = ctx.rssm
         eng = rssm._rt.engine
+        if eng is not ctx.eng:
+            raise RuntimeError("RSSM.observe backward: the engine that holds this call's tape was rebuilt (a later call needed more "
+                               "rows / steps than rssm.max_rows / max_steps); set those limits before the forward")
+        eng.check_tape("scan", ctx.gen, "RSSM.observe backward")
         need_embed, need_init, need_w = ctx.need
         names = eng.weight_names(MOD_RSSM)
         wg = None
@@ -192,6 +198,7 @@ class _PriorFn(torch.autograd.Function):
         eng = rssm._get_engine(min(rows, rssm.max_rows), 1, tape=True, tape_rows=1)
         stoch, logit = eng.prior(deter, u, flags=rssm._flags() | SD_FLAG_SAVE_TAPE)
         ctx.rssm, ctx.rows, ctx.lead = rssm, rows, lead
+        ctx.eng, ctx.gen = eng, eng.tape_gen["prior"]
         ctx.need = (ctx.needs_input_grad[1], any(ctx.needs_input_grad[3:]))
         ctx.flags = rssm._flags()
         return stoch, logit
@@ -200,6 +207,10 @@ class _PriorFn(torch.autograd.Function):
     def backward(ctx, d_stoch, d_logit):
         rssm = ctx.rssm
         eng = rssm._rt.engine
+        if eng is not ctx.eng:
+            raise RuntimeError("RSSM.prior backward: the engine that holds this call's tape was rebuilt (a later call needed more "
+                               "rows / steps than rssm.max_rows / max_steps); set those limits before the forward")
+        eng.check_tape("prior", ctx.gen, "RSSM.prior backward")
         need_deter, need_w = ctx.need
         wg = None
         if need_w:

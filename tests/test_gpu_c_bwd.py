@@ -278,3 +278,55 @@ def test_imagine_bwd_tcgen05_dgrad():
             cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref)))
             print(f"imagine_bwd flags={flags} {name}: rel L2 err {rel:.2e}, cosine {cos:.6f}")
             assert rel <= tol and cos >= 0.999, (flags, name, rel, cos)
+
+
+def _tiny_module(max_rows, max_steps):
+    from types import SimpleNamespace as NS
+    from safe_dreamer_b200.rssm import RSSM
+    c, z = load_golden("tiny_cont")
+    P = golden_params(c, z)
+    cfg = NS(stoch=c.S, deter=c.D, hidden=c.U, discrete=c.K, act="SiLU", unimix_ratio=c.unimix, initial="learned",
+             device="cuda", obs_layers=c.obs_layers, img_layers=c.img_layers, dyn_layers=1, blocks=c.G)
+    rssm = RSSM(cfg, c.E, c.A).cuda()
+    rssm.load_state_dict({k: cu(v) for k, v in P["rssm"].items()})
+    rssm.max_rows, rssm.max_steps = max_rows, max_steps
+    return c, P, rssm
+
+
+def test_module_update_with_more_rows_than_max_rows():
+    """B*T > rssm.max_rows: the batched prior / kl_loss must not rebuild the engine between observe's forward and its
+    backward (the tape lives in the engine).  Gradients equal those of a module whose max_rows covers B*T."""
+    B, T = 5, 8
+    grads = []
+    for max_rows in (16, 64):       # 40 rows: above / below the limit
+        c, P, rssm = _tiny_module(max_rows, 8)
+        embed, action, reset, u = O.synth_observe_inputs(c, B, T, seed=2)
+        up = O.clamp_u(np.random.Generator(np.random.Philox(41)).random((B, T, c.S, c.K), dtype=np.float32))
+        queue = [u, up]
+        rssm.noise_source = lambda shape, dev: cu(queue.pop(0)).reshape(shape)
+        e = cu(embed).requires_grad_(True)
+        st, dt, lg = rssm.observe(e, cu(action), rssm.initial(B), cu(reset)[..., None])
+        eng0 = rssm._rt.engine
+        _, plog = rssm.prior(dt)
+        dyn, rep = rssm.kl_loss(lg, plog, 1.0)
+        assert rssm._rt.engine is eng0
+        (dyn.mean() + 0.1 * rep.mean() + (st * 0.01).sum()).backward()
+        grads.append([_np(e.grad)] + [_np(p.grad) for p in rssm.parameters()])
+    for a, b in zip(*grads):
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_stale_tape_is_detected():
+    """The library keeps one tape per handle: a second grad-enabled observe() before the first backward overwrites it, and the
+    first backward must fail loudly instead of returning gradients of the wrong call."""
+    B, T = 3, 4
+    c, P, rssm = _tiny_module(16, 8)
+    embed, action, reset, u = O.synth_observe_inputs(c, B, T, seed=2)
+    e1 = cu(embed).requires_grad_(True)
+    e2 = cu(embed * 0.5).requires_grad_(True)
+    out1 = rssm.observe(e1, cu(action), rssm.initial(B), cu(reset)[..., None])
+    out2 = rssm.observe(e2, cu(action), rssm.initial(B), cu(reset)[..., None])
+    with pytest.raises(RuntimeError, match="tape"):
+        out1[1].sum().backward()
+    out2[1].sum().backward()          # the latest forward still owns the tape
+    assert e2.grad is not None and torch.isfinite(e2.grad).all()

@@ -90,3 +90,50 @@ def test_cuda_fused_agc_laprop(golden):
     assert int(flag.item()) == 1
     for p_, b_ in zip(params, before):
         assert torch.equal(p_.detach(), b_)
+
+
+@pytest.mark.gpu
+def test_cuda_fused_step_unscales_before_the_clip(golden):
+    """GradScaler folded into the step (dreamer.py:422,432-433): gradients arrive multiplied by the loss scale; they must be
+    unscaled BEFORE the AGC clip.  A power-of-two scale is exact, so the goldens of the unscaled run apply unchanged."""
+    import torch
+    from safe_dreamer_b200.optim import LaProp
+    params = [torch.nn.Parameter(torch.from_numpy(x.copy()).cuda()) for x in _inputs(-1)]
+    opt = LaProp(params, lr=LR, betas=(B1, B2), eps=EPS, agc=CLIP, pmin=PMIN)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for step in range(3):
+        for p_, g_ in zip(params, _inputs(step)):
+            p_.grad = torch.from_numpy(g_.copy()).cuda() * 65536.0
+        opt.step(inv_scale=1.0 / 65536.0, found_inf=flag, sync=True)
+        assert int(flag.item()) == 0
+        for i, p_ in enumerate(params):
+            _close(p_.grad.cpu().numpy(), golden[f"s{step}_g{i}"], f"unscaled + clipped grad, step {step} tensor {i}")
+            _close(p_.detach().cpu().numpy(), golden[f"s{step}_p{i}"], f"p step {step} tensor {i}")
+            _close(opt.state[p_]["exp_avg"].cpu().numpy(), golden[f"s{step}_m{i}"], f"m step {step} tensor {i}")
+            _close(opt.state[p_]["exp_avg_sq"].cpu().numpy(), golden[f"s{step}_v{i}"], f"v step {step} tensor {i}")
+
+
+@pytest.mark.gpu
+def test_cuda_overflow_skips_every_bucket_and_rolls_back():
+    """Two parameter groups with different learning rates are two launches: an overflow in the SECOND one must leave the
+    first untouched as well, and the host-side step counters must not advance (GradScaler.step skips optimizer.step())."""
+    import torch
+    from safe_dreamer_b200.optim import LaProp
+    a = [torch.nn.Parameter(torch.from_numpy(x.copy()).cuda()) for x in _inputs(-1)[:3]]
+    b = [torch.nn.Parameter(torch.from_numpy(x.copy()).cuda()) for x in _inputs(-1)[3:]]
+    opt = LaProp([{"params": a, "lr": LR}, {"params": b, "lr": 3 * LR}], betas=(B1, B2), eps=EPS, agc=CLIP, pmin=PMIN)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for p_, g_ in zip(a + b, _inputs(0)):
+        p_.grad = torch.from_numpy(g_.copy()).cuda()
+    opt.step(found_inf=flag, sync=True)                   # a clean step first (different bias corrections per group from now on)
+    assert int(flag.item()) == 0 and opt.state[a[0]]["step"] == 1
+    before = [p_.detach().clone() for p_ in a + b]
+    moments = [opt.state[p_]["exp_avg"].clone() for p_ in a + b]
+    for p_, g_ in zip(a + b, _inputs(1)):
+        p_.grad = torch.from_numpy(g_.copy()).cuda()
+    b[-1].grad.view(-1)[0] = float("nan")
+    opt.step(found_inf=flag, sync=True)
+    assert int(flag.item()) == 1
+    for p_, b_, m_ in zip(a + b, before, moments):
+        assert torch.equal(p_.detach(), b_) and torch.equal(opt.state[p_]["exp_avg"], m_)
+        assert opt.state[p_]["step"] == 1                 # rolled back
