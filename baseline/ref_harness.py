@@ -242,3 +242,212 @@ def time_gpu(c, P, B, T, H, dev, iters=5, modes=("eager_fp16", "eager_fp32", "co
         if log:
             log(mode, res)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ whole-agent harness
+class AttrDict(dict):
+    """Attribute access over nested dicts (what Hydra's DictConfig gives the reference)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _load_base_config():
+    """configs/base.yaml of the reference with ${a.b} interpolations resolved by hand and numeric strings ('5e5', '1e-4':
+    PyYAML reads those as str) converted."""
+    import re
+
+    import yaml
+    raw = yaml.safe_load(open(os.path.join(REF, "configs", "base.yaml")))
+
+    def lookup(path):
+        node = raw
+        for part in path.split("."):
+            node = node[part]
+        return node
+
+    num = re.compile(r"^[+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?$")
+
+    def resolve(x):
+        if isinstance(x, dict):
+            return AttrDict({k: resolve(v) for k, v in x.items()})
+        if isinstance(x, list):
+            return [resolve(v) for v in x]
+        if isinstance(x, str):
+            m = re.fullmatch(r"\$\{([^}]+)\}", x)
+            if m:
+                return resolve(lookup(m.group(1)))
+            if "${" in x:
+                return re.sub(r"\$\{([^}]+)\}", lambda mm: str(resolve(lookup(mm.group(1)))), x)
+            if num.match(x):
+                return float(x)
+        return x
+
+    return resolve(raw)
+
+
+class _Space:
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
+class _DictSpace:
+    def __init__(self, spaces):
+        self.spaces = spaces
+
+
+class _Discrete:
+    def __init__(self, n):
+        self.n, self.discrete = n, True
+
+
+class TensorDictStub(dict):
+    """What `_cal_grad` needs of a TensorDict: mapping + `.shape` (B, T) (dreamer.py:467,711,718)."""
+
+    def __init__(self, data, batch_size):
+        super().__init__(data)
+        self.shape = self.batch_size = tuple(batch_size)
+
+
+def build_dreamer(dev, kind="proprio", rep_loss="dreamer", act_dim=6, obs_dim=24, discrete_actions=0, compile=False, seed=0):
+    """The reference's own `Dreamer` (dreamer.py:22-233) from its own base.yaml.
+    kind = "proprio": one vector observation of `obs_dim` through the MLP encoder (config C1: embed size 256);
+    kind = "vision": a 64x64x3 image through the ConvEncoder (config C2: embed size 1024)."""
+    M = import_reference()
+    cfg = _load_base_config()
+    model = cfg.model
+    model.device = str(dev)
+    for sub in ("rssm", "reward", "cont", "actor", "critic"):
+        model[sub].device = str(dev)
+    model.encoder.mlp.device = str(dev)
+    model.decoder.mlp.device = str(dev)
+    model.rep_loss = rep_loss
+    model.compile = bool(compile)
+    if kind == "proprio":
+        model.encoder.mlp_keys, model.encoder.cnn_keys = "state", "$^"
+        model.decoder.mlp_keys, model.decoder.cnn_keys = "state", "$^"
+        spaces = {"state": _Space((obs_dim,))}
+    else:
+        spaces = {"image": _Space((64, 64, 3))}
+    for k in ("is_first", "is_last", "is_terminal"):
+        spaces[k] = _Space((1,))
+    spaces["reward"] = _Space((1,))
+    act_space = _Discrete(discrete_actions) if discrete_actions else _Space((act_dim,))
+    torch.manual_seed(seed)
+    agent = M.dreamer.Dreamer(model, _DictSpace(spaces), act_space).to(dev)
+    return agent, cfg
+
+
+def perturb_agent(agent, seed=1):
+    """the reference initialises reward / critic last layers to zero and RMS scales to one; perturb biases, RMS
+    scales and those last layers (peaked two-hot bias) so every number downstream is informative."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    with torch.no_grad():
+        for name, p in agent.named_parameters():
+            if name.startswith("_frozen") or name.startswith("_slow"):
+                continue
+            if name.endswith("bias"):
+                p.add_(0.1 * torch.randn(p.shape, generator=g).to(p.device))
+            elif p.dim() == 1:
+                p.copy_((0.5 + torch.rand(p.shape, generator=g)).to(p.device))
+        for head in (agent.reward, agent.value):
+            w = head.last.weight
+            w.copy_((0.01 * torch.randn(w.shape, generator=g) / (w.shape[1] ** 0.5)).to(w.device))
+            n = head.last.bias.shape[0]
+            head.last.bias.copy_((-0.5 * (torch.arange(n) - (n - 1) / 2).abs()).to(w.device))
+        w = agent.actor.last.weight
+        w.copy_((torch.randn(w.shape, generator=g) / (w.shape[1] ** 0.5)).to(w.device))
+        for v, s in zip(agent.value.parameters(), agent._slow_value.parameters()):
+            s.data.copy_(v.data)
+    agent.clone_and_freeze()
+
+
+def make_batch(agent, B, T, dev, kind="proprio", obs_dim=24, seed=2):
+    """Synthetic replay batch in the layout Dreamer.preprocess hands to `_cal_grad` (dreamer.py:709-723)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = agent.act_dim
+    data = {
+        "action": (torch.rand(B, T, A, generator=g) * 2 - 1),
+        "reward": torch.randn(B, T, 1, generator=g),
+        "is_first": (torch.rand(B, T, 1, generator=g) < 1 / 64),
+        "is_last": torch.zeros(B, T, 1, dtype=torch.bool),
+        "is_terminal": (torch.rand(B, T, 1, generator=g) < 1 / 128),
+    }
+    data["is_first"][:, 0] = True
+    if agent.act_discrete:
+        idx = torch.randint(0, A, (B, T), generator=g)
+        data["action"] = torch.nn.functional.one_hot(idx, A).float()
+    if kind == "proprio":
+        data["state"] = torch.randn(B, T, obs_dim, generator=g)
+    else:
+        data["image"] = torch.rand(B, T, 64, 64, 3, generator=g) - 0.5
+    data = TensorDictStub({k: v.to(dev) for k, v in data.items()}, (B, T))
+    initial = agent.rssm.initial(B)
+    return data, initial
+
+
+class NoiseTape:
+    """Injected noise shared by the pure reference and the installed build: uniforms for every categorical draw and
+    standard normals for the actor, consumed in the reference's order (per-step draws of `observe`, one batched `prior`
+    draw, then per imagination step actor noise followed by the prior uniforms; dreamer.py:483-485,684,688)."""
+
+    def __init__(self, B, T, N, H, S, K, A, discrete_actor, seed=3):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        lo = 2.0 ** -24
+        self.u_obs = torch.rand(B, T, S, K, generator=g).clamp_(lo, 1 - lo)
+        self.u_prior = torch.rand(B, T, S, K, generator=g).clamp_(lo, 1 - lo)
+        self.u_img = torch.rand(N, H, S, K, generator=g).clamp_(lo, 1 - lo)
+        self.a_noise = (torch.rand(N, H, A, generator=g).clamp_(lo, 1 - lo) if discrete_actor
+                        else torch.randn(N, H, A, generator=g))
+        self.discrete_actor = discrete_actor
+        self.shape = (B, T, N, H)
+
+    def reference_queues(self, dev):
+        B, T, N, H = self.shape
+        uq = [self.u_obs[:, t].to(dev) for t in range(T)] + [self.u_prior.to(dev)]
+        eq = []
+        for h in range(H):
+            if self.discrete_actor:
+                uq.append(self.a_noise[:, h].to(dev))
+            else:
+                eq.append(self.a_noise[:, h].to(dev))
+            uq.append(self.u_img[:, h].to(dev))
+        return uq, eq
+
+
+def patch_reference_noise(uq, eq):
+    """Replace the reference's two RNG draws by queue pops (same formulas: F.gumbel_softmax(hard=True) with
+    g = -log(-log u); Normal.rsample's standard normal)."""
+    M = import_reference()
+
+    def rsample(self, sample_shape=(), temperature=1.0):
+        u = uq.pop(0)
+        assert u.shape == self.logits.shape, (u.shape, self.logits.shape)
+        g = -torch.log(-torch.log(u))
+        y = ((self.logits + g) / temperature).softmax(-1)
+        index = y.max(-1, keepdim=True)[1]
+        y_hard = torch.zeros_like(self.logits, memory_format=torch.legacy_contiguous_format).scatter_(-1, index, 1.0)
+        return y_hard - y.detach() + y
+
+    old = M.dists.OneHotDist.rsample
+    M.dists.OneHotDist.rsample = rsample
+    import torch.distributions.normal as tdn
+    old_n = tdn._standard_normal
+
+    def std_normal(shape, dtype, device):
+        e = eq.pop(0)
+        assert tuple(e.shape) == tuple(shape), (e.shape, shape)
+        return e.to(dtype)
+
+    tdn._standard_normal = std_normal
+
+    def undo():
+        M.dists.OneHotDist.rsample = old
+        tdn._standard_normal = old_n
+    return undo

@@ -256,25 +256,35 @@ static bool pdl_enabled() {
 // All kernels ask for the same (maximum) shared-memory carve-out: consecutive kernels of a scan alternate
 // between 0 B and ~200 KB of dynamic shared memory, and an SM can only change its L1/shared split when it is
 // idle, which would serialise every kernel boundary.  SD_CARVEOUT=0 disables (for A/B measurements).
+// cudaFuncSetAttribute is per device: a process that drives several GPUs must set it on each (one bit per device ordinal)
+static bool dev_done(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return true;
+  mask |= bit;
+  return false;
+}
 static void prefer_max_smem(const void* kernel) {
-  static std::vector<const void*> done;
+  static std::vector<std::pair<const void*, int>> done;   // (kernel, device)
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("SD_CARVEOUT");
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
   if (!enabled) return;
-  for (const void* k : done) if (k == kernel) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (const auto& k : done) if (k.first == kernel && k.second == dev) return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-  done.push_back(kernel);
+  done.push_back({kernel, dev});
 }
 
 // fp32 skinny GEMM launch: K is split over a thread-block cluster along grid.y (see gemm_f32_kernel).
 static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n, int max_k, int R, bool gates = false) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
+  if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
-    attr_done = true;
   }
   int ksplit = 1;
   while (ksplit < sd::GB_MAXSPLIT && (max_k + ksplit - 1) / ksplit > sd::GB_KC) ksplit *= 2;
@@ -375,10 +385,9 @@ static bool tc_split_enabled() { static int v = env_flag("SD_TC_SPLIT", 1); retu
 template <int BN, int NST>
 static void launch_tc(Ctx& cx, const sd::tc::Batch& b, int ntiles_n, int R) {
   using L = sd::tc::SmemLayout<BN, NST>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
+  if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<BN, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    attr_done = true;
   }
   dim3 grid(ntiles_n, (R + sd::tc::BM - 1) / sd::tc::BM, b.count * b.ksplit);
   static long long* timing_dev = nullptr;
@@ -596,10 +605,9 @@ static bool linear_norm_tc(Ctx& cx, int R, const LinearW& L, Operand a, const St
   tb.count = 1; tb.R = R; tb.ksplit = 1;
   using LN = sd::tc::SmemLayout<64, 4>;
   auto kern = sd::tc::gemm_bf16_tc_kernel<64, 4, sd::tc::EPI_NORM>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
+  if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LN::kTotal);
-    attr_done = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -641,10 +649,9 @@ static bool linear_norm_tc_wide(Ctx& cx, int R, const LinearW& L, Operand a, con
   tb.count = 1; tb.R = R; tb.ksplit = 1;
   using LW = sd::tc::SmemLayout<256, 4>;
   auto kern = sd::tc::gemm_bf16_tc_kernel<256, 4, sd::tc::EPI_NORMW>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
+  if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LW::kTotal);
-    attr_done = true;
   }
   launch_k(cx.st, kern, dim3(1, (R + 127) / 128, 1), dim3(sd::tc::THREADS), (size_t)LW::kTotal, tb);
   cx.check("tc<256,4,normw>");
@@ -660,10 +667,9 @@ static bool wide_in_enabled() { static int v = env_flag("SD_WIDE_IN", 1); return
 
 static void launch_chain(Ctx& cx, const sd::chain::Params& P, int side_ctas, const char* what) {
   if (cx.err) return;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
+  if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(sd::chain::mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::chain::kSmemBytes);
-    attr_done = true;
   }
   static long long* timing_dev = nullptr;
   static int timing_budget = 12;
@@ -1465,10 +1471,9 @@ static void deter_core(Ctx& cx, const StepBufs& sb, int R, Operand z, Operand d,
     tb.count = c.G; tb.R = R; tb.ksplit = 1; tb.part_stride = 0; tb.timing = nullptr;
     // 2 stages (80 KB): two CTAs per SM, so the 256 tiles of the base config run as one wave; K = Dg is short
     using LG = sd::tc::SmemLayout<192, 2>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
+    if (!dev_done(attr_done)) {
       cudaFuncSetAttribute(sd::tc::gemm_bf16_tc_kernel<192, 2, sd::tc::EPI_GATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, LG::kTotal);
-      attr_done = true;
     }
     launch_k(cx.st, sd::tc::gemm_bf16_tc_kernel<192, 2, sd::tc::EPI_GATES>, dim3(Dg / 64, (R + 127) / 128, c.G),
              dim3(sd::tc::THREADS), LG::kTotal, tb);
@@ -1571,9 +1576,36 @@ static int check_rows(sd_handle* h, const char* fn, long long rows, long long st
 // ------------------------------------------------------------------------------------------------ persistent posterior scan
 static bool pscan_enabled() { static int v = env_flag("SD_PSCAN", 1); return v != 0; }
 // The persistent kernel covers the base architecture at small batch (rssm.py:140-178 with base.yaml sizes).
+// The persistent posterior scan spins on a grid barrier: all its CTAs (32 clusters of 4, one CTA per SM) must be able to
+// be resident at the same time on this device.  Checked once per device with the occupancy API; a device (or an SM
+// partition) that cannot hold them gets the layer-by-layer launch sequence instead.
+static bool pscan_coresident() {
+  static int state[64];   // per device ordinal: 0 = unknown, 1 = ok, -1 = no
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& st = state[dev & 63];
+  if (st == 0) {
+    cudaFuncSetAttribute(sd::scan::observe_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::scan::kSmemBytes);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(sd::scan::NCTA); cfg.blockDim = dim3(sd::scan::THREADS); cfg.dynamicSmemBytes = sd::scan::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = sd::scan::CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, sd::scan::observe_scan_kernel, &cfg);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    st = (e == cudaSuccess && ncl * sd::scan::CLUSTER >= sd::scan::NCTA) ? 1 : -1;
+    if (st < 0)
+      fprintf(stderr, "[safedreamer] persistent posterior scan disabled on device %d: %d co-resident clusters of %d, %d CTAs needed\n",
+              dev, ncl, sd::scan::CLUSTER, sd::scan::NCTA);
+  }
+  return st > 0;
+}
 static bool pscan_ok(const sd_handle& h, int B, int T) {
   const sd_config& c = h.c;
-  return pscan_enabled() && B >= 1 && B <= 16 && T >= 1 && c.U == sd::scan::HW && h.Dg == sd::scan::HW && c.G == 8 &&
+  return pscan_enabled() && pscan_coresident() && B >= 1 && B <= 16 && T >= 1 && c.U == sd::scan::HW && h.Dg == sd::scan::HW && c.G == 8 &&
          c.D == 4 * sd::scan::KC && (h.SK % 16) == 0 && h.SK <= 512 && (16 % c.K) == 0 && c.K >= 2 && c.obs_layers == 1 &&
          c.A <= 32 && (c.E % 4) == 0 && T <= c.max_steps;
 }
@@ -1628,10 +1660,9 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   P.lg = base.lg; P.vobs = base.vobs[0]; P.o = base.o[0];
   P.step = tape ? 1 : 0;
   P.ssq_h = h.ps_ssq; P.idx = h.ps_idx; P.bar = h.ps_bar;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
+  if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(sd::scan::observe_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::scan::kSmemBytes);
-    attr_done = true;
   }
   // no PDL attribute: all 128 CTAs must become resident together (they spin on a grid barrier)
   static long long* timing_dev = nullptr;

@@ -270,6 +270,8 @@ class RSSM(nn.Module):
         self.cache_params = False      # True = Parameter OBJECTS never change (in-place optimizers): skip the module-tree
         #                                walk (named_parameters) on every call
         self.noise_source = None       # callable(shape, device) -> uniforms, for injected-noise parity
+        self.use_custom_ops = False    # True: route through the torch.library operators of safe_dreamer_b200.ops (traceable
+        #                                by torch.compile / capturable in CUDA graphs) instead of autograd.Function
         self.max_rows, self.max_steps = 1024, 64
         self.head_modules = {}         # module id -> nn.Module (actor / reward / cont / value / slow value)
         self._rt = _Runtime()
@@ -362,6 +364,11 @@ class RSSM(nn.Module):
         needs_grad = torch.is_grad_enabled() and (
             embed.requires_grad or stoch.requires_grad or deter.requires_grad
             or any(p.requires_grad for p in self._params()))
+        if self.use_custom_ops:
+            from . import ops
+            return torch.ops.safedreamer.observe(embed.float(), action.float(), stoch.float(), deter.float(),
+                                                 reset.reshape(B, T).to(torch.uint8), u, self._params(), ops.module_key(self),
+                                                 bool(needs_grad))
         if needs_grad:
             return _ObserveFn.apply(self, embed.float(), action, stoch.float(), deter.float(), reset, u,
                                     *self._params())
@@ -387,12 +394,21 @@ class RSSM(nn.Module):
         if rows > eng.cfg.max_rows * eng.cfg.max_steps:
             eng = self._get_engine(self.max_rows, -(-rows // self.max_rows))
         u = self._uniform(*lead, self._stoch, self._discrete)
-        if torch.is_grad_enabled() and (deter.requires_grad or any(p.requires_grad for p in self.parameters())):
+        needs_grad = torch.is_grad_enabled() and (deter.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.use_custom_ops:
+            from . import ops
+            return torch.ops.safedreamer.prior(deter.float(), u, list(self.parameters()), ops.module_key(self), bool(needs_grad))
+        if needs_grad:
             return _PriorFn.apply(self, deter.float(), u, *self.parameters())
         return eng.prior(deter, u, flags=self._flags())
 
     def imagine_with_action(self, stoch, deter, actions):
-        """rssm.py:197-209."""
+        """rssm.py:197-209.  Forward only: the differentiable rollout is `dreamer_ops.imagine_grad` (the attack shape); asking
+        this entry for gradients fails loudly instead of silently returning constants."""
+        if torch.is_grad_enabled() and (stoch.requires_grad or deter.requires_grad or actions.requires_grad):
+            raise RuntimeError("RSSM.img_step / imagine_with_action are forward-only in this build: gradients w.r.t. the state or "
+                               "the actions are not propagated.  Use safe_dreamer_b200.dreamer_ops.imagine_grad for the "
+                               "differentiable rollout, or call under torch.no_grad() / detach the inputs.")
         R, T = actions.shape[:2]
         eng = self._get_engine(R, T)
         u = self._uniform(R, T, self._stoch, self._discrete)
@@ -412,6 +428,9 @@ class RSSM(nn.Module):
         """rssm.py:222-230 -> (dyn_loss, rep_loss).  CUDA tensors go through sd_kl_loss / sd_kl_loss_bwd (values and the
         gradients of the reference's detach pattern); anything else through the torch restatement."""
         if post_logit.is_cuda and prior_logit.is_cuda:
+            if self.use_custom_ops:
+                from . import ops
+                return torch.ops.safedreamer.kl_loss(post_logit.float(), prior_logit.float(), float(free), ops.module_key(self))
             return _KLFn.apply(self, post_logit.float(), prior_logit.float(), float(free))
         from .distributions import kl
         rep_loss = kl(post_logit, prior_logit.detach()).sum(-1)
