@@ -94,10 +94,11 @@ class _FusedHeads:
         if o is not None and value is o["value"] and boot is o["value"] and reward is o["reward"]:
             return o["ret"]
         fr = a._frozen_rssm
-        if getattr(fr, "use_custom_ops", False):
-            return torch.ops.safedreamer.lambda_return(last.float(), term.float(), reward.float(), value.float(), boot.float(),
-                                                       float(disc), float(lamb), fr._ops_key)
-        return dreamer_ops.lambda_return(fr, last, term, reward, value, boot, disc, lamb)
+        with torch.no_grad():       # the reference's _lambda_return is @torch.no_grad() (dreamer.py:694)
+            args = [x.detach().float() for x in (last, term, reward, value, boot)]
+            if getattr(fr, "use_custom_ops", False):
+                return torch.ops.safedreamer.lambda_return(*args, float(disc), float(lamb), fr._ops_key)
+            return dreamer_ops.lambda_return(fr, *args, disc, lamb)
 
 
 _FROZEN = ("reward", "cont", "value", "slow_value")

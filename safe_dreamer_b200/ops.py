@@ -99,21 +99,21 @@ def observe_bwd(d_stochs: Tensor, d_deters: Tensor, d_logits: Tensor, params: Li
         d_embed, d_is, d_id = eng.observe_bwd(B, T, d_stochs, d_deters, d_logits, need_embed, need_init, wg, rssm._flags())
     finally:
         eng.static_outputs = so
-    empty = torch.empty(0, device=dev)
+    empty = lambda: torch.empty(0, device=dev)      # (every returned tensor must be its own object: no aliasing between outputs)
     assert set(names) == set(pnames)
-    return (d_embed if d_embed is not None else empty, d_is if d_is is not None else empty,
-            d_id if d_id is not None else empty, [wg[n] for n in pnames] if need_w else [empty for _ in pnames])
+    return (d_embed if d_embed is not None else empty(), d_is if d_is is not None else empty(),
+            d_id if d_id is not None else empty(), [wg[n] for n in pnames] if need_w else [empty() for _ in pnames])
 
 
 @observe_bwd.register_fake
 def _(d_stochs, d_deters, d_logits, params, mod, need_embed, need_init, need_w):
     rssm = _mod(mod)
     B, T = d_deters.shape[0], d_deters.shape[1]
-    e = d_deters.new_empty(0)
-    return (d_deters.new_empty(B, T, rssm._embed_size) if need_embed else e,
-            d_deters.new_empty(B, rssm._stoch, rssm._discrete) if need_init else e,
-            d_deters.new_empty(B, rssm._deter) if need_init else e,
-            [torch.empty_like(p, dtype=torch.float32) if need_w else e for p in params])
+    e = lambda: d_deters.new_empty(0)
+    return (d_deters.new_empty(B, T, rssm._embed_size) if need_embed else e(),
+            d_deters.new_empty(B, rssm._stoch, rssm._discrete) if need_init else e(),
+            d_deters.new_empty(B, rssm._deter) if need_init else e(),
+            [torch.empty_like(p, dtype=torch.float32) if need_w else e() for p in params])
 
 
 def _observe_setup(ctx, inputs, output):
@@ -179,19 +179,19 @@ def prior_bwd(d_stoch: Tensor, d_logit: Tensor, params: List[Tensor], mod: int, 
         d_deter = eng.prior_bwd(rows, d_stoch, d_logit, need_deter, wg, rssm._flags())
     finally:
         eng.static_outputs = so
-    empty = torch.empty(0, device=d_logit.device)
-    return (d_deter.reshape(*lead, -1) if d_deter is not None else empty,
-            [(wg[n] if (need_w and wg[n] is not None) else empty) for n in pnames])
+    empty = lambda: torch.empty(0, device=d_logit.device)
+    return (d_deter.reshape(*lead, -1).clone() if d_deter is not None else empty(),
+            [(wg[n] if (need_w and wg[n] is not None) else empty()) for n in pnames])
 
 
 @prior_bwd.register_fake
 def _(d_stoch, d_logit, params, mod, need_deter, need_w):
     rssm = _mod(mod)
     lead = d_logit.shape[:-2]
-    e = d_logit.new_empty(0)
+    e = lambda: d_logit.new_empty(0)
     names = [n for n, _ in rssm.named_parameters()]
-    return (d_logit.new_empty(*lead, rssm._deter) if need_deter else e,
-            [torch.empty_like(p, dtype=torch.float32) if (need_w and n.startswith("_img_net")) else e for n, p in zip(names, params)])
+    return (d_logit.new_empty(*lead, rssm._deter) if need_deter else e(),
+            [torch.empty_like(p, dtype=torch.float32) if (need_w and n.startswith("_img_net")) else e() for n, p in zip(names, params)])
 
 
 def _prior_setup(ctx, inputs, output):

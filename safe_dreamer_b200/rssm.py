@@ -277,6 +277,14 @@ class RSSM(nn.Module):
         self._rt = _Runtime()
 
     # ------------------------------------------------------------------ runtime plumbing
+    def _key(self):
+        """Integer the torch.library operators identify this module by (set once: operator arguments must be plain data)."""
+        k = self.__dict__.get("_ops_key")
+        if k is None:
+            from . import ops
+            k = self.__dict__["_ops_key"] = ops.module_key(self)
+        return k
+
     def _flags(self):
         f = SD_FLAG_BF16 if self.precision == "bf16" else 0
         if getattr(self, "background", False):   # calls issued beside latency-critical work on another stream
@@ -367,7 +375,7 @@ class RSSM(nn.Module):
         if self.use_custom_ops:
             from . import ops
             return torch.ops.safedreamer.observe(embed.float(), action.float(), stoch.float(), deter.float(),
-                                                 reset.reshape(B, T).to(torch.uint8), u, self._params(), ops.module_key(self),
+                                                 reset.reshape(B, T).to(torch.uint8), u, self._params(), self._key(),
                                                  bool(needs_grad))
         if needs_grad:
             return _ObserveFn.apply(self, embed.float(), action, stoch.float(), deter.float(), reset, u,
@@ -390,14 +398,13 @@ class RSSM(nn.Module):
         """rssm.py:189-195; also called batched on (B,T,D) (dreamer.py:485)."""
         lead = deter.shape[:-1]
         rows = int(math.prod(lead))
+        u = self._uniform(*lead, self._stoch, self._discrete)
+        needs_grad = torch.is_grad_enabled() and (deter.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.use_custom_ops:     # (the operator fetches the engine itself: nothing here may touch ctypes under tracing)
+            return torch.ops.safedreamer.prior(deter.float(), u, list(self.parameters()), self._key(), bool(needs_grad))
         eng = self._get_engine(min(rows, self.max_rows), 1)
         if rows > eng.cfg.max_rows * eng.cfg.max_steps:
             eng = self._get_engine(self.max_rows, -(-rows // self.max_rows))
-        u = self._uniform(*lead, self._stoch, self._discrete)
-        needs_grad = torch.is_grad_enabled() and (deter.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if self.use_custom_ops:
-            from . import ops
-            return torch.ops.safedreamer.prior(deter.float(), u, list(self.parameters()), ops.module_key(self), bool(needs_grad))
         if needs_grad:
             return _PriorFn.apply(self, deter.float(), u, *self.parameters())
         return eng.prior(deter, u, flags=self._flags())
@@ -430,7 +437,7 @@ class RSSM(nn.Module):
         if post_logit.is_cuda and prior_logit.is_cuda:
             if self.use_custom_ops:
                 from . import ops
-                return torch.ops.safedreamer.kl_loss(post_logit.float(), prior_logit.float(), float(free), ops.module_key(self))
+                return torch.ops.safedreamer.kl_loss(post_logit.float(), prior_logit.float(), float(free), self._key())
             return _KLFn.apply(self, post_logit.float(), prior_logit.float(), float(free))
         from .distributions import kl
         rep_loss = kl(post_logit, prior_logit.detach()).sum(-1)
