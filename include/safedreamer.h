@@ -168,6 +168,13 @@ int sd_imagine_bwd(sd_handle* h, int N, int H, const float* d_feats, const float
 int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feats, float disc, float lamb,
                         float* reward, float* cont, float* value, float* slow_value, float* weight,
                         float* ret, uint32_t flags, void* stream);
+/* Backward of sd_heads_lambda_fwd w.r.t. feats with frozen head weights (the adversarial-patch attack's
+ * d(imagined return)/d(feats), README.md:68-116; dreamer.py:589-602 with _lambda_return differentiated).
+ *   in : feats (N,H,F); d_ret (N,H-1,1) and optional direct cotangents d_reward / d_cont / d_value (N,H,1), each nullable
+ *   out: d_feats (N,H,F).  Needs a handle created with max_tape_rows >= N.  H <= 64. */
+int sd_heads_lambda_bwd(sd_handle* h, int N, int H, const float* feats, float disc, float lamb, const float* d_ret,
+                        const float* d_reward, const float* d_cont, const float* d_value, float* d_feats,
+                        uint32_t flags, void* stream);
 /* Dreamer._lambda_return (dreamer.py:694-707) on (N,T,1) inputs -> out (N,T-1,1). */
 int sd_lambda_return(int N, int T, const float* last, const float* term, const float* reward,
                      const float* value, const float* boot, float disc, float lamb, float* out,

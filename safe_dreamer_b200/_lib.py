@@ -97,6 +97,7 @@ _SIGS = {
     "sd_imagine_fwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 6 + [C.c_uint32, _P]),
     "sd_imagine_bwd": (C.c_int, [_P, C.c_int, C.c_int] + [_P] * 4 + [C.c_uint32, _P]),
     "sd_heads_lambda_fwd": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_float, C.c_float] + [_P] * 6 + [C.c_uint32, _P]),
+    "sd_heads_lambda_bwd": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_float, C.c_float] + [_P] * 5 + [C.c_uint32, _P]),
     "sd_lambda_return": (C.c_int, [C.c_int, C.c_int] + [_P] * 5 + [C.c_float, C.c_float, _P, _P]),
     "sd_kl_loss": (C.c_int, [_P, C.c_int, _P, _P, C.c_float] + [_P] * 4 + [_P]),
     "sd_kl_loss_bwd": (C.c_int, [_P, C.c_int, _P, _P, C.c_float] + [_P] * 4 + [_P]),

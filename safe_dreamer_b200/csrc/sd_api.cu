@@ -138,6 +138,11 @@ struct sd_handle {
   float *scratch_stoch, *scratch_deter, *abar, *abar0;
   // heads workspace
   float *hv, *ho, *hl, *h_rew, *h_cont, *h_val, *kl_a, *kl_b, *kl_c;
+  // backward of the imagined head evaluation (sd_heads_lambda_bwd; allocated with the tape): per-layer pre-norm values,
+  // gradient temporaries over N*H rows
+  float* hb_v[4] = {nullptr, nullptr, nullptr, nullptr};
+  float *hb_do = nullptr, *hb_dv = nullptr, *hb_dfeat = nullptr, *hb_dr = nullptr, *hb_dc = nullptr, *hb_dval = nullptr;
+  bf16* hb_dv_bf = nullptr;
   std::vector<GraphEntry> graphs;
   float* part = nullptr;               // split-K partial slices of the tcgen05 GEMMs (kMaxParts x part_stride)
   size_t part_stride = 0;
@@ -990,6 +995,15 @@ static void layout(sd_handle& h, Arena& a) {
   h.h_rew = a.take<float>(NH);
   h.h_cont = a.take<float>(NH);
   h.h_val = a.take<float>(NH);
+  if (c.max_tape_rows > 0) {
+    const size_t NHt = (size_t)c.max_tape_rows * T;     // rows of a grad-enabled rollout (attack shape)
+    for (int i = 0; i < 4; ++i) h.hb_v[i] = a.take<float>(NHt * c.units);
+    h.hb_do = a.take<float>(NHt * c.units);
+    h.hb_dv = a.take<float>(NHt * c.units);
+    h.hb_dv_bf = a.take<bf16>(NHt * c.units);
+    h.hb_dfeat = a.take<float>(NHt * F);
+    h.hb_dr = a.take<float>(NHt); h.hb_dc = a.take<float>(NHt); h.hb_dval = a.take<float>(NHt);
+  }
   h.kl_a = a.take<float>(NH * c.S);
   h.kl_b = a.take<float>(NH * c.S);
   h.kl_c = a.take<float>(NH * c.S);
@@ -1823,7 +1837,7 @@ extern "C" int sd_imagine_with_action(sd_handle* h, int R, int T, const float* s
 // ------------------------------------------------------------------------------------------------ imagine
 // MLPHead trunk + last layer on `R` rows of feat (networks.py:339-377); returns last-layer output in `out`.
 static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, float* const* v, float* const* o,
-                         bf16* const* o_bf, float* out, int ld_out) {
+                         bf16* const* o_bf, float* out, int ld_out, bool keep_prenorm = false) {
   sd_handle& h = *cx.h;
   const int units = h.c.units;
   Operand cur = feat;
@@ -1831,7 +1845,7 @@ static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, f
   for (int i = 0; i < hw.layers; ++i) {
     // (in-place bf16 input/output is safe for the fused kernel: tiles of different clusters touch different
     //  rows, and inside a cluster every store happens after the cluster barrier that follows all MMAs)
-    if (k == hw.l[i].K && (linear_norm_tc(cx, R, hw.l[i], cur, h.sb, o[i], units, o_bf[i], units) ||
+    if (!keep_prenorm && k == hw.l[i].K && (linear_norm_tc(cx, R, hw.l[i], cur, h.sb, o[i], units, o_bf[i], units) ||
                            linear_norm_tc_wide(cx, R, hw.l[i], cur, h.sb,
                                                (i == hw.layers - 1 && hw.last.N < 64) ? o[i] : nullptr,   // fp32 only when the
                                                units, o_bf[i], units))) {                                 // last layer is SIMT
@@ -2706,6 +2720,89 @@ extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feat
     if (weight || ret) {
       launch_k(cx.st, sd::imag_weight_ret_kernel, dim3((N + 127) / 128), dim3(128), 0, N, H, rw, ct, vl, disc, lamb, weight, ret);
       cx.check("imag_weight_ret_kernel");
+    }
+  });
+}
+
+// Backward of sd_heads_lambda_fwd with respect to feats (frozen head weights): the attack's d(imagined return)/d(feats).
+// dreamer.py:589-602 with `_lambda_return` differentiated (README.md:68-116).  The scalars are recomputed with the fused
+// forward; then each of reward / cont / value re-runs its trunk keeping the pre-norm values and back-propagates
+// d(mode) / d(mean) through TwoHot.mode / sigmoid and the MLP (dgrad only) into d_feats.
+extern "C" int sd_heads_lambda_bwd(sd_handle* h, int N, int H, const float* feats, float disc, float lamb, const float* d_ret,
+                                   const float* d_reward, const float* d_cont, const float* d_value, float* d_feats,
+                                   uint32_t flags, void* stream) {
+  if (int e = check_rows(h, "sd_heads_lambda_bwd", N, H)) return e;
+  if (!feats || !d_feats) return fail(SD_ERR_INVALID, "sd_heads_lambda_bwd: null tensor");
+  if (!h->hb_dfeat || N > h->c.max_tape_rows)
+    return fail(SD_ERR_WORKSPACE, "sd_heads_lambda_bwd: N=%d > max_tape_rows=%d (create the handle with a tape)", N, h->c.max_tape_rows);
+  if (H > 64) return fail(SD_ERR_INVALID, "sd_heads_lambda_bwd: H=%d > 64", H);
+  for (int m : {SD_MOD_REWARD, SD_MOD_CONT, SD_MOD_VALUE})
+    if (!h->heads[m].set) return fail(SD_ERR_WEIGHTS, "sd_heads_lambda_bwd: head %d weights not set", m);
+  const sd_config& c = h->c;
+  const int F = h->F;
+  const long long NH = (long long)N * H;
+  const bool tc = (flags & SD_FLAG_BF16) && NH >= 128;
+  if (tc) h->bigbf_feats = nullptr;   // the cast below overwrites big_bf
+  Key key;
+  key.add(15).add(N).add(H).add(feats).add(disc).add(lamb).add(d_ret).add(d_reward).add(d_cont).add(d_value).add(d_feats).add(flags);
+  return run(h, key.v, flags, (cudaStream_t)stream, tc, [&](Ctx& cx) {
+    const int R = (int)NH;
+    const int units = c.units;
+    if (cx.tc) cast_bf(cx, feats, F, h->big_bf, F, R, F);
+    Operand feat = opfb(feats, F, cx.tc ? h->big_bf : nullptr, F);
+    bf16* ob[4];
+    float* o[4];
+    for (int i = 0; i < 4; ++i) { ob[i] = h->trunk_bf; o[i] = h->ho; }
+    const int ldl = up(c.bins, 4);
+    auto fwd_head = [&](int m, float* scalar) {     // taped forward of one head: pre-norm values stay in hb_v[layer]
+      const HeadW& hw = h->heads[m];
+      head_forward(cx, R, hw, feat, F, h->hb_v, o, ob, h->hl, up(hw.out, 4), true);
+      if (cx.err) return;
+      if (m == SD_MOD_CONT) {
+        launch_k(cx.st, sd::sigmoid_kernel, dim3((R + 255) / 256), dim3(256), 0, h->hl, up(hw.out, 4), scalar, R);
+        cx.check("sigmoid_kernel");
+      } else {
+        launch_k(cx.st, sd::twohot_mode_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, h->hl, ldl, h->bins, c.bins, R, scalar);
+        cx.check("twohot_mode_kernel");
+      }
+    };
+    // 1. scalars of all three heads (the lambda-return needs them together)
+    fwd_head(SD_MOD_REWARD, h->h_rew);
+    fwd_head(SD_MOD_CONT, h->h_cont);
+    fwd_head(SD_MOD_VALUE, h->h_val);   // (the value head's pre-norm values are still in hb_v: it goes first below)
+    if (cx.err) return;
+    // 2. d(ret) -> d(reward), d(cont), d(value)
+    launch_k(cx.st, sd::lambda_return_bwd_kernel, dim3((N + 127) / 128), dim3(128), 0, N, H, (const float*)h->h_rew, (const float*)h->h_cont,
+             (const float*)h->h_val, disc, lamb, d_ret, d_reward, d_cont, d_value, h->hb_dr, h->hb_dc, h->hb_dval);
+    cx.check("lambda_return_bwd_kernel");
+    // 3. per head: d(scalar) -> d(last-layer output) in place over the logits -> MLP dgrad -> d_feats (+)=
+    StepBufs sbh;
+    memset(&sbh, 0, sizeof(sbh));
+    for (int i = 0; i < 4; ++i) sbh.va[i] = h->hb_v[i];
+    BwdBufs bwh;
+    memset(&bwh, 0, sizeof(bwh));
+    bwh.t_do = h->hb_do; bwh.d_v[0] = h->hb_dv; bwh.d_v_bf = h->hb_dv_bf;
+    const int order[3] = {SD_MOD_VALUE, SD_MOD_REWARD, SD_MOD_CONT};
+    for (int k = 0; k < 3 && !cx.err; ++k) {
+      const int m = order[k];
+      const HeadW& hw = h->heads[m];
+      float* scalar = m == SD_MOD_REWARD ? h->h_rew : m == SD_MOD_CONT ? h->h_cont : h->h_val;
+      const float* dsc = m == SD_MOD_REWARD ? h->hb_dr : m == SD_MOD_CONT ? h->hb_dc : h->hb_dval;
+      if (k > 0) fwd_head(m, scalar);      // recompute this head's activations (the trunk buffers are shared)
+      if (cx.err) return;
+      if (m == SD_MOD_CONT) {
+        launch_k(cx.st, sd::sigmoid_bwd_kernel, dim3((R + 255) / 256), dim3(256), 0, h->hl, up(hw.out, 4), (const float*)scalar, dsc, R);
+        cx.check("sigmoid_bwd_kernel");
+      } else {
+        launch_k(cx.st, sd::twohot_mode_bwd_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, h->hl, ldl, (const float*)h->bins, c.bins, R,
+                 (const float*)scalar, dsc);
+        cx.check("twohot_mode_bwd_kernel");
+      }
+      head_bwd(cx, sbh, bwh, R, hw, h->hl, up(hw.out, 4), h->hb_dfeat, F);
+      if (cx.err) return;
+      const long long n4 = (long long)R * F / 4;
+      launch_k(cx.st, sd::accum_kernel, dim3(grid1d(n4, 256)), dim3(256), 0, (const float4*)h->hb_dfeat, (float4*)d_feats, n4, k == 0 ? 1 : 0);
+      cx.check("accum_kernel");
     }
   });
 }

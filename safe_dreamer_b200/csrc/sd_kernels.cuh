@@ -1373,6 +1373,74 @@ __global__ void twohot_logprob_bwd_kernel(const float* __restrict__ logits, int 
 }
 
 // cont head mean = sigmoid(logit) (distributions.py:238-239, Bernoulli.mean).
+// ---- backward of the imagined head evaluation (attack shape: d(lambda-return) / d(feats), frozen weights)
+// TwoHot.mode = sum_j softmax(l)_j * bins_j (distributions.py:78-98): d l_j = p_j (bins_j - mode) d_mode.  In place over the
+// logits (row stride ld); one warp per row.
+__global__ void twohot_mode_bwd_kernel(float* __restrict__ logits, int ld, const float* __restrict__ bins, int n, int R,
+                                       const float* __restrict__ mode, const float* __restrict__ d_mode) {
+  pdl_prologue();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  float* lp = logits + (size_t)warp * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < n; j += 32) m = fmaxf(m, lp[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s += expf(lp[j] - m);
+  s = warp_sum(s);
+  const float mo = mode[warp], g = d_mode[warp];
+  for (int j = lane; j < n; j += 32) lp[j] = (expf(lp[j] - m) / s) * (bins[j] - mo) * g;
+}
+// Bernoulli mean = sigmoid(l): d l = c (1 - c) d_c; writes the gradient over the logit (column 0 of a row of stride ld).
+__global__ void sigmoid_bwd_kernel(float* __restrict__ logit, int ld, const float* __restrict__ c, const float* __restrict__ d_c, int n) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) logit[(size_t)i * ld] = c[i] * (1.f - c[i]) * d_c[i];
+}
+// Reverse of imag_weight_ret_kernel's recursion (dreamer.py:694-707 made differentiable: the attack's objective):
+//   ret_i = r_{i+1} + live_{i+1} ((1 - lamb) v_{i+1} + lamb ret_{i+1}),  live = c * disc,  ret_{H-1} := v_{H-1}
+// a_i = total gradient reaching ret_i.  Optional direct cotangents of reward / cont / value are added.
+__global__ void lambda_return_bwd_kernel(int N, int H, const float* __restrict__ reward, const float* __restrict__ cont,
+                                         const float* __restrict__ value, float disc, float lamb, const float* __restrict__ d_ret,
+                                         const float* __restrict__ g_reward, const float* __restrict__ g_cont,
+                                         const float* __restrict__ g_value, float* d_reward, float* d_cont, float* d_value) {
+  pdl_prologue();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t o = (size_t)n * H;
+  // forward values of ret (needed by d_cont), recomputed: ret_{i+1} for i = H-2 .. 0
+  float retv[64];
+  retv[H - 1] = value[o + H - 1];
+  for (int i = H - 2; i >= 0; --i) {
+    const float live = cont[o + i + 1] * disc;
+    retv[i] = reward[o + i + 1] + live * ((1.f - lamb) * value[o + i + 1] + lamb * retv[i + 1]);
+  }
+  d_reward[o] = g_reward ? g_reward[o] : 0.f;
+  d_cont[o] = g_cont ? g_cont[o] : 0.f;
+  d_value[o] = g_value ? g_value[o] : 0.f;
+  float a = 0.f;
+  for (int i = 0; i <= H - 2; ++i) {
+    a = (d_ret ? d_ret[(size_t)n * (H - 1) + i] : 0.f) + a;    // a_i = g_i + carried
+    const float c = cont[o + i + 1], v = value[o + i + 1];
+    const float dr = a, dc = a * disc * ((1.f - lamb) * v + lamb * retv[i + 1]);
+    float dv = a * c * disc * (1.f - lamb);
+    const float carry = a * c * disc * lamb;                   // into ret_{i+1}
+    if (i + 1 == H - 1) dv += carry;                           // ret_{H-1} is value_{H-1}
+    d_reward[o + i + 1] = dr + (g_reward ? g_reward[o + i + 1] : 0.f);
+    d_cont[o + i + 1] = dc + (g_cont ? g_cont[o + i + 1] : 0.f);
+    d_value[o + i + 1] = dv + (g_value ? g_value[o + i + 1] : 0.f);
+    a = carry;
+  }
+}
+// out (+)= in, contiguous
+__global__ void accum_kernel(const float4* __restrict__ in, float4* out, long long n4, int first) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = in[i];
+    if (!first) { const float4 b = out[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+    out[i] = a;
+  }
+}
 __global__ void sigmoid_kernel(const float* __restrict__ in, int ld, float* out, int n) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

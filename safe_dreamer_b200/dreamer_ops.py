@@ -68,6 +68,72 @@ def heads_lambda(rssm, imag_feat, horizon=333, lamb=0.95, slow=True):
     return eng.heads_lambda(imag_feat, 1 - 1 / horizon, lamb, flags=rssm._flags(), slow=slow)
 
 
+class _ImagineFn(torch.autograd.Function):
+    """Grad-enabled rollout: sd_imagine_fwd with a tape / sd_imagine_bwd (dgrad only: frozen weights)."""
+
+    @staticmethod
+    def forward(ctx, rssm, stoch, deter, u, act_noise, H):
+        N = deter.shape[0]
+        eng = rssm._get_engine(N, H, tape=True, tape_rows=N)
+        from .engine import SD_FLAG_SAVE_TAPE
+        feats, actions = eng.imagine(stoch, deter, u, act_noise, H, flags=rssm._flags() | SD_FLAG_SAVE_TAPE)
+        ctx.rssm, ctx.eng, ctx.gen, ctx.N, ctx.H = rssm, eng, eng.tape_gen["scan"], N, H
+        ctx.flags = rssm._flags()
+        return feats.clone(), actions.clone()
+
+    @staticmethod
+    def backward(ctx, d_feats, d_actions):
+        eng = ctx.rssm._rt.engine
+        if eng is not ctx.eng:
+            raise RuntimeError("imagine_grad backward: the engine holding this rollout's tape was rebuilt; raise rssm.max_rows / "
+                               "max_steps before the forward")
+        eng.check_tape("scan", ctx.gen, "imagine_grad backward")
+        d_s, d_d = eng.imagine_bwd(ctx.N, ctx.H, d_feats.contiguous(), d_actions.contiguous(), flags=ctx.flags)
+        return None, d_s, d_d, None, None, None
+
+
+def imagine_grad(rssm, start, imag_horizon, act_noise=None, u=None):
+    """Differentiable Dreamer._imagine (the adversarial-patch attack shape, README.md:68-116): gradients flow from
+    feats / actions back to the start state through the frozen actor and img_step (straight-through samples)."""
+    stoch, deter = start
+    N = deter.shape[0]
+    dev = deter.device
+    if u is None:
+        u = rssm._uniform(N, imag_horizon, rssm._stoch, rssm._discrete)
+    if act_noise is None:
+        eng = rssm._get_engine(N, imag_horizon, tape=True, tape_rows=N)
+        shape = (N, imag_horizon, rssm._act_dim)
+        act_noise = torch.randn(*shape, device=dev) if eng.cfg.act_kind == 0 else torch.rand(*shape, device=dev).clamp_(_U_LO, 1 - _U_LO)
+    return _ImagineFn.apply(rssm, stoch.float(), deter.float(), u, act_noise, int(imag_horizon))
+
+
+class _HeadsLambdaFn(torch.autograd.Function):
+    """Differentiable heads + lambda-return on imagined feats: sd_heads_lambda_fwd / sd_heads_lambda_bwd."""
+
+    @staticmethod
+    def forward(ctx, rssm, feats, horizon, lamb):
+        N, H = feats.shape[:2]
+        eng = rssm._get_engine(N, H, tape=True, tape_rows=N)
+        disc = 1 - 1 / horizon
+        out = eng.heads_lambda(feats, disc, lamb, flags=rssm._flags())
+        ctx.save_for_backward(feats)
+        ctx.rssm, ctx.disc, ctx.lamb, ctx.flags = rssm, disc, lamb, rssm._flags()
+        ctx.mark_non_differentiable(out[3], out[4])     # slow value and the cumprod weights carry no gradient here
+        return tuple(o.clone() for o in out)
+
+    @staticmethod
+    def backward(ctx, d_rew, d_cont, d_val, d_sval, d_wgt, d_ret):
+        (feats,) = ctx.saved_tensors
+        eng = ctx.rssm._rt.engine
+        d_feats = eng.heads_lambda_bwd(feats, ctx.disc, ctx.lamb, d_ret, d_rew, d_cont, d_val, flags=ctx.flags)
+        return None, d_feats, None, None
+
+
+def heads_lambda_grad(rssm, imag_feat, horizon=333, lamb=0.95):
+    """heads_lambda with gradients w.r.t. imag_feat (frozen heads; the lambda-return recursion differentiated)."""
+    return _HeadsLambdaFn.apply(rssm, imag_feat.float(), horizon, lamb)
+
+
 @torch.no_grad()
 def lambda_return(rssm, last, term, reward, value, boot, disc, lamb):
     eng = rssm._get_engine(1, 1)

@@ -295,6 +295,19 @@ class Engine:
                                                 self.stream), "sd_heads_lambda_fwd")
         return rew, cont, val, sval, wgt, ret
 
+    def heads_lambda_bwd(self, feats, disc, lamb, d_ret=None, d_reward=None, d_cont=None, d_value=None, flags=0):
+        """d(feats) of heads_lambda for cotangents of ret (N,H-1,1) and optionally reward / cont / value (N,H,1)."""
+        N, H = feats.shape[:2]
+        feats = _f32c(feats, "feats")
+        gs = [None if g is None else _f32c(g, "cotangent") for g in (d_ret, d_reward, d_cont, d_value)]
+        d_feats = torch.empty_like(feats)
+        if flags & SD_FLAG_BF16:
+            self._imag_feats = None
+        _lib.check(self.lib.sd_heads_lambda_bwd(self.h, N, H, _ptr(feats), float(disc), float(lamb), _ptr(gs[0]), _ptr(gs[1]),
+                                                _ptr(gs[2]), _ptr(gs[3]), _ptr(d_feats), flags, self.stream),
+                   "sd_heads_lambda_bwd")
+        return d_feats
+
     def lambda_return(self, last, term, reward, value, boot, disc, lamb):
         N, T = reward.shape[:2]
         last, term, reward, value, boot = (_f32c(x, "lambda_return input") for x in (last, term, reward, value, boot))

@@ -480,8 +480,58 @@ def run_return_ema(networks):
     print("return_ema ->", path)
 
 
+def run_attack(tag, c, N, H, rssm_mod, dists, networks, dreamer):
+    """The adversarial-patch attack's gradient path after the posterior (README.md:68-116): grad-enabled
+    Dreamer._imagine body -> frozen reward / cont / value heads -> Dreamer._lambda_return body (differentiated) -> a seeded
+    linear objective over ret; autograd gives d(objective)/d(feats) and d/d(start state)."""
+    torch.manual_seed(0)
+    P = O.init_params(c, seed=0)
+    R, heads = build_reference(c, P, rssm_mod, networks)
+    for p_ in list(R.parameters()) + [q for h in heads.values() for q in h.parameters()]:
+        p_.requires_grad_(False)
+    st0, dt0, ui, noise = O.synth_imagine_inputs(c, N, H, seed=3)
+    st_t, dt_t = t(st0).requires_grad_(True), t(dt0).requires_grad_(True)
+    fake = NS(_frozen_rssm=R, _frozen_actor=heads["actor"])
+    U_QUEUE[:] = []
+    EPS_QUEUE[:] = []
+    for i in range(H):
+        if c.act_kind == "cont":
+            EPS_QUEUE.append(t(noise[:, i]))
+        else:
+            U_QUEUE.append(t(noise[:, i]))
+        U_QUEUE.append(t(ui[:, i]))
+    feats, acts = dreamer.Dreamer._imagine.__wrapped__(fake, (st_t, dt_t), H)
+    assert not U_QUEUE and not EPS_QUEUE
+    feats.retain_grad()
+    rew = heads["reward"](feats).mode()
+    cont = heads["cont"](feats).mean
+    val = heads["value"](feats).mode()
+    disc = 1 - 1 / c.horizon
+    ret = dreamer.Dreamer._lambda_return.__wrapped__(None, torch.zeros_like(cont), 1 - cont, rew, val, val, disc, c.lamb)
+    g = np.random.Generator(np.random.Philox(19))
+    c_ret = g.standard_normal(tuple(ret.shape), dtype=np.float32)
+    c_rew = g.standard_normal(tuple(rew.shape), dtype=np.float32) * np.float32(0.1)
+    loss = (ret * t(c_ret)).sum() + (rew * t(c_rew)).sum()
+    loss.backward()
+    out = dict(N=N, H=H, feats=feats.detach().numpy(), ret=ret.detach().numpy(), c_ret=c_ret, c_rew=c_rew,
+               d_feats=feats.grad.numpy(), d_stoch=st_t.grad.numpy(), d_deter=dt_t.grad.numpy(), loss=np.float64(loss.item()))
+    path = os.path.join(ROOT, "tests", "golden", f"attack_{tag}.npz")
+    np.savez_compressed(path, **out)
+    print("attack", tag, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB  loss {loss.item():.6f}")
+
+
+def run_attacks(rssm_mod, dists, networks, dreamer):
+    patch_noise(dists)
+    tiny = dict(D=256, U=64, S=8, K=8, G=4, E=48, units=64)
+    run_attack("tiny_cont", O.Cfg(A=3, **tiny), 6, 5, rssm_mod, dists, networks, dreamer)
+    run_attack("base_cont", O.Cfg(), 4, 16, rssm_mod, dists, networks, dreamer)
+
+
 def main():
     rssm_mod, dists, networks, dreamer = import_reference()
+    if "--attack-only" in sys.argv:
+        run_attacks(rssm_mod, dists, networks, dreamer)
+        return
     if "--return-ema-only" in sys.argv:
         run_return_ema(networks)
         return
@@ -517,6 +567,7 @@ def main():
     run_barlow()
     run_latent_store()
     run_cnn_encoder(networks)
+    run_attacks(rssm_mod, dists, networks, dreamer)
 
 
 if __name__ == "__main__":
