@@ -529,6 +529,12 @@ def run_attacks(rssm_mod, dists, networks, dreamer):
 
 def main():
     rssm_mod, dists, networks, dreamer = import_reference()
+    if "--c1-k32-only" in sys.argv:
+        patch_noise(dists)
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        run_case("base_e256", O.Cfg(E=256), 2, 5, 4, 3, rssm_mod, dists, networks, dreamer, False)
+        run_case("base_k32", O.Cfg(K=32), 2, 4, 3, 3, rssm_mod, dists, networks, dreamer, False)
+        return
     if "--attack-only" in sys.argv:
         run_attacks(rssm_mod, dists, networks, dreamer)
         return
@@ -560,6 +566,8 @@ def main():
     run_case("tiny_onehot", O.Cfg(A=5, act_kind="onehot", **tiny), 3, 6, 5, 4, rssm_mod, dists, networks, dreamer, True)
     run_case("base_cont", O.Cfg(), 2, 5, 4, 3, rssm_mod, dists, networks, dreamer, False)
     run_case("base_onehot18", O.Cfg(A=18, act_kind="onehot"), 2, 3, 3, 3, rssm_mod, dists, networks, dreamer, False)
+    run_case("base_e256", O.Cfg(E=256), 2, 5, 4, 3, rssm_mod, dists, networks, dreamer, False)   # config C1: proprio embed size
+    run_case("base_k32", O.Cfg(K=32), 2, 4, 3, 3, rssm_mod, dists, networks, dreamer, False)     # 32 classes at base widths
     run_return_ema(networks)
     run_kl_grad(rssm_mod)
     run_twohot(dists)

@@ -13,7 +13,7 @@ from tests.helpers import (assert_indices, cu, golden_initial, golden_params, lo
                            perturbed_scores)
 
 pytestmark = pytest.mark.gpu
-CASES = ["tiny_cont", "tiny_onehot", "base_cont", "base_onehot18"]
+CASES = ["tiny_cont", "tiny_onehot", "base_cont", "base_onehot18", "base_e256", "base_k32"]
 ATOL = 5e-5
 
 
@@ -47,14 +47,17 @@ def test_observe(case):
         torch.cuda.synchronize()
         st, dt, lg = _np(st), _np(dt), _np(lg)
         assert set(np.unique(st)) <= {0.0, 1.0} and np.all(st.sum(-1) == 1.0)
-        n_mis = assert_indices(st.argmax(-1), idx_o, perturbed_scores(lg_o, u, c.unimix), 1e-4, 2e-3, f"{tag} observe")
-        if n_mis == 0:
-            np.testing.assert_allclose(dt, dt_o, atol=ATOL, rtol=0)
-            np.testing.assert_allclose(lg, lg_o, atol=ATOL * 4, rtol=0)
-            # and against the reference's own outputs
-            np.testing.assert_array_equal(st.argmax(-1).astype(np.int8), z["obs_stoch_idx"])
-            np.testing.assert_allclose(dt, z["obs_deter"], atol=ATOL, rtol=0)
-            np.testing.assert_allclose(lg, z["obs_logit"], atol=ATOL * 4, rtol=0)
+        assert_indices(st.argmax(-1), idx_o, perturbed_scores(lg_o, u, c.unimix), 1e-4, 2e-3, f"{tag} observe")
+        # a flipped near-tie sample changes the rest of THAT batch row only: every row without a flip is compared
+        # unconditionally, and (the goldens are tie-free at this tolerance) at least half of the rows must be clean
+        ok = (st.argmax(-1) == idx_o).reshape(B, -1).all(1)
+        assert ok.sum() * 2 >= B, f"{tag}: only {ok.sum()}/{B} trajectories without a flipped sample"
+        np.testing.assert_allclose(dt[ok], dt_o[ok], atol=ATOL, rtol=0)
+        np.testing.assert_allclose(lg[ok], lg_o[ok], atol=ATOL * 4, rtol=0)
+        # and against the reference's own outputs
+        np.testing.assert_array_equal(st.argmax(-1).astype(np.int8)[ok], z["obs_stoch_idx"][ok])
+        np.testing.assert_allclose(dt[ok], z["obs_deter"][ok], atol=ATOL, rtol=0)
+        np.testing.assert_allclose(lg[ok], z["obs_logit"][ok], atol=ATOL * 4, rtol=0)
 
 
 def test_obs_step_and_img_step(case):

@@ -11,7 +11,7 @@ import pytest
 from oracle import rssm_oracle as O
 from tests.helpers import golden_initial, golden_params, load_golden
 
-CASES = ["tiny_cont", "tiny_onehot", "base_cont", "base_onehot18"]
+CASES = ["tiny_cont", "tiny_onehot", "base_cont", "base_onehot18", "base_e256", "base_k32"]
 ATOL = 2e-5
 
 
