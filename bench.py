@@ -241,7 +241,9 @@ def run_gpu(args):
             bucket.wait()
         return outs[-1]
 
-    def timed(fn, iters, do_flush=True):
+    def timed(fn, iters, do_flush=True, warm=0):
+        for _ in range(warm):   # first call of a (flags, shape) key captures its CUDA graph: never inside the timed region
+            fn()
         total = 0.0
         for _ in range(iters):
             if do_flush:
@@ -288,16 +290,16 @@ def run_gpu(args):
     # dominant kernel sequence: the imagination scan alone (CUDA events on the launching stream)
     st, dt, lg = eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out)
     st, dt = st.reshape(N, c.S, c.K), dt.reshape(N, c.D)
-    ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | PERSIST, out=(feats, actions)), args.steps)
-    ms_imag_lw = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | LAYERWISE, out=(feats, actions)), args.steps)
-    ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out), args.steps)
-    ms_heads = timed(lambda: eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs), args.steps)
+    ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | PERSIST, out=(feats, actions)), args.steps, warm=2)
+    ms_imag_lw = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | LAYERWISE, out=(feats, actions)), args.steps, warm=2)
+    ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out), args.steps, warm=2)
+    ms_heads = timed(lambda: eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs), args.steps, warm=2)
     ms_obs_fb = ms_wm = None
     if have_bwd:
         def fb():
             eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH | TAPE, out=obs_out)
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
-        ms_obs_fb = timed(fb, args.steps)
+        ms_obs_fb = timed(fb, args.steps, warm=2)
         # one world-model update: observe fwd + batched prior + kl values + backward of all of them
         up = torch.rand(N, c.S, c.K, device=dev).clamp_(1e-6, 1 - 1e-6)
         gpl = torch.randn(N, c.S, c.K, device=dev) * 0.01
@@ -313,7 +315,7 @@ def run_gpu(args):
             bucket.wait()
         for _ in range(3):
             wm()
-        ms_wm = timed(wm, args.steps)
+        ms_wm = timed(wm, args.steps, warm=2)
     # ---- grad-enabled imagination (attack shape: frozen weights, dgrad-only; README.md:68-116): fwd + bwd scans
     ms_imag_fb = None
     if have_bwd and not args.no_imagine_bwd:
@@ -328,7 +330,7 @@ def run_gpu(args):
             eng2.imagine_bwd(N, H, d_feats, d_acts, flags=BF16 | GRAPH)
         for _ in range(3):
             imag_fb()
-        ms_imag_fb = timed(imag_fb, args.steps)
+        ms_imag_fb = timed(imag_fb, args.steps, warm=2)
         del eng2
     # ---- end-to-end through the public module API with HOST buffers (pinned) and a D2H result read
     from types import SimpleNamespace as NS
