@@ -256,6 +256,31 @@ int sd_agc_laprop_step(const sd_opt_tensor* tensors, int count, int mode, float 
                        float bias_correction2, float eps, float weight_decay, void* table_dev, void* scratch_dev,
                        int* found_inf, void* stream);
 
+/* ---- CNN encoder ------------------------------------------------------ */
+/* ConvEncoder (networks.py:192-234): obs - 0.5 -> `layers` x [Conv2dSamePad k=5 stride 1 (networks.py:59-86) ->
+ * MaxPool2d(2,2) -> RMSNorm2D over channels, eps 1e-4 (networks.py:89-98,212) -> SiLU] -> flatten in (C,H,W) order.
+ * Implicit-GEMM convolutions on tcgen05 (bf16 operands, fp32 accumulate) with the pool / norm / activation in the
+ * epilogue; activations between stages are bf16 NHWC and owned by the handle.
+ * Supported: kernel 5, 3 input channels, even sizes at every stage, frame width 32 / 64 / 128, depths <= 64. */
+typedef struct sd_cnn_config {
+  int32_t height, width, channels; /* frame (64, 64, 3) */
+  int32_t layers;                  /* stages (4) */
+  int32_t kernel;                  /* 5 */
+  int32_t depths[8];               /* output channels per stage: depth * mults (32, 48, 64, 64) */
+  int32_t max_frames;              /* largest B*T of a call */
+  int32_t max_tape_frames;         /* largest B*T of a SD_FLAG_SAVE_TAPE call (0 = forward only) */
+} sd_cnn_config;
+typedef struct sd_cnn sd_cnn;
+int sd_cnn_create(const sd_cnn_config* cfg, sd_cnn** out);
+int sd_cnn_destroy(sd_cnn* h);
+int64_t sd_cnn_embed_size(const sd_cnn* h);   /* depths[layers-1] * (height >> layers) * (width >> layers) */
+/* tensors: per stage (conv weight (Cout,Cin,5,5), conv bias (Cout), RMS scale (Cout)) = state_dict entries
+ * layers.{4i}.weight, layers.{4i}.bias, layers.{4i+2}.weight; fp32 device pointers, repacked to bf16 internally. */
+int sd_cnn_set_weights(sd_cnn* h, const float* const* tensors, int count, void* stream);
+/* ConvEncoder.forward: obs (frames, H, W, 3) fp32 in [0,1] -> embed (frames, sd_cnn_embed_size) fp32.
+ * SD_FLAG_SAVE_TAPE keeps the pooled pre-norm maps and arg-max positions for sd_cnn_backward (obs must stay alive). */
+int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* embed, uint32_t flags, void* stream);
+
 /* Kernels launched by this library since process start (all handles): bench.py's gpu_launches. */
 uint64_t sd_launch_count(void);
 

@@ -1,0 +1,45 @@
+"""Debug driver of the CNN encoder kernels: per-case difference against the numpy oracle (test infrastructure; python
+profiles/cnn_debug.py [time])."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from oracle import cnn_oracle as CO
+from safe_dreamer_b200.encoder import CnnEngine
+
+for tag, hw, depth, n in (("tiny", 32, 4, 2), ("base", 64, 16, 1)):
+    depths = [depth * m for m in (2, 3, 4, 4)]
+    P = CO.encoder_params(depths, 3, 5, seed=77 + hw)
+    for L in (1, 2, 3, 4):
+        eng = CnnEngine(hw, hw, 3, depths[:L], 5, max_frames=2 * n)
+        ts = []
+        for i in range(L):
+            ts += [P[f"layers.{4 * i}.weight"], P[f"layers.{4 * i}.bias"], P[f"layers.{4 * i + 2}.weight"]]
+        eng.set_weights([torch.from_numpy(t).cuda() for t in ts])
+        rng = np.random.Generator(np.random.Philox(5150 + hw))
+        obs = rng.random((n, 2, hw, hw, 3), dtype=np.float32)
+        emb = eng.forward(torch.from_numpy(obs).cuda()).cpu().numpy()
+        ref = CO.encoder_fwd(P, obs, n_layers=L)
+        d = np.abs(emb - ref)
+        print(f"{tag} layers={L}: shape {emb.shape} max|d| {d.max():.4f} mean|d| {d.mean():.5f} |ref| mean {np.abs(ref).mean():.3f} max {np.abs(ref).max():.3f}", flush=True)
+if len(sys.argv) > 1:
+    depths = [32, 48, 64, 64]
+    P = CO.encoder_params(depths, 3, 5, seed=1)
+    eng = CnnEngine(64, 64, 3, depths, 5, max_frames=1024)
+    ts = []
+    for i in range(4):
+        ts += [P[f"layers.{4 * i}.weight"], P[f"layers.{4 * i}.bias"], P[f"layers.{4 * i + 2}.weight"]]
+    eng.set_weights([torch.from_numpy(t).cuda() for t in ts])
+    obs = torch.rand(1024, 64, 64, 3, device="cuda")
+    for _ in range(3):
+        eng.forward(obs)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(20):
+        eng.forward(obs)
+    b.record(); b.synchronize()
+    ms = a.elapsed_time(b) / 20
+    print(f"encoder forward, 1024 frames 64x64x3: {ms:.3f} ms  ({0.1507 * 1024 / ms:.1f} TFLOP/s)")

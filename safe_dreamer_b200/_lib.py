@@ -15,10 +15,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libsafedreamer.so")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "safedreamer.h")
-_SOURCES = ["sd_api.cu", "sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh", "sd_pimg.cuh"]
+# translation units of the library and the headers each one includes (a unit is recompiled when any of them is newer
+# than its object file under csrc/_obj/)
+_UNITS = {
+    "sd_api.cu": ["sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh", "sd_pimg.cuh", "sd_internal.h"],
+    "sd_cnn.cu": ["sd_cnn.cuh", "sd_tc.cuh", "sd_internal.h"],
+}
+_SOURCES = sorted(set(_UNITS) | {h for hs in _UNITS.values() for h in hs})
+_OBJ = os.path.join(_CSRC, "_obj")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 SD_FLAG_BF16, SD_FLAG_SAVE_TAPE, SD_FLAG_GRAPH, SD_FLAG_FEATS_FROM_IMAGINE, SD_FLAG_BACKGROUND = 1, 2, 4, 8, 16
 SD_FLAG_PERSISTENT, SD_FLAG_LAYERWISE = 32, 64
@@ -28,6 +35,11 @@ MOD_RSSM, MOD_ACTOR, MOD_REWARD, MOD_CONT, MOD_VALUE, MOD_SLOW_VALUE = range(6)
 class sd_opt_tensor(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("numel", C.c_int64)]
+
+
+class sd_cnn_config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("height", "width", "channels", "layers", "kernel")] + \
+               [("depths", C.c_int32 * 8), ("max_frames", C.c_int32), ("max_tape_frames", C.c_int32)]
 
 
 class sd_config(C.Structure):
@@ -60,15 +72,35 @@ def build(force=False, verbose=False):
             if not force and not _stale():      # another rank built it while we waited
                 return _SO
             nvcc = os.environ.get("NVCC", "nvcc")
+            os.makedirs(_OBJ, exist_ok=True)
+            jobs = []
+            for unit, headers in _UNITS.items():
+                obj = os.path.join(_OBJ, unit + ".o")
+                deps = [os.path.join(_CSRC, unit), _INCLUDE] + [os.path.join(_CSRC, h) for h in headers]
+                if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
+                    cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(_CSRC, unit), "-o", obj]
+                    if verbose:
+                        print(" ".join(cmd))
+                    jobs.append((unit, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            for unit, proc in jobs:      # the units compile side by side
+                out, _ = proc.communicate()
+                if proc.returncode != 0:
+                    obj = os.path.join(_OBJ, unit + ".o")
+                    if os.path.exists(obj):
+                        os.remove(obj)
+                    raise RuntimeError(f"nvcc failed on {unit}:\n" + out)
+                if verbose and out.strip():
+                    print(out)
             tmp = f"{_SO}.tmp.{os.getpid()}"
-            cmd = [nvcc] + NVCC_FLAGS + [os.path.join(_CSRC, "sd_api.cu"), "-o", tmp]
+            cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + \
+                  [os.path.join(_OBJ, u + ".o") for u in _UNITS] + ["-o", tmp]
             if verbose:
                 print(" ".join(cmd))
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 if os.path.exists(tmp):
                     os.remove(tmp)
-                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+                raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
             os.replace(tmp, _SO)
         finally:
             fcntl.flock(lk, fcntl.LOCK_UN)
@@ -112,6 +144,11 @@ _SIGS = {
     "sd_latent_writeback": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [_P] * 5),
     "sd_latent_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [_P] * 6),
     "sd_launch_count": (C.c_uint64, []),
+    "sd_cnn_create": (C.c_int, [C.POINTER(sd_cnn_config), C.POINTER(_P)]),
+    "sd_cnn_destroy": (C.c_int, [_P]),
+    "sd_cnn_embed_size": (C.c_int64, [_P]),
+    "sd_cnn_set_weights": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P]),
+    "sd_cnn_forward": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint32, _P]),
 }
 
 

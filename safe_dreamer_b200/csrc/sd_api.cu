@@ -25,6 +25,7 @@
 #include "sd_scan.cuh"
 #include "sd_pimg.cuh"
 
+#include "sd_internal.h"
 using bf16 = __nv_bfloat16;
 
 // ------------------------------------------------------------------------------------------------ errors
@@ -38,6 +39,15 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+// shared with the other translation units (sd_internal.h)
+int sd_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void sd_count_launches(uint64_t n) { g_launches += n; }
 #define CUDA_TRY(expr)                                                                               \
   do {                                                                                               \
     cudaError_t e_ = (expr);                                                                         \

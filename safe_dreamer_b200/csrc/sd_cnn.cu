@@ -1,0 +1,221 @@
+// sd_cnn.cu -- host side of the CNN encoder entry points (include/safedreamer.h: sd_cnn_*).
+// Replaces world_model/networks.py:192-234 (ConvEncoder) for kernel_size 5, 3-channel frames and up to 64 channels per
+// stage (configs/base.yaml:300-310: depth 16, mults [2,3,4,4] -> 32/48/64/64).  Kernels: sd_cnn.cuh.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/safedreamer.h"
+#include "sd_cnn.cuh"
+#include "sd_internal.h"
+
+using sd::cnn::bf16;
+
+namespace {
+constexpr int kMaxLayers = 8;
+inline int round16(int v) { return (v + 15) / 16 * 16; }
+inline int pad_cin(int v) { return v <= 16 ? 16 : (v <= 32 ? 32 : 64); }
+}  // namespace
+
+struct sd_cnn {
+  sd_cnn_config cfg;
+  int L = 0;
+  int H[kMaxLayers + 1], W[kMaxLayers + 1];   // H[l] x W[l]: input resolution of stage l; [L] = final feature map
+  int C[kMaxLayers + 1];                      // real channels entering stage l; C[L] = final channels
+  int CP[kMaxLayers];                         // output channels of stage l rounded up to 16 (TMEM columns / MMA N)
+  int CS[kMaxLayers + 1];                     // channel stride of the bf16 activation entering stage l (l >= 1)
+  bf16* act[kMaxLayers + 1] = {};             // act[l], l >= 1: [max_frames][H[l]][W[l]][CS[l]]
+  float* pool[kMaxLayers] = {};               // tape (max_tape_frames)
+  uint8_t* arg[kMaxLayers] = {};
+  bf16* wpk[kMaxLayers] = {};
+  float* bias[kMaxLayers] = {};
+  float* gain[kMaxLayers] = {};
+  bool weights_set = false;
+  int tape_frames = 0;
+  const float* tape_obs = nullptr;
+  int sms = 148;
+  int device = 0;
+  std::vector<void*> allocs;
+};
+
+static int cnn_validate(const sd_cnn_config& c) {
+  if (c.kernel != sd::cnn::KSZ) return sd_fail(SD_ERR_INVALID, "sd_cnn: kernel_size %d unsupported (5 only)", c.kernel);
+  if (c.channels != 3) return sd_fail(SD_ERR_INVALID, "sd_cnn: %d input channels unsupported (3 only)", c.channels);
+  if (c.layers < 1 || c.layers > kMaxLayers) return sd_fail(SD_ERR_INVALID, "sd_cnn: layers must be 1..%d", kMaxLayers);
+  if (c.max_frames < 1) return sd_fail(SD_ERR_INVALID, "sd_cnn: max_frames must be positive");
+  int h = c.height, w = c.width;
+  for (int l = 0; l < c.layers; ++l) {
+    if (c.depths[l] < 1 || c.depths[l] > 64) return sd_fail(SD_ERR_INVALID, "sd_cnn: depth %d of stage %d outside 1..64", c.depths[l], l);
+    if ((h & 1) || (w & 1) || h < 2 || w < 2)
+      return sd_fail(SD_ERR_INVALID, "sd_cnn: stage %d input %dx%d is not even (MaxPool2d(2,2) would drop a row: unsupported)", l, h, w);
+    h /= 2;
+    w /= 2;
+  }
+  const int wp = c.width / 2, hp = c.height / 2;
+  if (!(wp == 16 || wp == 32 || wp == 64) || (hp * wp) % 128 != 0)
+    return sd_fail(SD_ERR_INVALID, "sd_cnn: frame %dx%d unsupported (width 32/64/128 and height*width/4 a multiple of 128)", c.height, c.width);
+  return SD_OK;
+}
+
+extern "C" int sd_cnn_create(const sd_cnn_config* cfg, sd_cnn** out) {
+  if (!cfg || !out) return sd_fail(SD_ERR_INVALID, "sd_cnn_create: null argument");
+  int rc = cnn_validate(*cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return sd_fail(SD_ERR_CUDA, "sd_cnn_create: no CUDA device (this library has no CPU path)");
+  sd_cnn* h = new sd_cnn();
+  h->cfg = *cfg;
+  h->L = cfg->layers;
+  cudaGetDevice(&h->device);
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, h->device);
+  h->H[0] = cfg->height; h->W[0] = cfg->width; h->C[0] = cfg->channels; h->CS[0] = cfg->channels;
+  for (int l = 0; l < h->L; ++l) {
+    h->H[l + 1] = h->H[l] / 2; h->W[l + 1] = h->W[l] / 2; h->C[l + 1] = cfg->depths[l];
+    h->CP[l] = round16(cfg->depths[l]);
+    h->CS[l + 1] = pad_cin(cfg->depths[l]);
+  }
+  auto alloc = [&](void** p, size_t bytes) -> bool {
+    if (cudaMalloc(p, bytes) != cudaSuccess) return false;
+    h->allocs.push_back(*p);
+    return true;
+  };
+  bool ok = true;
+  const size_t F = (size_t)cfg->max_frames, TF = (size_t)(cfg->max_tape_frames > 0 ? cfg->max_tape_frames : 0);
+  for (int l = 0; l < h->L && ok; ++l) {
+    const size_t px_out = (size_t)h->H[l + 1] * h->W[l + 1];
+    if (l + 1 < h->L) ok = ok && alloc((void**)&h->act[l + 1], F * px_out * h->CS[l + 1] * sizeof(bf16));
+    if (TF) {
+      ok = ok && alloc((void**)&h->pool[l], TF * px_out * h->CP[l] * sizeof(float));
+      ok = ok && alloc((void**)&h->arg[l], TF * px_out * h->CP[l]);
+    }
+    const int cinp = l == 0 ? 16 : h->CS[l];
+    const size_t wel = l == 0 ? (size_t)sd::cnn::K1C * h->CP[l] * 8 : (size_t)25 * cinp * h->CP[l];
+    ok = ok && alloc((void**)&h->wpk[l], wel * sizeof(bf16));
+    ok = ok && alloc((void**)&h->bias[l], 64 * sizeof(float));
+    ok = ok && alloc((void**)&h->gain[l], 64 * sizeof(float));
+  }
+  if (!ok) {
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return sd_fail(SD_ERR_CUDA, "sd_cnn_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  *out = h;
+  return SD_OK;
+}
+
+extern "C" int sd_cnn_destroy(sd_cnn* h) {
+  if (!h) return SD_OK;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return SD_OK;
+}
+
+extern "C" int64_t sd_cnn_embed_size(const sd_cnn* h) {
+  return h ? (int64_t)h->C[h->L] * h->H[h->L] * h->W[h->L] : 0;
+}
+
+extern "C" int sd_cnn_set_weights(sd_cnn* h, const float* const* tensors, int count, void* stream) {
+  if (!h || !tensors) return sd_fail(SD_ERR_INVALID, "sd_cnn_set_weights: null argument");
+  if (count != 3 * h->L) return sd_fail(SD_ERR_INVALID, "sd_cnn_set_weights: expected %d tensors (conv weight, conv bias, RMS scale per stage), got %d", 3 * h->L, count);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < h->L; ++l) {
+    const float *w = tensors[3 * l], *b = tensors[3 * l + 1], *g = tensors[3 * l + 2];
+    if (!w || !b || !g) return sd_fail(SD_ERR_INVALID, "sd_cnn_set_weights: null tensor for stage %d", l);
+    if (l == 0)
+      sd::cnn::pack_conv1_kernel<<<8, 256, 0, st>>>(w, b, g, h->C[1], h->CP[0], h->wpk[0], h->bias[0], h->gain[0]);
+    else
+      sd::cnn::pack_conv_kernel<<<64, 256, 0, st>>>(w, b, g, h->C[l + 1], h->C[l], h->CP[l], h->CS[l], h->wpk[l], h->bias[l], h->gain[l]);
+  }
+  sd_count_launches(h->L);
+  SD_CUDA_TRY(cudaGetLastError());
+  h->weights_set = true;
+  return SD_OK;
+}
+
+template <typename K>
+static cudaError_t ensure_smem(K kernel, int bytes, unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return cudaSuccess;
+  mask |= bit;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+static sd::cnn::StageOut stage_out(sd_cnn* h, int l, bool tape, float* embed) {
+  sd::cnn::StageOut o;
+  const bool last = l + 1 == h->L;
+  o.y = last ? nullptr : h->act[l + 1];
+  o.pool = tape ? h->pool[l] : nullptr;
+  o.arg = tape ? h->arg[l] : nullptr;
+  o.embed = last ? embed : nullptr;
+  o.bias = h->bias[l];
+  o.gain = h->gain[l];
+  o.cout = h->C[l + 1];
+  o.cp = h->CP[l];
+  o.cnext = last ? h->CP[l] : h->CS[l + 1];
+  o.HpWp = h->H[l + 1] * h->W[l + 1];
+  o.total = 0;
+  return o;
+}
+
+template <int CIN>
+static int launch_conv(sd_cnn* h, int l, int frames, const sd::cnn::StageOut& o, cudaStream_t st) {
+  static unsigned long long mask = 0;
+  using L = sd::cnn::ConvSmem<CIN>;
+  SD_CUDA_TRY(ensure_smem(sd::cnn::conv_pool_kernel<CIN>, L::kTotal, mask));
+  sd::cnn::ConvParams p;
+  p.x = h->act[l];
+  p.wpk = h->wpk[l];
+  p.out = o;
+  p.Hin = h->H[l]; p.Win = h->W[l]; p.Hp = h->H[l + 1]; p.Wp = h->W[l + 1];
+  p.out.total = frames * p.Hp * p.Wp;
+  p.tiles = (p.out.total + sd::cnn::BM - 1) / sd::cnn::BM;
+  const int grid = p.tiles < h->sms ? p.tiles : h->sms;
+  sd::cnn::conv_pool_kernel<CIN><<<grid, sd::cnn::THREADS, L::kTotal, st>>>(p);
+  return SD_OK;
+}
+
+extern "C" int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* embed, uint32_t flags, void* stream) {
+  if (!h || !obs || !embed) return sd_fail(SD_ERR_INVALID, "sd_cnn_forward: null argument");
+  if (!h->weights_set) return sd_fail(SD_ERR_WEIGHTS, "sd_cnn_forward: sd_cnn_set_weights was never called");
+  if (frames < 1 || frames > h->cfg.max_frames) return sd_fail(SD_ERR_WORKSPACE, "sd_cnn_forward: %d frames exceed max_frames %d", frames, h->cfg.max_frames);
+  const bool tape = (flags & SD_FLAG_SAVE_TAPE) != 0;
+  if (tape && frames > h->cfg.max_tape_frames)
+    return sd_fail(SD_ERR_WORKSPACE, "sd_cnn_forward: %d frames exceed max_tape_frames %d", frames, h->cfg.max_tape_frames);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    static unsigned long long mask = 0;
+    SD_CUDA_TRY(ensure_smem(sd::cnn::conv1_pool_kernel, sd::cnn::Conv1Smem::kTotal, mask));
+    sd::cnn::Conv1Params p;
+    p.obs = obs;
+    p.wpk = h->wpk[0];
+    p.out = stage_out(h, 0, tape, embed);
+    p.Hin = h->H[0]; p.Win = h->W[0]; p.Hp = h->H[1]; p.Wp = h->W[1];
+    p.out.total = frames * p.Hp * p.Wp;
+    p.tiles = p.out.total / sd::cnn::BM;
+    const int grid = p.tiles < h->sms ? p.tiles : h->sms;
+    sd::cnn::conv1_pool_kernel<<<grid, sd::cnn::THREADS, sd::cnn::Conv1Smem::kTotal, st>>>(p);
+  }
+  for (int l = 1; l < h->L; ++l) {
+    const sd::cnn::StageOut o = stage_out(h, l, tape, embed);
+    int rc;
+    switch (h->CS[l]) {
+      case 16: rc = launch_conv<16>(h, l, frames, o, st); break;
+      case 32: rc = launch_conv<32>(h, l, frames, o, st); break;
+      default: rc = launch_conv<64>(h, l, frames, o, st); break;
+    }
+    if (rc) return rc;
+  }
+  sd_count_launches(h->L);
+  SD_CUDA_TRY(cudaGetLastError());
+  h->tape_frames = tape ? frames : 0;
+  h->tape_obs = tape ? obs : nullptr;
+  return SD_OK;
+}

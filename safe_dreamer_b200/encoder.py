@@ -1,0 +1,139 @@
+"""CUDA replacement of the reference's CNN encoder (world_model/networks.py:192-234, ConvEncoder).
+
+`ConvEncoder(config, input_shape)` has the reference's constructor, attribute names (`depths`, `kernel_size`, `out_dim`,
+`layers`) and state_dict (`layers.{4i}.weight/bias` = conv, `layers.{4i+2}.weight` = RMS scale), so checkpoints load
+unchanged; the modules inside `layers` are parameter containers only -- `forward` goes through the C ABI
+(sd_cnn_forward / sd_cnn_backward: implicit-GEMM convolutions on tcgen05).  CUDA only, no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+
+SD_FLAG_SAVE_TAPE = _lib.SD_FLAG_SAVE_TAPE
+
+
+class CnnEngine:
+    """One sd_cnn handle: frame size, depths and capacity are fixed at creation."""
+
+    def __init__(self, height, width, channels, depths, kernel=5, max_frames=1024, max_tape_frames=0, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("safe_dreamer_b200: the CNN encoder needs a CUDA device (there is no CPU path)")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        cfg = _lib.sd_cnn_config()
+        cfg.height, cfg.width, cfg.channels, cfg.layers, cfg.kernel = int(height), int(width), int(channels), len(depths), int(kernel)
+        for i, d in enumerate(depths):
+            cfg.depths[i] = int(d)
+        cfg.max_frames, cfg.max_tape_frames = int(max_frames), int(max_tape_frames)
+        self.cfg = cfg
+        self.depths = tuple(int(d) for d in depths)
+        self.frame = (int(height), int(width), int(channels))
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sd_cnn_create(C.byref(cfg), C.byref(h)), "sd_cnn_create")
+        self.h = h
+        self.embed_size = int(self.lib.sd_cnn_embed_size(self.h))
+        self.max_frames, self.max_tape_frames = int(max_frames), int(max_tape_frames)
+        self._wkey = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.sd_cnn_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def set_weights(self, tensors):
+        """tensors: [conv weight, conv bias, RMS scale] per stage (fp32 CUDA, reference layouts)."""
+        keep = [t.detach().to(self.device, torch.float32).contiguous() for t in tensors]
+        arr = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        _lib.check(self.lib.sd_cnn_set_weights(self.h, arr, len(keep), self.stream), "sd_cnn_set_weights")
+
+    def forward(self, obs, tape=False):
+        """obs (..., H, W, C) fp32 CUDA in [0, 1] -> embed (..., embed_size) fp32."""
+        if not obs.is_cuda:
+            raise RuntimeError("safe_dreamer_b200: expected a CUDA tensor (there is no CPU path)")
+        lead = obs.shape[:-3]
+        if tuple(obs.shape[-3:]) != self.frame:
+            raise ValueError(f"frame shape {tuple(obs.shape[-3:])} != {self.frame}")
+        x = obs.to(torch.float32).contiguous()
+        frames = int(x.numel() // (self.frame[0] * self.frame[1] * self.frame[2]))
+        out = torch.empty(frames, self.embed_size, device=x.device, dtype=torch.float32)
+        _lib.check(self.lib.sd_cnn_forward(self.h, frames, x.data_ptr(), out.data_ptr(), SD_FLAG_SAVE_TAPE if tape else 0,
+                                           self.stream), "sd_cnn_forward")
+        self._tape_obs = x if tape else None
+        return out.reshape(*lead, self.embed_size)
+
+
+class ConvEncoder(nn.Module):
+    """Drop-in for networks.ConvEncoder (same constructor and state_dict)."""
+
+    def __init__(self, config, input_shape):
+        super().__init__()
+        if str(config.act) != "SiLU" or not bool(config.norm):
+            raise NotImplementedError("ConvEncoder: only act=SiLU with norm=True (configs/base.yaml) has kernels")
+        h, w, input_ch = input_shape
+        self.depths = tuple(int(config.depth) * int(m) for m in list(config.mults))
+        self.kernel_size = int(config.kernel_size)
+        self._input_shape = (int(h), int(w), int(input_ch))
+        layers, in_dim = [], input_ch
+        for depth in self.depths:
+            layers += [nn.Conv2d(in_dim, depth, self.kernel_size, stride=1, bias=True), nn.MaxPool2d(2, 2),
+                       nn.RMSNorm(depth, eps=1e-4, dtype=torch.float32), nn.SiLU()]
+            in_dim = depth
+            h, w = h // 2, w // 2
+        self.out_dim = self.depths[-1] * h * w
+        self.layers = nn.Sequential(*layers)          # parameter containers: names / shapes of the reference
+        self.max_frames = 1024
+        self._eng = None
+        self._wkey = None
+
+    def _tensors(self):
+        out = []
+        for i in range(len(self.depths)):
+            out += [self.layers[4 * i].weight, self.layers[4 * i].bias, self.layers[4 * i + 2].weight]
+        return out
+
+    def __deepcopy__(self, memo):
+        new = ConvEncoder.__new__(ConvEncoder)
+        nn.Module.__init__(new)
+        import copy
+        for k, v in self.__dict__.items():
+            if k in ("_eng", "_wkey"):
+                new.__dict__[k] = None
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _engine(self, frames, tape):
+        ts = self._tensors()
+        dev = ts[0].device
+        eng = self._eng
+        need_tape = frames if tape else 0
+        if eng is None or eng.device != dev or frames > eng.max_frames or need_tape > eng.max_tape_frames:
+            mf = max(frames, self.max_frames, eng.max_frames if eng else 0)
+            mt = max(need_tape, eng.max_tape_frames if eng else 0)
+            eng = self._eng = CnnEngine(*self._input_shape, self.depths, self.kernel_size, mf, mt, device=dev)
+            self._wkey = None
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if key != self._wkey:
+            eng.set_weights(ts)
+            self._wkey = key
+        return eng
+
+    def forward(self, obs):
+        """(B, T, H, W, C) in [0, 1] -> (B, T, out_dim) (networks.py:218-234)."""
+        frames = int(obs.numel() // (self._input_shape[0] * self._input_shape[1] * self._input_shape[2]))
+        need_grad = torch.is_grad_enabled() and (obs.requires_grad or any(t.requires_grad for t in self._tensors()))
+        if need_grad:
+            raise NotImplementedError("ConvEncoder: backward is not wired yet")
+        return self._engine(frames, False).forward(obs)
