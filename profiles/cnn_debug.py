@@ -43,3 +43,13 @@ if len(sys.argv) > 1:
     b.record(); b.synchronize()
     ms = a.elapsed_time(b) / 20
     print(f"encoder forward, 1024 frames 64x64x3: {ms:.3f} ms  ({0.1507 * 1024 / ms:.1f} TFLOP/s)")
+    for L in (1, 2, 3):
+        e2 = CnnEngine(64, 64, 3, depths[:L], 5, max_frames=1024)
+        e2.set_weights([torch.from_numpy(t).cuda() for t in ts[:3 * L]])
+        for _ in range(3):
+            e2.forward(obs)
+        torch.cuda.synchronize(); a.record()
+        for _ in range(20):
+            e2.forward(obs)
+        b.record(); b.synchronize()
+        print(f"  first {L} stage(s): {a.elapsed_time(b) / 20:.3f} ms")

@@ -165,11 +165,11 @@ static sd::cnn::StageOut stage_out(sd_cnn* h, int l, bool tape, float* embed) {
   return o;
 }
 
-template <int CIN>
-static int launch_conv(sd_cnn* h, int l, int frames, const sd::cnn::StageOut& o, cudaStream_t st) {
+template <int CIN, bool RES>
+static int launch_conv_t(sd_cnn* h, int l, int frames, const sd::cnn::StageOut& o, cudaStream_t st) {
   static unsigned long long mask = 0;
-  using L = sd::cnn::ConvSmem<CIN>;
-  SD_CUDA_TRY(ensure_smem(sd::cnn::conv_pool_kernel<CIN>, L::kTotal, mask));
+  using L = sd::cnn::ConvSmem<CIN, RES>;
+  SD_CUDA_TRY(ensure_smem(sd::cnn::conv_pool_kernel<CIN, RES>, sd::cnn::kConvSmemBudget, mask));
   sd::cnn::ConvParams p;
   p.x = h->act[l];
   p.wpk = h->wpk[l];
@@ -177,9 +177,32 @@ static int launch_conv(sd_cnn* h, int l, int frames, const sd::cnn::StageOut& o,
   p.Hin = h->H[l]; p.Win = h->W[l]; p.Hp = h->H[l + 1]; p.Wp = h->W[l + 1];
   p.out.total = frames * p.Hp * p.Wp;
   p.tiles = (p.out.total + sd::cnn::BM - 1) / sd::cnn::BM;
+  p.stages = L::stages(o.cp);
   const int grid = p.tiles < h->sms ? p.tiles : h->sms;
-  sd::cnn::conv_pool_kernel<CIN><<<grid, sd::cnn::THREADS, L::kTotal, st>>>(p);
+  static const bool trace2 = getenv("SD_TRACE_CNN") && atoi(getenv("SD_TRACE_CNN")) >= 2;
+  static long long* dbg = nullptr;
+  p.dbg = nullptr;
+  p.dbg_skip = getenv("SD_CNN_SKIP") ? atoi(getenv("SD_CNN_SKIP")) : 0;
+  if (trace2) {
+    if (!dbg) cudaMalloc(&dbg, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
+    p.dbg = dbg;
+  }
+  sd::cnn::conv_pool_kernel<CIN, RES><<<grid, sd::cnn::THREADS, L::total(o.cp), st>>>(p);
+  if (trace2) {
+    long long v[16];
+    cudaMemcpyAsync(v, dbg, sizeof(v), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[SD_TRACE_CNN] stage %d (%s weights, %d ring stages) CTA0: producer total %lld empty-wait %lld group-wait %lld views %lld | mma total %lld full-wait %lld free-wait %lld tiles %lld | epilogue wait %lld work %lld | mma fence %lld issue %lld commit %lld\n",
+            l + 1, RES ? "resident" : "streamed", p.stages, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12]);
+  }
   return SD_OK;
+}
+// weights stay resident in shared memory when all 25 tiles leave room for a useful ring (<= 100 KB)
+template <int CIN>
+static int launch_conv(sd_cnn* h, int l, int frames, const sd::cnn::StageOut& o, cudaStream_t st) {
+  if (25 * (CIN / 8) * o.cp * 16 <= 100 * 1024) return launch_conv_t<CIN, true>(h, l, frames, o, st);
+  return launch_conv_t<CIN, false>(h, l, frames, o, st);
 }
 
 extern "C" int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* embed, uint32_t flags, void* stream) {
@@ -190,6 +213,12 @@ extern "C" int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* em
   if (tape && frames > h->cfg.max_tape_frames)
     return sd_fail(SD_ERR_WORKSPACE, "sd_cnn_forward: %d frames exceed max_tape_frames %d", frames, h->cfg.max_tape_frames);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool trace = getenv("SD_TRACE_CNN") != nullptr;   // diagnostic: per-stage times (synchronises)
+  cudaEvent_t ev[kMaxLayers + 1];
+  if (trace) {
+    for (int l = 0; l <= h->L; ++l) cudaEventCreate(&ev[l]);
+    cudaEventRecord(ev[0], st);
+  }
   {
     static unsigned long long mask = 0;
     SD_CUDA_TRY(ensure_smem(sd::cnn::conv1_pool_kernel, sd::cnn::Conv1Smem::kTotal, mask));
@@ -201,7 +230,23 @@ extern "C" int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* em
     p.out.total = frames * p.Hp * p.Wp;
     p.tiles = p.out.total / sd::cnn::BM;
     const int grid = p.tiles < h->sms ? p.tiles : h->sms;
-    sd::cnn::conv1_pool_kernel<<<grid, sd::cnn::THREADS, sd::cnn::Conv1Smem::kTotal, st>>>(p);
+    static const bool trace2 = getenv("SD_TRACE_CNN") && atoi(getenv("SD_TRACE_CNN")) >= 2;
+    static long long* dbg = nullptr;
+    p.dbg = nullptr;
+    if (trace2) {
+      if (!dbg) cudaMalloc(&dbg, 16 * sizeof(long long));
+      cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
+      p.dbg = dbg;
+    }
+    sd::cnn::conv1_pool_kernel<<<grid, sd::cnn::THREADS1, sd::cnn::Conv1Smem::kTotal, st>>>(p);
+    if (trace2) {
+      long long v[16];
+      cudaMemcpyAsync(v, dbg, sizeof(v), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[SD_TRACE_CNN] stage 1 CTA0: producer total %lld patch %lld empty-wait %lld build %lld | mma total %lld full-wait %lld free-wait %lld tiles %lld | epilogue wait %lld work %lld\n",
+              v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9]);
+    }
+    if (trace) cudaEventRecord(ev[1], st);
   }
   for (int l = 1; l < h->L; ++l) {
     const sd::cnn::StageOut o = stage_out(h, l, tape, embed);
@@ -212,6 +257,18 @@ extern "C" int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* em
       default: rc = launch_conv<64>(h, l, frames, o, st); break;
     }
     if (rc) return rc;
+    if (trace) cudaEventRecord(ev[l + 1], st);
+  }
+  if (trace) {
+    cudaEventSynchronize(ev[h->L]);
+    fprintf(stderr, "[SD_TRACE_CNN] forward %d frames:", frames);
+    for (int l = 0; l < h->L; ++l) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[l], ev[l + 1]);
+      fprintf(stderr, " stage%d %.1f us", l + 1, ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+    for (int l = 0; l <= h->L; ++l) cudaEventDestroy(ev[l]);
   }
   sd_count_launches(h->L);
   SD_CUDA_TRY(cudaGetLastError());
