@@ -280,6 +280,11 @@ int sd_cnn_set_weights(sd_cnn* h, const float* const* tensors, int count, void* 
 /* ConvEncoder.forward: obs (frames, H, W, 3) fp32 in [0,1] -> embed (frames, sd_cnn_embed_size) fp32.
  * SD_FLAG_SAVE_TAPE keeps the pooled pre-norm maps and arg-max positions for sd_cnn_backward (obs must stay alive). */
 int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* embed, uint32_t flags, void* stream);
+/* Backward of the last SD_FLAG_SAVE_TAPE sd_cnn_forward (autograd of networks.py:192-234).
+ *   d_embed (frames, embed_size) fp32 -> d_obs (frames, H, W, 3) fp32 (nullable: skipped; only the attack needs it),
+ *   weight_grads: 3 * layers fp32 tensors in the order / layouts of sd_cnn_set_weights, ACCUMULATED into
+ *   (nullable array or entries = skip: frozen encoder).  Deterministic: partial sums are reduced in a fixed order. */
+int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, float* d_obs, float* const* weight_grads, void* stream);
 
 /* Kernels launched by this library since process start (all handles): bench.py's gpu_launches. */
 uint64_t sd_launch_count(void);

@@ -102,32 +102,46 @@ def encoder_params(depths, cin, k, seed=0, dtype=np.float32):
     return P
 
 
-def encoder_fwd(P, obs, n_layers=4, tape=None):
-    """ConvEncoder.forward (networks.py:218-234): obs (..., H, W, C) in [0, 1] -> (..., Cf*Hf*Wf)."""
+def round_bf16(x):
+    """fp32 -> nearest-even bfloat16 -> fp32: the rounding the tcgen05 path applies to every conv operand."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def encoder_fwd(P, obs, n_layers=4, tape=None, rnd=None):
+    """ConvEncoder.forward (networks.py:218-234): obs (..., H, W, C) in [0, 1] -> (..., Cf*Hf*Wf).
+    rnd (e.g. round_bf16): applied to every convolution operand (stage inputs and conv weights), which models the CUDA
+    path's bf16 operands / fp32 accumulation; None = the reference's fp32 arithmetic."""
+    rnd = rnd or (lambda a: a)
     lead = obs.shape[:-3]
-    x = (obs - obs.dtype.type(0.5)).reshape((-1,) + obs.shape[-3:])
+    x = rnd((obs - obs.dtype.type(0.5)).reshape((-1,) + obs.shape[-3:]))
     for i in range(n_layers):
-        w, b, g = P[f"layers.{4 * i}.weight"], P[f"layers.{4 * i}.bias"], P[f"layers.{4 * i + 2}.weight"]
+        w, b, g = rnd(P[f"layers.{4 * i}.weight"]), P[f"layers.{4 * i}.bias"], P[f"layers.{4 * i + 2}.weight"]
         y = conv_same(x, w, b)
         p, arg = maxpool2(y)
         if tape is not None:
             tape.append((x, y.shape, arg, p))
         x = norm_act(p, g)
+        if i + 1 < n_layers:
+            x = rnd(x)
     out = x.transpose(0, 3, 1, 2).reshape(x.shape[0], -1)        # flatten in (C, H, W) order
     if tape is not None:
         tape.append(x.shape)
     return out.reshape(lead + (out.shape[-1],))
 
 
-def encoder_bwd(P, tape, d_out, n_layers=4):
-    """-> (d_obs, {name: grad}) given d(loss)/d(embedding)."""
+def encoder_bwd(P, tape, d_out, n_layers=4, rnd=None):
+    """-> (d_obs, {name: grad}) given d(loss)/d(embedding).  rnd: as in encoder_fwd (conv weights and the conv-output
+    gradient dy are the rounded operands of the backward convolutions; the tape already holds the rounded stage inputs)."""
+    rnd = rnd or (lambda a: a)
     N, Hf, Wf, Cf = tape[-1]
     dx = d_out.reshape(N, Cf, Hf, Wf).transpose(0, 2, 3, 1)
     G = {}
     for i in reversed(range(n_layers)):
         x, yshape, arg, p = tape[i]
-        w, g = P[f"layers.{4 * i}.weight"], P[f"layers.{4 * i + 2}.weight"]
+        w, g = rnd(P[f"layers.{4 * i}.weight"]), P[f"layers.{4 * i + 2}.weight"]
         dp, G[f"layers.{4 * i + 2}.weight"] = norm_act_bwd(p, g, dx)
-        dy = maxpool2_bwd(dp, arg, yshape)
+        dy = rnd(maxpool2_bwd(dp, arg, yshape))
         dx, G[f"layers.{4 * i}.weight"], G[f"layers.{4 * i}.bias"] = conv_same_bwd(x, w, dy)
     return dx, G

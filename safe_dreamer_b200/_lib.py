@@ -19,7 +19,7 @@ _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "safedreamer.h")
 # than its object file under csrc/_obj/)
 _UNITS = {
     "sd_api.cu": ["sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh", "sd_pimg.cuh", "sd_internal.h"],
-    "sd_cnn.cu": ["sd_cnn.cuh", "sd_tc.cuh", "sd_internal.h"],
+    "sd_cnn.cu": ["sd_cnn.cuh", "sd_cnn_bwd.cuh", "sd_tc.cuh", "sd_internal.h"],
 }
 _SOURCES = sorted(set(_UNITS) | {h for hs in _UNITS.values() for h in hs})
 _OBJ = os.path.join(_CSRC, "_obj")
@@ -149,6 +149,7 @@ _SIGS = {
     "sd_cnn_embed_size": (C.c_int64, [_P]),
     "sd_cnn_set_weights": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P]),
     "sd_cnn_forward": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint32, _P]),
+    "sd_cnn_backward": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(_P), _P]),
 }
 
 

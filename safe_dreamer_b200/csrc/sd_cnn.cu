@@ -8,10 +8,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/safedreamer.h"
 #include "sd_cnn.cuh"
+#include "sd_cnn_bwd.cuh"
 #include "sd_internal.h"
 
 using sd::cnn::bf16;
@@ -33,6 +36,11 @@ struct sd_cnn {
   float* pool[kMaxLayers] = {};               // tape (max_tape_frames)
   uint8_t* arg[kMaxLayers] = {};
   bf16* wpk[kMaxLayers] = {};
+  bf16* wT[kMaxLayers] = {};                  // dgrad weights (only with a tape)
+  bf16* dy[kMaxLayers] = {};                  // gradient of the conv output of stage l (dense, bf16 NHWC, CP[l] channels)
+  float* dx[kMaxLayers + 1] = {};             // gradient of act[l], l >= 1 (fp32 NHWC, CS[l] channels)
+  float* scratch = nullptr;                   // partial sums of the weight / bias / scale gradients
+  size_t scratch_floats = 0;
   float* bias[kMaxLayers] = {};
   float* gain[kMaxLayers] = {};
   bool weights_set = false;
@@ -93,12 +101,22 @@ extern "C" int sd_cnn_create(const sd_cnn_config* cfg, sd_cnn** out) {
     if (TF) {
       ok = ok && alloc((void**)&h->pool[l], TF * px_out * h->CP[l] * sizeof(float));
       ok = ok && alloc((void**)&h->arg[l], TF * px_out * h->CP[l]);
+      ok = ok && alloc((void**)&h->dy[l], TF * 4 * px_out * h->CP[l] * sizeof(bf16));
+      if (l >= 1) ok = ok && alloc((void**)&h->dx[l], TF * 4 * px_out * h->CS[l] * sizeof(float));
+      const int cin_pad = l == 0 ? 16 : h->CS[l];
+      ok = ok && alloc((void**)&h->wT[l], (size_t)25 * h->CP[l] * cin_pad * sizeof(bf16));
+      const size_t wg = l == 0 ? (size_t)sd::cnn::BM * h->CP[l] : (size_t)(25 + 128 / h->CS[l]) * h->CS[l] * h->CP[l];
+      if (wg * h->sms > h->scratch_floats) h->scratch_floats = wg * h->sms;
     }
     const int cinp = l == 0 ? 16 : h->CS[l];
     const size_t wel = l == 0 ? (size_t)sd::cnn::K1C * h->CP[l] * 8 : (size_t)25 * cinp * h->CP[l];
     ok = ok && alloc((void**)&h->wpk[l], wel * sizeof(bf16));
     ok = ok && alloc((void**)&h->bias[l], 64 * sizeof(float));
     ok = ok && alloc((void**)&h->gain[l], 64 * sizeof(float));
+  }
+  if (TF && ok) {
+    if ((size_t)h->sms * 8 * 128 > h->scratch_floats) h->scratch_floats = (size_t)h->sms * 8 * 128;
+    ok = alloc((void**)&h->scratch, h->scratch_floats * sizeof(float));
   }
   if (!ok) {
     for (void* p : h->allocs) cudaFree(p);
@@ -131,8 +149,9 @@ extern "C" int sd_cnn_set_weights(sd_cnn* h, const float* const* tensors, int co
       sd::cnn::pack_conv1_kernel<<<8, 256, 0, st>>>(w, b, g, h->C[1], h->CP[0], h->wpk[0], h->bias[0], h->gain[0]);
     else
       sd::cnn::pack_conv_kernel<<<64, 256, 0, st>>>(w, b, g, h->C[l + 1], h->C[l], h->CP[l], h->CS[l], h->wpk[l], h->bias[l], h->gain[l]);
+    if (h->wT[l]) sd::cnn::pack_dgrad_kernel<<<64, 256, 0, st>>>(w, h->C[l + 1], h->C[l], h->CP[l], l == 0 ? 16 : h->CS[l], h->wT[l]);
   }
-  sd_count_launches(h->L);
+  sd_count_launches(h->L * (h->wT[0] ? 2 : 1));
   SD_CUDA_TRY(cudaGetLastError());
   h->weights_set = true;
   return SD_OK;
@@ -274,5 +293,153 @@ extern "C" int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* em
   SD_CUDA_TRY(cudaGetLastError());
   h->tape_frames = tape ? frames : 0;
   h->tape_obs = tape ? obs : nullptr;
+  return SD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+template <int CK, bool RES>
+static int launch_dgrad_t(sd_cnn* h, const sd::cnn::DgradParams& p0, cudaStream_t st) {
+  static unsigned long long mask = 0;
+  using L = sd::cnn::DgradSmem<CK, RES>;
+  SD_CUDA_TRY(ensure_smem(sd::cnn::conv_dgrad_kernel<CK, RES>, sd::cnn::kConvSmemBudget, mask));
+  sd::cnn::DgradParams p = p0;
+  p.stages = L::stages(p.cinp);
+  const int grid = p.tiles < h->sms ? p.tiles : h->sms;
+  sd::cnn::conv_dgrad_kernel<CK, RES><<<grid, sd::cnn::DG_THREADS, L::total(p.cinp), st>>>(p);
+  return SD_OK;
+}
+template <int CK>
+static int launch_dgrad(sd_cnn* h, const sd::cnn::DgradParams& p, cudaStream_t st) {
+  if (25 * (CK / 8) * p.cinp * 16 <= 100 * 1024) return launch_dgrad_t<CK, true>(h, p, st);
+  return launch_dgrad_t<CK, false>(h, p, st);
+}
+template <int CX>
+static int launch_wgrad(sd_cnn* h, const sd::cnn::WgradParams& p0, int* nblocks, cudaStream_t st) {
+  static unsigned long long mask = 0;
+  SD_CUDA_TRY(ensure_smem(sd::cnn::conv_wgrad_kernel<CX>, sd::cnn::kWgSmem, mask));
+  sd::cnn::WgradParams p = p0;
+  const int tpg = 128 / CX, ngrp = (25 + tpg - 1) / tpg;
+  int gph = 512 / p.cp;
+  if (gph > ngrp) gph = ngrp;
+  const int halves = (ngrp + gph - 1) / gph;
+  gph = (ngrp + halves - 1) / halves;
+  p.gph = gph;
+  p.taps_padded = halves * gph * tpg;
+  int gx = h->sms / halves;
+  if (gx > p.tiles) gx = p.tiles;
+  if (gx < 1) gx = 1;
+  *nblocks = gx;
+  sd::cnn::conv_wgrad_kernel<CX><<<dim3(gx, halves), sd::cnn::WG_THREADS, sd::cnn::kWgSmem, st>>>(p);
+  return SD_OK;
+}
+
+extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, float* d_obs, float* const* weight_grads, void* stream) {
+  if (!h || !d_embed) return sd_fail(SD_ERR_INVALID, "sd_cnn_backward: null argument");
+  if (h->tape_frames != frames || frames < 1)
+    return sd_fail(SD_ERR_NO_TAPE, "sd_cnn_backward: no SD_FLAG_SAVE_TAPE forward with %d frames on this handle (last taped forward: %d frames)", frames, h->tape_frames);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint64_t launches = 0;
+  static const bool trace = getenv("SD_TRACE_CNN") != nullptr;   // diagnostic: per-kernel times (synchronises)
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  auto mark = [&](const char* what, int l) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    marks.push_back({std::string(what) + std::to_string(l + 1), e});
+  };
+  mark("start", -1);
+  for (int l = h->L - 1; l >= 0; --l) {
+    const bool last = l + 1 == h->L;
+    const int Hp = h->H[l + 1], Wp = h->W[l + 1], cp = h->CP[l];
+    float* g_w = weight_grads ? weight_grads[3 * l] : nullptr;
+    float* g_b = weight_grads ? weight_grads[3 * l + 1] : nullptr;
+    float* g_g = weight_grads ? weight_grads[3 * l + 2] : nullptr;
+    {  // 1. SiLU / RMSNorm / max-pool backward
+      sd::cnn::NormBwdParams p;
+      p.pool = h->pool[l]; p.arg = h->arg[l]; p.gain = h->gain[l];
+      p.dout = last ? d_embed : h->dx[l + 1];
+      p.dy = h->dy[l];
+      p.partial = h->scratch;
+      p.total = frames * Hp * Wp; p.cp = cp; p.cout = h->C[l + 1];
+      p.ldo = last ? 0 : h->CS[l + 1]; p.embed = last ? 1 : 0; p.HpWp = Hp * Wp; p.Wp = Wp;
+      int blocks = (p.total + 31) / 32;
+      if (blocks > h->sms * 8) blocks = h->sms * 8;
+      if (cp <= 32) sd::cnn::norm_pool_bwd_kernel<1><<<blocks, 256, 0, st>>>(p);
+      else sd::cnn::norm_pool_bwd_kernel<2><<<blocks, 256, 0, st>>>(p);
+      ++launches;
+      if (g_b || g_g) {
+        sd::cnn::norm_bwd_reduce_kernel<<<1, 128, 0, st>>>(h->scratch, blocks, h->C[l + 1], g_g, g_b);
+        ++launches;
+      }
+      mark("norm_pool_bwd", l);
+    }
+    const int Hc = h->H[l], Wc = h->W[l], total = frames * Hc * Wc;
+    if (g_w) {  // 3. weight gradient
+      int nblocks = 0;
+      if (l == 0) {
+        static unsigned long long mask = 0;
+        SD_CUDA_TRY(ensure_smem(sd::cnn::conv1_wgrad_kernel, sd::cnn::kW1Smem, mask));
+        sd::cnn::Wgrad1Params p;
+        p.obs = h->tape_obs; p.dy = h->dy[0]; p.partial = h->scratch;
+        p.H = Hc; p.W = Wc; p.total = total; p.tiles = total / sd::cnn::BM; p.cp = cp;
+        nblocks = p.tiles < h->sms ? p.tiles : h->sms;
+        sd::cnn::conv1_wgrad_kernel<<<nblocks, sd::cnn::WG_THREADS, sd::cnn::kW1Smem, st>>>(p);
+        sd::cnn::wgrad1_reduce_kernel<<<20, 256, 0, st>>>(h->scratch, nblocks, cp, h->C[1], g_w);
+      } else {
+        sd::cnn::WgradParams p;
+        p.x = h->act[l]; p.dy = h->dy[l]; p.partial = h->scratch;
+        p.H = Hc; p.W = Wc; p.total = total; p.tiles = (total + sd::cnn::BM - 1) / sd::cnn::BM; p.cp = cp;
+        int rc;
+        switch (h->CS[l]) {
+          case 16: rc = launch_wgrad<16>(h, p, &nblocks, st); break;
+          case 32: rc = launch_wgrad<32>(h, p, &nblocks, st); break;
+          default: rc = launch_wgrad<64>(h, p, &nblocks, st); break;
+        }
+        if (rc) return rc;
+        const int tpg = 128 / h->CS[l], ngrp = (25 + tpg - 1) / tpg;
+        int gph = 512 / cp;
+        if (gph > ngrp) gph = ngrp;
+        const int halves = (ngrp + gph - 1) / gph;
+        gph = (ngrp + halves - 1) / halves;
+        sd::cnn::wgrad_reduce_kernel<<<400, 256, 0, st>>>(h->scratch, nblocks, halves * gph * tpg, h->CS[l], cp, h->C[l + 1], h->C[l], g_w);
+      }
+      launches += 2;
+      mark("wgrad", l);
+    }
+    if (l >= 1 || d_obs) {  // 2. input gradient
+      sd::cnn::DgradParams p;
+      p.dy = h->dy[l]; p.wT = h->wT[l];
+      p.dx = l >= 1 ? h->dx[l] : d_obs;
+      p.H = Hc; p.W = Wc; p.total = total; p.tiles = (total + sd::cnn::BM - 1) / sd::cnn::BM;
+      p.cinp = l >= 1 ? h->CS[l] : 16;
+      p.ldx = l >= 1 ? h->CS[l] : 3;
+      p.nwrite = l >= 1 ? h->CS[l] : 3;
+      p.stages = 0;
+      int rc;
+      switch (cp) {
+        case 16: rc = launch_dgrad<16>(h, p, st); break;
+        case 32: rc = launch_dgrad<32>(h, p, st); break;
+        case 48: rc = launch_dgrad<48>(h, p, st); break;
+        default: rc = launch_dgrad<64>(h, p, st); break;
+      }
+      if (rc) return rc;
+      ++launches;
+      mark("dgrad", l);
+    }
+  }
+  if (trace) {
+    cudaEventSynchronize(marks.back().second);
+    fprintf(stderr, "[SD_TRACE_CNN] backward %d frames:", frames);
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      fprintf(stderr, " %s %.1f us", marks[i].first.c_str(), ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
+  sd_count_launches(launches);
+  SD_CUDA_TRY(cudaGetLastError());
   return SD_OK;
 }

@@ -1,0 +1,671 @@
+// sd_cnn_bwd.cuh -- backward of the CNN encoder stages (autograd of world_model/networks.py:192-234) for sm_100a.
+//
+// Per stage, in reverse order:
+//   1. norm_pool_bwd_kernel  (SIMT, warp per pooled pixel, lane = channel): SiLU / RMSNorm backward on the pooled pre-norm
+//      map kept by the forward, RMS-scale and bias gradient partials, and the max-pool scatter -- writes dy, the gradient
+//      of the conv output, as a dense bf16 NHWC map (zeros off the arg-max).
+//   2. conv_dgrad_kernel     (tcgen05): dx = conv of dy with the flipped, transposed taps: 25 shifted views of dy, one
+//      accumulator of N = Cin columns, same chunk-major no-swizzle operands / cp.async producer as the forward.
+//   3. conv_wgrad_kernel     (tcgen05, MN-major operands): dW[tap][ci][co] = sum over pixels x[p + tap][ci] dy[p][co].  The
+//      K dimension is the pixel index, so the SAME [chunk][pixel][16 B] shared-memory image the forward uses as a K-major
+//      operand is read as an MN-major one (LBO = 128 B between 8-pixel K blocks, SBO = 2 KB between 8-channel MN blocks);
+//      128 / Cin views are stacked into one M = 128 operand.  Each CTA keeps its tap groups' accumulators in TMEM over all
+//      of its pixel tiles and writes one fp32 partial; wgrad_reduce_kernel sums the partials in a fixed order into the
+//      reference layout (Cout, Cin, 5, 5), accumulating into the caller's gradient tensors.
+#pragma once
+#include "sd_cnn.cuh"
+
+namespace sd {
+namespace cnn {
+
+// ------------------------------------------------------------------------------------------------ 1. norm / pool backward
+struct NormBwdParams {
+  const float* pool;      // [total][cp] pooled pre-norm values (forward tape)
+  const uint8_t* arg;     // [total][cp]
+  const float* gain;      // [64] zero padded
+  const float* dout;      // gradient of the stage output: fp32 [total][ldo] NHWC, or (embed != 0) [N][cout * HpWp] in (C,H,W) order
+  bf16* dy;               // [N][2 Hp][2 Wp][cp] bf16, fully written
+  float* partial;         // [gridDim.x][2][64]: per-CTA sums of d(gain), d(bias)
+  int total, cp, cout, ldo, embed, HpWp, Wp;
+};
+
+// CPL = channels per lane (cp <= 32 * CPL)
+template <int CPL>
+__global__ void __launch_bounds__(256) norm_pool_bwd_kernel(const NormBwdParams P) {
+  __shared__ float red[8][2][64];
+  constexpr int U = 4;                         // pixels per warp iteration: all of their loads are issued before any math
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = lane * CPL;
+  const bool act = c0 < P.cp;
+  float g[CPL], dg[CPL], db[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) { g[j] = act ? P.gain[c0 + j] : 0.f; dg[j] = 0.f; db[j] = 0.f; }
+  const float inv_c = 1.f / (float)P.cout;
+  const int W = 2 * P.Wp, Hp = P.HpWp / P.Wp;
+  for (int px0 = (blockIdx.x * 8 + warp) * U; px0 < P.total; px0 += gridDim.x * 8 * U) {
+    float p[U][CPL], d[U][CPL];
+    uint32_t ar[U][CPL];
+    int nn_[U], rem_[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int px = px0 + u;
+      const bool ok = act && px < P.total;
+      nn_[u] = px / P.HpWp; rem_[u] = px - nn_[u] * P.HpWp;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        p[u][j] = 0.f; d[u][j] = 0.f; ar[u][j] = 0u;
+        if (ok) {
+          p[u][j] = __ldg(P.pool + (size_t)px * P.cp + c0 + j);
+          ar[u][j] = __ldg(P.arg + (size_t)px * P.cp + c0 + j);
+          if (c0 + j < P.cout)
+            d[u][j] = P.embed ? __ldg(P.dout + (size_t)nn_[u] * P.cout * P.HpWp + (size_t)(c0 + j) * P.HpWp + rem_[u])
+                              : __ldg(P.dout + (size_t)px * P.ldo + c0 + j);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int px = px0 + u;
+      if (px >= P.total) break;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) ss = fmaf(p[u][j], p[u][j], ss);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float rho = 1.f / sqrtf(ss * inv_c + kRmsEps);
+      float nn[CPL], dn[CPL], dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        nn[j] = p[u][j] * rho;
+        const float m = nn[j] * g[j];
+        const float sg = 1.f / (1.f + __expf(-m));
+        const float dm = d[u][j] * (sg * (1.f + m * (1.f - sg)));
+        dg[j] = fmaf(dm, nn[j], dg[j]);
+        dn[j] = dm * g[j];
+        dot = fmaf(dn[j], nn[j], dot);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      dot *= inv_c;
+      const int py = rem_[u] / P.Wp, pxx = rem_[u] - py * P.Wp;
+      bf16* base = P.dy + ((size_t)(nn_[u] * 2 * Hp + 2 * py) * W + 2 * pxx) * P.cp + c0;
+      float v[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) { v[j] = rho * (dn[j] - nn[j] * dot); db[j] += v[j]; }
+      if (act) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          bf16* dst = base + ((size_t)(q >> 1) * W + (q & 1)) * P.cp;
+          if (CPL == 2) *reinterpret_cast<uint32_t*>(dst) = pack2(ar[u][0] == (uint32_t)q ? v[0] : 0.f, ar[u][CPL - 1] == (uint32_t)q ? v[CPL - 1] : 0.f);
+          else dst[0] = __float2bfloat16(ar[u][0] == (uint32_t)q ? v[0] : 0.f);
+        }
+      }
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { red[warp][0][c0 + j] = dg[j]; red[warp][1][c0 + j] = db[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float s = 0.f;
+    if (c < P.cp)
+      for (int w = 0; w < 8; ++w) s += red[w][k][c];
+    P.partial[((size_t)blockIdx.x * 2 + k) * 64 + c] = s;
+  }
+}
+
+// sums the per-CTA partials in order and ACCUMULATES into the caller's gradient tensors (nullable)
+__global__ void norm_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int cout, float* __restrict__ d_gain,
+                                       float* __restrict__ d_bias) {
+  const int k = threadIdx.x >> 6, c = threadIdx.x & 63;
+  if (c >= cout) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[((size_t)b * 2 + k) * 64 + c];
+  float* dst = k == 0 ? d_gain : d_bias;
+  if (dst) dst[c] += s;
+}
+
+// ------------------------------------------------------------------------------------------------ 2. dgrad
+// dx[n][iy][ix][ci] = sum_{ky,kx,co} dy[n][iy - ky + 2][ix - kx + 2][co] w[co][ci][ky][kx]
+struct DgradParams {
+  const bf16* dy;    // [N][H][W][CK] bf16 (CK = template parameter = the stage's cp)
+  const bf16* wT;    // [25 taps][CK/8][cinp][8]: w[co = k][ci = row][ky][kx], zero padded
+  float* dx;         // [N][H][W][ldx] fp32; the first `cin` channels are written ... up to ldx (zero padded by the weights)
+  int H, W, total, tiles, cinp, ldx, nwrite, stages;
+};
+
+template <int CK, bool RES>
+struct DgradSmem {
+  static constexpr int KC = CK / 8;
+  static constexpr int kA = KC * BM * 16;
+  static constexpr int kBt = KC * 64 * 16;                         // streamed: one tap tile at cinp = 64
+  static constexpr int VPS = RES ? 5 : 2;                          // taps per ring stage
+  static constexpr int NG = (25 + VPS - 1) / VPS;
+  static constexpr int kStage = RES ? VPS * kA : VPS * (kA + kBt);
+  static constexpr int kMaxStages = 8;
+  static constexpr int kFixed = 8 * (2 * kMaxStages + 4) + 16 + 256;
+  static int resident_bytes(int cinp) { return RES ? 25 * KC * cinp * 16 : 0; }
+  static int stages(int cinp) {
+    int n = (kConvSmemBudget - kFixed - resident_bytes(cinp)) / kStage;
+    return n > kMaxStages ? kMaxStages : n;
+  }
+  static int total(int cinp) { return kFixed + resident_bytes(cinp) + stages(cinp) * kStage; }
+};
+
+constexpr int DG_THREADS = 416;   // warps 0-3 producers, 4 MMA, 5-8 / 9-12 two epilogue groups
+
+template <int CK, bool RES>
+__global__ void __launch_bounds__(DG_THREADS, 1) conv_dgrad_kernel(const __grid_constant__ DgradParams P) {
+  using L = DgradSmem<CK, RES>;
+  constexpr int KC = L::KC;
+  const int STAGES = P.stages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int cinp = P.cinp;
+  const int resB = RES ? 25 * KC * cinp * 16 : 0;
+  const uint32_t ring = base + (uint32_t)resB;
+  const int off_bar = resB + STAGES * L::kStage;
+  const uint32_t bar_full = base + (uint32_t)off_bar, bar_empty = bar_full + 8 * L::kMaxStages, bar_accf = bar_empty + 8 * L::kMaxStages,
+                 bar_free = bar_accf + 16, tmem_slot = bar_free + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 8 * (2 * L::kMaxStages + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (RES) {
+    const int n16 = 25 * KC * cinp;      // global [tap][c][row][8] -> shared [c][tap * cinp + row][16 B]
+    for (int i = threadIdx.x; i < n16; i += DG_THREADS) {
+      const int row = i % cinp, c = (i / cinp) % KC, tap = i / (cinp * KC);
+      reinterpret_cast<uint4*>(gbase)[(size_t)c * 25 * cinp + tap * cinp + row] = __ldg(reinterpret_cast<const uint4*>(P.wT) + i);
+    }
+    fence_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, PROD);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_accf + 8 * s, 1);
+      mbar_init(bar_free + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const int HW = P.H * P.W;
+
+  if (warp < 4) {
+    const int tid = threadIdx.x;
+    int s = 0;
+    uint32_t eph = 1;
+    const int rowpitch = P.W * CK;
+    const int wrow = tid & 63, wc0 = tid >> 6;
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+      const int g = tile * BM + tid;
+      const bool ok = g < P.total;
+      const int n = g / HW, rem = g - n * HW, iy = rem / P.W, ix = rem - iy * P.W;
+      const bf16* src0 = P.dy + ((size_t)(n * P.H + iy) * P.W + ix) * CK;
+      uint32_t rmask = 0, cmask = 0;   // bit k: row iy + 2 - k / column ix + 2 - k is inside the map
+#pragma unroll
+      for (int k = 0; k < KSZ; ++k) {
+        rmask |= (uint32_t)(ok && iy + 2 - k >= 0 && iy + 2 - k < P.H) << k;
+        cmask |= (uint32_t)(ix + 2 - k >= 0 && ix + 2 - k < P.W) << k;
+      }
+#pragma unroll
+      for (int vg = 0; vg < L::NG; ++vg) {
+        mbar_wait(bar_empty + 8 * s, eph);
+        const uint32_t stg = ring + (uint32_t)(s * L::kStage);
+#pragma unroll
+        for (int u = 0; u < L::VPS; ++u) {
+          const int t = vg * L::VPS + u;
+          if (t >= 25) break;
+          const int ky = t / KSZ, kx = t - ky * KSZ;
+          const bool valid = ((rmask >> ky) & (cmask >> kx) & 1u) != 0u;
+          const bf16* src = valid ? src0 + (2 - ky) * rowpitch + (2 - kx) * CK : P.dy;
+          const uint32_t nbytes = valid ? 16u : 0u;
+          const uint32_t va = stg + (uint32_t)(u * (RES ? L::kA : L::kA + L::kBt));
+#pragma unroll
+          for (int c = 0; c < KC; ++c) cp_async16(va + (uint32_t)(c * BM * 16 + tid * 16), src + c * 8, nbytes);
+          if (!RES) {
+            if (wrow < cinp) {
+              const uint4* w = reinterpret_cast<const uint4*>(P.wT) + (size_t)(t * KC + wc0) * cinp + wrow;
+              const uint32_t dst = va + (uint32_t)(L::kA + wrow * 16 + wc0 * cinp * 16);
+#pragma unroll
+              for (int c = 0; c < KC / 2; ++c) cp_async16(dst + (uint32_t)(c * 2 * cinp * 16), w + (size_t)c * 2 * cinp, 16u);
+            }
+          }
+        }
+        cp_async_arrive(bar_full + 8 * s);
+        if (++s == STAGES) { s = 0; eph ^= 1u; }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(BM, cinp);
+      const uint64_t dA0 = make_desc_nosw(0, BM * 16, 128);
+      const uint32_t ldB = (uint32_t)((RES ? 25 : 1) * cinp * 16);
+      const uint64_t dB0 = make_desc_nosw(0, ldB, 128);
+      const uint32_t ahi = (uint32_t)(dA0 >> 32), bhi = (uint32_t)(dB0 >> 32), alo0 = (uint32_t)dA0, blo0 = (uint32_t)dB0;
+      const uint32_t kstepB = (2 * ldB) >> 4, blo_res = (base & 0x3FFFFu) >> 4;
+      int lt = 0, s = 0;
+      uint32_t fph = 0;
+      for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+        const int set = lt & 1;
+        if (lt >= 2) mbar_wait(bar_free + 8 * set, (uint32_t)((lt >> 1) - 1) & 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem + (uint32_t)(set * 64);
+#pragma unroll
+        for (int vg = 0; vg < L::NG; ++vg) {
+          mbar_wait(bar_full + 8 * s, fph);
+          fence_async_smem();
+          tc_fence_after();
+          const uint32_t stlo = ((ring + (uint32_t)(s * L::kStage)) & 0x3FFFFu) >> 4;
+#pragma unroll
+          for (int u = 0; u < L::VPS; ++u) {
+            const int t = vg * L::VPS + u;
+            if (t >= 25) break;
+            const uint32_t alo = alo0 + stlo + (uint32_t)((u * (RES ? L::kA : L::kA + L::kBt)) >> 4);
+            const uint32_t blo = blo0 + (RES ? blo_res + (uint32_t)(t * cinp) : stlo + (uint32_t)((u * (L::kA + L::kBt) + L::kA) >> 4));
+#pragma unroll
+            for (int kk = 0; kk < CK / 16; ++kk)
+              mma_lh(acc, alo + (uint32_t)((kk * 2 * BM * 16) >> 4), ahi, blo + kk * kstepB, bhi, idesc, (t | kk) == 0 ? 0u : 1u);
+          }
+          tc_commit(bar_empty + 8 * s);
+          if (++s == STAGES) { s = 0; fph ^= 1u; }
+        }
+        tc_commit(bar_accf + 8 * set);
+      }
+    }
+  } else {
+    // epilogue: thread = input pixel; fp32 NHWC store of the first nwrite channels (row stride ldx)
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const int set = warp >= 9 ? 1 : 0;
+    for (int lt = set, tile = blockIdx.x + set * gridDim.x; tile < P.tiles; tile += 2 * gridDim.x, lt += 2) {
+      mbar_wait(bar_accf + 8 * set, (uint32_t)(lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tm = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * 64);
+      float v[64];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16)
+        if (c0 < cinp) {
+          uint32_t r[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(tm + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[c0 + i] = __uint_as_float(r[i]);
+        }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free + 8 * set);
+      const int g = tile * BM + row;
+      if (g < P.total) {
+        float* dst = P.dx + (size_t)g * P.ldx;
+        if ((P.nwrite & 3) == 0 && (P.ldx & 3) == 0) {
+#pragma unroll
+          for (int c = 0; c < 64; c += 4)
+            if (c < P.nwrite) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c < P.nwrite) dst[c] = v[c];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
+  }
+}
+
+// w (cout, cin, 5, 5) fp32 -> wT [25][ckp/8][cinp][8] bf16: element (tap, k = co, row = ci)
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int ckp, int cinp, bf16* __restrict__ wT) {
+  const int total = KSZ * KSZ * ckp * cinp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7, ci = (i >> 3) % cinp, c8 = (i >> 3) / cinp % (ckp / 8), tap = i / (ckp * cinp);
+    const int co = c8 * 8 + e;
+    float v = 0.f;
+    if (co < cout && ci < cin) v = w[((size_t)co * cin + ci) * (KSZ * KSZ) + tap];
+    wT[i] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3. wgrad
+// instruction descriptor with both operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) { return tc::make_idesc(M, N) | (1u << 15) | (1u << 16); }
+// MN-major, no swizzle, [chunk][128 pixels][16 B] image: 8-pixel K blocks 128 B apart (LBO), 8-channel MN blocks 2 KB apart (SBO)
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) { return make_desc_nosw(saddr, 128, BM * 16); }
+
+struct WgradParams {
+  const bf16* x;       // stage input [N][H][W][CX] bf16
+  const bf16* dy;      // [N][H][W][cp] bf16
+  float* partial;      // [gridDim.x][taps_padded][CX][cp] fp32 (this half's tap range only is written)
+  int H, W, total, tiles, cp;
+  int gph;             // tap groups per CTA (TMEM columns = gph * cp <= 512)
+  int taps_padded;     // halves * gph * (128 / CX)
+};
+
+constexpr int WG_THREADS = 288;    // warps 0-3 producers, 4 MMA, 5-8 epilogue (once, at the end)
+constexpr int WG_STAGES = 5;
+constexpr int kWgStage = 32 * 1024;   // one tap group: 128 (tap, channel) rows x 128 pixels
+constexpr int kWgDy = 16 * 1024;      // dy tile slot (cp <= 64)
+constexpr int kWgSmem = WG_STAGES * kWgStage + 2 * kWgDy + 8 * (2 * WG_STAGES + 6) + 16 + 256;
+
+template <int CX>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  constexpr int XC = CX / 8, TPG = 128 / CX;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t dyb = base + WG_STAGES * kWgStage;
+  const uint32_t bar_full = dyb + 2 * kWgDy, bar_empty = bar_full + 8 * WG_STAGES, bar_dyf = bar_empty + 8 * WG_STAGES,
+                 bar_dye = bar_dyf + 16, bar_done = bar_dye + 16, tmem_slot = bar_done + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + WG_STAGES * kWgStage + 2 * kWgDy + 8 * (2 * WG_STAGES + 6));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cp = P.cp, DC = cp / 8;
+  const int tap0 = blockIdx.y * P.gph * TPG;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, PROD);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_dyf + 8 * s, PROD);
+      mbar_init(bar_dye + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const int HW = P.H * P.W;
+
+  if (warp < 4) {
+    const int tid = threadIdx.x;
+    int s = 0, lt = 0;
+    uint32_t eph = 1;
+    const int rowpitch = P.W * CX;
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+      const int g = tile * BM + tid;
+      const bool ok = g < P.total;
+      const int n = g / HW, rem = g - n * HW, oy = rem / P.W, ox = rem - oy * P.W;
+      // dy tile (the N operand of every group of this pixel tile)
+      mbar_wait(bar_dye + 8 * (lt & 1), (uint32_t)(((lt >> 1) & 1) ^ 1));
+      {
+        const bf16* src = ok ? P.dy + (size_t)g * cp : P.dy;
+        const uint32_t dst = dyb + (uint32_t)((lt & 1) * kWgDy + tid * 16);
+        for (int c = 0; c < DC; ++c) cp_async16(dst + (uint32_t)(c * BM * 16), src + c * 8, ok ? 16u : 0u);
+        cp_async_arrive(bar_dyf + 8 * (lt & 1));
+      }
+      const bf16* src0 = P.x + ((size_t)(n * P.H + oy) * P.W + ox) * CX;
+      uint32_t rmask = 0, cmask = 0;   // bit k: row oy + k - 2 / column ox + k - 2 inside the map
+#pragma unroll
+      for (int k = 0; k < KSZ; ++k) {
+        rmask |= (uint32_t)(ok && oy + k - 2 >= 0 && oy + k - 2 < P.H) << k;
+        cmask |= (uint32_t)(ox + k - 2 >= 0 && ox + k - 2 < P.W) << k;
+      }
+#pragma unroll 1
+      for (int j = 0; j < P.gph; ++j) {
+        mbar_wait(bar_empty + 8 * s, eph);
+        const uint32_t stg = base + (uint32_t)(s * kWgStage + tid * 16);
+#pragma unroll
+        for (int u = 0; u < TPG; ++u) {
+          const int t = tap0 + j * TPG + u;
+          const int ky = t / KSZ, kx = t - ky * KSZ;
+          const bool valid = t < 25 && ((rmask >> ky) & (cmask >> kx) & 1u) != 0u;
+          const bf16* src = valid ? src0 + (ky - 2) * rowpitch + (kx - 2) * CX : P.x;
+#pragma unroll
+          for (int c = 0; c < XC; ++c) cp_async16(stg + (uint32_t)((u * XC + c) * BM * 16), src + c * 8, valid ? 16u : 0u);
+        }
+        cp_async_arrive(bar_full + 8 * s);
+        if (++s == WG_STAGES) { s = 0; eph ^= 1u; }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(BM, cp);
+      const uint64_t d0 = make_desc_mn(0);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), dlo0 = (uint32_t)d0;
+      int s = 0, lt = 0;
+      uint32_t fph = 0;
+      for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+        mbar_wait(bar_dyf + 8 * (lt & 1), (uint32_t)(lt >> 1) & 1u);
+        const uint32_t blo = dlo0 + (((dyb + (uint32_t)((lt & 1) * kWgDy)) & 0x3FFFFu) >> 4);
+#pragma unroll 1
+        for (int j = 0; j < P.gph; ++j) {
+          mbar_wait(bar_full + 8 * s, fph);
+          fence_async_smem();
+          tc_fence_after();
+          const uint32_t alo = dlo0 + (((base + (uint32_t)(s * kWgStage)) & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < BM / 16; ++kk)     // K step = 16 pixels = two 128-byte K blocks
+            mma_lh(tmem + (uint32_t)(j * cp), alo + (uint32_t)(kk * 16), dhi, blo + (uint32_t)(kk * 16), dhi, idesc, (lt | kk) == 0 ? 0u : 1u);
+          tc_commit(bar_empty + 8 * s);
+          if (++s == WG_STAGES) { s = 0; fph ^= 1u; }
+        }
+        tc_commit(bar_dye + 8 * (lt & 1));
+      }
+      tc_commit(bar_done);
+    }
+  } else {
+    // one epilogue at the very end: row r of group j = (tap tap0 + j TPG + r / CX, input channel r % CX)
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const bool any = blockIdx.x < P.tiles;   // a CTA without pixel tiles never ran an MMA: its accumulators are undefined
+    for (int j = 0; j < P.gph; ++j) {
+      const int t = tap0 + j * TPG + row / CX, ci = row % CX;
+      float* dst = P.partial + (((size_t)blockIdx.x * P.taps_padded + t) * CX + ci) * cp;
+      for (int c0 = 0; c0 < cp; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * cp + c0)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(dst + c0 + 4 * q) =
+              any ? make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  }
+}
+
+// dw (cout, cin, 5, 5) += sum over CTAs of partial[b][tap][ci][co]; fixed order = run-to-run identical
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nblocks, int taps_padded, int cx, int cp, int cout, int cin,
+                                    float* __restrict__ dw) {
+  // threads walk the partial's own order (co fastest): coalesced reads; the 25 * cin * cout scattered writes are few
+  const int total = KSZ * KSZ * cx * cp;
+  const size_t stride = (size_t)taps_padded * cx * cp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cp, ci = (i / cp) % cx, tap = i / (cp * cx);
+    if (co >= cout || ci >= cin) continue;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * stride + i];
+    dw[((size_t)co * cin + ci) * (KSZ * KSZ) + tap] += s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3'. wgrad of stage 1
+// M rows = the forward's K index k = ky * 16 + kx * 3 + c (80 used of 128), K = 128 conv pixels (BM / W full rows of one
+// frame), N = cp.  The im2col operand is built from an fp32 patch of the frame exactly like the forward's.
+struct Wgrad1Params {
+  const float* obs;    // [N][H][W][3]
+  const bf16* dy;      // [N][H][W][cp]
+  float* partial;      // [gridDim.x][128][cp]
+  int H, W, total, tiles, cp;
+};
+constexpr int kW1A = 16 * BM * 16;      // 32 KB: [16 chunks][128 px][16 B], chunks 10..15 stay zero
+constexpr int kW1Smem = 2 * kW1A + 2 * kWgDy + kPatchFloats * 4 + 8 * 10 + 16 + 256;
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv1_wgrad_kernel(const __grid_constant__ Wgrad1Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t dyb = base + 2 * kW1A;
+  float* patch = reinterpret_cast<float*>(gbase + 2 * kW1A + 2 * kWgDy);
+  const uint32_t bar_full = dyb + 2 * kWgDy + kPatchFloats * 4, bar_empty = bar_full + 16, bar_dyf = bar_empty + 16,
+                 bar_done = bar_dyf + 16, tmem_slot = bar_done + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + 2 * kW1A + 2 * kWgDy + kPatchFloats * 4 + 64);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cp = P.cp, DC = cp / 8;
+  for (int i = threadIdx.x; i < 2 * kW1A / 16; i += WG_THREADS) reinterpret_cast<uint4*>(gbase)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8 * s, 2 * PROD);   // each producer thread: one plain arrive (operand built) + one cp.async arrive (dy landed)
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(64));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const int R = BM / P.W;                          // conv rows per tile
+  const int rowf = P.W * 3, PR = R + 4, PW = rowf + 16;
+  const int tiles_per_frame = P.H / R;
+
+  if (warp < 4) {
+    const int tid = threadIdx.x;
+    const int lrow = tid / P.W, ox = tid - lrow * P.W;
+    const int r4 = rowf >> 2, n4 = PR * r4;
+    for (int i = tid; i < PR * 4; i += PROD) {
+      const int r = i >> 2, q = i & 3;
+      reinterpret_cast<float4*>(patch + r * PW + (q < 2 ? q * 4 : rowf + q * 4))[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
+      const int n = tile / tiles_per_frame, oy0 = (tile - n * tiles_per_frame) * R;
+      const int s = it & 1;
+      if (it >= 2) mbar_wait(bar_empty + 8 * s, (uint32_t)((it >> 1) - 1) & 1u);
+      // dy tile: rows of the tile are consecutive pixels of the frame
+      {
+        const size_t g = (size_t)tile * BM + tid;
+        const uint32_t dst = dyb + (uint32_t)(s * kWgDy + tid * 16);
+        for (int c = 0; c < DC; ++c) cp_async16(dst + (uint32_t)(c * BM * 16), P.dy + g * cp + c * 8, 16u);
+        cp_async_arrive(bar_full + 8 * s);
+      }
+      named_bar(1, PROD);
+      const float* frame = P.obs + (size_t)n * P.H * rowf;
+      for (int i = tid; i < n4; i += PROD) {
+        const int r = i / r4, c = i - r * r4, iy = oy0 - 2 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < P.H) {
+          v = __ldg(reinterpret_cast<const float4*>(frame + (size_t)iy * rowf) + c);
+          v = make_float4(v.x - 0.5f, v.y - 0.5f, v.z - 0.5f, v.w - 0.5f);
+        }
+        reinterpret_cast<float4*>(patch + r * PW + 8)[c] = v;
+      }
+      named_bar(1, PROD);
+      uint8_t* st = gbase + (size_t)s * kW1A;
+      // input pixel (ox - 2 + j) of patch row (lrow + ky) starts at float 8 + (ox - 2 + j) * 3 = 2 + 3 ox + 3 j
+      const float* prow = patch + lrow * PW + 2 + 3 * ox;
+#pragma unroll
+      for (int ky = 0; ky < KSZ; ++ky) {
+        float u[16];
+#pragma unroll
+        for (int e = 0; e < 15; ++e) u[e] = prow[ky * PW + e];
+        u[15] = 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(st + (size_t)(ky * 2) * BM * 16 + tid * 16);
+        dst[0] = make_uint4(pack2(u[0], u[1]), pack2(u[2], u[3]), pack2(u[4], u[5]), pack2(u[6], u[7]));
+        dst[BM] = make_uint4(pack2(u[8], u[9]), pack2(u[10], u[11]), pack2(u[12], u[13]), pack2(u[14], u[15]));
+      }
+      fence_async_smem();
+      mbar_arrive(bar_full + 8 * s);
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(BM, cp);
+      const uint64_t d0 = make_desc_mn(0);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), dlo0 = (uint32_t)d0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(bar_full + 8 * s, (uint32_t)(it >> 1) & 1u);
+        fence_async_smem();
+        tc_fence_after();
+        const uint32_t alo = dlo0 + (((base + (uint32_t)(s * kW1A)) & 0x3FFFFu) >> 4);
+        const uint32_t blo = dlo0 + (((dyb + (uint32_t)(s * kWgDy)) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < BM / 16; ++kk) mma_lh(tmem, alo + (uint32_t)(kk * 16), dhi, blo + (uint32_t)(kk * 16), dhi, idesc, (it | kk) == 0 ? 0u : 1u);
+        tc_commit(bar_empty + 8 * s);
+      }
+      tc_commit(bar_done);
+    }
+  } else {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const bool any = blockIdx.x < P.tiles;
+    float* dst = P.partial + ((size_t)blockIdx.x * BM + row) * cp;
+    for (int c0 = 0; c0 < cp; c0 += 16) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(dst + c0 + 4 * q) =
+            any ? make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]))
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64));
+  }
+}
+
+// dw1 (cout, 3, 5, 5) += sum_b partial[b][ky * 16 + kx * 3 + c][co]
+__global__ void wgrad1_reduce_kernel(const float* __restrict__ partial, int nblocks, int cp, int cout, float* __restrict__ dw) {
+  const int total = 80 * cp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cp, k = i / cp, ky = k >> 4, r = k & 15;
+    if (co >= cout || r >= 15) continue;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * BM * cp + i];
+    dw[((size_t)co * 3 + (r % 3)) * (KSZ * KSZ) + ky * KSZ + r / 3] += s;
+  }
+}
+
+}  // namespace cnn
+}  // namespace sd

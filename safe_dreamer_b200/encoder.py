@@ -39,6 +39,8 @@ class CnnEngine:
         self.embed_size = int(self.lib.sd_cnn_embed_size(self.h))
         self.max_frames, self.max_tape_frames = int(max_frames), int(max_tape_frames)
         self._wkey = None
+        self.tape_gen = 0
+        self._tape_obs, self._tape_frames = None, 0
 
     def __del__(self):
         try:
@@ -70,8 +72,25 @@ class CnnEngine:
         out = torch.empty(frames, self.embed_size, device=x.device, dtype=torch.float32)
         _lib.check(self.lib.sd_cnn_forward(self.h, frames, x.data_ptr(), out.data_ptr(), SD_FLAG_SAVE_TAPE if tape else 0,
                                            self.stream), "sd_cnn_forward")
-        self._tape_obs = x if tape else None
+        if tape:
+            self._tape_obs, self._tape_frames = x, frames   # sd_cnn_backward re-reads the frames (stage-1 weight gradient)
+            self.tape_gen += 1
         return out.reshape(*lead, self.embed_size)
+
+    def backward(self, d_embed, want_obs_grad=False, weight_grads=None):
+        """Backward of the last tape=True forward.  d_embed (..., embed_size) -> d_obs (frames, H, W, C) or None;
+        weight_grads: list of 3 * layers fp32 CUDA tensors (or None entries) the gradients are ACCUMULATED into."""
+        frames = self._tape_frames
+        g = d_embed.to(torch.float32).contiguous()
+        if g.numel() != frames * self.embed_size:
+            raise ValueError(f"d_embed has {g.numel()} elements, the taped forward produced {frames * self.embed_size}")
+        d_obs = torch.empty(frames, *self.frame, device=g.device, dtype=torch.float32) if want_obs_grad else None
+        arr = None
+        if weight_grads is not None:
+            arr = (C.c_void_p * len(weight_grads))(*[0 if t is None else t.data_ptr() for t in weight_grads])
+        _lib.check(self.lib.sd_cnn_backward(self.h, frames, g.data_ptr(), None if d_obs is None else d_obs.data_ptr(), arr,
+                                            self.stream), "sd_cnn_backward")
+        return d_obs
 
 
 class ConvEncoder(nn.Module):
@@ -135,5 +154,30 @@ class ConvEncoder(nn.Module):
         frames = int(obs.numel() // (self._input_shape[0] * self._input_shape[1] * self._input_shape[2]))
         need_grad = torch.is_grad_enabled() and (obs.requires_grad or any(t.requires_grad for t in self._tensors()))
         if need_grad:
-            raise NotImplementedError("ConvEncoder: backward is not wired yet")
+            return _EncoderFn.apply(self, obs, *self._tensors())
         return self._engine(frames, False).forward(obs)
+
+
+class _EncoderFn(torch.autograd.Function):
+    """sd_cnn_forward with a tape / sd_cnn_backward.  One tape per engine: a second taped forward before this one's backward
+    is detected (generation counter) instead of silently differentiating the wrong frames."""
+
+    @staticmethod
+    def forward(ctx, module, obs, *weights):
+        frames = int(obs.numel() // (module._input_shape[0] * module._input_shape[1] * module._input_shape[2]))
+        eng = module._engine(frames, True)
+        out = eng.forward(obs, tape=True)
+        ctx.eng, ctx.gen, ctx.obs_shape = eng, eng.tape_gen, tuple(obs.shape)
+        ctx.wshapes = [tuple(w.shape) for w in weights]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = ctx.eng
+        if eng.tape_gen != ctx.gen:
+            raise RuntimeError("ConvEncoder backward: another grad-enabled forward ran on this encoder since this one; "
+                               "call backward before the next forward (one activation tape per encoder)")
+        need_w = ctx.needs_input_grad[2:]
+        wg = [torch.zeros(s, device=g.device, dtype=torch.float32) if n else None for s, n in zip(ctx.wshapes, need_w)]
+        d_obs = eng.backward(g, want_obs_grad=ctx.needs_input_grad[1], weight_grads=wg if any(need_w) else None)
+        return (None, None if d_obs is None else d_obs.reshape(ctx.obs_shape), *wg)

@@ -52,3 +52,17 @@ def test_same_padding_and_pool_edges():
     # even kernel: one more pad cell after than before
     xp, (p0, p1) = CO._pad_same(np.zeros((1, 7, 7, 1), np.float32), 4)
     assert xp.shape == (1, 10, 10, 1) and (p0, p1) == (1, 1)
+
+
+def test_bf16_operand_model_stays_close_to_fp32(golden):
+    """oracle.round_bf16 models the CUDA path's bf16 convolution operands: nearest-even, idempotent, and the rounded encoder
+    stays within bf16 distance of the reference embedding (the GPU parity tests compare against this rounded oracle)."""
+    x = np.array([1.0, 1.00390625, 1.001953125, -3.1415927, 1e-30, 65504.0], np.float32)
+    r = CO.round_bf16(x)
+    np.testing.assert_array_equal(CO.round_bf16(r), r)
+    assert r[0] == 1.0 and r[1] == 1.0 and r[2] == 1.0          # ties / below half an ulp (2^-8) round to even
+    assert abs(r[3] + 3.140625) < 1e-6
+    P = CO.encoder_params([8, 12, 16, 16], 3, 5, seed=77 + 32)
+    emb = CO.encoder_fwd(P, _inputs(32, 2), rnd=CO.round_bf16)
+    d = np.abs(emb - golden["tiny/emb"])
+    assert d.max() <= 0.03 and d.mean() <= 3e-3
