@@ -40,10 +40,11 @@ __global__ void __launch_bounds__(256, 1) probe(int N, int layout, int reps, int
     while (!*stop && n < 2000000) { for (int j = 0; j < 2; ++j) dst[j * 128] = make_uint4(n, n, n, n); ++n; }
   }
   if (threadIdx.x == 32) {
-    const uint32_t idesc = make_idesc(128, N);
+    const uint32_t idesc = make_idesc(128, N) | (layout == 2 ? (1u << 15) | (1u << 16) : 0u);
     const uint32_t a = base, b = base + 32 * 1024;   // A: 128 x 64 bf16 (16 KB), B: up to 256 x 64 (32 KB)
     uint64_t dA, dB; uint32_t ka, kb;
     if (layout == 0) { dA = make_desc_sw128(a); dB = make_desc_sw128(b); ka = kb = 32 >> 4; }
+    else if (layout == 2) { dA = desc_nosw(a, 128, 2048); dB = desc_nosw(b, 128, 2048); ka = kb = 256 >> 4; }   // MN-major: [chunk][128 px][16 B], K = pixels
     else { const int lb = lboB ? lboB : N * 16; dA = desc_nosw(a, 128 * 16, 128); dB = desc_nosw(b, lb, 128); ka = (2 * 128 * 16) >> 4; kb = (2 * lb) >> 4; }
     uint32_t phase = 0;
     for (int rep = 0; rep < 3; ++rep) {
@@ -93,6 +94,12 @@ int main() {
       printf("no-swizzle N=%3d, %d accumulators round robin: issue %.1f, complete %.1f cycles/MMA (%.0f flop/clk)\n", N, nacc,
              (double)h[4] / reps, (double)h[5] / reps, 2.0 * 128 * N * 16 / ((double)h[5] / reps));
     }
+  for (int N : {32, 48, 64, 128}) {
+    probe<<<1, 256, 200 * 1024>>>(N, 2, reps, 4, 1, d);
+    long long h[6]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("error\n"); return 1; }
+    printf("MN-major (both operands) N=%3d: issue %.1f, complete %.1f cycles/MMA\n", N, (double)h[4] / reps, (double)h[5] / reps);
+  }
   struct V { int N, lbo, nacc, noise; const char* what; };
   const V vs[] = {{96, 0, 1, 0, "N=96 dense B"}, {96, 19200, 1, 0, "N=96 B rows 19200 B apart per K chunk"}, {96, 19200, 2, 0, "same, two accumulators"},
                   {96, 19200, 2, 1, "same + 4 warps storing to shared memory"}, {256, 0, 1, 1, "N=256 + store noise"}, {64, 0, 1, 1, "N=64 + store noise"}};

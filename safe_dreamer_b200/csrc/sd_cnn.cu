@@ -105,7 +105,7 @@ extern "C" int sd_cnn_create(const sd_cnn_config* cfg, sd_cnn** out) {
       if (l >= 1) ok = ok && alloc((void**)&h->dx[l], TF * 4 * px_out * h->CS[l] * sizeof(float));
       const int cin_pad = l == 0 ? 16 : h->CS[l];
       ok = ok && alloc((void**)&h->wT[l], (size_t)25 * h->CP[l] * cin_pad * sizeof(bf16));
-      const size_t wg = l == 0 ? (size_t)sd::cnn::BM * h->CP[l] : (size_t)(25 + 128 / h->CS[l]) * h->CS[l] * h->CP[l];
+      const size_t wg = l == 0 ? (size_t)sd::cnn::BM * h->CP[l] : (size_t)48 * h->CS[l] * h->CP[l];   // <= 48 (group, stacked tap) slots
       if (wg * h->sms > h->scratch_floats) h->scratch_floats = wg * h->sms;
     }
     const int cinp = l == 0 ? 16 : h->CS[l];
@@ -308,10 +308,24 @@ static int launch_dgrad_t(sd_cnn* h, const sd::cnn::DgradParams& p0, cudaStream_
   sd::cnn::conv_dgrad_kernel<CK, RES><<<grid, sd::cnn::DG_THREADS, L::total(p.cinp), st>>>(p);
   return SD_OK;
 }
+template <int CK, bool RES>
+static int launch_dgrad_patch_t(sd_cnn* h, const sd::cnn::DgradParams& p0, cudaStream_t st) {
+  static unsigned long long mask = 0;
+  using L = sd::cnn::DgradPatchSmem<CK, RES>;
+  SD_CUDA_TRY(ensure_smem(sd::cnn::conv_dgrad_patch_kernel<CK, RES>, sd::cnn::kConvSmemBudget, mask));
+  sd::cnn::DgradParams p = p0;
+  p.tiles = p.total / sd::cnn::BM;                 // 16 x 8 blocks: H % 16 == 0 and W % 8 == 0
+  const int grid = p.tiles < h->sms ? p.tiles : h->sms;
+  sd::cnn::conv_dgrad_patch_kernel<CK, RES><<<grid, sd::cnn::DG_THREADS, L::total(p.cinp), st>>>(p);
+  return SD_OK;
+}
 template <int CK>
 static int launch_dgrad(sd_cnn* h, const sd::cnn::DgradParams& p, cudaStream_t st) {
-  if (25 * (CK / 8) * p.cinp * 16 <= 100 * 1024) return launch_dgrad_t<CK, true>(h, p, st);
-  return launch_dgrad_t<CK, false>(h, p, st);
+  const bool res = 25 * (CK / 8) * p.cinp * 16 <= 100 * 1024;
+  static const bool no_patch = getenv("SD_CNN_NO_PATCH") != nullptr;   // A/B switch: stage every view separately
+  if (!no_patch && p.H % sd::cnn::PT_H == 0 && p.W % sd::cnn::PT_W == 0)
+    return res ? launch_dgrad_patch_t<CK, true>(h, p, st) : launch_dgrad_patch_t<CK, false>(h, p, st);
+  return res ? launch_dgrad_t<CK, true>(h, p, st) : launch_dgrad_t<CK, false>(h, p, st);
 }
 template <int CX>
 static int launch_wgrad(sd_cnn* h, const sd::cnn::WgradParams& p0, int* nblocks, cudaStream_t st) {
@@ -329,7 +343,52 @@ static int launch_wgrad(sd_cnn* h, const sd::cnn::WgradParams& p0, int* nblocks,
   if (gx > p.tiles) gx = p.tiles;
   if (gx < 1) gx = 1;
   *nblocks = gx;
+  static const bool trace2 = getenv("SD_TRACE_CNN") && atoi(getenv("SD_TRACE_CNN")) >= 2;
+  static long long* dbg = nullptr;
+  p.dbg = nullptr;
+  if (trace2) {
+    if (!dbg) cudaMalloc(&dbg, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
+    p.dbg = dbg;
+  }
   sd::cnn::conv_wgrad_kernel<CX><<<dim3(gx, halves), sd::cnn::WG_THREADS, sd::cnn::kWgSmem, st>>>(p);
+  if (trace2) {
+    long long v[16];
+    cudaMemcpyAsync(v, dbg, sizeof(v), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[SD_TRACE_CNN] wgrad CX=%d cp=%d grid %dx%d gph %d: producer total %lld empty-wait %lld dy-empty-wait %lld tiles %lld | mma total %lld full-wait %lld dy-full-wait %lld | epilogue waited %lld stored %lld\n",
+            CX, p.cp, gx, halves, gph, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[8], v[9]);
+  }
+  return SD_OK;
+}
+
+// patch-resident wgrad (CX = 32 / 64; maps W % 8 == 0 and H % 16 == 0 or H == 8 with an even frame count)
+template <int CX>
+static int launch_wgrad_patch(sd_cnn* h, const bf16* x, const bf16* dy, int frames, int H, int W, int cp, int cout, int cin, float* g_w,
+                              cudaStream_t st) {
+  using Cfg = sd::cnn::WgradPatchCfg<CX>;
+  static unsigned long long mask = 0;
+  SD_CUDA_TRY(ensure_smem(sd::cnn::conv_wgrad_patch_kernel<CX>, sd::cnn::kConvSmemBudget, mask));
+  sd::cnn::WgradPatchParams p;
+  p.x = x; p.dy = dy; p.partial = h->scratch;
+  p.H = H; p.W = W; p.cp = cp;
+  p.sh = H % 16 == 0 ? 16 : 8;
+  p.nsub = H % 16 == 0 ? 1 : 2;
+  p.patch_bytes = Cfg::patch_bytes(p.sh, p.nsub);
+  const int smem = Cfg::smem(p.sh, p.nsub);
+  if (smem > sd::cnn::kConvSmemBudget) return 1;    // caller falls back to the view-staging kernel
+  p.tiles = frames * H * W / sd::cnn::BM;
+  int gph = 512 / cp;
+  if (gph > Cfg::NGRP) gph = Cfg::NGRP;
+  const int halves = (Cfg::NGRP + gph - 1) / gph;
+  gph = (Cfg::NGRP + halves - 1) / halves;
+  p.gph = gph;
+  p.ngroups_padded = halves * gph;
+  int gx = h->sms / halves;
+  if (gx > p.tiles) gx = p.tiles;
+  if (gx < 1) gx = 1;
+  sd::cnn::conv_wgrad_patch_kernel<CX><<<dim3(gx, halves), sd::cnn::WG_THREADS, smem, st>>>(p);
+  sd::cnn::wgrad_patch_reduce_kernel<<<400, 256, 0, st>>>(h->scratch, gx, p.ngroups_padded * Cfg::TPG, Cfg::TPG, Cfg::NKG, CX, cp, cout, cin, g_w);
   return SD_OK;
 }
 
@@ -387,10 +446,15 @@ extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, floa
         sd::cnn::conv1_wgrad_kernel<<<nblocks, sd::cnn::WG_THREADS, sd::cnn::kW1Smem, st>>>(p);
         sd::cnn::wgrad1_reduce_kernel<<<20, 256, 0, st>>>(h->scratch, nblocks, cp, h->C[1], g_w);
       } else {
+        int rc = 1;
+        if (!getenv("SD_CNN_NO_PATCH") && (h->CS[l] == 32 || h->CS[l] == 64) && Wc % 8 == 0 && (Hc % 16 == 0 || (Hc == 8 && frames % 2 == 0)))
+          rc = h->CS[l] == 64 ? launch_wgrad_patch<64>(h, h->act[l], h->dy[l], frames, Hc, Wc, cp, h->C[l + 1], h->C[l], g_w, st)
+                              : launch_wgrad_patch<32>(h, h->act[l], h->dy[l], frames, Hc, Wc, cp, h->C[l + 1], h->C[l], g_w, st);
+        if (rc < 0) return rc;
+        if (rc == 1) {   // view-staging kernel (any map size)
         sd::cnn::WgradParams p;
         p.x = h->act[l]; p.dy = h->dy[l]; p.partial = h->scratch;
         p.H = Hc; p.W = Wc; p.total = total; p.tiles = (total + sd::cnn::BM - 1) / sd::cnn::BM; p.cp = cp;
-        int rc;
         switch (h->CS[l]) {
           case 16: rc = launch_wgrad<16>(h, p, &nblocks, st); break;
           case 32: rc = launch_wgrad<32>(h, p, &nblocks, st); break;
@@ -403,6 +467,7 @@ extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, floa
         const int halves = (ngrp + gph - 1) / gph;
         gph = (ngrp + halves - 1) / halves;
         sd::cnn::wgrad_reduce_kernel<<<400, 256, 0, st>>>(h->scratch, nblocks, halves * gph * tpg, h->CS[l], cp, h->C[l + 1], h->C[l], g_w);
+        }
       }
       launches += 2;
       mark("wgrad", l);

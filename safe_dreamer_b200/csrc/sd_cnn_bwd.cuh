@@ -46,11 +46,14 @@ __global__ void __launch_bounds__(256) norm_pool_bwd_kernel(const NormBwdParams 
     float p[U][CPL], d[U][CPL];
     uint32_t ar[U][CPL];
     int nn_[U], rem_[U];
+    const int n_first = px0 / P.HpWp, rem_first = px0 - n_first * P.HpWp;   // one division per U pixels
+    const int py_first = rem_first / P.Wp, pc_first = rem_first - py_first * P.Wp;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int px = px0 + u;
       const bool ok = act && px < P.total;
-      nn_[u] = px / P.HpWp; rem_[u] = px - nn_[u] * P.HpWp;
+      nn_[u] = n_first; rem_[u] = rem_first + u;
+      if (rem_[u] >= P.HpWp) { rem_[u] -= P.HpWp; ++nn_[u]; }
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         p[u][j] = 0.f; d[u][j] = 0.f; ar[u][j] = 0u;
@@ -72,13 +75,13 @@ __global__ void __launch_bounds__(256) norm_pool_bwd_kernel(const NormBwdParams 
       for (int j = 0; j < CPL; ++j) ss = fmaf(p[u][j], p[u][j], ss);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float rho = 1.f / sqrtf(ss * inv_c + kRmsEps);
+      const float rho = rsqrtf(ss * inv_c + kRmsEps);
       float nn[CPL], dn[CPL], dot = 0.f;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         nn[j] = p[u][j] * rho;
         const float m = nn[j] * g[j];
-        const float sg = 1.f / (1.f + __expf(-m));
+        const float sg = __fdividef(1.f, 1.f + __expf(-m));
         const float dm = d[u][j] * (sg * (1.f + m * (1.f - sg)));
         dg[j] = fmaf(dm, nn[j], dg[j]);
         dn[j] = dm * g[j];
@@ -87,7 +90,14 @@ __global__ void __launch_bounds__(256) norm_pool_bwd_kernel(const NormBwdParams 
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       dot *= inv_c;
-      const int py = rem_[u] / P.Wp, pxx = rem_[u] - py * P.Wp;
+      int py, pxx;
+      if (P.Wp >= U) {                 // U consecutive pixels cross at most one row end: no division per pixel
+        py = py_first; pxx = pc_first + u;
+        if (pxx >= P.Wp) { pxx -= P.Wp; ++py; }
+        if (rem_first + u >= P.HpWp) { py = 0; pxx = rem_first + u - P.HpWp; }
+      } else {
+        py = rem_[u] / P.Wp; pxx = rem_[u] - py * P.Wp;
+      }
       bf16* base = P.dy + ((size_t)(nn_[u] * 2 * Hp + 2 * py) * W + 2 * pxx) * P.cp + c0;
       float v[CPL];
 #pragma unroll
@@ -331,6 +341,228 @@ __global__ void __launch_bounds__(DG_THREADS, 1) conv_dgrad_kernel(const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 2b. dgrad, patch-resident
+// The 25 shifted views of dy overlap almost completely, so for maps with H % 16 == 0 and W % 8 == 0 a tile is a 16 x 8 pixel
+// block and ONE (16+4) x (8+4) halo patch of dy is staged per tile ([chunk][240 patch pixels][16 B], zero filled outside the
+// map); the view of tap (ky, kx) is the patch read through a shifted descriptor: 8 consecutive pixels of a patch row are
+// one 128-byte core matrix, SBO = the patch row pitch (192 B), LBO = the chunk plane (3840 B), start += ((4-ky) 12 + 4-kx) 16.
+// 12x less shared-memory ingest than staging every view (23 KB instead of 300 KB per tile at 48 channels).
+constexpr int PT_W = 8, PT_H = 16, PP_W = PT_W + 4, PP_H = PT_H + 4, PP = PP_W * PP_H;   // 240 patch pixels
+template <int CK, bool RES>
+struct DgradPatchSmem {
+  static constexpr int KC = CK / 8;
+  static constexpr int kPatch = KC * PP * 16;
+  static constexpr int kBt = KC * 64 * 16;
+  static constexpr int VPS = 2;                                    // streamed weight tiles per ring stage
+  static constexpr int NG = (25 + VPS - 1) / VPS;
+  static constexpr int kStage = VPS * kBt;
+  static constexpr int STAGES = RES ? 0 : 6;
+  static constexpr int kFixed = 8 * (2 * 6 + 8) + 16 + 256;
+  static int resident_bytes(int cinp) { return RES ? 25 * KC * cinp * 16 : 0; }
+  static int total(int cinp) { return kFixed + resident_bytes(cinp) + 2 * kPatch + STAGES * kStage; }
+};
+
+template <int CK, bool RES>
+__global__ void __launch_bounds__(DG_THREADS, 1) conv_dgrad_patch_kernel(const __grid_constant__ DgradParams P) {
+  using L = DgradPatchSmem<CK, RES>;
+  constexpr int KC = L::KC, STAGES = L::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int cinp = P.cinp;
+  const int resB = RES ? 25 * KC * cinp * 16 : 0;
+  const uint32_t patch0 = base + (uint32_t)resB, ring = patch0 + 2 * L::kPatch;
+  const int off_bar = resB + 2 * L::kPatch + STAGES * L::kStage;
+  const uint32_t bar_full = base + (uint32_t)off_bar, bar_empty = bar_full + 48, bar_pf = bar_empty + 48, bar_pe = bar_pf + 16,
+                 bar_accf = bar_pe + 16, bar_free = bar_accf + 16, tmem_slot = bar_free + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 160);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (RES) {
+    const int n16 = 25 * KC * cinp;
+    for (int i = threadIdx.x; i < n16; i += DG_THREADS) {
+      const int row = i % cinp, c = (i / cinp) % KC, tap = i / (cinp * KC);
+      reinterpret_cast<uint4*>(gbase)[(size_t)c * 25 * cinp + tap * cinp + row] = __ldg(reinterpret_cast<const uint4*>(P.wT) + i);
+    }
+    fence_async_smem();
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 6; ++s) {
+      mbar_init(bar_full + 8 * s, PROD);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_pf + 8 * s, PROD);
+      mbar_init(bar_pe + 8 * s, 1);
+      mbar_init(bar_accf + 8 * s, 1);
+      mbar_init(bar_free + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const int tx_n = P.W / PT_W, tiles_per_img = tx_n * (P.H / PT_H);
+
+  if (warp < 4) {
+    const int tid = threadIdx.x;
+    constexpr int NI = (KC * PP + PROD - 1) / PROD;       // patch items (pixel, chunk) per thread
+    int item[NI];                                          // (chunk << 16) | (patch row << 8) | patch column; -1 = none
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * PROD;
+      const int c = i / PP, pp = i - c * PP, pr = pp / PP_W, pc = pp - pr * PP_W;
+      item[k] = i < KC * PP ? (c << 16) | (pr << 8) | pc : -1;
+    }
+    const int wrow = tid & 63, wc0 = tid >> 6;
+    int s = 0, lt = 0;
+    uint32_t eph = 1;
+    auto load_patch = [&](int tile, int pb) {
+      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img, ty = r / tx_n, tx = r - ty * tx_n;
+      const bf16* img = P.dy + (size_t)n * P.H * P.W * CK;
+      const uint32_t dst0 = patch0 + (uint32_t)(pb * L::kPatch);
+#pragma unroll
+      for (int k = 0; k < NI; ++k) {
+        if (item[k] < 0) continue;
+        const int c = item[k] >> 16, pr = (item[k] >> 8) & 0xff, pc = item[k] & 0xff;
+        const int gy = ty * PT_H - 2 + pr, gx = tx * PT_W - 2 + pc;
+        const bool valid = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
+        const bf16* src = valid ? img + ((size_t)gy * P.W + gx) * CK + c * 8 : P.dy;
+        cp_async16(dst0 + (uint32_t)((c * PP + pr * PP_W + pc) * 16), src, valid ? 16u : 0u);
+      }
+      cp_async_arrive(bar_pf + 8 * pb);
+    };
+    if (blockIdx.x < P.tiles) load_patch(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+      const int nt = tile + gridDim.x;
+      if (RES) {
+        if (nt < P.tiles) {
+          mbar_wait(bar_pe + 8 * ((lt + 1) & 1), (uint32_t)((((lt + 1) >> 1) & 1) ^ 1));
+          load_patch(nt, (lt + 1) & 1);
+        }
+      } else {
+#pragma unroll 1
+        for (int vg = 0; vg < L::NG; ++vg) {
+          if (vg == 4 && nt < P.tiles) {           // next patch goes out while this tile's weights still stream
+            mbar_wait(bar_pe + 8 * ((lt + 1) & 1), (uint32_t)((((lt + 1) >> 1) & 1) ^ 1));
+            load_patch(nt, (lt + 1) & 1);
+          }
+          mbar_wait(bar_empty + 8 * s, eph);
+          if (wrow < cinp) {
+#pragma unroll
+            for (int u = 0; u < L::VPS; ++u) {
+              const int t = vg * L::VPS + u;
+              if (t < 25) {
+                const uint4* w = reinterpret_cast<const uint4*>(P.wT) + (size_t)(t * KC + wc0) * cinp + wrow;
+                const uint32_t dst = ring + (uint32_t)(s * L::kStage + u * L::kBt + wrow * 16 + wc0 * cinp * 16);
+#pragma unroll
+                for (int c = 0; c < KC / 2; ++c) cp_async16(dst + (uint32_t)(c * 2 * cinp * 16), w + (size_t)c * 2 * cinp, 16u);
+              }
+            }
+          }
+          cp_async_arrive(bar_full + 8 * s);
+          if (++s == STAGES) { s = 0; eph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(BM, cinp);
+      const uint64_t dA0 = make_desc_nosw(0, PP * 16, PP_W * 16);
+      const uint32_t ldB = (uint32_t)((RES ? 25 : 1) * cinp * 16);
+      const uint64_t dB0 = make_desc_nosw(0, ldB, 128);
+      const uint32_t ahi = (uint32_t)(dA0 >> 32), bhi = (uint32_t)(dB0 >> 32), alo0 = (uint32_t)dA0, blo0 = (uint32_t)dB0;
+      const uint32_t kstepB = (2 * ldB) >> 4, blo_res = (base & 0x3FFFFu) >> 4;
+      int lt = 0, s = 0;
+      uint32_t fph = 0;
+      for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+        const int set = lt & 1, pb = lt & 1;
+        if (lt >= 2) mbar_wait(bar_free + 8 * set, (uint32_t)((lt >> 1) - 1) & 1u);
+        mbar_wait(bar_pf + 8 * pb, (uint32_t)(lt >> 1) & 1u);
+        fence_async_smem();
+        tc_fence_after();
+        const uint32_t acc = tmem + (uint32_t)(set * 64);
+        const uint32_t plo = alo0 + (((patch0 + (uint32_t)(pb * L::kPatch)) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int vg = 0; vg < L::NG; ++vg) {
+          uint32_t stlo = 0;
+          if (!RES) {
+            mbar_wait(bar_full + 8 * s, fph);
+            fence_async_smem();
+            tc_fence_after();
+            stlo = ((ring + (uint32_t)(s * L::kStage)) & 0x3FFFFu) >> 4;
+          }
+#pragma unroll
+          for (int u = 0; u < L::VPS; ++u) {
+            const int t = vg * L::VPS + u;
+            if (t >= 25) break;
+            const int ky = t / KSZ, kx = t - ky * KSZ;
+            const uint32_t alo = plo + (uint32_t)((4 - ky) * PP_W + (4 - kx));
+            const uint32_t blo = blo0 + (RES ? blo_res + (uint32_t)(t * cinp) : stlo + (uint32_t)((u * L::kBt) >> 4));
+#pragma unroll
+            for (int kk = 0; kk < CK / 16; ++kk)
+              mma_lh(acc, alo + (uint32_t)(kk * 2 * PP), ahi, blo + kk * kstepB, bhi, idesc, (t | kk) == 0 ? 0u : 1u);
+          }
+          if (!RES) {
+            tc_commit(bar_empty + 8 * s);
+            if (++s == STAGES) { s = 0; fph ^= 1u; }
+          }
+        }
+        tc_commit(bar_pe + 8 * pb);
+        tc_commit(bar_accf + 8 * set);
+      }
+    }
+  } else {
+    // epilogue: TMEM lane r = tile pixel (r / 8, r % 8); fp32 NHWC store of the first nwrite channels (row stride ldx)
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    const int set = warp >= 9 ? 1 : 0;
+    for (int lt = set, tile = blockIdx.x + set * gridDim.x; tile < P.tiles; tile += 2 * gridDim.x, lt += 2) {
+      mbar_wait(bar_accf + 8 * set, (uint32_t)(lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tm = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * 64);
+      float v[64];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16)
+        if (c0 < cinp) {
+          uint32_t r[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(tm + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[c0 + i] = __uint_as_float(r[i]);
+        }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_free + 8 * set);
+      const int n = tile / tiles_per_img, rr = tile - n * tiles_per_img, ty = rr / tx_n, tx = rr - ty * tx_n;
+      const size_t g = ((size_t)n * P.H + ty * PT_H + (row >> 3)) * P.W + tx * PT_W + (row & 7);
+      float* dst = P.dx + g * P.ldx;
+      if ((P.nwrite & 3) == 0 && (P.ldx & 3) == 0) {
+#pragma unroll
+        for (int c = 0; c < 64; c += 4)
+          if (c < P.nwrite) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c < P.nwrite) dst[c] = v[c];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
+  }
+}
+
 // w (cout, cin, 5, 5) fp32 -> wT [25][ckp/8][cinp][8] bf16: element (tap, k = co, row = ci)
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int ckp, int cinp, bf16* __restrict__ wT) {
   const int total = KSZ * KSZ * ckp * cinp;
@@ -356,6 +588,7 @@ struct WgradParams {
   int H, W, total, tiles, cp;
   int gph;             // tap groups per CTA (TMEM columns = gph * cp <= 512)
   int taps_padded;     // halves * gph * (128 / CX)
+  long long* dbg;      // diagnostic (SD_TRACE_CNN=2)
 };
 
 constexpr int WG_THREADS = 288;    // warps 0-3 producers, 4 MMA, 5-8 epilogue (once, at the end)
@@ -404,12 +637,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
     int s = 0, lt = 0;
     uint32_t eph = 1;
     const int rowpitch = P.W * CX;
+    const bool dbg = P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+    long long t_empty = 0, t_dye = 0, c0 = 0, t0 = clock64();
     for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
       const int g = tile * BM + tid;
       const bool ok = g < P.total;
       const int n = g / HW, rem = g - n * HW, oy = rem / P.W, ox = rem - oy * P.W;
       // dy tile (the N operand of every group of this pixel tile)
+      if (dbg) c0 = clock64();
       mbar_wait(bar_dye + 8 * (lt & 1), (uint32_t)(((lt >> 1) & 1) ^ 1));
+      if (dbg) t_dye += clock64() - c0;
       {
         const bf16* src = ok ? P.dy + (size_t)g * cp : P.dy;
         const uint32_t dst = dyb + (uint32_t)((lt & 1) * kWgDy + tid * 16);
@@ -425,7 +662,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
       }
 #pragma unroll 1
       for (int j = 0; j < P.gph; ++j) {
+        if (dbg) c0 = clock64();
         mbar_wait(bar_empty + 8 * s, eph);
+        if (dbg) t_empty += clock64() - c0;
         const uint32_t stg = base + (uint32_t)(s * kWgStage + tid * 16);
 #pragma unroll
         for (int u = 0; u < TPG; ++u) {
@@ -440,6 +679,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
         if (++s == WG_STAGES) { s = 0; eph ^= 1u; }
       }
     }
+    if (dbg) { P.dbg[0] = clock64() - t0; P.dbg[1] = t_empty; P.dbg[2] = t_dye; P.dbg[3] = lt; }
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_mn(BM, cp);
@@ -447,12 +687,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
       const uint32_t dhi = (uint32_t)(d0 >> 32), dlo0 = (uint32_t)d0;
       int s = 0, lt = 0;
       uint32_t fph = 0;
+      const bool dbg = P.dbg && blockIdx.x == 0 && blockIdx.y == 0;
+      long long t_full = 0, t_dyf = 0, c0 = 0, t0 = clock64();
       for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+        if (dbg) c0 = clock64();
         mbar_wait(bar_dyf + 8 * (lt & 1), (uint32_t)(lt >> 1) & 1u);
+        if (dbg) t_dyf += clock64() - c0;
         const uint32_t blo = dlo0 + (((dyb + (uint32_t)((lt & 1) * kWgDy)) & 0x3FFFFu) >> 4);
 #pragma unroll 1
         for (int j = 0; j < P.gph; ++j) {
+          if (dbg) c0 = clock64();
           mbar_wait(bar_full + 8 * s, fph);
+          if (dbg) t_full += clock64() - c0;
           fence_async_smem();
           tc_fence_after();
           const uint32_t alo = dlo0 + (((base + (uint32_t)(s * kWgStage)) & 0x3FFFFu) >> 4);
@@ -465,16 +711,211 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
         tc_commit(bar_dye + 8 * (lt & 1));
       }
       tc_commit(bar_done);
+      if (dbg) { P.dbg[4] = clock64() - t0; P.dbg[5] = t_full; P.dbg[6] = t_dyf; }
     }
   } else {
     // one epilogue at the very end: row r of group j = (tap tap0 + j TPG + r / CX, input channel r % CX)
     const int quarter = warp & 3, row = quarter * 32 + lane;
+    const long long e0 = clock64();
     mbar_wait(bar_done, 0);
+    const long long e1 = clock64();
     tc_fence_after();
     const bool any = blockIdx.x < P.tiles;   // a CTA without pixel tiles never ran an MMA: its accumulators are undefined
     for (int j = 0; j < P.gph; ++j) {
       const int t = tap0 + j * TPG + row / CX, ci = row % CX;
       float* dst = P.partial + (((size_t)blockIdx.x * P.taps_padded + t) * CX + ci) * cp;
+      for (int c0 = 0; c0 < cp; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * cp + c0)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(dst + c0 + 4 * q) =
+              any ? make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]))
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 5 * 32) { P.dbg[8] = e1 - e0; P.dbg[9] = clock64() - e1; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 3b. wgrad, patch-resident
+// Same idea as the patch dgrad: a tile is a 16 x 8 pixel block (or two 8 x 8 maps) and the x views of all taps are windows
+// of ONE halo patch of x, read through shifted MN-major descriptors (K block = 8 pixels of a tile row, LBO = the patch row
+// pitch 192 B; MN block = 8 channels, SBO = the chunk plane).  An M = 128 operand stacks TPG = 128 / CX vertically
+// adjacent taps (ky0 .. ky0 + TPG - 1, same kx): MN block b must sit at start + b * PLANE, so the patch is staged TPG
+// times, copy j at + j * (XC * PLANE - 192): through the same descriptor, copy j shows the window one patch row further
+// down.  Taps with ky > 4 are padding (they read zero rows; their accumulator rows are never stored).  Per tile this moves
+// ~80 KB into shared memory instead of ~240 KB, and every cp.async instruction reads consecutive 16-byte pieces (the old
+// thread-per-pixel gather touched 32 cache lines per instruction and was bound by that).
+template <int CX>
+struct WgradPatchCfg {
+  static constexpr int XC = CX / 8, TPG = 128 / CX, NKG = (KSZ + TPG - 1) / TPG;     // tap groups per kx
+  static constexpr int NGRP = KSZ * NKG;                                              // 15 (CX = 64) / 10 (CX = 32)
+  static constexpr int SBR(int sh) { return sh + TPG + 4; }                           // patch rows per sub-block (zero rows below the halo)
+  static constexpr int kDyPlane = BM * 16 + 16;
+  static constexpr int kDy = 8 * kDyPlane;
+  static int plane(int sh, int nsub) { return nsub * (sh + TPG + 4) * PP_W * 16 + 16; }
+  static int patch_bytes(int sh, int nsub) { return ((TPG - 1) * (XC * plane(sh, nsub) - PP_W * 16) + XC * plane(sh, nsub) + 127) / 128 * 128; }
+  static int smem(int sh, int nsub) { return 2 * patch_bytes(sh, nsub) + 2 * kDy + 8 * 12 + 16 + 256; }
+};
+
+struct WgradPatchParams {
+  const bf16* x;       // [N][H][W][CX]
+  const bf16* dy;      // [N][H][W][cp]
+  float* partial;      // [gridDim.x][taps_padded][CX][cp]: tap index here = group * TPG + j, see wgrad_patch_reduce_kernel
+  int H, W, tiles, cp, sh, nsub;   // tile = nsub sub-blocks of sh rows x 8 columns (16 x 1 block or 8 x 2 maps)
+  int gph;             // groups per CTA (blockIdx.y picks the range)
+  int ngroups_padded;  // gridDim.y * gph
+  int patch_bytes;     // one patch buffer: (TPG - 1) * copy stride + XC * plane, rounded up to 128
+};
+
+template <int CX>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const __grid_constant__ WgradPatchParams P) {
+  using Cfg = WgradPatchCfg<CX>;
+  constexpr int XC = Cfg::XC, TPG = Cfg::TPG, NKG = Cfg::NKG;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const int sh = P.sh, nsub = P.nsub, sbr = sh + TPG + 4;
+  const int plane = nsub * sbr * PP_W * 16 + 16;               // + 16: consecutive chunks land in different banks
+  const int copy_stride = XC * plane - PP_W * 16;
+  const uint32_t dyb = base + 2 * (uint32_t)P.patch_bytes;
+  const uint32_t bar_pf = dyb + 2 * Cfg::kDy, bar_pe = bar_pf + 16, bar_done = bar_pe + 16, tmem_slot = bar_done + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + 2 * P.patch_bytes + 2 * Cfg::kDy + 48);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cp = P.cp, DC = cp / 8;
+  // zero rows / padding are never written by the loads: clear both buffers once
+  for (int i = threadIdx.x; i < 2 * P.patch_bytes / 16; i += WG_THREADS) reinterpret_cast<uint4*>(gbase)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_async_smem();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_pf + 8 * s, PROD);
+      mbar_init(bar_pe + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const int tx_n = P.W / PT_W;
+  const int tiles_per_img = nsub == 1 ? tx_n * (P.H / sh) : tx_n;     // nsub == 2: a tile covers the same column block of two maps
+  const int g0 = blockIdx.y * P.gph;
+
+  if (warp < 4) {
+    const int tid = threadIdx.x;
+    const int prow = sh + 4, npx = nsub * prow * PP_W;                 // loaded patch pixels
+    const int nitems = npx * XC, ndy = BM * DC;
+    // this thread's items do not depend on the tile: (destination, source offset from the tile origin, patch row / column)
+    constexpr int NI = 18, ND = 8;
+    int x_dst[NI], x_src[NI], x_rc[NI], d_dst[ND], d_src[ND];
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * PROD;
+      const int c = i % XC, pp = i / XC, sb = pp / (prow * PP_W), q = pp - sb * (prow * PP_W), pr = q / PP_W, pc = q - pr * PP_W;
+      x_dst[k] = c * plane + ((sb * sbr + pr) * PP_W + pc) * 16;
+      x_src[k] = ((sb * P.H + pr) * P.W + pc) * CX + c * 8;
+      x_rc[k] = i < nitems ? (pr << 8) | pc : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      const int i = tid + k * PROD;
+      const int c = i % DC, p = i / DC, sb = p / (sh * PT_W), q = p - sb * (sh * PT_W), y = q >> 3, xx = q & 7;
+      d_dst[k] = i < ndy ? c * Cfg::kDyPlane + p * 16 : -1;
+      d_src[k] = ((sb * P.H + y) * P.W + xx) * cp + c * 8;
+    }
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+      const int pb = lt & 1;
+      mbar_wait(bar_pe + 8 * pb, (uint32_t)(((lt >> 1) & 1) ^ 1));
+      int n0, ty, tx;
+      if (nsub == 1) { n0 = tile / tiles_per_img; const int r = tile - n0 * tiles_per_img; ty = r / tx_n; tx = r - ty * tx_n; }
+      else { const int pair = tile / tiles_per_img; tx = tile - pair * tiles_per_img; ty = 0; n0 = pair * 2; }
+      const int gy0 = ty * sh - 2, gx0 = tx * PT_W - 2;
+      uint32_t rmask = 0, cmask = 0;
+      for (int k = 0; k < prow; ++k) rmask |= (uint32_t)(gy0 + k >= 0 && gy0 + k < P.H) << k;
+#pragma unroll
+      for (int k = 0; k < PP_W; ++k) cmask |= (uint32_t)(gx0 + k >= 0 && gx0 + k < P.W) << k;
+      const uint32_t pdst = base + (uint32_t)(pb * P.patch_bytes);
+      const bf16* xorg = P.x + (((long long)n0 * P.H + gy0) * P.W + gx0) * CX;   // may point before the map: only valid items are read
+      // x patch: item = (patch pixel, chunk), chunk fastest: a warp instruction reads 512 consecutive bytes of a row
+#pragma unroll
+      for (int k = 0; k < NI; ++k) {
+        if (x_rc[k] < 0) continue;
+        const bool valid = ((rmask >> (x_rc[k] >> 8)) & (cmask >> (x_rc[k] & 0xff)) & 1u) != 0u;
+        const bf16* src = valid ? xorg + x_src[k] : P.x;
+#pragma unroll
+        for (int j = 0; j < TPG; ++j) cp_async16(pdst + (uint32_t)(x_dst[k] + j * copy_stride), src, valid ? 16u : 0u);
+      }
+      // dy tile: row p = tile pixel (p / 8, p % 8) of sub-block p / (8 sh)
+      const bf16* dorg = P.dy + (((size_t)n0 * P.H + ty * sh) * P.W + tx * PT_W) * cp;
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        if (d_dst[k] >= 0) cp_async16(dyb + (uint32_t)(pb * Cfg::kDy + d_dst[k]), dorg + d_src[k], 16u);
+      cp_async_arrive(bar_pf + 8 * pb);
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(BM, cp);
+      const uint64_t dA0 = make_desc_nosw(0, PP_W * 16, (uint32_t)plane), dB0 = make_desc_nosw(0, 128, Cfg::kDyPlane);
+      const uint32_t ahi = (uint32_t)(dA0 >> 32), bhi = (uint32_t)(dB0 >> 32), alo0 = (uint32_t)dA0, blo0 = (uint32_t)dB0;
+      // per K step (two tile rows): patch pixel offset of its first row; per group: (ky0, kx) -> ky0 * 12 + kx.  Nothing in the
+      // issue loop below divides: one thread issues every MMA and each of its instructions costs ~10 cycles
+      uint32_t rowoff[BM / 16];
+#pragma unroll
+      for (int kk = 0; kk < BM / 16; ++kk) {
+        const int r2 = 2 * kk, sb = r2 / sh, y = r2 - sb * sh;
+        rowoff[kk] = (uint32_t)((sb * sbr + y) * PP_W);
+      }
+      const int kx_first = g0 / NKG, kg_first = g0 - kx_first * NKG;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
+        const int pb = lt & 1;
+        mbar_wait(bar_pf + 8 * pb, (uint32_t)(lt >> 1) & 1u);
+        fence_async_smem();
+        tc_fence_after();
+        const uint32_t plo = alo0 + (((base + (uint32_t)(pb * P.patch_bytes)) & 0x3FFFFu) >> 4);
+        const uint32_t blo = blo0 + (((dyb + (uint32_t)(pb * Cfg::kDy)) & 0x3FFFFu) >> 4);
+        const uint32_t first = lt == 0 ? 0u : 1u;
+        int kx = kx_first, kg = kg_first;
+        uint32_t acc = tmem;
+#pragma unroll 1
+        for (int j = 0; j < P.gph && kx < KSZ; ++j, acc += (uint32_t)cp) {
+          const uint32_t a = plo + (uint32_t)(kg * TPG * PP_W + kx);
+#pragma unroll
+          for (int kk = 0; kk < BM / 16; ++kk) mma_lh(acc, a + rowoff[kk], ahi, blo + (uint32_t)(kk * 16), bhi, idesc, kk == 0 ? first : 1u);
+          if (++kg == NKG) { kg = 0; ++kx; }
+        }
+        tc_commit(bar_pe + 8 * pb);
+      }
+      tc_commit(bar_done);
+    }
+  } else {
+    const int quarter = warp & 3, row = quarter * 32 + lane;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const bool any = blockIdx.x < P.tiles;
+    for (int j = 0; j < P.gph; ++j) {
+      const int gi = g0 + j;
+      if (gi / NKG >= KSZ) break;
+      // accumulator row = (stacked tap row / CX, channel row % CX); slot = group * TPG + stacked tap
+      float* dst = P.partial + (((size_t)blockIdx.x * P.ngroups_padded * TPG + (size_t)gi * TPG + row / CX) * CX + row % CX) * cp;
       for (int c0 = 0; c0 < cp; c0 += 16) {
         uint32_t r[16];
         asm volatile(
@@ -496,6 +937,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+  }
+}
+
+// partial slot (group gi = kx * NKG + kg, stacked tap j) holds tap (ky = kg * TPG + j, kx); dw (cout, cin, 5, 5) += sum_b
+__global__ void wgrad_patch_reduce_kernel(const float* __restrict__ partial, int nblocks, int slots_padded, int tpg, int nkg, int cx, int cp,
+                                          int cout, int cin, float* __restrict__ dw) {
+  const int total = KSZ * nkg * tpg * cx * cp;
+  const size_t stride = (size_t)slots_padded * cx * cp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cp, ci = (i / cp) % cx, slot = i / (cp * cx);
+    const int gi = slot / tpg, j = slot - gi * tpg, kx = gi / nkg, ky = (gi - kx * nkg) * tpg + j;
+    if (co >= cout || ci >= cin || ky >= KSZ) continue;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * stride + i];
+    dw[((size_t)co * cin + ci) * (KSZ * KSZ) + ky * KSZ + kx] += s;
   }
 }
 
