@@ -387,7 +387,22 @@ static int launch_wgrad_patch(sd_cnn* h, const bf16* x, const bf16* dy, int fram
   int gx = h->sms / halves;
   if (gx > p.tiles) gx = p.tiles;
   if (gx < 1) gx = 1;
-  sd::cnn::conv_wgrad_patch_kernel<CX><<<dim3(gx, halves), sd::cnn::WG_THREADS, smem, st>>>(p);
+  static const bool trace2 = getenv("SD_TRACE_CNN") && atoi(getenv("SD_TRACE_CNN")) >= 2;
+  static long long* dbg = nullptr;
+  p.dbg = nullptr;
+  if (trace2) {
+    if (!dbg) cudaMalloc(&dbg, 16 * sizeof(long long));
+    cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), st);
+    p.dbg = dbg;
+  }
+  sd::cnn::conv_wgrad_patch_kernel<CX><<<dim3(gx, halves), sd::cnn::WGP_THREADS, smem, st>>>(p);
+  if (trace2) {
+    long long v[16];
+    cudaMemcpyAsync(v, dbg, sizeof(v), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[SD_TRACE_CNN] wgrad-patch CX=%d cp=%d grid %dx%d gph %d smem %d: producer total %lld patch-empty-wait %lld tiles %lld | issuer0 total %lld patch-full-wait %lld\n",
+            CX, cp, gx, halves, gph, smem, v[0], v[1], v[3], v[4], v[5]);
+  }
   sd::cnn::wgrad_patch_reduce_kernel<<<400, 256, 0, st>>>(h->scratch, gx, p.ngroups_padded * Cfg::TPG, Cfg::TPG, Cfg::NKG, CX, cp, cout, cin, g_w);
   return SD_OK;
 }
@@ -443,7 +458,7 @@ extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, floa
         p.obs = h->tape_obs; p.dy = h->dy[0]; p.partial = h->scratch;
         p.H = Hc; p.W = Wc; p.total = total; p.tiles = total / sd::cnn::BM; p.cp = cp;
         nblocks = p.tiles < h->sms ? p.tiles : h->sms;
-        sd::cnn::conv1_wgrad_kernel<<<nblocks, sd::cnn::WG_THREADS, sd::cnn::kW1Smem, st>>>(p);
+        sd::cnn::conv1_wgrad_kernel<<<nblocks, sd::cnn::W1_THREADS, sd::cnn::kW1Smem, st>>>(p);
         sd::cnn::wgrad1_reduce_kernel<<<20, 256, 0, st>>>(h->scratch, nblocks, cp, h->C[1], g_w);
       } else {
         int rc = 1;

@@ -348,10 +348,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) conv_dgrad_kernel(const __grid_
 // one 128-byte core matrix, SBO = the patch row pitch (192 B), LBO = the chunk plane (3840 B), start += ((4-ky) 12 + 4-kx) 16.
 // 12x less shared-memory ingest than staging every view (23 KB instead of 300 KB per tile at 48 channels).
 constexpr int PT_W = 8, PT_H = 16, PP_W = PT_W + 4, PP_H = PT_H + 4, PP = PP_W * PP_H;   // 240 patch pixels
+constexpr int PPL = PP + 1;   // chunk plane in 16-byte units: + 1 so that the chunks of one pixel fall into different banks
 template <int CK, bool RES>
 struct DgradPatchSmem {
   static constexpr int KC = CK / 8;
-  static constexpr int kPatch = KC * PP * 16;
+  static constexpr int kPatch = (KC * PPL * 16 + 127) / 128 * 128;
   static constexpr int kBt = KC * 64 * 16;
   static constexpr int VPS = 2;                                    // streamed weight tiles per ring stage
   static constexpr int NG = (25 + VPS - 1) / VPS;
@@ -410,32 +411,36 @@ __global__ void __launch_bounds__(DG_THREADS, 1) conv_dgrad_patch_kernel(const _
 
   if (warp < 4) {
     const int tid = threadIdx.x;
-    constexpr int NI = (KC * PP + PROD - 1) / PROD;       // patch items (pixel, chunk) per thread
-    int item[NI];                                          // (chunk << 16) | (patch row << 8) | patch column; -1 = none
+    constexpr int NI = (KC * PP + PROD - 1) / PROD;       // patch items (pixel, chunk) per thread, chunk fastest
+    int it_dst[NI], it_src[NI], it_rc[NI];                // destination, source offset from the patch origin, (row << 8 | column); -1 = none
 #pragma unroll
     for (int k = 0; k < NI; ++k) {
       const int i = tid + k * PROD;
-      const int c = i / PP, pp = i - c * PP, pr = pp / PP_W, pc = pp - pr * PP_W;
-      item[k] = i < KC * PP ? (c << 16) | (pr << 8) | pc : -1;
+      const int c = i % KC, pp = i / KC, pr = pp / PP_W, pc = pp - pr * PP_W;
+      it_dst[k] = (c * PPL + pr * PP_W + pc) * 16;
+      it_src[k] = (pr * P.W + pc) * CK + c * 8;
+      it_rc[k] = i < KC * PP ? (pr << 8) | pc : -1;
     }
     const int wrow = tid & 63, wc0 = tid >> 6;
     int s = 0, lt = 0;
     uint32_t eph = 1;
+    const int ty_n = P.H / PT_H;
     auto load_patch = [&](int tile, int pb) {
       const int n = tile / tiles_per_img, r = tile - n * tiles_per_img, ty = r / tx_n, tx = r - ty * tx_n;
-      const bf16* img = P.dy + (size_t)n * P.H * P.W * CK;
+      const int gy0 = ty * PT_H - 2, gx0 = tx * PT_W - 2;
+      const int rlo = gy0 < 0 ? -gy0 : 0, rhi = min(PP_H, P.H - gy0), clo = gx0 < 0 ? -gx0 : 0, chi = min(PP_W, P.W - gx0);
+      const uint32_t rmask = ((1u << rhi) - 1u) & ~((1u << rlo) - 1u), cmask = ((1u << chi) - 1u) & ~((1u << clo) - 1u);
+      const bf16* org = P.dy + (((long long)n * P.H + gy0) * P.W + gx0) * CK;   // may lie before the map: only valid items are read
       const uint32_t dst0 = patch0 + (uint32_t)(pb * L::kPatch);
 #pragma unroll
       for (int k = 0; k < NI; ++k) {
-        if (item[k] < 0) continue;
-        const int c = item[k] >> 16, pr = (item[k] >> 8) & 0xff, pc = item[k] & 0xff;
-        const int gy = ty * PT_H - 2 + pr, gx = tx * PT_W - 2 + pc;
-        const bool valid = gy >= 0 && gy < P.H && gx >= 0 && gx < P.W;
-        const bf16* src = valid ? img + ((size_t)gy * P.W + gx) * CK + c * 8 : P.dy;
-        cp_async16(dst0 + (uint32_t)((c * PP + pr * PP_W + pc) * 16), src, valid ? 16u : 0u);
+        if (it_rc[k] < 0) continue;
+        const bool valid = ((rmask >> (it_rc[k] >> 8)) & (cmask >> (it_rc[k] & 0xff)) & 1u) != 0u;
+        cp_async16(dst0 + (uint32_t)it_dst[k], valid ? org + it_src[k] : P.dy, valid ? 16u : 0u);
       }
       cp_async_arrive(bar_pf + 8 * pb);
     };
+    (void)ty_n;
     if (blockIdx.x < P.tiles) load_patch(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
       const int nt = tile + gridDim.x;
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) conv_dgrad_patch_kernel(const _
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(BM, cinp);
-      const uint64_t dA0 = make_desc_nosw(0, PP * 16, PP_W * 16);
+      const uint64_t dA0 = make_desc_nosw(0, PPL * 16, PP_W * 16);
       const uint32_t ldB = (uint32_t)((RES ? 25 : 1) * cinp * 16);
       const uint64_t dB0 = make_desc_nosw(0, ldB, 128);
       const uint32_t ahi = (uint32_t)(dA0 >> 32), bhi = (uint32_t)(dB0 >> 32), alo0 = (uint32_t)dA0, blo0 = (uint32_t)dB0;
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) conv_dgrad_patch_kernel(const _
             const uint32_t blo = blo0 + (RES ? blo_res + (uint32_t)(t * cinp) : stlo + (uint32_t)((u * L::kBt) >> 4));
 #pragma unroll
             for (int kk = 0; kk < CK / 16; ++kk)
-              mma_lh(acc, alo + (uint32_t)(kk * 2 * PP), ahi, blo + kk * kstepB, bhi, idesc, (t | kk) == 0 ? 0u : 1u);
+              mma_lh(acc, alo + (uint32_t)(kk * 2 * PPL), ahi, blo + kk * kstepB, bhi, idesc, (t | kk) == 0 ? 0u : 1u);
           }
           if (!RES) {
             tc_commit(bar_empty + 8 * s);
@@ -573,6 +578,19 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, int cout, int cin
     if (co < cout && ci < cin) v = w[((size_t)co * cin + ci) * (KSZ * KSZ) + tap];
     wT[i] = __float2bfloat16(v);
   }
+}
+
+// sum of p[0], p[stride], ... in a fixed association (eight interleaved running sums, then a fixed tree): the same bits on
+// every run, with eight loads in flight instead of one
+__device__ __forceinline__ float ordered_sum(const float* __restrict__ p, int n, size_t stride) {
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int b = 0;
+  for (; b + 8 <= n; b += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += __ldg(p + (size_t)(b + k) * stride);
+  }
+  for (int k = 0; b < n; ++b, ++k) a[k] += __ldg(p + (size_t)b * stride);
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
 // ------------------------------------------------------------------------------------------------ 3. wgrad
@@ -758,6 +776,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
 // down.  Taps with ky > 4 are padding (they read zero rows; their accumulator rows are never stored).  Per tile this moves
 // ~80 KB into shared memory instead of ~240 KB, and every cp.async instruction reads consecutive 16-byte pieces (the old
 // thread-per-pixel gather touched 32 cache lines per instruction and was bound by that).
+constexpr int WGP_ISSUERS = 4;                       // power of two
+constexpr int WGP_THREADS = 32 * (4 + WGP_ISSUERS + 4);   // warps 0-3 producers, 4-7 MMA issuers, 8-11 epilogue
 template <int CX>
 struct WgradPatchCfg {
   static constexpr int XC = CX / 8, TPG = 128 / CX, NKG = (KSZ + TPG - 1) / TPG;     // tap groups per kx
@@ -778,10 +798,11 @@ struct WgradPatchParams {
   int gph;             // groups per CTA (blockIdx.y picks the range)
   int ngroups_padded;  // gridDim.y * gph
   int patch_bytes;     // one patch buffer: (TPG - 1) * copy stride + XC * plane, rounded up to 128
+  long long* dbg;      // diagnostic (SD_TRACE_CNN=2)
 };
 
 template <int CX>
-__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const __grid_constant__ WgradPatchParams P) {
+__global__ void __launch_bounds__(WGP_THREADS, 1) conv_wgrad_patch_kernel(const __grid_constant__ WgradPatchParams P) {
   using Cfg = WgradPatchCfg<CX>;
   constexpr int XC = Cfg::XC, TPG = Cfg::TPG, NKG = Cfg::NKG;
   extern __shared__ uint8_t smem_raw[];
@@ -796,14 +817,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cp = P.cp, DC = cp / 8;
   // zero rows / padding are never written by the loads: clear both buffers once
-  for (int i = threadIdx.x; i < 2 * P.patch_bytes / 16; i += WG_THREADS) reinterpret_cast<uint4*>(gbase)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 2 * P.patch_bytes / 16; i += WGP_THREADS) reinterpret_cast<uint4*>(gbase)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_async_smem();
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_pf + 8 * s, PROD);
-      mbar_init(bar_pe + 8 * s, 1);
+      mbar_init(bar_pe + 8 * s, WGP_ISSUERS);
     }
-    mbar_init(bar_done, 1);
+    mbar_init(bar_done, WGP_ISSUERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -823,7 +844,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const _
     const int prow = sh + 4, npx = nsub * prow * PP_W;                 // loaded patch pixels
     const int nitems = npx * XC, ndy = BM * DC;
     // this thread's items do not depend on the tile: (destination, source offset from the tile origin, patch row / column)
-    constexpr int NI = 18, ND = 8;
+    constexpr int NI = CX == 64 ? 18 : 9, ND = 8;        // (2 x 12 x 12 patch pixels) x XC chunks / 128 threads
     int x_dst[NI], x_src[NI], x_rc[NI], d_dst[ND], d_src[ND];
 #pragma unroll
     for (int k = 0; k < NI; ++k) {
@@ -841,17 +862,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const _
       d_src[k] = ((sb * P.H + y) * P.W + xx) * cp + c * 8;
     }
     int lt = 0;
+    const bool dbg = P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+    long long t_pe = 0, c0 = 0, t0 = clock64();
+    // tile -> (first map, row block, column block), advanced by gridDim.x per step without dividing
+    const int tyn = nsub == 1 ? P.H / sh : 1;
+    int tx = blockIdx.x % tx_n, ty = (blockIdx.x / tx_n) % tyn, tn = blockIdx.x / (tx_n * tyn);
+    const int dtx = gridDim.x % tx_n, dty = (gridDim.x / tx_n) % tyn, dtn = gridDim.x / (tx_n * tyn);
     for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
       const int pb = lt & 1;
+      if (dbg) c0 = clock64();
       mbar_wait(bar_pe + 8 * pb, (uint32_t)(((lt >> 1) & 1) ^ 1));
-      int n0, ty, tx;
-      if (nsub == 1) { n0 = tile / tiles_per_img; const int r = tile - n0 * tiles_per_img; ty = r / tx_n; tx = r - ty * tx_n; }
-      else { const int pair = tile / tiles_per_img; tx = tile - pair * tiles_per_img; ty = 0; n0 = pair * 2; }
+      if (dbg) t_pe += clock64() - c0;
+      const int n0 = tn * nsub;
       const int gy0 = ty * sh - 2, gx0 = tx * PT_W - 2;
-      uint32_t rmask = 0, cmask = 0;
-      for (int k = 0; k < prow; ++k) rmask |= (uint32_t)(gy0 + k >= 0 && gy0 + k < P.H) << k;
-#pragma unroll
-      for (int k = 0; k < PP_W; ++k) cmask |= (uint32_t)(gx0 + k >= 0 && gx0 + k < P.W) << k;
+      // bit k of rmask / cmask: patch row / column k lies inside the map (rows [max(0,-gy0), min(prow, H - gy0)))
+      const int rlo = gy0 < 0 ? -gy0 : 0, rhi = min(prow, P.H - gy0), clo = gx0 < 0 ? -gx0 : 0, chi = min(PP_W, P.W - gx0);
+      const uint32_t rmask = ((1u << rhi) - 1u) & ~((1u << rlo) - 1u), cmask = ((1u << chi) - 1u) & ~((1u << clo) - 1u);
       const uint32_t pdst = base + (uint32_t)(pb * P.patch_bytes);
       const bf16* xorg = P.x + (((long long)n0 * P.H + gy0) * P.W + gx0) * CX;   // may point before the map: only valid items are read
       // x patch: item = (patch pixel, chunk), chunk fastest: a warp instruction reads 512 consecutive bytes of a row
@@ -869,9 +895,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const _
       for (int k = 0; k < ND; ++k)
         if (d_dst[k] >= 0) cp_async16(dyb + (uint32_t)(pb * Cfg::kDy + d_dst[k]), dorg + d_src[k], 16u);
       cp_async_arrive(bar_pf + 8 * pb);
+      tx += dtx; ty += dty; tn += dtn;
+      if (tx >= tx_n) { tx -= tx_n; ++ty; }
+      if (ty >= tyn) { ty -= tyn; ++tn; }
     }
-  } else if (warp == MMA_WARP) {
+    if (dbg) { P.dbg[0] = clock64() - t0; P.dbg[1] = t_pe; P.dbg[3] = lt; }
+  } else if (warp < 4 + WGP_ISSUERS) {
+    // WGP_ISSUERS single-thread MMA issuers: issuer q owns groups j = q, q + WGP_ISSUERS, ... (disjoint accumulators).  One
+    // thread cannot issue a tcgen05.mma more often than every ~60 cycles whatever its size (profiles/r02_umma_probe.txt),
+    // and an N <= 64 MMA needs only half of that on the tensor pipe
     if (lane == 0) {
+      const int q = warp - 4;
       const uint32_t idesc = make_idesc_mn(BM, cp);
       const uint64_t dA0 = make_desc_nosw(0, PP_W * 16, (uint32_t)plane), dB0 = make_desc_nosw(0, 128, Cfg::kDyPlane);
       const uint32_t ahi = (uint32_t)(dA0 >> 32), bhi = (uint32_t)(dB0 >> 32), alo0 = (uint32_t)dA0, blo0 = (uint32_t)dB0;
@@ -885,9 +919,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const _
       }
       const int kx_first = g0 / NKG, kg_first = g0 - kx_first * NKG;
       int lt = 0;
+      const bool dbg = P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && q == 0;
+      long long t_pf = 0, c0 = 0, t0 = clock64();
       for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++lt) {
         const int pb = lt & 1;
+        if (dbg) c0 = clock64();
         mbar_wait(bar_pf + 8 * pb, (uint32_t)(lt >> 1) & 1u);
+        if (dbg) t_pf += clock64() - c0;
         fence_async_smem();
         tc_fence_after();
         const uint32_t plo = alo0 + (((base + (uint32_t)(pb * P.patch_bytes)) & 0x3FFFFu) >> 4);
@@ -897,14 +935,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_patch_kernel(const _
         uint32_t acc = tmem;
 #pragma unroll 1
         for (int j = 0; j < P.gph && kx < KSZ; ++j, acc += (uint32_t)cp) {
-          const uint32_t a = plo + (uint32_t)(kg * TPG * PP_W + kx);
+          if ((j & (WGP_ISSUERS - 1)) == q) {
+            const uint32_t a = plo + (uint32_t)(kg * TPG * PP_W + kx);
 #pragma unroll
-          for (int kk = 0; kk < BM / 16; ++kk) mma_lh(acc, a + rowoff[kk], ahi, blo + (uint32_t)(kk * 16), bhi, idesc, kk == 0 ? first : 1u);
+            for (int kk = 0; kk < BM / 16; ++kk) mma_lh(acc, a + rowoff[kk], ahi, blo + (uint32_t)(kk * 16), bhi, idesc, kk == 0 ? first : 1u);
+          }
           if (++kg == NKG) { kg = 0; ++kx; }
         }
         tc_commit(bar_pe + 8 * pb);
       }
       tc_commit(bar_done);
+      if (dbg) { P.dbg[4] = clock64() - t0; P.dbg[5] = t_pf; }
     }
   } else {
     const int quarter = warp & 3, row = quarter * 32 + lane;
@@ -949,8 +990,7 @@ __global__ void wgrad_patch_reduce_kernel(const float* __restrict__ partial, int
     const int co = i % cp, ci = (i / cp) % cx, slot = i / (cp * cx);
     const int gi = slot / tpg, j = slot - gi * tpg, kx = gi / nkg, ky = (gi - kx * nkg) * tpg + j;
     if (co >= cout || ci >= cin || ky >= KSZ) continue;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * stride + i];
+    float s = ordered_sum(partial + i, nblocks, stride);
     dw[((size_t)co * cin + ci) * (KSZ * KSZ) + ky * KSZ + kx] += s;
   }
 }
@@ -964,8 +1004,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nbloc
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i % cp, ci = (i / cp) % cx, tap = i / (cp * cx);
     if (co >= cout || ci >= cin) continue;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * stride + i];
+    float s = ordered_sum(partial + i, nblocks, stride);
     dw[((size_t)co * cin + ci) * (KSZ * KSZ) + tap] += s;
   }
 }
@@ -980,20 +1019,21 @@ struct Wgrad1Params {
   int H, W, total, tiles, cp;
 };
 constexpr int kW1A = 16 * BM * 16;      // 32 KB: [16 chunks][128 px][16 B], chunks 10..15 stay zero
-constexpr int kW1Smem = 2 * kW1A + 2 * kWgDy + kPatchFloats * 4 + 8 * 10 + 16 + 256;
+constexpr int W1_THREADS = 32 * 13;     // warps 0-3 / 4-7: two producer groups (tiles alternate), 8 MMA, 9-12 epilogue
+constexpr int W1_MMA_WARP = 8;
+constexpr int kW1Smem = 2 * kW1A + 2 * kWgDy + 2 * kPatchFloats * 4 + 8 * 10 + 16 + 256;
 
-__global__ void __launch_bounds__(WG_THREADS, 1) conv1_wgrad_kernel(const __grid_constant__ Wgrad1Params P) {
+__global__ void __launch_bounds__(W1_THREADS, 1) conv1_wgrad_kernel(const __grid_constant__ Wgrad1Params P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t dyb = base + 2 * kW1A;
-  float* patch = reinterpret_cast<float*>(gbase + 2 * kW1A + 2 * kWgDy);
-  const uint32_t bar_full = dyb + 2 * kWgDy + kPatchFloats * 4, bar_empty = bar_full + 16, bar_dyf = bar_empty + 16,
-                 bar_done = bar_dyf + 16, tmem_slot = bar_done + 16;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + 2 * kW1A + 2 * kWgDy + kPatchFloats * 4 + 64);
+  const int off_bar = 2 * kW1A + 2 * kWgDy + 2 * kPatchFloats * 4;
+  const uint32_t bar_full = base + (uint32_t)off_bar, bar_empty = bar_full + 16, bar_done = bar_empty + 16, tmem_slot = bar_done + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + off_bar + 48);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cp = P.cp, DC = cp / 8;
-  for (int i = threadIdx.x; i < 2 * kW1A / 16; i += WG_THREADS) reinterpret_cast<uint4*>(gbase)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 2 * kW1A / 16; i += W1_THREADS) reinterpret_cast<uint4*>(gbase)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_async_smem();
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -1003,7 +1043,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv1_wgrad_kernel(const __grid
     mbar_init(bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == MMA_WARP) {
+  if (warp == W1_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(64));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -1015,38 +1055,52 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv1_wgrad_kernel(const __grid
   const int rowf = P.W * 3, PR = R + 4, PW = rowf + 16;
   const int tiles_per_frame = P.H / R;
 
-  if (warp < 4) {
-    const int tid = threadIdx.x;
+  if (warp < 8) {
+    // producer group grp builds the operand of tiles it = grp, grp + 2, ... in stage grp from its own patch buffer
+    const int grp = warp >> 2, tid = threadIdx.x & (PROD - 1);
+    float* patch = reinterpret_cast<float*>(gbase + 2 * kW1A + 2 * kWgDy) + grp * kPatchFloats;
     const int lrow = tid / P.W, ox = tid - lrow * P.W;
     const int r4 = rowf >> 2, n4 = PR * r4;
     for (int i = tid; i < PR * 4; i += PROD) {
       const int r = i >> 2, q = i & 3;
       reinterpret_cast<float4*>(patch + r * PW + (q < 2 ? q * 4 : rowf + q * 4))[0] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x, ++it) {
-      const int n = tile / tiles_per_frame, oy0 = (tile - n * tiles_per_frame) * R;
-      const int s = it & 1;
-      if (it >= 2) mbar_wait(bar_empty + 8 * s, (uint32_t)((it >> 1) - 1) & 1u);
-      // dy tile: rows of the tile are consecutive pixels of the frame
+    constexpr int NI = 4;                            // float4 patch items per thread ((R + 4) rows x W * 3 / 4 <= 512)
+    int rc[NI];
+#pragma unroll
+    for (int k = 0; k < NI; ++k) {
+      const int i = tid + k * PROD;
+      rc[k] = i < n4 ? ((i / r4) << 16) | (i % r4) : -1;
+    }
+    const int s = grp;
+    int fn = (blockIdx.x + grp * gridDim.x) / tiles_per_frame, ft = (blockIdx.x + grp * gridDim.x) - fn * tiles_per_frame;
+    const int dn = (2 * gridDim.x) / tiles_per_frame, dt = (2 * gridDim.x) - dn * tiles_per_frame;
+    int use = 0;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < P.tiles; tile += 2 * gridDim.x, ++use) {
+      const int oy0 = ft * R;
+      // frame rows first: their latency overlaps the wait for the stage
+      float4 pre[NI];
+      const float* frame = P.obs + (size_t)fn * P.H * rowf;
+#pragma unroll
+      for (int k = 0; k < NI; ++k) {
+        pre[k] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+        const int iy = oy0 - 2 + (rc[k] >> 16);
+        if (rc[k] >= 0 && iy >= 0 && iy < P.H) pre[k] = __ldg(reinterpret_cast<const float4*>(frame + (size_t)iy * rowf) + (rc[k] & 0xffff));
+      }
+      if (use >= 1) mbar_wait(bar_empty + 8 * s, (uint32_t)(use - 1) & 1u);
       {
         const size_t g = (size_t)tile * BM + tid;
         const uint32_t dst = dyb + (uint32_t)(s * kWgDy + tid * 16);
         for (int c = 0; c < DC; ++c) cp_async16(dst + (uint32_t)(c * BM * 16), P.dy + g * cp + c * 8, 16u);
         cp_async_arrive(bar_full + 8 * s);
       }
-      named_bar(1, PROD);
-      const float* frame = P.obs + (size_t)n * P.H * rowf;
-      for (int i = tid; i < n4; i += PROD) {
-        const int r = i / r4, c = i - r * r4, iy = oy0 - 2 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < P.H) {
-          v = __ldg(reinterpret_cast<const float4*>(frame + (size_t)iy * rowf) + c);
-          v = make_float4(v.x - 0.5f, v.y - 0.5f, v.z - 0.5f, v.w - 0.5f);
-        }
-        reinterpret_cast<float4*>(patch + r * PW + 8)[c] = v;
-      }
-      named_bar(1, PROD);
+      named_bar(1 + grp, PROD);                    // the previous tile's build has finished reading the patch
+#pragma unroll
+      for (int k = 0; k < NI; ++k)
+        if (rc[k] >= 0)
+          reinterpret_cast<float4*>(patch + (rc[k] >> 16) * PW + 8)[rc[k] & 0xffff] =
+              make_float4(pre[k].x - 0.5f, pre[k].y - 0.5f, pre[k].z - 0.5f, pre[k].w - 0.5f);
+      named_bar(1 + grp, PROD);
       uint8_t* st = gbase + (size_t)s * kW1A;
       // input pixel (ox - 2 + j) of patch row (lrow + ky) starts at float 8 + (ox - 2 + j) * 3 = 2 + 3 ox + 3 j
       const float* prow = patch + lrow * PW + 2 + 3 * ox;
@@ -1062,8 +1116,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv1_wgrad_kernel(const __grid
       }
       fence_async_smem();
       mbar_arrive(bar_full + 8 * s);
+      fn += dn; ft += dt;
+      if (ft >= tiles_per_frame) { ft -= tiles_per_frame; ++fn; }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == W1_MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_mn(BM, cp);
       const uint64_t d0 = make_desc_mn(0);
@@ -1105,7 +1161,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv1_wgrad_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == W1_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64));
   }
@@ -1117,8 +1173,7 @@ __global__ void wgrad1_reduce_kernel(const float* __restrict__ partial, int nblo
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int co = i % cp, k = i / cp, ky = k >> 4, r = k & 15;
     if (co >= cout || r >= 15) continue;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * BM * cp + i];
+    float s = ordered_sum(partial + i, nblocks, (size_t)BM * cp);
     dw[((size_t)co * 3 + (r % 3)) * (KSZ * KSZ) + ky * KSZ + r / 3] += s;
   }
 }
