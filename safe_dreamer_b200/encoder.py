@@ -113,6 +113,7 @@ class ConvEncoder(nn.Module):
         self.out_dim = self.depths[-1] * h * w
         self.layers = nn.Sequential(*layers)          # parameter containers: names / shapes of the reference
         self.max_frames = 1024
+        self.auto_refresh = False      # True: repack the weights on every call (frozen copies alias live storage, dreamer.py:279)
         self._eng = None
         self._wkey = None
 
@@ -144,7 +145,7 @@ class ConvEncoder(nn.Module):
             eng = self._eng = CnnEngine(*self._input_shape, self.depths, self.kernel_size, mf, mt, device=dev)
             self._wkey = None
         key = tuple((t.data_ptr(), t._version) for t in ts)
-        if key != self._wkey:
+        if key != self._wkey or self.auto_refresh:
             eng.set_weights(ts)
             self._wkey = key
         return eng

@@ -12,6 +12,8 @@ reference's own code):
                                        cumprod weights and the imagined lambda-return in one fused call          dreamer.py:589-602
   agent.return_ema                  -> sd_return_ema (exact quantiles + EMA in one launch)                     networks.py:405-422
   agent._optimizer / agent._agc     -> fused multi-tensor AGC + LaProp (optional)                              dreamer.py:219-224,432-433
+  agent.encoder.encoders[i] (ConvEncoder; optional, `encoder=True`, eager mode) -> safe_dreamer_b200.encoder.ConvEncoder
+                                       adopting the same Parameter objects: tcgen05 implicit-GEMM forward / backward  networks.py:192-234
 With `custom_ops=True` (default when the agent was built with config.compile) the RSSM calls go through the
 torch.library operators of `safe_dreamer_b200.ops`, which torch.compile(mode="reduce-overhead") traces as opaque nodes.
 """
@@ -40,6 +42,18 @@ def _adopt_parameters(dst, src):
         for part in parts[:-1]:
             mod = getattr(mod, part)
         mod._parameters[parts[-1]] = p
+
+
+def mirror_conv_encoder(ref, input_shape):
+    """A safe_dreamer_b200 ConvEncoder sharing the parameters of the reference ConvEncoder `ref` (networks.py:192-234)."""
+    from .encoder import ConvEncoder
+    n = len(ref.depths)
+    if len(ref.layers) != 4 * n or not isinstance(ref.layers[3], torch.nn.SiLU):
+        raise NotImplementedError("install(encoder=True): only conv -> maxpool -> RMSNorm2D -> SiLU stages (configs/base.yaml) have kernels")
+    cfg = NS(act="SiLU", norm=True, depth=1, mults=list(ref.depths), kernel_size=ref.kernel_size)
+    new = ConvEncoder(cfg, tuple(int(v) for v in input_shape)).to(next(ref.parameters()).device)
+    _adopt_parameters(new, ref)
+    return new
 
 
 def mirror_rssm(ref, embed_size):
@@ -114,6 +128,10 @@ def _post_clone(agent, opt):
     # the frozen copies alias the live parameters' storage through fresh tensors (param_new.data = param_orig.data,
     # dreamer.py:279): their version counters never move, so the packed copies are refreshed on every call
     fr.auto_refresh = True
+    from .encoder import ConvEncoder
+    for enc in getattr(getattr(agent, "_frozen_encoder", None), "encoders", []):
+        if isinstance(enc, ConvEncoder):
+            enc.auto_refresh = True      # same aliasing: the frozen encoder behind Dreamer.act (dreamer.py:341)
     mods = {nm: agent._modules[f"_frozen_{nm}"] for nm in _FROZEN}
     kw = dict(getattr(getattr(agent._frozen_actor, "_dist", None), "keywords", {}) or {})
     dreamer_ops.attach_heads(fr, actor=agent._frozen_actor, reward=mods["reward"], cont=mods["cont"], value=mods["value"],
@@ -131,7 +149,7 @@ def _post_clone(agent, opt):
 
 
 def install(agent, precision="fp32", imagine_precision="bf16", fuse_heads=None, optimizer=False, return_ema=True,
-            custom_ops=None, use_graph=True):
+            custom_ops=None, use_graph=True, encoder=False):
     """Swap the hot path of the reference `agent` (see module docstring).  Returns the agent.
     precision: "fp32" (3xTF32, parity with the fp32 reference) or "bf16" for the posterior path;
     imagine_precision: precision of the (no-grad) imagination rollout and the fused heads."""
@@ -146,6 +164,17 @@ def install(agent, precision="fp32", imagine_precision="bf16", fuse_heads=None, 
     new.use_graph = use_graph
     new.use_custom_ops = bool(custom_ops)
     agent.rssm = new
+    if encoder:
+        if custom_ops:
+            raise NotImplementedError("install(encoder=True) is eager-only: the CNN encoder has no torch.library operator yet")
+        encs = getattr(agent.encoder, "encoders", None)
+        shapes = getattr(agent.encoder, "cnn_shapes", None)
+        if encs is None or not shapes:
+            raise NotImplementedError("install(encoder=True): agent.encoder is not a MultiEncoder with image keys")
+        shape = tuple(shapes.values())[0][:2] + (sum(v[-1] for v in shapes.values()),)
+        for i, enc in enumerate(encs):
+            if type(enc).__name__ == "ConvEncoder":
+                encs[i] = mirror_conv_encoder(enc, shape)
     ref_clone = type(agent).clone_and_freeze
 
     def clone_and_freeze(self):

@@ -124,3 +124,58 @@ def test_installed_agent_under_torch_compile():
     for k in ("loss/dyn", "loss/rep", "loss/rew", "loss/con"):
         vals = [m[k] for m in outs]
         assert max(vals) - min(vals) <= 0.1 * abs(np.mean(vals)) + 0.05, (k, vals)
+
+
+def test_installed_cnn_encoder_in_the_reference_dreamer():
+    """Config C2 (vision, r2dreamer): the reference Dreamer with `install(agent, encoder=True)` -- its ConvEncoder replaced by
+    the tcgen05 encoder (same Parameter objects), forward AND backward inside the reference's own `_cal_grad`.
+    The encoder computes with bf16 operands, so sampled posterior indices may differ from the fp32 reference at near ties
+    and every downstream number moves a little: losses are compared at 10 %, and the encoder's gradients (which now come
+    from sd_cnn_backward) against the reference's autograd at 25 % rel. L2 per tensor (tests/test_gpu_k_cnn.py is the tight
+    parity gate of the kernels; this test proves the wiring)."""
+    RH = _harness()
+    import safe_dreamer_b200
+    from safe_dreamer_b200.encoder import ConvEncoder
+    dev = torch.device("cuda")
+    B, T = 4, 16
+    agent, cfg = RH.build_dreamer(dev, kind="vision", rep_loss="r2dreamer", compile=False)
+    RH.perturb_agent(agent)
+    data, initial = RH.make_batch(agent, B, T, dev, kind="vision")
+    H = agent.imag_horizon + 1
+    S, K, A = agent.rssm._stoch, agent.rssm._discrete, agent.act_dim
+    nt = RH.NoiseTape(B, T, B * T, H, S, K, A, False)
+
+    def enc_grads():
+        return {n: p.grad.detach().clone() for n, p in agent.encoder.named_parameters() if p.grad is not None}
+
+    uq, eq = nt.reference_queues(dev)
+    undo = RH.patch_reference_noise(uq, eq)
+    try:
+        st_r, dt_r, m_r, _ = _run_cal_grad(agent, data, initial)
+        ge_r = enc_grads()
+    finally:
+        undo()
+    agent.return_ema.ema_vals.zero_()
+    safe_dreamer_b200.install(agent, precision="fp32", imagine_precision="fp32", encoder=True)
+    assert any(isinstance(e, ConvEncoder) for e in agent.encoder.encoders)
+    assert any(isinstance(e, ConvEncoder) and e.auto_refresh for e in agent._frozen_encoder.encoders)
+    q_live = [nt.u_obs.to(dev), nt.u_prior.to(dev)]
+    agent.rssm.noise_source = lambda shape, d: q_live.pop(0).reshape(shape)
+    q_img = [nt.u_img.to(dev)]
+    agent._frozen_rssm.noise_source = lambda shape, d: q_img.pop(0).reshape(shape)
+    agent._frozen_rssm.act_noise_source = lambda shape, d: nt.a_noise.to(d).reshape(shape)
+    st_i, dt_i, m_i, _ = _run_cal_grad(agent, data, initial)
+    ge_i = enc_grads()
+    mism = (st_i.argmax(-1) != st_r.argmax(-1)).float().mean().item()
+    print(f"posterior index mismatch rate with the bf16 encoder: {mism:.3e}")
+    assert mism <= 0.05
+    assert set(m_i) == set(m_r) and all(np.isfinite(v) for v in m_i.values())
+    for k in sorted(m_r):
+        if k.startswith("loss/") or k.endswith("_loss"):
+            print(f"  {k:28s} reference {m_r[k]: .5e}  installed {m_i[k]: .5e}")
+            assert abs(m_i[k] - m_r[k]) <= 0.1 * abs(m_r[k]) + 1e-2, k
+    assert set(ge_i) == set(ge_r) and len(ge_i) == 12
+    for n in sorted(ge_r):
+        rel = float((ge_i[n] - ge_r[n]).norm() / ge_r[n].norm().clamp_min(1e-30))
+        print(f"  encoder grad {n:22s} rel L2 diff {rel:.3f}")
+        assert rel <= 0.25, n
