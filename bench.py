@@ -332,6 +332,47 @@ def run_gpu(args):
             imag_fb()
         ms_imag_fb = timed(imag_fb, args.steps, warm=2)
         del eng2
+    # ---- CNN encoder (networks.py:192-234) on this rank's B*T frames of 64x64x3: forward, and forward + backward
+    # with all weight gradients (no d(obs): training never needs it).  Reported next to the hot path, not inside `value`.
+    cnn = None
+    if E == 1024 and not args.no_encoder:
+        from safe_dreamer_b200.encoder import CnnEngine
+        from safe_dreamer_b200.synth import encoder_params
+        depths = [32, 48, 64, 64]
+        frames = B * T
+        PE = encoder_params(depths, 3, 5, seed=0)
+        names = []
+        for i in range(4):
+            names += [f"layers.{4 * i}.weight", f"layers.{4 * i}.bias", f"layers.{4 * i + 2}.weight"]
+        ceng = CnnEngine(64, 64, 3, depths, 5, max_frames=frames, max_tape_frames=frames, device=dev)
+        ceng.set_weights([cu(PE[k]) for k in names])
+        frames_in = torch.rand(frames, 64, 64, 3, device=dev)
+        g_emb = torch.randn(frames, 1024, device=dev)
+        wg = [torch.zeros(PE[k].shape, device=dev) for k in names]
+
+        def enc_fb():
+            ceng.forward(frames_in, tape=True)
+            ceng.backward(g_emb, want_obs_grad=False, weight_grads=wg)
+        l_e0 = _lib.launch_count()
+        enc_fb()
+        l_enc = _lib.launch_count() - l_e0
+        ms_ef = timed(lambda: ceng.forward(frames_in), args.steps, warm=2) / args.steps
+        ms_efb = timed(enc_fb, args.steps, warm=2) / args.steps
+        gflop = 0.1507 * frames      # 150.7 MFLOP per frame forward
+        cnn = {"frames": frames, "forward_ms": ms_ef, "forward_backward_ms": ms_efb, "launches_fwd_bwd": int(l_enc),
+               "forward_tflops": gflop / ms_ef, "forward_backward_tflops": 3 * gflop / ms_efb,
+               "frac_of_bf16_burst_peak_fwd": gflop / ms_ef / peaks()[1], "dtype": "bf16 operands, fp32 accumulate",
+               "note": "implicit-GEMM conv 5x5 on tcgen05 with pool / RMSNorm / SiLU epilogue; backward = norm/pool bwd + dgrad + wgrad"}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_cnn_reference.json")) as f:
+                refc = json.load(f)["cnn_encoder_ms"]
+            if frames == 1024:
+                cnn["reference_on_this_gpu_ms"] = dict(refc, source="profiles/r02_cnn_reference.json (profiles/cnn_reference_time.py, earlier run)")
+                cnn["speedup_vs_reference_compiled_fp16"] = {"fwd": refc["ref_compiled_fp16"]["fwd"] / ms_ef,
+                                                             "fwd_bwd": refc["ref_compiled_fp16"]["fwd_bwd"] / ms_efb}
+        except (OSError, KeyError, ValueError):
+            pass
+        del ceng
     # ---- end-to-end through the public module API with HOST buffers (pinned) and a D2H result read
     from types import SimpleNamespace as NS
     from safe_dreamer_b200 import dreamer_ops
@@ -565,6 +606,7 @@ def run_gpu(args):
                                            "barriers + dependent phases of a step, not by the tensor or HBM roofline"},
             "cpu_baseline": cpu,
             "gpu_reference": gpu_ref,
+            "cnn_encoder": cnn,
             "e2e": {"value": N * H * args.steps * world / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(pin_res[0].numel() * 4), "ms_per_step": 1e3 * e2e_s / args.steps},
             "e2e_async_read": {"value": N * H * args.steps * world / e2e_async_s, "unit": "steps/s", "ms_per_step": 1e3 * e2e_async_s / args.steps,
@@ -588,6 +630,7 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the unmodified reference modules on this GPU")
     ap.add_argument("--ref-compile", action="store_true", help="also time the reference under torch.compile(mode='reduce-overhead') (minutes)")
     ap.add_argument("--no-imagine-bwd", action="store_true", help="skip the grad-enabled imagination (attack shape) measurement")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the CNN encoder (forward / forward + backward) measurement")
     ap.add_argument("--schedule", default="auto", help="hot-path schedule: auto (fastest of the measured ones) or a name from the JSON's schedules_ms")
     ap.add_argument("--no-overlap", action="store_true", help="run imagination after (not concurrently with) the posterior backward")
     ap.add_argument("--batch", type=int, default=16, help="replay batch B per GPU (default: base.yaml's 16; the headline config)")

@@ -89,17 +89,7 @@ def norm_act_bwd(x, g, dy):
     return dx.astype(x.dtype), dg
 
 
-def encoder_params(depths, cin, k, seed=0, dtype=np.float32):
-    """Seeded weights in the reference's state_dict naming (layers.{4i}.weight/bias = conv, layers.{4i+2}.weight = RMS scale)."""
-    rng = np.random.Generator(np.random.Philox(seed))
-    P = {}
-    for i, co in enumerate(depths):
-        fan = cin * k * k
-        P[f"layers.{4 * i}.weight"] = (rng.standard_normal((co, cin, k, k), dtype=np.float32) / np.sqrt(fan)).astype(dtype)
-        P[f"layers.{4 * i}.bias"] = (0.1 * rng.standard_normal(co, dtype=np.float32)).astype(dtype)
-        P[f"layers.{4 * i + 2}.weight"] = (1.0 + 0.1 * rng.standard_normal(co, dtype=np.float32)).astype(dtype)
-        cin = co
-    return P
+from safe_dreamer_b200.synth import encoder_params  # noqa: E402,F401  (seeded weights: shared with the benchmark)
 
 
 def round_bf16(x):

@@ -175,3 +175,17 @@ def cast_params(P, dtype):
     return {m: {k: v.astype(dtype) for k, v in d.items()} for m, d in P.items()}
 
 
+
+
+def encoder_params(depths, cin, k, seed=0, dtype=np.float32):
+    """Seeded CNN encoder weights in the reference's state_dict naming (networks.py:192-234: layers.{4i}.weight/bias = conv,
+    layers.{4i+2}.weight = RMS scale); shared by the oracle (oracle/cnn_oracle.py re-exports it) and the benchmark."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    P = {}
+    for i, co in enumerate(depths):
+        fan = cin * k * k
+        P[f"layers.{4 * i}.weight"] = (rng.standard_normal((co, cin, k, k), dtype=np.float32) / np.sqrt(fan)).astype(dtype)
+        P[f"layers.{4 * i}.bias"] = (0.1 * rng.standard_normal(co, dtype=np.float32)).astype(dtype)
+        P[f"layers.{4 * i + 2}.weight"] = (1.0 + 0.1 * rng.standard_normal(co, dtype=np.float32)).astype(dtype)
+        cin = co
+    return P
