@@ -282,9 +282,11 @@ int sd_cnn_set_weights(sd_cnn* h, const float* const* tensors, int count, void* 
 int sd_cnn_forward(sd_cnn* h, int frames, const float* obs, float* embed, uint32_t flags, void* stream);
 /* Backward of the last SD_FLAG_SAVE_TAPE sd_cnn_forward (autograd of networks.py:192-234).
  *   d_embed (frames, embed_size) fp32 -> d_obs (frames, H, W, 3) fp32 (nullable: skipped; only the attack needs it),
+ *   obs: the frames of that forward (the stage-1 weight gradient re-reads them); NULL = the pointer the forward was given,
  *   weight_grads: 3 * layers fp32 tensors in the order / layouts of sd_cnn_set_weights, ACCUMULATED into
  *   (nullable array or entries = skip: frozen encoder).  Deterministic: partial sums are reduced in a fixed order. */
-int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, float* d_obs, float* const* weight_grads, void* stream);
+int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, const float* obs, float* d_obs, float* const* weight_grads,
+                    void* stream);
 
 /* Kernels launched by this library since process start (all handles): bench.py's gpu_launches. */
 uint64_t sd_launch_count(void);

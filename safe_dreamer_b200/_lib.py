@@ -149,7 +149,7 @@ _SIGS = {
     "sd_cnn_embed_size": (C.c_int64, [_P]),
     "sd_cnn_set_weights": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P]),
     "sd_cnn_forward": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint32, _P]),
-    "sd_cnn_backward": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(_P), _P]),
+    "sd_cnn_backward": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P), _P]),
 }
 
 

@@ -407,7 +407,8 @@ static int launch_wgrad_patch(sd_cnn* h, const bf16* x, const bf16* dy, int fram
   return SD_OK;
 }
 
-extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, float* d_obs, float* const* weight_grads, void* stream) {
+extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, const float* obs, float* d_obs, float* const* weight_grads,
+                               void* stream) {
   if (!h || !d_embed) return sd_fail(SD_ERR_INVALID, "sd_cnn_backward: null argument");
   if (h->tape_frames != frames || frames < 1)
     return sd_fail(SD_ERR_NO_TAPE, "sd_cnn_backward: no SD_FLAG_SAVE_TAPE forward with %d frames on this handle (last taped forward: %d frames)", frames, h->tape_frames);
@@ -455,7 +456,7 @@ extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, floa
         static unsigned long long mask = 0;
         SD_CUDA_TRY(ensure_smem(sd::cnn::conv1_wgrad_kernel, sd::cnn::kW1Smem, mask));
         sd::cnn::Wgrad1Params p;
-        p.obs = h->tape_obs; p.dy = h->dy[0]; p.partial = h->scratch;
+        p.obs = obs ? obs : h->tape_obs; p.dy = h->dy[0]; p.partial = h->scratch;
         p.H = Hc; p.W = Wc; p.total = total; p.tiles = total / sd::cnn::BM; p.cp = cp;
         nblocks = p.tiles < h->sms ? p.tiles : h->sms;
         sd::cnn::conv1_wgrad_kernel<<<nblocks, sd::cnn::W1_THREADS, sd::cnn::kW1Smem, st>>>(p);

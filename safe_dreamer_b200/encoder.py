@@ -60,8 +60,10 @@ class CnnEngine:
         arr = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
         _lib.check(self.lib.sd_cnn_set_weights(self.h, arr, len(keep), self.stream), "sd_cnn_set_weights")
 
-    def forward(self, obs, tape=False):
-        """obs (..., H, W, C) fp32 CUDA in [0, 1] -> embed (..., embed_size) fp32."""
+    def forward(self, obs, tape=False, keep_obs=True):
+        """obs (..., H, W, C) fp32 CUDA in [0, 1] -> embed (..., embed_size) fp32.
+        keep_obs=False: do not hold on to the frames (the caller hands them to `backward` itself; needed under CUDA-graph
+        capture, where nothing may keep pool tensors alive behind torch's back)."""
         if not obs.is_cuda:
             raise RuntimeError("safe_dreamer_b200: expected a CUDA tensor (there is no CPU path)")
         lead = obs.shape[:-3]
@@ -73,11 +75,11 @@ class CnnEngine:
         _lib.check(self.lib.sd_cnn_forward(self.h, frames, x.data_ptr(), out.data_ptr(), SD_FLAG_SAVE_TAPE if tape else 0,
                                            self.stream), "sd_cnn_forward")
         if tape:
-            self._tape_obs, self._tape_frames = x, frames   # sd_cnn_backward re-reads the frames (stage-1 weight gradient)
+            self._tape_obs, self._tape_frames = (x if keep_obs else None), frames   # sd_cnn_backward re-reads the frames (stage-1 weight gradient)
             self.tape_gen += 1
         return out.reshape(*lead, self.embed_size)
 
-    def backward(self, d_embed, want_obs_grad=False, weight_grads=None):
+    def backward(self, d_embed, want_obs_grad=False, weight_grads=None, obs=None):
         """Backward of the last tape=True forward.  d_embed (..., embed_size) -> d_obs (frames, H, W, C) or None;
         weight_grads: list of 3 * layers fp32 CUDA tensors (or None entries) the gradients are ACCUMULATED into."""
         frames = self._tape_frames
@@ -88,8 +90,12 @@ class CnnEngine:
         arr = None
         if weight_grads is not None:
             arr = (C.c_void_p * len(weight_grads))(*[0 if t is None else t.data_ptr() for t in weight_grads])
-        _lib.check(self.lib.sd_cnn_backward(self.h, frames, g.data_ptr(), None if d_obs is None else d_obs.data_ptr(), arr,
-                                            self.stream), "sd_cnn_backward")
+        if obs is not None:
+            obs = obs.to(torch.float32).contiguous()
+        elif self._tape_obs is None and weight_grads is not None:
+            raise RuntimeError("CnnEngine.backward: the forward ran with keep_obs=False, pass obs=")
+        _lib.check(self.lib.sd_cnn_backward(self.h, frames, g.data_ptr(), None if obs is None else obs.data_ptr(),
+                                            None if d_obs is None else d_obs.data_ptr(), arr, self.stream), "sd_cnn_backward")
         return d_obs
 
 
@@ -114,6 +120,8 @@ class ConvEncoder(nn.Module):
         self.layers = nn.Sequential(*layers)          # parameter containers: names / shapes of the reference
         self.max_frames = 1024
         self.auto_refresh = False      # True: repack the weights on every call (frozen copies alias live storage, dreamer.py:279)
+        self.use_custom_ops = False    # True: go through torch.ops.safedreamer.cnn_encoder (traceable by torch.compile)
+        self._ops_key = None
         self._eng = None
         self._wkey = None
 
@@ -128,7 +136,7 @@ class ConvEncoder(nn.Module):
         nn.Module.__init__(new)
         import copy
         for k, v in self.__dict__.items():
-            if k in ("_eng", "_wkey"):
+            if k in ("_eng", "_wkey", "_ops_key"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
@@ -152,6 +160,10 @@ class ConvEncoder(nn.Module):
 
     def forward(self, obs):
         """(B, T, H, W, C) in [0, 1] -> (B, T, out_dim) (networks.py:218-234)."""
+        if self.use_custom_ops:
+            ts = self._tensors()
+            taped = torch.is_grad_enabled() and (obs.requires_grad or any(t.requires_grad for t in ts))
+            return torch.ops.safedreamer.cnn_encoder(obs.float(), ts, self._ops_key, taped)
         frames = int(obs.numel() // (self._input_shape[0] * self._input_shape[1] * self._input_shape[2]))
         need_grad = torch.is_grad_enabled() and (obs.requires_grad or any(t.requires_grad for t in self._tensors()))
         if need_grad:

@@ -132,6 +132,9 @@ def _post_clone(agent, opt):
     for enc in getattr(getattr(agent, "_frozen_encoder", None), "encoders", []):
         if isinstance(enc, ConvEncoder):
             enc.auto_refresh = True      # same aliasing: the frozen encoder behind Dreamer.act (dreamer.py:341)
+            if enc.use_custom_ops:
+                from . import ops
+                enc._ops_key = ops.module_key(enc)
     mods = {nm: agent._modules[f"_frozen_{nm}"] for nm in _FROZEN}
     kw = dict(getattr(getattr(agent._frozen_actor, "_dist", None), "keywords", {}) or {})
     dreamer_ops.attach_heads(fr, actor=agent._frozen_actor, reward=mods["reward"], cont=mods["cont"], value=mods["value"],
@@ -165,8 +168,6 @@ def install(agent, precision="fp32", imagine_precision="bf16", fuse_heads=None, 
     new.use_custom_ops = bool(custom_ops)
     agent.rssm = new
     if encoder:
-        if custom_ops:
-            raise NotImplementedError("install(encoder=True) is eager-only: the CNN encoder has no torch.library operator yet")
         encs = getattr(agent.encoder, "encoders", None)
         shapes = getattr(agent.encoder, "cnn_shapes", None)
         if encs is None or not shapes:
@@ -175,6 +176,10 @@ def install(agent, precision="fp32", imagine_precision="bf16", fuse_heads=None, 
         for i, enc in enumerate(encs):
             if type(enc).__name__ == "ConvEncoder":
                 encs[i] = mirror_conv_encoder(enc, shape)
+                if custom_ops:
+                    from . import ops
+                    encs[i].use_custom_ops = True
+                    encs[i]._ops_key = ops.module_key(encs[i])
     ref_clone = type(agent).clone_and_freeze
 
     def clone_and_freeze(self):

@@ -16,6 +16,7 @@ its parameters are ALSO passed as a tensor list so autograd sees them as inputs 
     safedreamer::imagine                        Dreamer._imagine        dreamer.py:673-692 (no_grad in training)
     safedreamer::heads_lambda                   frozen heads + weights + _lambda_return   dreamer.py:589-602
     safedreamer::lambda_return                  Dreamer._lambda_return  dreamer.py:694-707
+    safedreamer::cnn_encoder / cnn_encoder_bwd  ConvEncoder.forward     networks.py:192-234 (+ autograd)
 """
 from __future__ import annotations
 
@@ -319,3 +320,63 @@ def lambda_return(last: Tensor, term: Tensor, reward: Tensor, value: Tensor, boo
 def _(last, term, reward, value, boot, disc, lamb, mod):
     N, T = reward.shape[0], reward.shape[1]
     return reward.new_empty(N, T - 1, 1, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------ CNN encoder
+@torch.library.custom_op("safedreamer::cnn_encoder", mutates_args=())
+def cnn_encoder(obs: Tensor, params: List[Tensor], mod: int, taped: bool) -> Tensor:
+    enc = _mod(mod)
+    frames = int(obs.numel() // (enc._input_shape[0] * enc._input_shape[1] * enc._input_shape[2]))
+    if _capturing(obs):
+        enc._wkey = None       # the weight re-pack must be part of the captured graph (see _engine above)
+    eng = enc._engine(frames, taped)
+    return eng.forward(obs, tape=taped, keep_obs=False)
+
+
+@cnn_encoder.register_fake
+def _(obs, params, mod, taped):
+    enc = _mod(mod)
+    return obs.new_empty(*obs.shape[:-3], enc.out_dim, dtype=torch.float32)
+
+
+@torch.library.custom_op("safedreamer::cnn_encoder_bwd", mutates_args=())
+def cnn_encoder_bwd(d_embed: Tensor, obs: Tensor, params: List[Tensor], mod: int, need_obs: bool,
+                    need_w: bool) -> Tuple[Tensor, List[Tensor]]:
+    enc = _mod(mod)
+    eng = enc._eng
+    if eng is None:
+        raise RuntimeError("safedreamer::cnn_encoder_bwd: no engine (forward not run?)")
+    wg = [torch.zeros_like(p, dtype=torch.float32) for p in params] if need_w else None
+    d_obs = eng.backward(d_embed, want_obs_grad=need_obs, weight_grads=wg, obs=obs)
+    empty = lambda: torch.empty(0, device=d_embed.device)
+    return (d_obs if d_obs is not None else empty(), wg if need_w else [empty() for _ in params])
+
+
+@cnn_encoder_bwd.register_fake
+def _(d_embed, obs, params, mod, need_obs, need_w):
+    enc = _mod(mod)
+    frames = 1
+    for d in d_embed.shape[:-1]:
+        frames *= int(d)
+    e = lambda: d_embed.new_empty(0)
+    return (d_embed.new_empty(frames, *enc._input_shape, dtype=torch.float32) if need_obs else e(),
+            [torch.empty_like(p, dtype=torch.float32) if need_w else e() for p in params])
+
+
+def _cnn_setup(ctx, inputs, output):
+    obs, params, mod, taped = inputs
+    ctx.mod, ctx.params, ctx.obs_shape = mod, params, obs.shape
+    ctx.save_for_backward(obs)
+    ctx.need = (obs.requires_grad, any(p.requires_grad for p in params))
+    if not taped and any(ctx.need):
+        raise RuntimeError("safedreamer::cnn_encoder: gradients requested from an untaped forward")
+
+
+def _cnn_backward(ctx, g):
+    need_obs, need_w = ctx.need
+    (obs,) = ctx.saved_tensors
+    d_obs, wg = torch.ops.safedreamer.cnn_encoder_bwd(g.contiguous(), obs, ctx.params, ctx.mod, need_obs, need_w)
+    return (d_obs.reshape(ctx.obs_shape) if need_obs else None, list(wg) if need_w else [None] * len(ctx.params), None, None)
+
+
+cnn_encoder.register_autograd(_cnn_backward, setup_context=_cnn_setup)

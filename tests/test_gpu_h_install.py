@@ -179,3 +179,33 @@ def test_installed_cnn_encoder_in_the_reference_dreamer():
         rel = float((ge_i[n] - ge_r[n]).norm() / ge_r[n].norm().clamp_min(1e-30))
         print(f"  encoder grad {n:22s} rel L2 diff {rel:.3f}")
         assert rel <= 0.25, n
+
+
+def test_installed_cnn_encoder_under_torch_compile():
+    """The vision agent built with config.compile: `install(agent, encoder=True)` routes the encoder through
+    torch.ops.safedreamer.cnn_encoder / cnn_encoder_bwd inside the compiled `_cal_grad` (CUDA-graph captured)."""
+    RH = _harness()
+    import safe_dreamer_b200
+    from safe_dreamer_b200.encoder import ConvEncoder
+    dev = torch.device("cuda")
+    B, T = 4, 16
+    agent, cfg = RH.build_dreamer(dev, kind="vision", rep_loss="r2dreamer", compile=True)
+    RH.perturb_agent(agent)
+    data, initial = RH.make_batch(agent, B, T, dev, kind="vision")
+    safe_dreamer_b200.install(agent, precision="fp32", imagine_precision="bf16", encoder=True)
+    enc = [e for e in agent.encoder.encoders if isinstance(e, ConvEncoder)][0]
+    assert enc.use_custom_ops
+    outs = []
+    for it in range(3):
+        torch.compiler.cudagraph_mark_step_begin()
+        for p in agent.parameters():
+            p.grad = None
+        with torch.autocast(device_type="cuda", dtype=torch.float16):
+            (st, dt), mets = agent._cal_grad(data, initial)
+        torch.cuda.synchronize()
+        outs.append({k: float(v) for k, v in mets.items()})
+        gn = sum(float(p.grad.float().norm()) for p in agent.encoder.parameters() if p.grad is not None)
+        assert np.isfinite(gn) and gn > 0
+        assert all(np.isfinite(v) for v in outs[-1].values())
+    for k in ("loss/dyn", "loss/rep", "loss/barlow"):
+        assert abs(outs[2][k] - outs[0][k]) <= 0.05 * abs(outs[0][k]) + 1e-3, (k, outs[0][k], outs[2][k])

@@ -56,3 +56,24 @@ def test_forward_only_entries_refuse_gradients():
         assert "forward-only" in str(e)
     else:
         raise AssertionError("img_step accepted an input that requires grad")
+
+
+def test_cnn_encoder_operator_fake_shapes():
+    from safe_dreamer_b200 import ops
+    from safe_dreamer_b200.encoder import ConvEncoder
+    cfg = NS(act="SiLU", norm=True, kernel_size=5, minres=4, depth=16, mults=[2, 3, 4, 4])
+    enc = ConvEncoder(cfg, (64, 64, 3))
+    assert enc.out_dim == 1024
+    assert sorted(enc.state_dict()) == sorted(f"layers.{4 * i + j}.{n}" for i in range(4) for j, n in ((0, "weight"), (0, "bias"), (2, "weight")))
+    key = ops.module_key(enc)
+    assert torch.ops.safedreamer.cnn_encoder.default._schema.name == "safedreamer::cnn_encoder"
+    with FakeTensorMode():
+        params = [torch.empty(p.shape) for p in enc._tensors()]
+        emb = torch.ops.safedreamer.cnn_encoder(torch.empty(2, 5, 64, 64, 3), params, key, True)
+        assert emb.shape == (2, 5, 1024)
+        d_obs, wg = torch.ops.safedreamer.cnn_encoder_bwd(emb, torch.empty(2, 5, 64, 64, 3), params, key, True, True)
+        assert d_obs.shape == (10, 64, 64, 3)
+        assert [tuple(g.shape) for g in wg] == [tuple(p.shape) for p in params]
+    import copy
+    twin = copy.deepcopy(enc)          # dreamer.py:263 clone_and_freeze deep-copies the encoder
+    assert twin._eng is None and twin._ops_key is None and sorted(twin.state_dict()) == sorted(enc.state_dict())
