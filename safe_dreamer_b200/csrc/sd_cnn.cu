@@ -438,10 +438,29 @@ extern "C" int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, cons
       p.partial = h->scratch;
       p.total = frames * Hp * Wp; p.cp = cp; p.cout = h->C[l + 1];
       p.ldo = last ? 0 : h->CS[l + 1]; p.embed = last ? 1 : 0; p.HpWp = Hp * Wp; p.Wp = Wp;
-      int blocks = (p.total + 31) / 32;
-      if (blocks > h->sms * 8) blocks = h->sms * 8;
-      if (cp <= 32) sd::cnn::norm_pool_bwd_kernel<1><<<blocks, 256, 0, st>>>(p);
-      else sd::cnn::norm_pool_bwd_kernel<2><<<blocks, 256, 0, st>>>(p);
+      int blocks;
+      static const bool lanes = getenv("SD_CNN_NORM_LANES") != nullptr;   // A/B switch: the lane-per-channel kernel
+      const bool aligned = last || (h->CS[l + 1] % 4 == 0);
+      static const bool perpx = getenv("SD_CNN_NORM_PX") != nullptr;      // A/B switch: the thread-per-pixel kernel
+      if (!lanes && !perpx && aligned && (cp == 32 || cp == 48 || cp == 64)) {
+        const int ppb = cp == 32 ? 128 : 64;       // pixels per 256-thread block (2 or 4 lanes per pixel)
+        blocks = (p.total + ppb - 1) / ppb;
+        if (blocks > h->sms * 8) blocks = h->sms * 8;
+        if (cp == 32) sd::cnn::norm_pool_bwd_split_kernel<32, 2><<<blocks, 256, 0, st>>>(p);
+        else if (cp == 48) sd::cnn::norm_pool_bwd_split_kernel<48, 4><<<blocks, 256, 0, st>>>(p);
+        else sd::cnn::norm_pool_bwd_split_kernel<64, 4><<<blocks, 256, 0, st>>>(p);
+      } else if (!lanes && aligned && (cp == 32 || cp == 48 || cp == 64)) {
+        blocks = (p.total + 127) / 128;
+        if (blocks > h->sms * 4) blocks = h->sms * 4;
+        if (cp == 32) sd::cnn::norm_pool_bwd_px_kernel<32><<<blocks, 128, 0, st>>>(p);
+        else if (cp == 48) sd::cnn::norm_pool_bwd_px_kernel<48><<<blocks, 128, 0, st>>>(p);
+        else sd::cnn::norm_pool_bwd_px_kernel<64><<<blocks, 128, 0, st>>>(p);
+      } else {
+        blocks = (p.total + 31) / 32;
+        if (blocks > h->sms * 8) blocks = h->sms * 8;
+        if (cp <= 32) sd::cnn::norm_pool_bwd_kernel<1><<<blocks, 256, 0, st>>>(p);
+        else sd::cnn::norm_pool_bwd_kernel<2><<<blocks, 256, 0, st>>>(p);
+      }
       ++launches;
       if (g_b || g_g) {
         sd::cnn::norm_bwd_reduce_kernel<<<1, 128, 0, st>>>(h->scratch, blocks, h->C[l + 1], g_g, g_b);

@@ -18,6 +18,28 @@
 namespace sd {
 namespace cnn {
 
+// sum of p[0], p[stride], ... in a fixed association (sixteen interleaved running sums, then a fixed tree): the same bits on
+// every run, with sixteen loads in flight instead of one
+__device__ __forceinline__ float ordered_sum(const float* __restrict__ p, int n, size_t stride) {
+  float a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = 0.f;
+  int b = 0;
+  for (; b + 16 <= n; b += 16) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __ldg(p + (size_t)(b + k) * stride);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] += v[k];
+  }
+  for (int k = 0; b < n; ++b, ++k) a[k] += __ldg(p + (size_t)b * stride);
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int k = 0; k < w; ++k) a[k] += a[k + w];
+  return a[0];
+}
+
 // ------------------------------------------------------------------------------------------------ 1. norm / pool backward
 struct NormBwdParams {
   const float* pool;      // [total][cp] pooled pre-norm values (forward tape)
@@ -126,13 +148,225 @@ __global__ void __launch_bounds__(256) norm_pool_bwd_kernel(const NormBwdParams 
   }
 }
 
+// Thread-per-pixel variant (the default): a thread keeps its pixel's CP channels in registers, so the row statistics need
+// no shuffles and the per-pixel scalar work (index arithmetic, rsqrt) is done once per pixel instead of once per lane; only
+// the two per-channel sums (d gain, d bias) cross lanes, as one warp reduction per channel and 32 pixels.  ~6x fewer warp
+// instructions per pixel than the lane-per-channel kernel above, which is kept for cp = 16 / odd shapes.
+template <int CP>
+__global__ void __launch_bounds__(128) norm_pool_bwd_px_kernel(const NormBwdParams P) {
+  __shared__ float red[4][2][64];
+  __shared__ float s_g[64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 64) s_g[threadIdx.x] = P.gain[threadIdx.x];
+  __syncthreads();
+  constexpr int NA = (CP + 31) / 32;
+  float acc_g[NA], acc_b[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) { acc_g[k] = 0.f; acc_b[k] = 0.f; }
+  const float inv_c = 1.f / (float)P.cout;
+  const int W = 2 * P.Wp, Hp = P.HpWp / P.Wp;
+  for (int px0 = (blockIdx.x * 4 + warp) * 32; px0 < P.total; px0 += gridDim.x * 128) {
+    const int px = px0 + lane;
+    const bool ok = px < P.total;
+    float p[CP], d[CP];
+    if (ok) {
+      const float4* src = reinterpret_cast<const float4*>(P.pool + (size_t)px * CP);
+#pragma unroll
+      for (int c = 0; c < CP; c += 4) { const float4 t = __ldg(src + (c >> 2)); p[c] = t.x; p[c + 1] = t.y; p[c + 2] = t.z; p[c + 3] = t.w; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CP; ++c) p[c] = 0.f;
+    }
+    const int n = px / P.HpWp, rem = px - n * P.HpWp;
+    if (ok && P.embed) {
+      const float* src = P.dout + (size_t)n * P.cout * P.HpWp + rem;     // (C, H, W) order: consecutive lanes = consecutive addresses
+#pragma unroll
+      for (int c = 0; c < CP; ++c) d[c] = c < P.cout ? __ldg(src + (size_t)c * P.HpWp) : 0.f;
+    } else if (ok) {
+      const float4* src = reinterpret_cast<const float4*>(P.dout + (size_t)px * P.ldo);
+#pragma unroll
+      for (int c = 0; c < CP; c += 4) { const float4 t = __ldg(src + (c >> 2)); d[c] = t.x; d[c + 1] = t.y; d[c + 2] = t.z; d[c + 3] = t.w; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CP; ++c) d[c] = 0.f;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) ss = fmaf(p[c], p[c], ss);
+    const float rho = rsqrtf(ss * inv_c + kRmsEps);
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      const float nn = p[c] * rho, g = s_g[c];
+      const float m = nn * g;
+      const float sg = __fdividef(1.f, 1.f + __expf(-m));
+      const float dm = d[c] * (sg * (1.f + m * (1.f - sg)));
+      float t = dm * nn;                                   // d gain contribution: summed over the warp's 32 pixels
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == (c & 31)) acc_g[c >> 5] += t;
+      d[c] = dm * g;                                       // dn
+      p[c] = nn;
+      dot = fmaf(d[c], nn, dot);
+    }
+    dot *= inv_c;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      const float v = rho * (d[c] - p[c] * dot);           // gradient of the pooled pre-norm value = of the bias
+      float t = v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == (c & 31)) acc_b[c >> 5] += t;
+      p[c] = v;
+    }
+    if (ok) {
+      uint32_t ar[CP / 4];
+      const uint4* asrc = reinterpret_cast<const uint4*>(P.arg + (size_t)px * CP);
+#pragma unroll
+      for (int c = 0; c < CP / 16; ++c) { const uint4 t = __ldg(asrc + c); ar[4 * c] = t.x; ar[4 * c + 1] = t.y; ar[4 * c + 2] = t.z; ar[4 * c + 3] = t.w; }
+      const int py = rem / P.Wp, pxx = rem - py * P.Wp;
+      bf16* base = P.dy + ((size_t)(n * 2 * Hp + 2 * py) * W + 2 * pxx) * CP;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4* dst = reinterpret_cast<uint4*>(base + ((size_t)(q >> 1) * W + (q & 1)) * CP);
+#pragma unroll
+        for (int c = 0; c < CP; c += 8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = ((ar[(c + e) >> 2] >> (8 * ((c + e) & 3))) & 0xffu) == (uint32_t)q ? p[c + e] : 0.f;
+          dst[c >> 3] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NA; ++k)
+    if (lane + 32 * k < 64) { red[warp][0][lane + 32 * k] = acc_g[k]; red[warp][1][lane + 32 * k] = acc_b[k]; }
+  if (NA == 1) { red[warp][0][lane + 32] = 0.f; red[warp][1][lane + 32] = 0.f; }
+  __syncthreads();
+  {
+    const int k = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float s = 0.f;
+    if (c < CP)
+      for (int w = 0; w < 4; ++w) s += red[w][k][c];
+    P.partial[((size_t)blockIdx.x * 2 + k) * 64 + c] = s;
+  }
+}
+
+// Split-pixel variant (the default for cp = 32 / 48 / 64): TPP = 2 or 4 adjacent lanes share a pixel, each with CPT = cp / TPP
+// (16 or 12) of its channels in registers.  Row statistics cost one or two xor-shuffles, the per-channel sums (d gain,
+// d bias) are per-thread running sums over all of the thread's pixels (reduced across lanes once, at the end), every load
+// and store of a pixel group is one contiguous run, and ~90 registers leave 20+ warps per SM to cover the memory latency
+// (the thread-per-pixel kernel above runs at 12 warps per SM and 2.1 TB/s; ncu: profiles/r02_norm_pool_bwd_ncu.txt).
+template <int CP, int TPP>
+__global__ void __launch_bounds__(256) norm_pool_bwd_split_kernel(const NormBwdParams P) {
+  constexpr int CPT = CP / TPP, PPW = 32 / TPP;          // channels per thread, pixels per warp
+  static_assert(CPT % 4 == 0 && CP % TPP == 0, "channel split");
+  __shared__ float red[8][2][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int part = lane % TPP, sub = lane / TPP, c0 = part * CPT;
+  float g[CPT], acc_g[CPT], acc_b[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) { g[j] = P.gain[c0 + j]; acc_g[j] = 0.f; acc_b[j] = 0.f; }
+  const float inv_c = 1.f / (float)P.cout;
+  const int W = 2 * P.Wp, Hp = P.HpWp / P.Wp;
+  for (int px0 = (blockIdx.x * 8 + warp) * PPW; px0 < P.total; px0 += gridDim.x * 8 * PPW) {
+    const int px = px0 + sub;
+    const bool ok = px < P.total;
+    float p[CPT], d[CPT];
+    uint32_t ar[CPT / 4];
+    const int n = px / P.HpWp, rem = px - n * P.HpWp;
+    if (ok) {
+      const float4* src = reinterpret_cast<const float4*>(P.pool + (size_t)px * CP + c0);
+#pragma unroll
+      for (int j = 0; j < CPT; j += 4) { const float4 t = __ldg(src + (j >> 2)); p[j] = t.x; p[j + 1] = t.y; p[j + 2] = t.z; p[j + 3] = t.w; }
+      if (P.embed) {
+        const float* e = P.dout + (size_t)n * P.cout * P.HpWp + rem;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) d[j] = c0 + j < P.cout ? __ldg(e + (size_t)(c0 + j) * P.HpWp) : 0.f;
+      } else {
+        const float4* dsrc = reinterpret_cast<const float4*>(P.dout + (size_t)px * P.ldo + c0);
+#pragma unroll
+        for (int j = 0; j < CPT; j += 4) { const float4 t = __ldg(dsrc + (j >> 2)); d[j] = t.x; d[j + 1] = t.y; d[j + 2] = t.z; d[j + 3] = t.w; }
+      }
+      const uint32_t* asrc = reinterpret_cast<const uint32_t*>(P.arg + (size_t)px * CP + c0);
+#pragma unroll
+      for (int j = 0; j < CPT / 4; ++j) ar[j] = __ldg(asrc + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { p[j] = 0.f; d[j] = 0.f; }
+#pragma unroll
+      for (int j = 0; j < CPT / 4; ++j) ar[j] = 0u;
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) ss = fmaf(p[j], p[j], ss);
+#pragma unroll
+    for (int o = 1; o < TPP; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rho = rsqrtf(ss * inv_c + kRmsEps);
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const float nn = p[j] * rho, m = nn * g[j];
+      const float sg = __fdividef(1.f, 1.f + __expf(-m));
+      const float dm = d[j] * (sg * (1.f + m * (1.f - sg)));
+      acc_g[j] = fmaf(dm, nn, acc_g[j]);
+      d[j] = dm * g[j];
+      p[j] = nn;
+      dot = fmaf(d[j], nn, dot);
+    }
+#pragma unroll
+    for (int o = 1; o < TPP; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    dot *= inv_c;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { p[j] = rho * (d[j] - p[j] * dot); acc_b[j] += p[j]; }
+    if (ok) {
+      const int py = rem / P.Wp, pxx = rem - py * P.Wp;
+      bf16* base = P.dy + ((size_t)(n * 2 * Hp + 2 * py) * W + 2 * pxx) * CP + c0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w[CPT / 2];
+#pragma unroll
+        for (int j = 0; j < CPT; j += 2) {
+          const float v0 = ((ar[j >> 2] >> (8 * (j & 3))) & 0xffu) == (uint32_t)q ? p[j] : 0.f;
+          const float v1 = ((ar[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu) == (uint32_t)q ? p[j + 1] : 0.f;
+          w[j >> 1] = pack2(v0, v1);
+        }
+        uint2* dst = reinterpret_cast<uint2*>(base + ((size_t)(q >> 1) * W + (q & 1)) * CP);
+#pragma unroll
+        for (int j = 0; j < CPT / 4; ++j) dst[j] = make_uint2(w[2 * j], w[2 * j + 1]);
+      }
+    }
+  }
+  // lanes with the same `part` hold sums of the same channels: fold them, then one smem pass over the 8 warps
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+#pragma unroll
+    for (int o = TPP; o < 32; o <<= 1) {
+      acc_g[j] += __shfl_xor_sync(0xffffffffu, acc_g[j], o);
+      acc_b[j] += __shfl_xor_sync(0xffffffffu, acc_b[j], o);
+    }
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { red[warp][0][c0 + j] = acc_g[j]; red[warp][1][c0 + j] = acc_b[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x >> 6, c = threadIdx.x & 63;
+    float s = 0.f;
+    if (c < CP)
+      for (int w = 0; w < 8; ++w) s += red[w][k][c];
+    P.partial[((size_t)blockIdx.x * 2 + k) * 64 + c] = s;
+  }
+}
+
 // sums the per-CTA partials in order and ACCUMULATES into the caller's gradient tensors (nullable)
 __global__ void norm_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int cout, float* __restrict__ d_gain,
                                        float* __restrict__ d_bias) {
   const int k = threadIdx.x >> 6, c = threadIdx.x & 63;
   if (c >= cout) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[((size_t)b * 2 + k) * 64 + c];
+  const float s = ordered_sum(partial + (size_t)k * 64 + c, nblocks, 128);
   float* dst = k == 0 ? d_gain : d_bias;
   if (dst) dst[c] += s;
 }
@@ -578,19 +812,6 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, int cout, int cin
     if (co < cout && ci < cin) v = w[((size_t)co * cin + ci) * (KSZ * KSZ) + tap];
     wT[i] = __float2bfloat16(v);
   }
-}
-
-// sum of p[0], p[stride], ... in a fixed association (eight interleaved running sums, then a fixed tree): the same bits on
-// every run, with eight loads in flight instead of one
-__device__ __forceinline__ float ordered_sum(const float* __restrict__ p, int n, size_t stride) {
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int b = 0;
-  for (; b + 8 <= n; b += 8) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] += __ldg(p + (size_t)(b + k) * stride);
-  }
-  for (int k = 0; b < n; ++b, ++k) a[k] += __ldg(p + (size_t)b * stride);
-  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
 // ------------------------------------------------------------------------------------------------ 3. wgrad
