@@ -13,7 +13,10 @@ step's result back with a blocking D2H copy.  `e2e_async_read` is that loop with
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 Under torchrun every rank runs the same per-GPU workload on its own replay slice (weak scaling).
---impl reference times the CPU port of the reference path (oracle/, numpy on all host cores).
+--impl reference times the UNMODIFIED reference modules (baseline/_ref) on the host cores (oracle port only if that copy is
+absent).  Extra keys: `gpu_reference` (the unmodified reference on THIS GPU, eager in-run, torch.compile from the committed
+run), `schedules_ms` (the three stream schedules of one pass), `roofline` / `roofline_posterior`, `cnn_encoder` (forward and
+forward + backward of the CNN encoder on the same B*T frames, with the reference's own numbers).
 """
 import argparse
 import json
