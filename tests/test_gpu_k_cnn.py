@@ -139,3 +139,44 @@ def test_module_autograd_and_state_dict():
     with pytest.raises(RuntimeError, match="one activation tape"):
         a.sum().backward()
     b.sum().backward()
+
+
+@pytest.mark.parametrize("frames,hw", [(3, 64), (5, 32)])
+def test_odd_frame_counts_and_fallback_kernels(frames, hw):
+    """An odd number of frames: the last pooled-pixel tiles are ragged, the 8x8 stage cannot pair two maps per wgrad tile (so it
+    takes the view-staging wgrad kernel) and the 4x4 / 2x2 maps take the view-staging dgrad.  Same parity gate as above."""
+    depth = 16 if hw == 64 else 4
+    eng, P = _engine(hw, depth, frames, tape=frames)
+    rng = np.random.Generator(np.random.Philox(900 + frames))
+    obs = rng.random((frames, hw, hw, 3), dtype=np.float32)
+    emb = eng.forward(torch.from_numpy(obs).cuda(), tape=True).cpu().numpy()
+    tape = []
+    emb_o = CO.encoder_fwd(P, obs, tape=tape, rnd=CO.round_bf16)
+    assert np.abs(emb - emb_o).max() <= 0.03 and np.abs(emb - emb_o).mean() <= 2e-3
+    g = rng.standard_normal(emb_o.shape, dtype=np.float32)
+    names = []
+    for i in range(4):
+        names += [f"layers.{4 * i}.weight", f"layers.{4 * i}.bias", f"layers.{4 * i + 2}.weight"]
+    wg = [torch.zeros(P[k].shape, device="cuda") for k in names]
+    d_obs = eng.backward(torch.from_numpy(g).cuda(), want_obs_grad=True, weight_grads=wg)
+    torch.cuda.synchronize()
+    d_o, G_o = CO.encoder_bwd(P, tape, g, rnd=CO.round_bf16)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+    assert rel(d_obs.cpu().numpy(), d_o) <= 0.05
+    for k, t in zip(names, wg):
+        assert rel(t.cpu().numpy(), G_o[k]) <= 0.05, k
+
+
+def test_unsupported_shapes_fail_loudly():
+    from safe_dreamer_b200.encoder import CnnEngine
+    with pytest.raises(RuntimeError, match="kernel_size"):
+        CnnEngine(64, 64, 3, [32, 48, 64, 64], kernel=3, max_frames=2)
+    with pytest.raises(RuntimeError, match="input channels"):
+        CnnEngine(64, 64, 1, [32, 48, 64, 64], kernel=5, max_frames=2)
+    with pytest.raises(RuntimeError, match="depth"):
+        CnnEngine(64, 64, 3, [32, 48, 96, 64], kernel=5, max_frames=2)
+    eng = CnnEngine(32, 32, 3, [8, 12, 16, 16], 5, max_frames=2, max_tape_frames=0)
+    with pytest.raises(RuntimeError, match="never called"):
+        eng.forward(torch.zeros(2, 32, 32, 3, device="cuda"))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        eng.forward(torch.zeros(2, 32, 32, 3))
