@@ -403,7 +403,7 @@ static int launch_wgrad_patch(sd_cnn* h, const bf16* x, const bf16* dy, int fram
     fprintf(stderr, "[SD_TRACE_CNN] wgrad-patch CX=%d cp=%d grid %dx%d gph %d smem %d: producer total %lld patch-empty-wait %lld tiles %lld | issuer0 total %lld patch-full-wait %lld\n",
             CX, cp, gx, halves, gph, smem, v[0], v[1], v[3], v[4], v[5]);
   }
-  sd::cnn::wgrad_patch_reduce_kernel<<<400, 256, 0, st>>>(h->scratch, gx, p.ngroups_padded * Cfg::TPG, Cfg::TPG, Cfg::NKG, CX, cp, cout, cin, g_w);
+  sd::cnn::wgrad_patch_reduce_kernel<<<148, 256, 0, st>>>(h->scratch, gx, p.ngroups_padded * Cfg::TPG, Cfg::TPG, Cfg::NKG, CX, cp, cout, cin, g_w);
   return SD_OK;
 }
 
