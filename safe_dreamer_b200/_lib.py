@@ -18,7 +18,8 @@ _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "safedreamer.h")
 # translation units of the library and the headers each one includes (a unit is recompiled when any of them is newer
 # than its object file under csrc/_obj/)
 _UNITS = {
-    "sd_api.cu": ["sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh", "sd_pimg.cuh", "sd_internal.h"],
+    "sd_api.cu": ["sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh", "sd_pimg.cuh", "sd_wgrad_tc.cuh",
+                  "sd_internal.h"],
     "sd_cnn.cu": ["sd_cnn.cuh", "sd_cnn_bwd.cuh", "sd_tc.cuh", "sd_internal.h"],
 }
 _SOURCES = sorted(set(_UNITS) | {h for hs in _UNITS.values() for h in hs})

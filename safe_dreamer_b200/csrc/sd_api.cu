@@ -24,6 +24,7 @@
 #include "sd_chain.cuh"
 #include "sd_scan.cuh"
 #include "sd_pimg.cuh"
+#include "sd_wgrad_tc.cuh"
 
 #include "sd_internal.h"
 using bf16 = __nv_bfloat16;
@@ -163,6 +164,8 @@ struct sd_handle {
   cudaStream_t side_stream = nullptr, cap_side = nullptr;   // direct launches / inside graph capture
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* wg_early = nullptr;           // per layer x per row-slice partials (all layers live at once)
+  bf16* wg_stage = nullptr;            // hi / lo bf16 images of one weight gradient's operands (tcgen05 path)
+  size_t wg_stage_elems = 0;
   // SD_FLAG_BACKGROUND with SD_BG_SMS=n: the call's graph is captured and launched on streams of a green context that
   // owns only n SMs, so the latency-critical stream always finds free SMs (spatial partition instead of time slicing)
   void* bg_ctx = nullptr;              // CUgreenCtx
@@ -565,6 +568,7 @@ static sd::NormActP with_parts(Ctx& cx, sd::NormActP p, const float* parts) {
 }
 
 static bool wgrad_early_enabled() { static int v = env_flag("SD_WGRAD_EARLY", 0); return v != 0; }
+static bool wgrad_tc_enabled() { static int v = env_flag("SD_WGRAD_TC", 1); return v != 0; }
 static bool normact_warp_enabled() { static int v = env_flag("SD_NORM_WARP", 1); return v != 0; }
 static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
   if (cx.err) return;
@@ -953,6 +957,9 @@ static void layout(sd_handle& h, Arena& a) {
     if ((size_t)c.units * F > big) big = (size_t)c.units * F;
     h.wg_scratch_elems = big * 8;
     h.wg_scratch = a.take<float>(h.wg_scratch_elems);
+    // tcgen05 weight gradients: hi + lo images of dY, X and X2 of one layer over all taped rows (widest: gates 3D + h D)
+    h.wg_stage_elems = wgrad_tc_enabled() ? 2 * (size_t)c.max_tape_rows * (T > 1 ? T : 2) * (4 * (size_t)c.D + c.E + 3 * c.U + 64) : 0;
+    h.wg_stage = a.take<bf16>(h.wg_stage_elems);
     // all posterior-path weight tensors x 8 row slices, live at once (early slices overlap the backward scan)
     const size_t rssm_w = (size_t)c.U * c.D + (size_t)c.U * h.SK + (size_t)c.U * c.A + hidw + gruw +
                           (size_t)c.U * (c.D + c.E) + (size_t)(c.obs_layers > 1 ? c.obs_layers - 1 : 0) * c.U * c.U +
@@ -2386,9 +2393,89 @@ static int wgrad_rows_per_slice() {
   static int v = env_flag("SD_WGRAD_ROWS", 256);   // measured on B200 (T*B = 1024 rows): 64: 4.81, 128: 4.78, 256: 4.74, 512: 4.79 ms fwd+bwd
   return v;
 }
+// tcgen05 path of a weight gradient (two-term bf16 split, csrc/sd_wgrad_tc.cuh): all rows in one pass, accumulated straight
+// into dW.  Needs 16-byte friendly operands (every extent, leading dimension, segment boundary and pointer a multiple of 8
+// elements / 16 bytes), enough rows to matter, and the hi / lo images of all operands inside the slice scratch.
+constexpr int kWgTcSlices = 4;     // row slices per tile: 4x the CTAs (the layers have 16-64 tiles), summed in order by the reduce
+static bool wgrad_tc_ok(const sd_handle& h, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride, const float* X,
+                        int ldx, int x_gstride, int K1, const float* X2, int ldx2) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!wgrad_tc_enabled() || R < 256 || L.G > sd::kMaxBatch) return false;
+  if ((L.N & 7) || (L.K & 7) || (K1 & 7) || (ldy & 3) || (ldx & 3) || (dy_gstride & 7) || (x_gstride & 7)) return false;
+  if (!al(dY) || !al(X)) return false;
+  if (K1 < L.K && (!X2 || (ldx2 & 3) || !al(X2))) return false;
+  // columns staged: dY spans G*N (block) or N, X spans the blocks' K1 ranges, X2 the shared tail
+  const size_t ca = (size_t)(block ? (L.G - 1) * dy_gstride : 0) + L.N, cb1 = (size_t)(block ? (L.G - 1) * x_gstride : 0) + K1,
+               cb2 = (size_t)(L.K - K1);
+  const size_t numel = (size_t)L.G * L.N * L.K;
+  return (ca + cb1 + cb2) * (size_t)R * 2 <= h.wg_stage_elems && numel * kWgTcSlices <= h.wg_scratch_elems;
+}
+static void wgrad_linear_tc(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride, const float* X,
+                            int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* dW) {
+  static unsigned long long attr_done = 0;
+  if (!dev_done(attr_done))
+    cudaFuncSetAttribute(sd::wgtc::wgrad_split_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::wgtc::kSmem);
+  sd_handle& h = *cx.h;
+  const int ca = (block ? (L.G - 1) * dy_gstride : 0) + L.N, cb1 = (block ? (L.G - 1) * x_gstride : 0) + K1, cb2 = L.K - K1;
+  bf16* a_hi = h.wg_stage;
+  bf16* a_lo = a_hi + (size_t)R * ca;
+  bf16* b1_hi = a_lo + (size_t)R * ca;
+  bf16* b1_lo = b1_hi + (size_t)R * cb1;
+  bf16* b2_hi = b1_lo + (size_t)R * cb1;
+  bf16* b2_lo = b2_hi + (size_t)R * cb2;
+  float* tile_out = h.wg_scratch;
+  const int slices = R >= kWgTcSlices * 128 ? kWgTcSlices : 1;
+  {
+    sd::wgtc::SplitBatch sb;
+    memset(&sb, 0, sizeof(sb));
+    sb.R = R;
+    long long n4 = 0;
+    auto add = [&](const float* src, int ld, int C, bf16* hi, bf16* lo) {
+      if (C <= 0) return;
+      sb.j[sb.count++] = {src, ld, C, hi, lo};
+      n4 += (long long)R * (C / 4);
+    };
+    add(dY, ldy, ca, a_hi, a_lo);
+    add(X, ldx, cb1, b1_hi, b1_lo);
+    add(X2, ldx2, cb2, b2_hi, b2_lo);
+    launch_k(cx.st, sd::wgtc::split_bf16_kernel, dim3(grid1d(n4, 256)), dim3(256), 0, sb);
+    cx.check("split_bf16_kernel");
+  }
+  sd::wgtc::Batch wb;
+  memset(&wb, 0, sizeof(wb));
+  wb.R = R;
+  wb.rows_per_slice = ((R + slices - 1) / slices + 63) / 64 * 64;
+  wb.slice_stride = (long long)L.G * L.N * L.K;
+  for (int g = 0; g < L.G; ++g) {
+    sd::wgtc::Problem& p = wb.p[wb.count++];
+    p.a_hi = a_hi + (size_t)g * dy_gstride; p.a_lo = a_lo + (size_t)g * dy_gstride; p.lda = ca;
+    p.b1_hi = b1_hi + (size_t)g * x_gstride; p.b1_lo = b1_lo + (size_t)g * x_gstride; p.ldb1 = cb1;
+    p.b2_hi = b2_hi; p.b2_lo = b2_lo; p.ldb2 = cb2;
+    p.K1 = K1; p.K = L.K; p.N = L.N;
+    p.dW = tile_out + (block ? (size_t)g * L.N * L.K : 0);     // dense [g][n][k] partial images (block_finish_kernel re-lays them out)
+    p.sn = L.K;
+    p.sk = 1;
+  }
+  const int kt = L.K >= sd::wgtc::KT_MAX ? sd::wgtc::KT_MAX : (L.K + 15) / 16 * 16;
+  const int nsl = (R + wb.rows_per_slice - 1) / wb.rows_per_slice;
+  dim3 grid((L.N + sd::wgtc::BMN - 1) / sd::wgtc::BMN, (L.K + kt - 1) / kt, wb.count * nsl);
+  launch_k(cx.st, sd::wgtc::wgrad_split_tc_kernel, grid, dim3(sd::wgtc::THREADS), (size_t)sd::wgtc::kSmem, wb, kt);
+  cx.check("wgrad_split_tc_kernel");
+  if (block) {
+    launch_k(cx.st, sd::wgtc::block_finish_kernel, dim3(grid1d((long long)L.N * L.K, 256)), dim3(256), 0, (const float*)tile_out, nsl, L.G,
+             L.N, L.K, dW);
+    cx.check("block_finish_kernel");
+  } else {
+    wgrad_finish(cx, L, tile_out, nsl, dW);
+  }
+}
 static void wgrad_linear(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride,
                          const float* X, int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* dW) {
   if (!dW || cx.err) return;
+  if (wgrad_tc_ok(*cx.h, R, L, block, dY, ldy, dy_gstride, X, ldx, x_gstride, K1, X2, ldx2)) {
+    wgrad_linear_tc(cx, R, L, block, dY, ldy, dy_gstride, X, ldx, x_gstride, K1, X2, ldx2, dW);
+    return;
+  }
   sd_handle& h = *cx.h;
   const long long numel = (long long)L.G * L.N * L.K;
   const int rows_per_slice = wgrad_rows_per_slice();
