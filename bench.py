@@ -592,7 +592,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": units / (ms * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 (imagination/heads GEMMs, fp32 accumulate) + f32 (posterior scan, all sampling)",
+            "vs_baseline": None, "dtype": "bf16 (imagination/heads GEMMs, fp32 accumulate) + f32 (posterior scan, all sampling; its weight gradients as a two-term bf16 split on tcgen05, 5e-6 from the 3xTF32 kernel)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "rows": N, "horizon": H, "posterior_bwd": bool(have_bwd), "schedule": sched["name"],
                        "l2": "256 MB flush write between timed iterations (outside the event pairs)",

@@ -170,26 +170,44 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_split_tc_kernel(const __grid
     const bf16* bl = seg1 ? p.b1_lo + kk : p.b2_lo + (kk - p.K1);
     const size_t b_ld = seg1 ? (size_t)p.ldb1 : (size_t)p.ldb2;
     uint32_t eph = 1;
+    // running source pointers of this thread's first row in the stage; a copy costs an add + the cp.async on the fast path
+    // (a lone producer warp pays ~10 cycles per instruction: per-copy index arithmetic made the first version 3x slower)
+    constexpr int RA = PROD / 16, RB = PROD / 32;                    // row step of the dY / X copies
+    const bf16* pah = p.a_hi + (size_t)(row_lo + ra) * p.lda + a_off;
+    const bf16* pal = p.a_lo + (size_t)(row_lo + ra) * p.lda + a_off;
+    const bf16* pbh = bh + (size_t)(row_lo + rb) * b_ld;
+    const bf16* pbl = bl + (size_t)(row_lo + rb) * b_ld;
+    const size_t sa_step = (size_t)RA * p.lda, sb_step = (size_t)RB * b_ld;
     for (int st = 0, s = 0; st < nst; ++st) {
       mbar_wait(bar_empty + 8 * s, eph);
       const int r0 = row_lo + st * RS;
-      const uint32_t sa = base + (uint32_t)(s * kStage + ca * kPlane), sb = base + (uint32_t)(s * kStage + 2 * kA + cb * kPlane);
+      const uint32_t sa = base + (uint32_t)(s * kStage + ca * kPlane + ra * 16), sb = base + (uint32_t)(s * kStage + 2 * kA + cb * kPlane + rb * 16);
+      if (r0 + RS <= row_hi && a_ok && b_ok) {
 #pragma unroll
-      for (int j = 0; j < RS / (PROD / 16); ++j) {
-        const int r = ra + (PROD / 16) * j;
-        const bool ok = a_ok && r0 + r < row_hi;
-        const size_t o = (size_t)(r0 + r) * p.lda + a_off;
-        cp_async16(sa + (uint32_t)r * 16u, ok ? p.a_hi + o : p.a_hi, ok ? 16u : 0u);
-        cp_async16(sa + (uint32_t)(kA + r * 16), ok ? p.a_lo + o : p.a_hi, ok ? 16u : 0u);
-      }
+        for (int j = 0; j < RS / RA; ++j) {
+          cp_async16(sa + (uint32_t)(j * RA * 16), pah + j * sa_step, 16u);
+          cp_async16(sa + (uint32_t)(kA + j * RA * 16), pal + j * sa_step, 16u);
+        }
 #pragma unroll
-      for (int j = 0; j < RS / (PROD / 32); ++j) {
-        const int r = rb + (PROD / 32) * j;
-        const bool ok = b_ok && r0 + r < row_hi;
-        const size_t o = (size_t)(r0 + r) * b_ld;
-        cp_async16(sb + (uint32_t)r * 16u, ok ? bh + o : p.a_hi, ok ? 16u : 0u);
-        cp_async16(sb + (uint32_t)(kB + r * 16), ok ? bl + o : p.a_hi, ok ? 16u : 0u);
+        for (int j = 0; j < RS / RB; ++j) {
+          cp_async16(sb + (uint32_t)(j * RB * 16), pbh + j * sb_step, 16u);
+          cp_async16(sb + (uint32_t)(kB + j * RB * 16), pbl + j * sb_step, 16u);
+        }
+      } else {
+#pragma unroll 2
+        for (int j = 0; j < RS / RA; ++j) {
+          const bool ok = a_ok && r0 + ra + j * RA < row_hi;
+          cp_async16(sa + (uint32_t)(j * RA * 16), ok ? pah + j * sa_step : p.a_hi, ok ? 16u : 0u);
+          cp_async16(sa + (uint32_t)(kA + j * RA * 16), ok ? pal + j * sa_step : p.a_hi, ok ? 16u : 0u);
+        }
+#pragma unroll 2
+        for (int j = 0; j < RS / RB; ++j) {
+          const bool ok = b_ok && r0 + rb + j * RB < row_hi;
+          cp_async16(sb + (uint32_t)(j * RB * 16), ok ? pbh + j * sb_step : p.a_hi, ok ? 16u : 0u);
+          cp_async16(sb + (uint32_t)(kB + j * RB * 16), ok ? pbl + j * sb_step : p.a_hi, ok ? 16u : 0u);
+        }
       }
+      pah += (size_t)RS * p.lda; pal += (size_t)RS * p.lda; pbh += (size_t)RS * b_ld; pbl += (size_t)RS * b_ld;
       cp_async_arrive(bar_full + 8 * s);
       if (++s == STAGES) { s = 0; eph ^= 1u; }
     }
