@@ -213,8 +213,10 @@ def run_gpu(args):
     #   overlap_layerwise   side stream: 13-launch-per-step sequence (SD_FLAG_BACKGROUND: no PDL pre-launch)
     #   overlap_persistent  side stream: persistent kernel on SD_PIMG_BG_TEAMS (default 4) teams = 64 SMs
     #   serial_persistent   one stream: backward, then the persistent kernel on all 8 teams, then the heads
+    #   overlap_rollout_only  side stream: the launch-sequence rollout only; the heads (saturating 128x256 GEMM tiles) run
+    #                         on the main stream after the backward
     SCHEDULES = {"overlap_layerwise": (True, LAYERWISE | BG), "overlap_persistent": (True, PERSIST | BG),
-                 "serial_persistent": (False, PERSIST)}
+                 "serial_persistent": (False, PERSIST), "overlap_rollout_only": (True, LAYERWISE | BG)}
     if not have_bwd or args.no_overlap:
         SCHEDULES = {"serial_persistent": (False, PERSIST), "serial_layerwise": (False, LAYERWISE)}
     sched = {"name": next(iter(SCHEDULES))}
@@ -230,13 +232,16 @@ def run_gpu(args):
             side.wait_event(ev_fwd)
             with torch.cuda.stream(side):
                 eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH | iflags, out=(feats, actions))
-                eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH | BG, out=outs)
+                if sched["name"] != "overlap_rollout_only":
+                    eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH | BG, out=outs)
                 ev_side.record(side)
         if have_bwd:
             eng.observe_bwd(B, T, gst, gdt, glg, True, True, wgrads, flags=GRAPH)
             bucket.allreduce_async()   # DP: ONE flat NCCL all-reduce of the RSSM grads
         if over:
             main.wait_event(ev_side)
+            if sched["name"] == "overlap_rollout_only":
+                eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
         else:
             eng.imagine(st.reshape(N, c.S, c.K), dt.reshape(N, c.D), ui, noise, H, flags=BF16 | GRAPH | iflags, out=(feats, actions))
             eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs)
