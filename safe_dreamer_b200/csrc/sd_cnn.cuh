@@ -43,8 +43,9 @@ using tc::tc_mma_f16;
 
 constexpr int BM = 128;
 constexpr int THREADS1 = 416;      // stage-1 kernel: warps 0-3 producers, 4 MMA, 5-8 / 9-12 two epilogue groups (accumulator set 0 / 1)
-constexpr int THREADS = 448;       // stages 2..L: + warp 13, the second MMA issuer (window row dy = 1)
+constexpr int THREADS = 480;       // stages 2..L: + warp 13, the second MMA issuer (window row dy = 1), + warp 14, the proxy-fence helper
 constexpr int MMA_WARP2 = 13;
+constexpr int FENCE_WARP = 14;
 constexpr int PROD = 128;          // producer threads (warps 0-3)
 constexpr int MMA_WARP = 4;
 constexpr int KSZ = 5;             // kernel size (configs/base.yaml encoder.cnn.kernel_size)
@@ -228,7 +229,7 @@ struct ConvSmem {
   static constexpr int kStage = RES ? VPS * kA : kA + kBslot;
   static constexpr int kLA = RES ? 4 : 2;                         // cp.async groups in flight per producer thread
   static constexpr int kMaxStages = 16;
-  static constexpr int kFixed = 512 /*bias, gain*/ + 8 * (2 * kMaxStages + 4) + 16 + 256;
+  static constexpr int kFixed = 512 /*bias, gain*/ + 8 * (3 * kMaxStages + 4) + 16 + 256;
   static int resident_bytes(int cp) { return RES ? 25 * KC * cp * 16 : 0; }
   static int stages(int cp) {
     int n = (kConvSmemBudget - kFixed - resident_bytes(cp)) / kStage;
@@ -258,8 +259,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_pool_kernel(const __grid_cons
   float* s_bias = reinterpret_cast<float*>(gbase + off_const);
   float* s_gain = s_bias + 64;
   const uint32_t bar_full = base + (uint32_t)off_const + 512u, bar_empty = bar_full + 8 * L::kMaxStages,
-                 bar_accf = bar_empty + 8 * L::kMaxStages, bar_free = bar_accf + 16, tmem_slot = bar_free + 16;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + off_const + 512 + 8 * (2 * L::kMaxStages + 4));
+                 bar_ready = bar_empty + 8 * L::kMaxStages, bar_accf = bar_ready + 8 * L::kMaxStages, bar_free = bar_accf + 16,
+                 tmem_slot = bar_free + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gbase + off_const + 512 + 8 * (3 * L::kMaxStages + 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 64) {
     s_bias[threadIdx.x] = o.bias[threadIdx.x];
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_pool_kernel(const __grid_cons
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, PROD);
       mbar_init(bar_empty + 8 * s, 2);          // one tcgen05.commit per MMA issuer
+      mbar_init(bar_ready + 8 * s, 1);          // the fence helper
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_accf + 8 * s, 2);
@@ -347,7 +350,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_pool_kernel(const __grid_cons
             }
           }
         }
+        c0 = dbg ? clock64() : 0;
         cp_async_arrive(bar_full + 8 * s);
+        if (dbg) t_grp += clock64() - c0;
         if (++s == STAGES) { s = 0; eph ^= 1u; }
       }
     }
@@ -379,9 +384,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_pool_kernel(const __grid_cons
 #pragma unroll
         for (int vg = 0; vg < 36 / L::VPS; ++vg, ++it) {
           c0 = dbg ? clock64() : 0;
-          mbar_wait(bar_full + 8 * s, fph);
+          mbar_wait(bar_ready + 8 * s, fph);       // data landed AND the helper warp's proxy fence is done
           if (dbg) { t_full += clock64() - c0; c0 = clock64(); }
-          fence_async_smem();      // the views were written through the generic proxy (cp.async); the MMA reads through the async proxy
           tc_fence_after();
           if (dbg) { t_fence += clock64() - c0; c0 = clock64(); }
           const uint32_t stlo = ((ring + (uint32_t)(s * L::kStage)) & 0x3FFFFu) >> 4;
@@ -411,6 +415,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_pool_kernel(const __grid_cons
         tc_commit(bar_accf + 8 * set);
       }
       if (dbg) { P.dbg[4] = clock64() - t0; P.dbg[5] = t_full; P.dbg[6] = t_free; P.dbg[7] = lt; P.dbg[10] = t_fence; P.dbg[11] = t_issue; P.dbg[12] = t_commit; }
+    }
+  } else if (warp == FENCE_WARP) {
+    // The views were written through the generic proxy (cp.async) and the MMA reads them through the async proxy: somebody has
+    // to run fence.proxy.async between the two.  It costs ~500 cycles; in a producer it drains that thread's copies in flight,
+    // in the issuing thread it sat on the critical path of every stage (30 % of the issue loop).  This warp does nothing else:
+    // wait for the stage's data, fence, release the stage to both issuers.
+    if (lane == 0) {
+      int s = 0;
+      uint32_t fph = 0;
+      for (int tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int vg = 0; vg < 36 / L::VPS; ++vg) {
+          mbar_wait(bar_full + 8 * s, fph);
+          fence_async_smem();
+          mbar_arrive(bar_ready + 8 * s);
+          if (++s == STAGES) { s = 0; fph ^= 1u; }
+        }
+      }
     }
   } else {
     // ---------------------------------------------------------------- epilogue: thread = pooled pixel = TMEM lane
