@@ -164,8 +164,10 @@ struct sd_handle {
   cudaStream_t side_stream = nullptr, cap_side = nullptr;   // direct launches / inside graph capture
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* wg_early = nullptr;           // per layer x per row-slice partials (all layers live at once)
-  bf16* wg_stage = nullptr;            // hi / lo bf16 images of one weight gradient's operands (tcgen05 path)
+  bf16* wg_stage = nullptr;            // hi / lo bf16 images of the weight gradients' operands (tcgen05 path)
   size_t wg_stage_elems = 0;
+  float* wg_part = nullptr;            // dense per-slice partial images of every posterior-path weight gradient (batched tcgen05 path)
+  size_t wg_part_elems = 0;
   // SD_FLAG_BACKGROUND with SD_BG_SMS=n: the call's graph is captured and launched on streams of a green context that
   // owns only n SMs, so the latency-critical stream always finds free SMs (spatial partition instead of time slicing)
   void* bg_ctx = nullptr;              // CUgreenCtx
@@ -568,6 +570,7 @@ static sd::NormActP with_parts(Ctx& cx, sd::NormActP p, const float* parts) {
 }
 
 static bool wgrad_early_enabled() { static int v = env_flag("SD_WGRAD_EARLY", 0); return v != 0; }
+constexpr int kWgTcSlicesAlloc = 4;   // row slices of the tcgen05 weight-gradient tiles (partial images allocated for)
 static bool wgrad_tc_enabled() { static int v = env_flag("SD_WGRAD_TC", 1); return v != 0; }
 static bool normact_warp_enabled() { static int v = env_flag("SD_NORM_WARP", 1); return v != 0; }
 static void normact(Ctx& cx, int R, const sd::NormActP* ps, int n) {
@@ -958,8 +961,6 @@ static void layout(sd_handle& h, Arena& a) {
     h.wg_scratch_elems = big * 8;
     h.wg_scratch = a.take<float>(h.wg_scratch_elems);
     // tcgen05 weight gradients: hi + lo images of dY, X and X2 of one layer over all taped rows (widest: gates 3D + h D)
-    h.wg_stage_elems = wgrad_tc_enabled() ? 2 * (size_t)c.max_tape_rows * (T > 1 ? T : 2) * (4 * (size_t)c.D + c.E + 3 * c.U + 64) : 0;
-    h.wg_stage = a.take<bf16>(h.wg_stage_elems);
     // all posterior-path weight tensors x 8 row slices, live at once (early slices overlap the backward scan)
     const size_t rssm_w = (size_t)c.U * c.D + (size_t)c.U * h.SK + (size_t)c.U * c.A + hidw + gruw +
                           (size_t)c.U * (c.D + c.E) + (size_t)(c.obs_layers > 1 ? c.obs_layers - 1 : 0) * c.U * c.U +
@@ -968,6 +969,17 @@ static void layout(sd_handle& h, Arena& a) {
     // dependent launches by as much as they save (fwd+bwd 4.78 -> 4.85 ms, two-stream step 5.70 -> 5.76 ms)
     h.wg_early_elems = wgrad_early_enabled() ? rssm_w * 8 : 0;
     h.wg_early = a.take<float>(h.wg_early_elems);
+    // tcgen05 weight gradients: hi + lo images of dY, X and X2 of ALL posterior layers over all taped rows (dY: 3U + D + 3D +
+    // obs; X: D + SK + D + 3U + D + D + E + U: ~22 k columns at base sizes), and the per-slice partial images
+    {
+      const size_t rows = (size_t)c.max_tape_rows * (T > 1 ? T : 2);
+      const size_t cols = 3 * (size_t)c.U + 4 * c.D + (size_t)c.obs_layers * c.U + h.SK      /* dY */
+                          + 4 * (size_t)c.D + h.SK + 3 * c.U + c.E + (size_t)c.obs_layers * c.U + 256;   /* X, X2 */
+      h.wg_stage_elems = wgrad_tc_enabled() ? 2 * rows * cols : 0;
+      h.wg_stage = a.take<bf16>(h.wg_stage_elems);
+      h.wg_part_elems = wgrad_tc_enabled() ? (size_t)kWgTcSlicesAlloc * rssm_w : 0;
+      h.wg_part = a.take<float>(h.wg_part_elems);
+    }
   }
   h.feat_bf = a.take<bf16>(R * F);
   h.x_bf = a.take<bf16>(R * 3 * c.U);
@@ -2396,7 +2408,7 @@ static int wgrad_rows_per_slice() {
 // tcgen05 path of a weight gradient (two-term bf16 split, csrc/sd_wgrad_tc.cuh): all rows in one pass, accumulated straight
 // into dW.  Needs 16-byte friendly operands (every extent, leading dimension, segment boundary and pointer a multiple of 8
 // elements / 16 bytes), enough rows to matter, and the hi / lo images of all operands inside the slice scratch.
-constexpr int kWgTcSlices = 4;     // row slices per tile: 4x the CTAs (the layers have 16-64 tiles), summed in order by the reduce
+constexpr int kWgTcSlices = kWgTcSlicesAlloc;     // row slices per tile: 4x the CTAs (the layers have 16-64 tiles), summed in order
 static bool wgrad_tc_ok(const sd_handle& h, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride, const float* X,
                         int ldx, int x_gstride, int K1, const float* X2, int ldx2) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
@@ -2469,6 +2481,100 @@ static void wgrad_linear_tc(Ctx& cx, int R, const LinearW& L, bool block, const 
     wgrad_finish(cx, L, tile_out, nsl, dW);
   }
 }
+// one weight gradient of the work list: dW (+)= dY^T [X | X2] for a Linear or the G blocks of a BlockLinear
+struct WgL {
+  const LinearW* L; bool block; const float* dY; int ldy, dyg; const float* X; int ldx, xg, K1; const float* X2; int ldx2;
+  float* dW; size_t off;
+};
+// All tensor-core-eligible layers of the list in three launches (split of every operand, every tile of every layer, finish);
+// marks them done[i] = true.  Returns false (nothing launched) when the staging / partial buffers cannot hold them all.
+static bool wgrad_batch_tc(Ctx& cx, int R, const std::vector<WgL>& wl, std::vector<char>& done) {
+  sd_handle& h = *cx.h;
+  if (!wgrad_tc_enabled() || cx.err) return false;
+  static const bool batched = env_flag("SD_WGRAD_TC_BATCH", 1) != 0;
+  if (!batched) return false;
+  static unsigned long long attr_done = 0;
+  if (!dev_done(attr_done))
+    cudaFuncSetAttribute(sd::wgtc::wgrad_multi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::wgtc::kSmem);
+  sd::wgtc::MultiBatch mb;
+  sd::wgtc::SplitMulti sm;
+  sd::wgtc::FinishMulti fm;
+  memset(&mb, 0, sizeof(mb));
+  memset(&sm, 0, sizeof(sm));
+  memset(&fm, 0, sizeof(fm));
+  const int slices = R >= kWgTcSlices * 128 ? kWgTcSlices : 1;
+  mb.R = R;
+  mb.rows_per_slice = ((R + slices - 1) / slices + 63) / 64 * 64;
+  mb.nslices = (R + mb.rows_per_slice - 1) / mb.rows_per_slice;
+  sm.R = R;
+  size_t st_off = 0, pt_off = 0;       // elements used in the staging (bf16) / partial (fp32) buffers
+  long long split_n4 = 0, fin_n = 0;
+  int tiles = 0;
+  std::vector<int> picked;
+  for (size_t i = 0; i < wl.size(); ++i) {
+    const WgL& l = wl[i];
+    const LinearW& L = *l.L;
+    if (!l.dW || !wgrad_tc_ok(h, R, L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2)) continue;
+    const int ca = (l.block ? (L.G - 1) * l.dyg : 0) + L.N, cb1 = (l.block ? (L.G - 1) * l.xg : 0) + l.K1, cb2 = L.K - l.K1;
+    const size_t need_st = (size_t)R * 2 * (ca + cb1 + cb2), need_pt = (size_t)mb.nslices * L.G * L.N * L.K;
+    if (mb.count + L.G > sd::wgtc::kMaxProb || sm.count + 3 > sd::wgtc::kMaxJobs || fm.count + 1 > sd::wgtc::kMaxLayers ||
+        st_off + need_st > h.wg_stage_elems || pt_off + need_pt > h.wg_part_elems)
+      continue;      // does not fit: this layer takes the one-by-one path
+    bf16* a_hi = h.wg_stage + st_off;
+    bf16* a_lo = a_hi + (size_t)R * ca;
+    bf16* b1_hi = a_lo + (size_t)R * ca;
+    bf16* b1_lo = b1_hi + (size_t)R * cb1;
+    bf16* b2_hi = b1_lo + (size_t)R * cb1;
+    bf16* b2_lo = b2_hi + (size_t)R * cb2;
+    st_off += need_st;
+    auto add_split = [&](const float* src, int ld, int C, bf16* hi, bf16* lo) {
+      if (C <= 0) return;
+      split_n4 += (long long)R * (C / 4);
+      sm.j[sm.count] = {src, ld, C, hi, lo};
+      sm.end[sm.count++] = split_n4;
+    };
+    // an operand another layer already staged (the taped deter rows feed dyn_in0, the hidden block layer and obs_net_0) is
+    // reused: same source, same extent
+    auto staged = [&](const float* src, int ld, int C, bf16*& hi, bf16*& lo) {
+      for (int q = 0; q < sm.count; ++q)
+        if (sm.j[q].src == src && sm.j[q].ld == ld && sm.j[q].C == C) { hi = sm.j[q].hi; lo = sm.j[q].lo; return true; }
+      return false;
+    };
+    if (!staged(l.dY, l.ldy, ca, a_hi, a_lo)) add_split(l.dY, l.ldy, ca, a_hi, a_lo);
+    if (!staged(l.X, l.ldx, cb1, b1_hi, b1_lo)) add_split(l.X, l.ldx, cb1, b1_hi, b1_lo);
+    if (cb2 > 0 && !staged(l.X2, l.ldx2, cb2, b2_hi, b2_lo)) add_split(l.X2, l.ldx2, cb2, b2_hi, b2_lo);
+    float* part = h.wg_part + pt_off;
+    pt_off += need_pt;
+    const long long img = (long long)L.G * L.N * L.K;
+    const int kt = L.K >= sd::wgtc::KT_MAX ? sd::wgtc::KT_MAX : (L.K + 15) / 16 * 16;
+    const int nkt = (L.K + kt - 1) / kt, nnt = (L.N + sd::wgtc::BMN - 1) / sd::wgtc::BMN;
+    for (int g = 0; g < L.G; ++g) {
+      sd::wgtc::Problem& p = mb.p[mb.count];
+      p.a_hi = a_hi + (size_t)g * l.dyg; p.a_lo = a_lo + (size_t)g * l.dyg; p.lda = ca;
+      p.b1_hi = b1_hi + (size_t)g * l.xg; p.b1_lo = b1_lo + (size_t)g * l.xg; p.ldb1 = cb1;
+      p.b2_hi = b2_hi; p.b2_lo = b2_lo; p.ldb2 = cb2;
+      p.K1 = l.K1; p.K = L.K; p.N = L.N;
+      p.dW = part + (size_t)g * L.N * L.K;      // dense [g][n][k] images, one set per row slice
+      p.sn = L.K; p.sk = 1;
+      mb.kt[mb.count] = kt; mb.nkt[mb.count] = nkt; mb.slice_stride[mb.count] = img;
+      tiles += nnt * nkt * mb.nslices;
+      mb.tile_end[mb.count++] = tiles;
+    }
+    fin_n += (long long)L.N * L.K;
+    fm.l[fm.count] = {part, l.dW, L.G, L.N, L.K, mb.nslices, img};
+    fm.end[fm.count++] = fin_n;
+    picked.push_back((int)i);
+  }
+  if (picked.empty()) return false;
+  launch_k(cx.st, sd::wgtc::split_multi_kernel, dim3(grid1d(split_n4, 256)), dim3(256), 0, sm);
+  cx.check("split_multi_kernel");
+  launch_k(cx.st, sd::wgtc::wgrad_multi_tc_kernel, dim3(tiles), dim3(sd::wgtc::THREADS), (size_t)sd::wgtc::kSmem, mb);
+  cx.check("wgrad_multi_tc_kernel");
+  launch_k(cx.st, sd::wgtc::finish_multi_kernel, dim3(grid1d(fin_n, 256)), dim3(256), 0, fm);
+  cx.check("finish_multi_kernel");
+  for (int i : picked) done[i] = 1;
+  return true;
+}
 static void wgrad_linear(Ctx& cx, int R, const LinearW& L, bool block, const float* dY, int ldy, int dy_gstride,
                          const float* X, int ldx, int x_gstride, int K1, const float* X2, int ldx2, float* dW) {
   if (!dW || cx.err) return;
@@ -2537,10 +2643,6 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
     // runs t = T-1 .. 0, so slice s (steps [s*sl_steps, (s+1)*sl_steps)) is final once step s*sl_steps is done: its
     // partial products are launched right then on a forked stream and overlap the rest of the latency-bound scan; only
     // slice 0 and the in-order slice sums remain after the scan.  Same slices, same summation order as the unforked pass.
-    struct WgL {
-      const LinearW* L; bool block; const float* dY; int ldy, dyg; const float* X; int ldx, xg, K1; const float* X2; int ldx2;
-      float* dW; size_t off;
-    };
     std::vector<WgL> wl;
     const int RT = B * T;
     const int Dg = h->Dg;
@@ -2631,8 +2733,13 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
       cudaStreamWaitEvent(cx.st, h->ev_join, 0);
       for (const WgL& l : wl) wgrad_finish(cx, *l.L, h->wg_early + l.off, nsl, l.dW);   // slices summed in ascending order
     } else {
-      for (const WgL& l : wl)
-        wgrad_linear(cx, RT, *l.L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2, l.dW);
+      std::vector<char> done(wl.size(), 0);
+      wgrad_batch_tc(cx, RT, wl, done);
+      for (size_t i = 0; i < wl.size(); ++i)
+        if (!done[i]) {
+          const WgL& l = wl[i];
+          wgrad_linear(cx, RT, *l.L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2, l.dW);
+        }
     }
     int i = 0;
     ColsumList cl;   // bias / RMS-scale gradients of every layer: one launch
