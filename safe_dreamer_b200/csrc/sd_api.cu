@@ -2863,14 +2863,22 @@ extern "C" int sd_prior_bwd(sd_handle* h, int R, const float* d_stoch, const flo
     if (d_deter) cudaMemcpyAsync(d_deter, bw.t_dxe, (size_t)R * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st);
     if (!wg) return;
     int i = 14 + 3 * c.obs_layers + 2;
+    std::vector<WgL> wl;       // the img-net weight gradients go through the batched tcgen05 pass when they qualify
     for (int l = 0; l < c.img_layers; ++l, i += 3) {
-      if (l == 0) wgrad_linear(cx, R, h->img[0], false, bw.d_v[0], U, 0, pt.dnew, D, 0, D, nullptr, 0, W[i]);
-      else wgrad_linear(cx, R, h->img[l], false, bw.d_v[l], U, 0, pt.o[l - 1], U, 0, U, nullptr, 0, W[i]);
+      if (l == 0) wl.push_back({&h->img[0], false, bw.d_v[0], U, 0, pt.dnew, D, 0, D, nullptr, 0, W[i], 0});
+      else wl.push_back({&h->img[l], false, bw.d_v[l], U, 0, pt.o[l - 1], U, 0, U, nullptr, 0, W[i], 0});
       colsum(cx, bw.d_v[l], U, R, U, W[i + 1]);
       colsum(cx, bw.dmn_v[l], U, R, U, W[i + 2]);
     }
-    wgrad_linear(cx, R, h->img_logit, false, d_lg, SK, 0, pt.o[c.img_layers - 1], U, 0, U, nullptr, 0, W[i]);
+    wl.push_back({&h->img_logit, false, d_lg, SK, 0, pt.o[c.img_layers - 1], U, 0, U, nullptr, 0, W[i], 0});
     colsum(cx, d_lg, SK, R, SK, W[i + 1]);
+    std::vector<char> done(wl.size(), 0);
+    wgrad_batch_tc(cx, R, wl, done);
+    for (size_t q = 0; q < wl.size(); ++q)
+      if (!done[q]) {
+        const WgL& l = wl[q];
+        wgrad_linear(cx, R, *l.L, l.block, l.dY, l.ldy, l.dyg, l.X, l.ldx, l.xg, l.K1, l.X2, l.ldx2, l.dW);
+      }
   });
 }
 
