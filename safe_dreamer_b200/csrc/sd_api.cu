@@ -305,7 +305,11 @@ static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n,
   static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
   if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(sd::gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
+    cudaFuncSetAttribute(sd::gemm_f32_bwdepi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::GB_SMEM);
   }
+  bool bwdepi = false;   // a problem with a fused reverse-scan epilogue: the instantiation that carries them
+  for (int i = 0; i < gb.count; ++i) bwdepi = bwdepi || gb.p[i].epi == sd::EPI_GATESBWD;
+  void (*kern)(const sd::GemmBatch, int, int) = bwdepi ? sd::gemm_f32_bwdepi_kernel : sd::gemm_f32_kernel;
   int ksplit = 1;
   while (ksplit < sd::GB_MAXSPLIT && (max_k + ksplit - 1) / ksplit > sd::GB_KC) ksplit *= 2;
   int kslice = ((max_k + ksplit - 1) / ksplit + 3) & ~3;
@@ -323,7 +327,7 @@ static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  prefer_max_smem((const void*)sd::gemm_f32_kernel);
+  prefer_max_smem((const void*)kern);
   static long long* timing_dev = nullptr;
   static int timing_budget = 24;
   if (getenv("SD_TRACE_G") && timing_budget > 0) {
@@ -331,7 +335,7 @@ static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n,
     cudaMemsetAsync(timing_dev, 0, 16 * sizeof(long long), st);
     sd::GemmBatch g2 = gb;
     g2.timing = timing_dev;
-    cudaLaunchKernelEx(&cfg, sd::gemm_f32_kernel, g2, ksplit, kslice);
+    cudaLaunchKernelEx(&cfg, kern, g2, ksplit, kslice);
     cudaStreamSynchronize(st);
     long long t[16];
     cudaMemcpy(t, timing_dev, sizeof(t), cudaMemcpyDeviceToHost);
@@ -341,7 +345,7 @@ static void launch_gemm_f32(cudaStream_t st, const sd::GemmBatch& gb, int max_n,
     --timing_budget;
     return;
   }
-  cudaLaunchKernelEx(&cfg, sd::gemm_f32_kernel, gb, ksplit, kslice);
+  cudaLaunchKernelEx(&cfg, kern, gb, ksplit, kslice);
 }
 
 static thread_local bool tl_no_pdl = false;   // SD_FLAG_BACKGROUND
@@ -2180,7 +2184,27 @@ struct PreNB {
   float* dv; int ld_dv;             // d-tape: grad w.r.t. the pre-norm values (what dy would have been)
   float* dmn; int ld_dmn;           // d-tape: dm * n (RMS-scale gradient term), nullable
 };
-static bool fuse_bwd_enabled() { static int v = env_flag("SD_FUSE_BWD", 1); return v != 0; }
+// Element-wise stage fused behind a dgrad (sd::EPI_GATESBWD, see sd_kernels.cuh): the aux operands of GemmP.
+struct EpiBwd {
+  int epi = 0;
+  const float *x0 = nullptr, *x1 = nullptr, *x2 = nullptr, *x3 = nullptr, *x4 = nullptr, *x5 = nullptr, *x6 = nullptr;
+  float *y0 = nullptr, *y1 = nullptr;
+  int xi0 = 0, xi1 = 0, xi2 = 0, xi3 = 0, xi4 = 0, e_k = 0;
+  float e_f = 0.f;
+};
+static void set_epi(sd::GemmP& p, const EpiBwd& e) {
+  p.epi = e.epi; p.x0 = e.x0; p.x1 = e.x1; p.x2 = e.x2; p.x3 = e.x3; p.x4 = e.x4; p.x5 = e.x5; p.x6 = e.x6; p.y0 = e.y0; p.y1 = e.y1;
+  p.xi0 = e.xi0; p.xi1 = e.xi1; p.xi2 = e.xi2; p.xi3 = e.xi3; p.xi4 = e.xi4; p.e_k = e.e_k; p.e_f = e.e_f;
+}
+// SD_FUSE_BWD bit mask: 1 = RMSNorm backward as the prologue of the dgrad it feeds, 2 = gates_bwd as the epilogue of the posterior
+// net's dgrad.  Measured on B200 (B=16, T=64 reverse scan + dgrad, profiles/r02_bwd_fusion_probe.txt): 1: 2.175 ms, 3: 2.148 ms.
+// Two more fusions were built, tested green and REMOVED because they cost time: sample_bwd of step t-1 behind dyn_in1's dgrad
+// (+0.05 ms) and the three input-norm backwards as prologues of the input dgrads (+0.44 ms: every one of the 384 CTAs re-reads
+// the G block-input gradient slices).  With PDL the element-wise kernels' tape-only work already overlaps their predecessor,
+// so a reverse step is bound by the latency of its five dependent dgrad kernels, not by the number of launches.
+static int fuse_bwd_level() { static int v = env_flag("SD_FUSE_BWD", 3); return v; }
+static bool fuse_bwd_has(int bit) { return (fuse_bwd_level() & 1) && (fuse_bwd_level() & bit); }
+static bool fuse_bwd_enabled() { return fuse_bwd_level() != 0; }
 static bool pre_nb_ok(const Ctx& cx, int width, const PreNB& q) {
   return fuse_bwd_enabled() && !cx.tc && width <= 256 && (width % 4) == 0 && (q.ld_dout % 4) == 0 && (q.ld_v % 4) == 0 &&
          (q.ld_dv % 4) == 0 && (q.ld_dmn % 4) == 0 && ((reinterpret_cast<uintptr_t>(q.dout) | reinterpret_cast<uintptr_t>(q.v) |
@@ -2231,6 +2255,7 @@ struct DgradCall {
   const float* dy; int ld_dy;
   float* dx; int ld_dx;
   int col0, ncols;   // input-column range [col0, col0+ncols) of L (ncols = 0 => all)
+  const EpiBwd* epi = nullptr;   // fused element-wise stage behind this call
 };
 static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n, const PreNB* pre = nullptr) {
   if (cx.err) return;
@@ -2248,6 +2273,7 @@ static void dgrad_multi(Ctx& cx, int R, const DgradCall* calls, int n, const Pre
     p.bias = nullptr;
     p.C = calls[i].dx; p.ldc = calls[i].ld_dx; p.N = nc;
     if (pre) set_pre(p, *pre, i == 0);
+    if (calls[i].epi) set_epi(p, *calls[i].epi);
     if (nc > max_n) max_n = nc;
     if (L.N > max_k) max_k = L.N;
   }
@@ -2272,11 +2298,15 @@ static void sample_bwd(Ctx& cx, const float* lg, int ld_l, const float* u, int l
   cx.check("sample_bwd_kernel");
 }
 // Backward of latent_logits: d(logits) -> d(layer-0 input) [R x K0] in `dx0`; fills the d-tape slots.
-static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, const LinearW* layers,
+// `gates_epi` (nullable): gates_bwd of the same step as the epilogue of the first layer's dgrad (its [0, k_first) column
+// range IS the gc term); returns true when that stage ran here, false when the caller still has to launch gates_bwd_kernel.
+static bool latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, const LinearW* layers,
                               int nl, const LinearW& last, const float* d_lg, float* dx0, int k_first = 0,
-                              float* dx0_b = nullptr, int ld_b = 0, const bf16* d_lg_bf = nullptr) {
+                              float* dx0_b = nullptr, int ld_b = 0, const bf16* d_lg_bf = nullptr,
+                              const EpiBwd* gates_epi = nullptr) {
   sd_handle& h = *cx.h;
   const int U = h.c.U;
+  bool gates_fused = false;
   bf16* dvb = cx.tc ? bw.d_v_bf : nullptr;   // one step's bf16 copy (tcgen05 dgrad; slot 0 callers only)
   dgrad_any(cx, R, last, d_lg, d_lg_bf, h.SK, 0, bw.t_do, U, 0);
   for (int i = nl - 1; i >= 0; --i) {
@@ -2288,6 +2318,7 @@ static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, si
       if (k_first > 0) {
         DgradCall dc[2] = {{&layers[0], dv, U, dx0, k_first, 0, k_first},
                            {&layers[0], dv, U, dx0_b, ld_b, k_first, layers[0].K - k_first}};
+        if (gates_epi && fuse_bwd_has(2)) { dc[0].epi = gates_epi; gates_fused = true; }
         dgrad_multi(cx, R, dc, dx0_b ? 2 : 1, &pre);
       } else dgrad(cx, R, layers[0], dv, U, 0, dx0, layers[0].K, 0, &pre);
       continue;
@@ -2304,13 +2335,14 @@ static void latent_logits_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, si
       dgrad_multi(cx, R, dc, dx0_b ? 2 : 1);
     } else dgrad(cx, R, layers[0], dv, U, 0, dx0, layers[0].K, 0);
   }
+  return gates_fused;
 }
 // Backward of deter_core given g = d(deter') in bw.gd: leaves d(deter_in) parts in bw.dd (+ bw.t_din0),
 // d(stoch) in bw.t_dz and, when want_act, d(abar) in bw.d_abar.
 static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_t slot, int R, bool want_act,
                            const float* deter_in, int ld_in, const float* ga, int ld_a, const float* gb, int ld_b,
                            const float* gc, int ld_c, const float* ga2 = nullptr, const float* dxin_prev = nullptr,
-                           const float* a_scale = nullptr) {
+                           const float* a_scale = nullptr, bool gates_done = false) {
   sd_handle& h = *cx.h;
   const sd_config& c = h.c;
   const int U = c.U, D = c.D, Dg = h.Dg, Kb = Dg + 3 * U;
@@ -2319,9 +2351,11 @@ static void deter_core_bwd(Ctx& cx, const StepBufs& sb, const BwdBufs& bw, size_
   float* d_vin = bw.d_vin + slot * 3 * U;
   if (cx.err) return;
   const bool tcb = cx.tc;   // large-row backward: bf16 copies of the gradients feed the tcgen05 dgrads
-  launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, ga, ld_a, gb, ld_b, gc, ld_c, ga2,
-           dxin_prev, c.G, Kb, a_scale, (const float*)sb.q, deter_in, ld_in, d_q, tcb ? bw.d_q_bf : (bf16*)nullptr, bw.dd, R, D, Dg);
-  cx.check("gates_bwd_kernel");
+  if (!gates_done) {        // (else: ran as the epilogue of the posterior net's dgrad, see latent_logits_bwd)
+    launch_k(cx.st, sd::gates_bwd_kernel, dim3(grid1d((long long)R * D, 256)), dim3(256), 0, ga, ld_a, gb, ld_b, gc, ld_c, ga2,
+             dxin_prev, c.G, Kb, a_scale, (const float*)sb.q, deter_in, ld_in, d_q, tcb ? bw.d_q_bf : (bf16*)nullptr, bw.dd, R, D, Dg);
+    cx.check("gates_bwd_kernel");
+  }
   dgrad_any(cx, R, h.gru, d_q, tcb ? bw.d_q_bf : nullptr, 3 * D, 3 * Dg, bw.t_dh, D, Dg);
   sd::NormActBwdP ph = nbp(bw.t_dh, D, sb.hpre, D, h.hid.gain, D, d_hpre, D, bw.dmn_h + slot * D, D,
                            tcb ? bw.d_hpre_bf : nullptr);
@@ -2683,6 +2717,9 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
     // The carry (grads of a step's input state, cut where is_first) is never materialised inside the loop:
     // the first consumers of step t (sample_bwd, gates_bwd) assemble it from step t+1's pieces
     // (t_dz | dd + t_din0 + dxin[:, g, :Dg]) and step t+1's keep mask.
+    // gates_bwd of step t rides on obs_net_0's dgrad of step t as its epilogue (SD_FUSE_BWD & 2, fp32 path): a reverse step
+    // is 8 dependent launches (sample_bwd, logit dgrad, obs_net_0 dgrad, gate dgrad, hidden-norm backward, hidden dgrad,
+    // input-norm backwards, input dgrads).
     for (int t = T - 1; t >= 0 && !cx.err; --t) {
       StepBufs sb = at_step(base, t, B, *h);
       const bool has_next = t + 1 < T;
@@ -2692,13 +2729,23 @@ extern "C" int sd_observe_bwd(sd_handle* h, int B, int T, const float* d_stochs,
       sample_bwd(cx, sb.lg, SK, sb.ucopy, SK, has_next ? bw.t_dz : nullptr, SK,
                  d_stochs ? d_stochs + (size_t)t * SK : nullptr, T * SK, d_logits ? d_logits + (size_t)t * SK : nullptr, T * SK,
                  B, c.S, c.K, c.unimix, d_lg, SK, nullptr, keep_next);
+      EpiBwd ge;   // gates_bwd of this step (operands as in deter_core_bwd's standalone launch below)
+      ge.epi = sd::EPI_GATESBWD;
+      ge.x0 = has_next ? bw.dd : nullptr; ge.xi0 = D;
+      ge.x1 = d_deters ? d_deters + (size_t)t * D : nullptr; ge.xi1 = T * D;
+      ge.x2 = has_next ? bw.t_din0 : nullptr;
+      ge.x3 = has_next ? bw.t_dxin : nullptr; ge.xi2 = c.G; ge.xi3 = h->Dg + 3 * U;
+      ge.x4 = keep_next;
+      ge.x5 = sb.q; ge.x6 = sb.din; ge.xi4 = D;
+      ge.y0 = bw.d_q + slot * 3 * D; ge.y1 = bw.dd;
+      ge.e_k = h->Dg;
       // d[deter' | embed]: the deter' part goes to a scratch, the embed part straight into d_embed[:, t]
-      latent_logits_bwd(cx, sb, bw, slot, B, h->obs, c.obs_layers, h->obs_logit, d_lg, bw.t_dxe, D,
-                        d_embed ? d_embed + (size_t)t * E : nullptr, T * E);
+      const bool gates_done = latent_logits_bwd(cx, sb, bw, slot, B, h->obs, c.obs_layers, h->obs_logit, d_lg, bw.t_dxe, D,
+                                                d_embed ? d_embed + (size_t)t * E : nullptr, T * E, nullptr, &ge);
       if (cx.err) return;
       deter_core_bwd(cx, sb, bw, slot, B, false, sb.din, D, has_next ? bw.dd : nullptr, D,
                      d_deters ? d_deters + (size_t)t * D : nullptr, T * D, bw.t_dxe, D, has_next ? bw.t_din0 : nullptr,
-                     has_next ? bw.t_dxin : nullptr, keep_next);
+                     has_next ? bw.t_dxin : nullptr, keep_next, gates_done);
       if (cx.err) return;
       if (early && t > 0 && t % sl_steps == 0) {   // slice t / sl_steps is final: fork its partial products
         const int sidx = t / sl_steps;

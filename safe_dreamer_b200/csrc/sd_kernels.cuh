@@ -129,9 +129,20 @@ struct GemmP {
   const float* pre_w;
   float* pre_dv; int pre_lddv;
   float* pre_dmn; int pre_lddmn;
+  // fused epilogue of the reverse posterior scan (single k-slice):
+  //  EPI_GATESBWD: the problem is the deter' column range of the dgrad of obs_net_0 at step t (C = gradient coming back
+  //              through the posterior net, N = D); the thread that owns output element (row, n) continues with
+  //              gates_bwd_kernel of step t for unit n (the gate pre-activations and the step's input deter are forward-tape
+  //              data: fetched, and the gate activations recomputed, BEFORE the PDL wait):
+  //              x0/xi0 carry dd (nullable), x1/xi1 upstream d(deter) (nullable), x2 carry t_din0 (nullable, stride D),
+  //              x3 carry block-input gradient dxin (nullable; xi2 = G, xi3 = Kb), x4 reset cut (nullable), x5 gate
+  //              pre-activations q (stride 3D), x6/xi4 the step's input deter, y0 dq out, y1 dd out, e_k = Dg; D = N.
+  const float *x0, *x1, *x2, *x3, *x4, *x5, *x6;
+  float *y0, *y1;
+  int xi0, xi1, xi2, xi3, xi4;
 };
 enum { PRE_NONE = 0, PRE_NORMBWD = 1 };
-enum { EPI_STORE = 0, EPI_GATES = 1, EPI_SAMPLE = 2 };
+enum { EPI_STORE = 0, EPI_GATES = 1, EPI_SAMPLE = 2, EPI_GATESBWD = 3 };
 constexpr int kMaxBatch = 8;
 struct GemmBatch {
   int count;
@@ -162,7 +173,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 // global round trip (its weight quads + its activation slice are all in flight together), reduces its 64
 // thread-group partials through shared memory, and ships its 16x16 partial tile to the cluster leader through
 // distributed shared memory; the leader adds the slices in rank order (deterministic) and stores.
-__global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ksplit, int kslice) {
+// BWDEPI selects the variant that carries the fused reverse-scan epilogue (EPI_GATESBWD): a separate
+// instantiation, so that the plain kernel keeps its register count (120: two CTAs per SM).
+template <bool BWDEPI>
+__device__ __forceinline__ void gemm_f32_body(const GemmBatch& b, int ksplit, int kslice) {
   SD_G_STAMP(0);
   const int prob = blockIdx.z % b.count, rtile = blockIdx.z / b.count;
   const GemmP& p = b.p[prob];
@@ -239,6 +253,22 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
       pn[i] = make_float4(nn[0], nn[1], nn[2], nn[3]);
       pc[i] = make_float4(cc[0], cc[1], cc[2], cc[3]);
       pre_w4[i] = pw[i];
+    }
+  }
+  // fused backward epilogues: forward-tape operands of this thread's output element and everything that only depends on them
+  const int erow = r0 + (tid >> 4), ecol = n0 + (tid & 15);
+  const bool eok = active && erow < b.R && ecol < p.N;
+  float ef0 = 0.f, ef1 = 0.f, ef2 = 0.f, ef3 = 0.f, ef4 = 0.f;
+  if (BWDEPI && p.epi == EPI_GATESBWD) {   // ef0 = reset gate, ef1 = candidate, ef2 = update gate, ef3 = raw cand pre-activation, ef4 = input deter
+    if (eok) {
+      const int Dg = p.e_k, gi = ecol / Dg, o = ecol - gi * Dg;
+      const size_t qo = (size_t)erow * 3 * p.N + (size_t)gi * 3 * Dg + o;
+      const float qr = __ldg(p.x5 + qo), qu = __ldg(p.x5 + qo + 2 * Dg);
+      ef3 = __ldg(p.x5 + qo + Dg);
+      ef4 = __ldg(p.x6 + (size_t)erow * p.xi4 + ecol);
+      ef0 = sigmoidf_(qr);
+      ef1 = tanhf(ef0 * ef3);
+      ef2 = sigmoidf_(qu - 1.f);
     }
   }
   pdl_prologue();
@@ -422,9 +452,31 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmBatch b, int ks
     }
     return;
   }
+  if (BWDEPI && p.epi == EPI_GATESBWD) {   // gates_bwd_kernel on unit n of this row; `val` is the gc term
+    if (!ok) return;
+    if (p.C) p.C[(size_t)row * p.ldc + n] = val;
+    const int D = p.N, Dg = p.e_k, gi = n / Dg, o = n - gi * Dg;
+    const size_t qo = (size_t)row * 3 * D + (size_t)gi * 3 * Dg + o;
+    const float Rg = ef0, Cc = ef1, Uu = ef2, c = ef3, din = ef4;
+    float carry = p.x0 ? p.x0[(size_t)row * p.xi0 + n] : 0.f;
+    if (p.x2) carry += p.x2[(size_t)row * D + n];
+    if (p.x3) carry += p.x3[((size_t)row * p.xi2 + gi) * (size_t)p.xi3 + o];
+    if (p.x4) carry *= p.x4[row];
+    const float gd = carry + (p.x1 ? p.x1[(size_t)row * p.xi1 + n] : 0.f) + val;
+    const float dUu = gd * (Cc - din);
+    const float dC = gd * Uu;
+    const float dtn = dC * (1.f - Cc * Cc);
+    p.y0[qo] = (dtn * c) * Rg * (1.f - Rg);
+    p.y0[qo + Dg] = dtn * Rg;
+    p.y0[qo + 2 * Dg] = dUu * Uu * (1.f - Uu);
+    p.y1[(size_t)row * D + n] = gd * (1.f - Uu);
+    return;
+  }
   if (ok) p.C[(size_t)row * p.ldc + n] = val;
   SD_G_STAMP(6);
 }
+__global__ void __launch_bounds__(256, 2) gemm_f32_kernel(const GemmBatch b, int ksplit, int kslice) { gemm_f32_body<false>(b, ksplit, kslice); }
+__global__ void __launch_bounds__(256, 2) gemm_f32_bwdepi_kernel(const GemmBatch b, int ksplit, int kslice) { gemm_f32_body<true>(b, ksplit, kslice); }
 
 // ------------------------------------------------------------------------------------------------
 // Weight-gradient GEMM (contraction over rows):  dW[n][k] (+)= sum_r dY[r][n] * X[r][k].
