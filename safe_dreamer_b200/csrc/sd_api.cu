@@ -1868,20 +1868,50 @@ extern "C" int sd_imagine_with_action(sd_handle* h, int R, int T, const float* s
 }
 
 // ------------------------------------------------------------------------------------------------ imagine
+// Everything of an MLPHead behind its first layer -- hidden layers 256 -> 256 (RMSNorm + SiLU) and the last layer -- as ONE
+// row-tile resident launch (sd_chain.cuh): a CTA keeps its 128 rows in shared memory / TMEM across the layers, the weights
+// stream through a TMA ring.  `in_bf` is the first layer's normalised bf16 output.  SD_HEADS_CHAIN=0: one launch per layer.
+static bool heads_chain_enabled() { static int v = env_flag("SD_HEADS_CHAIN", 1); return v != 0; }
+static bool head_chain_ok(const Ctx& cx, const HeadW& hw) {
+  if (!heads_chain_enabled() || !cx.tc || cx.h->c.units != sd::chain::HID || hw.layers < 1 || hw.layers > sd::chain::kMaxLayers) return false;
+  if (hw.last.N > 512 || hw.last.K != sd::chain::HID || !hw.last.w_bf) return false;
+  for (int i = 1; i < hw.layers; ++i)
+    if (hw.l[i].K != sd::chain::HID || hw.l[i].N != sd::chain::HID || !hw.l[i].w_bf || !hw.l[i].gain) return false;
+  return true;
+}
+static void head_chain(Ctx& cx, int R, const HeadW& hw, const bf16* in_bf, int ld_in, float* out, int ld_out) {
+  if (cx.err) return;
+  sd::chain::Params P;
+  memset(&P, 0, sizeof(P));
+  bool ok = (ld_in % 8) == 0 && (reinterpret_cast<uintptr_t>(in_bf) & 15) == 0;
+  for (int i = 1; i < hw.layers; ++i) ok = ok && chain_add_layer(P, hw.l[i], 256);
+  ok = ok && chain_add_layer(P, hw.last, hw.last.N <= 64 ? 64 : 256);
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "chain: tensor map / layer setup failed (head)"); return; }
+  P.R = R; P.n_tiles = (R + 127) / 128;
+  P.in_bf = in_bf; P.ld_in = ld_in;
+  P.fin_mode = 1; P.out = out; P.ld_out = ld_out;
+  P.n_side = 0;
+  launch_chain(cx, P, 0, "chain(head)");
+}
 // MLPHead trunk + last layer on `R` rows of feat (networks.py:339-377); returns last-layer output in `out`.
 static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, float* const* v, float* const* o,
-                         bf16* const* o_bf, float* out, int ld_out, bool keep_prenorm = false) {
+                         bf16* const* o_bf, float* out, int ld_out, bool keep_prenorm = false, bool allow_chain = false) {
   sd_handle& h = *cx.h;
   const int units = h.c.units;
   Operand cur = feat;
   int k = F;
+  const bool chain = allow_chain && !keep_prenorm && head_chain_ok(cx, hw);
   for (int i = 0; i < hw.layers; ++i) {
     // (in-place bf16 input/output is safe for the fused kernel: tiles of different clusters touch different
     //  rows, and inside a cluster every store happens after the cluster barrier that follows all MMAs)
     if (!keep_prenorm && k == hw.l[i].K && (linear_norm_tc(cx, R, hw.l[i], cur, h.sb, o[i], units, o_bf[i], units) ||
                            linear_norm_tc_wide(cx, R, hw.l[i], cur, h.sb,
-                                               (i == hw.layers - 1 && hw.last.N < 64) ? o[i] : nullptr,   // fp32 only when the
-                                               units, o_bf[i], units))) {                                 // last layer is SIMT
+                                               (!chain && i == hw.layers - 1 && hw.last.N < 64) ? o[i] : nullptr,   // fp32 only when the
+                                               units, o_bf[i], units))) {                                           // last layer is SIMT
+      if (chain && i == 0) {   // the rest of the head in one launch
+        head_chain(cx, R, hw, o_bf[0], units, out, ld_out);
+        return;
+      }
       cur = opfb(o[i], units, o_bf[i], units);
       k = units;
       continue;
@@ -2963,7 +2993,7 @@ extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feat
     const bool tc_saved = cx.tc;
     auto run_head = [&](int m, float* rew_like, bool twohot) {
       const HeadW& hw = h->heads[m];
-      head_forward(cx, R, hw, feat, F, v, o, ob, h->hl, up(hw.out, 4));
+      head_forward(cx, R, hw, feat, F, v, o, ob, h->hl, up(hw.out, 4), false, true);
       if (cx.err) return;
       if (twohot) {
         launch_k(cx.st, sd::twohot_mode_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, h->hl, up(hw.out, 4), h->bins, c.bins, R, rew_like);

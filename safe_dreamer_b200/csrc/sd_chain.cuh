@@ -1,5 +1,10 @@
 // sd_chain.cuh -- row-tile resident MLP chain on tcgen05 (sm_100a).
 //
+// On the measured path as the trunk of the frozen heads (reward / cont / value / slow value, dreamer.py:589-596): after the
+// wide first layer (F -> 256) a head is hidden layers 256 -> 256 + a last layer 256 -> bins on N*H = 16384 rows, i.e. 128
+// row tiles: one launch per head instead of one per layer (head_chain in sd_api.cu).  The imagination variants below are
+// opt-in (SD_CHAIN=1): at N = 1024 only 8 CTAs have rows, see profiles/r01b_chain_phase_stamps.txt.
+//
 // The imagination step is a chain of small dependent dense layers: actor2 -> actor3 -> actor head -> action sample
 // -> dyn_in2 (dreamer.py:684, networks.py:339-377, rssm.py:44-48) and img_net_1 -> img_net_logit (rssm.py:119-130).
 // Every one of them is 256 -> 256 (or 256 -> <= 512) on the same rows, so launching them as separate kernels is
@@ -82,6 +87,9 @@ struct Params {
   __nv_bfloat16* x2_bf; int ld_x2;
   Side side[2];
   int n_side;
+  // alternative input: the ALREADY normalised + activated bf16 output of the preceding layer (row stride ld_in elements);
+  // the prologue then only copies rows into the swizzled A tile (frozen-head trunks, networks.py:339-377)
+  const __nv_bfloat16* in_bf;
   long long* timing;   // diagnostic (SD_TRACE_CHAIN=1): clock64 stamps of CTA 0; null in production
 };
 #define SD_CH_STAMP(i) do { if (P.timing && blockIdx.x == 0) P.timing[i] = clock64(); } while (0)
@@ -246,13 +254,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
     // weights (biases, RMS scales) before the PDL wait
     for (int l = 0; l < nl; ++l) {
       const Layer& L = P.layer[l];
-      for (int i = e * 32 + lane; i < 512; i += EPI_WARPS * 32) s_bias[l * 512 + i] = i < L.N ? __ldg(L.bias + i) : 0.f;
+      for (int i = e * 32 + lane; i < 512; i += EPI_WARPS * 32) s_bias[l * 512 + i] = (L.bias && i < L.N) ? __ldg(L.bias + i) : 0.f;
       if (L.gain)
         for (int i = e * 32 + lane; i < HID; i += EPI_WARPS * 32) s_gain[l * HID + i] = __ldg(L.gain + i);
     }
     float gin[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gin[i] = __ldg(P.in_gain + lane * 8 + i);
+    for (int i = 0; i < 8; ++i) gin[i] = P.in_bf ? 0.f : __ldg(P.in_gain + lane * 8 + i);
     if (threadIdx.x == 64) SD_CH_STAMP(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -264,9 +272,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
       const int gr = m0 + rr;
       uint4 pk = make_uint4(0u, 0u, 0u, 0u);
       if (gr < P.R) {
-        float y[8];
-        norm_row_256(P.in + (size_t)gr * P.ld_in, P.parts + (size_t)gr * P.ld_in, P.nparts, P.part_stride, gin, lane, y);
-        pk = pack_bf8(y);
+        if (P.in_bf) {
+          pk = *reinterpret_cast<const uint4*>(P.in_bf + (size_t)gr * P.ld_in + lane * 8);
+        } else {
+          float y[8];
+          norm_row_256(P.in + (size_t)gr * P.ld_in, P.parts + (size_t)gr * P.ld_in, P.nparts, P.part_stride, gin, lane, y);
+          pk = pack_bf8(y);
+        }
       }
       // columns [8*lane, +8) = 16-byte chunk (lane & 7) of k-block (lane >> 3)
       uint8_t* dst = gbase + kOffA + (lane >> 3) * kATile + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4);
