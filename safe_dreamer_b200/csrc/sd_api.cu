@@ -685,10 +685,14 @@ static bool linear_norm_tc_wide(Ctx& cx, int R, const LinearW& L, Operand a, con
 }
 
 // ------------------------------------------------------------------------------------------------ chain kernels
-// SD_CHAIN=1 selects the row-tile resident chain kernels (sd_chain.cuh).  Measured on B200 at N = 1024 they tie with
-// the layer-by-layer path (8 CTAs own all the element-wise work of a 1024 x 256 layer: MUFU / TMEM-read bound, see
-// profiles/r01b_chain_phase_stamps.txt), so the default is the 13-launch variant below; the chain pays at larger N.
-static bool chain_enabled() { static int v = env_flag("SD_CHAIN", 0); return v != 0; }
+// Row-tile resident chain kernels (sd_chain.cuh) inside the launch-sequence rollout.  Measured on B200: at N = 1024 they tie
+// with the layer-by-layer path and at N = 2048 they lose (2.49 vs 2.26 ms: 8-16 CTAs own all the element-wise work of a
+// 256-wide layer, MUFU / TMEM-read bound, profiles/r01b_chain_phase_stamps.txt); at N = 8192 (64 row tiles) they win
+// (6.14 vs 6.57 ms).  Default (SD_CHAIN unset): from 4096 rows; SD_CHAIN=0 / 1 forces them off / on.
+static bool chain_enabled(int N) {
+  static int v = env_flag("SD_CHAIN", -1);
+  return v > 0 || (v < 0 && N >= 4096);
+}
 static bool wide_in_enabled() { static int v = env_flag("SD_WIDE_IN", 1); return v != 0; }
 
 static void launch_chain(Ctx& cx, const sd::chain::Params& P, int side_ctas, const char* what) {
@@ -728,10 +732,10 @@ static bool chain_add_layer(sd::chain::Params& P, const LinearW& L, int box_rows
   return true;
 }
 // The chain kernels cover the base architecture (256-wide hidden layers); anything else keeps the layer-by-layer path.
-static bool imagine_chain_ok(const sd_handle& h) {
+static bool imagine_chain_ok(const sd_handle& h, int N) {
   const sd_config& c = h.c;
   const HeadW& actor = h.heads[SD_MOD_ACTOR];
-  return chain_enabled() && fused_epi_enabled() && c.U == sd::chain::HID && c.units == sd::chain::HID && actor.layers >= 1 &&
+  return chain_enabled(N) && fused_epi_enabled() && c.U == sd::chain::HID && c.units == sd::chain::HID && actor.layers >= 1 &&
          actor.layers <= 3 && h.act_out <= sd::chain::kTailMaxOut && c.A <= 32 && c.img_layers >= 1 && c.img_layers <= 3 &&
          h.SK <= 512 && (h.SK % 64) == 0 && (c.D % 64) == 0 && (h.Dg % 64) == 0 && c.G <= sd::tc::kMaxProblems;
 }
@@ -2045,7 +2049,7 @@ extern "C" int sd_imagine_fwd(sd_handle* h, int N, int H, const float* stoch0, c
     const int ldfb = bigbf ? H * F : F;
     auto fbt = [&](int t) -> bf16* { return bigbf ? h->big_bf + (size_t)t * F : h->feat_bf; };
     if (cx.tc) cast_bf(cx, feats, ldf, fbt(0), ldfb, N, F);
-    const bool use_chain = cx.tc && !tape && imagine_chain_ok(*h);
+    const bool use_chain = cx.tc && !tape && imagine_chain_ok(*h, N);
     const size_t tsm = sd::actor_tail_smem(h->act_out, c.units, A, c.U);
     const bool use_wide = cx.tc && !tape && wide_in_enabled() && fused_epi_enabled() && c.U == 256 && c.units == 256 &&
                           actor.layers >= 1 && h->act_out <= sd::kTailMaxOut && A <= 32 && tsm <= 48 * 1024 &&

@@ -134,3 +134,35 @@ def test_pimg_h16_statistical_parity(full):
         print(f"lambda-return mean / q05 / q50 / q95  fp32: {r32.mean():.5f} {q32}   bf16 {name}: {rb.mean():.5f} {qb}")
         assert abs(rb.mean() - r32.mean()) <= 0.03 * scale, name
         assert np.abs(qb - q32).max() <= 0.06 * scale, name
+
+
+def test_layerwise_chain_rollout_large_n_matches_small_n_and_oracle():
+    """From 4096 rows the launch-sequence rollout runs the actor and img_net trunks as row-tile resident chain kernels
+    (csrc/sd_chain.cuh; SD_CHAIN unset).  Rows are independent, so the first rows of a 4096-row call must agree with the same
+    rows run as a 384-row call (no chain kernels) within the teacher-forced bf16 bounds, and with the fp32 oracle."""
+    c = O.Cfg()
+    P = O.init_params(c, seed=0)
+    N, M, H = 4096, 384, 3
+    eng = make_engine(c, P, max_rows=N, max_steps=H)
+    st0, dt0, u, noise = O.synth_imagine_inputs(c, N, H, seed=41)
+    fc, ac = [_np(x).copy() for x in eng.imagine(cu(st0), cu(dt0), cu(u), cu(noise), H, flags=BF16 | LAYERWISE)]
+    fs, as_ = [_np(x).copy() for x in eng.imagine(cu(st0[:M]), cu(dt0[:M]), cu(u[:M]), cu(noise[:M]), H, flags=BF16 | LAYERWISE)]
+    torch.cuda.synchronize()
+    oh = fc[..., :c.SK].reshape(N, H, c.S, c.K)
+    assert set(np.unique(oh)) == {0.0, 1.0} and np.all(oh.sum(-1) == 1.0)
+    assert np.isfinite(fc).all() and np.isfinite(ac).all()
+    np.testing.assert_array_equal(fc[:, 0, :c.SK], st0.reshape(N, -1))
+    print("chain vs launch sequence: |dact0| =", np.abs(ac[:M, 0] - as_[:, 0]).max(), " |ddeter1| =", np.abs(fc[:M, 1, c.SK:] - fs[:, 1, c.SK:]).max())
+    assert np.abs(ac[:M, 0] - as_[:, 0]).max() <= 0.03
+    assert np.abs(fc[:M, 1, c.SK:] - fs[:, 1, c.SK:]).max() <= 0.04
+    mis = (_idx(fc[:M, 1], c) != _idx(fs[:, 1], c)).mean()
+    print("chain vs launch sequence: step-1 index mismatch rate", mis)
+    assert mis <= 0.02
+    feats_o, acts_o = O.imagine(c, P["rssm"], P["actor"], (st0[:M], dt0[:M]), 2, u[:M], noise[:M])
+    assert np.abs(ac[:M, 0] - acts_o[:, 0]).max() <= 0.03
+    assert np.abs(fc[:M, 1, c.SK:] - feats_o[:, 1, c.SK:]).max() <= 0.04
+    mis_o = (_idx(fc[:M, 1], c) != _idx(feats_o[:, 1], c)).mean()
+    print("chain vs oracle: step-1 index mismatch rate", mis_o)
+    assert mis_o <= 0.02
+    # the last row tile (rows 3968 .. 4095) went through the same kernels: same statistics as the first one
+    assert abs(np.abs(ac[-128:]).mean() - np.abs(ac[:128]).mean()) <= 0.1
