@@ -203,7 +203,7 @@ def run_gpu(args):
     # start states), so they run on a second stream concurrently with the posterior backward scan and the
     # gradient all-reduce; both are latency bound and use disjoint workspace regions.
     side = torch.cuda.Stream(device=dev)
-    ev_fwd, ev_side, ev_w = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    ev_fwd, ev_side, ev_w, ev_w2 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     overlap = have_bwd and not args.no_overlap
 
     PERSIST, LAYERWISE = 32, 64
@@ -431,8 +431,10 @@ def run_gpu(args):
         main0 = torch.cuda.current_stream(dev)
         side.wait_stream(main0)
         with torch.cuda.stream(side):                   # weight repack (weights change once per update in training) runs
-            rssm.refresh_weights(force=True)            # beside the host->device copies of the step's inputs
-            ev_w.record(side)
+            rssm.refresh_weights(force=True, heads=False)   # beside the host->device copies of the step's inputs; the
+            ev_w.record(side)                               # posterior scan waits for the RSSM's tensors only, the heads'
+            rssm.refresh_weights(force=True, rssm=False)    # (needed by the imagination, same stream) repack beside it
+            ev_w2.record(side)
         with torch.no_grad():
             for dst_, src_ in zip(dev_in, (h_embed, h_action, h_first, h_s0, h_d0)):   # host -> device, every step
                 dst_.copy_(src_, non_blocking=True)
@@ -479,6 +481,7 @@ def run_gpu(args):
             if heads_late:   # heads on the main stream: they hide the all-reduce running on NCCL's stream
                 r_ = imag(rollout=False, ft_=r_)
         else:
+            main.wait_event(ev_w2)
             r_ = imag()
         if work is not None:
             work.wait()

@@ -333,8 +333,10 @@ class RSSM(nn.Module):
     def _params(self):
         return list(self._param_dicts()[0][1].values())
 
-    def refresh_weights(self, force=True):
-        """Repack the (possibly updated in place) parameters into the kernels' layouts."""
+    def refresh_weights(self, force=True, heads=True, rssm=True):
+        """Repack the (possibly updated in place) parameters into the kernels' layouts.  `rssm` / `heads` select the RSSM's
+        own tensors and those of the attached head modules: a training step needs the RSSM's before `observe`, the heads'
+        only before the imagination, so a caller may enqueue the two halves at different points (bench.py's end-to-end step)."""
         rt = self._rt
         if rt.engine is None:
             return
@@ -342,8 +344,10 @@ class RSSM(nn.Module):
         sig = tuple((p.data_ptr(), p._version) for p in pds[0][1].values())
         if force or self.auto_refresh or sig != rt.sig:
             for mod, named in pds:
-                rt.engine.set_weights(mod, named)
-            rt.sig = sig
+                if (mod == MOD_RSSM and rssm) or (mod != MOD_RSSM and heads):
+                    rt.engine.set_weights(mod, named)
+            if rssm:
+                rt.sig = sig
 
     def _uniform(self, *shape):
         dev = next(self.parameters()).device
