@@ -168,12 +168,6 @@ struct sd_handle {
   size_t wg_stage_elems = 0;
   float* wg_part = nullptr;            // dense per-slice partial images of every posterior-path weight gradient (batched tcgen05 path)
   size_t wg_part_elems = 0;
-  // SD_FLAG_BACKGROUND with SD_BG_SMS=n: the call's graph is captured and launched on streams of a green context that
-  // owns only n SMs, so the latency-critical stream always finds free SMs (spatial partition instead of time slicing)
-  void* bg_ctx = nullptr;              // CUgreenCtx
-  cudaStream_t bg_cap = nullptr, bg_launch = nullptr;
-  cudaEvent_t ev_bg_in = nullptr, ev_bg_out = nullptr;
-  int bg_state = 0;                    // 0 = not tried, 1 = ready, -1 = unavailable
   size_t wg_early_elems = 0;
   bf16* trunk_bf = nullptr;
   // persistent posterior scan (sd_scan.cuh): input-only precomputations and cross-CTA exchange
@@ -1296,56 +1290,6 @@ struct Key {
   template <class T> Key& add(const T& x) { v = fnv(v, &x, sizeof(T)); return *this; }
 };
 
-template <class Fn>
-static Fn drv(const char* name) {
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
-  return reinterpret_cast<Fn>(p);
-}
-// Green context with SD_BG_SMS SMs for SD_FLAG_BACKGROUND calls (0 / unset = off).  Returns true when its streams exist.
-static bool bg_partition(sd_handle* h) {
-  if (h->bg_state != 0) return h->bg_state > 0;
-  h->bg_state = -1;
-  const int want = env_flag("SD_BG_SMS", 0);
-  if (want <= 0) return false;
-  auto getRes = drv<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
-  auto split = drv<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>(
-      "cuDevSmResourceSplitByCount");
-  auto genDesc = drv<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
-  auto create = drv<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
-  auto mkStream = drv<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
-  if (!getRes || !split || !genDesc || !create || !mkStream) return false;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  CUdevResource all, part, rest;
-  unsigned int groups = 1;
-  CUdevResourceDesc desc;
-  CUgreenCtx g;
-  CUstream s1, s2;
-  CUresult r;
-  if ((r = getRes((CUdevice)dev, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS ||
-      (r = split(&part, &groups, &all, &rest, 0, (unsigned)want)) != CUDA_SUCCESS || groups < 1 ||
-      (r = genDesc(&desc, &part, 1)) != CUDA_SUCCESS ||
-      (r = create(&g, desc, (CUdevice)dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS ||
-      (r = mkStream(&s1, g, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS ||
-      (r = mkStream(&s2, g, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS) {
-    fprintf(stderr, "[safedreamer] SD_BG_SMS=%d: green context unavailable (CUresult %d); background calls share all SMs\n",
-            want, (int)r);
-    return false;
-  }
-  if (cudaEventCreateWithFlags(&h->ev_bg_in, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_bg_out, cudaEventDisableTiming) != cudaSuccess)
-    return false;
-  h->bg_ctx = g;
-  h->bg_cap = (cudaStream_t)s1;
-  h->bg_launch = (cudaStream_t)s2;
-  h->bg_state = 1;
-  if (getenv("SD_BG_VERBOSE"))
-    fprintf(stderr, "[safedreamer] background partition: %u of %u SMs\n", part.sm.smCount, all.sm.smCount);
-  return true;
-}
-
 template <class F>
 static int run(sd_handle* h, uint64_t key, uint32_t flags, cudaStream_t st, bool tc, F&& body) {
   auto direct = [&]() -> int {
@@ -1384,25 +1328,16 @@ static int run(sd_handle* h, uint64_t key, uint32_t flags, cudaStream_t st, bool
     (void)cudaGetLastError();
     return direct();
   }
-  const bool bg = (flags & SD_FLAG_BACKGROUND) && bg_partition(h);
   for (auto& g : h->graphs)
     if (g.key == key) {
-      if (bg) {   // run inside the SM partition, ordered after / before the caller's stream
-        CUDA_TRY(cudaEventRecord(h->ev_bg_in, st));
-        CUDA_TRY(cudaStreamWaitEvent(h->bg_launch, h->ev_bg_in, 0));
-        CUDA_TRY(cudaGraphLaunch(g.exec, h->bg_launch));
-        CUDA_TRY(cudaEventRecord(h->ev_bg_out, h->bg_launch));
-        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_bg_out, 0));
-      } else {
-        CUDA_TRY(cudaGraphLaunch(g.exec, st));
-      }
+      CUDA_TRY(cudaGraphLaunch(g.exec, st));
       g_launches += g.launches;
       return SD_OK;
     }
   // warm any lazily-set function attributes / driver entry points outside capture with a direct run
   // (results are identical; the captured replay below overwrites them).
   if (int e = direct()) return e;
-  cudaStream_t cap = bg ? h->bg_cap : h->cap_stream;
+  cudaStream_t cap = h->cap_stream;
   CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
   Ctx cx{h, cap, tc};
   tl_no_pdl = (flags & SD_FLAG_BACKGROUND) != 0;
