@@ -18,7 +18,7 @@ _INCLUDE = os.path.join(os.path.dirname(_HERE), "include", "safedreamer.h")
 # translation units of the library and the headers each one includes (a unit is recompiled when any of them is newer
 # than its object file under csrc/_obj/)
 _UNITS = {
-    "sd_api.cu": ["sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_scan.cuh", "sd_pimg.cuh", "sd_wgrad_tc.cuh",
+    "sd_api.cu": ["sd_kernels.cuh", "sd_tc.cuh", "sd_bwd.cuh", "sd_chain.cuh", "sd_tc2.cuh", "sd_scan.cuh", "sd_pimg.cuh", "sd_wgrad_tc.cuh",
                   "sd_internal.h"],
     "sd_cnn.cu": ["sd_cnn.cuh", "sd_cnn_bwd.cuh", "sd_tc.cuh", "sd_internal.h"],
 }
@@ -79,7 +79,7 @@ def build(force=False, verbose=False):
                 obj = os.path.join(_OBJ, unit + ".o")
                 deps = [os.path.join(_CSRC, unit), _INCLUDE] + [os.path.join(_CSRC, h) for h in headers]
                 if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in deps):
-                    cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(_CSRC, unit), "-o", obj]
+                    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("SD_NVCC_EXTRA", "").split() + ["-c", os.path.join(_CSRC, unit), "-o", obj]
                     if verbose:
                         print(" ".join(cmd))
                     jobs.append((unit, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

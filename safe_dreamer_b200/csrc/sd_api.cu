@@ -22,6 +22,7 @@
 #include "sd_bwd.cuh"
 #include "sd_tc.cuh"
 #include "sd_chain.cuh"
+#include "sd_tc2.cuh"
 #include "sd_scan.cuh"
 #include "sd_pimg.cuh"
 #include "sd_wgrad_tc.cuh"
@@ -1019,7 +1020,7 @@ static void layout(sd_handle& h, Arena& a) {
   h.abar0 = a.take<float>(R * c.A);
   // heads workspace over N*H rows
   const size_t NH = R * T;
-  h.trunk_bf = a.take<bf16>(NH * c.units);
+  h.trunk_bf = a.take<bf16>(2 * NH * c.units);   // two slabs: the CTA-pair first-layer kernel evaluates two heads per launch
   h.hv = a.take<float>(NH * c.units);
   h.ho = a.take<float>(NH * c.units);
   h.hl = a.take<float>(NH * up(c.bins, 4));
@@ -1818,7 +1819,10 @@ static bool head_chain_ok(const Ctx& cx, const HeadW& hw) {
     if (hw.l[i].K != sd::chain::HID || hw.l[i].N != sd::chain::HID || !hw.l[i].w_bf || !hw.l[i].gain) return false;
   return true;
 }
-static void head_chain(Ctx& cx, int R, const HeadW& hw, const bf16* in_bf, int ld_in, float* out, int ld_out) {
+// `scalar` non-null: the head's scalar (TwoHot.mode over `bins`, or the sigmoid of logit 0 when bins is null) is computed in
+// the chain's last epilogue and the logits are not stored at all.
+static void head_chain(Ctx& cx, int R, const HeadW& hw, const bf16* in_bf, int ld_in, float* out, int ld_out,
+                       float* scalar = nullptr, const float* bins = nullptr) {
   if (cx.err) return;
   sd::chain::Params P;
   memset(&P, 0, sizeof(P));
@@ -1829,8 +1833,40 @@ static void head_chain(Ctx& cx, int R, const HeadW& hw, const bf16* in_bf, int l
   P.R = R; P.n_tiles = (R + 127) / 128;
   P.in_bf = in_bf; P.ld_in = ld_in;
   P.fin_mode = 1; P.out = out; P.ld_out = ld_out;
+  if (scalar) { P.fin_mode = bins ? 3 : 4; P.scalar = scalar; P.bins = bins; }
   P.n_side = 0;
   launch_chain(cx, P, 0, "chain(head)");
+}
+// First layers (F -> 256, RMSNorm, SiLU) of one or two heads that read the same features, on CTA pairs (sd_tc2.cuh:
+// tcgen05 cta_group::2, M = 256 per pair, both heads share the feature tile).  SD_HEADS_PAIR=0: one single-CTA launch per head.
+static bool heads_pair_enabled() { static int v = env_flag("SD_HEADS_PAIR", 1); return v != 0; }
+static bool head_pair_ok(const Ctx& cx, int R, const HeadW& hw, int F) {
+  return heads_pair_enabled() && fused_epi_enabled() && cx.tc && R >= 4096 && (F % 64) == 0 && head_chain_ok(cx, hw) &&
+         hw.l[0].K == F && hw.l[0].N == sd::tc2::NH && hw.l[0].G == 1 && hw.l[0].w_bf && hw.l[0].gain && hw.l[0].npad >= sd::tc2::NH;
+}
+static void heads_first_pair(Ctx& cx, int R, const HeadW* h0, const HeadW* h1, const bf16* feat_bf, int ld_feat, int F,
+                             bf16* out0, bf16* out1, int ld_out) {
+  if (cx.err) return;
+  namespace t2 = sd::tc2;
+  static unsigned long long attr_done = 0;
+  if (!dev_done(attr_done))
+    cudaFuncSetAttribute(t2::heads_first_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t2::kSmem);
+  t2::Params P;
+  memset(&P, 0, sizeof(P));
+  const HeadW* hs[2] = {h0, h1};
+  bf16* outs[2] = {out0, out1};
+  bool ok = make_map(&P.map_a, feat_bf, (uint64_t)R, (uint64_t)F, (uint64_t)ld_feat, 128);
+  P.nheads = h1 ? 2 : 1;
+  for (int i = 0; i < P.nheads; ++i) {
+    const LinearW& L = hs[i]->l[0];
+    ok = ok && make_map(&P.map_w[i], L.w_bf, (uint64_t)L.npad, (uint64_t)F, (uint64_t)F, 128);
+    P.bias[i] = L.bias; P.gain[i] = L.gain; P.out[i] = outs[i];
+  }
+  if (!ok) { cx.err = fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed (head pair)"); return; }
+  P.ld_out = ld_out; P.R = R; P.K = F;
+  const int pairs = (R + 2 * sd::tc::BM - 1) / (2 * sd::tc::BM);
+  launch_k(cx.st, t2::heads_first_pair_kernel, dim3(2 * pairs), dim3(t2::THREADS), (size_t)t2::kSmem, P);
+  cx.check("heads_first_pair_kernel");
 }
 // MLPHead trunk + last layer on `R` rows of feat (networks.py:339-377); returns last-layer output in `out`.
 static void head_forward(Ctx& cx, int R, const HeadW& hw, Operand feat, int F, float* const* v, float* const* o,
@@ -2945,10 +2981,42 @@ extern "C" int sd_heads_lambda_fwd(sd_handle* h, int N, int H, const float* feat
     float* rw = reward ? reward : h->h_rew;
     float* ct = cont ? cont : h->h_cont;
     float* vl = value ? value : h->h_val;
-    run_head(SD_MOD_REWARD, rw, true);
-    run_head(SD_MOD_CONT, ct, false);
-    run_head(SD_MOD_VALUE, vl, true);
-    if (slow_value) run_head(SD_MOD_SLOW_VALUE, slow_value, true);
+    struct Job { int m; float* dst; bool twohot; };
+    Job jobs[4] = {{SD_MOD_REWARD, rw, true}, {SD_MOD_CONT, ct, false}, {SD_MOD_VALUE, vl, true}, {SD_MOD_SLOW_VALUE, slow_value, true}};
+    const int njobs = slow_value ? 4 : 3;
+    bool pair = feat.b != nullptr;
+    for (int j = 0; j < njobs; ++j) pair = pair && head_pair_ok(cx, R, h->heads[jobs[j].m], F);
+    if (pair) {
+      // two heads per CTA-pair launch (they share the feature tiles), then per head: the rest of the trunk + last layer as
+      // one chain launch, and TwoHot.mode / sigmoid
+      bf16* slab[2] = {h->trunk_bf, h->trunk_bf + (size_t)R * c.units};
+      static const int single = env_flag("SD_HEADS_PAIR_SINGLE", 0);   // diagnostic: one head per CTA-pair launch
+      const int stepj = single ? 1 : 2;
+      for (int j = 0; j < njobs && !cx.err; j += stepj) {
+        const HeadW* h1 = (!single && j + 1 < njobs) ? &h->heads[jobs[j + 1].m] : nullptr;
+        heads_first_pair(cx, R, &h->heads[jobs[j].m], h1, feat.b, feat.ldb, F, slab[0], slab[1], c.units);
+        for (int q = j; q < j + stepj && q < njobs && !cx.err; ++q) {
+          const HeadW& hw = h->heads[jobs[q].m];
+          // TwoHot.mode / sigmoid inside the chain's last epilogue: the (R x 255) logits never reach memory
+          const bool fuse_scalar = hw.last.N <= 256 && (!jobs[q].twohot || hw.last.N == c.bins);
+          if (fuse_scalar) {
+            head_chain(cx, R, hw, slab[q - j], c.units, nullptr, 0, jobs[q].dst, jobs[q].twohot ? h->bins : nullptr);
+            continue;
+          }
+          head_chain(cx, R, hw, slab[q - j], c.units, h->hl, up(hw.out, 4));
+          if (cx.err) break;
+          if (jobs[q].twohot) {
+            launch_k(cx.st, sd::twohot_mode_kernel, dim3((R * 32 + 255) / 256), dim3(256), 0, h->hl, up(hw.out, 4), h->bins, c.bins, R, jobs[q].dst);
+            cx.check("twohot_mode_kernel");
+          } else {
+            launch_k(cx.st, sd::sigmoid_kernel, dim3((R + 255) / 256), dim3(256), 0, h->hl, up(hw.out, 4), jobs[q].dst, R);
+            cx.check("sigmoid_kernel");
+          }
+        }
+      }
+    } else {
+      for (int j = 0; j < njobs; ++j) run_head(jobs[j].m, jobs[j].dst, jobs[j].twohot);
+    }
     cx.tc = tc_saved;
     if (cx.err) return;
     if (weight || ret) {

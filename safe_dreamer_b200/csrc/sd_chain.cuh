@@ -75,7 +75,7 @@ struct Params {
   const float* parts; int nparts;
   const float* in_gain;
   long long part_stride;
-  int fin_mode;  // 1: store fp32; 2: actor tail
+  int fin_mode;  // 1: store fp32; 2: actor tail; 3: TwoHot.mode; 4: sigmoid of logit 0
   float* out; int ld_out;
   // actor tail
   int act_out, A, act_kind;
@@ -90,6 +90,10 @@ struct Params {
   // alternative input: the ALREADY normalised + activated bf16 output of the preceding layer (row stride ld_in elements);
   // the prologue then only copies rows into the swizzled A tile (frozen-head trunks, networks.py:339-377)
   const __nv_bfloat16* in_bf;
+  // fin_mode 3: TwoHot.mode of the last layer's `N` logits over `bins` (distributions.py:78-98) -> scalar[row];
+  // fin_mode 4: sigmoid of logit 0 (the cont head's mean, dreamer.py:592) -> scalar[row].  The logits never leave the CTA.
+  const float* bins;
+  float* scalar;
   long long* timing;   // diagnostic (SD_TRACE_CHAIN=1): clock64 stamps of CTA 0; null in production
 };
 #define SD_CH_STAMP(i) do { if (P.timing && blockIdx.x == 0) P.timing[i] = clock64(); } while (0)
@@ -99,7 +103,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.f + __expf(-y)); }
+// y * sigmoid(y) = y * (0.5 + 0.5 tanh(y / 2)): ONE MUFU op per element (exp + reciprocal are two); the epilogues of the
+// 128 x 256 tiles are MUFU bound
+__device__ __forceinline__ float silu_fast(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  return y * fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -267,18 +277,27 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
     if (threadIdx.x == 64) SD_CH_STAMP(2);
 
     // ---- prologue: A0 = SiLU(RMSNorm(in + parts)) for rows e, e+16, ... (warp = row)
+    if (P.in_bf) {   // already normalised bf16 rows: a plain copy into the swizzled tile, the warp's 8 row loads in flight together
+      uint4 pk[BM / EPI_WARPS];
+#pragma unroll
+      for (int i = 0; i < BM / EPI_WARPS; ++i) {
+        const int gr = m0 + e + i * EPI_WARPS;
+        pk[i] = gr < P.R ? *reinterpret_cast<const uint4*>(P.in_bf + (size_t)gr * P.ld_in + lane * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < BM / EPI_WARPS; ++i) {
+        const int rr = e + i * EPI_WARPS;
+        *reinterpret_cast<uint4*>(gbase + kOffA + (lane >> 3) * kATile + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4)) = pk[i];
+      }
+    } else
 #pragma unroll 2
     for (int rr = e; rr < BM; rr += EPI_WARPS) {
       const int gr = m0 + rr;
       uint4 pk = make_uint4(0u, 0u, 0u, 0u);
       if (gr < P.R) {
-        if (P.in_bf) {
-          pk = *reinterpret_cast<const uint4*>(P.in_bf + (size_t)gr * P.ld_in + lane * 8);
-        } else {
-          float y[8];
-          norm_row_256(P.in + (size_t)gr * P.ld_in, P.parts + (size_t)gr * P.ld_in, P.nparts, P.part_stride, gin, lane, y);
-          pk = pack_bf8(y);
-        }
+        float y[8];
+        norm_row_256(P.in + (size_t)gr * P.ld_in, P.parts + (size_t)gr * P.ld_in, P.nparts, P.part_stride, gin, lane, y);
+        pk = pack_bf8(y);
       }
       // columns [8*lane, +8) = 16-byte chunk (lane & 7) of k-block (lane >> 3)
       uint8_t* dst = gbase + kOffA + (lane >> 3) * kATile + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4);
@@ -374,6 +393,64 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const __grid_cons
           cptr += (size_t)4 * P.ld_out;
         }
         __syncwarp();
+      }
+    } else if (P.fin_mode == 3 || P.fin_mode == 4) {
+      // ---- scalar heads: the tile's logits (+ bias) go to shared memory (the A tile and the weight ring are free), then a
+      // warp per row evaluates TwoHot.mode with the operation order of twohot_mode_kernel (softmax, then the reference's
+      // symmetric pairing sum_j (p[m-1-j] b[m-1-j] + p[m+1+j] b[m+1+j]) + p[m] b[m]) or the sigmoid of logit 0
+      constexpr int RLD = 257;
+      float* rows = reinterpret_cast<float*>(gbase + kOffA);   // [128][RLD]
+      const float* bs = s_bias + lf * 512;
+      {
+        float v[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tc::tmem_ld32(trow + (uint32_t)(colq * 64 + hh * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rows[r * RLD + colq * 64 + hh * 32 + j] = v[j] + bs[colq * 64 + hh * 32 + j];
+        }
+      }
+      epi_bar();
+      const int n = LF.N;
+      for (int rr = e; rr < BM; rr += EPI_WARPS) {
+        const int gr = m0 + rr;
+        if (gr >= P.R) break;   // warp-uniform
+        float* lp = rows + rr * RLD;
+        if (P.fin_mode == 4) {
+          if (lane == 0) P.scalar[gr] = sigmoidf_(lp[0]);
+          continue;
+        }
+        float m = -INFINITY;
+        for (int j = lane; j < n; j += 32) m = fmaxf(m, lp[j]);
+        m = warp_max(m);
+        float sm = 0.f;
+        for (int j = lane; j < n; j += 32) {   // the exponentials are computed once and replace the logits in the row buffer
+          const float ex = expf(lp[j] - m);
+          lp[j] = ex;
+          sm += ex;
+        }
+        sm = warp_sum(sm);
+        __syncwarp();
+        float acc = 0.f;
+        if (n & 1) {
+          const int mid = (n - 1) / 2;
+          for (int j = lane; j < mid; j += 32) {
+            const float lo = (lp[mid - 1 - j] / sm) * __ldg(P.bins + mid - 1 - j);
+            const float hi = (lp[mid + 1 + j] / sm) * __ldg(P.bins + mid + 1 + j);
+            acc += lo + hi;
+          }
+          acc = warp_sum(acc);
+          acc += (lp[mid] / sm) * __ldg(P.bins + mid);
+        } else {
+          const int hn = n / 2;
+          for (int j = lane; j < hn; j += 32) {
+            const float lo = (lp[hn - 1 - j] / sm) * __ldg(P.bins + hn - 1 - j);
+            const float hi = (lp[hn + j] / sm) * __ldg(P.bins + hn + j);
+            acc += lo + hi;
+          }
+          acc = warp_sum(acc);
+        }
+        if (lane == 0) P.scalar[gr] = acc;
       }
     } else {
       // ---- actor tail (dreamer.py:684, distributions.py:217-231, rssm.py:44,48)

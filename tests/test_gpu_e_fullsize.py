@@ -132,3 +132,30 @@ def test_imagine_heads_properties(full):
         live = cont[:, i + 1] * disc
         nxt = rew[:, i + 1] + live * ((1 - lamb) * val[:, i + 1] + lamb * nxt)
         np.testing.assert_allclose(ret[:, i], nxt, rtol=2e-4, atol=1e-4)
+
+
+def test_heads_chain_ragged_rows_match_fp32_path():
+    """Frozen-head trunks as one row-tile resident chain launch per head (csrc/sd_chain.cuh, taken from 4096 rows on the bf16
+    path): a row count that is not a multiple of the 128-row tile (300 x 15 = 4500 rows: 35 full tiles + 20 rows) against the
+    fp32 path of the same library (which is pinned to the oracle), and the last rows against the oracle directly."""
+    c = O.Cfg()
+    P = O.init_params(c, seed=0)
+    N, H = 300, 15
+    eng = make_engine(c, P, max_rows=N, max_steps=H)
+    rng = np.random.default_rng(7)
+    feats = np.concatenate([np.eye(c.K, dtype=np.float32)[rng.integers(0, c.K, (N, H, c.S))].reshape(N, H, c.SK),
+                            np.tanh(rng.standard_normal((N, H, c.D))).astype(np.float32)], axis=-1)
+    disc, lamb = 1 - 1 / c.horizon, c.lamb
+    out32 = [_np(x).astype(np.float64) for x in eng.heads_lambda(cu(feats), disc, lamb, flags=0)]
+    outbf = [_np(x).astype(np.float64) for x in eng.heads_lambda(cu(feats), disc, lamb, flags=1)]
+    for name, a, b in zip(("reward", "cont", "value", "slow_value"), outbf, out32):
+        assert np.isfinite(a).all(), name
+        if name == "cont":
+            np.testing.assert_allclose(a, b, atol=0.02, err_msg=name)
+        else:
+            np.testing.assert_allclose(a, b, rtol=0.1, atol=0.05, err_msg=name)
+    M = 8   # the last trajectories live in the ragged tile
+    rew_o, cont_o, val_o, sval_o, wgt_o, ret_o = O.heads_lambda(c, P["reward"], P["cont"], P["value"], P["slow_value"], feats[-M:])
+    np.testing.assert_allclose(outbf[0][-M:], rew_o, rtol=0.1, atol=0.05)
+    np.testing.assert_allclose(outbf[1][-M:], cont_o, atol=0.02)
+    np.testing.assert_allclose(outbf[2][-M:], val_o, rtol=0.1, atol=0.05)
