@@ -1249,6 +1249,15 @@ extern "C" int sd_set_weights(sd_handle* h, int module, const float* const* t, i
     long long nb = (total + 2047) / 2048;
     if (nb < 1) nb = 1;
     if (nb > 592) nb = 592;
+    static const int tiled = env_flag("SD_PACK_TILED", 1);
+    e.mode = 0;
+    if (tiled && !blk && L.G == 1) {                 // nn.Linear (N, K): one block per 64 x 64 tile
+      e.mode = 1;
+      nb = (long long)((L.N + 63) / 64) * ((L.K + 63) / 64);
+    } else if (tiled && blk && L.G == 8) {           // BlockLinear (O/G, I/G, G = 8): one block per 8 x 64 tile of all 8 blocks
+      e.mode = 2;
+      nb = (long long)((L.N + 7) / 8) * ((L.K + 63) / 64);
+    }
     e.blk0 = nblocks; e.nblk = (int)nb;
     nblocks += (int)nb;
   };

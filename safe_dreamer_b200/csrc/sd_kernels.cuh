@@ -648,6 +648,7 @@ struct PackEntry {
   const float* bias_src; float* bias_dst; int nbias;
   const float* gain_src; float* gain_dst; int ngain;
   int blk0, nblk;
+  int mode;   // 0: element-wise (any strides); 1: nn.Linear source, 64 x 64 tiles; 2: BlockLinear source with G = 8, 8 x 64 x 8 tiles
 };
 constexpr int kMaxPack = 16;
 struct PackTable {
@@ -661,6 +662,91 @@ __global__ void __launch_bounds__(256) pack_module_kernel(const PackTable t) {
   const PackEntry& e = t.e[ei];
   const int lb = blockIdx.x - e.blk0;
   const long long total = (long long)e.G * e.N * e.K;
+  if (lb == 0) {
+    if (e.bias_src && e.bias_dst)
+      for (int i = threadIdx.x; i < e.nbias; i += 256) e.bias_dst[i] = e.bias_src[i];
+    if (e.gain_src && e.gain_dst)
+      for (int i = threadIdx.x; i < e.ngain; i += 256) e.gain_dst[i] = e.gain_src[i];
+  }
+  // Tiled paths: a tile of the source is read ONCE with coalesced loads into shared memory and written to the k-contiguous
+  // layouts (Wn, bf16 [n][K]) and, transposed, to the n-contiguous ones (Wt, bf16 [k][N]) with coalesced stores; 32-bit
+  // index arithmetic.  (The element-wise path below costs two strided passes and 64-bit divisions per element: 0.20 ms
+  // for the six modules of the base model, on the critical path of every training step; tiled: see profiles/refresh_time.py.)
+  __shared__ float tile[64 * 65];
+  const int tid = threadIdx.x;
+  if (e.mode == 1) {   // source (N, K), k fastest
+    const int tk = (e.K + 63) >> 6;
+    const int n0 = (lb / tk) << 6, k0 = (lb % tk) << 6;
+    {
+      const int kk = tid & 63, k = k0 + kk;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int nl = (tid >> 6) + 4 * i, n = n0 + nl;
+        const float v = (n < e.N && k < e.K) ? __ldg(e.src + (size_t)n * e.K + k) : 0.f;
+        tile[nl * 65 + kk] = v;
+        if (n < e.N && k < e.K) {
+          if (e.wn) e.wn[(size_t)n * e.ldk + k] = v;
+          if (e.w_bf) e.w_bf[(size_t)n * e.K + k] = __float2bfloat16(v);
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int nn = tid & 63, n = n0 + nn;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int kl = (tid >> 6) + 4 * i, k = k0 + kl;
+        if (n < e.N && k < e.K) {
+          const float v = tile[nn * 65 + kl];
+          if (e.wt) e.wt[(size_t)k * e.ldw + n] = v;
+          if (e.wT_bf) e.wT_bf[(size_t)k * e.N + n] = __float2bfloat16(v);
+        }
+      }
+    }
+    return;
+  }
+  if (e.mode == 2) {   // source (N, K, G = 8), block index fastest; tile = 8 n x 64 k x 8 g, shared memory [g][n][k] (65-float rows)
+    const int tk = (e.K + 63) >> 6;
+    const int n0 = (lb / tk) << 3, k0 = (lb % tk) << 6;
+    const int kw = min(64, e.K - k0);
+    for (int nl = 0; nl < 8; ++nl) {
+      const int n = n0 + nl;
+      if (n >= e.N) break;
+      const float* row = e.src + ((size_t)n * e.K + k0) * 8;   // kw * 8 contiguous floats
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int idx = tid + 256 * j, kl = idx >> 3, g = idx & 7;
+        if (kl < kw) tile[(g * 8 + nl) * 65 + kl] = __ldg(row + idx);
+      }
+    }
+    __syncthreads();
+    {
+      const int kk = tid & 63, k = k0 + kk;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int rs = (tid >> 6) + 4 * i, g = rs >> 3, nl = rs & 7, n = n0 + nl;
+        if (n < e.N && k < e.K) {
+          const float v = tile[rs * 65 + kk];
+          if (e.wn) e.wn[((size_t)g * e.N + n) * e.ldk + k] = v;
+          if (e.w_bf) e.w_bf[((size_t)g * e.npad + n) * e.K + k] = __float2bfloat16(v);
+        }
+      }
+    }
+    {
+      const int nl = tid & 7, n = n0 + nl;
+      for (int g = 0; g < 8; ++g)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int kl = hf * 32 + (tid >> 3), k = k0 + kl;
+          if (n < e.N && k < e.K) {
+            const float v = tile[(g * 8 + nl) * 65 + kl];
+            if (e.wt) e.wt[((size_t)g * e.K + k) * e.ldw + n] = v;
+            if (e.wT_bf) e.wT_bf[((size_t)g * e.kpad + k) * e.N + n] = __float2bfloat16(v);
+          }
+        }
+    }
+    return;
+  }
   // two passes so that every WRITE is coalesced: k fastest for the k-contiguous layouts, n fastest for the n-contiguous
   // ones (the strided reads of the second pass hit L2: a module's weights are a few MB)
   for (long long i = lb * 256ll + threadIdx.x; i < total; i += e.nblk * 256ll) {
@@ -678,12 +764,6 @@ __global__ void __launch_bounds__(256) pack_module_kernel(const PackTable t) {
     const float v = e.src[g * e.s_g + n * e.s_n + k * e.s_k];
     if (e.wt) e.wt[((size_t)g * e.K + k) * e.ldw + n] = v;
     if (e.wT_bf) e.wT_bf[((size_t)g * e.kpad + k) * e.N + n] = __float2bfloat16(v);
-  }
-  if (lb == 0) {
-    if (e.bias_src && e.bias_dst)
-      for (int i = threadIdx.x; i < e.nbias; i += 256) e.bias_dst[i] = e.bias_src[i];
-    if (e.gain_src && e.gain_dst)
-      for (int i = threadIdx.x; i < e.ngain; i += 256) e.gain_dst[i] = e.gain_src[i];
   }
 }
 
