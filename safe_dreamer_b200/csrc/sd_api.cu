@@ -173,7 +173,8 @@ struct sd_handle {
   bf16* trunk_bf = nullptr;
   // persistent posterior scan (sd_scan.cuh): input-only precomputations and cross-CTA exchange
   float *ps_x2 = nullptr, *ps_eproj = nullptr, *ps_ssq = nullptr;
-  int* ps_idx = nullptr;
+  unsigned int* ps_idx = nullptr;   // [16][S] tagged sample indices, followed by ps_ll (one memset clears both)
+  float2* ps_ll = nullptr;          // 3 x [16][256] flagged hand-off buffers of the persistent scan
   unsigned int* ps_bar = nullptr;
   // persistent imagination scan (sd_pimg.cuh): packed shared-slab weights, bf16 exchange buffer, team counters / row statistics
   bf16 *pi_wp7 = nullptr, *pi_wz = nullptr, *pi_act = nullptr;
@@ -1003,7 +1004,8 @@ static void layout(sd_handle& h, Arena& a) {
   h.ps_x2 = a.take<float>((size_t)16 * T * c.U);
   h.ps_eproj = a.take<float>((size_t)16 * T * c.U);
   h.ps_ssq = a.take<float>((size_t)sd::scan::NCTA * 16);
-  h.ps_idx = a.take<int>((size_t)16 * c.S);
+  h.ps_idx = a.take<unsigned int>((size_t)16 * c.S);
+  h.ps_ll = a.take<float2>((size_t)3 * 16 * sd::scan::HW);
   h.ps_bar = a.take<unsigned int>(64);
   if (pimg_shape_ok(h)) {
     h.pi_wp7 = a.take<bf16>((size_t)768 * sd::pimg::D);
@@ -1640,6 +1642,9 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   }
   if (cx.err) return;
   cudaMemsetAsync(h.ps_bar, 0, 64 * sizeof(unsigned int), cx.st);
+  // tags of the flagged hand-offs restart at 1 with every launch (also every replay of a captured graph): clear the old ones
+  cudaMemsetAsync(h.ps_idx, 0, (size_t)16 * c.S * sizeof(unsigned int), cx.st);
+  cudaMemsetAsync(h.ps_ll, 0, (size_t)3 * 16 * sd::scan::HW * sizeof(float2), cx.st);
   sd::scan::Params P;
   memset(&P, 0, sizeof(P));
   P.B = B; P.T = T; P.D = D; P.SK = SK; P.S = c.S; P.K = c.K; P.G = c.G; P.E = E; P.A = A; P.unimix = c.unimix;
@@ -1656,6 +1661,7 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   P.lg = base.lg; P.vobs = base.vobs[0]; P.o = base.o[0];
   P.step = tape ? 1 : 0;
   P.ssq_h = h.ps_ssq; P.idx = h.ps_idx; P.bar = h.ps_bar;
+  P.ll_x0 = h.ps_ll; P.ll_vobs = h.ps_ll + 16 * sd::scan::HW; P.ll_x1 = h.ps_ll + 2 * 16 * sd::scan::HW;
   static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
   if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(sd::scan::observe_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::scan::kSmemBytes);

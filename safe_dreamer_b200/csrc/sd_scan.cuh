@@ -64,7 +64,8 @@ struct Params {
   float *zin, *din, *vin, *x, *hpre, *h, *q, *lg, *vobs, *o;
   int step;
   float* ssq_h;        // [128 tiles][16 rows]
-  int* idx;            // [16][S]
+  unsigned int* idx;   // [16][S]: (tag << 8) | class index of the step's sample
+  float2 *ll_x0, *ll_vobs, *ll_x1;   // [16][256] {value, tag} pairs: flagged hand-offs P3 -> next hidden layer, P3 -> P4, P5 -> P1
   unsigned int* bar;   // grid barrier counter, zeroed before the launch
   long long* timing;   // diagnostic (SD_TRACE_SCAN=1): clock64 stamps of CTA 0 / 40 during step 2; null in production
 };
@@ -94,6 +95,44 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int& epoch
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncthreads();
+}
+
+// Flagged hand-offs ("LL": value and tag travel in ONE 8-byte store, so the consumer may poll the data itself -- no fence,
+// no counter).  Three of the five phase boundaries of a step have few producers (the 16 P3 cluster leaders, the 32 sampling
+// CTAs, the 16 P5 CTAs): there a grid barrier costs a store-ack wait + an atomic + a poll (~2.7k cycles); polling the
+// tagged data is one L2 hop behind the producer's store.  Tag = step + 1 of the producing step; the host zeroes the
+// buffers before every launch (also inside a replayed graph), so a stale tag can never match.  Re-use is safe because the
+// two remaining grid barriers (after P1 and P2) of the next step lie between any consumer's read and the producer's next write.
+__device__ __forceinline__ void ll_store(float2* p, float v, unsigned int tag) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+// One lane per warp waits for the tag of ONE element before the whole warp polls its data: 80+ CTAs spinning with every
+// thread on the same 32 KB (measured) saturate the L2 slices that hold it and slow the producers down.
+__device__ __forceinline__ void ll_prewait(const void* tagword, unsigned int tag, bool lane_polls) {
+  if (lane_polls) {
+    unsigned int v = 0;
+#pragma unroll 1
+    for (unsigned int spin = 0; spin < (1u << 24); ++spin) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tagword) : "memory");
+      if (v == tag) break;
+    }
+    if (v != tag) __trap();
+  }
+  __syncwarp();
+}
+// 4 consecutive values (p is 32-byte aligned: the lane's float4 of the plain layout); bounded spin, trap on a protocol bug
+__device__ __forceinline__ float4 ll_load4(const float2* p, unsigned int tag) {
+  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  bool ok = false;
+#pragma unroll 1
+  for (unsigned int spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "l"(p + 2) : "memory");
+    ok = (a1 == tag) && (a3 == tag) && (b1 == tag) && (b3 == tag);
+    if (ok) break;
+  }
+  if (!ok) __trap();
+  return make_float4(__uint_as_float(a0), __uint_as_float(a2), __uint_as_float(b0), __uint_as_float(b2));
 }
 
 // copy W[k0 .. k0+K)[col0 .. col0+16) (global, row stride ld) into the swizzled k-quad-major layout:
@@ -200,14 +239,21 @@ __device__ __forceinline__ void normact8(const float4 (&v)[2], float rs, const f
 // First half of the block-GRU hidden layer of step tt: s_a = W_hid[g][:, 0:512] . [keep * d_g | x0], x0 = SiLU(RMSNorm(v_in0)).
 // Neither operand depends on the sample of the previous step (v_in0 is produced two phases earlier, in P3), so this
 // runs in the otherwise idle P4 / P5 slot and only its 16x16 partial tile (one float per thread) is carried into P1.
-__device__ __noinline__ float hid_first_half(const float* dsrc, float keep, const float* v0src, bool lok, float* A_s,
-                                             const float* W1, const float* G_s, int lrow, int ls, float* din_t, float* x_t) {
+// v0 comes from the plain buffer (step 0: written by the host-side launches) or, when v0ll is set, from the flagged hand-off.
+__device__ __noinline__ float hid_first_half(const float* dsrc, float keep, const float* v0src, const float2* v0ll, unsigned int tag,
+                                             bool lok, float* A_s, const float* W1, const float* G_s, int lrow, int ls,
+                                             float* din_t, float* x_t) {
   float4 dv[2], v0[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int k = i * 128 + ls * 4;
     dv[i] = lok ? ldcg4(dsrc + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    v0[i] = lok ? ldcg4(v0src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!v0ll) v0[i] = lok ? ldcg4(v0src + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (v0ll) {
+    ll_prewait(reinterpret_cast<const unsigned int*>(v0ll) + 1, tag, lok && ls == 0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) v0[i] = lok ? ll_load4(v0ll + i * 128 + ls * 4, tag) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float ss0 = warp_sum(sq4(v0[0]) + sq4(v0[1]));
   const float rs0 = 1.f / sqrtf(ss0 / (float)HW + kRmsEps);
@@ -278,7 +324,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   __syncthreads();
   // first half of step 0's hidden layer (v_in0 of step 0 comes from the host-side launches)
   float s_a = hid_first_half(P.init_deter + (size_t)lrow * D + g * HW, (lok && P.is_first[(size_t)lrow * T]) ? 0.f : 1.f,
-                             P.vin + (size_t)lrow * (3 * HW), lok, A_s, W1, G_s, lrow, ls,
+                             P.vin + (size_t)lrow * (3 * HW), nullptr, 0u, lok, A_s, W1, G_s, lrow, ls,
                              (P.step && lok && jt == 0) ? P.din + (size_t)lrow * D + g * HW : nullptr,
                              (P.step && lok && cta == 0) ? P.x + (size_t)lrow * (3 * HW) : nullptr);
 
@@ -288,6 +334,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     const float keep_n = (t + 1 < T && rok && P.is_first[(size_t)row * T + t + 1]) ? 0.f : 1.f;
     const float lkeep_n = (t + 1 < T && lok && P.is_first[(size_t)lrow * T + t + 1]) ? 0.f : 1.f;
     float* vin_t = P.vin + (size_t)t * sstep * (3 * HW);
+    const unsigned int tag = (unsigned int)t + 1u;   // of everything this step hands over through the flagged buffers
     float* hpre_t = P.hpre + (size_t)t * sstep * D;
     float* vobs_t = P.vobs + (size_t)t * sstep * HW;
     // pure inputs of this step, fetched now so that their latency is hidden behind P1 / P2
@@ -301,8 +348,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int k = i * 128 + ls * 4;
-        v1[i] = lok ? ldcg4(vin_t + (size_t)lrow * (3 * HW) + HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t == 0) v1[i] = lok ? ldcg4(vin_t + (size_t)lrow * (3 * HW) + HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         xv2[i] = lok ? __ldg(reinterpret_cast<const float4*>(P.x2 + ((size_t)t * B + lrow) * HW + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (t > 0) {   // produced by P5 of the previous step (tag t)
+        ll_prewait(reinterpret_cast<const unsigned int*>(P.ll_x1 + lrow * HW) + 1, tag - 1u, lok && ls == 0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          v1[i] = lok ? ll_load4(P.ll_x1 + lrow * HW + i * 128 + ls * 4, tag - 1u) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       const float ss1 = warp_sum(sq4(v1[0]) + sq4(v1[1]));
       const float rs1 = 1.f / sqrtf(ss1 / (float)HW + kRmsEps);
@@ -401,26 +454,31 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
         const float extra = bias_3 + ep_t;   // bias (+ embed part of obs_net_0)
         const float tot = ((slots[tid] + slots[256 + tid]) + slots[512 + tid]) + slots[768 + tid];
         if (p3 == 0) {
-          if (t + 1 < T) P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + n] = extra + keep_n * tot;
+          if (t + 1 < T) {
+            const float v = extra + keep_n * tot;
+            ll_store(P.ll_x0 + row * HW + n, v, tag);
+            P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + n] = v;   // backward tape
+          }
         } else {
-          vobs_t[(size_t)row * HW + n] = tot + extra;
+          ll_store(P.ll_vobs + row * HW + n, tot + extra, tag);
+          vobs_t[(size_t)row * HW + n] = tot + extra;   // backward tape
         }
       }
     }
     SD_SC_STAMP(5);
-    grid_sync(P.bar, epoch);
-    SD_SC_STAMP(6);
+    SD_SC_STAMP(6);   // (no grid barrier: P4 and the next hidden layer poll the flagged hand-offs of the P3 leaders)
 
     // ================================================================ P4: logits + sample (other CTAs: first half of the next hidden layer)
     if (!do4 && t + 1 < T)
       s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
-                           P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), lok, A_s, W1, G_s, lrow, ls,
+                           nullptr, P.ll_x0 + lrow * HW, tag, lok, A_s, W1, G_s, lrow, ls,
                            (P.step && lok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + g * HW : nullptr,
                            (P.step && lok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + lrow) * (3 * HW) : nullptr);
     if (do4) {
       float4 vv[2];
+      ll_prewait(reinterpret_cast<const unsigned int*>(P.ll_vobs + lrow * HW) + 1, tag, lok && ls == 0);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) vv[i] = lok ? ldcg4(vobs_t + (size_t)lrow * HW + i * 128 + ls * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 2; ++i) vv[i] = lok ? ll_load4(P.ll_vobs + lrow * HW + i * 128 + ls * 4, tag) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float ss = warp_sum(sq4(vv[0]) + sq4(vv[1]));
       const float rs = 1.f / sqrtf(ss / (float)HW + kRmsEps);
       float4 oo[2];
@@ -453,32 +511,64 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
             P.lg[((size_t)t * sstep + row) * SK + n] = lgv;
             if (t + 1 < T) P.zin[((size_t)(t + 1) * sstep + row) * SK + n] = keep_n * oh;
           }
-          if (kcls == 0) P.idx[row * P.S + n / Kc] = best;
+          if (kcls == 0)
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(P.idx + row * P.S + n / Kc), "r"((tag << 8) | (unsigned int)best) : "memory");
         }
       }
+      __syncthreads();   // the reduction buffer of the logit tile aliases A_s, which hid_first_half overwrites next
     }
     SD_SC_STAMP(7);
-    grid_sync(P.bar, epoch);
-    SD_SC_STAMP(8);
+    SD_SC_STAMP(8);   // (no grid barrier: the P5 CTAs poll the tagged indices)
 
     // ================================================================ P5: next step's dyn_in1 (gather-sum of one-hot rows)
     if (do4 && t + 1 < T)
       s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
-                           P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), lok, A_s, W1, G_s, lrow, ls,
+                           nullptr, P.ll_x0 + lrow * HW, tag, lok, A_s, W1, G_s, lrow, ls,
                            (P.step && lok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + g * HW : nullptr,
                            (P.step && lok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + lrow) * (3 * HW) : nullptr);
-    if (do5 && t + 1 < T && rok) {
+    if (do5 && t + 1 < T && et) {   // whole warps (et = tid < 256)
+      {   // pre-wait: one lane per row spins on the row's first index word
+        unsigned int v = 0;
+        if (rok && col == 0) {
+#pragma unroll 1
+          for (unsigned int spin = 0; spin < (1u << 24); ++spin) {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.idx + row * P.S) : "memory");
+            if ((v >> 8) == tag) break;
+          }
+          if ((v >> 8) != tag) __trap();
+        }
+        __syncwarp();
+      }
+     if (rok) {
       float v = 0.f;
       const int Kc = P.K;
-      for (int s = 0; s < P.S; ++s) {
-        const int id = __ldcg(P.idx + row * P.S + s);
-        v += W45[(s * Kc + id) * 16 + col];
+      for (int s0 = 0; s0 < P.S; s0 += 32) {   // all loads of a chunk in flight together; re-poll the chunk until every tag matches
+        unsigned int w[32];
+        bool ok = false;
+#pragma unroll 1
+        for (unsigned int spin = 0; spin < (1u << 22) && !ok; ++spin) {
+          ok = true;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            w[j] = tag << 8;
+            if (s0 + j < P.S) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w[j]) : "l"(P.idx + row * P.S + s0 + j) : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ok = ok && ((w[j] >> 8) == tag);
+        }
+        if (!ok) __trap();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (s0 + j < P.S) v += W45[((s0 + j) * Kc + (int)(w[j] & 0xffu)) * 16 + col];
       }
       const int n = j5 * 16 + col;
-      P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = bias_5 + keep_n * v;
+      const float v1n = bias_5 + keep_n * v;
+      ll_store(P.ll_x1 + row * HW + n, v1n, tag);
+      P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = v1n;   // backward tape
+     }
     }
     SD_SC_STAMP(9);
-    if (t + 1 < T) grid_sync(P.bar, epoch);
+    __syncthreads();   // (no grid barrier: P1 of the next step polls the flagged x1; A_s is free once every thread is past hid_first_half)
     SD_SC_STAMP(10);
   }
 }
