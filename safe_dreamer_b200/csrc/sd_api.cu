@@ -1660,6 +1660,8 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   P.zin = base.zin; P.din = base.din; P.vin = base.vin; P.x = base.x; P.hpre = base.hpre; P.h = base.h; P.q = base.q;
   P.lg = base.lg; P.vobs = base.vobs[0]; P.o = base.o[0];
   P.step = tape ? 1 : 0;
+  static const int scan_ll = env_flag("SD_SCAN_LL", 1);
+  P.ll = scan_ll;
   P.ssq_h = h.ps_ssq; P.idx = h.ps_idx; P.bar = h.ps_bar;
   P.ll_x0 = h.ps_ll; P.ll_vobs = h.ps_ll + 16 * sd::scan::HW; P.ll_x1 = h.ps_ll + 2 * 16 * sd::scan::HW;
   static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)

@@ -63,6 +63,7 @@ struct Params {
   // per-step buffers: step t lives at base + t * step * B * width (step = 0: reused, 1: backward tape)
   float *zin, *din, *vin, *x, *hpre, *h, *q, *lg, *vobs, *o;
   int step;
+  int ll;              // 1: flagged hand-offs instead of the grid barriers after P3 / P4 / P5 (SD_SCAN_LL=0 restores the barriers: A/B knob)
   float* ssq_h;        // [128 tiles][16 rows]
   unsigned int* idx;   // [16][S]: (tag << 8) | class index of the step's sample
   float2 *ll_x0, *ll_vobs, *ll_x1;   // [16][256] {value, tag} pairs: flagged hand-offs P3 -> next hidden layer, P3 -> P4, P5 -> P1
@@ -348,10 +349,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int k = i * 128 + ls * 4;
-        if (t == 0) v1[i] = lok ? ldcg4(vin_t + (size_t)lrow * (3 * HW) + HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t == 0 || !P.ll) v1[i] = lok ? ldcg4(vin_t + (size_t)lrow * (3 * HW) + HW + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         xv2[i] = lok ? __ldg(reinterpret_cast<const float4*>(P.x2 + ((size_t)t * B + lrow) * HW + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (t > 0) {   // produced by P5 of the previous step (tag t)
+      if (t > 0 && P.ll) {   // produced by P5 of the previous step (tag t)
         ll_prewait(reinterpret_cast<const unsigned int*>(P.ll_x1 + lrow * HW) + 1, tag - 1u, lok && ls == 0);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
@@ -466,19 +467,26 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
       }
     }
     SD_SC_STAMP(5);
+    if (!P.ll) grid_sync(P.bar, epoch);
     SD_SC_STAMP(6);   // (no grid barrier: P4 and the next hidden layer poll the flagged hand-offs of the P3 leaders)
 
     // ================================================================ P4: logits + sample (other CTAs: first half of the next hidden layer)
     if (!do4 && t + 1 < T)
       s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
-                           nullptr, P.ll_x0 + lrow * HW, tag, lok, A_s, W1, G_s, lrow, ls,
+                           P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), P.ll ? P.ll_x0 + lrow * HW : nullptr, tag,
+                           lok, A_s, W1, G_s, lrow, ls,
                            (P.step && lok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + g * HW : nullptr,
                            (P.step && lok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + lrow) * (3 * HW) : nullptr);
     if (do4) {
       float4 vv[2];
-      ll_prewait(reinterpret_cast<const unsigned int*>(P.ll_vobs + lrow * HW) + 1, tag, lok && ls == 0);
+      if (P.ll) {
+        ll_prewait(reinterpret_cast<const unsigned int*>(P.ll_vobs + lrow * HW) + 1, tag, lok && ls == 0);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) vv[i] = lok ? ll_load4(P.ll_vobs + lrow * HW + i * 128 + ls * 4, tag) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 2; ++i) vv[i] = lok ? ll_load4(P.ll_vobs + lrow * HW + i * 128 + ls * 4, tag) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) vv[i] = lok ? ldcg4(vobs_t + (size_t)lrow * HW + i * 128 + ls * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       const float ss = warp_sum(sq4(vv[0]) + sq4(vv[1]));
       const float rs = 1.f / sqrtf(ss / (float)HW + kRmsEps);
       float4 oo[2];
@@ -518,18 +526,20 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
       __syncthreads();   // the reduction buffer of the logit tile aliases A_s, which hid_first_half overwrites next
     }
     SD_SC_STAMP(7);
+    if (!P.ll) grid_sync(P.bar, epoch);
     SD_SC_STAMP(8);   // (no grid barrier: the P5 CTAs poll the tagged indices)
 
     // ================================================================ P5: next step's dyn_in1 (gather-sum of one-hot rows)
     if (do4 && t + 1 < T)
       s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
-                           nullptr, P.ll_x0 + lrow * HW, tag, lok, A_s, W1, G_s, lrow, ls,
+                           P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), P.ll ? P.ll_x0 + lrow * HW : nullptr, tag,
+                           lok, A_s, W1, G_s, lrow, ls,
                            (P.step && lok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + g * HW : nullptr,
                            (P.step && lok && cta == 0) ? P.x + ((size_t)(t + 1) * sstep + lrow) * (3 * HW) : nullptr);
     if (do5 && t + 1 < T && et) {   // whole warps (et = tid < 256)
       {   // pre-wait: one lane per row spins on the row's first index word
         unsigned int v = 0;
-        if (rok && col == 0) {
+        if (P.ll && rok && col == 0) {
 #pragma unroll 1
           for (unsigned int spin = 0; spin < (1u << 24); ++spin) {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.idx + row * P.S) : "memory");
@@ -546,7 +556,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
         unsigned int w[32];
         bool ok = false;
 #pragma unroll 1
-        for (unsigned int spin = 0; spin < (1u << 22) && !ok; ++spin) {
+        for (unsigned int spin = 0; spin < (P.ll ? (1u << 22) : 1u) && !ok; ++spin) {
           ok = true;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -556,7 +566,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
 #pragma unroll
           for (int j = 0; j < 32; ++j) ok = ok && ((w[j] >> 8) == tag);
         }
-        if (!ok) __trap();
+        if (!ok && P.ll) __trap();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (s0 + j < P.S) v += W45[((s0 + j) * Kc + (int)(w[j] & 0xffu)) * 16 + col];
@@ -568,6 +578,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
      }
     }
     SD_SC_STAMP(9);
+    if (!P.ll && t + 1 < T) grid_sync(P.bar, epoch);
     __syncthreads();   // (no grid barrier: P1 of the next step polls the flagged x1; A_s is free once every thread is past hid_first_half)
     SD_SC_STAMP(10);
   }
