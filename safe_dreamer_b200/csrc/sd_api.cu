@@ -84,6 +84,9 @@ struct WeightDesc {
   int64_t numel;
 };
 
+// flagged hand-off buffers of the persistent posterior scan: x0 | vobs | x1 ([16][256] each) | first-half tiles of the 32 sampling CTAs ([32][256])
+constexpr size_t kPsLlElems = (size_t)3 * 16 * 256 + (size_t)32 * 256;
+
 struct Arena {
   uint8_t* base = nullptr;
   size_t off = 0, cap = 0;
@@ -1005,7 +1008,7 @@ static void layout(sd_handle& h, Arena& a) {
   h.ps_eproj = a.take<float>((size_t)16 * T * c.U);
   h.ps_ssq = a.take<float>((size_t)sd::scan::NCTA * 16);
   h.ps_idx = a.take<unsigned int>((size_t)16 * c.S);
-  h.ps_ll = a.take<float2>((size_t)3 * 16 * sd::scan::HW);
+  h.ps_ll = a.take<float2>(kPsLlElems);
   h.ps_bar = a.take<unsigned int>(64);
   if (pimg_shape_ok(h)) {
     h.pi_wp7 = a.take<bf16>((size_t)768 * sd::pimg::D);
@@ -1644,7 +1647,7 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   cudaMemsetAsync(h.ps_bar, 0, 64 * sizeof(unsigned int), cx.st);
   // tags of the flagged hand-offs restart at 1 with every launch (also every replay of a captured graph): clear the old ones
   cudaMemsetAsync(h.ps_idx, 0, (size_t)16 * c.S * sizeof(unsigned int), cx.st);
-  cudaMemsetAsync(h.ps_ll, 0, (size_t)3 * 16 * sd::scan::HW * sizeof(float2), cx.st);
+  cudaMemsetAsync(h.ps_ll, 0, kPsLlElems * sizeof(float2), cx.st);
   sd::scan::Params P;
   memset(&P, 0, sizeof(P));
   P.B = B; P.T = T; P.D = D; P.SK = SK; P.S = c.S; P.K = c.K; P.G = c.G; P.E = E; P.A = A; P.unimix = c.unimix;
@@ -1660,10 +1663,11 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   P.zin = base.zin; P.din = base.din; P.vin = base.vin; P.x = base.x; P.hpre = base.hpre; P.h = base.h; P.q = base.q;
   P.lg = base.lg; P.vobs = base.vobs[0]; P.o = base.o[0];
   P.step = tape ? 1 : 0;
-  static const int scan_ll = env_flag("SD_SCAN_LL", 1);
+  static const int scan_ll = env_flag("SD_SCAN_LL", 2);
   P.ll = scan_ll;
   P.ssq_h = h.ps_ssq; P.idx = h.ps_idx; P.bar = h.ps_bar;
   P.ll_x0 = h.ps_ll; P.ll_vobs = h.ps_ll + 16 * sd::scan::HW; P.ll_x1 = h.ps_ll + 2 * 16 * sd::scan::HW;
+  P.ll_sa = h.ps_ll + 3 * 16 * sd::scan::HW;
   static unsigned long long attr_done = 0;   // bit d: attribute set on device d (the attribute is per device)
   if (!dev_done(attr_done)) {
     cudaFuncSetAttribute(sd::scan::observe_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::scan::kSmemBytes);
@@ -1686,6 +1690,8 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
                       "P5=%lld bar=%lld | step=%lld\n", c0 ? 40 : 0, tt[c0 + 1] - tt[c0 + 0], tt[c0 + 2] - tt[c0 + 1], tt[c0 + 3] - tt[c0 + 2],
               tt[c0 + 4] - tt[c0 + 3], tt[c0 + 5] - tt[c0 + 4], tt[c0 + 6] - tt[c0 + 5], tt[c0 + 7] - tt[c0 + 6], tt[c0 + 8] - tt[c0 + 7],
               tt[c0 + 9] - tt[c0 + 8], tt[c0 + 10] - tt[c0 + 9], tt[c0 + 10] - tt[c0 + 0]);
+    fprintf(stderr, "[SD_TRACE_SCAN] cta 40 P5 detail: pre-wait=%lld poll=%lld gather+publish=%lld\n", tt[16 + 14] - tt[16 + 8], tt[16 + 15] - tt[16 + 14],
+            tt[16 + 9] - tt[16 + 15]);
     fprintf(stderr, "[SD_TRACE_SCAN] cta 0 P3 detail: loads+stage=%lld product=%lld dsmem+cluster=%lld tail=%lld\n", tt[11] - tt[4],
             tt[12] - tt[11], tt[13] - tt[12], tt[5] - tt[13]);
   }

@@ -63,9 +63,10 @@ struct Params {
   // per-step buffers: step t lives at base + t * step * B * width (step = 0: reused, 1: backward tape)
   float *zin, *din, *vin, *x, *hpre, *h, *q, *lg, *vobs, *o;
   int step;
-  int ll;              // 1: flagged hand-offs instead of the grid barriers after P3 / P4 / P5 (SD_SCAN_LL=0 restores the barriers: A/B knob)
+  int ll;              // 0: five grid barriers per step; 1: flagged hand-offs instead of the barriers after P3 / P4 / P5; 2: + helper CTAs (SD_SCAN_LL)
   float* ssq_h;        // [128 tiles][16 rows]
   unsigned int* idx;   // [16][S]: (tag << 8) | class index of the step's sample
+  float2* ll_sa;       // [32 sampling CTAs][256]: first-half hidden-layer tiles computed for them by the helper CTAs 48..79
   float2 *ll_x0, *ll_vobs, *ll_x1;   // [16][256] {value, tag} pairs: flagged hand-offs P3 -> next hidden layer, P3 -> P4, P5 -> P1
   unsigned int* bar;   // grid barrier counter, zeroed before the launch
   long long* timing;   // diagnostic (SD_TRACE_SCAN=1): clock64 stamps of CTA 0 / 40 during step 2; null in production
@@ -274,6 +275,53 @@ __device__ __noinline__ float hid_first_half(const float* dsrc, float keep, cons
   return s;
 }
 
+// Helper CTAs (48 .. 48 + SK/16): their own first half, then the first half of sampling CTA `cta - 48` with that CTA's weight
+// slice (kept in the helper's otherwise unused W45 region).  The sampling CTAs run P4 right after P3, so their own
+// hid_first_half would sit on the step's critical path (P3 -> P4 -> hid_first_half -> P1: 16 k cycles, everyone else is
+// done after 12 k); the helpers have that slack.  Same operands, same tile_product: bit-identical to the CTA's own result.
+__device__ __noinline__ float hid_first_half_pair(const float* dsrc, const float* dsrc_p, float keep, const float2* v0ll, unsigned int tag,
+                                                  bool lok, bool rok, float* A_s, const float* W1, const float* Wp, const float* G_s,
+                                                  int lrow, int ls, float* din_t, float* din_p, float* x_p, float2* sa_ll) {
+  float4 dv[2], dp[2], v0[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int k = i * 128 + ls * 4;
+    dv[i] = lok ? ldcg4(dsrc + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dp[i] = lok ? ldcg4(dsrc_p + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  ll_prewait(reinterpret_cast<const unsigned int*>(v0ll) + 1, tag, lok && ls == 0);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) v0[i] = lok ? ll_load4(v0ll + i * 128 + ls * 4, tag) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float ss0 = warp_sum(sq4(v0[0]) + sq4(v0[1]));
+  const float rs0 = 1.f / sqrtf(ss0 / (float)HW + kRmsEps);
+  float4 x0[2];
+  normact8(v0, rs0, G_s, ls, x0);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    dv[i].x *= keep; dv[i].y *= keep; dv[i].z *= keep; dv[i].w *= keep;
+    dp[i].x *= keep; dp[i].y *= keep; dp[i].z *= keep; dp[i].w *= keep;
+    *reinterpret_cast<float4*>(A_s + lrow * ALD + i * 128 + ls * 4) = dv[i];
+    *reinterpret_cast<float4*>(A_s + lrow * ALD + HW + i * 128 + ls * 4) = x0[i];
+    if (din_t) *reinterpret_cast<float4*>(din_t + i * 128 + ls * 4) = dv[i];   // backward tape: masked deter input (own block)
+    if (din_p) *reinterpret_cast<float4*>(din_p + i * 128 + ls * 4) = dp[i];   // ... and the sampling CTA's block
+    if (x_p) *reinterpret_cast<float4*>(x_p + i * 128 + ls * 4) = x0[i];       // backward tape: x0 (written by CTA 0 otherwise)
+  }
+  __syncthreads();
+  float s;
+  tile_product<1>(A_s, W1, 0, KC / 4, &s);
+  __syncthreads();   // the reduction buffer aliases the A tile: restage both halves
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    *reinterpret_cast<float4*>(A_s + lrow * ALD + i * 128 + ls * 4) = dp[i];
+    *reinterpret_cast<float4*>(A_s + lrow * ALD + HW + i * 128 + ls * 4) = x0[i];
+  }
+  __syncthreads();
+  float sp;
+  tile_product<1>(A_s, Wp, 0, KC / 4, &sp);
+  if (rok) ll_store(sa_ll + threadIdx.x, sp, tag);
+  return s;
+}
+
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) observe_scan_kernel(const Params P) {
   extern __shared__ __align__(16) float sm[];
   float* W1 = sm + kW1;
@@ -297,6 +345,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   const int n4tiles = SK / 16;
   const bool do4 = cta < n4tiles, do5 = cta >= 32 && cta < 48;
   const int j5 = cta - 32;
+  // first-half hidden-layer tiles of the sampling CTAs are computed by helper CTAs (flagged hand-off mode only)
+  const bool offload = P.ll >= 2;
+  const bool helper = offload && cta >= 48 && cta - 48 < n4tiles;
+  const int pc = cta - 48, gp = (pc >> 4) & 7, jtp = pc & 15;   // the helper's sampling CTA, its block and column tile
   const size_t sstep = (size_t)P.step * B;   // rows between consecutive steps of the per-step buffers
 
   // ---------------------------------------------------------------- one-time: weights -> shared memory
@@ -306,6 +358,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   stage_w(W3, p3 == 0 ? P.w_in0 : P.w_obs, p3 == 0 ? P.ld_in0 : P.ld_obs, r3 * KC, KC, j3 * 16, false);
   if (do4) stage_w(W45, P.w_lg, P.ld_lg, 0, HW, cta * 16, false);
   if (do5) stage_w(W45, P.w_in1, P.ld_in1, 0, SK, j5 * 16, false);
+  if (helper) stage_w(W45, P.w_hid + (size_t)gp * (4 * HW) * P.ld_hid, P.ld_hid, 0, 2 * HW, jtp * 16, false);
   // RMS scales -> shared memory, per-thread biases -> registers (the acquire of every grid barrier invalidates L1, so
   // anything re-read from global each phase would pay an L2 round trip on the critical path)
   if (et) {
@@ -375,6 +428,20 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
       __syncthreads();
       float s2;
       tile_product<1>(A_s, W1 + (KC / 4) * 64, 0, KC / 4, &s2);
+      if (do4 && offload && t > 0 && et) {   // this CTA's first half was computed by helper CTA 48 + cta during the previous step
+        uint32_t v0 = 0, v1 = 0;
+        ll_prewait(reinterpret_cast<const unsigned int*>(P.ll_sa + cta * 256 + tid) + 1, tag - 1u, rok && (tid & 31) == 0);
+        if (rok) {
+          const float2* src = P.ll_sa + cta * 256 + tid;
+#pragma unroll 1
+          for (unsigned int spin = 0; spin < (1u << 24); ++spin) {
+            asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "l"(src) : "memory");
+            if (v1 == tag - 1u) break;
+          }
+          if (v1 != tag - 1u) __trap();
+        }
+        s_a = __uint_as_float(v0);
+      }
       if (et) {
         const int n = g * HW + jt * 16 + col;
         const float hp = (s_a + s2) + bias_h;
@@ -471,7 +538,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     SD_SC_STAMP(6);   // (no grid barrier: P4 and the next hidden layer poll the flagged hand-offs of the P3 leaders)
 
     // ================================================================ P4: logits + sample (other CTAs: first half of the next hidden layer)
-    if (!do4 && t + 1 < T)
+    if (helper && t + 1 < T)
+      s_a = hid_first_half_pair(P.deters + ((size_t)lrow * T + t) * D + g * HW, P.deters + ((size_t)lrow * T + t) * D + gp * HW, lkeep_n,
+                                P.ll_x0 + lrow * HW, tag, lok, rok, A_s, W1, W45, G_s, lrow, ls,
+                                (P.step && lok && jt == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + g * HW : nullptr,
+                                (P.step && lok && jtp == 0) ? P.din + ((size_t)(t + 1) * sstep + lrow) * D + gp * HW : nullptr,
+                                (P.step && lok && pc == 0) ? P.x + ((size_t)(t + 1) * sstep + lrow) * (3 * HW) : nullptr,
+                                P.ll_sa + pc * 256);
+    else if (!do4 && t + 1 < T)
       s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
                            P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), P.ll ? P.ll_x0 + lrow * HW : nullptr, tag,
                            lok, A_s, W1, G_s, lrow, ls,
@@ -530,7 +604,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     SD_SC_STAMP(8);   // (no grid barrier: the P5 CTAs poll the tagged indices)
 
     // ================================================================ P5: next step's dyn_in1 (gather-sum of one-hot rows)
-    if (do4 && t + 1 < T)
+    if (do4 && !offload && t + 1 < T)
       s_a = hid_first_half(P.deters + ((size_t)lrow * T + t) * D + g * HW, lkeep_n,
                            P.vin + (size_t)(t + 1) * sstep * (3 * HW) + (size_t)lrow * (3 * HW), P.ll ? P.ll_x0 + lrow * HW : nullptr, tag,
                            lok, A_s, W1, G_s, lrow, ls,
@@ -539,7 +613,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     if (do5 && t + 1 < T && et) {   // whole warps (et = tid < 256)
       {   // pre-wait: one lane per row spins on the row's first index word
         unsigned int v = 0;
-        if (P.ll && rok && col == 0) {
+        if (P.ll && P.S != 32 && rok && col == 0) {
 #pragma unroll 1
           for (unsigned int spin = 0; spin < (1u << 24); ++spin) {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.idx + row * P.S) : "memory");
@@ -549,7 +623,37 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
         }
         __syncwarp();
       }
-     if (rok) {
+      SD_SC_STAMP(14);
+     if (P.S == 32 && P.ll) {
+      // every thread polls TWO of its row's 32 index words (one L2 round trip), the 16 lanes of the row exchange them by shuffle
+      const int lane = tid & 31;
+      unsigned int w0 = tag << 8, w1 = tag << 8;
+      if (rok) {
+        const unsigned int* src = P.idx + row * 32 + col * 2;
+        bool ok = false;
+#pragma unroll 1
+        for (unsigned int spin = 0; spin < (1u << 22) && !ok; ++spin) {
+          asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "l"(src) : "memory");
+          ok = ((w0 >> 8) == tag) && ((w1 >> 8) == tag);
+        }
+        if (!ok) __trap();
+      }
+      __syncwarp();
+      SD_SC_STAMP(15);
+      float v = 0.f;
+      const int Kc = P.K;
+#pragma unroll
+      for (int sI = 0; sI < 32; ++sI) {   // ascending s: same summation order as the general path
+        const unsigned int wsel = __shfl_sync(0xffffffffu, (sI & 1) ? w1 : w0, (lane & 16) | (sI >> 1));
+        v += W45[(sI * Kc + (int)(wsel & 0xffu)) * 16 + col];
+      }
+      if (rok) {
+        const int n = j5 * 16 + col;
+        const float v1n = bias_5 + keep_n * v;
+        ll_store(P.ll_x1 + row * HW + n, v1n, tag);
+        P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = v1n;   // backward tape
+      }
+     } else if (rok) {
       float v = 0.f;
       const int Kc = P.K;
       for (int s0 = 0; s0 < P.S; s0 += 32) {   // all loads of a chunk in flight together; re-poll the chunk until every tag matches
@@ -567,6 +671,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
           for (int j = 0; j < 32; ++j) ok = ok && ((w[j] >> 8) == tag);
         }
         if (!ok && P.ll) __trap();
+        SD_SC_STAMP(15);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (s0 + j < P.S) v += W45[((s0 + j) * Kc + (int)(w[j] & 0xffu)) * 16 + col];
