@@ -1675,16 +1675,18 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   // no PDL attribute: all 128 CTAs must become resident together (they spin on a grid barrier)
   static long long* timing_dev = nullptr;
   if (cx.trace && getenv("SD_TRACE_SCAN")) {
-    if (!timing_dev) cudaMalloc(&timing_dev, 32 * sizeof(long long));
-    cudaMemsetAsync(timing_dev, 0, 32 * sizeof(long long), cx.st);
+    if (!timing_dev) cudaMalloc(&timing_dev, 48 * sizeof(long long));
+    cudaMemsetAsync(timing_dev, 0, 48 * sizeof(long long), cx.st);
     P.timing = timing_dev;
   }
   sd::scan::observe_scan_kernel<<<sd::scan::NCTA, sd::scan::THREADS, sd::scan::kSmemBytes, cx.st>>>(P);
   cx.check("observe_scan_kernel");
   if (P.timing) {
     cudaStreamSynchronize(cx.st);
-    long long tt[32];
+    long long tt[48];
     cudaMemcpy(tt, timing_dev, sizeof(tt), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[SD_TRACE_SCAN] cta 0 kernel: weight staging=%lld first half of step 0=%lld step 0=%lld steps 1..T/2-1=%lld (%lld per step) steps T/2..T-1=%lld\n",
+            tt[33] - tt[32], tt[34] - tt[33], tt[35] - tt[34], tt[36] - tt[35], (tt[36] - tt[35]) / (T / 2 > 1 ? T / 2 - 1 : 1), tt[37] - tt[36]);
     for (int c0 = 0; c0 < 32; c0 += 16)
       fprintf(stderr, "[SD_TRACE_SCAN] cta %d step 2 cycles: P1=%lld bar=%lld | P2=%lld bar=%lld | P3=%lld bar=%lld | P4=%lld bar=%lld | "
                       "P5=%lld bar=%lld | step=%lld\n", c0 ? 40 : 0, tt[c0 + 1] - tt[c0 + 0], tt[c0 + 2] - tt[c0 + 1], tt[c0 + 3] - tt[c0 + 2],

@@ -71,6 +71,7 @@ struct Params {
   unsigned int* bar;   // grid barrier counter, zeroed before the launch
   long long* timing;   // diagnostic (SD_TRACE_SCAN=1): clock64 stamps of CTA 0 / 40 during step 2; null in production
 };
+#define SD_SC_KSTAMP(i) do { if (P.timing && threadIdx.x == 0 && blockIdx.x == 0) P.timing[32 + (i)] = clock64(); } while (0)
 #define SD_SC_STAMP(i) do { if (P.timing && t == 2 && tid == 0 && (cta == 0 || cta == 40)) P.timing[(cta ? 16 : 0) + (i)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
@@ -351,6 +352,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   const int pc = cta - 48, gp = (pc >> 4) & 7, jtp = pc & 15;   // the helper's sampling CTA, its block and column tile
   const size_t sstep = (size_t)P.step * B;   // rows between consecutive steps of the per-step buffers
 
+  SD_SC_KSTAMP(0);
   // ---------------------------------------------------------------- one-time: weights -> shared memory
   stage_w(W1, P.w_hid + (size_t)g * (4 * HW) * P.ld_hid, P.ld_hid, 0, 4 * HW, jt * 16, false);
   for (int gate = 0; gate < 3; ++gate)
@@ -376,13 +378,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
   const float bias_5 = do5 ? __ldg(P.b_in1 + j5 * 16 + col) : 0.f;
   unsigned int epoch = 0;
   __syncthreads();
+  SD_SC_KSTAMP(1);
   // first half of step 0's hidden layer (v_in0 of step 0 comes from the host-side launches)
   float s_a = hid_first_half(P.init_deter + (size_t)lrow * D + g * HW, (lok && P.is_first[(size_t)lrow * T]) ? 0.f : 1.f,
                              P.vin + (size_t)lrow * (3 * HW), nullptr, 0u, lok, A_s, W1, G_s, lrow, ls,
                              (P.step && lok && jt == 0) ? P.din + (size_t)lrow * D + g * HW : nullptr,
                              (P.step && lok && cta == 0) ? P.x + (size_t)lrow * (3 * HW) : nullptr);
 
+  SD_SC_KSTAMP(2);
   for (int t = 0; t < T; ++t) {
+    if (t == 1) SD_SC_KSTAMP(3);
+    if (t == T / 2) SD_SC_KSTAMP(4);
     // reset masks (rssm.py:161-165) in both mappings
     const float keep_t = (rok && P.is_first[(size_t)row * T + t]) ? 0.f : 1.f;
     const float keep_n = (t + 1 < T && rok && P.is_first[(size_t)row * T + t + 1]) ? 0.f : 1.f;
@@ -585,6 +591,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
         else if (Kc == 4) best = sample_group<4>(lgv, uu_t, true, kcls, Kc, P.unimix, nullptr);
         else best = sample_group<2>(lgv, uu_t, true, kcls, Kc, P.unimix, nullptr);
         if (rok) {
+          if (kcls == 0)   // the hand-off to P5 first: the output / tape stores below are off the critical path
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(P.idx + row * P.S + n / Kc), "r"((tag << 8) | (unsigned int)best) : "memory");
           const float oh = (kcls == best) ? 1.f : 0.f;
           const size_t off = ((size_t)row * T + t) * SK + n;
           P.stochs[off] = oh;
@@ -593,8 +601,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
             P.lg[((size_t)t * sstep + row) * SK + n] = lgv;
             if (t + 1 < T) P.zin[((size_t)(t + 1) * sstep + row) * SK + n] = keep_n * oh;
           }
-          if (kcls == 0)
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(P.idx + row * P.S + n / Kc), "r"((tag << 8) | (unsigned int)best) : "memory");
         }
       }
       __syncthreads();   // the reduction buffer of the logit tile aliases A_s, which hid_first_half overwrites next
@@ -687,6 +693,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
     __syncthreads();   // (no grid barrier: P1 of the next step polls the flagged x1; A_s is free once every thread is past hid_first_half)
     SD_SC_STAMP(10);
   }
+  SD_SC_KSTAMP(5);
 }
 
 // Everything of the posterior scan that only depends on the inputs (rssm.py:44,48,161-165): per (t, b)
