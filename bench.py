@@ -632,10 +632,11 @@ def run_gpu(args):
                          "flop_per_unit": flop_row / H, "units_per_launch": N * H,
                          "note": "flop_per_unit = executed FLOP per imagined row-step: H actor + (H-1) Deter/prior evaluations per row"},
             "roofline_posterior": {"bound": "latency", "kernel": "observe_scan_kernel (persistent weight-stationary posterior scan, fp32 3xTF32 mma.sync)",
-                                   "us_per_step": 1e3 * ms_obs / args.steps / T, "grid_barriers_per_step": 5,
+                                   "us_per_step": 1e3 * ms_obs / args.steps / T, "grid_barriers_per_step": 2, "flagged_handoffs_per_step": 4,
                                    "achieved_tflops": B * T * FLOP_POST_STEP / (ms_obs / args.steps * 1e-3) / 1e12,
-                                   "note": "M = 16 rows per step: 168 MFLOP per step against 10.5 MB of resident weights; bounded by the 5 grid "
-                                           "barriers + dependent phases of a step, not by the tensor or HBM roofline"},
+                                   "note": "M = 16 rows per step: 168 MFLOP per step against 10.5 MB of resident weights; bounded by the five dependent phases "
+                                           "of a step and their hand-offs (2 grid barriers where every CTA consumes every CTA's output, flagged "
+                                           "value+tag stores polled by the consumer elsewhere), not by the tensor or HBM roofline"},
             "cpu_baseline": cpu,
             "gpu_reference": gpu_ref,
             "cnn_encoder": cnn,
