@@ -6,14 +6,19 @@
 //
 //   * every CTA copies its slices of the fp32 weights into shared memory ONCE (~144-176 KB per CTA, 21 MB in
 //     total across the grid) and keeps them there for the whole scan;
-//   * a step is five phases separated by grid barriers (one L2 atomic + acquire spin each); activations (16 rows)
-//     travel between CTAs through L2 (ld.global.cg), never through HBM:
+//   * a step is five phases; activations (16 rows) travel between CTAs through L2, never through HBM.  Where every CTA
+//     consumes every CTA's output (after P1 and P2) the phases are separated by a grid barrier (one L2 atomic + acquire
+//     spin); the three boundaries with few producers (P3 -> P4 / next hidden layer, P4 -> P5, P5 -> P1) are flagged
+//     hand-offs: value + tag in ONE 8-byte store, polled by the consumer (see ll_store / ll_load4 / ll_prewait):
 //       P1  block-GRU hidden layer   h_pre[g] = W_hid[g] [d_g | x0 | x1 | x2]         (rssm.py:52-61)   128 tiles of 16 columns
 //       P2  gate projection + gates  d' = GRU(W_gru[g] SiLU(RMSNorm_2048(h_pre)))     (rssm.py:63-75)   128 tiles of 16 units
 //       P3  the two K = 2048 layers that read d':  obs_net_0 (deter part, + the precomputed embed part) and dyn_in0
 //           of the NEXT step; K split over the 4 CTAs of a cluster, partial tiles reduced through DSMEM in rank order
 //       P4  logits = W_logit SiLU(RMSNorm(v_obs)) + unimix Gumbel sample                (rssm.py:171-177) one tile per 16 classes
 //       P5  dyn_in1 of the next step as a gather-sum of the sampled one-hot rows       (rssm.py:47)      16 tiles
+//     The first half of the NEXT step's hidden layer (deter + x0 columns) runs in the P4 / P5 slot of the CTAs that do not
+//     sample; for the 32 sampling CTAs it is computed by helper CTAs 48..79 (hid_first_half_pair), so that the step's
+//     critical path is P3 -> P4 -> P5 -> P1 only.
 //   * everything that does not depend on the recurrence is computed before the scan: the embed part of obs_net_0 for
 //     all (b, t) (one batched GEMM) and x2 = SiLU(RMSNorm(dyn_in2(action_t))) (obs_prep_kernel).
 // All arithmetic is fp32 FMA with fixed reduction orders (k-group tree inside a warp, warps in order, cluster ranks
