@@ -291,6 +291,15 @@ int sd_cnn_backward(sd_cnn* h, int frames, const float* d_embed, const float* ob
 /* Kernels launched by this library since process start (all handles): bench.py's gpu_launches. */
 uint64_t sd_launch_count(void);
 
+/* Hand-off mode of the persistent posterior scan (sd_observe_fwd at B <= 16; csrc/sd_scan.cuh) on the CURRENT device:
+ *   0 = five grid barriers per step, 1 = two grid barriers + flagged (value + tag) hand-offs, 2 = 1 + helper CTAs.
+ * All modes compute bit-identical results.  By default the first full-length (T >= 16) direct call on a device times the
+ * three modes once on its own inputs (about 10 ms, one stream synchronisation, never inside a stream capture) and keeps the
+ * fastest; the environment variable SD_SCAN_LL pins the mode for the process.
+ *   set = -1: query only; set = 0 | 1 | 2: pin the mode for this device; set = -2: forget it (the next call tunes again).
+ * Returns the mode in force BEFORE the call (-1 = not tuned yet).  No reference counterpart (the reference has no such kernel). */
+int sd_scan_mode(int set);
+
 #ifdef __cplusplus
 }
 #endif

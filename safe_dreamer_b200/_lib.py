@@ -145,6 +145,7 @@ _SIGS = {
     "sd_latent_writeback": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [_P] * 5),
     "sd_latent_gather": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [_P] * 6),
     "sd_launch_count": (C.c_uint64, []),
+    "sd_scan_mode": (C.c_int, [C.c_int]),
     "sd_cnn_create": (C.c_int, [C.POINTER(sd_cnn_config), C.POINTER(_P)]),
     "sd_cnn_destroy": (C.c_int, [_P]),
     "sd_cnn_embed_size": (C.c_int64, [_P]),
@@ -187,3 +188,8 @@ def check(rc, what):
 
 def launch_count():
     return int(load().sd_launch_count())
+
+
+def scan_mode(set=-1):
+    """include/safedreamer.h: sd_scan_mode (hand-off mode of the persistent posterior scan on the current device)."""
+    return int(load().sd_scan_mode(int(set)))

@@ -1604,6 +1604,16 @@ static bool pscan_coresident() {
   }
   return st > 0;
 }
+static int g_scan_mode[64];   // per device ordinal: 0 = not tuned yet, else hand-off mode + 1 (see observe_persistent)
+extern "C" int sd_scan_mode(int set) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& slot = g_scan_mode[dev & 63];
+  const int before = slot - 1;
+  if (set >= 0 && set <= 2) slot = set + 1;
+  else if (set == -2) slot = 0;
+  return before;
+}
 static bool pscan_ok(const sd_handle& h, int B, int T) {
   const sd_config& c = h.c;
   return pscan_enabled() && pscan_coresident() && B >= 1 && B <= 16 && T >= 1 && c.U == sd::scan::HW && h.Dg == sd::scan::HW && c.G == 8 &&
@@ -1663,8 +1673,7 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
   P.zin = base.zin; P.din = base.din; P.vin = base.vin; P.x = base.x; P.hpre = base.hpre; P.h = base.h; P.q = base.q;
   P.lg = base.lg; P.vobs = base.vobs[0]; P.o = base.o[0];
   P.step = tape ? 1 : 0;
-  static const int scan_ll = env_flag("SD_SCAN_LL", 2);
-  P.ll = scan_ll;
+  P.ll = 2;
   P.ssq_h = h.ps_ssq; P.idx = h.ps_idx; P.bar = h.ps_bar;
   P.ll_x0 = h.ps_ll; P.ll_vobs = h.ps_ll + 16 * sd::scan::HW; P.ll_x1 = h.ps_ll + 2 * 16 * sd::scan::HW;
   P.ll_sa = h.ps_ll + 3 * 16 * sd::scan::HW;
@@ -1678,6 +1687,56 @@ static void observe_persistent(Ctx& cx, int B, int T, const float* embed, const 
     if (!timing_dev) cudaMalloc(&timing_dev, 48 * sizeof(long long));
     cudaMemsetAsync(timing_dev, 0, 48 * sizeof(long long), cx.st);
     P.timing = timing_dev;
+  }
+  // Hand-off mode (sd_scan.cuh, Params::ll).  All three modes compute bit-identical results; which one is fastest depends on
+  // how the device's L2 answers many polling CTAs (2 won by 18 % on the single- and 2-GPU boxes, and lost to itself by 0.5 ms
+  // on one 8-GPU box), so the first full-length direct call on a device times each mode once on the real inputs and keeps the
+  // fastest (one-off: ~10 ms and one stream synchronisation; never inside a stream capture).  SD_SCAN_LL=0|1|2 pins the mode.
+  {
+    static const char* env = getenv("SD_SCAN_LL");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& slot = g_scan_mode[dev & 63];
+    if (env) {
+      P.ll = atoi(env) < 0 ? 0 : (atoi(env) > 2 ? 2 : atoi(env));
+    } else if (slot) {
+      P.ll = slot - 1;
+    } else {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      const bool capturing = cudaStreamIsCapturing(cx.st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+      if (capturing) (void)cudaGetLastError();
+      if (!capturing && !cx.trace && T >= 16) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float best_ms = 0.f;
+        int best = 2;
+        for (int mode = 2; mode >= 0; --mode) {
+          P.ll = mode;
+          float ms = 0.f;
+          for (int rep = 0; rep < 2; ++rep) {   // the second run is timed
+            linear_multi(cx, B, in, 2);           // without a tape the scan re-uses (overwrites) step 0's v_in slot: restore it
+            cudaMemsetAsync(h.ps_bar, 0, 64 * sizeof(unsigned int), cx.st);
+            cudaMemsetAsync(h.ps_idx, 0, (size_t)16 * c.S * sizeof(unsigned int), cx.st);
+            cudaMemsetAsync(h.ps_ll, 0, kPsLlElems * sizeof(float2), cx.st);
+            cudaEventRecord(e0, cx.st);
+            sd::scan::observe_scan_kernel<<<sd::scan::NCTA, sd::scan::THREADS, sd::scan::kSmemBytes, cx.st>>>(P);
+            cudaEventRecord(e1, cx.st);
+          }
+          if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) { ms = 0.f; (void)cudaGetLastError(); }
+          g_launches += 2;
+          if (ms > 0.f && (best_ms == 0.f || ms < best_ms)) { best_ms = ms; best = mode; }
+          if (getenv("SD_TRACE_SCAN_TUNE")) fprintf(stderr, "[safedreamer] device %d posterior scan hand-off mode %d: %.3f ms\n", dev, mode, ms);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        slot = best + 1;
+        P.ll = best;
+        // the timed runs left the barrier counter, the tags and (without a tape) the v_in slot of a finished scan behind
+        linear_multi(cx, B, in, 2);
+        cudaMemsetAsync(h.ps_bar, 0, 64 * sizeof(unsigned int), cx.st);
+        cudaMemsetAsync(h.ps_idx, 0, (size_t)16 * c.S * sizeof(unsigned int), cx.st);
+        cudaMemsetAsync(h.ps_ll, 0, kPsLlElems * sizeof(float2), cx.st);
+      }
+    }
   }
   sd::scan::observe_scan_kernel<<<sd::scan::NCTA, sd::scan::THREADS, sd::scan::kSmemBytes, cx.st>>>(P);
   cx.check("observe_scan_kernel");

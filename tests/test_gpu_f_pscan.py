@@ -142,3 +142,36 @@ def test_act_step_matches_oracle():
                 gap = np.sort(out_o, -1)
                 sure = (gap[:, -1] - gap[:, -2]) > 1e-3
                 assert (_np(mode).argmax(-1)[sure] == out_o.argmax(-1)[sure]).all()
+
+
+def test_pscan_handoff_modes_are_bit_identical():
+    """sd_scan_mode (include/safedreamer.h): five grid barriers per step, flagged hand-offs, flagged hand-offs + helper CTAs
+    and the self-tuning first call all give the same bits, without and with a backward tape, for a ragged batch."""
+    c = O.Cfg()
+    P = O.init_params(c, seed=0)
+    B, T = 5, 24
+    eng = make_engine(c, P, max_rows=16, max_steps=T, max_tape_rows=16)
+    embed, action, reset, u = O.synth_observe_inputs(c, B, T, seed=77, p_reset=0.2)
+    s0 = np.zeros((B, c.S, c.K), np.float32); d0 = np.zeros((B, c.D), np.float32)
+    st_o, dt_o, lg_o, idx_o = O.observe(c, P["rssm"], embed, action, (s0, d0), reset, u)
+    args = [cu(x) for x in (embed, action, s0, d0, reset, u)]
+    before = _lib.scan_mode(-1)
+    try:
+        outs = {}
+        for mode in (0, 1, 2):
+            _lib.scan_mode(mode)
+            for flags in (0, 2):   # 2 = SD_FLAG_SAVE_TAPE
+                outs[(mode, flags)] = [x.clone() for x in eng.observe(*args, flags=flags)]
+        _lib.scan_mode(-2)          # forget: the next full-length direct call times the three modes on these inputs
+        outs[("tuned", 0)] = [x.clone() for x in eng.observe(*args, flags=0)]
+        assert _lib.scan_mode(-1) in (0, 1, 2)
+        outs[("after", 0)] = [x.clone() for x in eng.observe(*args, flags=0)]
+        torch.cuda.synchronize()
+    finally:
+        _lib.scan_mode(before if before >= 0 else -2)
+    ref = outs[(0, 0)]
+    for key, val in outs.items():
+        for a, b in zip(ref, val):
+            assert torch.equal(a, b), f"posterior scan hand-off mode {key} differs from the grid-barrier mode"
+    assert_indices(_np(ref[0]).argmax(-1), idx_o, perturbed_scores(lg_o, u, c.unimix), 1e-4, 5e-3, "pscan modes")
+    np.testing.assert_allclose(_np(ref[1]), dt_o, atol=5e-5, rtol=0)
