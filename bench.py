@@ -311,6 +311,8 @@ def run_gpu(args):
     ms_imag = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | PERSIST, out=(feats, actions)), args.steps, warm=2)
     ms_imag_lw = timed(lambda: eng.imagine(st, dt, ui, noise, H, flags=BF16 | GRAPH | LAYERWISE, out=(feats, actions)), args.steps, warm=2)
     ms_obs = timed(lambda: eng.observe(embed, action, s0, d0, reset, u, flags=GRAPH, out=obs_out), args.steps, warm=2)
+    scan_mode = _lib.scan_mode(-1) if os.environ.get("SD_SCAN_LL") is None else int(os.environ["SD_SCAN_LL"])   # self-tuned per device (include/safedreamer.h)
+    scan_mode = 2 if scan_mode < 0 else scan_mode
     ms_heads = timed(lambda: eng.heads_lambda(feats, disc, c.lamb, flags=BF16 | GRAPH, out=outs), args.steps, warm=2)
     ms_obs_fb = ms_wm = None
     if have_bwd:
@@ -632,11 +634,13 @@ def run_gpu(args):
                          "flop_per_unit": flop_row / H, "units_per_launch": N * H,
                          "note": "flop_per_unit = executed FLOP per imagined row-step: H actor + (H-1) Deter/prior evaluations per row"},
             "roofline_posterior": {"bound": "latency", "kernel": "observe_scan_kernel (persistent weight-stationary posterior scan, fp32 3xTF32 mma.sync)",
-                                   "us_per_step": 1e3 * ms_obs / args.steps / T, "grid_barriers_per_step": 2, "flagged_handoffs_per_step": 4,
+                                   "us_per_step": 1e3 * ms_obs / args.steps / T, "handoff_mode": scan_mode,
+                                   "grid_barriers_per_step": 5 if scan_mode == 0 else 2, "flagged_handoffs_per_step": (0, 3, 4)[max(scan_mode, 0)],
                                    "achieved_tflops": B * T * FLOP_POST_STEP / (ms_obs / args.steps * 1e-3) / 1e12,
                                    "note": "M = 16 rows per step: 168 MFLOP per step against 10.5 MB of resident weights; bounded by the five dependent phases "
-                                           "of a step and their hand-offs (2 grid barriers where every CTA consumes every CTA's output, flagged "
-                                           "value+tag stores polled by the consumer elsewhere), not by the tensor or HBM roofline"},
+                                           "of a step and their hand-offs (mode 1 / 2: grid barriers only where every CTA consumes every CTA's output, "
+                                           "flagged value+tag stores polled by the consumer elsewhere; the mode is timed once per device and the "
+                                           "fastest kept), not by the tensor or HBM roofline"},
             "cpu_baseline": cpu,
             "gpu_reference": gpu_ref,
             "cnn_encoder": cnn,
