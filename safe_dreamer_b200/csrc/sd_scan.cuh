@@ -635,63 +635,63 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) ob
         __syncwarp();
       }
       SD_SC_STAMP(14);
-     if (P.S == 32 && P.ll) {
-      // every thread polls TWO of its row's 32 index words (one L2 round trip), the 16 lanes of the row exchange them by shuffle
-      const int lane = tid & 31;
-      unsigned int w0 = tag << 8, w1 = tag << 8;
-      if (rok) {
-        const unsigned int* src = P.idx + row * 32 + col * 2;
-        bool ok = false;
+      if (P.S == 32 && P.ll) {
+        // every thread polls TWO of its row's 32 index words (one L2 round trip), the 16 lanes of the row exchange them by shuffle
+        const int lane = tid & 31;
+        unsigned int w0 = tag << 8, w1 = tag << 8;
+        if (rok) {
+          const unsigned int* src = P.idx + row * 32 + col * 2;
+          bool ok = false;
 #pragma unroll 1
-        for (unsigned int spin = 0; spin < (1u << 22) && !ok; ++spin) {
-          asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "l"(src) : "memory");
-          ok = ((w0 >> 8) == tag) && ((w1 >> 8) == tag);
+          for (unsigned int spin = 0; spin < (1u << 22) && !ok; ++spin) {
+            asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(w1) : "l"(src) : "memory");
+            ok = ((w0 >> 8) == tag) && ((w1 >> 8) == tag);
+          }
+          if (!ok) __trap();
         }
-        if (!ok) __trap();
-      }
-      __syncwarp();
-      SD_SC_STAMP(15);
-      float v = 0.f;
-      const int Kc = P.K;
+        __syncwarp();
+        SD_SC_STAMP(15);
+        float v = 0.f;
+        const int Kc = P.K;
 #pragma unroll
-      for (int sI = 0; sI < 32; ++sI) {   // ascending s: same summation order as the general path
-        const unsigned int wsel = __shfl_sync(0xffffffffu, (sI & 1) ? w1 : w0, (lane & 16) | (sI >> 1));
-        v += W45[(sI * Kc + (int)(wsel & 0xffu)) * 16 + col];
-      }
-      if (rok) {
+        for (int sI = 0; sI < 32; ++sI) {   // ascending s: same summation order as the general path
+          const unsigned int wsel = __shfl_sync(0xffffffffu, (sI & 1) ? w1 : w0, (lane & 16) | (sI >> 1));
+          v += W45[(sI * Kc + (int)(wsel & 0xffu)) * 16 + col];
+        }
+        if (rok) {
+          const int n = j5 * 16 + col;
+          const float v1n = bias_5 + keep_n * v;
+          ll_store(P.ll_x1 + row * HW + n, v1n, tag);
+          P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = v1n;   // backward tape
+        }
+      } else if (rok) {
+        float v = 0.f;
+        const int Kc = P.K;
+        for (int s0 = 0; s0 < P.S; s0 += 32) {   // all loads of a chunk in flight together; re-poll the chunk until every tag matches
+          unsigned int w[32];
+          bool ok = false;
+#pragma unroll 1
+          for (unsigned int spin = 0; spin < (P.ll ? (1u << 22) : 1u) && !ok; ++spin) {
+            ok = true;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              w[j] = tag << 8;
+              if (s0 + j < P.S) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w[j]) : "l"(P.idx + row * P.S + s0 + j) : "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ok = ok && ((w[j] >> 8) == tag);
+          }
+          if (!ok && P.ll) __trap();
+          SD_SC_STAMP(15);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (s0 + j < P.S) v += W45[((s0 + j) * Kc + (int)(w[j] & 0xffu)) * 16 + col];
+        }
         const int n = j5 * 16 + col;
         const float v1n = bias_5 + keep_n * v;
         ll_store(P.ll_x1 + row * HW + n, v1n, tag);
         P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = v1n;   // backward tape
       }
-     } else if (rok) {
-      float v = 0.f;
-      const int Kc = P.K;
-      for (int s0 = 0; s0 < P.S; s0 += 32) {   // all loads of a chunk in flight together; re-poll the chunk until every tag matches
-        unsigned int w[32];
-        bool ok = false;
-#pragma unroll 1
-        for (unsigned int spin = 0; spin < (P.ll ? (1u << 22) : 1u) && !ok; ++spin) {
-          ok = true;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            w[j] = tag << 8;
-            if (s0 + j < P.S) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w[j]) : "l"(P.idx + row * P.S + s0 + j) : "memory");
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) ok = ok && ((w[j] >> 8) == tag);
-        }
-        if (!ok && P.ll) __trap();
-        SD_SC_STAMP(15);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (s0 + j < P.S) v += W45[((s0 + j) * Kc + (int)(w[j] & 0xffu)) * 16 + col];
-      }
-      const int n = j5 * 16 + col;
-      const float v1n = bias_5 + keep_n * v;
-      ll_store(P.ll_x1 + row * HW + n, v1n, tag);
-      P.vin[(size_t)(t + 1) * sstep * (3 * HW) + (size_t)row * (3 * HW) + HW + n] = v1n;   // backward tape
-     }
     }
     SD_SC_STAMP(9);
     if (!P.ll && t + 1 < T) grid_sync(P.bar, epoch);
